@@ -1,0 +1,196 @@
+"""Oracle (CPU, numpy) restatement of the multi-crop augmentation arithmetic.  TEST INFRASTRUCTURE ONLY.
+
+Follows the reference call sites utils/get_data.py:21-27 (GaussianNoise), :29-58 (TimeWarpWithStretch),
+:60-108 (GroupedMasking), :121-231 (chains), :233-257 (view loop) and the third-party transforms those call
+(torchvision RandomResizedCrop / RandomRotation / RandomAffine / RandomErasing, torchaudio
+FrequencyMasking / TimeMasking / TimeStretch — un-vendored; algorithms restated from SURVEY.md Appendix A1-A5).
+
+Every op takes an already *sampled* parameter record (see `OP_*`), so the functions are deterministic; the
+record layout is the same one the CUDA kernels consume (include/avmnist_b200.h `b200_aug_op`).
+"""
+import math
+
+import numpy as np
+
+f32 = np.float32
+
+# op kinds -- must match include/avmnist_b200.h
+OP_NOP = 0
+OP_CROP_RESIZE = 1    # ints  i, j, h, w
+OP_AFFINE = 2         # f32   m0..m5 (inverse affine matrix, torchvision convention)
+OP_ERASE = 3          # ints  i, j, h, w
+OP_FREQ_MASK = 4      # ints  start, end   (rows)
+OP_TIME_MASK = 5      # ints  start, end   (columns)
+OP_NOISE = 6          # f32   std
+OP_GROUP_MASK = 7     # bits live in a side array (one bit per 4x4 group, row-major 28x28)
+OP_TIME_WARP = 8      # f32   rate
+
+
+def inverse_affine_matrix(angle, tx, ty, scale):
+    """torchvision.transforms.functional._get_inverse_affine_matrix with center=[0,0], shear=[0,0]
+    (the only form reached from get_data.py:124-125,129-130,151-155,184-187); Python doubles."""
+    rot = math.radians(angle)
+    a = math.cos(rot)
+    b = -math.sin(rot)
+    c = math.sin(rot)
+    d = math.cos(rot)
+    m = [d, -b, 0.0, -c, a, 0.0]
+    m = [x / scale for x in m]
+    m[2] += m[0] * (-tx) + m[1] * (-ty)
+    m[5] += m[3] * (-tx) + m[4] * (-ty)
+    return m
+
+
+def affine_index_map(m, H, W):
+    """Integer source index (or -1 = fill) for every output pixel of a NEAREST rotate/affine
+    (torchvision _gen_affine_grid + grid_sample(nearest, zeros, align_corners=False))."""
+    th = np.asarray(m, dtype=f32).reshape(2, 3)
+    xs = np.arange(W, dtype=f32) + f32(-W * 0.5 + 0.5)
+    ys = np.arange(H, dtype=f32) + f32(-H * 0.5 + 0.5)
+    X, Y = np.meshgrid(xs, ys)
+    r00, r10, r20 = (th[0, :] / f32(0.5 * W)).astype(f32)
+    r01, r11, r21 = (th[1, :] / f32(0.5 * H)).astype(f32)
+    # torch's CPU bmm accumulates k=0..2 with FMAs: acc = x*r0; acc = fma(y, r1, acc); acc = fma(1, r2, acc)
+    # (pinned empirically against torch 2.11 CPU: 0 mismatching grid values in 1.3 M; the un-fused form
+    # differs in the last ulp for ~14 % of grid values and flips ~1e-5 of the rounded indices)
+    def fma(a, b, c):
+        return (a.astype(np.float64) * np.float64(b) + c.astype(np.float64)).astype(f32)
+    gx = fma(Y, r10, (X * r00).astype(f32)) + r20
+    gy = fma(Y, r11, (X * r01).astype(f32)) + r21
+    ix = (((gx + f32(1)) * f32(W)).astype(f32) - f32(1)) / f32(2)
+    iy = (((gy + f32(1)) * f32(H)).astype(f32) - f32(1)) / f32(2)
+    jx = np.rint(ix).astype(np.int64)
+    jy = np.rint(iy).astype(np.int64)
+    ok = (jx >= 0) & (jx < W) & (jy >= 0) & (jy < H)
+    return np.where(ok, jy * W + jx, -1)
+
+
+def op_affine(x, m):
+    H, W = x.shape
+    idx = affine_index_map(m, H, W)
+    flat = np.concatenate([x.reshape(-1), np.zeros(1, dtype=f32)])
+    return flat[idx].astype(f32)           # idx == -1 picks the appended zero
+
+
+def aa_weights(in_size, out_size):
+    """ATen _upsample_bilinear2d_aa weight table.  Returns (xmin[out], n[out], w[out,3])."""
+    scale = f32(in_size) / f32(out_size)
+    support = f32(scale) if scale >= 1.0 else f32(1.0)
+    invscale = f32(1.0 / scale) if scale >= 1.0 else f32(1.0)
+    xmin = np.zeros(out_size, dtype=np.int64)
+    cnt = np.zeros(out_size, dtype=np.int64)
+    wts = np.zeros((out_size, 3), dtype=f32)
+    for i in range(out_size):
+        center = f32(float(scale) * (i + 0.5))
+        lo = max(int(float(center) - float(support) + 0.5), 0)
+        n = min(int(float(center) + float(support) + 0.5), in_size) - lo
+        n = max(0, min(n, 3))
+        total = f32(0.0)
+        for j in range(n):
+            t = f32((j + lo - float(center) + 0.5) * float(invscale))
+            w = f32(1.0) - abs(t) if abs(t) < 1.0 else f32(0.0)
+            wts[i, j] = w
+            total = f32(total + w)
+        if total != 0:
+            norm = f32(1.0 / float(total))
+            wts[i, :n] = (wts[i, :n] * norm).astype(f32)
+        xmin[i], cnt[i] = lo, n
+    return xmin, cnt, wts
+
+
+def op_crop_resize(x, i, j, h, w):
+    """RandomResizedCrop body: crop [i:i+h, j:j+w] then antialiased bilinear resize to x.shape
+    (horizontal pass first, then vertical; fp32 intermediates)."""
+    H, W = x.shape
+    c = x[i:i + h, j:j + w].astype(f32)
+    xm, xn, xw = aa_weights(w, W)
+    tmp = np.zeros((h, W), dtype=f32)
+    for o in range(W):
+        acc = np.zeros(h, dtype=f32)
+        for t in range(xn[o]):
+            acc = (acc + c[:, xm[o] + t] * xw[o, t]).astype(f32)
+        tmp[:, o] = acc
+    ym, yn, yw = aa_weights(h, H)
+    out = np.zeros((H, W), dtype=f32)
+    for o in range(H):
+        acc = np.zeros(W, dtype=f32)
+        for t in range(yn[o]):
+            acc = (acc + tmp[ym[o] + t, :] * yw[o, t]).astype(f32)
+        out[o, :] = acc
+    return out
+
+
+def op_erase(x, i, j, h, w):
+    out = x.copy()
+    out[i:i + h, j:j + w] = 0
+    return out
+
+
+def op_freq_mask(x, start, end):
+    out = x.copy()
+    out[start:end, :] = 0
+    return out
+
+
+def op_time_mask(x, start, end):
+    out = x.copy()
+    out[:, start:end] = 0
+    return out
+
+
+def op_noise(x, std, noise):
+    return (x + (noise * f32(std)).astype(f32)).astype(f32)
+
+
+def op_group_mask(x, bits, group=4):
+    """bits: iterable of 0/1, one per group (row-major over (H/4)x(W/4)); 1 = zero the group
+    (get_data.py:86-106)."""
+    H, W = x.shape
+    m = np.asarray(bits, dtype=bool).reshape(H // group, W // group)
+    keep = ~np.kron(m, np.ones((group, group), dtype=bool))
+    return (x * keep.astype(f32)).astype(f32)
+
+
+def op_time_warp(x, rate):
+    """TimeWarpWithStretch (get_data.py:42-58) == linear interpolation of |x| along time."""
+    H, W = x.shape
+    n_frames = int(math.ceil(W / rate))
+    k = np.arange(n_frames, dtype=np.float64)
+    t = (k * rate).astype(f32)                     # torch.arange(0, W, rate) in fp32
+    alpha = np.fmod(t, f32(1.0)).astype(f32)
+    i0 = t.astype(np.int64)
+    xp = np.concatenate([np.abs(x), np.zeros((H, 2), dtype=f32)], axis=1)
+    n0 = xp[:, i0]
+    n1 = xp[:, i0 + 1]
+    mag = ((alpha * n1).astype(f32) + ((f32(1.0) - alpha).astype(f32) * n0).astype(f32)).astype(f32)
+    out = np.zeros((H, W), dtype=f32)
+    n = min(n_frames, W)
+    out[:, :n] = mag[:, :n]
+    return out
+
+
+def apply_chain(src, ops, group_bits=None, noise=None):
+    """Run one view's op list over a [H,W] fp32 array.  `ops` = list of (kind, params-tuple)."""
+    x = np.asarray(src, dtype=f32)
+    for kind, p in ops:
+        if kind == OP_NOP:
+            continue
+        elif kind == OP_CROP_RESIZE:
+            x = op_crop_resize(x, *[int(v) for v in p[:4]])
+        elif kind == OP_AFFINE:
+            x = op_affine(x, p[:6])
+        elif kind == OP_ERASE:
+            x = op_erase(x, *[int(v) for v in p[:4]])
+        elif kind == OP_FREQ_MASK:
+            x = op_freq_mask(x, int(p[0]), int(p[1]))
+        elif kind == OP_TIME_MASK:
+            x = op_time_mask(x, int(p[0]), int(p[1]))
+        elif kind == OP_NOISE:
+            x = op_noise(x, p[0], noise)
+        elif kind == OP_GROUP_MASK:
+            x = op_group_mask(x, group_bits)
+        elif kind == OP_TIME_WARP:
+            x = op_time_warp(x, p[0])
+        else:
+            raise ValueError(f"unknown op kind {kind}")
+    return x
