@@ -1,0 +1,210 @@
+/*
+ * avmnist_b200.h -- C ABI of the B200-native DINO training-step library (libavmnist_b200.so).
+ *
+ * The reference (wardvdnb/Multimodal-SSL-AVMNIST) is pure Python/PyTorch and has no FFI of its own; its boundary
+ * for this path is the Python API in AVMNIST_Experiments/{models/dino.py, utils/get_data.py}.  Each entry point
+ * below therefore cites the reference *Python* call site whose arithmetic it replaces (paths relative to
+ * /root/reference/AVMNIST_Experiments/).  The Python binding a maintainer adds is a ctypes stub
+ * (multimodal_ssl_avmnist_b200/_lib.py).
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it, never allocate,
+ *     never synchronise; the caller owns every buffer (workspaces included);
+ *   - return value: 0 = ok, <0 = argument / shape error (B200_E_*), >0 = cudaError_t of the launch;
+ *     b200_last_error() returns a thread-local description of the last non-zero return;
+ *   - fp32 everywhere unless stated; tensors are dense row-major in the stated shape.
+ */
+#ifndef AVMNIST_B200_H
+#define AVMNIST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_E_ARG (-1)        /* null pointer / non-positive size / misaligned pointer */
+#define B200_E_SHAPE (-2)      /* shape not supported by the compiled kernels */
+#define B200_E_SMEM (-3)       /* kernel needs more shared memory than the device grants */
+
+const char* b200_last_error(void);
+int b200_abi_version(void);                      /* bumped whenever a signature below changes */
+int b200_device_sm_count(int device);            /* helper for the host-side launch planner */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Teacher EMA  --  MultiModalDINO.update_teacher, models/dino.py:635-646 (UniModalDINO :1300-1311)
+ *   t <- RN(RN(m*t) + RN((1-m)*s)), two products and one sum, never contracted to an FMA (bit-exact with ATen).
+ * b200_ema_flat  : one contiguous arena of n floats (the layout the engine uses: all teacher params in one arena).
+ * b200_ema_multi : n_tensors separate tensors in ONE launch; t_ptrs/s_ptrs are device arrays of device pointers,
+ *                  offsets is a device array of n_tensors+1 exclusive prefix sums of the tensor sizes.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200_ema_flat(float* teacher, const float* student, int64_t n, float m, float one_minus_m, void* stream);
+int b200_ema_multi(float* const* t_ptrs, const float* const* s_ptrs, const int64_t* offsets, int n_tensors,
+                   int64_t total, float m, float one_minus_m, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused DINO loss, forward + backward + teacher column sums
+ *   -- MultiModalDINOLightning.dino_loss, models/dino.py:822-854 (variant 0)
+ *   -- UniModalDINOLightning.dino_loss,   models/dino.py:1596-1635 (variant 1: needs t_colmean from
+ *      b200_teacher_norm_colmean)
+ *   -- the centre subtraction of MultiModalDINO.forward, models/dino.py:711-714, is folded in: `t` holds the
+ *      UNcentred teacher projections and `center` is subtracted on load.
+ *   s [Vs,B,D], t [Vt,B,D], center [D], grad_s [Vs,B,D] (d loss / d s, times grad_scale),
+ *   part_loss [n_parts], part_colsum [n_parts, D]: per-CTA partials, n_parts = b200_dino_loss_parts(B);
+ *   they are reduced in a fixed order by b200_center_update (deterministic).
+ *   D must be a multiple of 32, D <= 1024.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200_dino_loss_parts(int B);
+int b200_dino_loss_fwd_bwd(const float* s, const float* t, const float* center, const float* t_colmean,
+                           int Vs, int Vt, int B, int D, float tau_s, float tau_t, float grad_scale, int variant,
+                           float* grad_s, float* part_loss, float* part_colsum, void* stream);
+/* column mean over the batch of the L2-normalised, centre-subtracted teacher outputs: out [Vt, D] */
+int b200_teacher_norm_colmean(const float* t, const float* center, int Vt, int B, int D, float* out, void* stream);
+
+/* Centre EMA + loss finalisation -- MultiModalDINO.update_center, models/dino.py:648-653
+ *   colsum = sum over parts (fixed order);  center <- center*m_c + (colsum / n_rows) * one_minus_mc;
+ *   loss_out[0] = sum over parts of part_loss.  If colsum_out != NULL the reduced column sums are also written
+ *   there instead of updating the centre (data-parallel: all-reduce colsum_out, then b200_center_apply). */
+int b200_center_update(float* center, const float* part_colsum, const float* part_loss, int n_parts, int D,
+                       int64_t n_rows, float m_c, float one_minus_mc, float* loss_out, float* colsum_out, void* stream);
+int b200_center_apply(float* center, const float* colsum, int D, int64_t n_rows, float m_c, float one_minus_mc,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Auxiliary losses, forward + backward fused (grad_scale multiplies the gradients)
+ *   b200_mse_align_fwd_bwd -- MultiModalDINOWithMSELightning.mse_loss, models/dino.py:1193-1211
+ *   b200_ce_fwd_bwd        -- supervised_loss, models/dino.py:1001-1025 (one call per modality; mean CE)
+ *   b200_infonce_fwd_bwd   -- infoNCE_loss, models/dino.py:1091-1128: sim = normalize(a) normalize(b)^T / temp,
+ *                             0.5*(CE(sim, I) + CE(sim^T, I)); the [B,B] matrix is never written to HBM.
+ *                             work: float[b200_infonce_work_floats(B, D)].
+ * loss_out[0] receives the scalar (written, not accumulated).
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200_mse_align_fwd_bwd(const float* a, const float* b, int B, int D, float grad_scale, float* grad_a,
+                           float* grad_b, float* loss_out, void* stream);
+int b200_ce_fwd_bwd(const float* logits, const int64_t* labels, int B, int C, float grad_scale, float* grad_logits,
+                    float* loss_out, void* stream);
+int64_t b200_infonce_work_floats(int B, int D);
+int b200_infonce_fwd_bwd(const float* a, const float* b, int B, int D, float temperature, float grad_scale,
+                         float* grad_a, float* grad_b, float* loss_out, float* work, void* stream);
+/* UniModalDINOLightning._cosine_consistency_loss, models/dino.py:1575-1594: emb [V,B,D] */
+int b200_cosine_consistency_fwd_bwd(const float* emb, int V, int B, int D, float grad_scale, float* grad_emb,
+                                    float* loss_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Multi-crop augmentation  --  MultiModalAugmentation.__call__, utils/get_data.py:233-257 and its chains
+ * :121-231 (GaussianNoise :21-27, TimeWarpWithStretch :29-58, GroupedMasking :60-108; torchvision
+ * RandomResizedCrop/RandomRotation/RandomAffine/RandomErasing, torchaudio Frequency/TimeMasking restated).
+ *
+ * One op record = 8 int32 words: kind, then 7 payload words (ints, or float bit patterns):
+ *   1 CROP_RESIZE i,j,h,w   2 AFFINE m0..m5 (fp32 inverse matrix)   3 ERASE i,j,h,w   4 FREQ_MASK start,end
+ *   5 TIME_MASK start,end   6 NOISE std   7 GROUP_MASK (bits in group_bits)   8 TIME_WARP rate   0 NOP
+ * ops: int32 [B, V, B200_AUG_MAX_OPS, 8]; group_bits: uint32 [B, V, 28] (784 bits, 4x4 groups, 1 = zeroed).
+ * Output is view-major: out [V, B, S, S] (S = 28 image / 112 audio) so that every view-call of the encoder
+ * reads a contiguous batch.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define B200_AUG_MAX_OPS 8
+#define B200_AUG_GROUP_WORDS 28
+
+/* image: src float [B,28,28] in [0,1] (src_u8 == 0) or uint8 [B,28,28] scaled by 1/255 (src_u8 == 1) */
+int b200_aug_apply_image(const void* src, int src_u8, const int32_t* ops, float* out, int B, int V, void* stream);
+/* audio: src uint8 [B,112,112] (scaled by 1/255, utils/get_data.py:467) or float; noise: optional injected N(0,1)
+ * field [B,V,112,112] (parity mode), NULL -> Philox(seed, sample*V+view) in-kernel */
+int b200_aug_apply_audio(const void* src, int src_u8, const int32_t* ops, const uint32_t* group_bits,
+                         const float* noise, uint64_t seed, float* out, int B, int V, void* stream);
+/* device-side parameter sampling: spec tables int32 [4][B200_AUG_MAX_OPS][8] in the order
+ * image-global, image-local, audio-global, audio-local (kind, p, a0..a5 as float bits; see augment.py pack_spec);
+ * fills img_ops/aud_ops/group_bits for B samples x (Vg+Vl) views from Philox(seed, step). */
+int b200_aug_sample(const int32_t* spec, int B, int Vg, int Vl, uint64_t seed, uint64_t step, int32_t* img_ops,
+                    int32_t* aud_ops, uint32_t* group_bits, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Encoder building blocks -- conv -> BatchNorm(train) -> ReLU -> MaxPool2 of CentralUnimodalImage/Audio
+ * (models/unimodal.py:127-143, 185-211) and image_encoder()/ImageEncoder (models/dino.py:18-41, 483-499).
+ * Activations are NCHW fp32.  A launch covers n_views view-calls at once: N = n_views*n_per_view samples,
+ * BatchNorm statistics stay segmented per view-call (the reference calls the encoder once per view).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* z = conv(x, w) + bias; stats[view][c] += {sum z, sum z^2} (double).  stats must be zeroed by the caller.
+ * Supported (Cin,Cout,H,W,K,pad): see b200_conv_supported. */
+int b200_conv_supported(int Cin, int Cout, int H, int W, int K, int pad);
+int b200_conv_fwd(const float* x, const float* w, const float* bias, float* z, double* stats, int N,
+                  int n_per_view, int Cin, int Cout, int H, int W, int K, int pad, void* stream);
+/* dx = conv_transpose(dz, w)  (gradient w.r.t. the conv input) */
+int b200_conv_bwd_data(const float* dz, const float* w, float* dx, int N, int Cin, int Cout, int H, int W, int K,
+                       int pad, void* stream);
+/* dw = sum_n corr(x_n, dz_n), db = sum dz.  work: float[b200_conv_bwd_weight_work_floats(...)] */
+int64_t b200_conv_bwd_weight_work_floats(int N, int Cin, int Cout, int H, int W, int K, int pad);
+int b200_conv_bwd_weight(const float* x, const float* dz, float* dw, float* db, float* work, int N, int Cin,
+                         int Cout, int H, int W, int K, int pad, void* stream);
+
+/* BatchNorm finalisation (nn.BatchNorm2d / BatchNorm1d train mode, eps 1e-5, momentum 0.1):
+ *   per view v (in order) and channel c: mean, biased var -> scale[v][c] = gamma*invstd, shift = beta - mean*scale,
+ *   save mean/invstd; running_mean/var updated sequentially over the views (unbiased var), nbt += n_views.
+ *   train == 0: scale/shift come from the running statistics (eval mode), stats ignored. */
+int b200_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, int64_t* num_batches_tracked, float* scale, float* shift, float* mean,
+                     float* invstd, int n_views, int C, int64_t count, float momentum, float eps, int train,
+                     void* stream);
+/* out[n,c,oy,ox] = relu(max over 2x2 of scale*z+shift)   (H, W even; out is [N,C,H/2,W/2]) */
+int b200_bn_relu_pool_fwd(const float* z, const float* scale, const float* shift, float* out, int N,
+                          int n_per_view, int C, int H, int W, void* stream);
+/* backward, pass 1: sums[view][c] += {sum dy, sum dy*xhat} (double; zeroed by caller), dy = unpool+relu' of dout */
+int b200_bn_relu_pool_bwd_reduce(const float* z, const float* dout, const float* scale, const float* shift,
+                                 const float* mean, const float* invstd, double* sums, int N, int n_per_view,
+                                 int C, int H, int W, void* stream);
+/* backward, pass 2: dz = scale*(dy - sum_dy/cnt - xhat*sum_dyxhat/cnt) */
+int b200_bn_relu_pool_bwd_apply(const float* z, const float* dout, const float* scale, const float* shift,
+                                const float* mean, const float* invstd, const double* sums, float* dz, int N,
+                                int n_per_view, int C, int H, int W, void* stream);
+/* dgamma[c] = sum_v sums[v][c].dyxhat, dbeta[c] = sum_v sums[v][c].dy  (accumulate != 0: add into dgamma/dbeta) */
+int b200_bn_param_grads(const double* sums, float* dgamma, float* dbeta, int n_views, int C, int accumulate,
+                        void* stream);
+/* global average pool (AdaptiveAvgPool2d(1), models/dino.py:34) forward / backward over [N,C,HW] */
+int b200_avgpool_fwd(const float* x, float* out, int N, int C, int HW, void* stream);
+int b200_avgpool_bwd(const float* dout, float* dx, int N, int C, int HW, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Linear layers and their fused middles -- nn.Linear of the encoders / fusion / ProjectionHead
+ * (models/dino.py:223-226, 459-468, 1244-1248).
+ *   b200_linear_fwd      : y[M,N] = act(x[M,K] w[N,K]^T + bias); act: 0 none, 1 relu, 2 relu + dropout keep-mask
+ *                          (mask uint8 [M,N], scaled by 1/(1-p)).  ldx/ldy = row strides in floats (concat support).
+ *   b200_linear_bwd_data : dx[M,K] = dy[M,N] w[N,K]            (act backward applied to dy by the caller kernels)
+ *   b200_linear_bwd_weight: dw[N,K] (+)= dy^T x, db[N] (+)= column sums of dy
+ *   b200_act_bwd         : dy <- dy * (y > 0) [* mask/(1-p)]  in place (relu / relu+dropout backward)
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200_linear_fwd(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t ldy, int M,
+                    int N, int K, int act, const uint8_t* mask, float drop_p, void* stream);
+int b200_linear_bwd_data(const float* dy, int64_t lddy, const float* w, float* dx, int64_t lddx, int M, int N,
+                         int K, void* stream);
+int b200_linear_bwd_weight(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dw, float* db, int M,
+                           int N, int K, int accumulate, void* stream);
+int b200_act_bwd(float* dy, const float* y, const uint8_t* mask, float drop_p, int64_t n, void* stream);
+/* BatchNorm1d statistics over the rows of h[M,C] (double sums, zeroed by the caller): stats[c] = {sum, sum^2} */
+int b200_colstats(const float* h, double* stats, int M, int C, void* stream);
+/* g = dropout(gelu_erf(scale*h + shift)) ; backward pass 1 accumulates {sum dy, sum dy*xhat}, pass 2 writes dh */
+int b200_bn1d_gelu_drop_fwd(const float* h, const float* scale, const float* shift, const uint8_t* mask,
+                            float drop_p, float* g, int M, int C, void* stream);
+int b200_bn1d_gelu_drop_bwd_reduce(const float* h, const float* dg, const float* scale, const float* shift,
+                                   const float* mean, const float* invstd, const uint8_t* mask, float drop_p,
+                                   double* sums, int M, int C, void* stream);
+int b200_bn1d_gelu_drop_bwd_apply(const float* h, const float* dg, const float* scale, const float* shift,
+                                  const float* mean, const float* invstd, const uint8_t* mask, float drop_p,
+                                  const double* sums, float* dh, int M, int C, void* stream);
+/* Bernoulli keep-mask from Philox(seed, offset): mask[i] = u >= p */
+int b200_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Optimiser -- torch.optim.Adam(lr, weight_decay) as configured at models/dino.py:953-962, over one flat arena;
+ * `has_grad` (uint8 per element-block of 1 << has_grad_shift elements, may be NULL = all) marks the parameters that
+ * received a gradient this step (Adam skips p.grad is None: the unused fc1/fc2 heads).
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
+                   float bias_correction2_sqrt, float grad_scale, void* stream);
+/* y <- y * alpha (used to apply an upstream autograd scale / the 1/world_size of the gradient all-reduce) */
+int b200_scale_flat(float* y, int64_t n, float alpha, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVMNIST_B200_H */

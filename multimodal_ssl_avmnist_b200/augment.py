@@ -300,9 +300,11 @@ def pack_ops(view_ops, out):
         if kind in (OP_CROP_RESIZE, OP_ERASE, OP_FREQ_MASK, OP_TIME_MASK):
             for t, v in enumerate(p):
                 out[k, 1 + t] = int(v)
-        elif kind in (OP_AFFINE, OP_NOISE, OP_TIME_WARP):
+        elif kind in (OP_AFFINE, OP_NOISE):
             vals = np.asarray(p, dtype=np.float32)
             out[k, 1:1 + len(vals)] = vals.view(np.int32)
+        elif kind == OP_TIME_WARP:            # the rate is a Python double (random.uniform): keep all 64 bits
+            out[k, 1:3] = np.asarray([p[0]], dtype=np.float64).view(np.int32)
 
 
 def pack_group_bits(bits):

@@ -1,0 +1,446 @@
+// Fused multi-crop augmentation for AVMNIST: one CTA stages one (sample, view) in shared memory, runs the whole
+// op chain there (ping-pong buffers, every op in the reference's own order and fp32 arithmetic) and writes the
+// finished view once.  HBM traffic = source read (re-reads by the other views hit L2) + one write per view:
+// the algorithmic minimum of SURVEY §8(d) (373,184 B / sample for 2 global + 4 local views of both modalities).
+//
+// Arithmetic restated from the third-party transforms the reference calls, pinned
+// against torch 2.11 / torchvision 0.26 / torchaudio 2.11 CPU through oracle/augment_ref.py:
+//   * nearest rotate/affine: integer gather, grid = fma(y, r1, x*r0) + r2 (ATen's bmm order), round-half-even;
+//   * antialiased bilinear resize: ATen's separable weight tables (fp32 weights, double index math), FMA sums;
+//   * time warp: linear interpolation of |x| at torch.arange(0, W, rate) time steps (vectorised-arange rounding);
+//   * frequency/time masks, grouped 4x4 masking, erasing, additive gaussian noise.
+#include "common.cuh"
+
+namespace b200 {
+
+enum { OP_NOP = 0, OP_CROP_RESIZE, OP_AFFINE, OP_ERASE, OP_FREQ_MASK, OP_TIME_MASK, OP_NOISE, OP_GROUP_MASK, OP_TIME_WARP };
+enum { SPEC_RRC = 1, SPEC_ROTATE, SPEC_AFFINE, SPEC_ERASE, SPEC_FREQ_MASK, SPEC_TIME_MASK, SPEC_NOISE, SPEC_GROUP_MASK, SPEC_TIME_WARP };
+
+struct AATable {  // per output index: first source index, tap count, up to 3 weights
+    int lo;
+    int n;
+    float w[3];
+};
+
+__device__ __forceinline__ void aa_entry(int i, int in_size, int out_size, AATable& e) {
+    const float scale = __fdiv_rn((float)in_size, (float)out_size);
+    const float support = (scale >= 1.0f) ? scale : 1.0f;
+    const float invscale = (scale >= 1.0f) ? (float)(1.0 / (double)scale) : 1.0f;
+    const float center = (float)((double)scale * ((double)i + 0.5));
+    int lo = (int)((double)center - (double)support + 0.5);
+    lo = lo < 0 ? 0 : lo;
+    int hi = (int)((double)center + (double)support + 0.5);
+    hi = hi > in_size ? in_size : hi;
+    int n = hi - lo;
+    n = n < 0 ? 0 : (n > 3 ? 3 : n);
+    float total = 0.f;
+    float w[3] = {0.f, 0.f, 0.f};
+    for (int j = 0; j < n; ++j) {
+        float t = (float)(((double)(j + lo) - (double)center + 0.5) * (double)invscale);
+        t = fabsf(t);
+        w[j] = t < 1.0f ? __fsub_rn(1.0f, t) : 0.f;
+        total = __fadd_rn(total, w[j]);
+    }
+    if (total != 0.f) {
+        const float norm = (float)(1.0 / (double)total);
+        for (int j = 0; j < n; ++j) w[j] = __fmul_rn(w[j], norm);
+    }
+    e.lo = lo;
+    e.n = n;
+    e.w[0] = w[0];
+    e.w[1] = w[1];
+    e.w[2] = w[2];
+}
+
+// torch.arange(0, stop, step, float32)[k] as ATen's CPU kernel rounds it (see oracle/augment_ref.py arange_f32)
+__device__ __forceinline__ float arange_f32(int k, int n, double step) {
+    if (k < (n / 16) * 16) {
+        int i8 = k & ~7;
+        float base = (float)((double)i8 * step);
+        return (float)((double)base + (double)(k & 7) * step);
+    }
+    return (float)((double)k * step);
+}
+
+template <int S, int T>
+__global__ void __launch_bounds__(T) aug_apply_kernel(const void* __restrict__ src, int src_u8, const int32_t* __restrict__ ops,
+                                                      const uint32_t* __restrict__ group_bits, const float* __restrict__ noise,
+                                                      uint64_t seed, float* __restrict__ out, int B, int V) {
+    constexpr int NPIX = S * S;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* bufA = reinterpret_cast<float*>(smem_raw);
+    float* bufB = bufA + NPIX;
+    AATable* xtab = reinterpret_cast<AATable*>(bufB + NPIX);
+    AATable* ytab = xtab + S;
+    __shared__ int32_t sops[B200_AUG_MAX_OPS * 8];
+    __shared__ uint32_t sbits[B200_AUG_GROUP_WORDS];
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x / V, v = blockIdx.x - b * V;
+    const size_t rec = (size_t)b * V + v;
+    if (tid < B200_AUG_MAX_OPS * 8) sops[tid] = __ldg(ops + rec * (B200_AUG_MAX_OPS * 8) + tid);
+    if (group_bits != nullptr && tid < B200_AUG_GROUP_WORDS) sbits[tid] = __ldg(group_bits + rec * B200_AUG_GROUP_WORDS + tid);
+
+    // ---- stage the source (coalesced, vectorised) ----
+    if (src_u8) {
+        const uint32_t* s4 = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(src) + (size_t)b * NPIX);
+        for (int i = tid; i < NPIX / 4; i += T) {
+            uint32_t w = __ldg(s4 + i);
+            bufA[4 * i + 0] = __fdiv_rn((float)(w & 0xff), 255.0f);
+            bufA[4 * i + 1] = __fdiv_rn((float)((w >> 8) & 0xff), 255.0f);
+            bufA[4 * i + 2] = __fdiv_rn((float)((w >> 16) & 0xff), 255.0f);
+            bufA[4 * i + 3] = __fdiv_rn((float)(w >> 24), 255.0f);
+        }
+    } else {
+        const float4* s4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + (size_t)b * NPIX);
+        for (int i = tid; i < NPIX / 4; i += T) reinterpret_cast<float4*>(bufA)[i] = __ldg(s4 + i);
+    }
+    __syncthreads();
+
+    float* cur = bufA;
+    float* alt = bufB;
+    for (int k = 0; k < B200_AUG_MAX_OPS; ++k) {
+        const int kind = sops[k * 8];
+        const int32_t* p = sops + k * 8 + 1;
+        if (kind == OP_NOP) continue;
+        if (kind == OP_CROP_RESIZE) {
+            const int ci = p[0], cj = p[1], ch = p[2], cw = p[3];
+            for (int i = tid; i < 2 * S; i += T) {
+                if (i < S) aa_entry(i, cw, S, xtab[i]);
+                else aa_entry(i - S, ch, S, ytab[i - S]);
+            }
+            __syncthreads();
+            // horizontal: alt[r][o] for r < ch
+            for (int e = tid; e < ch * S; e += T) {
+                const int r = e / S, o = e - r * S;
+                const AATable te = xtab[o];
+                const float* row = cur + (ci + r) * S + cj + te.lo;
+                float acc = 0.f;
+                if (te.n > 0) acc = __fmul_rn(row[0], te.w[0]);
+                if (te.n > 1) acc = __fmaf_rn(row[1], te.w[1], acc);
+                if (te.n > 2) acc = __fmaf_rn(row[2], te.w[2], acc);
+                alt[e] = acc;
+            }
+            __syncthreads();
+            // vertical: cur[o][x]
+            for (int e = tid; e < NPIX; e += T) {
+                const int o = e / S, x = e - o * S;
+                const AATable te = ytab[o];
+                const float* col = alt + te.lo * S + x;
+                float acc = 0.f;
+                if (te.n > 0) acc = __fmul_rn(col[0], te.w[0]);
+                if (te.n > 1) acc = __fmaf_rn(col[S], te.w[1], acc);
+                if (te.n > 2) acc = __fmaf_rn(col[2 * S], te.w[2], acc);
+                cur[e] = acc;
+            }
+            __syncthreads();
+        } else if (kind == OP_AFFINE) {
+            const float half = 0.5f * (float)S;
+            const float r00 = __fdiv_rn(__int_as_float(p[0]), half), r10 = __fdiv_rn(__int_as_float(p[1]), half),
+                        r20 = __fdiv_rn(__int_as_float(p[2]), half);
+            const float r01 = __fdiv_rn(__int_as_float(p[3]), half), r11 = __fdiv_rn(__int_as_float(p[4]), half),
+                        r21 = __fdiv_rn(__int_as_float(p[5]), half);
+            const float off = -(float)S * 0.5f + 0.5f;
+            for (int e = tid; e < NPIX; e += T) {
+                const int y = e / S, x = e - y * S;
+                const float xs = (float)x + off, ys = (float)y + off;
+                const float gx = __fadd_rn(__fmaf_rn(ys, r10, __fmul_rn(xs, r00)), r20);
+                const float gy = __fadd_rn(__fmaf_rn(ys, r11, __fmul_rn(xs, r01)), r21);
+                const float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), (float)S), 1.0f), 2.0f);
+                const float iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), (float)S), 1.0f), 2.0f);
+                const float fx = rintf(ix), fy = rintf(iy);
+                float val = 0.f;
+                if (fx >= 0.f && fx < (float)S && fy >= 0.f && fy < (float)S) val = cur[(int)fy * S + (int)fx];
+                alt[e] = val;
+            }
+            __syncthreads();
+            float* t = cur; cur = alt; alt = t;
+        } else if (kind == OP_ERASE) {
+            const int ei = p[0], ej = p[1], eh = p[2], ew = p[3];
+            for (int e = tid; e < eh * ew; e += T) {
+                const int r = e / ew, c = e - r * ew;
+                cur[(ei + r) * S + ej + c] = 0.f;
+            }
+            __syncthreads();
+        } else if (kind == OP_FREQ_MASK) {
+            const int s0 = p[0], s1 = p[1];
+            for (int e = tid; e < (s1 - s0) * S; e += T) cur[s0 * S + e] = 0.f;
+            __syncthreads();
+        } else if (kind == OP_TIME_MASK) {
+            const int s0 = p[0], n = p[1] - p[0];
+            for (int e = tid; e < n * S; e += T) {
+                const int y = e / n, c = e - y * n;
+                cur[y * S + s0 + c] = 0.f;
+            }
+            __syncthreads();
+        } else if (kind == OP_NOISE) {
+            const float std = __int_as_float(p[0]);
+            if (noise != nullptr) {
+                const float* nz = noise + rec * NPIX;
+                for (int e = tid; e < NPIX; e += T) cur[e] = __fadd_rn(cur[e], __fmul_rn(__ldg(nz + e), std));
+            } else {
+                Philox rng(seed);
+                for (int q = tid; q < NPIX / 4; q += T) {
+                    uint4 r = rng((uint64_t)q, (uint64_t)rec * 4 + 1);
+                    // two Box-Muller pairs
+                    float u1 = 1.0f - u01(r.x), u2 = u01(r.y), u3 = 1.0f - u01(r.z), u4 = u01(r.w);
+                    float ra = sqrtf(-2.0f * logf(u1)), rb = sqrtf(-2.0f * logf(u3));
+                    float s1, c1, s2, c2;
+                    sincospif(2.0f * u2, &s1, &c1);
+                    sincospif(2.0f * u4, &s2, &c2);
+                    cur[4 * q + 0] += ra * c1 * std;
+                    cur[4 * q + 1] += ra * s1 * std;
+                    cur[4 * q + 2] += rb * c2 * std;
+                    cur[4 * q + 3] += rb * s2 * std;
+                }
+            }
+            __syncthreads();
+        } else if (kind == OP_GROUP_MASK) {
+            constexpr int GW = S / 4;
+            for (int e = tid; e < NPIX; e += T) {
+                const int y = e / S, x = e - y * S;
+                const int g = (y >> 2) * GW + (x >> 2);
+                if ((sbits[g >> 5] >> (g & 31)) & 1u) cur[e] = 0.f;
+            }
+            __syncthreads();
+        } else if (kind == OP_TIME_WARP) {
+            const double rate = __hiloint2double(p[1], p[0]);
+            const int n_frames = (int)ceil((double)S / rate);
+            for (int e = tid; e < NPIX; e += T) {
+                const int y = e / S, kx = e - y * S;
+                float val = 0.f;
+                if (kx < n_frames) {
+                    const float ts = arange_f32(kx, n_frames, rate);
+                    const float alpha = fmodf(ts, 1.0f);
+                    const int i0 = (int)ts;
+                    const float n0 = i0 < S ? fabsf(cur[y * S + i0]) : 0.f;
+                    const float n1 = (i0 + 1) < S ? fabsf(cur[y * S + i0 + 1]) : 0.f;
+                    val = __fadd_rn(__fmul_rn(alpha, n1), __fmul_rn(__fsub_rn(1.0f, alpha), n0));
+                }
+                alt[e] = val;
+            }
+            __syncthreads();
+            float* t = cur; cur = alt; alt = t;
+        }
+    }
+    // ---- write the finished view (view-major layout [V,B,S,S]) ----
+    float4* o4 = reinterpret_cast<float4*>(out + ((size_t)v * B + b) * NPIX);
+    for (int i = tid; i < NPIX / 4; i += T) o4[i] = reinterpret_cast<const float4*>(cur)[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Device-side parameter sampling (throughput mode).  Same distributions as the host sampler (augment.py), drawn
+// from Philox(seed; stream = step, sample, view, modality).  One CTA per (sample, view); thread 0 walks the two
+// chains, all threads cooperate on the grouped-masking subset selection.
+// ---------------------------------------------------------------------------------------------------------
+struct Draw {
+    Philox rng;
+    uint64_t stream;
+    uint64_t ctr;
+    __device__ Draw(uint64_t seed, uint64_t s) : rng(seed), stream(s), ctr(0) {}
+    __device__ uint32_t bits() { return rng(ctr++, stream).x; }
+    __device__ float uniform(float lo, float hi) { return u01(bits()) * (hi - lo) + lo; }   // torch uniform_ on float
+    __device__ float rand01() { return u01(bits()); }
+    __device__ int randint(int n) { return (int)(bits() % (uint32_t)n); }
+};
+
+__device__ void store_affine(int32_t* rec, double angle_deg, double tx, double ty, double scale) {
+    const double rot = angle_deg * 0.017453292519943295;
+    const double a = cos(rot), b = -sin(rot), c = sin(rot), d = cos(rot);
+    double m[6] = {d / scale, -b / scale, 0.0, -c / scale, a / scale, 0.0};
+    m[2] += m[0] * (-tx) + m[1] * (-ty);
+    m[5] += m[3] * (-tx) + m[4] * (-ty);
+    rec[0] = OP_AFFINE;
+    for (int i = 0; i < 6; ++i) rec[1 + i] = __float_as_int((float)m[i]);
+}
+
+__device__ int sample_chain(const int32_t* spec, int S, Draw& d, int32_t* rec /*[MAX_OPS*8]*/, int* group_count) {
+    int n_out = 0;
+    *group_count = -1;
+    for (int i = 0; i < B200_AUG_MAX_OPS * 8; ++i) rec[i] = 0;     // unused payload words are defined (zero)
+    for (int k = 0; k < B200_AUG_MAX_OPS; ++k) {
+        const int kind = spec[k * 8];
+        if (kind == 0) continue;
+        const float p = __int_as_float(spec[k * 8 + 1]);
+        float a[6];
+        for (int i = 0; i < 6; ++i) a[i] = __int_as_float(spec[k * 8 + 2 + i]);
+        int32_t* r = rec + n_out * 8;
+        if (kind == SPEC_ERASE) {
+            if (!(d.rand01() < p)) continue;
+            const double area = (double)S * S;
+            for (int t = 0; t < 10; ++t) {
+                const double ea = area * (double)d.uniform(a[0], a[1]);
+                const double ar = (double)expf(d.uniform(a[2], a[3]));
+                const int h = (int)rint(sqrt(ea * ar)), w = (int)rint(sqrt(ea / ar));
+                if (!(h < S && w < S)) continue;
+                r[0] = OP_ERASE;
+                r[1] = d.randint(S - h + 1);
+                r[2] = d.randint(S - w + 1);
+                r[3] = h;
+                r[4] = w;
+                ++n_out;
+                break;
+            }
+            continue;
+        }
+        if (p >= 0.f && p < d.rand01()) continue;   // RandomApply: skip iff p < r
+        if (kind == SPEC_RRC) {
+            const double area = (double)S * S;
+            bool done = false;
+            int ci = 0, cj = 0, ch = S, cw = S;
+            for (int t = 0; t < 10 && !done; ++t) {
+                const double target = area * (double)d.uniform(a[0], a[1]);
+                const double ar = (double)expf(d.uniform(a[2], a[3]));
+                const int w = (int)rint(sqrt(target * ar)), h = (int)rint(sqrt(target / ar));
+                if (w > 0 && w <= S && h > 0 && h <= S) {
+                    ci = d.randint(S - h + 1);
+                    cj = d.randint(S - w + 1);
+                    ch = h;
+                    cw = w;
+                    done = true;
+                }
+            }
+            if (!done) {  // central-crop fallback (square input: in_ratio == 1)
+                const float rlo = expf(a[2]), rhi = expf(a[3]);
+                if (1.0f < fminf(rlo, rhi)) { cw = S; ch = (int)rint((double)S / fminf(rlo, rhi)); }
+                else if (1.0f > fmaxf(rlo, rhi)) { ch = S; cw = (int)rint((double)S * fmaxf(rlo, rhi)); }
+                ci = (S - ch) / 2;
+                cj = (S - cw) / 2;
+            }
+            r[0] = OP_CROP_RESIZE; r[1] = ci; r[2] = cj; r[3] = ch; r[4] = cw;
+            ++n_out;
+        } else if (kind == SPEC_ROTATE) {
+            const double angle = (double)d.uniform(-a[0], a[0]);
+            store_affine(r, -angle, 0.0, 0.0, 1.0);
+            ++n_out;
+        } else if (kind == SPEC_AFFINE) {
+            const double angle = (double)d.uniform(-a[0], a[0]);
+            const int flags = (int)a[5];
+            double tx = 0.0, ty = 0.0, sc = 1.0;
+            if (flags & 2) {
+                const float mdx = a[1] * (float)S, mdy = a[2] * (float)S;
+                tx = rint((double)d.uniform(-mdx, mdx));
+                ty = rint((double)d.uniform(-mdy, mdy));
+            }
+            if (flags & 1) sc = (double)d.uniform(a[3], a[4]);
+            store_affine(r, angle, tx, ty, sc);
+            ++n_out;
+        } else if (kind == SPEC_FREQ_MASK || kind == SPEC_TIME_MASK) {
+            const int param = (int)a[0];
+            if (param < 1) continue;
+            const float value = d.rand01() * (float)param;
+            const float minv = d.rand01() * ((float)S - value);
+            r[0] = kind == SPEC_FREQ_MASK ? OP_FREQ_MASK : OP_TIME_MASK;
+            r[1] = (int)minv;
+            r[2] = (int)minv + (int)value;
+            ++n_out;
+        } else if (kind == SPEC_NOISE) {
+            r[0] = OP_NOISE;
+            r[1] = __float_as_int(a[0]);
+            ++n_out;
+        } else if (kind == SPEC_GROUP_MASK) {
+            r[0] = OP_GROUP_MASK;
+            *group_count = (int)a[0];
+            ++n_out;
+        } else if (kind == SPEC_TIME_WARP) {
+            const double u = u01d(d.bits(), d.bits());
+            const double rate = (double)a[0] + ((double)a[1] - (double)a[0]) * u;   // random.uniform(min, max)
+            r[0] = OP_TIME_WARP;
+            r[1] = __double2loint(rate);
+            r[2] = __double2hiint(rate);
+            ++n_out;
+        }
+    }
+    return n_out;
+}
+
+constexpr int NGROUPS = 784;
+__global__ void __launch_bounds__(128) aug_sample_kernel(const int32_t* __restrict__ spec, int B, int Vg, int Vl, uint64_t seed,
+                                                         uint64_t step, int32_t* __restrict__ img_ops, int32_t* __restrict__ aud_ops,
+                                                         uint32_t* __restrict__ group_bits) {
+    __shared__ int32_t sspec[4 * B200_AUG_MAX_OPS * 8];
+    __shared__ int32_t rec_i[B200_AUG_MAX_OPS * 8], rec_a[B200_AUG_MAX_OPS * 8];
+    __shared__ int gcount;
+    __shared__ uint32_t keys[NGROUPS];
+    __shared__ uint32_t bits[B200_AUG_GROUP_WORDS];
+    const int V = Vg + Vl;
+    const int b = blockIdx.x / V, v = blockIdx.x - b * V;
+    const size_t rec = (size_t)b * V + v;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 4 * B200_AUG_MAX_OPS * 8; i += blockDim.x) sspec[i] = __ldg(spec + i);
+    if (tid < B200_AUG_GROUP_WORDS) bits[tid] = 0u;
+    __syncthreads();
+    const bool local = v >= Vg;
+    const uint64_t stream = (step << 36) ^ ((uint64_t)rec << 4);
+    if (tid == 0) {
+        Draw di(seed, stream | 2), da(seed, stream | 3);
+        int gc;
+        sample_chain(sspec + (local ? 1 : 0) * B200_AUG_MAX_OPS * 8, 28, di, rec_i, &gc);
+        sample_chain(sspec + (local ? 3 : 2) * B200_AUG_MAX_OPS * 8, 112, da, rec_a, &gc);
+        gcount = gc;
+    }
+    __syncthreads();
+    const int gc = gcount;
+    if (gc > 0) {
+        // uniformly random subset of gc groups: rank of a random key (ties broken by index) < gc
+        Philox rng(seed);
+        for (int g = tid; g < NGROUPS; g += blockDim.x) keys[g] = rng((uint64_t)g, stream | 4).x;
+        __syncthreads();
+        for (int g = tid; g < NGROUPS; g += blockDim.x) {
+            const uint32_t kg = keys[g];
+            int rank = 0;
+            for (int h = 0; h < NGROUPS; ++h) {
+                const uint32_t kh = keys[h];
+                rank += (kh < kg) || (kh == kg && h < g);
+            }
+            if (rank < gc) atomicOr(&bits[g >> 5], 1u << (g & 31));
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < B200_AUG_MAX_OPS * 8; i += blockDim.x) {
+        img_ops[rec * (B200_AUG_MAX_OPS * 8) + i] = rec_i[i];
+        aud_ops[rec * (B200_AUG_MAX_OPS * 8) + i] = rec_a[i];
+    }
+    if (tid < B200_AUG_GROUP_WORDS) group_bits[rec * B200_AUG_GROUP_WORDS + tid] = bits[tid];
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_aug_apply_image(const void* src, int src_u8, const int32_t* ops, float* out, int B, int V, void* stream) {
+    B200_REQUIRE(src && ops && out && B > 0 && V > 0, B200_E_ARG, "aug_apply_image: bad arguments");
+    B200_REQUIRE((((uintptr_t)src | (uintptr_t)out) & 15) == 0, B200_E_ARG, "aug_apply_image: pointers must be 16-byte aligned");
+    constexpr int S = 28, T = 128;
+    const size_t smem = 2 * S * S * sizeof(float) + 2 * S * sizeof(AATable);
+    aug_apply_kernel<S, T><<<B * V, T, smem, as_stream(stream)>>>(src, src_u8, ops, nullptr, nullptr, 0, out, B, V);
+    return launch_status("aug_apply_image");
+}
+
+int b200_aug_apply_audio(const void* src, int src_u8, const int32_t* ops, const uint32_t* group_bits, const float* noise,
+                         uint64_t seed, float* out, int B, int V, void* stream) {
+    B200_REQUIRE(src && ops && group_bits && out && B > 0 && V > 0, B200_E_ARG, "aug_apply_audio: bad arguments");
+    B200_REQUIRE((((uintptr_t)src | (uintptr_t)out) & 15) == 0, B200_E_ARG, "aug_apply_audio: pointers must be 16-byte aligned");
+    constexpr int S = 112, T = 256;
+    const size_t smem = 2 * S * S * sizeof(float) + 2 * S * sizeof(AATable);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(aug_apply_kernel<S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        B200_REQUIRE(e == cudaSuccess, B200_E_SMEM, "aug_apply_audio: cannot reserve %zu B of shared memory", smem);
+        attr_done = true;
+    }
+    aug_apply_kernel<S, T><<<B * V, T, smem, as_stream(stream)>>>(src, src_u8, ops, group_bits, noise, seed, out, B, V);
+    return launch_status("aug_apply_audio");
+}
+
+int b200_aug_sample(const int32_t* spec, int B, int Vg, int Vl, uint64_t seed, uint64_t step, int32_t* img_ops,
+                    int32_t* aud_ops, uint32_t* group_bits, void* stream) {
+    B200_REQUIRE(spec && img_ops && aud_ops && group_bits && B > 0 && Vg >= 0 && Vl >= 0 && Vg + Vl > 0, B200_E_ARG,
+                 "aug_sample: bad arguments");
+    aug_sample_kernel<<<B * (Vg + Vl), 128, 0, as_stream(stream)>>>(spec, B, Vg, Vl, seed, step, img_ops, aud_ops, group_bits);
+    return launch_status("aug_sample");
+}
+
+}  // extern "C"

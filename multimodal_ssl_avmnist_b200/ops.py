@@ -1,0 +1,291 @@
+"""Thin tensor-level wrappers over the C ABI (one Python function per `b200_*` entry point).
+
+torch is used only for device memory and the current CUDA stream; every wrapper hands raw pointers to the
+library and raises if the call fails.  Tensors must live on a CUDA device and be contiguous.
+"""
+import torch
+
+from . import _lib
+
+
+def _lib_():
+    return _lib.load()
+
+
+def _ptr(t, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.B200Error("B200 ops need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise _lib.B200Error("B200 ops need contiguous tensors")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.B200Error(f"expected {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+F32, F64, I32, I64, U8 = torch.float32, torch.float64, torch.int32, torch.int64, torch.uint8
+
+
+# ---- flat arena ops ----------------------------------------------------------------------------------------
+def ema_flat(teacher, student, m):
+    """teacher <- m*teacher + (1-m)*student (bit-exact with the reference's mul/mul/add, dino.py:635-646)."""
+    one_minus_m = 1 - m          # Python double, rounded to fp32 by the call
+    _lib.check(_lib_().b200_ema_flat(_ptr(teacher, F32), _ptr(student, F32), teacher.numel(), m, one_minus_m, _stream()), "ema_flat")
+
+
+class MultiTensorTable:
+    """Device-side pointer/offset table for b200_ema_multi (built once per parameter set)."""
+
+    def __init__(self, teacher_tensors, student_tensors):
+        assert len(teacher_tensors) == len(student_tensors) and len(teacher_tensors) > 0
+        dev = teacher_tensors[0].device
+        sizes = [t.numel() for t in teacher_tensors]
+        for t, s in zip(teacher_tensors, student_tensors):
+            assert t.numel() == s.numel() and t.is_contiguous() and s.is_contiguous() and t.dtype == F32 and s.dtype == F32
+        off = [0]
+        for n in sizes:
+            off.append(off[-1] + n)
+        self.total = off[-1]
+        self.n = len(sizes)
+        self.t_ptrs = torch.tensor([t.data_ptr() for t in teacher_tensors], dtype=I64, device=dev)
+        self.s_ptrs = torch.tensor([s.data_ptr() for s in student_tensors], dtype=I64, device=dev)
+        self.offsets = torch.tensor(off, dtype=I64, device=dev)
+        self._keep = (teacher_tensors, student_tensors)
+
+
+def ema_multi(table, m):
+    one_minus_m = 1 - m
+    _lib.check(_lib_().b200_ema_multi(table.t_ptrs.data_ptr(), table.s_ptrs.data_ptr(), table.offsets.data_ptr(), table.n,
+                                      table.total, m, one_minus_m, _stream()), "ema_multi")
+
+
+def adam_flat(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    bc1 = 1 - beta1 ** step
+    bc2s = (1 - beta2 ** step) ** 0.5
+    _lib.check(_lib_().b200_adam_flat(_ptr(param, F32), _ptr(grad, F32), _ptr(exp_avg, F32), _ptr(exp_avg_sq, F32), param.numel(),
+                                      lr, beta1, beta2, eps, weight_decay, bc1, bc2s, grad_scale, _stream()), "adam_flat")
+
+
+def scale_flat(y, alpha):
+    _lib.check(_lib_().b200_scale_flat(_ptr(y, F32), y.numel(), alpha, _stream()), "scale_flat")
+
+
+def dropout_mask(mask, p, seed, offset):
+    _lib.check(_lib_().b200_dropout_mask(_ptr(mask, U8), mask.numel(), p, seed, offset, _stream()), "dropout_mask")
+
+
+# ---- losses ------------------------------------------------------------------------------------------------
+def dino_loss_parts(B):
+    return _lib_().b200_dino_loss_parts(B)
+
+
+def dino_loss_fwd_bwd(s, t, center, tau_s, tau_t, grad_s, part_loss, part_colsum, grad_scale=1.0, variant=0, t_colmean=None):
+    Vs, B, D = s.shape
+    Vt = t.shape[0]
+    _lib.check(_lib_().b200_dino_loss_fwd_bwd(_ptr(s, F32), _ptr(t, F32), _ptr(center, F32), _ptr(t_colmean, F32), Vs, Vt, B, D,
+                                              tau_s, tau_t, grad_scale, variant, _ptr(grad_s, F32), _ptr(part_loss, F32),
+                                              _ptr(part_colsum, F32), _stream()), "dino_loss_fwd_bwd")
+
+
+def teacher_norm_colmean(t, center, out):
+    Vt, B, D = t.shape
+    _lib.check(_lib_().b200_teacher_norm_colmean(_ptr(t, F32), _ptr(center, F32), Vt, B, D, _ptr(out, F32), _stream()), "teacher_norm_colmean")
+
+
+def center_update(center, part_colsum, part_loss, n_rows, m_c, loss_out, colsum_out=None):
+    n_parts, D = part_colsum.shape
+    _lib.check(_lib_().b200_center_update(_ptr(center, F32), _ptr(part_colsum, F32), _ptr(part_loss, F32), n_parts, D, n_rows,
+                                          m_c, 1 - m_c, _ptr(loss_out, F32), _ptr(colsum_out, F32), _stream()), "center_update")
+
+
+def center_apply(center, colsum, n_rows, m_c):
+    _lib.check(_lib_().b200_center_apply(_ptr(center, F32), _ptr(colsum, F32), colsum.numel(), n_rows, m_c, 1 - m_c, _stream()), "center_apply")
+
+
+def mse_align_fwd_bwd(a, b, grad_a, grad_b, loss_out, grad_scale=1.0):
+    B, D = a.shape
+    _lib.check(_lib_().b200_mse_align_fwd_bwd(_ptr(a, F32), _ptr(b, F32), B, D, grad_scale, _ptr(grad_a, F32), _ptr(grad_b, F32),
+                                              _ptr(loss_out, F32), _stream()), "mse_align_fwd_bwd")
+
+
+def ce_fwd_bwd(logits, labels, grad_logits, loss_out, grad_scale=1.0):
+    B, Cc = logits.shape
+    _lib.check(_lib_().b200_ce_fwd_bwd(_ptr(logits, F32), _ptr(labels, I64), B, Cc, grad_scale, _ptr(grad_logits, F32),
+                                       _ptr(loss_out, F32), _stream()), "ce_fwd_bwd")
+
+
+def infonce_work_floats(B, D):
+    return _lib_().b200_infonce_work_floats(B, D)
+
+
+def infonce_fwd_bwd(a, b, grad_a, grad_b, loss_out, work, temperature=0.07, grad_scale=1.0):
+    B, D = a.shape
+    _lib.check(_lib_().b200_infonce_fwd_bwd(_ptr(a, F32), _ptr(b, F32), B, D, temperature, grad_scale, _ptr(grad_a, F32),
+                                            _ptr(grad_b, F32), _ptr(loss_out, F32), _ptr(work, F32), _stream()), "infonce_fwd_bwd")
+
+
+def cosine_consistency_fwd_bwd(emb, grad_emb, loss_out, grad_scale=1.0):
+    V, B, D = emb.shape
+    _lib.check(_lib_().b200_cosine_consistency_fwd_bwd(_ptr(emb, F32), V, B, D, grad_scale, _ptr(grad_emb, F32), _ptr(loss_out, F32),
+                                                       _stream()), "cosine_consistency_fwd_bwd")
+
+
+# ---- augmentation ------------------------------------------------------------------------------------------
+def aug_apply_image(src, ops, out):
+    V, B = out.shape[0], out.shape[1]
+    _lib.check(_lib_().b200_aug_apply_image(_ptr(src), 1 if src.dtype == U8 else 0, _ptr(ops, I32), _ptr(out, F32), B, V, _stream()),
+               "aug_apply_image")
+
+
+def aug_apply_audio(src, ops, group_bits, out, noise=None, seed=0):
+    V, B = out.shape[0], out.shape[1]
+    _lib.check(_lib_().b200_aug_apply_audio(_ptr(src), 1 if src.dtype == U8 else 0, _ptr(ops, I32), _ptr(group_bits, I32),
+                                            _ptr(noise, F32), seed, _ptr(out, F32), B, V, _stream()), "aug_apply_audio")
+
+
+def aug_sample(spec, B, Vg, Vl, seed, step, img_ops, aud_ops, group_bits):
+    _lib.check(_lib_().b200_aug_sample(_ptr(spec, I32), B, Vg, Vl, seed, step, _ptr(img_ops, I32), _ptr(aud_ops, I32),
+                                       _ptr(group_bits, I32), _stream()), "aug_sample")
+
+
+# ---- encoder blocks ----------------------------------------------------------------------------------------
+def conv_supported(Cin, Cout, H, W, K, pad):
+    return bool(_lib_().b200_conv_supported(Cin, Cout, H, W, K, pad))
+
+
+def conv_fwd(x, w, bias, z, stats, n_per_view, pad):
+    N, Cin, H, W = x.shape
+    Cout, _, K, _ = w.shape
+    _lib.check(_lib_().b200_conv_fwd(_ptr(x, F32), _ptr(w, F32), _ptr(bias, F32), _ptr(z, F32), _ptr(stats, F64), N, n_per_view, Cin,
+                                     Cout, H, W, K, pad, _stream()), "conv_fwd")
+
+
+def conv_bwd_data(dz, w, dx, pad):
+    N, Cin, H, W = dx.shape
+    Cout, _, K, _ = w.shape
+    _lib.check(_lib_().b200_conv_bwd_data(_ptr(dz, F32), _ptr(w, F32), _ptr(dx, F32), N, Cin, Cout, H, W, K, pad, _stream()), "conv_bwd_data")
+
+
+def conv_bwd_weight_work_floats(N, Cin, Cout, H, W, K, pad):
+    n = _lib_().b200_conv_bwd_weight_work_floats(N, Cin, Cout, H, W, K, pad)
+    if n < 0:
+        raise _lib.B200Error(f"conv_bwd_weight: shape {(Cin, Cout, H, W, K, pad)} not compiled")
+    return n
+
+
+def conv_bwd_weight(x, dz, dw, db, work, pad):
+    N, Cin, H, W = x.shape
+    Cout, _, K, _ = dw.shape
+    _lib.check(_lib_().b200_conv_bwd_weight(_ptr(x, F32), _ptr(dz, F32), _ptr(dw, F32), _ptr(db, F32), _ptr(work, F32), N, Cin, Cout, H, W,
+                                            K, pad, _stream()), "conv_bwd_weight")
+
+
+def bn_finalize(stats, gamma, beta, running_mean, running_var, nbt, scale, shift, mean, invstd, n_views, count, train=True,
+                momentum=0.1, eps=1e-5):
+    Cc = gamma.numel()
+    _lib.check(_lib_().b200_bn_finalize(_ptr(stats, F64), _ptr(gamma, F32), _ptr(beta, F32), _ptr(running_mean, F32), _ptr(running_var, F32),
+                                        _ptr(nbt, I64), _ptr(scale, F32), _ptr(shift, F32), _ptr(mean, F32), _ptr(invstd, F32), n_views,
+                                        Cc, count, momentum, eps, 1 if train else 0, _stream()), "bn_finalize")
+
+
+def bn_relu_pool_fwd(z, scale, shift, out, n_per_view):
+    N, Cc, H, W = z.shape
+    _lib.check(_lib_().b200_bn_relu_pool_fwd(_ptr(z, F32), _ptr(scale, F32), _ptr(shift, F32), _ptr(out, F32), N, n_per_view, Cc, H, W,
+                                             _stream()), "bn_relu_pool_fwd")
+
+
+def bn_relu_pool_bwd_reduce(z, dout, scale, shift, mean, invstd, sums, n_per_view):
+    N, Cc, H, W = z.shape
+    _lib.check(_lib_().b200_bn_relu_pool_bwd_reduce(_ptr(z, F32), _ptr(dout, F32), _ptr(scale, F32), _ptr(shift, F32), _ptr(mean, F32),
+                                                    _ptr(invstd, F32), _ptr(sums, F64), N, n_per_view, Cc, H, W, _stream()),
+               "bn_relu_pool_bwd_reduce")
+
+
+def bn_relu_pool_bwd_apply(z, dout, scale, shift, mean, invstd, sums, dz, n_per_view):
+    N, Cc, H, W = z.shape
+    _lib.check(_lib_().b200_bn_relu_pool_bwd_apply(_ptr(z, F32), _ptr(dout, F32), _ptr(scale, F32), _ptr(shift, F32), _ptr(mean, F32),
+                                                   _ptr(invstd, F32), _ptr(sums, F64), _ptr(dz, F32), N, n_per_view, Cc, H, W, _stream()),
+               "bn_relu_pool_bwd_apply")
+
+
+def bn_param_grads(sums, dgamma, dbeta, n_views, accumulate=False):
+    _lib.check(_lib_().b200_bn_param_grads(_ptr(sums, F64), _ptr(dgamma, F32), _ptr(dbeta, F32), n_views, dgamma.numel(),
+                                           1 if accumulate else 0, _stream()), "bn_param_grads")
+
+
+def avgpool_fwd(x, out):
+    N, Cc = x.shape[0], x.shape[1]
+    _lib.check(_lib_().b200_avgpool_fwd(_ptr(x, F32), _ptr(out, F32), N, Cc, x[0, 0].numel(), _stream()), "avgpool_fwd")
+
+
+def avgpool_bwd(dout, dx):
+    N, Cc = dx.shape[0], dx.shape[1]
+    _lib.check(_lib_().b200_avgpool_bwd(_ptr(dout, F32), _ptr(dx, F32), N, Cc, dx[0, 0].numel(), _stream()), "avgpool_bwd")
+
+
+# ---- linear layers -----------------------------------------------------------------------------------------
+def _rows(t):
+    """(pointer, row stride) of a 2-D tensor whose rows are contiguous (column slices of a wider matrix allowed)."""
+    if not t.is_cuda or t.dtype != F32 or t.dim() != 2 or t.stride(1) != 1:
+        raise _lib.B200Error("linear ops need 2-D fp32 CUDA tensors with unit column stride")
+    return t.data_ptr(), t.stride(0)
+
+
+def linear_fwd(x, w, bias, y, act=0, mask=None, drop_p=0.0):
+    M, K = x.shape
+    N = w.shape[0]
+    xp, ldx = _rows(x)
+    yp, ldy = _rows(y)
+    _lib.check(_lib_().b200_linear_fwd(xp, ldx, _ptr(w, F32), _ptr(bias, F32), yp, ldy, M, N, K, act, _ptr(mask, U8), drop_p, _stream()),
+               "linear_fwd")
+
+
+def linear_bwd_data(dy, w, dx):
+    M, N = dy.shape
+    K = w.shape[1]
+    dyp, lddy = _rows(dy)
+    dxp, lddx = _rows(dx)
+    _lib.check(_lib_().b200_linear_bwd_data(dyp, lddy, _ptr(w, F32), dxp, lddx, M, N, K, _stream()), "linear_bwd_data")
+
+
+def linear_bwd_weight(dy, x, dw, db, accumulate=False):
+    M, N = dy.shape
+    K = x.shape[1]
+    dyp, lddy = _rows(dy)
+    xp, ldx = _rows(x)
+    _lib.check(_lib_().b200_linear_bwd_weight(dyp, lddy, xp, ldx, _ptr(dw, F32), _ptr(db, F32), M, N, K, 1 if accumulate else 0, _stream()),
+               "linear_bwd_weight")
+
+
+def act_bwd(dy, y, drop_p=0.0):
+    _lib.check(_lib_().b200_act_bwd(_ptr(dy, F32), _ptr(y, F32), None, drop_p, dy.numel(), _stream()), "act_bwd")
+
+
+def colstats(h, stats):
+    M, Cc = h.shape
+    _lib.check(_lib_().b200_colstats(_ptr(h, F32), _ptr(stats, F64), M, Cc, _stream()), "colstats")
+
+
+def bn1d_gelu_drop_fwd(h, scale, shift, mask, drop_p, g):
+    M, Cc = h.shape
+    _lib.check(_lib_().b200_bn1d_gelu_drop_fwd(_ptr(h, F32), _ptr(scale, F32), _ptr(shift, F32), _ptr(mask, U8), drop_p, _ptr(g, F32), M, Cc,
+                                               _stream()), "bn1d_gelu_drop_fwd")
+
+
+def bn1d_gelu_drop_bwd_reduce(h, dg, scale, shift, mean, invstd, mask, drop_p, sums):
+    M, Cc = h.shape
+    _lib.check(_lib_().b200_bn1d_gelu_drop_bwd_reduce(_ptr(h, F32), _ptr(dg, F32), _ptr(scale, F32), _ptr(shift, F32), _ptr(mean, F32),
+                                                      _ptr(invstd, F32), _ptr(mask, U8), drop_p, _ptr(sums, F64), M, Cc, _stream()),
+               "bn1d_gelu_drop_bwd_reduce")
+
+
+def bn1d_gelu_drop_bwd_apply(h, dg, scale, shift, mean, invstd, mask, drop_p, sums, dh):
+    M, Cc = h.shape
+    _lib.check(_lib_().b200_bn1d_gelu_drop_bwd_apply(_ptr(h, F32), _ptr(dg, F32), _ptr(scale, F32), _ptr(shift, F32), _ptr(mean, F32),
+                                                     _ptr(invstd, F32), _ptr(mask, U8), drop_p, _ptr(sums, F64), _ptr(dh, F32), M, Cc,
+                                                     _stream()), "bn1d_gelu_drop_bwd_apply")

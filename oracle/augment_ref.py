@@ -105,17 +105,19 @@ def op_crop_resize(x, i, j, h, w):
     c = x[i:i + h, j:j + w].astype(f32)
     xm, xn, xw = aa_weights(w, W)
     tmp = np.zeros((h, W), dtype=f32)
+    def fma(a, b, acc):      # ATen's AA loops contract to FMAs (bit-exact against torch 2.11 CPU)
+        return (a.astype(np.float64) * np.float64(b) + acc.astype(np.float64)).astype(f32)
     for o in range(W):
         acc = np.zeros(h, dtype=f32)
         for t in range(xn[o]):
-            acc = (acc + c[:, xm[o] + t] * xw[o, t]).astype(f32)
+            acc = (c[:, xm[o] + t] * xw[o, t]).astype(f32) if t == 0 else fma(c[:, xm[o] + t], xw[o, t], acc)
         tmp[:, o] = acc
     ym, yn, yw = aa_weights(h, H)
     out = np.zeros((H, W), dtype=f32)
     for o in range(H):
         acc = np.zeros(W, dtype=f32)
         for t in range(yn[o]):
-            acc = (acc + tmp[ym[o] + t, :] * yw[o, t]).astype(f32)
+            acc = (tmp[ym[o] + t, :] * yw[o, t]).astype(f32) if t == 0 else fma(tmp[ym[o] + t, :], yw[o, t], acc)
         out[o, :] = acc
     return out
 
@@ -151,12 +153,23 @@ def op_group_mask(x, bits, group=4):
     return (x * keep.astype(f32)).astype(f32)
 
 
+def arange_f32(n, step):
+    """torch.arange(0, stop, step, dtype=float32) as ATen's CPU kernel evaluates it (RangeFactoriesKernel: the
+    first floor(n/16)*16 values come from 8-lane vectors `float(double(float(step*i8)) + lane*step)`, the tail from
+    the scalar `float(step*i)`; pinned empirically against torch 2.11 in the build container, 0 mismatches)."""
+    k = np.arange(n, dtype=np.int64)
+    scalar = (k.astype(np.float64) * step).astype(f32)
+    i8 = k - (k % 8)
+    base = (i8.astype(np.float64) * step).astype(f32)
+    vec = (base.astype(np.float64) + (k % 8).astype(np.float64) * step).astype(f32)
+    return np.where(k < (n // 16) * 16, vec, scalar)
+
+
 def op_time_warp(x, rate):
     """TimeWarpWithStretch (get_data.py:42-58) == linear interpolation of |x| along time."""
     H, W = x.shape
     n_frames = int(math.ceil(W / rate))
-    k = np.arange(n_frames, dtype=np.float64)
-    t = (k * rate).astype(f32)                     # torch.arange(0, W, rate) in fp32
+    t = arange_f32(n_frames, rate)                 # torch.arange(0, W, rate, dtype=float32)
     alpha = np.fmod(t, f32(1.0)).astype(f32)
     i0 = t.astype(np.int64)
     xp = np.concatenate([np.abs(x), np.zeros((H, 2), dtype=f32)], axis=1)

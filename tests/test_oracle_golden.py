@@ -93,11 +93,11 @@ def test_augment_against_reference_outputs(tag, golden, golden_aug):
         for k, ref in zip(("gi", "ga", "li", "la"), sums[s]):
             assert abs(float(o[k].astype(np.float64).sum()) - ref) < 2e-3 * max(1.0, abs(ref)) * 1e-2, (tag, s, k)
         if s < 2:
-            np.testing.assert_allclose(o["gi"][:, None], golden_aug[f"{tag}_{s}_gi"], atol=2e-5, rtol=0)
-            np.testing.assert_allclose(o["li"][:, None], golden_aug[f"{tag}_{s}_li"], atol=2e-5, rtol=0)
+            np.testing.assert_allclose(o["gi"][:, None], golden_aug[f"{tag}_{s}_gi"], atol=1e-6, rtol=0)
+            np.testing.assert_allclose(o["li"][:, None], golden_aug[f"{tag}_{s}_li"], atol=1e-6, rtol=0)
             for nm in ("ga", "la"):
                 a = o[nm][:, None]
-                np.testing.assert_allclose(a[:, :, ::4, 1::4], golden_aug[f"{tag}_{s}_{nm}_dec"], atol=2e-5, rtol=0)
+                np.testing.assert_allclose(a[:, :, ::4, 1::4], golden_aug[f"{tag}_{s}_{nm}_dec"], atol=1e-6, rtol=0)
                 np.testing.assert_allclose(a.astype(np.float64).sum(-1), golden_aug[f"{tag}_{s}_{nm}_rows"], atol=2e-3)
                 np.testing.assert_allclose(a.astype(np.float64).sum(-2), golden_aug[f"{tag}_{s}_{nm}_cols"], atol=2e-3)
 
