@@ -1,0 +1,598 @@
+"""The DINO training-step engine: flat parameter arenas + the launch schedule of one step.
+
+One engine instance owns, on one GPU,
+  * the student / teacher parameter arenas (fp32, one contiguous buffer each; `nn.Parameter`s of the API
+    modules are views into them, named exactly like the reference's state_dict entries),
+  * the gradient arena and the Adam moment arenas (same layout as the student arena),
+  * BatchNorm running statistics, the DINO centre, and per-batch-size activation workspaces,
+and runs the reference's step order: multi-crop augmentation -> student on all views and
+teacher on the global views (BatchNorm statistics per view-call) -> projection heads -> fused DINO loss
+(+ centre EMA) [+ MSE / InfoNCE / CE on an extra un-augmented pass] -> teacher EMA -> backward -> Adam.
+
+Every arithmetic stage is a `b200_*` call into libavmnist_b200.so (ops.py); torch only provides device memory,
+streams and (for data parallel runs) the NCCL all-reduce of the gradient arena and of the centre column sums.
+
+Arena layout (student):  [ encoder params that receive gradients | projection head | unused fc1/fc2 | mode heads ]
+        (teacher):       [ encoder params that receive gradients | projection head | unused fc1/fc2 ]
+so the teacher EMA is ONE flat kernel over the common prefix and Adam is one flat kernel over the trainable
+prefix (plus one over the mode heads); the unused CentralNet classifier heads (models/unimodal.py:121-125,
+179-183) are EMA'd and check-pointed like in the reference but never receive gradients.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import augment as A
+from . import ops
+
+F32 = torch.float32
+
+
+# ---------------------------------------------------------------------------------------------------------
+# parameter inventories (names as in the reference state_dict; see models/dino.py:454-468, unimodal.py:105-183)
+# ---------------------------------------------------------------------------------------------------------
+def _conv(n, co, ci, k):
+    return [(f"{n}.weight", (co, ci, k, k)), (f"{n}.bias", (co,))]
+
+
+def _vec2(n, c):
+    return [(f"{n}.weight", (c,)), (f"{n}.bias", (c,))]
+
+
+def _lin(n, o, i):
+    return [(f"{n}.weight", (o, i)), (f"{n}.bias", (o,))]
+
+
+def central_encoder_params(E, O):
+    """(used, unused) parameter specs of CentralMultiModalEncoder, each in the reference's declaration order."""
+    used, unused = [], []
+    p = "image_encoder.0"
+    used += _conv(f"{p}.conv1", 32, 1, 5) + _vec2(f"{p}.bn1", 32) + _conv(f"{p}.conv2", 64, 32, 5) + _vec2(f"{p}.bn2", 64)
+    unused += _lin(f"{p}.fc1", 1024, 1600) + _lin(f"{p}.fc2", 10, 1024)
+    used += _lin("image_encoder.1", E, 1600)
+    p = "audio_encoder.0"
+    used += _conv(f"{p}.conv1", 8, 1, 5) + _vec2(f"{p}.bn1", 8) + _conv(f"{p}.conv2", 16, 8, 5) + _vec2(f"{p}.bn2", 16)
+    used += _conv(f"{p}.conv3", 32, 16, 5) + _vec2(f"{p}.bn3", 32) + _conv(f"{p}.conv4", 64, 32, 5) + _vec2(f"{p}.bn4", 64)
+    unused += _lin(f"{p}.fc1", 1024, 3136) + _lin(f"{p}.fc2", 10, 1024)
+    used += _lin("audio_encoder.1", E, 3136)
+    used += _lin("fusion.0", E, 2 * E) + _lin("fusion.3", O, E)
+    return used, unused
+
+
+def central_reference_order(E, O):
+    """Parameter names in the reference's `.parameters()` order (for state_dict / optimizer compatibility)."""
+    names = []
+    p = "image_encoder.0"
+    for l in ("conv1", "bn1", "conv2", "bn2", "fc1", "fc2"):
+        names += [f"{p}.{l}.weight", f"{p}.{l}.bias"]
+    names += ["image_encoder.1.weight", "image_encoder.1.bias"]
+    p = "audio_encoder.0"
+    for l in ("conv1", "bn1", "conv2", "bn2", "conv3", "bn3", "conv4", "bn4", "fc1", "fc2"):
+        names += [f"{p}.{l}.weight", f"{p}.{l}.bias"]
+    names += ["audio_encoder.1.weight", "audio_encoder.1.bias", "fusion.0.weight", "fusion.0.bias", "fusion.3.weight", "fusion.3.bias"]
+    return names
+
+
+def image_simple_params(O):
+    used = _conv("encoder.0", 32, 1, 3) + _vec2("encoder.1", 32) + _conv("encoder.4", 64, 32, 3) + _vec2("encoder.5", 64)
+    used += _conv("encoder.8", 128, 64, 3) + _vec2("encoder.9", 128) + _lin("encoder.14", 512, 128) + _lin("projection.0", O, 512)
+    return used, []
+
+
+def head_params(in_dim, out_dim, hidden=512):
+    return _lin("mlp.0", hidden, in_dim) + _vec2("mlp.1", hidden) + _lin("mlp.4", out_dim, hidden)
+
+
+CENTRAL_IMAGE_LAYERS = [("image_encoder.0.conv1", "image_encoder.0.bn1", 1, 32, 28, 5, 2),
+                        ("image_encoder.0.conv2", "image_encoder.0.bn2", 32, 64, 14, 5, 0)]
+CENTRAL_AUDIO_LAYERS = [("audio_encoder.0.conv1", "audio_encoder.0.bn1", 1, 8, 112, 5, 2),
+                        ("audio_encoder.0.conv2", "audio_encoder.0.bn2", 8, 16, 56, 5, 2),
+                        ("audio_encoder.0.conv3", "audio_encoder.0.bn3", 16, 32, 28, 5, 2),
+                        ("audio_encoder.0.conv4", "audio_encoder.0.bn4", 32, 64, 14, 5, 2)]
+SIMPLE_IMAGE_LAYERS = [("encoder.0", "encoder.1", 1, 32, 28, 3, 1), ("encoder.4", "encoder.5", 32, 64, 14, 3, 1),
+                       ("encoder.8", "encoder.9", 64, 128, 7, 3, 1)]
+
+
+class Arena:
+    """A flat fp32 buffer with named views."""
+
+    def __init__(self, spec, device, pad_to=4):
+        self.spec = list(spec)
+        self.offsets = {}
+        off = 0
+        for name, shape in self.spec:
+            n = int(np.prod(shape))
+            self.offsets[name] = (off, n, tuple(shape))
+            off += (n + pad_to - 1) // pad_to * pad_to          # keep every tensor 16-byte aligned
+        self.size = off
+        self.flat = torch.zeros(max(off, 4), dtype=F32, device=device)
+
+    def view(self, name, flat=None):
+        off, n, shape = self.offsets[name]
+        return (self.flat if flat is None else flat)[off:off + n].view(shape)
+
+    def views(self, flat=None):
+        return {name: self.view(name, flat) for name, _ in self.spec}
+
+    def range_of(self, names):
+        lo = min(self.offsets[n][0] for n in names)
+        hi = max(self.offsets[n][0] + (self.offsets[n][1] + 3) // 4 * 4 for n in names)
+        return lo, hi
+
+
+class _BN:
+    """Running statistics + per-step scale/shift/mean/invstd scratch of one BatchNorm layer."""
+
+    def __init__(self, C, device):
+        self.C = C
+        self.running_mean = torch.zeros(C, device=device)
+        self.running_var = torch.ones(C, device=device)
+        self.num_batches_tracked = torch.zeros(1, dtype=torch.int64, device=device)
+
+
+class DinoStepEngine:
+    """See module docstring.  kind: 'multi_central' (CentralMultiModalEncoder) or 'image_simple' (ImageEncoder);
+    mode: 'default' | 'semi_supervised' | 'infonce' | 'mse' (multi_central only)."""
+
+    def __init__(self, kind="multi_central", mode="default", encoder_output_dim=256, output_dim=256, projection_dim=128,
+                 n_global_views=2, n_local_views=4, momentum=0.996, center_momentum=0.9, student_temperature=0.1,
+                 teacher_temperature=0.04, learning_rate=1e-4, weight_decay=1e-6, dropout=0.3, fusion_dropout=0.3, alpha=1.0,
+                 cosine_loss_alpha=0.0, augment_values=None, seed=0, device=None, process_group=None):
+        if not torch.cuda.is_available():
+            raise ops._lib.B200Error("DinoStepEngine needs a CUDA device: the hot path has no CPU fallback")
+        ops._lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        assert kind in ("multi_central", "image_simple")
+        assert mode == "default" or kind == "multi_central"
+        self.kind, self.mode = kind, mode
+        self.E, self.O, self.P = encoder_output_dim, output_dim, projection_dim
+        self.Vg, self.Vl = n_global_views, n_local_views
+        self.V = self.Vg + self.Vl
+        self.momentum, self.center_momentum = momentum, center_momentum
+        self.tau_s, self.tau_t = student_temperature, teacher_temperature
+        self.lr, self.weight_decay = learning_rate, weight_decay
+        self.dropout, self.fusion_dropout, self.alpha = dropout, fusion_dropout, alpha
+        self.cosine_loss_alpha = cosine_loss_alpha
+        self.seed = seed
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if (process_group is not None or (
+            torch.distributed.is_available() and torch.distributed.is_initialized())) else 1
+        self.step_count = 0          # optimizer steps taken (Adam bias correction)
+        self.rng_step = 0            # augmentation / dropout stream position
+
+        if kind == "multi_central":
+            used, unused = central_encoder_params(self.E, self.O)
+            self.img_layers, self.aud_layers = CENTRAL_IMAGE_LAYERS, CENTRAL_AUDIO_LAYERS
+        else:
+            used, unused = image_simple_params(self.O)
+            self.img_layers, self.aud_layers = SIMPLE_IMAGE_LAYERS, []
+        head = [("head." + n, s) for n, s in head_params(self.O, self.P)]
+        enc_used = [("enc." + n, s) for n, s in used]
+        enc_unused = [("enc." + n, s) for n, s in unused]
+        aux = []
+        if mode != "default":
+            out = 10 if mode == "semi_supervised" else self.P
+            for m in ("aux_image", "aux_audio"):
+                aux += [(f"{m}.{n}", s) for n, s in head_params(self.E, out)]
+        self.student = Arena(enc_used + head + enc_unused + aux, self.device)
+        self.teacher = Arena(enc_used + head + enc_unused, self.device)
+        self.n_ema = self.teacher.size
+        self.n_trainable_prefix = self.student.range_of([n for n, _ in enc_used + head])[1]
+        self.aux_range = self.student.range_of([n for n, _ in aux]) if aux else None
+        self.grad = torch.zeros_like(self.student.flat)
+        self.exp_avg = torch.zeros_like(self.student.flat)
+        self.exp_avg_sq = torch.zeros_like(self.student.flat)
+        self.S = self.student.views()
+        self.T = self.teacher.views()
+        self.G = self.student.views(self.grad)
+        self.center = torch.zeros(1, self.P, device=self.device)
+        # BatchNorm buffers
+        self.bn_s, self.bn_t = {}, {}
+        for conv, bn, ci, co, hw, k, pad in self.img_layers + self.aud_layers:
+            self.bn_s["enc." + bn], self.bn_t["enc." + bn] = _BN(co, self.device), _BN(co, self.device)
+        self.bn_s["head.mlp.1"], self.bn_t["head.mlp.1"] = _BN(512, self.device), _BN(512, self.device)
+        for m in ("aux_image", "aux_audio"):
+            if aux:
+                self.bn_s[f"{m}.mlp.1"] = _BN(512, self.device)
+        self._ws = {}
+        self._init_parameters()
+        self.set_augmentation(augment_values)
+
+    # ------------------------------------------------------------------------------------------------------
+    def _init_parameters(self):
+        """PyTorch default init (kaiming_uniform(a=sqrt 5) == U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weights and biases,
+        BatchNorm weight 1 / bias 0); the teacher starts as a copy of the student (models/dino.py:617, 627)."""
+        g = torch.Generator(device="cpu").manual_seed(self.seed)
+        bn_bases = {"enc." + bn for _, bn, *_ in self.img_layers + self.aud_layers} | {"head.mlp.1", "aux_image.mlp.1", "aux_audio.mlp.1"}
+        bounds = {}
+        for name, shape in self.student.spec:
+            v = self.student.view(name)
+            base = name.rsplit(".", 1)[0]
+            if base in bn_bases:
+                v.fill_(1.0 if name.endswith(".weight") else 0.0)
+            elif len(shape) > 1:
+                bounds[base] = 1.0 / math.sqrt(int(np.prod(shape[1:])))
+                v.copy_(((torch.rand(shape, generator=g) * 2 - 1) * bounds[base]).to(self.device))
+            else:
+                v.copy_(((torch.rand(shape, generator=g) * 2 - 1) * bounds[base]).to(self.device))
+        self.sync_teacher()
+
+    def sync_teacher(self):
+        self.teacher.flat.copy_(self.student.flat[:self.n_ema])
+        for k in self.bn_t:
+            self.bn_t[k].running_mean.copy_(self.bn_s[k].running_mean)
+            self.bn_t[k].running_var.copy_(self.bn_s[k].running_var)
+            self.bn_t[k].num_batches_tracked.copy_(self.bn_s[k].num_batches_tracked)
+
+    def load_named(self, student=None, teacher=None, student_head=None, teacher_head=None, aux_image=None, aux_audio=None):
+        """Copy tensors given by reference names (e.g. 'image_encoder.0.conv1.weight', 'mlp.0.weight') into the arenas."""
+        for prefix, arena_views, src in (("enc.", self.S, student), ("enc.", self.T, teacher), ("head.", self.S, student_head),
+                                         ("head.", self.T, teacher_head), ("aux_image.", self.S, aux_image), ("aux_audio.", self.S, aux_audio)):
+            if src is None:
+                continue
+            for k, v in src.items():
+                if prefix + k in arena_views:
+                    arena_views[prefix + k].copy_(v.to(self.device))
+
+    def set_augmentation(self, augment_values):
+        ig, il = A.image_chains()
+        ag, al = A.default_audio_chains() if augment_values is None else A.audio_chains_from_values(augment_values)
+        self.chains = (ig, il, ag, al)
+        spec = np.stack([A.pack_spec(c) for c in self.chains])
+        self.aug_spec = torch.from_numpy(spec).to(self.device)
+
+    # ------------------------------------------------------------------------------------------------------
+    def _workspace(self, B):
+        if B in self._ws:
+            return self._ws[B]
+        dev, V, Vg = self.device, self.V, self.Vg
+        extra = 1 if self.mode != "default" else 0
+        Ns, Nt = (V + extra) * B, Vg * B
+
+        def e(*shape, dtype=F32):
+            return torch.empty(*shape, dtype=dtype, device=dev)
+
+        w = {"B": B, "Ns": Ns, "Nt": Nt}
+        # augmentation
+        w["img_ops"] = torch.zeros(B, V, A.MAX_OPS, A.OP_WORDS, dtype=torch.int32, device=dev)
+        w["aud_ops"] = torch.zeros(B, V, A.MAX_OPS, A.OP_WORDS, dtype=torch.int32, device=dev)
+        w["group_bits"] = torch.zeros(B, V, A.GROUP_WORDS, dtype=torch.int32, device=dev)
+        w["x_img"] = e(Ns, 1, 28, 28)
+        if self.aud_layers:
+            w["x_aud"] = e(Ns, 1, 112, 112)
+        wg_work = 0
+        for role, N in (("s", Ns), ("t", Nt)):
+            for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers)):
+                for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers):
+                    ho = hw + 2 * pad - k + 1
+                    nv = N // B
+                    w[f"{role}.{mod}.z{li}"] = e(N, co, ho, ho)
+                    w[f"{role}.{mod}.p{li}"] = e(N, co, ho // 2, ho // 2)
+                    w[f"{role}.{mod}.stats{li}"] = torch.zeros(nv, co, 2, dtype=torch.float64, device=dev)
+                    for nm in ("scale", "shift", "mean", "invstd"):
+                        w[f"{role}.{mod}.{nm}{li}"] = e(nv, co)
+                    if role == "s":
+                        w[f"s.{mod}.sums{li}"] = torch.zeros(nv, co, 2, dtype=torch.float64, device=dev)
+                        wg_work = max(wg_work, ops.conv_bwd_weight_work_floats(N, ci, co, hw, hw, k, pad))
+        zmax = max([w[k].numel() for k in w if isinstance(w[k], torch.Tensor) and k.startswith("s.") and ".z" in k])
+        pmax = max([w[k].numel() for k in w if isinstance(w[k], torch.Tensor) and k.startswith("s.") and ".p" in k])
+        w["dz"] = e(zmax)
+        w["dp_a"], w["dp_b"] = e(pmax), e(pmax)
+        w["wg_work"] = e(max(wg_work, 4))
+        E, O, P = self.E, self.O, self.P
+        Nv = V * B
+        if self.kind == "multi_central":
+            for role, N, nfus in (("s", Ns, Nv), ("t", Nt, Nt)):
+                w[f"{role}.cat"] = e(N, 2 * E)
+                w[f"{role}.h1"] = e(nfus, E)
+                w[f"{role}.feat"] = e(nfus, O)
+                w[f"{role}.fmask"] = torch.ones(nfus, E, dtype=torch.uint8, device=dev)
+            w["d.cat"] = e(Ns, 2 * E)
+            w["d.h1"] = e(Nv, E)
+        else:
+            for role, N in (("s", Ns), ("t", Nt)):
+                w[f"{role}.pool"] = e(N, 128)
+                w[f"{role}.e14"] = e(N, 512)
+                w[f"{role}.feat"] = e(N, O)
+            w["d.pool"], w["d.e14"] = e(Ns, 128), e(Ns, 512)
+        w["d.feat"] = e(Nv, O)
+        for role, N in (("s", Nv), ("t", Nt)):
+            w[f"{role}.hh"] = e(N, 512)
+            w[f"{role}.g"] = e(N, 512)
+            w[f"{role}.proj"] = e(N, P)
+            w[f"{role}.hstats"] = torch.zeros(512, 2, dtype=torch.float64, device=dev)
+            for nm in ("hscale", "hshift", "hmean", "hinvstd"):
+                w[f"{role}.{nm}"] = e(1, 512)
+        w["s.hmask"] = torch.ones(Nv, 512, dtype=torch.uint8, device=dev)
+        w["s.hsums"] = torch.zeros(512, 2, dtype=torch.float64, device=dev)
+        w["d.proj"], w["d.g"], w["d.hh"] = e(Nv, P), e(Nv, 512), e(Nv, 512)
+        parts = ops.dino_loss_parts(B)
+        w["part_loss"], w["part_colsum"] = e(parts), e(parts, P)
+        w["t_colmean"] = e(Vg, P)
+        w["colsum"] = e(P + 1)
+        w["loss"] = torch.zeros(4, device=dev)             # [dino, aux, cosine, total]
+        if self.mode != "default":
+            out = 10 if self.mode == "semi_supervised" else P
+            for m in ("aux_image", "aux_audio"):
+                w[f"{m}.hh"], w[f"{m}.g"], w[f"{m}.out"] = e(B, 512), e(B, 512), e(B, out)
+                w[f"{m}.d.out"], w[f"{m}.d.g"], w[f"{m}.d.hh"] = e(B, out), e(B, 512), e(B, 512)
+                w[f"{m}.hstats"] = torch.zeros(512, 2, dtype=torch.float64, device=dev)
+                w[f"{m}.hsums"] = torch.zeros(512, 2, dtype=torch.float64, device=dev)
+                for nm in ("hscale", "hshift", "hmean", "hinvstd"):
+                    w[f"{m}.{nm}"] = e(1, 512)
+            if self.mode == "infonce":
+                w["infonce_work"] = e(ops.infonce_work_floats(B, P))
+        if self.cosine_loss_alpha > 0:
+            w["d.emb"] = e(Nv, O)
+        self._ws[B] = w
+        return w
+
+    # ------------------------------------------------------------------------------------------------------
+    # augmentation
+    # ------------------------------------------------------------------------------------------------------
+    def augment(self, images, audios, B=None):
+        """Device-sampled multi-crop views of a raw batch: images [B,28,28] (fp32 in [0,1] or uint8),
+        audios [B,112,112] (uint8 or fp32).  Returns view-major tensors ([V,B,28,28], [V,B,112,112])."""
+        B = images.shape[0]
+        w = self._workspace(B)
+        ops.aug_sample(self.aug_spec, B, self.Vg, self.Vl, self.seed, self.rng_step, w["img_ops"], w["aud_ops"], w["group_bits"])
+        return self.augment_with_params(images, audios, w["img_ops"], w["aud_ops"], w["group_bits"], None)
+
+    def augment_with_params(self, images, audios, img_ops, aud_ops, group_bits, noise):
+        B = images.shape[0]
+        w = self._workspace(B)
+        V = self.V
+        xi = w["x_img"][:V * B].view(V, B, 28, 28)
+        ops.aug_apply_image(images.reshape(B, 28, 28), img_ops, xi)
+        xa = None
+        if self.aud_layers and audios is not None:
+            xa = w["x_aud"][:V * B].view(V, B, 112, 112)
+            ops.aug_apply_audio(audios.reshape(B, 112, 112), aud_ops, group_bits, xa, noise=noise,
+                                seed=(self.seed * 1000003 + self.rng_step) & 0xFFFFFFFFFFFF)
+        return xi, xa
+
+    # ------------------------------------------------------------------------------------------------------
+    # forward building blocks
+    # ------------------------------------------------------------------------------------------------------
+    def _conv_stack(self, w, role, mod, layers, x, N, B, P, bns, train=True):
+        nv = N // B
+        cur = x
+        for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers):
+            z, p, stats = w[f"{role}.{mod}.z{li}"], w[f"{role}.{mod}.p{li}"], w[f"{role}.{mod}.stats{li}"]
+            stats.zero_()
+            ops.conv_fwd(cur.view(N, ci, hw, hw), P["enc." + conv + ".weight"], P["enc." + conv + ".bias"], z, stats, B, pad)
+            b = bns["enc." + bn]
+            ho = z.shape[-1]
+            ops.bn_finalize(stats, P["enc." + bn + ".weight"], P["enc." + bn + ".bias"], b.running_mean, b.running_var,
+                            b.num_batches_tracked, w[f"{role}.{mod}.scale{li}"], w[f"{role}.{mod}.shift{li}"],
+                            w[f"{role}.{mod}.mean{li}"], w[f"{role}.{mod}.invstd{li}"], nv, B * ho * ho, train=train)
+            ops.bn_relu_pool_fwd(z, w[f"{role}.{mod}.scale{li}"], w[f"{role}.{mod}.shift{li}"], p, B)
+            cur = p
+        return cur
+
+    def _head_fwd(self, w, role, prefix, P, bn, x, out, hh, g, mask, drop_p, tag=""):
+        M = x.shape[0]
+        ops.linear_fwd(x, P[prefix + "mlp.0.weight"], P[prefix + "mlp.0.bias"], hh)
+        st = w[f"{role}.{tag}hstats"]
+        st.zero_()
+        ops.colstats(hh, st)
+        ops.bn_finalize(st, P[prefix + "mlp.1.weight"], P[prefix + "mlp.1.bias"], bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                        w[f"{role}.{tag}hscale"], w[f"{role}.{tag}hshift"], w[f"{role}.{tag}hmean"], w[f"{role}.{tag}hinvstd"], 1, M)
+        ops.bn1d_gelu_drop_fwd(hh, w[f"{role}.{tag}hscale"], w[f"{role}.{tag}hshift"], mask, drop_p, g)
+        ops.linear_fwd(g, P[prefix + "mlp.4.weight"], P[prefix + "mlp.4.bias"], out)
+
+    def _head_bwd(self, w, role, prefix, x, d_out, hh, g, d_g, d_hh, d_x, mask, drop_p, tag=""):
+        S, G = self.S, self.G
+        ops.linear_bwd_weight(d_out, g, G[prefix + "mlp.4.weight"], G[prefix + "mlp.4.bias"])
+        ops.linear_bwd_data(d_out, S[prefix + "mlp.4.weight"], d_g)
+        sums = w[f"{role}.{tag}hsums"]
+        sums.zero_()
+        sc, sh, mu, inv = (w[f"{role}.{tag}h{n}"] for n in ("scale", "shift", "mean", "invstd"))
+        ops.bn1d_gelu_drop_bwd_reduce(hh, d_g, sc, sh, mu, inv, mask, drop_p, sums)
+        ops.bn1d_gelu_drop_bwd_apply(hh, d_g, sc, sh, mu, inv, mask, drop_p, sums, d_hh)
+        ops.bn_param_grads(sums, G[prefix + "mlp.1.weight"], G[prefix + "mlp.1.bias"], 1)
+        ops.linear_bwd_weight(d_hh, x, G[prefix + "mlp.0.weight"], G[prefix + "mlp.0.bias"])
+        ops.linear_bwd_data(d_hh, S[prefix + "mlp.0.weight"], d_x)
+
+    def _encode(self, w, role, P, bns, x_img, x_aud, N, B, n_fusion, fmask):
+        """Encoder forward for N = n_views*B samples; fusion only over the first n_fusion rows."""
+        if self.kind == "multi_central":
+            E = self.E
+            cat = w[f"{role}.cat"]
+            pi = self._conv_stack(w, role, "img", self.img_layers, x_img, N, B, P, bns)
+            ops.linear_fwd(pi.view(N, 1600), P["enc.image_encoder.1.weight"], P["enc.image_encoder.1.bias"], cat[:, :E])
+            pa = self._conv_stack(w, role, "aud", self.aud_layers, x_aud, N, B, P, bns)
+            ops.linear_fwd(pa.view(N, 3136), P["enc.audio_encoder.1.weight"], P["enc.audio_encoder.1.bias"], cat[:, E:])
+            h1, feat = w[f"{role}.h1"], w[f"{role}.feat"]
+            ops.linear_fwd(cat[:n_fusion], P["enc.fusion.0.weight"], P["enc.fusion.0.bias"], h1, act=2, mask=fmask, drop_p=self.fusion_dropout)
+            ops.linear_fwd(h1, P["enc.fusion.3.weight"], P["enc.fusion.3.bias"], feat)
+            return feat
+        pi = self._conv_stack(w, role, "img", self.img_layers, x_img, N, B, P, bns)      # [N,128,3,3]
+        ops.avgpool_fwd(pi, w[f"{role}.pool"])
+        ops.linear_fwd(w[f"{role}.pool"], P["enc.encoder.14.weight"], P["enc.encoder.14.bias"], w[f"{role}.e14"])
+        ops.linear_fwd(w[f"{role}.e14"], P["enc.projection.0.weight"], P["enc.projection.0.bias"], w[f"{role}.feat"])
+        return w[f"{role}.feat"]
+
+    def _conv_stack_bwd(self, w, mod, layers, x, d_top, N, B):
+        """Backward through a conv stack; d_top = gradient w.r.t. the last pooled activation (any shape, N*C*h*w)."""
+        S, G = self.S, self.G
+        d_p = d_top
+        for li in range(len(layers) - 1, -1, -1):
+            conv, bn, ci, co, hw, k, pad = layers[li]
+            z = w[f"s.{mod}.z{li}"]
+            sums = w[f"s.{mod}.sums{li}"]
+            sums.zero_()
+            sc, sh, mu, inv = (w[f"s.{mod}.{n}{li}"] for n in ("scale", "shift", "mean", "invstd"))
+            dz = w["dz"][:z.numel()].view_as(z)
+            ops.bn_relu_pool_bwd_reduce(z, d_p, sc, sh, mu, inv, sums, B)
+            ops.bn_relu_pool_bwd_apply(z, d_p, sc, sh, mu, inv, sums, dz, B)
+            ops.bn_param_grads(sums, G["enc." + bn + ".weight"], G["enc." + bn + ".bias"], N // B)
+            xin = x if li == 0 else w[f"s.{mod}.p{li - 1}"]
+            ops.conv_bwd_weight(xin.view(N, ci, hw, hw), dz, G["enc." + conv + ".weight"], G["enc." + conv + ".bias"], w["wg_work"], pad)
+            if li > 0:
+                nxt = w["dp_a"] if d_p.data_ptr() != w["dp_a"].data_ptr() else w["dp_b"]
+                d_in = nxt[:N * ci * hw * hw].view(N, ci, hw, hw)
+                ops.conv_bwd_data(dz, S["enc." + conv + ".weight"], d_in, pad)
+                d_p = d_in
+
+    # ------------------------------------------------------------------------------------------------------
+    # the step
+    # ------------------------------------------------------------------------------------------------------
+    def forward_backward(self, x_img, x_aud, masks=None, raw=None, labels=None):
+        """Student + teacher forward, losses, centre EMA and the full backward for already-augmented views.
+
+        x_img [V,B,28,28] (and x_aud [V,B,112,112]) view-major, global views first; masks (optional, parity tests):
+        dict of uint8 keep-masks 'student_fusion' [V*B,E], 'teacher_fusion' [Vg*B,E], 'student_head' [V*B,512];
+        raw = (image [B,28,28], audio [B,112,112]) fp32 for the non-default modes; labels int64 [B].
+        Leaves the gradients in self.grad (all-reduced when data parallel) and returns the loss tensor [4] =
+        (dino, aux, cosine, total) on the device."""
+        V, Vg, E, O, P = self.V, self.Vg, self.E, self.O, self.P
+        B = x_img.shape[1]
+        w = self._workspace(B)
+        Ns, Nt, Nv = w["Ns"], w["Nt"], V * B
+        S, T, G = self.S, self.T, self.G
+        multi = self.kind == "multi_central"
+        # ---- inputs into the (V[+1])*B batch buffers ----
+        xi = w["x_img"]
+        if x_img.data_ptr() != xi.data_ptr():
+            xi[:Nv].copy_(x_img.reshape(Nv, 1, 28, 28))
+        xa = None
+        if multi:
+            xa = w["x_aud"]
+            if x_aud.data_ptr() != xa.data_ptr():
+                xa[:Nv].copy_(x_aud.reshape(Nv, 1, 112, 112))
+        if self.mode != "default":
+            xi[Nv:].copy_(raw[0].reshape(B, 1, 28, 28))
+            xa[Nv:].copy_(raw[1].reshape(B, 1, 112, 112))
+        # ---- dropout masks ----
+        if masks is not None:
+            if multi:
+                w["s.fmask"].copy_(masks["student_fusion"].reshape(Nv, E))
+                w["t.fmask"].copy_(masks["teacher_fusion"].reshape(Nt, E))
+            w["s.hmask"].copy_(masks["student_head"].reshape(Nv, 512))
+        else:
+            base = self.rng_step * 4
+            if multi:
+                ops.dropout_mask(w["s.fmask"], self.fusion_dropout, self.seed + 1, base)
+                ops.dropout_mask(w["t.fmask"], self.fusion_dropout, self.seed + 1, base + 1)
+            if self.dropout > 0:
+                ops.dropout_mask(w["s.hmask"], self.dropout, self.seed + 1, base + 2)
+        # ---- forward ----
+        feat_s = self._encode(w, "s", S, self.bn_s, xi, xa, Ns, B, Nv, w.get("s.fmask"))
+        feat_t = self._encode(w, "t", T, self.bn_t, xi[:Nt], xa[:Nt] if multi else None, Nt, B, Nt, w.get("t.fmask"))
+        self._head_fwd(w, "s", "head.", S, self.bn_s["head.mlp.1"], feat_s, w["s.proj"], w["s.hh"], w["s.g"], w["s.hmask"], self.dropout)
+        self._head_fwd(w, "t", "head.", T, self.bn_t["head.mlp.1"], feat_t, w["t.proj"], w["t.hh"], w["t.g"], None, 0.0)
+        # ---- DINO loss (fwd + bwd) and centre ----
+        s_out, t_out = w["s.proj"].view(V, B, P), w["t.proj"].view(Vg, B, P)
+        variant = 0 if multi else 1
+        if variant == 1:
+            ops.teacher_norm_colmean(t_out, self.center, w["t_colmean"])
+        ops.dino_loss_fwd_bwd(s_out, t_out, self.center, self.tau_s, self.tau_t, w["d.proj"].view(V, B, P), w["part_loss"], w["part_colsum"],
+                              variant=variant, t_colmean=w["t_colmean"] if variant == 1 else None)
+        loss = w["loss"]
+        loss.zero_()
+        if self.world > 1:
+            # data parallel: centre = EMA of the mean over ALL ranks' teacher rows
+            ops.center_update(None, w["part_colsum"], w["part_loss"], Vg * B, self.center_momentum, loss[0:1], colsum_out=w["colsum"][:P])
+            torch.distributed.all_reduce(w["colsum"][:P], group=self.pg)
+            ops.center_apply(self.center, w["colsum"][:P], Vg * B * self.world, self.center_momentum)
+        else:
+            ops.center_update(self.center, w["part_colsum"], w["part_loss"], Vg * B, self.center_momentum, loss[0:1])
+        # ---- auxiliary passes ----
+        d_feat = w["d.feat"]
+        if self.mode != "default":
+            cat = w["s.cat"]
+            outs = {}
+            for m, sl in (("aux_image", slice(0, E)), ("aux_audio", slice(E, 2 * E))):
+                self._head_fwd(w, m, m + ".", S, self.bn_s[f"{m}.mlp.1"], cat[Nv:, sl], w[f"{m}.out"], w[f"{m}.hh"], w[f"{m}.g"], None, 0.0)
+                outs[m] = w[f"{m}.out"]
+            if self.mode == "semi_supervised":
+                ops.ce_fwd_bwd(outs["aux_image"], labels, w["aux_image.d.out"], loss[1:2], grad_scale=self.alpha)
+                ops.ce_fwd_bwd(outs["aux_audio"], labels, w["aux_audio.d.out"], loss[2:3], grad_scale=self.alpha)
+                loss[1:2].add_(loss[2:3])
+                loss[2:3].zero_()
+            elif self.mode == "infonce":
+                ops.infonce_fwd_bwd(outs["aux_image"], outs["aux_audio"], w["aux_image.d.out"], w["aux_audio.d.out"], loss[1:2],
+                                    w["infonce_work"], grad_scale=self.alpha)
+            else:
+                ops.mse_align_fwd_bwd(outs["aux_image"], outs["aux_audio"], w["aux_image.d.out"], w["aux_audio.d.out"], loss[1:2],
+                                      grad_scale=self.alpha)
+        # ---- backward: head -> fusion -> encoders ----
+        self._head_bwd(w, "s", "head.", feat_s, w["d.proj"], w["s.hh"], w["s.g"], w["d.g"], w["d.hh"], d_feat, w["s.hmask"], self.dropout)
+        if self.cosine_loss_alpha > 0:
+            ops.cosine_consistency_fwd_bwd(feat_s.view(V, B, O), w["d.emb"].view(V, B, O), loss[2:3], grad_scale=self.cosine_loss_alpha)
+            d_feat.add_(w["d.emb"])
+        if multi:
+            d_cat, d_h1 = w["d.cat"], w["d.h1"]
+            ops.linear_bwd_weight(d_feat, w["s.h1"], G["enc.fusion.3.weight"], G["enc.fusion.3.bias"])
+            ops.linear_bwd_data(d_feat, S["enc.fusion.3.weight"], d_h1)
+            ops.act_bwd(d_h1, w["s.h1"], self.fusion_dropout)
+            ops.linear_bwd_weight(d_h1, w["s.cat"][:Nv], G["enc.fusion.0.weight"], G["enc.fusion.0.bias"])
+            ops.linear_bwd_data(d_h1, S["enc.fusion.0.weight"], d_cat[:Nv])
+            if self.mode != "default":
+                for m, sl in (("aux_image", slice(0, E)), ("aux_audio", slice(E, 2 * E))):
+                    self._head_bwd(w, m, m + ".", w["s.cat"][Nv:, sl], w[f"{m}.d.out"], w[f"{m}.hh"], w[f"{m}.g"], w[f"{m}.d.g"],
+                                   w[f"{m}.d.hh"], d_cat[Nv:, sl], None, 0.0)
+            for mod, layers, sl, nflat, lin, x in (("img", self.img_layers, slice(0, E), 1600, "enc.image_encoder.1", xi),
+                                                   ("aud", self.aud_layers, slice(E, 2 * E), 3136, "enc.audio_encoder.1", xa)):
+                p_last = w[f"s.{mod}.p{len(layers) - 1}"].view(Ns, nflat)
+                ops.linear_bwd_weight(d_cat[:, sl], p_last, G[lin + ".weight"], G[lin + ".bias"])
+                d_p = w["dp_a"][:Ns * nflat].view(Ns, nflat)
+                ops.linear_bwd_data(d_cat[:, sl], S[lin + ".weight"], d_p)
+                self._conv_stack_bwd(w, mod, layers, x, d_p, Ns, B)
+        else:
+            ops.linear_bwd_weight(d_feat, w["s.e14"], G["enc.projection.0.weight"], G["enc.projection.0.bias"])
+            ops.linear_bwd_data(d_feat, S["enc.projection.0.weight"], w["d.e14"])
+            ops.linear_bwd_weight(w["d.e14"], w["s.pool"], G["enc.encoder.14.weight"], G["enc.encoder.14.bias"])
+            ops.linear_bwd_data(w["d.e14"], S["enc.encoder.14.weight"], w["d.pool"])
+            d_p = w["dp_a"][:Ns * 128 * 9].view(Ns, 128, 3, 3)
+            ops.avgpool_bwd(w["d.pool"], d_p)
+            self._conv_stack_bwd(w, "img", self.img_layers, xi, d_p, Ns, B)
+        loss[3:4].copy_(loss[0:1] + loss[1:2] + loss[2:3])
+        if self.world > 1:
+            self.allreduce_gradients()
+        return loss
+
+    def allreduce_gradients(self):
+        """Data parallel exchange: ONE NCCL all-reduce of the trainable gradient prefix (+ one for the mode heads);
+        the 1/world average is folded into Adam's grad_scale."""
+        torch.distributed.all_reduce(self.grad[:self.n_trainable_prefix], group=self.pg)
+        if self.aux_range is not None:
+            lo, hi = self.aux_range
+            torch.distributed.all_reduce(self.grad[lo:hi], group=self.pg)
+
+    def update_teacher(self):
+        """Teacher EMA over the whole common arena prefix: one kernel (models/dino.py:635-646)."""
+        ops.ema_flat(self.teacher.flat[:self.n_ema], self.student.flat[:self.n_ema], self.momentum)
+
+    def optimizer_step(self, grad_scale=None):
+        """Adam (lr, weight_decay; models/dino.py:953-962) over the parameters that received gradients."""
+        self.step_count += 1
+        gs = (1.0 / self.world) if grad_scale is None else grad_scale
+        n = self.n_trainable_prefix
+        ops.adam_flat(self.student.flat[:n], self.grad[:n], self.exp_avg[:n], self.exp_avg_sq[:n], self.step_count, self.lr,
+                      weight_decay=self.weight_decay, grad_scale=gs)
+        if self.aux_range is not None:
+            lo, hi = self.aux_range
+            ops.adam_flat(self.student.flat[lo:hi], self.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.step_count,
+                          self.lr, weight_decay=self.weight_decay, grad_scale=gs)
+
+    def train_step_views(self, x_img, x_aud, masks=None, raw=None, labels=None):
+        """Reference step order on given views: forward/loss/backward, EMA (before the optimizer, dino.py:871), Adam."""
+        loss = self.forward_backward(x_img, x_aud, masks=masks, raw=raw, labels=labels)
+        self.update_teacher()
+        self.optimizer_step()
+        self.rng_step += 1
+        return loss
+
+    def train_step(self, images, audios=None, labels=None):
+        """Whole step from a raw device batch: images [B,28,28] fp32 in [0,1] or uint8; audios [B,112,112] uint8 (or fp32);
+        labels int64 [B] (semi_supervised).  Returns the device loss tensor [4] (dino, aux, cosine, total)."""
+        xi, xa = self.augment(images, audios)
+        raw = None
+        if self.mode != "default":
+            img_f = images.float() / 255.0 if images.dtype == torch.uint8 else images
+            aud_f = audios.float() / 255.0 if audios.dtype == torch.uint8 else audios
+            raw = (img_f, aud_f)
+        return self.train_step_views(xi, xa, raw=raw, labels=labels)
