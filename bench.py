@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the DINO training step (BASELINE.json metric: DINO train samples/s + roofline fraction, next to the
+host-CPU reference path).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+Workload (config.workload): BASELINE.json configs[1] -- multimodal central DINO (CentralMultiModalEncoder, image 28x28 +
+spectrogram 112x112, 2 global + 4 local views, tuned YAML augmentations, E=O=256, P=128), default training mode, synthetic
+AVMNIST-shaped data, per-GPU batch --batch (weak scaling).  One step = augmentation (device-sampled) + student/teacher
+forward + fused DINO loss + centre EMA + teacher EMA + backward + gradient all-reduce (N > 1) + Adam.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "DINO train samples/sec"
+UNIT = "samples/s"
+WORKLOAD = "multi_central DINO step (2 global + 4 local views, img 28x28 + spec 112x112, E=O=256, P=128), default mode"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "tflops": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback"}
+
+
+def augment_values():
+    import yaml
+    from multimodal_ssl_avmnist_b200 import augment as A
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "multimodal_ssl_avmnist_b200", "AVMNIST_Experiments", "configs", "config_multimodal_dino.yaml")))
+    return A.values_from_config(cfg)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc, self.path = None, None
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                                          str(gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference(batch, steps, warmup, cores, with_aug=True):
+    """The reference's CPU path for this workload (oracle port): torchvision-composed augmentation in `cores` worker
+    processes + the fp32 torch-CPU step (forward, loss, EMA, backward, Adam) with `cores` intra-op threads.
+    Returns (samples/s, ms per step, description)."""
+    import torch
+    from oracle import augment_tv as TV
+    from oracle import dino_ref as R
+    from oracle.fixtures import make_masks, synth_views, views_to_vb
+    torch.set_num_threads(cores)
+    st = R.CentralDinoState(seed=1, mode="default")
+    img, aud = views_to_vb(*synth_views(batch, seed=1))
+    masks = make_masks(seed=2, V=6, Vg=2, B=batch, E=256, hidden=512)
+    for _ in range(warmup):
+        R.central_dino_step(st, img, aud, masks)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        R.central_dino_step(st, img, aud, masks)
+    step_s = (time.perf_counter() - t0) / steps
+    step_rate = batch / step_s
+    aug_rate = None
+    if with_aug:
+        per_worker = max(2, min(8, batch // cores))
+        aug_rate = TV.time_augmentation(per_worker, cores, augment_values())
+    rate = min(step_rate, aug_rate) if aug_rate else step_rate
+    desc = (f"{steps} steps of B={batch} (fwd+loss+EMA+bwd+Adam, fp32 torch CPU, {cores} threads): {step_rate:.1f} samples/s; "
+            + (f"augmentation (torchvision chains, {cores} worker processes): {aug_rate:.1f} samples/s; value = min of the two" if aug_rate
+               else "augmentation not timed"))
+    return rate, 1e3 * batch / rate, desc
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cores = os.cpu_count() or 1
+    # size the per-step sample so that the whole run stays within a couple of minutes
+    import torch
+    torch.set_num_threads(cores)
+    t0 = time.perf_counter()
+    cpu_reference(8, 1, 1, cores, with_aug=False)
+    t8 = (time.perf_counter() - t0) / 2
+    budget = 100.0 / max(1, args.steps + args.warmup)
+    batch = int(max(8, min(256, 8 * budget / max(t8, 1e-3)))) // 8 * 8
+    rate, ms, desc = cpu_reference(batch, args.steps, args.warmup, cores)
+    line = {"metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_step_batch": batch, "inputs": "host"}, "impl": "reference",
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def op_cost(name, meta):
+    """Algorithmic (flops, bytes) of one op launch from the shapes of its first tensor arguments."""
+    import math
+
+    def numel(s):
+        return math.prod(s) if s else 0
+    if name in ("conv_fwd", "conv_bwd_data", "conv_bwd_weight") and len(meta) >= 2:
+        if name == "conv_fwd":
+            x, w = meta[0], meta[1]
+            N, Cin, H, W = x
+            Cout, _, K, _ = w
+            z = meta[3] if len(meta) > 3 else (N, Cout, H, W)
+            Ho, Wo = z[2], z[3]
+        elif name == "conv_bwd_data":
+            dz, w, dx = meta[0], meta[1], meta[2]
+            N, Cout, Ho, Wo = dz
+            _, Cin, K, _ = w
+        else:
+            x, dz, dw = meta[0], meta[1], meta[2]
+            N, Cin, H, W = x
+            _, Cout, Ho, Wo = dz
+            K = dw[2]
+        return 2.0 * N * Cout * Ho * Wo * Cin * K * K, 0.0
+    if name == "linear_fwd" and len(meta) >= 2:
+        (M, K), (N, _) = meta[0], meta[1]
+        return 2.0 * M * N * K, 0.0
+    if name == "linear_bwd_data" and len(meta) >= 2:
+        (M, N), (_, K) = meta[0], meta[1]
+        return 2.0 * M * N * K, 0.0
+    if name == "linear_bwd_weight" and len(meta) >= 2:
+        (M, N), (_, K) = meta[0], meta[1]
+        return 2.0 * M * N * K, 0.0
+    if name == "aug_apply_audio":        # src u8 [B,112,112] read once (+L2 re-reads) + [V,B,112,112] fp32 written
+        out = meta[-1] if len(meta[-1]) == 4 else meta[0]
+        return 0.0, numel(meta[0]) * 1.0 + numel(out) * 4.0
+    if name == "aug_apply_image":
+        return 0.0, numel(meta[0]) * 4.0 + numel(meta[-1]) * 4.0
+    if name == "ema_flat":
+        return 0.0, 12.0 * numel(meta[0])
+    if name == "adam_flat":
+        return 0.0, 28.0 * numel(meta[0])
+    if name == "dino_loss_fwd_bwd":
+        return 0.0, 4.0 * (2 * numel(meta[0]) + numel(meta[1]))
+    if name == "bn_relu_pool_fwd":
+        return 0.0, 4.0 * numel(meta[0]) * 1.25
+    if name == "bn_relu_pool_bwd_reduce":
+        return 0.0, 4.0 * numel(meta[0]) * 1.25
+    if name == "bn_relu_pool_bwd_apply":
+        return 0.0, 4.0 * numel(meta[0]) * 2.25
+    return 0.0, 0.0
+
+
+def profile_ops(engine, images, audios, steps=2):
+    """Per-op CUDA-event timing of `steps` whole steps (events on the launching stream)."""
+    import torch
+    from multimodal_ssl_avmnist_b200 import ops
+    rec = ops.start_profile()
+    for _ in range(steps):
+        engine.train_step(images, audios)
+    torch.cuda.synchronize()
+    ops.stop_profile()
+    agg = {}
+    for name, a, b, meta in rec:
+        ms = a.elapsed_time(b)
+        key = (name, meta)
+        d = agg.setdefault(key, {"ms": 0.0, "calls": 0})
+        d["ms"] += ms
+        d["calls"] += 1
+    rows = []
+    for (name, meta), d in agg.items():
+        fl, by = op_cost(name, meta)
+        per = d["ms"] / d["calls"]
+        rows.append({"op": name, "shapes": [list(s) for s in meta], "calls_per_step": d["calls"] / steps, "ms_per_call": per,
+                     "ms_per_step": d["ms"] / steps, "flops": fl, "bytes": by,
+                     "tflops": fl / per / 1e9 if per > 0 else 0.0, "gbs": by / per / 1e6 if per > 0 else 0.0})
+    rows.sort(key=lambda r: -r["ms_per_step"])
+    return rows
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from multimodal_ssl_avmnist_b200 import ops
+    from multimodal_ssl_avmnist_b200.engine import DinoStepEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    eng = DinoStepEngine(kind="multi_central", mode="default", augment_values=augment_values(), seed=1 + rank, device=dev)
+    g = torch.Generator().manual_seed(1 + rank)
+    img_h = torch.rand(B, 28, 28, generator=g).pin_memory()
+    aud_h = torch.randint(0, 256, (B, 112, 112), generator=g, dtype=torch.uint8).pin_memory()
+    img_d, aud_d = img_h.to(dev), aud_h.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also sizes the workspaces) ----
+    for _ in range(max(args.warmup, 3)):
+        eng.train_step(img_d, aud_d)
+    barrier()
+    # ---- timed region 1: inputs resident in HBM ----
+    clocks = ClockSampler(local) if rank == 0 else None
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = eng.train_step(img_d, aud_d)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (ops.launch_count() - l0) // args.steps
+    # ---- timed region 2: end to end through the host-facing call (pinned host buffers in, loss out) ----
+    for _ in range(2):
+        eng.train_step_host(img_h, aud_h)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    last = None
+    for _ in range(args.steps):
+        last = eng.train_step_host(img_h, aud_h)
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3) / args.steps
+    clk = clocks.stop() if clocks is not None else None
+    t = torch.tensor([ms, ms_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    rows = profile_ops(eng, img_d, aud_d, steps=2)       # every rank runs it (the step contains collectives when N > 1)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    step_ms_prof = sum(r["ms_per_step"] for r in rows)
+    conv_rows = [r for r in rows if r["flops"] > 0 and r["op"].startswith("conv")]
+    top = max(conv_rows, key=lambda r: r["ms_per_step"]) if conv_rows else rows[0]
+    conv_ms = sum(r["ms_per_step"] for r in conv_rows)
+    conv_fl = sum(r["flops"] * r["calls_per_step"] for r in conv_rows)
+    roof = {"bound": "tensor", "kernel": f"{top['op']} {top['shapes'][:2]}", "achieved": top["tflops"], "peak": peaks["tflops"],
+            "unit": "TFLOP/s", "frac": top["tflops"] / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
+            "share_of_step": top["ms_per_step"] / step_ms_prof,
+            "note": "FP32 SIMT direct convolution in this revision (FP32 SIMT peak ~72 TFLOP/s); all conv kernels together: "
+                    f"{conv_fl / conv_ms / 1e9:.1f} TFLOP/s over {100 * conv_ms / step_ms_prof:.0f}% of the step"}
+    hbm = {}
+    for r in rows:
+        if r["bytes"] > 0 and r["op"] in ("aug_apply_audio", "aug_apply_image", "ema_flat", "adam_flat", "dino_loss_fwd_bwd",
+                                            "bn_relu_pool_fwd", "bn_relu_pool_bwd_apply"):
+            k = r["op"]
+            if k not in hbm or r["ms_per_step"] > hbm[k]["_ms"]:
+                hbm[k] = {"gbs": round(r["gbs"], 1), "frac": round(r["gbs"] / peaks["hbm_gbs"], 3), "us": round(1e3 * r["ms_per_call"], 1),
+                          "_ms": r["ms_per_step"]}
+    for v in hbm.values():
+        v.pop("_ms")
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, f"bench_ops_n{world}_b{B}.json"), "w") as f:
+            json.dump({"ms_per_step": ms, "profiled_ms_per_step": step_ms_prof, "ops": rows}, f, indent=1)
+    except Exception:
+        pass
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        rate, _, desc = cpu_reference(64, 2, 1, cores)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+    h2d = img_h.numel() * 4 + aud_h.numel()
+    line = {"metric": METRIC, "value": B * world / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "per-step working set (activations) is several GB, far larger than the 126 MB L2"},
+            "e2e": {"value": B * world / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
+                    "ms_per_step": ms_e2e, "last_loss": last},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "hbm_kernels": hbm, "cpu_baseline": cpu, "impl": "ours"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -596,3 +596,22 @@ class DinoStepEngine:
             aud_f = audios.float() / 255.0 if audios.dtype == torch.uint8 else audios
             raw = (img_f, aud_f)
         return self.train_step_views(xi, xa, raw=raw, labels=labels)
+
+    def train_step_host(self, images_host, audios_host=None, labels_host=None):
+        """The host-facing call: raw batch in (pinned) host memory -> H2D copies -> whole step -> the total loss as a Python
+        float (D2H read).  This is what `e2e` in bench.py times."""
+        B = images_host.shape[0]
+        buf = self._ws.setdefault(("host", B, images_host.dtype, None if audios_host is None else audios_host.dtype), {})
+        if not buf:
+            buf["img"] = torch.empty(images_host.shape, dtype=images_host.dtype, device=self.device)
+            if audios_host is not None:
+                buf["aud"] = torch.empty(audios_host.shape, dtype=audios_host.dtype, device=self.device)
+            if labels_host is not None:
+                buf["lab"] = torch.empty(labels_host.shape, dtype=labels_host.dtype, device=self.device)
+        buf["img"].copy_(images_host, non_blocking=True)
+        if audios_host is not None:
+            buf["aud"].copy_(audios_host, non_blocking=True)
+        if labels_host is not None:
+            buf["lab"].copy_(labels_host, non_blocking=True)
+        loss = self.train_step(buf["img"], buf.get("aud"), buf.get("lab"))
+        return float(loss[3].item())

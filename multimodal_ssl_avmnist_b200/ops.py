@@ -289,3 +289,56 @@ def bn1d_gelu_drop_bwd_apply(h, dg, scale, shift, mean, invstd, mask, drop_p, su
     _lib.check(_lib_().b200_bn1d_gelu_drop_bwd_apply(_ptr(h, F32), _ptr(dg, F32), _ptr(scale, F32), _ptr(shift, F32), _ptr(mean, F32),
                                                      _ptr(invstd, F32), _ptr(mask, U8), drop_p, _ptr(sums, F64), _ptr(dh, F32), M, Cc,
                                                      _stream()), "bn1d_gelu_drop_bwd_apply")
+
+
+# ---- launch accounting and optional per-op timing ------------------------------------------------------------
+# Every wrapper above issues a fixed number of kernel launches; the table lists the ones that issue more than one.
+_LAUNCHES = {"conv_bwd_weight": 3, "linear_bwd_weight": 2, "infonce_fwd_bwd": 9}
+_NOT_KERNELS = {"dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats"}
+LAUNCH_COUNT = 0
+_PROFILE = None          # None, or a list receiving (name, start_event, end_event, meta)
+
+
+def launch_count():
+    return LAUNCH_COUNT
+
+
+def start_profile():
+    """Record a CUDA-event pair around every op call (events are recorded on the current stream, the stream the kernels
+    are launched on).  Returns the list that collects (name, start, end, meta) until stop_profile()."""
+    global _PROFILE
+    _PROFILE = []
+    return _PROFILE
+
+
+def stop_profile():
+    global _PROFILE
+    rec, _PROFILE = _PROFILE, None
+    return rec
+
+
+def _wrap(name, fn):
+    n_launch = _LAUNCHES.get(name, 1)
+
+    def wrapped(*args, **kwargs):
+        global LAUNCH_COUNT
+        LAUNCH_COUNT += n_launch
+        if _PROFILE is None:
+            return fn(*args, **kwargs)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn(*args, **kwargs)
+        b.record()
+        meta = tuple(tuple(t.shape) for t in args[:4] if isinstance(t, torch.Tensor))
+        _PROFILE.append((name, a, b, meta))
+        return out
+
+    wrapped.__name__ = name
+    wrapped.__doc__ = fn.__doc__
+    return wrapped
+
+
+for _name, _fn in list(globals().items()):
+    if callable(_fn) and not _name.startswith("_") and _name not in _NOT_KERNELS and getattr(_fn, "__module__", None) == __name__ \
+            and _name not in ("launch_count", "start_profile", "stop_profile", "MultiTensorTable"):
+        globals()[_name] = _wrap(_name, _fn)
