@@ -169,15 +169,17 @@ int b200_avgpool_bwd(const float* dout, float* dx, int N, int C, int HW, void* s
  *   b200_linear_fwd      : y[M,N] = act(x[M,K] w[N,K]^T + bias); act: 0 none, 1 relu, 2 relu + dropout keep-mask
  *                          (mask uint8 [M,N], scaled by 1/(1-p)).  ldx/ldy = row strides in floats (concat support).
  *   b200_linear_bwd_data : dx[M,K] = dy[M,N] w[N,K]            (act backward applied to dy by the caller kernels)
- *   b200_linear_bwd_weight: dw[N,K] (+)= dy^T x, db[N] (+)= column sums of dy
+ *   b200_linear_bwd_weight: dw[N,K] (+)= dy^T x, db[N] (+)= column sums of dy; the reduction over M is split across
+ *                          CTAs through `work` (float[b200_linear_bwd_weight_work_floats]) and summed in a fixed order
  *   b200_act_bwd         : dy <- dy * (y > 0) [* mask/(1-p)]  in place (relu / relu+dropout backward)
  * ---------------------------------------------------------------------------------------------------------- */
 int b200_linear_fwd(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t ldy, int M,
                     int N, int K, int act, const uint8_t* mask, float drop_p, void* stream);
 int b200_linear_bwd_data(const float* dy, int64_t lddy, const float* w, float* dx, int64_t lddx, int M, int N,
                          int K, void* stream);
-int b200_linear_bwd_weight(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dw, float* db, int M,
-                           int N, int K, int accumulate, void* stream);
+int64_t b200_linear_bwd_weight_work_floats(int M, int N, int K);
+int b200_linear_bwd_weight(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dw, float* db, float* work,
+                           int M, int N, int K, int accumulate, void* stream);
 int b200_act_bwd(float* dy, const float* y, const uint8_t* mask, float drop_p, int64_t n, void* stream);
 /* BatchNorm1d statistics over the rows of h[M,C] (double sums, zeroed by the caller): stats[c] = {sum, sum^2} */
 int b200_colstats(const float* h, double* stats, int M, int C, void* stream);

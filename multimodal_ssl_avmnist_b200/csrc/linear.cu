@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(GT) gemm_kernel(const float* __restrict__ A, i
             float v = acc[i][j];
             float* cp = C + (int64_t)gm * ldc + gn;
             if (EPI == 4) {
-                atomicAdd(cp, v);
+                cp[(int64_t)blockIdx.z * M * ldc] = v;       // split-K partial: C holds [splits][M][ldc], reduced in fixed order
             } else {
                 if (EPI >= 1 && bias) v += __ldg(bias + gn);
                 if (EPI >= 2) v = fmaxf(v, 0.f);
@@ -123,6 +123,16 @@ __global__ void __launch_bounds__(GT) gemm_kernel(const float* __restrict__ A, i
                 *cp = v;
             }
         }
+    }
+}
+
+// out[i] = (accumulate ? out[i] : 0) + sum_p part[p][i], p in fixed order (deterministic split-K reduction)
+__global__ void __launch_bounds__(256) reduce_splits_kernel(const float* __restrict__ part, int n_parts, int64_t n, float* __restrict__ out,
+                                                            int accumulate) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float a = accumulate ? out[i] : 0.f;
+        for (int p = 0; p < n_parts; ++p) a += part[(int64_t)p * n + i];
+        out[i] = a;
     }
 }
 
@@ -277,25 +287,39 @@ int b200_linear_bwd_data(const float* dy, int64_t lddy, const float* w, float* d
     return launch_status("linear_bwd_data");
 }
 
-int b200_linear_bwd_weight(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dw, float* db, int M, int N, int K,
-                           int accumulate, void* stream) {
-    B200_REQUIRE(dy && x && dw && M > 0 && N > 0 && K > 0 && lddy >= N && ldx >= K, B200_E_ARG, "linear_bwd_weight: bad arguments");
-    cudaStream_t st = as_stream(stream);
-    // dw[n,k] = sum_m dy[m,n] x[m,k]:  C[N,K]; A(n, m) = dy[m*lddy + n] (n contiguous), B(k, m) = x[m*ldx + k] (k contiguous)
-    dim3 grid((K + BN - 1) / BN, (N + BM - 1) / BM, 1);
-    const int tiles = grid.x * grid.y;
+static int wgrad_splits(int M, int N, int K) {
+    const int tiles = ((K + BN - 1) / BN) * ((N + BM - 1) / BM);
     int splits = (sm_count() * 2 + tiles - 1) / tiles;
     const int max_splits = (M + 255) / 256;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
-    int kps = ((M + splits - 1) / splits + BK - 1) / BK * BK;
-    splits = (M + kps - 1) / kps;
+    const int kps = ((M + splits - 1) / splits + BK - 1) / BK * BK;
+    return (M + kps - 1) / kps;
+}
+
+int64_t b200_linear_bwd_weight_work_floats(int M, int N, int K) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    const int splits = wgrad_splits(M, N, K);
+    return (int64_t)splits * N * K;      // also covers splits == 1 with accumulate
+}
+
+int b200_linear_bwd_weight(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dw, float* db, float* work, int M, int N,
+                           int K, int accumulate, void* stream) {
+    B200_REQUIRE(dy && x && dw && M > 0 && N > 0 && K > 0 && lddy >= N && ldx >= K, B200_E_ARG, "linear_bwd_weight: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    // dw[n,k] = sum_m dy[m,n] x[m,k]:  C[N,K]; A(n, m) = dy[m*lddy + n] (n contiguous), B(k, m) = x[m*ldx + k] (k contiguous)
+    dim3 grid((K + BN - 1) / BN, (N + BM - 1) / BM, 1);
+    const int splits = wgrad_splits(M, N, K);
+    const int kps = ((M + splits - 1) / splits + BK - 1) / BK * BK;
     if (splits == 1 && !accumulate) {
         gemm_kernel<false, false, 0><<<grid, GT, 0, st>>>(dy, lddy, x, ldx, dw, K, N, K, M, M, nullptr, nullptr, 1.f);
     } else {
-        if (!accumulate) cudaMemsetAsync(dw, 0, (size_t)N * K * sizeof(float), st);
+        B200_REQUIRE(work, B200_E_ARG, "linear_bwd_weight: split-K needs the work buffer (b200_linear_bwd_weight_work_floats)");
         grid.z = splits;
-        gemm_kernel<false, false, 4><<<grid, GT, 0, st>>>(dy, lddy, x, ldx, dw, K, N, K, M, kps, nullptr, nullptr, 1.f);
+        gemm_kernel<false, false, 4><<<grid, GT, 0, st>>>(dy, lddy, x, ldx, work, K, N, K, M, kps, nullptr, nullptr, 1.f);
+        const int64_t n = (int64_t)N * K;
+        reduce_splits_kernel<<<(int)((n + 1023) / 1024 < sm_count() * 8 ? (n + 1023) / 1024 : sm_count() * 8), 256, 0, st>>>(work, splits, n, dw,
+                                                                                                                          accumulate);
     }
     int rc = launch_status("linear_bwd_weight");
     if (rc || !db) return rc;

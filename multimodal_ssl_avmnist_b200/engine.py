@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from . import augment as A
+from . import dp
 from . import ops
 
 F32 = torch.float32
@@ -138,7 +139,7 @@ class DinoStepEngine:
     def __init__(self, kind="multi_central", mode="default", encoder_output_dim=256, output_dim=256, projection_dim=128,
                  n_global_views=2, n_local_views=4, momentum=0.996, center_momentum=0.9, student_temperature=0.1,
                  teacher_temperature=0.04, learning_rate=1e-4, weight_decay=1e-6, dropout=0.3, fusion_dropout=0.3, alpha=1.0,
-                 cosine_loss_alpha=0.0, augment_values=None, seed=0, device=None, process_group=None):
+                 cosine_loss_alpha=0.0, augment_values=None, seed=0, device=None, process_group=None, data_parallel=None):
         if not torch.cuda.is_available():
             raise ops._lib.B200Error("DinoStepEngine needs a CUDA device: the hot path has no CPU fallback")
         ops._lib.load()
@@ -156,8 +157,7 @@ class DinoStepEngine:
         self.cosine_loss_alpha = cosine_loss_alpha
         self.seed = seed
         self.pg = process_group
-        self.world = torch.distributed.get_world_size(process_group) if (process_group is not None or (
-            torch.distributed.is_available() and torch.distributed.is_initialized())) else 1
+        self.world = dp.world_size(process_group) if (data_parallel is None or data_parallel) else 1
         self.step_count = 0          # optimizer steps taken (Adam bias correction)
         self.rng_step = 0            # augmentation / dropout stream position
 
@@ -180,6 +180,8 @@ class DinoStepEngine:
         self.n_ema = self.teacher.size
         self.n_trainable_prefix = self.student.range_of([n for n, _ in enc_used + head])[1]
         self.aux_range = self.student.range_of([n for n, _ in aux]) if aux else None
+        self.grad_plan = dp.GradientPlan([(0, self.n_trainable_prefix)] + ([self.aux_range] if self.aux_range else []))
+        self._grad_scale = 1.0
         self.grad = torch.zeros_like(self.student.flat)
         self.exp_avg = torch.zeros_like(self.student.flat)
         self.exp_avg_sq = torch.zeros_like(self.student.flat)
@@ -495,8 +497,8 @@ class DinoStepEngine:
         if self.world > 1:
             # data parallel: centre = EMA of the mean over ALL ranks' teacher rows
             ops.center_update(None, w["part_colsum"], w["part_loss"], Vg * B, self.center_momentum, loss[0:1], colsum_out=w["colsum"][:P])
-            torch.distributed.all_reduce(w["colsum"][:P], group=self.pg)
-            ops.center_apply(self.center, w["colsum"][:P], Vg * B * self.world, self.center_momentum)
+            rows = dp.allreduce_colsum_(w["colsum"][:P], Vg * B, self.pg)
+            ops.center_apply(self.center, w["colsum"][:P], rows, self.center_momentum)
         else:
             ops.center_update(self.center, w["part_colsum"], w["part_loss"], Vg * B, self.center_momentum, loss[0:1])
         # ---- auxiliary passes ----
@@ -557,10 +559,7 @@ class DinoStepEngine:
     def allreduce_gradients(self):
         """Data parallel exchange: ONE NCCL all-reduce of the trainable gradient prefix (+ one for the mode heads);
         the 1/world average is folded into Adam's grad_scale."""
-        torch.distributed.all_reduce(self.grad[:self.n_trainable_prefix], group=self.pg)
-        if self.aux_range is not None:
-            lo, hi = self.aux_range
-            torch.distributed.all_reduce(self.grad[lo:hi], group=self.pg)
+        self._grad_scale = self.grad_plan.allreduce_(self.grad, self.pg)
 
     def update_teacher(self):
         """Teacher EMA over the whole common arena prefix: one kernel (models/dino.py:635-646)."""
@@ -569,7 +568,7 @@ class DinoStepEngine:
     def optimizer_step(self, grad_scale=None):
         """Adam (lr, weight_decay; models/dino.py:953-962) over the parameters that received gradients."""
         self.step_count += 1
-        gs = (1.0 / self.world) if grad_scale is None else grad_scale
+        gs = self._grad_scale if grad_scale is None else grad_scale
         n = self.n_trainable_prefix
         ops.adam_flat(self.student.flat[:n], self.grad[:n], self.exp_avg[:n], self.exp_avg_sq[:n], self.step_count, self.lr,
                       weight_decay=self.weight_decay, grad_scale=gs)

@@ -253,13 +253,21 @@ def linear_bwd_data(dy, w, dx):
     _lib.check(_lib_().b200_linear_bwd_data(dyp, lddy, _ptr(w, F32), dxp, lddx, M, N, K, _stream()), "linear_bwd_data")
 
 
-def linear_bwd_weight(dy, x, dw, db, accumulate=False):
+_LINEAR_WORK = {}
+
+
+def linear_bwd_weight(dy, x, dw, db, accumulate=False, work=None):
     M, N = dy.shape
     K = x.shape[1]
     dyp, lddy = _rows(dy)
     xp, ldx = _rows(x)
-    _lib.check(_lib_().b200_linear_bwd_weight(dyp, lddy, xp, ldx, _ptr(dw, F32), _ptr(db, F32), M, N, K, 1 if accumulate else 0, _stream()),
-               "linear_bwd_weight")
+    need = _lib_().b200_linear_bwd_weight_work_floats(M, N, K)
+    if work is None and need > 0:          # one cached split-K scratch per device, grown on demand
+        work = _LINEAR_WORK.get(dy.device)
+        if work is None or work.numel() < need:
+            work = _LINEAR_WORK[dy.device] = torch.empty(need, dtype=F32, device=dy.device)
+    _lib.check(_lib_().b200_linear_bwd_weight(dyp, lddy, xp, ldx, _ptr(dw, F32), _ptr(db, F32), _ptr(work, F32), M, N, K,
+                                              1 if accumulate else 0, _stream()), "linear_bwd_weight")
 
 
 def act_bwd(dy, y, drop_p=0.0):
@@ -293,8 +301,8 @@ def bn1d_gelu_drop_bwd_apply(h, dg, scale, shift, mean, invstd, mask, drop_p, su
 
 # ---- launch accounting and optional per-op timing ------------------------------------------------------------
 # Every wrapper above issues a fixed number of kernel launches; the table lists the ones that issue more than one.
-_LAUNCHES = {"conv_bwd_weight": 3, "linear_bwd_weight": 2, "infonce_fwd_bwd": 9}
-_NOT_KERNELS = {"dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats"}
+_LAUNCHES = {"conv_bwd_weight": 3, "linear_bwd_weight": 3, "infonce_fwd_bwd": 9}
+_NOT_KERNELS = {"dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
 LAUNCH_COUNT = 0
 _PROFILE = None          # None, or a list receiving (name, start_event, end_event, meta)
 
