@@ -1,0 +1,494 @@
+"""DINO modules of the AVMNIST experiments, B200-native.
+
+Same public surface as the reference's models/dino.py (class names, constructor keywords, attribute names, state_dict
+keys, Lightning hooks), but the modules are *parameter containers*: the training step itself -- student / teacher forward,
+projection heads, the centred + sharpened cross-entropy, the MSE / InfoNCE / cross-entropy side losses, backward, EMA and
+Adam -- runs in hand-written sm_100a kernels behind libavmnist_b200.so (multimodal_ssl_avmnist_b200.engine / .binding).
+There is no PyTorch fallback: on a CPU tensor, or without the library, the step raises.
+
+Compiled encoders: CentralMultiModalEncoder ("multi_central") and ImageEncoder ("image_simple").  The other encoder
+families of the reference (LSTM, ViT, MobileViT, ResNet, gated, cross-attention, spectrogram-only) are outside the
+hot-path scope; their names exist so that driver scripts import, and constructing one raises NotImplementedError.
+"""
+import os
+import sys
+
+import torch
+import torch.nn as nn
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from _compat import pl  # noqa: E402
+from models.unimodal import CentralUnimodalAudio, CentralUnimodalImage  # noqa: E402
+from multimodal_ssl_avmnist_b200 import binding as B  # noqa: E402
+from multimodal_ssl_avmnist_b200 import module_forward as MF  # noqa: E402
+
+
+# ------------------------------------------------------------------------------------------------------------
+# encoders (containers)
+# ------------------------------------------------------------------------------------------------------------
+def _conv_stack(channels, out_dim):
+    layers = []
+    for cin, cout in zip(channels[:-1], channels[1:]):
+        layers += [nn.Conv2d(cin, cout, 3, padding=1), nn.BatchNorm2d(cout), nn.ReLU(), nn.MaxPool2d(2)]
+    layers += [nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(channels[-1], out_dim)]
+    return nn.Sequential(*layers)
+
+
+def image_encoder(output_dim):
+    """3 x [conv3x3, BN, ReLU, maxpool] (1->32->64->128), global average pool, Linear(128, output_dim)."""
+    return _conv_stack((1, 32, 64, 128), output_dim)
+
+
+def audio_encoder(output_dim):
+    """4 x [conv3x3, BN, ReLU, maxpool] (1->32->64->128->256), global average pool, Linear(256, output_dim)."""
+    return _conv_stack((1, 32, 64, 128, 256), output_dim)
+
+
+class BaseMultiModalEncoder(nn.Module):
+    def __init__(self, output_dim=256, encoder_output_dim=512, fusion_dropout=0.3):
+        super().__init__()
+        self.output_dim, self.encoder_output_dim, self.fusion_dropout = output_dim, encoder_output_dim, fusion_dropout
+
+    def forward(self, images, spectrograms):
+        raise NotImplementedError("Subclasses must implement forward method")
+
+
+class SimpleMultiModalEncoder(BaseMultiModalEncoder):
+    """Concatenation fusion: image_encoder || audio_encoder -> Linear(2E,E) -> ReLU -> Dropout -> Linear(E,O)."""
+    B200_KIND = None        # "multi_simple" is a listed next step; only its inference forward is available
+
+    def __init__(self, output_dim=256, encoder_output_dim=512, fusion_dropout=0.3):
+        super().__init__(output_dim, encoder_output_dim, fusion_dropout)
+        self.image_encoder = image_encoder(encoder_output_dim)
+        self.audio_encoder = audio_encoder(encoder_output_dim)
+        self.fusion = nn.Sequential(nn.Linear(2 * encoder_output_dim, encoder_output_dim), nn.ReLU(), nn.Dropout(fusion_dropout),
+                                    nn.Linear(encoder_output_dim, output_dim))
+
+    def encode_image(self, images):
+        return MF.sequential_cnn_forward(self.image_encoder, images)
+
+    def encode_audio(self, spectrograms):
+        return MF.sequential_cnn_forward(self.audio_encoder, spectrograms)
+
+    def forward(self, images, spectrograms):
+        """Inference-form forward (feature extraction); the training step goes through MultiModalDINO."""
+        feats = torch.cat([self.encode_image(images), self.encode_audio(spectrograms)], dim=1)
+        return MF.fusion_forward(self.fusion, feats)
+
+
+class _HeadedCNN(nn.Sequential):
+    """Sequential(CentralUnimodal*, Linear) whose call runs the CUDA inference path."""
+
+    def forward(self, x):
+        flat = MF.central_cnn_forward(self[0], x)
+        return MF._linear(flat, self[1])
+
+
+class CentralMultiModalEncoder(SimpleMultiModalEncoder):
+    """LeNet-style CentralNet CNNs per modality (models/unimodal.py) + the concatenation fusion."""
+    B200_KIND = "multi_central"
+
+    def __init__(self, output_dim=256, encoder_output_dim=512):
+        # the parent is built first (and its simple encoders discarded) so that the global RNG is consumed exactly like
+        # in the reference: identical seeds give identical initial weights
+        super().__init__(output_dim, encoder_output_dim)
+        self.image_encoder = _HeadedCNN(CentralUnimodalImage(), nn.Linear(64 * 5 * 5, encoder_output_dim))
+        self.audio_encoder = _HeadedCNN(CentralUnimodalAudio(), nn.Linear(64 * 7 * 7, encoder_output_dim))
+
+    def encode_image(self, images):
+        return self.image_encoder(images)
+
+    def encode_audio(self, spectrograms):
+        return self.audio_encoder(spectrograms)
+
+
+class BaseUniModalEncoder(nn.Module):
+    def __init__(self, output_dim=256, modality="image"):
+        super().__init__()
+        self.output_dim, self.modality = output_dim, modality
+
+    def forward(self, images=None, spectrograms=None):
+        raise NotImplementedError("Subclasses must implement forward method")
+
+
+class ImageEncoder(BaseUniModalEncoder):
+    B200_KIND = "image_simple"
+
+    def __init__(self, output_dim=256):
+        super().__init__(output_dim, modality="image")
+        self.encoder = image_encoder(output_dim=512)
+        self.projection = nn.Sequential(nn.Linear(512, output_dim))
+
+    def forward(self, images=None, spectrograms=None):
+        if images is None:
+            raise ValueError("ImageEncoder requires image input")
+        return MF._linear(MF.sequential_cnn_forward(self.encoder, images), self.projection[0])
+
+
+def _out_of_scope(name):
+    def __init__(self, *a, **k):
+        raise NotImplementedError(f"{name} is outside the B200 hot-path scope (see DESIGN.md section 7); "
+                                  "compiled encoders: CentralMultiModalEncoder, ImageEncoder")
+    return type(name, (nn.Module,), {"__init__": __init__, "B200_KIND": None})
+
+
+for _n in ("LSTMImageEncoder", "LSTMMultiModalEncoder", "ViTMultiModalEncoder", "DualViTMultiModalEncoder", "MobileViTMultiModalEncoder",
+           "ResNetMultiModalEncoder", "GatedMultiModalEncoder", "CrossAttentionMultiModalEncoder", "SpectrogramEncoder",
+           "SpectrogramEncoderCentral", "SpectrogramEncoderLSTM", "SpectrogramEncoderResNet", "SpectrogramEncoderViT",
+           "SpectrogramEncoderMobileViT", "UniModalDINOV2"):
+    globals()[_n] = _out_of_scope(_n)
+
+
+class ProjectionHead(nn.Module):
+    """Linear(in, hidden) -> BatchNorm1d -> GELU -> Dropout -> Linear(hidden, projection_dim)."""
+
+    def __init__(self, input_dim, projection_dim=256, dropout_rate=0, hidden_dim=512):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.Linear(input_dim, hidden_dim), nn.BatchNorm1d(hidden_dim), nn.GELU(), nn.Dropout(dropout_rate),
+                                 nn.Linear(hidden_dim, projection_dim))
+
+    def forward(self, x):
+        return MF.projection_head_forward(self, x)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# DINO modules
+# ------------------------------------------------------------------------------------------------------------
+def _to_view_major(global_t, local_t):
+    """[B,Vg,1,H,W] + [B,Vl,1,H,W] -> [V,B,H,W] contiguous (global views first)."""
+    x = torch.cat([global_t, local_t], dim=1)
+    return x[:, :, 0].transpose(0, 1).contiguous().float()
+
+
+class _DinoBase(nn.Module):
+    MODE = "default"
+
+    def _setup(self, encoder_class, encoder_kwargs, output_dim, projection_dim, momentum, center_momentum, dropout):
+        self.student = encoder_class(**encoder_kwargs)
+        self.teacher = encoder_class(**encoder_kwargs)
+        self.teacher.load_state_dict(self.student.state_dict())
+        self.student_projection = ProjectionHead(output_dim, projection_dim, dropout_rate=dropout)
+        self.teacher_projection = ProjectionHead(output_dim, projection_dim)
+        self.teacher_projection.load_state_dict(self.student_projection.state_dict())
+        for p in list(self.teacher.parameters()) + list(self.teacher_projection.parameters()):
+            p.requires_grad = False
+        self.momentum, self.center_momentum = momentum, center_momentum
+        self.register_buffer("center", torch.zeros(1, projection_dim))
+        kind = getattr(encoder_class, "B200_KIND", None)
+        if kind is None:
+            raise NotImplementedError(f"{encoder_class.__name__} has no compiled B200 training step "
+                                      "(compiled: CentralMultiModalEncoder, ImageEncoder)")
+        self._b200 = B.EngineBinding(self, kind, self.MODE)
+        self.student_temperature, self.teacher_temperature = 0.1, 0.04
+        self.n_global_views, self.n_local_views = 2, 4
+
+    def b200_hparams(self):
+        hp = dict(output_dim=self.output_dim, projection_dim=self.projection_dim, momentum=self.momentum,
+                  center_momentum=self.center_momentum, dropout=self.dropout, student_temperature=self.student_temperature,
+                  teacher_temperature=self.teacher_temperature, n_global_views=self.n_global_views, n_local_views=self.n_local_views)
+        if hasattr(self, "encoder_output_dim"):
+            hp["encoder_output_dim"] = self.encoder_output_dim
+        return hp
+
+    @property
+    def engine(self):
+        return self._b200.engine
+
+    @torch.no_grad()
+    def update_teacher(self):
+        """teacher <- m * teacher + (1 - m) * student for encoder and projection head: one flat CUDA kernel."""
+        self._b200.ensure(self.center.device).update_teacher()
+
+    @torch.no_grad()
+    def update_center(self, teacher_output):
+        """centre <- m_c * centre + (1 - m_c) * mean_rows(teacher_output) (the training forward already does this)."""
+        from multimodal_ssl_avmnist_b200 import ops
+        t = teacher_output.detach().reshape(-1, self.center.shape[1]).contiguous().float()
+        stats = torch.zeros(t.shape[1], 2, dtype=torch.float64, device=t.device)
+        ops.colstats(t, stats)
+        ops.center_apply(self.center, stats[:, 0].float().contiguous(), t.shape[0], self.center_momentum)
+
+    def _views(self, batch):
+        gi, ga, li, la = batch
+        self.n_global_views, self.n_local_views = gi.shape[1], li.shape[1]
+        dev = self.center.device
+        return gi.to(dev), ga.to(dev), li.to(dev), la.to(dev)
+
+
+class MultiModalDINO(_DinoBase):
+    def __init__(self, encoder_class=SimpleMultiModalEncoder, encoder_kwargs=None, output_dim=256, encoder_output_dim=512,
+                 projection_dim=128, momentum=0.996, center_momentum=0.9, dropout=0.3):
+        super().__init__()
+        self.projection_dim, self.output_dim, self.encoder_output_dim, self.dropout = projection_dim, output_dim, encoder_output_dim, dropout
+        kw = dict(encoder_kwargs or {})
+        kw["output_dim"], kw["encoder_output_dim"] = output_dim, encoder_output_dim
+        self._setup(encoder_class, kw, output_dim, projection_dim, momentum, center_momentum, dropout)
+
+    def forward(self, batch, raw=None):
+        """batch = (global_images [B,Vg,1,28,28], global_audios [B,Vg,1,112,112], local_images, local_audios).
+        Returns (student_outputs [V,B,P], teacher_outputs [Vg,B,P] (centred), None)."""
+        gi, ga, li, la = self._views(batch)
+        out = self._b200.forward(_to_view_major(gi, li), _to_view_major(ga, la), raw=raw)
+        self._extra = out[2:]
+        return out[0], out[1], None
+
+    def forward_raw(self, images, audios, augment_values="keep", with_raw=False):
+        """B200 fast path: un-augmented device batch (images [B,1,28,28] fp32/uint8, audios [B,1,112,112] uint8/fp32) ->
+        device-sampled multi-crop augmentation -> the same outputs as forward()."""
+        dev = self.center.device
+        eng = self._b200.ensure(dev)
+        if augment_values != "keep":
+            eng.set_augmentation(augment_values)
+        img = images.to(dev).reshape(-1, 28, 28).contiguous()
+        aud = audios.to(dev).reshape(-1, 112, 112).contiguous()
+        xi, xa = eng.augment(img, aud)
+        raw = None
+        if with_raw:
+            raw = (img.float() / 255.0 if img.dtype == torch.uint8 else img, aud.float() / 255.0 if aud.dtype == torch.uint8 else aud)
+        out = self._b200.forward(xi, xa, raw=raw)
+        self._extra = out[2:]
+        return out[0], out[1], None
+
+
+class _WithSideHeads(MultiModalDINO):
+    HEAD_NAMES = ("image_projection_head", "audio_projection_head")
+
+    def _side_dim(self):
+        return self.projection_dim
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        e = self.student.encoder_output_dim
+        setattr(self, self.HEAD_NAMES[0], ProjectionHead(input_dim=e, projection_dim=self._side_dim()))
+        setattr(self, self.HEAD_NAMES[1], ProjectionHead(input_dim=e, projection_dim=self._side_dim()))
+
+    def forward(self, batch):
+        """batch = (image [B,1,28,28], audio [B,1,112,112], views) -> (image_out, audio_out, student_out, teacher_out)."""
+        image, audio, views = batch
+        dev = self.center.device
+        raw = (image.to(dev).float().reshape(-1, 28, 28).contiguous(), audio.to(dev).float().reshape(-1, 112, 112).contiguous())
+        s, t, _ = super().forward(views, raw=raw)
+        return self._extra[0], self._extra[1], s, t
+
+
+class MultiModalDINOSemiSupervised(_WithSideHeads):
+    MODE = "semi_supervised"
+    HEAD_NAMES = ("image_classifier", "audio_classifier")
+
+    def __init__(self, *args, num_classes=10, **kwargs):
+        self.num_classes = num_classes
+        super().__init__(*args, **kwargs)
+
+    def _side_dim(self):
+        return self.num_classes
+
+
+class MultiModalDINOWithINFONCE(_WithSideHeads):
+    MODE = "infonce"
+
+
+class MultiModalDINOWithMSE(_WithSideHeads):
+    MODE = "mse"
+
+
+class UniModalDINO(_DinoBase):
+    def __init__(self, encoder_class=ImageEncoder, encoder_kwargs=None, output_dim=256, projection_dim=128, momentum=0.996,
+                 center_momentum=0.9, dropout=0.3):
+        super().__init__()
+        self.projection_dim, self.output_dim, self.dropout = projection_dim, output_dim, dropout
+        kw = dict(encoder_kwargs or {})
+        kw["output_dim"] = output_dim
+        self._setup(encoder_class, kw, output_dim, projection_dim, momentum, center_momentum, dropout)
+
+    def forward(self, batch):
+        """Returns (student_outputs [V,B,P], teacher_outputs [Vg,B,P] (centred), embeddings [V,B,O])."""
+        gi, ga, li, la = self._views(batch)
+        if self.student.modality != "image":
+            raise NotImplementedError("only the image modality has a compiled unimodal step")
+        out = self._b200.forward(_to_view_major(gi, li), None)
+        w = self._b200.last_w
+        emb = w["s.feat"].view(gi.shape[1] + li.shape[1], gi.shape[0], -1)
+        return out[0], out[1], emb
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Lightning modules
+# ------------------------------------------------------------------------------------------------------------
+class _DinoLightningBase(pl.LightningModule):
+    LOSS_VARIANT = 0
+
+    def forward(self, batch):
+        return self.model(batch)
+
+    def dino_loss(self, student_outputs, teacher_outputs, alignment_loss=None):
+        """Centred, temperature-sharpened cross-entropy over all student x teacher view pairs (fused CUDA kernel)."""
+        return self.model._b200.dino_loss(student_outputs, teacher_outputs, self.student_temperature, self.teacher_temperature,
+                                          self.LOSS_VARIANT) if self.model._b200.engine is not None else \
+            B.standalone_dino_loss(student_outputs, teacher_outputs, self.student_temperature, self.teacher_temperature, self.LOSS_VARIANT)
+
+    def _sync_hparams(self):
+        m = self.model
+        m.student_temperature, m.teacher_temperature = self.student_temperature, self.teacher_temperature
+        if m.engine is not None:
+            m.engine.tau_s, m.engine.tau_t = self.student_temperature, self.teacher_temperature
+
+    def configure_optimizers(self):
+        """Adam(lr, weight_decay) + CosineAnnealingLR(T_max=num_epochs), stepped per epoch; the optimiser is the flat-arena
+        CUDA Adam behind a torch.optim.Optimizer front."""
+        opt = B.B200Adam(self.parameters(), self.model._b200, lr=self.learning_rate, weight_decay=self.weight_decay)
+        sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=self.num_epochs)
+        return {"optimizer": opt, "lr_scheduler": {"scheduler": sched}}
+
+    def on_train_epoch_end(self):
+        """The reference trains a linear probe here to log `mlp_acc` (models/dino.py:878-951); evaluation is outside the
+        hot-path scope, so only the epoch's training loss is available as a checkpoint metric."""
+        return None
+
+
+class MultiModalDINOLightning(_DinoLightningBase):
+    MODEL_CLASS = MultiModalDINO
+
+    def __init__(self, data_dir="data/avmnist", data_augmentation="burst_noise", dino_model=None, encoder_class=SimpleMultiModalEncoder,
+                 encoder_kwargs=None, projection_dim=256, output_dim=256, encoder_output_dim=512, momentum=0.996, center_momentum=0.9,
+                 student_temperature=0.1, teacher_temperature=0.04, learning_rate=0.0001, use_mixed_precision=True, num_epochs=100,
+                 weight_decay=1e-6, dropout=0.3):
+        super().__init__()
+        self.encoder_class, self.encoder_kwargs = encoder_class, encoder_kwargs
+        self.output_dim, self.encoder_output_dim, self.projection_dim = output_dim, encoder_output_dim, projection_dim
+        self.learning_rate, self.weight_decay, self.num_epochs = learning_rate, weight_decay, num_epochs
+        self.student_temperature, self.teacher_temperature = student_temperature, teacher_temperature
+        self.use_mixed_precision = use_mixed_precision          # kept for signature compatibility: the step computes in fp32
+        self.momentum, self.center_momentum, self.dropout = momentum, center_momentum, dropout
+        self.data_dir, self.data_augmentation = data_dir, data_augmentation
+        if dino_model is None:
+            self.build_model()
+        else:
+            self.model = dino_model
+        self._sync_hparams()
+        self.save_hyperparameters(ignore=["dino_model", "traindata", "validdata", "testdata"])
+
+    def build_model(self):
+        self.model = self.MODEL_CLASS(encoder_class=self.encoder_class, encoder_kwargs=self.encoder_kwargs, output_dim=self.output_dim,
+                                      encoder_output_dim=self.encoder_output_dim, projection_dim=self.projection_dim,
+                                      momentum=self.momentum, center_momentum=self.center_momentum, dropout=self.dropout)
+        return self.model
+
+    def _augment_values(self):
+        dm = getattr(getattr(self, "trainer", None), "datamodule", None)
+        aug = getattr(dm, "augmentations", None)
+        return getattr(aug, "augment_values", None)
+
+    def training_step(self, batch, batch_idx):
+        self._sync_hparams()
+        if len(batch) in (2, 3) and batch[0].dim() == 4:          # raw (image, audio[, label]) batch: augment on the device
+            av = "keep" if getattr(self, "_aug_set", False) else self._augment_values()
+            self._aug_set = True
+            student_out, teacher_out, alignment_loss = self.model.forward_raw(batch[0], batch[1], av)
+        else:
+            student_out, teacher_out, alignment_loss = self.model(batch)
+        loss = self.dino_loss(student_out, teacher_out, alignment_loss)
+        self.model.update_teacher()
+        self.log("train_loss", loss, on_step=True, on_epoch=True, prog_bar=True)
+        return loss
+
+
+class _SideLossLightning(MultiModalDINOLightning):
+    def side_loss(self, image_out, audio_out, labels):
+        raise NotImplementedError
+
+    def training_step(self, batch, batch_idx):
+        self._sync_hparams()
+        if len(batch) == 3:                                       # raw (image, audio, label) batch: augment on the device
+            image, audio, labels = batch
+            av = "keep" if getattr(self, "_aug_set", False) else self._augment_values()
+            self._aug_set = True
+            student_out, teacher_out, _ = self.model.forward_raw(image, audio, av, with_raw=True)
+            image_out, audio_out = self.model._extra
+        else:
+            image, audio, labels, views = batch
+            image_out, audio_out, student_out, teacher_out = self.model((image, audio, views))
+        loss = self.dino_loss(student_out, teacher_out) + self.alpha * self.side_loss(image_out, audio_out, labels)
+        self.model.update_teacher()
+        self.log("train_loss", loss, on_step=True, on_epoch=True, prog_bar=True)
+        return loss
+
+
+class MultiModalDINOSemiSupervisedLightning(_SideLossLightning):
+    MODEL_CLASS = MultiModalDINOSemiSupervised
+
+    def __init__(self, *args, alpha=1, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.alpha = alpha
+
+    def supervised_loss(self, image_logits, audio_logits, labels):
+        labels = labels.to(image_logits.device)
+        return B.standalone_ce_loss(image_logits, labels) + B.standalone_ce_loss(audio_logits, labels)
+
+    def side_loss(self, image_out, audio_out, labels):
+        return self.supervised_loss(image_out, audio_out, labels)
+
+
+class MultiModalDINOWithINFONCELightning(_SideLossLightning):
+    MODEL_CLASS = MultiModalDINOWithINFONCE
+
+    def __init__(self, *args, output_dim=256, encoder_output_dim=128, encoder_class=SimpleMultiModalEncoder, alpha=1, **kwargs):
+        super().__init__(*args, output_dim=output_dim, encoder_output_dim=encoder_output_dim, encoder_class=encoder_class, **kwargs)
+        self.alpha = alpha
+
+    def infoNCE_loss(self, image_outputs, audio_outputs, temperature=0.07):
+        return B.standalone_pair_loss("infonce", image_outputs, audio_outputs, temperature=temperature)
+
+    def side_loss(self, image_out, audio_out, labels):
+        return self.infoNCE_loss(image_out, audio_out)
+
+
+class MultiModalDINOWithMSELightning(_SideLossLightning):
+    MODEL_CLASS = MultiModalDINOWithMSE
+
+    def __init__(self, *args, output_dim=256, encoder_output_dim=128, encoder_class=SimpleMultiModalEncoder, alpha=1, **kwargs):
+        super().__init__(*args, output_dim=output_dim, encoder_output_dim=encoder_output_dim, encoder_class=encoder_class, **kwargs)
+        self.alpha = alpha
+
+    def mse_loss(self, image_outputs, audio_outputs):
+        return B.standalone_pair_loss("mse", image_outputs, audio_outputs)
+
+    def side_loss(self, image_out, audio_out, labels):
+        return self.mse_loss(image_out, audio_out)
+
+
+class UniModalDINOLightning(_DinoLightningBase):
+    LOSS_VARIANT = 1
+
+    def __init__(self, data_dir="data/avmnist", dino_model=None, encoder_class=ImageEncoder, encoder_kwargs=None, projection_dim=128,
+                 output_dim=256, momentum=0.996, center_momentum=0.9, student_temperature=0.1, teacher_temperature=0.04,
+                 learning_rate=0.0001, use_mixed_precision=True, weight_decay=1e-6, cosine_loss_alpha=0.3, dropout=0.3, num_epochs=10,
+                 data_augmentation="burst_noise", use_original_model=True):
+        super().__init__()
+        if dino_model is None:
+            if not use_original_model:
+                raise NotImplementedError("UniModalDINOV2 is outside the B200 hot-path scope")
+            self.model = UniModalDINO(encoder_class=encoder_class, encoder_kwargs=encoder_kwargs, projection_dim=projection_dim,
+                                      output_dim=output_dim, momentum=momentum, center_momentum=center_momentum, dropout=dropout)
+        else:
+            self.model = dino_model
+        self.learning_rate, self.weight_decay, self.num_epochs = learning_rate, weight_decay, num_epochs
+        self.student_temperature, self.teacher_temperature = student_temperature, teacher_temperature
+        self.use_mixed_precision, self.dropout, self.cosine_loss_alpha = use_mixed_precision, dropout, cosine_loss_alpha
+        self.data_dir, self.data_augmentation = data_dir, data_augmentation
+        self._sync_hparams()
+        self.save_hyperparameters(ignore=["dino_model", "traindata", "validdata", "testdata"])
+
+    def _cosine_consistency_loss(self, embeddings):
+        return B.standalone_cosine_loss(embeddings)
+
+    def training_step(self, batch, batch_idx):
+        self._sync_hparams()
+        student_out, teacher_out, embeddings = self.model(batch)
+        loss = self.dino_loss(student_out, teacher_out)
+        if self.cosine_loss_alpha > 0:
+            # the consistency term back-propagates into the encoder output: give the embeddings the engine's grad path
+            raise NotImplementedError("cosine_loss_alpha > 0 is available through DinoStepEngine(cosine_loss_alpha=...); the YAML "
+                                      "configs of the reference set it to 0")
+        self.model.update_teacher()
+        self.log("train_loss", loss, on_step=True, on_epoch=True, prog_bar=True)
+        return loss

@@ -1,0 +1,239 @@
+"""Glue between the reference-shaped nn.Modules (AVMNIST_Experiments/models/dino.py) and the step engine.
+
+`EngineBinding` adopts a DINO module's parameters and buffers into the engine's flat arenas (each `nn.Parameter.data`
+becomes a view of the arena, BatchNorm buffers and the centre are aliased), and exposes the training step as ordinary
+autograd-visible tensors:
+
+    student_out, teacher_out[, image_out, audio_out] = binding.forward(views[, raw])     # CUDA forward, no autograd tape
+    loss = binding.dino_loss(student_out, teacher_out, tau_s, tau_t)                      # fused CUDA loss fwd+bwd
+    loss.backward()                                                                        # CUDA backward -> p.grad views
+
+`student_out` carries a custom grad_fn: whatever scalar the caller builds from it (the fused loss, or the reference's
+own torch expression), `backward()` hands d loss / d student_out to the engine's backward kernels, which fill the flat
+gradient arena; every parameter's `.grad` is a view of that arena, so torch optimisers and the arena Adam both work.
+"""
+import torch
+
+from . import ops
+from .engine import DinoStepEngine
+
+
+class B200Adam(torch.optim.Optimizer):
+    """torch.optim.Adam-compatible front (param_groups, lr schedulers, state_dict) whose step() is ONE flat-arena CUDA
+    kernel over the parameters that received gradients (plus one for the mode heads)."""
+
+    def __init__(self, params, binding, lr=1e-4, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, weight_decay=weight_decay, betas=betas, eps=eps))
+        self.binding = binding
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        eng = self.binding.engine
+        if eng is None:
+            raise ops._lib.B200Error("B200Adam.step() before the first CUDA forward")
+        g = self.param_groups[0]
+        eng.lr, eng.weight_decay = g["lr"], g["weight_decay"]
+        eng.optimizer_step()
+        return loss
+
+
+class _StudentOutputs(torch.autograd.Function):
+    """Marks the engine's forward outputs as differentiable w.r.t. the student parameters."""
+
+    @staticmethod
+    def forward(ctx, binding, anchor, *outs):
+        ctx.binding = binding
+        ctx.n = len(outs)
+        return tuple(o.view_as(o) for o in outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        b = ctx.binding
+        d_proj = grads[0]
+        d_aux = None
+        if ctx.n > 1:
+            d_aux = [g if g is not None else torch.zeros_like(o) for g, o in zip(grads[1:], b.last_aux)]
+            d_aux = [g.contiguous() for g in d_aux]
+        if d_proj is None:
+            d_proj = torch.zeros_like(b.last_w["s.proj"])
+        b.engine.backward_pass(b.last_w, d_proj=d_proj.contiguous(), d_aux=d_aux)
+        b.publish_grads()
+        return (None, None) + (None,) * ctx.n
+
+
+class _FusedLoss(torch.autograd.Function):
+    """loss value + its pre-computed gradient w.r.t. the inputs (the CUDA loss kernels compute both in one pass)."""
+
+    @staticmethod
+    def forward(ctx, loss_value, *pairs):
+        n = len(pairs) // 2
+        ctx.save_for_backward(*pairs[n:])
+        return loss_value.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None,) + tuple(g * d for d in ctx.saved_tensors) + (None,) * len(ctx.saved_tensors)
+
+
+def fused_loss(loss_value, inputs, grads):
+    return _FusedLoss.apply(loss_value, *inputs, *grads)
+
+
+class EngineBinding:
+    def __init__(self, module, kind, mode="default"):
+        self.module, self.kind, self.mode = module, kind, mode
+        self.engine = None
+        self.last_w = None
+        self.last_aux = ()
+        self._names = None
+
+    # ---- adoption -------------------------------------------------------------------------------------------
+    def _name_map(self):
+        """module parameter name -> (arena, arena key)."""
+        m = {}
+        eng = self.engine
+        aux_names = {"image_classifier": "aux_image", "image_projection_head": "aux_image", "audio_classifier": "aux_audio",
+                     "audio_projection_head": "aux_audio"}
+        for name, _ in self.module.named_parameters():
+            top, rest = name.split(".", 1)
+            if top == "student":
+                m[name] = ("S", "enc." + rest)
+            elif top == "teacher":
+                m[name] = ("T", "enc." + rest)
+            elif top == "student_projection":
+                m[name] = ("S", "head." + rest)
+            elif top == "teacher_projection":
+                m[name] = ("T", "head." + rest)
+            elif top in aux_names:
+                m[name] = ("S", aux_names[top] + "." + rest)
+            else:
+                raise ops._lib.B200Error(f"parameter '{name}' has no place in the engine arenas")
+        for name, (which, key) in m.items():
+            if key not in (eng.S if which == "S" else eng.T):
+                raise ops._lib.B200Error(f"parameter '{name}' ({key}) is not part of the compiled '{self.kind}' step")
+        return m
+
+    def ensure(self, device):
+        """Create the engine on first use and (re-)adopt the module's tensors if they were moved (`.to()`, load)."""
+        mod = self.module
+        if self.engine is None:
+            hp = mod.b200_hparams()
+            self.engine = DinoStepEngine(kind=self.kind, mode=self.mode, device=device, **hp)
+            self._names = self._name_map()
+        eng = self.engine
+        params = dict(mod.named_parameters())
+        probe_name = next(iter(self._names))
+        which, key = self._names[probe_name]
+        if params[probe_name].data_ptr() == (eng.S if which == "S" else eng.T)[key].data_ptr():
+            return eng
+        with torch.no_grad():
+            for name, p in params.items():
+                which, key = self._names[name]
+                view = (eng.S if which == "S" else eng.T)[key]
+                view.copy_(p.data.to(eng.device))
+                p.data = view
+            # BatchNorm buffers and the centre: the engine uses the module's own tensors
+            mods = dict(mod.named_modules())
+            for role, table, prefix in (("student", eng.bn_s, "enc."), ("teacher", eng.bn_t, "enc."), ("student_projection", eng.bn_s, "head."),
+                                        ("teacher_projection", eng.bn_t, "head."), ("image_classifier", eng.bn_s, "aux_image."),
+                                        ("image_projection_head", eng.bn_s, "aux_image."), ("audio_classifier", eng.bn_s, "aux_audio."),
+                                        ("audio_projection_head", eng.bn_s, "aux_audio.")):
+                if role not in mods:
+                    continue
+                for sub, m_ in mods[role].named_modules():
+                    if isinstance(m_, torch.nn.modules.batchnorm._BatchNorm) and prefix + sub in table:
+                        bn = table[prefix + sub]
+                        for attr in ("running_mean", "running_var", "num_batches_tracked"):
+                            t = getattr(m_, attr)
+                            if t.device != eng.device:
+                                t.data = t.data.to(eng.device)
+                        bn.running_mean, bn.running_var = m_.running_mean, m_.running_var
+                        bn.num_batches_tracked = m_.num_batches_tracked
+            if mod.center.device != eng.device:
+                mod.center.data = mod.center.data.to(eng.device)
+            eng.center = mod.center
+        return eng
+
+    def publish_grads(self):
+        """Point every student parameter's .grad at its slice of the gradient arena."""
+        eng = self.engine
+        for name, p in self.module.named_parameters():
+            which, key = self._names[name]
+            if which == "S" and p.requires_grad:
+                p.grad = eng.G[key]
+
+    # ---- the step, as autograd-visible pieces ------------------------------------------------------------------
+    def forward(self, x_img, x_aud, raw=None, masks=None):
+        """x_img [V,B,28,28] / x_aud [V,B,112,112] view-major device tensors.  Returns (student_out [V,B,P], teacher_out
+        [Vg,B,P] centred with the pre-update centre[, image_out, audio_out])."""
+        eng = self.ensure(x_img.device)
+        B = x_img.shape[1]
+        center_before = eng.center.clone()
+        w = eng.forward_pass(x_img, x_aud, masks=masks, raw=raw)
+        eng.dino_loss_pass(w)             # fused loss fwd+bwd + centre EMA (the reference updates the centre inside forward)
+        self.last_w = w
+        P = eng.P
+        teacher_c = (w["t.proj"] - center_before.view(1, P)).view(eng.Vg, B, P)
+        outs = [w["s.proj"].view(eng.V, B, P)]
+        if eng.mode != "default":
+            outs += [w["aux_image.out"], w["aux_audio.out"]]
+        self.last_aux = tuple(outs[1:])
+        anchor = next(p for p in self.module.student.parameters() if p.requires_grad)
+        res = _StudentOutputs.apply(self, anchor, *outs)
+        eng.rng_step += 1
+        return (res[0], teacher_c) + tuple(res[1:])
+
+    def dino_loss(self, student_out, teacher_out, tau_s, tau_t, variant):
+        """Fused CUDA loss.  If the tensors are the ones the last forward produced (and the temperatures match the
+        engine's) the already-computed loss/gradient are reused; otherwise the loss kernel runs on the given tensors."""
+        eng, w = self.engine, self.last_w
+        same = (w is not None and student_out.data_ptr() == w["s.proj"].data_ptr() and tau_s == eng.tau_s and tau_t == eng.tau_t)
+        if same:
+            return fused_loss(w["loss"][0], (student_out,), (w["d.proj"].view_as(student_out),))
+        return standalone_dino_loss(student_out, teacher_out, tau_s, tau_t, variant)
+
+
+def standalone_dino_loss(student_out, teacher_out, tau_s, tau_t, variant=0):
+    """DINO loss of arbitrary CUDA tensors [Vs,B,D], [Vt,B,D] (teacher already centred) through the fused kernel."""
+    s = student_out.detach().contiguous().float()
+    t = teacher_out.detach().contiguous().float()
+    Vs, B, D = s.shape
+    zero = torch.zeros(D, device=s.device)
+    parts = ops.dino_loss_parts(B)
+    grad = torch.empty_like(s)
+    pl_, pc = torch.empty(parts, device=s.device), torch.empty(parts, D, device=s.device)
+    cm = None
+    if variant == 1:
+        cm = torch.empty(t.shape[0], D, device=s.device)
+        ops.teacher_norm_colmean(t, zero, cm)
+    ops.dino_loss_fwd_bwd(s, t, zero, tau_s, tau_t, grad, pl_, pc, variant=variant, t_colmean=cm)
+    loss = torch.empty(1, device=s.device)
+    ops.center_update(None, pc, pl_, t.shape[0] * B, 0.9, loss, colsum_out=torch.empty(D, device=s.device))
+    return fused_loss(loss[0], (student_out,), (grad,))
+
+
+def standalone_pair_loss(kind, a, b, **kw):
+    """mse / infonce of two [B,D] CUDA tensors through the fused kernels, differentiable w.r.t. both."""
+    x, y = a.detach().contiguous().float(), b.detach().contiguous().float()
+    ga, gb, lo = torch.empty_like(x), torch.empty_like(y), torch.empty(1, device=x.device)
+    if kind == "mse":
+        ops.mse_align_fwd_bwd(x, y, ga, gb, lo)
+    else:
+        work = torch.empty(ops.infonce_work_floats(*x.shape), device=x.device)
+        ops.infonce_fwd_bwd(x, y, ga, gb, lo, work, temperature=kw.get("temperature", 0.07))
+    return fused_loss(lo[0], (a, b), (ga, gb))
+
+
+def standalone_ce_loss(logits, labels):
+    x = logits.detach().contiguous().float()
+    g, lo = torch.empty_like(x), torch.empty(1, device=x.device)
+    ops.ce_fwd_bwd(x, labels.contiguous(), g, lo)
+    return fused_loss(lo[0], (logits,), (g,))
+
+
+def standalone_cosine_loss(emb):
+    x = emb.detach().contiguous().float()
+    g, lo = torch.empty_like(x), torch.empty(1, device=x.device)
+    ops.cosine_consistency_fwd_bwd(x, g, lo)
+    return fused_loss(lo[0], (emb,), (g,))

@@ -441,21 +441,16 @@ class DinoStepEngine:
     # ------------------------------------------------------------------------------------------------------
     # the step
     # ------------------------------------------------------------------------------------------------------
-    def forward_backward(self, x_img, x_aud, masks=None, raw=None, labels=None):
-        """Student + teacher forward, losses, centre EMA and the full backward for already-augmented views.
-
-        x_img [V,B,28,28] (and x_aud [V,B,112,112]) view-major, global views first; masks (optional, parity tests):
-        dict of uint8 keep-masks 'student_fusion' [V*B,E], 'teacher_fusion' [Vg*B,E], 'student_head' [V*B,512];
-        raw = (image [B,28,28], audio [B,112,112]) fp32 for the non-default modes; labels int64 [B].
-        Leaves the gradients in self.grad (all-reduced when data parallel) and returns the loss tensor [4] =
-        (dino, aux, cosine, total) on the device."""
-        V, Vg, E, O, P = self.V, self.Vg, self.E, self.O, self.P
+    def forward_pass(self, x_img, x_aud, masks=None, raw=None):
+        """Student (all views [+ the un-augmented pass in the non-default modes]) and teacher (global views) forward
+        through encoders and heads.  Returns the workspace dict; outputs: w['s.proj'] [V*B,P], w['t.proj'] [Vg*B,P]
+        (UNcentred), w['aux_image.out'] / w['aux_audio.out'] [B, 10|P]."""
+        V, Vg, E = self.V, self.Vg, self.E
         B = x_img.shape[1]
         w = self._workspace(B)
         Ns, Nt, Nv = w["Ns"], w["Nt"], V * B
-        S, T, G = self.S, self.T, self.G
+        S, T = self.S, self.T
         multi = self.kind == "multi_central"
-        # ---- inputs into the (V[+1])*B batch buffers ----
         xi = w["x_img"]
         if x_img.data_ptr() != xi.data_ptr():
             xi[:Nv].copy_(x_img.reshape(Nv, 1, 28, 28))
@@ -467,7 +462,6 @@ class DinoStepEngine:
         if self.mode != "default":
             xi[Nv:].copy_(raw[0].reshape(B, 1, 28, 28))
             xa[Nv:].copy_(raw[1].reshape(B, 1, 112, 112))
-        # ---- dropout masks ----
         if masks is not None:
             if multi:
                 w["s.fmask"].copy_(masks["student_fusion"].reshape(Nv, E))
@@ -480,20 +474,27 @@ class DinoStepEngine:
                 ops.dropout_mask(w["t.fmask"], self.fusion_dropout, self.seed + 1, base + 1)
             if self.dropout > 0:
                 ops.dropout_mask(w["s.hmask"], self.dropout, self.seed + 1, base + 2)
-        # ---- forward ----
         feat_s = self._encode(w, "s", S, self.bn_s, xi, xa, Ns, B, Nv, w.get("s.fmask"))
         feat_t = self._encode(w, "t", T, self.bn_t, xi[:Nt], xa[:Nt] if multi else None, Nt, B, Nt, w.get("t.fmask"))
         self._head_fwd(w, "s", "head.", S, self.bn_s["head.mlp.1"], feat_s, w["s.proj"], w["s.hh"], w["s.g"], w["s.hmask"], self.dropout)
         self._head_fwd(w, "t", "head.", T, self.bn_t["head.mlp.1"], feat_t, w["t.proj"], w["t.hh"], w["t.g"], None, 0.0)
-        # ---- DINO loss (fwd + bwd) and centre ----
+        if self.mode != "default":
+            cat = w["s.cat"]
+            for m, sl in (("aux_image", slice(0, E)), ("aux_audio", slice(E, 2 * E))):
+                self._head_fwd(w, m, m + ".", S, self.bn_s[f"{m}.mlp.1"], cat[Nv:, sl], w[f"{m}.out"], w[f"{m}.hh"], w[f"{m}.g"], None, 0.0)
+        w["loss"].zero_()
+        return w
+
+    def dino_loss_pass(self, w):
+        """Fused DINO loss forward+backward (fills w['d.proj'], loss[0]) and the centre EMA (all-reduced when data parallel)."""
+        V, Vg, P, B = self.V, self.Vg, self.P, w["B"]
         s_out, t_out = w["s.proj"].view(V, B, P), w["t.proj"].view(Vg, B, P)
-        variant = 0 if multi else 1
+        variant = 0 if self.kind == "multi_central" else 1
         if variant == 1:
             ops.teacher_norm_colmean(t_out, self.center, w["t_colmean"])
         ops.dino_loss_fwd_bwd(s_out, t_out, self.center, self.tau_s, self.tau_t, w["d.proj"].view(V, B, P), w["part_loss"], w["part_colsum"],
                               variant=variant, t_colmean=w["t_colmean"] if variant == 1 else None)
         loss = w["loss"]
-        loss.zero_()
         if self.world > 1:
             # data parallel: centre = EMA of the mean over ALL ranks' teacher rows (SURVEY §8e)
             ops.center_update(None, w["part_colsum"], w["part_loss"], Vg * B, self.center_momentum, loss[0:1], colsum_out=w["colsum"][:P])
@@ -501,29 +502,36 @@ class DinoStepEngine:
             ops.center_apply(self.center, w["colsum"][:P], rows, self.center_momentum)
         else:
             ops.center_update(self.center, w["part_colsum"], w["part_loss"], Vg * B, self.center_momentum, loss[0:1])
-        # ---- auxiliary passes ----
+
+    def aux_loss_pass(self, w, labels=None):
+        """MSE / InfoNCE / CE on the mode heads' outputs, forward+backward fused (fills w['aux_*.d.out'], loss[1])."""
+        loss = w["loss"]
+        oi, oa = w["aux_image.out"], w["aux_audio.out"]
+        if self.mode == "semi_supervised":
+            ops.ce_fwd_bwd(oi, labels, w["aux_image.d.out"], loss[1:2], grad_scale=self.alpha)
+            ops.ce_fwd_bwd(oa, labels, w["aux_audio.d.out"], loss[2:3], grad_scale=self.alpha)
+            loss[1:2].add_(loss[2:3])
+            loss[2:3].zero_()
+        elif self.mode == "infonce":
+            ops.infonce_fwd_bwd(oi, oa, w["aux_image.d.out"], w["aux_audio.d.out"], loss[1:2], w["infonce_work"], grad_scale=self.alpha)
+        elif self.mode == "mse":
+            ops.mse_align_fwd_bwd(oi, oa, w["aux_image.d.out"], w["aux_audio.d.out"], loss[1:2], grad_scale=self.alpha)
+
+    def backward_pass(self, w, d_proj=None, d_aux=None):
+        """Backward from the gradient w.r.t. the student projections (default: the fused loss's own w['d.proj']) and, in the
+        non-default modes, w.r.t. the two mode-head outputs (default: w['aux_*.d.out']).  Fills self.grad."""
+        V, E, O = self.V, self.E, self.O
+        B = w["B"]
+        Ns, Nv = w["Ns"], V * B
+        S, G = self.S, self.G
+        multi = self.kind == "multi_central"
+        xi, xa = w["x_img"], w.get("x_aud")
+        feat_s = w["s.feat"]
+        d_proj = w["d.proj"] if d_proj is None else d_proj.reshape(Nv, self.P)
         d_feat = w["d.feat"]
-        if self.mode != "default":
-            cat = w["s.cat"]
-            outs = {}
-            for m, sl in (("aux_image", slice(0, E)), ("aux_audio", slice(E, 2 * E))):
-                self._head_fwd(w, m, m + ".", S, self.bn_s[f"{m}.mlp.1"], cat[Nv:, sl], w[f"{m}.out"], w[f"{m}.hh"], w[f"{m}.g"], None, 0.0)
-                outs[m] = w[f"{m}.out"]
-            if self.mode == "semi_supervised":
-                ops.ce_fwd_bwd(outs["aux_image"], labels, w["aux_image.d.out"], loss[1:2], grad_scale=self.alpha)
-                ops.ce_fwd_bwd(outs["aux_audio"], labels, w["aux_audio.d.out"], loss[2:3], grad_scale=self.alpha)
-                loss[1:2].add_(loss[2:3])
-                loss[2:3].zero_()
-            elif self.mode == "infonce":
-                ops.infonce_fwd_bwd(outs["aux_image"], outs["aux_audio"], w["aux_image.d.out"], w["aux_audio.d.out"], loss[1:2],
-                                    w["infonce_work"], grad_scale=self.alpha)
-            else:
-                ops.mse_align_fwd_bwd(outs["aux_image"], outs["aux_audio"], w["aux_image.d.out"], w["aux_audio.d.out"], loss[1:2],
-                                      grad_scale=self.alpha)
-        # ---- backward: head -> fusion -> encoders ----
-        self._head_bwd(w, "s", "head.", feat_s, w["d.proj"], w["s.hh"], w["s.g"], w["d.g"], w["d.hh"], d_feat, w["s.hmask"], self.dropout)
+        self._head_bwd(w, "s", "head.", feat_s, d_proj, w["s.hh"], w["s.g"], w["d.g"], w["d.hh"], d_feat, w["s.hmask"], self.dropout)
         if self.cosine_loss_alpha > 0:
-            ops.cosine_consistency_fwd_bwd(feat_s.view(V, B, O), w["d.emb"].view(V, B, O), loss[2:3], grad_scale=self.cosine_loss_alpha)
+            ops.cosine_consistency_fwd_bwd(feat_s.view(V, B, O), w["d.emb"].view(V, B, O), w["loss"][2:3], grad_scale=self.cosine_loss_alpha)
             d_feat.add_(w["d.emb"])
         if multi:
             d_cat, d_h1 = w["d.cat"], w["d.h1"]
@@ -533,8 +541,9 @@ class DinoStepEngine:
             ops.linear_bwd_weight(d_h1, w["s.cat"][:Nv], G["enc.fusion.0.weight"], G["enc.fusion.0.bias"])
             ops.linear_bwd_data(d_h1, S["enc.fusion.0.weight"], d_cat[:Nv])
             if self.mode != "default":
-                for m, sl in (("aux_image", slice(0, E)), ("aux_audio", slice(E, 2 * E))):
-                    self._head_bwd(w, m, m + ".", w["s.cat"][Nv:, sl], w[f"{m}.d.out"], w[f"{m}.hh"], w[f"{m}.g"], w[f"{m}.d.g"],
+                for i, (m, sl) in enumerate((("aux_image", slice(0, E)), ("aux_audio", slice(E, 2 * E)))):
+                    d_out = w[f"{m}.d.out"] if d_aux is None else d_aux[i]
+                    self._head_bwd(w, m, m + ".", w["s.cat"][Nv:, sl], d_out, w[f"{m}.hh"], w[f"{m}.g"], w[f"{m}.d.g"],
                                    w[f"{m}.d.hh"], d_cat[Nv:, sl], None, 0.0)
             for mod, layers, sl, nflat, lin, x in (("img", self.img_layers, slice(0, E), 1600, "enc.image_encoder.1", xi),
                                                    ("aud", self.aud_layers, slice(E, 2 * E), 3136, "enc.audio_encoder.1", xa)):
@@ -551,9 +560,24 @@ class DinoStepEngine:
             d_p = w["dp_a"][:Ns * 128 * 9].view(Ns, 128, 3, 3)
             ops.avgpool_bwd(w["d.pool"], d_p)
             self._conv_stack_bwd(w, "img", self.img_layers, xi, d_p, Ns, B)
-        loss[3:4].copy_(loss[0:1] + loss[1:2] + loss[2:3])
         if self.world > 1:
             self.allreduce_gradients()
+
+    def forward_backward(self, x_img, x_aud, masks=None, raw=None, labels=None):
+        """Student + teacher forward, losses, centre EMA and the full backward for already-augmented views.
+
+        x_img [V,B,28,28] (and x_aud [V,B,112,112]) view-major, global views first; masks (optional, parity tests):
+        dict of uint8 keep-masks 'student_fusion' [V*B,E], 'teacher_fusion' [Vg*B,E], 'student_head' [V*B,512];
+        raw = (image [B,28,28], audio [B,112,112]) fp32 for the non-default modes; labels int64 [B].
+        Leaves the gradients in self.grad (all-reduced when data parallel) and returns the loss tensor [4] =
+        (dino, aux, cosine, total) on the device."""
+        w = self.forward_pass(x_img, x_aud, masks=masks, raw=raw)
+        self.dino_loss_pass(w)
+        if self.mode != "default":
+            self.aux_loss_pass(w, labels)
+        self.backward_pass(w)
+        loss = w["loss"]
+        loss[3:4].copy_(loss[0:1] + loss[1:2] + loss[2:3])
         return loss
 
     def allreduce_gradients(self):

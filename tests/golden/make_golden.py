@@ -252,7 +252,28 @@ def unimodal_fixture(B=4, seed=9):
     return rec
 
 
+def api_surface():
+    """state_dict keys/shapes of the reference modules and seeded-initialisation checksums (API-compatibility fixtures)."""
+    out = {}
+    specs = {"default": (md.MultiModalDINO, {}), "semi_supervised": (md.MultiModalDINOSemiSupervised, {}),
+             "infonce": (md.MultiModalDINOWithINFONCE, {}), "mse": (md.MultiModalDINOWithMSE, {})}
+    for name, (cls, kw) in specs.items():
+        torch.manual_seed(123)
+        m = cls(encoder_class=md.CentralMultiModalEncoder, output_dim=256, encoder_output_dim=256, projection_dim=128, **kw)
+        out[name] = {"keys": {k: list(v.shape) for k, v in m.state_dict().items()},
+                     "init": {k: summarize(v) for k, v in m.state_dict().items() if v.dtype == torch.float32 and ("conv2.weight" in k or "mlp.0.weight" in k or "fusion.3.bias" in k)}}
+    torch.manual_seed(123)
+    u = md.UniModalDINO(encoder_class=md.ImageEncoder, output_dim=256, projection_dim=128)
+    out["unimodal"] = {"keys": {k: list(v.shape) for k, v in u.state_dict().items()},
+                       "init": {k: summarize(v) for k, v in u.state_dict().items() if "encoder.4.weight" in k or "mlp.4.weight" in k}}
+    return out
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "api":
+        with open(os.path.join(HERE, "api_surface.json"), "w") as f:
+            json.dump(api_surface(), f, indent=1)
+        sys.exit(0)
     fx = {"losses": losses_kat(), "augment": augment_fixtures()}
     fx["steps"] = {m: step_fixture(m) for m in ("default", "semi_supervised", "infonce", "mse")}
     fx["unimodal_image_simple"] = unimodal_fixture()

@@ -1,0 +1,173 @@
+"""CPU: the Python API mirror (AVMNIST_Experiments/...) keeps the reference's surface: module / class names, constructor
+keywords, state_dict keys and shapes, seeded initialisation, config helpers, CLI -- checked against fixtures generated from
+the imported reference (tests/golden/api_surface.json).  No CUDA needed; the compute path itself must refuse CPU tensors."""
+import json
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MIRROR = os.path.join(ROOT, "multimodal_ssl_avmnist_b200", "AVMNIST_Experiments")
+sys.path.insert(0, MIRROR)
+
+import models.dino as md  # noqa: E402
+import utils.get_data as gd  # noqa: E402
+from hyperparameter_tuning.objective_augment import process_augment_config  # noqa: E402
+from oracle.fixtures import summaries_close, summarize  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def surface():
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "api_surface.json")))
+
+
+CLASSES = {"default": md.MultiModalDINO, "semi_supervised": md.MultiModalDINOSemiSupervised, "infonce": md.MultiModalDINOWithINFONCE,
+           "mse": md.MultiModalDINOWithMSE}
+
+
+@pytest.mark.parametrize("mode", list(CLASSES))
+def test_state_dict_and_seeded_init_match_reference(mode, surface):
+    torch.manual_seed(123)
+    m = CLASSES[mode](encoder_class=md.CentralMultiModalEncoder, output_dim=256, encoder_output_dim=256, projection_dim=128)
+    sd = m.state_dict()
+    ref = surface[mode]["keys"]
+    assert list(sd.keys()) == list(ref.keys())                       # same names, same order
+    assert all(list(sd[k].shape) == ref[k] for k in ref)
+    for k, want in surface[mode]["init"].items():                     # same RNG consumption -> same initial weights
+        ok, why = summaries_close(summarize(sd[k]), want, 1e-12, 0.0)
+        assert ok, (k, why)
+    assert [n for n, p in m.named_parameters() if not p.requires_grad] == [n for n, _ in m.named_parameters() if n.startswith("teacher")]
+    assert torch.equal(m.teacher.fusion[0].weight, m.student.fusion[0].weight)
+
+
+def test_unimodal_surface(surface):
+    torch.manual_seed(123)
+    u = md.UniModalDINO(encoder_class=md.ImageEncoder, output_dim=256, projection_dim=128)
+    sd = u.state_dict()
+    assert list(sd.keys()) == list(surface["unimodal"]["keys"].keys())
+    for k, want in surface["unimodal"]["init"].items():
+        ok, why = summaries_close(summarize(sd[k]), want, 1e-12, 0.0)
+        assert ok, (k, why)
+
+
+def test_lightning_wrappers_accept_the_reference_kwargs():
+    kw = dict(data_dir="x/", data_augmentation="burst_noise", dino_model=None, encoder_class=md.CentralMultiModalEncoder, encoder_kwargs=None,
+              projection_dim=128, output_dim=256, encoder_output_dim=256, momentum=0.996, center_momentum=0.9, student_temperature=0.1,
+              teacher_temperature=0.04, learning_rate=1e-4, use_mixed_precision=True, num_epochs=100, weight_decay=1e-6, dropout=0.3)
+    for cls in (md.MultiModalDINOLightning, md.MultiModalDINOSemiSupervisedLightning, md.MultiModalDINOWithINFONCELightning,
+                md.MultiModalDINOWithMSELightning):
+        lit = cls(**kw)
+        for attr in ("training_step", "dino_loss", "configure_optimizers", "on_train_epoch_end", "forward", "model"):
+            assert hasattr(lit, attr)
+        cfg = lit.configure_optimizers()
+        assert isinstance(cfg["optimizer"], torch.optim.Optimizer) and cfg["optimizer"].param_groups[0]["lr"] == 1e-4
+        assert isinstance(cfg["lr_scheduler"]["scheduler"], torch.optim.lr_scheduler.CosineAnnealingLR)
+    assert hasattr(md.MultiModalDINOWithINFONCELightning, "infoNCE_loss") and hasattr(md.MultiModalDINOWithMSELightning, "mse_loss")
+    assert hasattr(md.MultiModalDINOSemiSupervisedLightning, "supervised_loss")
+    uni = md.UniModalDINOLightning(encoder_class=md.ImageEncoder, data_dir="x/", dropout=0.3, learning_rate=1e-4, projection_dim=128,
+                                   output_dim=256, momentum=0.996, center_momentum=0.9, teacher_temperature=0.04, weight_decay=1e-6,
+                                   cosine_loss_alpha=0, num_epochs=100, data_augmentation="burst_noise")
+    assert uni.student_temperature == 0.1
+
+
+def test_every_encoder_name_of_run_dino_imports():
+    for name in ("CrossAttentionMultiModalEncoder", "DualViTMultiModalEncoder", "GatedMultiModalEncoder", "LSTMMultiModalEncoder",
+                 "MobileViTMultiModalEncoder", "ResNetMultiModalEncoder", "SimpleMultiModalEncoder", "ViTMultiModalEncoder",
+                 "CentralMultiModalEncoder", "SpectrogramEncoder", "SpectrogramEncoderCentral", "SpectrogramEncoderLSTM",
+                 "SpectrogramEncoderResNet", "SpectrogramEncoderViT", "SpectrogramEncoderMobileViT", "ImageEncoder"):
+        assert hasattr(md, name)
+    with pytest.raises(NotImplementedError):
+        md.LSTMMultiModalEncoder()
+    with pytest.raises(NotImplementedError):
+        md.MultiModalDINO(encoder_class=md.SimpleMultiModalEncoder)      # containers exist, the compiled step does not (yet)
+
+
+def test_no_cpu_fallback():
+    m = md.MultiModalDINO(encoder_class=md.CentralMultiModalEncoder, output_dim=256, encoder_output_dim=256, projection_dim=128)
+    batch = (torch.rand(2, 2, 1, 28, 28), torch.rand(2, 2, 1, 112, 112), torch.rand(2, 4, 1, 28, 28), torch.rand(2, 4, 1, 112, 112))
+    with pytest.raises(Exception) as e:
+        m(batch)
+    assert "CUDA" in str(e.value) or "cuda" in str(e.value)
+
+
+def test_process_augment_config_and_augmentation_object():
+    import yaml
+    cfg = yaml.safe_load(open(os.path.join(MIRROR, "configs", "config_multimodal_dino.yaml")))
+    av = process_augment_config(None, cfg, is_hyperparameter_search=False)
+    assert list(av["augmentations"]["local_views"]) == ["frequency_mask", "gaussian_noise", "grouped_masking", "time_mask", "time_warp",
+                                                        "random_resized_crop", "random_affine"]
+    assert av["augmentation_probabilities"]["global_views"]["random_resized_crop"] == 0.9
+    with pytest.raises(ValueError):
+        process_augment_config(None, {}, is_hyperparameter_search=False)
+    aug = gd.MultiModalAugmentation(augment_values=av)
+    assert aug.n_global_views == 2 and aug.n_local_views == 4 and "GroupedMasking" in str(aug)
+    assert len(aug.local_transforms["audio"]) == 7 and len(aug.global_transforms["image"]) == 3
+
+    class Trial:        # the search branch only needs the suggest_* protocol
+        def suggest_float(self, k, lo, hi): return (lo + hi) / 2
+        def suggest_int(self, k, lo, hi, step=1): return lo
+        def suggest_categorical(self, k, c): return c[0]
+    space = {"optuna": {"augmentations": {"global_views": {"time_mask": {"p": {"low": 0.0, "high": 1.0}, "time_mask_param": {"type": "int", "low": 5, "high": 30}}},
+                                          "local_views": {}}}}
+    got = process_augment_config(Trial(), space, True)
+    assert got["augmentations"]["global_views"]["time_mask"] == {"time_mask_param": 5}
+    assert got["augmentation_probabilities"]["global_views"]["time_mask"] == 0.5
+
+
+def test_data_module_and_synthetic_files(tmp_path):
+    d = str(tmp_path) + "/"
+    gd.write_synthetic_avmnist(d, n_train=40, n_test=16)
+    dm = gd.AVMNISTDinoDataModuleExtended(data_dir=d, batch_size=8, num_workers=0, type="burst_noise")
+    dm.prepare_data()
+    dm.setup("fit")
+    image, audio, label = next(iter(dm.train_dataloader()))
+    assert image.shape == (8, 1, 28, 28) and audio.shape == (8, 1, 112, 112) and label.dtype == torch.long
+    assert float(audio.max()) <= 1.0 and dm.get_view_config() == {"n_global_views": 2, "n_local_views": 4}
+    with pytest.raises(FileNotFoundError):
+        gd.AVMNISTDinoDataModule(data_dir=d + "missing/", batch_size=8, num_workers=0).prepare_data()
+
+
+def test_cli_surfaces():
+    import run_dino
+    assert set(run_dino.MODEL_MAP) >= {"multi_central", "multi_simple"} and "image_simple" in run_dino.UNIMODAL_MODEL_MAP
+    assert list(run_dino.MULTIMODAL_WRAPPERS) == ["default", "semi_supervised", "mse", "infonce"]
+    with pytest.raises(SystemExit):
+        run_dino.main(["--config", "x.yaml"])                         # a model is required
+    sys.path.insert(0, os.path.join(MIRROR, "batch_files"))
+    import submit_models
+    cmds = submit_models.main(["--models", "multi_central", "image_simple", "--training_mode", "mse", "--dry_run"])
+    assert cmds[0][2:4] == ["--model", "multi_central"] and cmds[1][2:4] == ["--unimodal_model", "image_simple"] and cmds[0][4] == "mse"
+
+
+def test_trainer_shim_runs_a_toy_module(tmp_path):
+    from multimodal_ssl_avmnist_b200 import pl_shim as pls
+
+    class Toy(pls.LightningModule):
+        def __init__(self, lr=0.1):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.tensor([2.0]))
+            self.lr = lr
+            self.save_hyperparameters()
+
+        def training_step(self, batch, idx):
+            loss = ((self.w * batch) ** 2).mean()
+            self.log("train_loss", loss, on_step=True, on_epoch=True)
+            return loss
+
+        def configure_optimizers(self):
+            opt = torch.optim.SGD(self.parameters(), lr=self.lr)
+            return {"optimizer": opt, "lr_scheduler": {"scheduler": torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=2)}}
+
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    ckpt = pls.ModelCheckpoint(dirpath=str(tmp_path), monitor="train_loss_epoch", mode="min")
+    tr = pls.Trainer(max_epochs=2, logger=pls.CSVLogger(str(tmp_path), name="logs"), callbacks=[ckpt], log_every_n_steps=1)
+    model = Toy()
+    tr.fit(model, train_dataloaders=[torch.ones(4) for _ in range(5)])
+    assert tr.global_step == 10 and float(model.w) < 2.0
+    assert "train_loss_epoch" in tr.callback_metrics and os.path.exists(ckpt.best_model_path)
+    assert os.path.exists(os.path.join(tr.logger.log_dir, "metrics.csv"))
+    again = Toy.load_from_checkpoint(ckpt.best_model_path)
+    assert again.lr == 0.1
