@@ -132,6 +132,20 @@ int b200_conv_fwd(const float* x, const float* w, const float* bias, float* z, d
 /* dx = conv_transpose(dz, w)  (gradient w.r.t. the conv input) */
 int b200_conv_bwd_data(const float* dz, const float* w, float* dx, int N, int Cin, int Cout, int H, int W, int K,
                        int pad, void* stream);
+/* ---- tensor-core path (tcgen05 + TMEM + TMA) for the C_in >= 8 convolutions: same call sites as above ----
+ * Activations are bf16 in the "act8" layout [N][C/8][H][W][8] (channel octets are planes; a pixel of a plane is one
+ * 16-byte unit); accumulation is fp32.  b200_conv_tc computes z = conv(x, w) (+ bias and the BatchNorm partial
+ * statistics when bias != NULL) and writes either fp32 NCHW (out_bf16 = 0) or bf16 act8 (out_bf16 = 1).  The data
+ * gradient of a convolution is the same call with (Cin, Cout) swapped, pad' = K-1-pad, H/W those of dz, and weights
+ * prepared with flip = 1.  wprep: b200_conv_tc_weight_bytes(Cin, Cout, K) bytes filled by b200_conv_tc_prep_weights
+ * from the fp32 OIHW weight (for flip = 1: `w` is the FORWARD weight [Cin][Cout][K][K]). */
+int b200_conv_tc_supported(int Cin, int Cout, int H, int W, int K, int pad);
+int64_t b200_conv_tc_weight_bytes(int Cin, int Cout, int K);
+int b200_conv_tc_prep_weights(const float* w, void* wprep, int Cin, int Cout, int K, int flip, void* stream);
+int b200_conv_tc(const void* x_act8, const void* wprep, const float* bias, void* out, double* stats, int N,
+                 int n_per_view, int Cin, int Cout, int H, int W, int K, int pad, int out_bf16, void* stream);
+/* fp32 NCHW -> bf16 act8 */
+int b200_pack_act8(const float* x, void* out, int N, int C, int H, int W, void* stream);
 /* dw = sum_n corr(x_n, dz_n), db = sum dz.  work: float[b200_conv_bwd_weight_work_floats(...)] */
 int64_t b200_conv_bwd_weight_work_floats(int N, int Cin, int Cout, int H, int W, int K, int pad);
 int b200_conv_bwd_weight(const float* x, const float* dz, float* dw, float* db, float* work, int N, int Cin,

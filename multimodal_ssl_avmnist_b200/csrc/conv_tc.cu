@@ -1,0 +1,419 @@
+// Tensor-core convolutions for the C_in >= 8 layers of the AVMNIST encoders (models/unimodal.py:129-140, 186-208;
+// models/dino.py:20-30): tcgen05.mma with TMEM accumulators, operands staged by TMA, NO im2col.
+//
+// Activation layout ("act8"): bf16 [N][C/8][H][W][8] -- channel octets are planes, a pixel of a plane is one 16-byte
+// unit.  A TMA box load of (8, W+2p, H'+K-1, C/8) starting at (-p, -p) drops a whole zero-padded image (or row band)
+// into shared memory (out-of-bounds = 0 is the convolution padding).  With output pixels numbered flat over the PADDED
+// pitch, q = y*(W+2p) + x, the input pixel of tap (kh,kw) is q + kh*(W+2p) + kw: for a tile of 128 consecutive q the A
+// operand of every tap is the SAME smem image at a shifted start address -- a K-major SWIZZLE_NONE UMMA descriptor
+// (8 consecutive pixels x 16 B = one core matrix, SBO = 128 B; the second K chunk is the next channel plane,
+// LBO = plane stride, or for C_in = 8 the next kw tap, LBO = 16 B).  Outputs at x >= W_out / y >= H_out are junk and
+// are masked in the epilogue (7-30 % of the MMA work, which is nowhere near the bound).
+//
+// Roles in a CTA (192 threads, one CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-5 =
+// epilogue (tcgen05.ld -> +bias -> BatchNorm partial statistics -> store), double-buffered TMEM accumulators.
+// The same kernel is the data-gradient convolution (flipped/transposed weights prepared by conv_tc_prep_weights).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace b200 {
+
+int encode_tmap_bf16_4d(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                        const uint32_t box[4]) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+            set_error("cuTensorMapEncodeTiled entry point not available (%d)", (int)e);
+            return -30;
+        }
+        fn = (EncodeFn)p;
+    }
+    cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+    cuuint64_t s[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+    cuuint32_t b[4] = {box[0], box[1], box[2], box[3]};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return -31;
+    }
+    return 0;
+}
+
+namespace {
+
+using namespace umma;
+
+constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
+constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+
+template <int CIN_, int COUT_, int NPAD_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_>
+struct TcCfg {
+    static constexpr int CIN = CIN_, COUT = COUT_, NPAD = NPAD_, HIN = HIN_, WIN = WIN_, KS = KS_, PAD = PAD_, BANDS = BANDS_, SLOTS = SLOTS_;
+    static constexpr int P = CIN / 8;                           // channel planes of the input
+    static constexpr int WP = WIN + 2 * PAD;                    // padded pitch (pixels)
+    static constexpr int HO = HIN + 2 * PAD - KS + 1, WO = WP - KS + 1;
+    static constexpr int HB = HO / BANDS;                       // output rows per band
+    static constexpr int HPB = HB + KS - 1;                     // input rows per band slab
+    static constexpr int Q = (HB - 1) * WP + WO;                // flat outputs per band (incl. junk columns)
+    static constexpr int TILES = (Q + 127) / 128;
+    static constexpr int PLANE_BYTES = HPB * WP * 16;
+    static constexpr int SLOT_BYTES = round_up(P * PLANE_BYTES, 128);
+    static constexpr int NJ = (KS + 1) / 2;                     // kw pairs when CIN == 8
+    static constexpr int PH = P / 2;                            // plane pairs when CIN >= 16
+    static constexpr int NMMA = (CIN == 8) ? KS * NJ : KS * KS * PH;
+    static constexpr int W_BYTES = round_up(NMMA * NPAD * 32, 128);
+    static constexpr int MAXPIX = TILES * 128 + (KS - 1) * WP + KS + 1;       // exclusive bound of pixels a tile may touch
+    static constexpr int TAIL = round_up((MAXPIX > HPB * WP ? (MAXPIX - HPB * WP) : 0) * 16, 128) + 128;
+    static constexpr int IMG_BYTES = SLOTS * SLOT_BYTES + TAIL;
+    static constexpr int BAR_OFF = W_BYTES + IMG_BYTES;
+    static constexpr int SMEM = BAR_OFF + 256 + NPAD * 4;
+    static constexpr int TMEM_COLS = pow2_cols(2 * NPAD);
+    static_assert(CIN % 8 == 0 && (CIN == 8 || CIN % 16 == 0), "C_in must be 8 or a multiple of 16");
+    static_assert(NPAD % 16 == 0 && NPAD >= 16 && NPAD <= 64 && COUT <= NPAD && COUT % 8 == 0, "N tile");
+    static_assert(HO % BANDS == 0, "bands must divide the output height");
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    static_assert(P * PLANE_BYTES < (1 << 18) && PLANE_BYTES % 16 == 0, "descriptor range");
+};
+
+// out: fp32 NCHW [N][COUT][HO][WO] (out_bf16 == 0) or bf16 act8 [N][COUT/8][HO][WO][8] (out_bf16 == 1).
+// bias may be null (no bias, no statistics); stats: double [views][COUT][2] (sum, sum of squares), accumulated.
+template <class C>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict__ wprep, const float* __restrict__ bias,
+               void* __restrict__ out, double* __restrict__ stats, int n_per_view, int out_bf16) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* w_s = smem;
+    uint8_t* img_s = smem + C::W_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);   // full[SLOTS], empty[SLOTS], tfull[2], tempty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::BAR_OFF + 192);
+    float* bias_s = reinterpret_cast<float*>(smem + C::BAR_OFF + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int view = blockIdx.y, G = gridDim.x, g = blockIdx.x;
+    const long items = (long)n_per_view * C::BANDS;
+    const int i0 = (int)(items * g / G), i1 = (int)(items * (g + 1) / G);
+
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (C::SLOTS + s); };
+    auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * C::SLOTS + b); };
+    auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * C::SLOTS + 2 + b); };
+
+    // ---- one-time setup: weights -> smem, zero the image slots (+tail), barriers, TMEM ----
+    {
+        const uint4* src = wprep;
+        uint4* dst = reinterpret_cast<uint4*>(w_s);
+        for (int i = threadIdx.x; i < C::NMMA * C::NPAD * 2; i += blockDim.x) dst[i] = src[i];
+        uint4* z = reinterpret_cast<uint4*>(img_s);
+        for (int i = threadIdx.x; i < C::IMG_BYTES / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < C::NPAD; i += blockDim.x) bias_s[i] = (bias != nullptr && i < C::COUT) ? bias[i] : 0.f;
+        fence_proxy_async_smem();
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap);
+        for (int s = 0; s < C::SLOTS; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<C::TMEM_COLS>(smem_u32(tmem_slot));
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t img_addr = smem_u32(img_s), w_addr = smem_u32(w_s);
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int i = i0; i < i1; ++i) {
+                const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
+                mbar_wait(empty_bar(slot), (use & 1) ^ 1);
+                mbar_expect_tx(full_bar(slot), C::P * C::PLANE_BYTES);
+                const int n = view * n_per_view + i / C::BANDS, band = i % C::BANDS;
+                tma_load_4d(img_addr + slot * C::SLOT_BYTES, &tmap, full_bar(slot), 0, -C::PAD, band * C::HB - C::PAD, n * C::P);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_bf16(C::NPAD);
+            uint32_t tcount = 0;
+            for (int i = i0; i < i1; ++i) {
+                const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
+                mbar_wait(full_bar(slot), use & 1);
+                tc_fence_after_sync();
+                const uint32_t slot_addr = img_addr + slot * C::SLOT_BYTES;
+                for (int t = 0; t < C::TILES; ++t, ++tcount) {
+                    const uint32_t buf = tcount & 1, u = tcount >> 1;
+                    mbar_wait(tempty_bar(buf), (u & 1) ^ 1);
+                    tc_fence_after_sync();
+                    const uint32_t d = tmem_base + buf * C::NPAD;
+                    const uint32_t a0 = slot_addr + t * 2048;
+                    int idx = 0;
+#pragma unroll
+                    for (int kh = 0; kh < C::KS; ++kh) {
+                        if constexpr (C::CIN == 8) {
+#pragma unroll
+                            for (int j = 0; j < C::NJ; ++j, ++idx) {
+                                const uint64_t ad = smem_desc(a0 + (kh * C::WP + 2 * j) * 16, 16, 128);
+                                const uint64_t bd = smem_desc(w_addr + idx * C::NPAD * 32, C::NPAD * 16, 128);
+                                mma_bf16(d, ad, bd, idesc, idx > 0);
+                            }
+                        } else {
+#pragma unroll
+                            for (int kw = 0; kw < C::KS; ++kw) {
+#pragma unroll
+                                for (int pp = 0; pp < C::PH; ++pp, ++idx) {
+                                    const uint64_t ad = smem_desc(a0 + (kh * C::WP + kw) * 16 + pp * 2 * C::PLANE_BYTES, C::PLANE_BYTES, 128);
+                                    const uint64_t bd = smem_desc(w_addr + idx * C::NPAD * 32, C::NPAD * 16, 128);
+                                    mma_bf16(d, ad, bd, idesc, idx > 0);
+                                }
+                            }
+                        }
+                    }
+                    mma_commit(tfull_bar(buf));
+                }
+                mma_commit(empty_bar(slot));
+            }
+        }
+    } else {
+        // ===== epilogue warps (TMEM lane quadrant = warp % 4) =====
+        const int quad = warp & 3, row = quad * 32 + lane;
+        float s1[C::COUT], s2[C::COUT];
+#pragma unroll
+        for (int c = 0; c < C::COUT; ++c) s1[c] = s2[c] = 0.f;
+        const bool do_stats = (bias != nullptr) && (stats != nullptr);
+        uint32_t tcount = 0;
+        for (int i = i0; i < i1; ++i) {
+            const int n = view * n_per_view + i / C::BANDS, band = i % C::BANDS;
+            for (int t = 0; t < C::TILES; ++t, ++tcount) {
+                const uint32_t buf = tcount & 1, u = tcount >> 1;
+                mbar_wait(tfull_bar(buf), u & 1);
+                tc_fence_after_sync();
+                const int q = t * 128 + row;
+                const int y = q / C::WP, x = q - y * C::WP;
+                const bool valid = (y < C::HB) && (x < C::WO);
+                const int yy = band * C::HB + y;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * C::NPAD;
+#pragma unroll
+                for (int cc = 0; cc < C::NPAD / 16; ++cc) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + cc * 16, v);
+                    tmem_ld_wait();
+                    if (cc == C::NPAD / 16 - 1) {                 // accumulator drained: hand the TMEM buffer back
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar(buf));
+                    }
+                    float f[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int ch = cc * 16 + j;
+                        f[j] = __uint_as_float(v[j]) + bias_s[ch];
+                        if (ch < C::COUT && valid) {
+                            s1[ch < C::COUT ? ch : 0] += f[j];
+                            s2[ch < C::COUT ? ch : 0] += f[j] * f[j];
+                        }
+                    }
+                    if (valid) {
+                        if (out_bf16) {
+#pragma unroll
+                            for (int o = 0; o < 2; ++o) {
+                                const int oct = cc * 2 + o;
+                                if (oct * 8 < C::COUT) {
+                                    uint4 pk;
+                                    pk.x = pack_bf16(f[o * 8 + 0], f[o * 8 + 1]);
+                                    pk.y = pack_bf16(f[o * 8 + 2], f[o * 8 + 3]);
+                                    pk.z = pack_bf16(f[o * 8 + 4], f[o * 8 + 5]);
+                                    pk.w = pack_bf16(f[o * 8 + 6], f[o * 8 + 7]);
+                                    uint4* dst = reinterpret_cast<uint4*>(out) + (((long)n * (C::COUT / 8) + oct) * C::HO + yy) * C::WO + x;
+                                    *dst = pk;
+                                }
+                            }
+                        } else {
+                            float* dst = reinterpret_cast<float*>(out) + (((long)n * C::COUT) * C::HO + yy) * C::WO + x;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int ch = cc * 16 + j;
+                                if (ch < C::COUT) dst[(long)ch * C::HO * C::WO] = f[j];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (do_stats) {
+#pragma unroll
+            for (int c = 0; c < C::COUT; ++c) {
+                const double a = warp_sum((double)s1[c]), b = warp_sum((double)s2[c]);
+                if (lane == 0) {
+                    atomicAdd(&stats[((long)view * C::COUT + c) * 2 + 0], a);
+                    atomicAdd(&stats[((long)view * C::COUT + c) * 2 + 1], b);
+                }
+            }
+        }
+    }
+    // ---- teardown ----
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    }
+}
+
+// fp32 OIHW weights -> the bf16 byte image the MMA issuer expects: [mma][k chunk (2)][n group][8 rows][8 k].
+// flip = 1 prepares the data-gradient convolution: w is the forward weight [CIN][COUT][KS][KS] and the taps are mirrored.
+__global__ void conv_tc_prep_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int CIN, int COUT, int NPAD,
+                                            int KS, int flip, int total) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int k8 = e & 7, r = (e >> 3) & 7, NG = NPAD / 8;
+    const int ng = (e >> 6) % NG, c = (e / (64 * NG)) & 1, m = e / (128 * NG);
+    const int co = ng * 8 + r;
+    int kh, kw, ci;
+    if (CIN == 8) {
+        const int NJ = (KS + 1) / 2;
+        kh = m / NJ;
+        kw = 2 * (m % NJ) + c;
+        ci = k8;
+    } else {
+        const int PH = CIN / 16;
+        kh = m / (KS * PH);
+        kw = (m / PH) % KS;
+        ci = (2 * (m % PH) + c) * 8 + k8;
+    }
+    float v = 0.f;
+    if (kw < KS && co < COUT) {
+        v = flip ? w[((ci * COUT + co) * KS + (KS - 1 - kh)) * KS + (KS - 1 - kw)] : w[((co * CIN + ci) * KS + kh) * KS + kw];
+    }
+    out[e] = __float2bfloat16_rn(v);
+}
+
+// fp32 NCHW -> bf16 act8 (tests and the hand-over from the fp32 first layer)
+__global__ void pack_act8_kernel(const float* __restrict__ x, uint4* __restrict__ out, long n_units, int C, int HW) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;     // one 16-byte unit: (n, octet, pixel)
+    if (i >= n_units) return;
+    const int pix = (int)(i % HW);
+    const long no = i / HW;
+    const int oct = (int)(no % (C / 8));
+    const long n = no / (C / 8);
+    const float* s = x + ((n * C + oct * 8) * (long)HW) + pix;
+    uint4 pk;
+    pk.x = pack_bf16(s[0], s[(long)HW]);
+    pk.y = pack_bf16(s[2L * HW], s[3L * HW]);
+    pk.z = pack_bf16(s[4L * HW], s[5L * HW]);
+    pk.w = pack_bf16(s[6L * HW], s[7L * HW]);
+    out[i] = pk;
+}
+
+template <class C>
+int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* out, double* stats, int N, int n_per_view, int out_bf16,
+                   cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) {
+            set_error("conv_tc: cannot set %d bytes of shared memory: %s", C::SMEM, cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured = true;
+    }
+    CUtensorMap tm;
+    const uint64_t dims[4] = {8, (uint64_t)C::WIN, (uint64_t)C::HIN, (uint64_t)N * C::P};
+    const uint64_t strides[3] = {16, (uint64_t)C::WIN * 16, (uint64_t)C::WIN * C::HIN * 16};
+    const uint32_t box[4] = {8, (uint32_t)C::WP, (uint32_t)C::HPB, (uint32_t)C::P};
+    int rc = encode_tmap_bf16_4d(&tm, x, dims, strides, box);
+    if (rc) return rc;
+    const int views = N / n_per_view;
+    int G = sm_count() / views;
+    if (G < 1) G = 1;
+    const long items = (long)n_per_view * C::BANDS;
+    if (G > items) G = (int)items;
+    conv_tc_kernel<C><<<dim3(G, views), 192, C::SMEM, st>>>(tm, reinterpret_cast<const uint4*>(wprep), bias, out, stats, n_per_view, out_bf16);
+    return launch_status("conv_tc_kernel");
+}
+
+//                         CIN COUT NPAD HIN  WIN KS PAD BANDS SLOTS
+using CfgA1 = TcCfg<8, 16, 16, 56, 56, 5, 2, 2, 4>;      // audio conv2 forward
+using CfgA2 = TcCfg<16, 32, 32, 28, 28, 5, 2, 1, 4>;     // audio conv3 forward
+using CfgA3 = TcCfg<32, 64, 64, 14, 14, 5, 2, 1, 4>;     // audio conv4 forward
+using CfgI1 = TcCfg<32, 64, 64, 14, 14, 5, 0, 1, 4>;     // image conv2 forward (no padding)
+using CfgA1d = TcCfg<16, 8, 16, 56, 56, 5, 2, 2, 3>;     // data gradients (C_in/C_out swapped, pad' = K-1-pad)
+using CfgA2d = TcCfg<32, 16, 16, 28, 28, 5, 2, 1, 2>;
+using CfgA3d = TcCfg<64, 32, 32, 14, 14, 5, 2, 1, 2>;
+using CfgI1d = TcCfg<64, 32, 32, 10, 10, 5, 4, 1, 2>;
+using CfgS1 = TcCfg<32, 64, 64, 14, 14, 3, 1, 1, 4>;     // image_simple conv2 forward / its data gradient
+using CfgS1d = TcCfg<64, 32, 32, 14, 14, 3, 1, 1, 4>;
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_conv_tc_supported(int Cin, int Cout, int H, int W, int K, int pad) {
+#define TC_MATCH(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) return 1;
+    TC_MATCH(CfgA1) TC_MATCH(CfgA2) TC_MATCH(CfgA3) TC_MATCH(CfgI1) TC_MATCH(CfgA1d) TC_MATCH(CfgA2d) TC_MATCH(CfgA3d) TC_MATCH(CfgI1d)
+    TC_MATCH(CfgS1) TC_MATCH(CfgS1d)
+#undef TC_MATCH
+    return 0;
+}
+
+int64_t b200_conv_tc_weight_bytes(int Cin, int Cout, int K) {
+    const int npad = (Cout + 15) / 16 * 16;
+    const int nmma = (Cin == 8) ? K * ((K + 1) / 2) : K * K * (Cin / 16);
+    return (int64_t)nmma * npad * 32;
+}
+
+int b200_conv_tc_prep_weights(const float* w, void* out, int Cin, int Cout, int K, int flip, void* stream) {
+    B200_REQUIRE(w && out, -1, "conv_tc_prep_weights: null pointer");
+    B200_REQUIRE(Cin == 8 || (Cin % 16 == 0 && Cin > 0), -2, "conv_tc_prep_weights: C_in must be 8 or a multiple of 16 (got %d)", Cin);
+    B200_REQUIRE(Cout % 8 == 0 && Cout > 0 && Cout <= 64, -2, "conv_tc_prep_weights: C_out must be a multiple of 8, <= 64 (got %d)", Cout);
+    const int npad = (Cout + 15) / 16 * 16;
+    const int total = (int)(b200_conv_tc_weight_bytes(Cin, Cout, K) / 2);
+    conv_tc_prep_weights_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(out), Cin, Cout, npad, K,
+                                                                                      flip, total);
+    return launch_status("conv_tc_prep_weights_kernel");
+}
+
+int b200_pack_act8(const float* x, void* out, int N, int C, int H, int W, void* stream) {
+    B200_REQUIRE(x && out, -1, "pack_act8: null pointer");
+    B200_REQUIRE(C % 8 == 0 && N > 0, -2, "pack_act8: C must be a multiple of 8");
+    const long units = (long)N * (C / 8) * H * W;
+    pack_act8_kernel<<<(unsigned)((units + 255) / 256), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<uint4*>(out), units, C, H * W);
+    return launch_status("pack_act8_kernel");
+}
+
+int b200_conv_tc(const void* x_act8, const void* wprep, const float* bias, void* out, double* stats, int N, int n_per_view, int Cin, int Cout,
+                 int H, int W, int K, int pad, int out_bf16, void* stream) {
+    B200_REQUIRE(x_act8 && wprep && out, -1, "conv_tc: null pointer");
+    B200_REQUIRE(N > 0 && n_per_view > 0 && N % n_per_view == 0, -2, "conv_tc: N=%d must be a multiple of n_per_view=%d", N, n_per_view);
+    B200_REQUIRE(((uintptr_t)x_act8 & 15) == 0 && ((uintptr_t)wprep & 15) == 0 && ((uintptr_t)out & 15) == 0, -3, "conv_tc: pointers must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+#define TC_RUN(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) \
+        return launch_conv_tc<CFG>(x_act8, wprep, bias, out, stats, N, n_per_view, out_bf16, st);
+    TC_RUN(CfgA1) TC_RUN(CfgA2) TC_RUN(CfgA3) TC_RUN(CfgI1) TC_RUN(CfgA1d) TC_RUN(CfgA2d) TC_RUN(CfgA3d) TC_RUN(CfgI1d) TC_RUN(CfgS1) TC_RUN(CfgS1d)
+#undef TC_RUN
+    set_error("conv_tc: unsupported geometry Cin=%d Cout=%d H=%d W=%d K=%d pad=%d", Cin, Cout, H, W, K, pad);
+    return -4;
+}
+
+}  // extern "C"

@@ -185,6 +185,41 @@ def conv_bwd_weight(x, dz, dw, db, work, pad):
                                             K, pad, _stream()), "conv_bwd_weight")
 
 
+# ---- tensor-core convolutions (tcgen05 / TMEM / TMA; bf16 "act8" activations [N][C/8][H][W][8]) -----------------
+BF16 = torch.bfloat16
+
+
+def conv_tc_supported(Cin, Cout, H, W, K, pad):
+    return bool(_lib_().b200_conv_tc_supported(Cin, Cout, H, W, K, pad))
+
+
+def conv_tc_weight_bytes(Cin, Cout, K):
+    return int(_lib_().b200_conv_tc_weight_bytes(Cin, Cout, K))
+
+
+def conv_tc_prep_weights(w, wprep, flip=False):
+    """fp32 OIHW weight -> the bf16 operand image of b200_conv_tc.  flip=True prepares the data-gradient convolution
+    (w stays the forward weight [Cout_fwd, Cin_fwd, K, K]; the call's Cin is Cout_fwd)."""
+    Co, Ci, K, _ = w.shape
+    cin, cout = (Co, Ci) if flip else (Ci, Co)
+    _lib.check(_lib_().b200_conv_tc_prep_weights(_ptr(w, F32), _ptr(wprep), cin, cout, K, 1 if flip else 0, _stream()), "conv_tc_prep_weights")
+
+
+def pack_act8(x, out):
+    """fp32 NCHW -> bf16 act8 [N, C/8, H, W, 8]"""
+    N, Cc, H, W = x.shape
+    _lib.check(_lib_().b200_pack_act8(_ptr(x, F32), _ptr(out, BF16), N, Cc, H, W, _stream()), "pack_act8")
+
+
+def conv_tc(x8, wprep, bias, out, stats, n_per_view, Cout, K, pad):
+    """x8: bf16 act8 [N, Cin/8, H, W, 8]; out: fp32 NCHW [N, Cout, Ho, Wo] or bf16 act8 [N, Cout/8, Ho, Wo, 8];
+    bias/stats may be None (data-gradient use)."""
+    N, P, H, W, _ = x8.shape
+    _lib.check(_lib_().b200_conv_tc(_ptr(x8, BF16), _ptr(wprep), _ptr(bias, F32) if bias is not None else None, _ptr(out),
+                                    _ptr(stats, F64) if stats is not None else None, N, n_per_view, P * 8, Cout, H, W, K, pad,
+                                    1 if out.dtype == BF16 else 0, _stream()), "conv_tc")
+
+
 def bn_finalize(stats, gamma, beta, running_mean, running_var, nbt, scale, shift, mean, invstd, n_views, count, train=True,
                 momentum=0.1, eps=1e-5):
     Cc = gamma.numel()
@@ -302,7 +337,7 @@ def bn1d_gelu_drop_bwd_apply(h, dg, scale, shift, mean, invstd, mask, drop_p, su
 # ---- launch accounting and optional per-op timing ------------------------------------------------------------
 # Every wrapper above issues a fixed number of kernel launches; the table lists the ones that issue more than one.
 _LAUNCHES = {"conv_bwd_weight": 3, "linear_bwd_weight": 3, "infonce_fwd_bwd": 9}
-_NOT_KERNELS = {"dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
+_NOT_KERNELS = {"conv_tc_supported", "conv_tc_weight_bytes", "dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
 LAUNCH_COUNT = 0
 _PROFILE = None          # None, or a list receiving (name, start_event, end_event, meta)
 
