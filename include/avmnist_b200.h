@@ -144,6 +144,11 @@ int64_t b200_conv_tc_weight_bytes(int Cin, int Cout, int K);
 int b200_conv_tc_prep_weights(const float* w, void* wprep, int Cin, int Cout, int K, int flip, void* stream);
 int b200_conv_tc(const void* x_act8, const void* wprep, const float* bias, void* out, double* stats, int N,
                  int n_per_view, int Cin, int Cout, int H, int W, int K, int pad, int out_bf16, void* stream);
+/* dw [Cout][Cin][K][K] = sum_n corr(x_n, dz_n), db [Cout] = sum dz (db may be NULL); x and dz bf16 act8, fp32 accumulate
+ * in TMEM; per-CTA partials in work (float[b200_conv_tc_wgrad_work_floats(...)]) reduced in a fixed order. */
+int64_t b200_conv_tc_wgrad_work_floats(int N, int Cin, int Cout, int H, int W, int K, int pad);
+int b200_conv_tc_wgrad(const void* x_act8, const void* dz_act8, float* dw, float* db, float* work, int N, int Cin,
+                       int Cout, int H, int W, int K, int pad, void* stream);
 /* fp32 NCHW -> bf16 act8 */
 int b200_pack_act8(const float* x, void* out, int N, int C, int H, int W, void* stream);
 /* dw = sum_n corr(x_n, dz_n), db = sum dz.  work: float[b200_conv_bwd_weight_work_floats(...)] */

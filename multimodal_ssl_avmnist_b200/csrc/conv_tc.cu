@@ -350,6 +350,236 @@ int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* ou
     return launch_status("conv_tc_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight gradient: dW[co][ci][kh][kw] = sum over samples and pixels of dz[co][q] * x[ci][q + kh*WP + kw].  The reduction
+// (GEMM K) dimension is the flat pixel index, so BOTH operands are MN-major views of act8 smem images (a 16-byte unit = 8
+// channels of one pixel; 8 consecutive pixels = the 8 K rows of a core matrix, LBO = 128 B to the next 8 pixels):
+//   A (M = 64): the x image of one channel plane; the 8 M units are 8 pixel shifts kw' = 0..7 (SBO = 16 B), start address
+//               moved by kh*WP pixels -> rows (kw', ci) of the accumulator, kw' < K are the real taps;
+//   B (N = C_out): the dz image, N units = channel planes (SBO = plane stride); dz is loaded with the PADDED pitch, its
+//               junk columns are TMA zero fill, so junk pixels contribute nothing.
+// One TMEM accumulator [64 x C_out] per (kh, x plane) lives for the whole kernel; a last accumulator multiplies dz by a
+// block of ones = the bias gradient.  Per-CTA partials go to `work`, reduced in a fixed order by wgrad_reduce_kernel.
+constexpr int hbz_for(int hb, int wp) {
+    int h = hb;
+    while ((h * wp) % 16) ++h;
+    return h;
+}
+
+template <int CIN_, int COUT_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int PSPLIT_>
+struct TcWgCfg {
+    static constexpr int CIN = CIN_, COUT = COUT_, HIN = HIN_, WIN = WIN_, KS = KS_, PAD = PAD_, BANDS = BANDS_, SLOTS = SLOTS_, PSPLIT = PSPLIT_;
+    static constexpr int P_IN = CIN / 8, P_OUT = COUT / 8, PI = P_IN / PSPLIT;
+    static constexpr int WP = WIN + 2 * PAD;
+    static constexpr int HO = HIN + 2 * PAD - KS + 1, WO = WP - KS + 1;
+    static constexpr int HB = HO / BANDS, HPB = HB + KS - 1;
+    static constexpr int HBZ = hbz_for(HB, WP);
+    static constexpr int KSTEPS = HBZ * WP / 16;
+    static constexpr int PLANE_X = HPB * WP * 16, PLANE_Z = HBZ * WP * 16;
+    static constexpr int X_BYTES = round_up(PI * PLANE_X, 128), Z_BYTES = round_up(P_OUT * PLANE_Z, 128);
+    static constexpr int SLOT_BYTES = X_BYTES + Z_BYTES;
+    static constexpr int NACC = KS * PI + 1;
+    static constexpr int TMEM_COLS = pow2_cols(NACC * COUT);
+    static constexpr int ONES_OFF = SLOTS * SLOT_BYTES;
+    static constexpr int BAR_OFF = ONES_OFF + 2048;
+    static constexpr int SMEM = BAR_OFF + 256;
+    static constexpr int DW = COUT * CIN * KS * KS;
+    static constexpr int PART = DW + COUT;                          // floats per CTA partial
+    static_assert(P_IN % PSPLIT == 0 && HO % BANDS == 0, "splits");
+    static_assert(BANDS == 1 || HBZ == HB, "row bands need HB*WP to be a multiple of 16");
+    static_assert(NACC * COUT <= 512, "TMEM columns");
+    static_assert(KS <= 8 && COUT % 8 == 0 && COUT >= 8 && COUT <= 256, "shape");
+    static_assert((KSTEPS * 16 + (KS - 1) * WP + 8 - HPB * WP) * 16 <= Z_BYTES, "x overrun must stay inside the slot");
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+template <class C>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_z, float* __restrict__ work, int N) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);     // full[SLOTS], empty[SLOTS], done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::BAR_OFF + 192);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = gridDim.x, g = blockIdx.x, split = blockIdx.z;
+    const long items = (long)N * C::BANDS;
+    const int i0 = (int)(items * g / G), i1 = (int)(items * (g + 1) / G);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (C::SLOTS + s); };
+    const uint32_t done_bar = bar0 + 8u * (2 * C::SLOTS);
+    {
+        uint4* z = reinterpret_cast<uint4*>(smem);
+        for (int i = threadIdx.x; i < C::ONES_OFF / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        uint32_t* o = reinterpret_cast<uint32_t*>(smem + C::ONES_OFF);
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) o[i] = 0x3F803F80u;      // bf16 1.0 pairs
+        fence_proxy_async_smem();
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        prefetch_tmap(&tmap_z);
+        for (int s = 0; s < C::SLOTS; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(done_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<C::TMEM_COLS>(smem_u32(tmem_slot));
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem0 = smem_u32(smem);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = i0; i < i1; ++i) {
+                const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
+                mbar_wait(empty_bar(slot), (use & 1) ^ 1);
+                mbar_expect_tx(full_bar(slot), C::PI * C::PLANE_X + C::P_OUT * C::PLANE_Z);
+                const int n = i / C::BANDS, band = i % C::BANDS;
+                const uint32_t sa = smem0 + slot * C::SLOT_BYTES;
+                tma_load_4d(sa, &tmap_x, full_bar(slot), 0, -C::PAD, band * C::HB - C::PAD, n * C::P_IN + split * C::PI);
+                tma_load_4d(sa + C::X_BYTES, &tmap_z, full_bar(slot), 0, 0, band * C::HB, n * C::P_OUT);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_bf16(C::COUT, true, true, 64);
+            const uint64_t ones_desc = smem_desc(smem0 + C::ONES_OFF, 1024, 128);
+            for (int i = i0; i < i1; ++i) {
+                const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
+                mbar_wait(full_bar(slot), use & 1);
+                tc_fence_after_sync();
+                const uint32_t xa = smem0 + slot * C::SLOT_BYTES, za = xa + C::X_BYTES;
+                for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                    const uint32_t acc = (i > i0 || ks > 0) ? 1u : 0u;
+                    const uint64_t bd = smem_desc(za + ks * 256, 128, C::PLANE_Z);
+#pragma unroll
+                    for (int kh = 0; kh < C::KS; ++kh) {
+#pragma unroll
+                        for (int pl = 0; pl < C::PI; ++pl) {
+                            const uint64_t ad = smem_desc(xa + pl * C::PLANE_X + (ks * 16 + kh * C::WP) * 16, 128, 16);
+                            mma_bf16(tmem_base + (kh * C::PI + pl) * C::COUT, ad, bd, idesc, acc);
+                        }
+                    }
+                    mma_bf16(tmem_base + (C::KS * C::PI) * C::COUT, ones_desc, bd, idesc, acc);
+                }
+                mma_commit(empty_bar(slot));
+            }
+            mma_commit(done_bar);
+        }
+    } else {
+        // epilogue: M = 64 accumulators occupy lanes 0-15 of each 32-lane quadrant: row m = quad*16 + lane
+        const int quad = warp & 3;
+        const int m = quad * 16 + (lane & 15), j = m >> 3, ci8 = m & 7;
+        const bool rowok = (lane < 16) && (j < C::KS);
+        float* part = work + (long)g * C::PART;
+        if (i1 > i0) {
+            mbar_wait(done_bar, 0);
+            tc_fence_after_sync();
+        }
+#pragma unroll 1
+        for (int a = 0; a <= C::KS * C::PI; ++a) {
+            const int kh = a / C::PI, pl = a % C::PI;
+            const bool is_bias = (a == C::KS * C::PI);
+#pragma unroll
+            for (int cc = 0; cc < (C::COUT + 15) / 16; ++cc) {
+                uint32_t v[16];
+                if (i1 > i0) {
+                    tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + a * C::COUT + cc * 16, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) v[t] = 0u;
+                }
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const int co = cc * 16 + t;
+                    if (co < C::COUT) {
+                        if (is_bias) {
+                            if (m == 0 && lane < 16 && split == 0) part[C::DW + co] = __uint_as_float(v[t]);
+                        } else if (rowok) {
+                            const int ci = (split * C::PI + pl) * 8 + ci8;
+                            part[((co * C::CIN + ci) * C::KS + kh) * C::KS + j] = __uint_as_float(v[t]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    }
+}
+
+// dw[e] (+)= sum over CTA partials in a fixed order (deterministic); the last COUT entries of a partial are the bias gradient
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ work, int n_parts, int part, int dw_n,
+                                                           float* __restrict__ dw, float* __restrict__ db) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= part) return;
+    float acc = 0.f;
+    for (int p = 0; p < n_parts; ++p) acc += work[(long)p * part + e];
+    if (e < dw_n) dw[e] = acc;
+    else if (db != nullptr) db[e - dw_n] = acc;
+}
+
+template <class C>
+int wgrad_ctas(int N) {
+    int G = sm_count() / C::PSPLIT;
+    const long items = (long)N * C::BANDS;
+    if (G > items) G = (int)items;
+    return G < 1 ? 1 : G;
+}
+
+template <class C>
+int launch_conv_tc_wgrad(const void* x, const void* dz, float* dw, float* db, float* work, int N, cudaStream_t st, int64_t* need) {
+    const int G = wgrad_ctas<C>(N);
+    if (need) {
+        *need = (int64_t)G * C::PART;
+        return 0;
+    }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) {
+            set_error("conv_tc_wgrad: cannot set %d bytes of shared memory: %s", C::SMEM, cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured = true;
+    }
+    CUtensorMap tx, tz;
+    {
+        const uint64_t dims[4] = {8, (uint64_t)C::WIN, (uint64_t)C::HIN, (uint64_t)N * C::P_IN};
+        const uint64_t strides[3] = {16, (uint64_t)C::WIN * 16, (uint64_t)C::WIN * C::HIN * 16};
+        const uint32_t box[4] = {8, (uint32_t)C::WP, (uint32_t)C::HPB, (uint32_t)C::PI};
+        int rc = encode_tmap_bf16_4d(&tx, x, dims, strides, box);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[4] = {8, (uint64_t)C::WO, (uint64_t)C::HO, (uint64_t)N * C::P_OUT};
+        const uint64_t strides[3] = {16, (uint64_t)C::WO * 16, (uint64_t)C::WO * C::HO * 16};
+        const uint32_t box[4] = {8, (uint32_t)C::WP, (uint32_t)C::HBZ, (uint32_t)C::P_OUT};
+        int rc = encode_tmap_bf16_4d(&tz, dz, dims, strides, box);
+        if (rc) return rc;
+    }
+    conv_tc_wgrad_kernel<C><<<dim3(G, 1, C::PSPLIT), 192, C::SMEM, st>>>(tx, tz, work, N);
+    int rc = launch_status("conv_tc_wgrad_kernel");
+    if (rc) return rc;
+    wgrad_reduce_kernel<<<(C::PART + 255) / 256, 256, 0, st>>>(work, G, C::PART, C::DW, dw, db);
+    return launch_status("wgrad_reduce_kernel");
+}
+
+//                           CIN COUT HIN WIN KS PAD BANDS SLOTS PSPLIT
+using WgA1 = TcWgCfg<8, 16, 56, 56, 5, 2, 2, 2, 1>;
+using WgA2 = TcWgCfg<16, 32, 28, 28, 5, 2, 1, 2, 1>;
+using WgA3 = TcWgCfg<32, 64, 14, 14, 5, 2, 1, 3, 4>;
+using WgI1 = TcWgCfg<32, 64, 14, 14, 5, 0, 1, 4, 4>;
+using WgS1 = TcWgCfg<32, 64, 14, 14, 3, 1, 1, 3, 2>;
+
 //                         CIN COUT NPAD HIN  WIN KS PAD BANDS SLOTS
 using CfgA1 = TcCfg<8, 16, 16, 56, 56, 5, 2, 2, 4>;      // audio conv2 forward
 using CfgA2 = TcCfg<16, 32, 32, 28, 28, 5, 2, 1, 4>;     // audio conv3 forward
@@ -392,6 +622,30 @@ int b200_conv_tc_prep_weights(const float* w, void* out, int Cin, int Cout, int 
     conv_tc_prep_weights_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(out), Cin, Cout, npad, K,
                                                                                       flip, total);
     return launch_status("conv_tc_prep_weights_kernel");
+}
+
+static int wgrad_tc_dispatch(const void* x, const void* dz, float* dw, float* db, float* work, int N, int Cin, int Cout, int H, int W,
+                             int K, int pad, cudaStream_t st, int64_t* need) {
+#define WG_RUN(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) \
+        return launch_conv_tc_wgrad<CFG>(x, dz, dw, db, work, N, st, need);
+    WG_RUN(WgA1) WG_RUN(WgA2) WG_RUN(WgA3) WG_RUN(WgI1) WG_RUN(WgS1)
+#undef WG_RUN
+    set_error("conv_tc_wgrad: unsupported geometry Cin=%d Cout=%d H=%d W=%d K=%d pad=%d", Cin, Cout, H, W, K, pad);
+    return -4;
+}
+
+int64_t b200_conv_tc_wgrad_work_floats(int N, int Cin, int Cout, int H, int W, int K, int pad) {
+    int64_t need = 0;
+    int rc = wgrad_tc_dispatch(nullptr, nullptr, nullptr, nullptr, nullptr, N, Cin, Cout, H, W, K, pad, nullptr, &need);
+    return rc ? -1 : need;
+}
+
+int b200_conv_tc_wgrad(const void* x_act8, const void* dz_act8, float* dw, float* db, float* work, int N, int Cin, int Cout, int H, int W,
+                       int K, int pad, void* stream) {
+    B200_REQUIRE(x_act8 && dz_act8 && dw && work, -1, "conv_tc_wgrad: null pointer");
+    B200_REQUIRE(N > 0, -2, "conv_tc_wgrad: N must be positive");
+    B200_REQUIRE(((uintptr_t)x_act8 & 15) == 0 && ((uintptr_t)dz_act8 & 15) == 0, -3, "conv_tc_wgrad: pointers must be 16-byte aligned");
+    return wgrad_tc_dispatch(x_act8, dz_act8, dw, db, work, N, Cin, Cout, H, W, K, pad, as_stream(stream), nullptr);
 }
 
 int b200_pack_act8(const float* x, void* out, int N, int C, int H, int W, void* stream) {

@@ -220,6 +220,21 @@ def conv_tc(x8, wprep, bias, out, stats, n_per_view, Cout, K, pad):
                                     1 if out.dtype == BF16 else 0, _stream()), "conv_tc")
 
 
+def conv_tc_wgrad_work_floats(N, Cin, Cout, H, W, K, pad):
+    n = int(_lib_().b200_conv_tc_wgrad_work_floats(N, Cin, Cout, H, W, K, pad))
+    if n < 0:
+        raise _lib.B200Error(f"conv_tc_wgrad: unsupported geometry {(Cin, Cout, H, W, K, pad)}")
+    return n
+
+
+def conv_tc_wgrad(x8, dz8, dw, db, work, pad):
+    """x8 [N, Cin/8, H, W, 8], dz8 [N, Cout/8, Ho, Wo, 8] bf16 act8 -> dw [Cout, Cin, K, K], db [Cout] (fp32)."""
+    N, P, H, W, _ = x8.shape
+    Cout, Cin, K, _ = dw.shape
+    _lib.check(_lib_().b200_conv_tc_wgrad(_ptr(x8, BF16), _ptr(dz8, BF16), _ptr(dw, F32), _ptr(db, F32) if db is not None else None,
+                                          _ptr(work, F32), N, Cin, Cout, H, W, K, pad, _stream()), "conv_tc_wgrad")
+
+
 def bn_finalize(stats, gamma, beta, running_mean, running_var, nbt, scale, shift, mean, invstd, n_views, count, train=True,
                 momentum=0.1, eps=1e-5):
     Cc = gamma.numel()
@@ -336,8 +351,8 @@ def bn1d_gelu_drop_bwd_apply(h, dg, scale, shift, mean, invstd, mask, drop_p, su
 
 # ---- launch accounting and optional per-op timing ------------------------------------------------------------
 # Every wrapper above issues a fixed number of kernel launches; the table lists the ones that issue more than one.
-_LAUNCHES = {"conv_bwd_weight": 3, "linear_bwd_weight": 3, "infonce_fwd_bwd": 9}
-_NOT_KERNELS = {"conv_tc_supported", "conv_tc_weight_bytes", "dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
+_LAUNCHES = {"conv_tc_wgrad": 2, "conv_bwd_weight": 3, "linear_bwd_weight": 3, "infonce_fwd_bwd": 9}
+_NOT_KERNELS = {"conv_tc_wgrad_work_floats", "conv_tc_supported", "conv_tc_weight_bytes", "dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
 LAUNCH_COUNT = 0
 _PROFILE = None          # None, or a list receiving (name, start_event, end_event, meta)
 

@@ -84,3 +84,32 @@ def test_conv_tc_data_gradient(geom):
     torch.cuda.synchronize()
     err = float((out - want).abs().max())
     assert err <= 2e-5 * float(want.abs().max()), (geom, err)
+
+
+@pytest.mark.parametrize("geom", FWD)
+@pytest.mark.parametrize("N", [1, 7, 300])
+def test_conv_tc_weight_gradient(geom, N):
+    """dW, db against autograd in fp64 on the same bf16-rounded x and dz (K = N*pixels, fp32 accumulate in TMEM)."""
+    Cin, Cout, H, W, K, pad = geom
+    Ho = H + 2 * pad - K + 1
+    g = torch.Generator().manual_seed(11 + Cin + N)
+    x = torch.randn(N, Cin, H, W, generator=g).to(DEV)
+    dz = torch.randn(N, Cout, Ho, Ho, generator=g).to(DEV)
+    xd = _bf(x).double().requires_grad_(False)
+    wd = torch.zeros(Cout, Cin, K, K, dtype=torch.float64, device=DEV, requires_grad=True)
+    bd = torch.zeros(Cout, dtype=torch.float64, device=DEV, requires_grad=True)
+    F.conv2d(xd, wd, bd, padding=pad).backward(_bf(dz).double())
+    x8 = torch.empty(N, Cin // 8, H, W, 8, dtype=torch.bfloat16, device=DEV)
+    dz8 = torch.empty(N, Cout // 8, Ho, Ho, 8, dtype=torch.bfloat16, device=DEV)
+    ops.pack_act8(x, x8)
+    ops.pack_act8(dz, dz8)
+    work = torch.empty(ops.conv_tc_wgrad_work_floats(N, Cin, Cout, H, W, K, pad), device=DEV)
+    dw = torch.full((Cout, Cin, K, K), float("nan"), device=DEV)
+    db = torch.full((Cout,), float("nan"), device=DEV)
+    ops.conv_tc_wgrad(x8, dz8, dw, db, work, pad)
+    torch.cuda.synchronize()
+    scale = float(wd.grad.abs().max())
+    err = float((dw.double() - wd.grad).abs().max())
+    assert err <= 3e-5 * scale, (geom, N, err, scale)
+    errb = float((db.double() - bd.grad).abs().max())
+    assert errb <= 3e-5 * float(bd.grad.abs().max()), (geom, N, errb)
