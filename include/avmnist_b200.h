@@ -149,6 +149,20 @@ int b200_conv_tc(const void* x_act8, const void* wprep, const float* bias, void*
 int64_t b200_conv_tc_wgrad_work_floats(int N, int Cin, int Cout, int H, int W, int K, int pad);
 int b200_conv_tc_wgrad(const void* x_act8, const void* dz_act8, float* dw, float* db, float* work, int N, int Cin,
                        int Cout, int H, int W, int K, int pad, void* stream);
+/* BatchNorm-apply + ReLU + MaxPool2 on bf16 act8 activations (same reference call sites as b200_bn_relu_pool_*):
+ *   z8 [N][C/8][H][W][8] bf16 (H, W even); scale/shift/mean/invstd [views][C] from b200_bn_finalize;
+ *   out_fmt / dp_fmt: 0 = fp32 NCHW [N][C][H/2][W/2], 1 = bf16 act8 [N][C/8][H/2][W/2][8];
+ *   sums: double [views][C][2] = {sum g, sum g*xhat} (zeroed by the caller before _bwd_reduce); dz8: bf16 act8 like z8. */
+int b200_bn_relu_pool8_fwd(const void* z8, const float* scale, const float* shift, void* out, int N, int n_per_view,
+                           int C, int H, int W, int out_fmt, void* stream);
+int b200_bn_relu_pool8_bwd_reduce(const void* z8, const void* dp, const float* scale, const float* shift,
+                                  const float* mean, const float* invstd, double* sums, int N, int n_per_view, int C,
+                                  int H, int W, int dp_fmt, void* stream);
+int b200_bn_relu_pool8_bwd_apply(const void* z8, const void* dp, const float* scale, const float* shift,
+                                 const float* mean, const float* invstd, const double* sums, void* dz8, int N,
+                                 int n_per_view, int C, int H, int W, int dp_fmt, void* stream);
+/* bf16 act8 -> fp32 NCHW */
+int b200_unpack_act8(const void* x8, float* out, int N, int C, int H, int W, void* stream);
 /* fp32 NCHW -> bf16 act8 */
 int b200_pack_act8(const float* x, void* out, int N, int C, int H, int W, void* stream);
 /* dw = sum_n corr(x_n, dz_n), db = sum dz.  work: float[b200_conv_bwd_weight_work_floats(...)] */

@@ -1,0 +1,259 @@
+// BatchNorm(train)-apply + ReLU + 2x2 max-pool, forward and backward, on bf16 "act8" activations
+// [N][C/8][H][W][8] (the layout the tensor-core convolutions of conv_tc.cu read and write).
+// Reference: the BN -> ReLU -> MaxPool2 triplets of models/unimodal.py:130-140, 187-208 and models/dino.py:21-33.
+//
+// One thread owns one pooled pixel of one channel octet: four 16-byte loads of the 2x2 window (two per row, adjacent),
+// all 8 channels in registers, one 16-byte store -- every access is a full, coalesced 16-byte unit.  A block works on
+// one (view-call, octet) pair, so the 8 (scale, shift, mean, invstd) tuples are block-uniform and the backward
+// reductions are per-thread registers -> warp shuffles -> one double atomicAdd per block and channel.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace b200 {
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xFFFF0000u);
+    f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xFFFF0000u);
+    f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xFFFF0000u);
+    f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xFFFF0000u);
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+}
+
+struct Tile {      // work split: grid (chunks, octets, views)
+    int n_per_view, C, H, W, HP, WP, P;
+    long u0, u1;   // unit range [u0, u1) of this block inside its (view, octet): unit = sample_in_view * HP*WP + pooled pixel
+};
+__device__ __forceinline__ Tile make_tile(int n_per_view, int C, int H, int W) {
+    Tile t;
+    t.n_per_view = n_per_view; t.C = C; t.H = H; t.W = W; t.HP = H >> 1; t.WP = W >> 1; t.P = C >> 3;
+    const long units = (long)n_per_view * t.HP * t.WP;
+    t.u0 = units * blockIdx.x / gridDim.x;
+    t.u1 = units * (blockIdx.x + 1) / gridDim.x;
+    return t;
+}
+
+// out_fmt 0: fp32 NCHW [N][C][HP][WP]; 1: bf16 act8 [N][C/8][HP][WP][8]
+__global__ void __launch_bounds__(256) bn_relu_pool8_fwd_kernel(const uint4* __restrict__ z8, const float* __restrict__ scale,
+                                                                const float* __restrict__ shift, void* __restrict__ out, int n_per_view,
+                                                                int C, int H, int W, int out_fmt) {
+    const Tile t = make_tile(n_per_view, C, H, W);
+    const int oct = blockIdx.y, v = blockIdx.z;
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        a[j] = __ldg(scale + v * C + oct * 8 + j);
+        b[j] = __ldg(shift + v * C + oct * 8 + j);
+    }
+    const int hw = t.HP * t.WP;
+    for (long u = t.u0 + threadIdx.x; u < t.u1; u += blockDim.x) {
+        const int s = (int)(u / hw), e = (int)(u - (long)s * hw);
+        const int py = e / t.WP, px = e - py * t.WP;
+        const long n = (long)v * n_per_view + s;
+        const uint4* zp = z8 + ((n * t.P + oct) * H + 2 * py) * W + 2 * px;
+        float w0[8], w1[8], w2[8], w3[8], m[8];
+        unpack8(__ldg(zp), w0);
+        unpack8(__ldg(zp + 1), w1);
+        unpack8(__ldg(zp + W), w2);
+        unpack8(__ldg(zp + W + 1), w3);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float y = fmaxf(fmaxf(fmaf(a[j], w0[j], b[j]), fmaf(a[j], w1[j], b[j])), fmaxf(fmaf(a[j], w2[j], b[j]), fmaf(a[j], w3[j], b[j])));
+            m[j] = fmaxf(y, 0.f);
+        }
+        if (out_fmt) {
+            reinterpret_cast<uint4*>(out)[((n * t.P + oct) * t.HP + py) * t.WP + px] = pack8(m);
+        } else {
+            float* op = reinterpret_cast<float*>(out) + ((n * C + oct * 8) * t.HP + py) * t.WP + px;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[(long)j * hw] = m[j];
+        }
+    }
+}
+
+// argmax in PyTorch scan order (first maximum wins)
+__device__ __forceinline__ int argmax4(float y0, float y1, float y2, float y3, float& m) {
+    int k = 0;
+    m = y0;
+    if (y1 > m) { m = y1; k = 1; }
+    if (y2 > m) { m = y2; k = 2; }
+    if (y3 > m) { m = y3; k = 3; }
+    return k;
+}
+
+// dp_fmt 0: fp32 NCHW [N][C][HP][WP]; 1: bf16 act8.  APPLY = false: sums[view][c] += {sum g, sum g*xhat};
+// APPLY = true: dz8 = a*(g_at_argmax - mean(g) - xhat*mean(g*xhat)) for all four window positions.
+template <bool APPLY>
+__global__ void __launch_bounds__(256) bn_relu_pool8_bwd_kernel(const uint4* __restrict__ z8, const void* __restrict__ dp,
+                                                                const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                double* __restrict__ sums, uint4* __restrict__ dz8, int n_per_view, int C, int H,
+                                                                int W, int dp_fmt) {
+    const Tile t = make_tile(n_per_view, C, H, W);
+    const int oct = blockIdx.y, v = blockIdx.z;
+    float a[8], b[8], mu[8], is[8], k1[8], k2[8], s1[8], s2[8];
+    const float inv_cnt = 1.0f / ((float)n_per_view * (float)H * (float)W);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = v * C + oct * 8 + j;
+        a[j] = __ldg(scale + c); b[j] = __ldg(shift + c); mu[j] = __ldg(mean + c); is[j] = __ldg(invstd + c);
+        s1[j] = s2[j] = 0.f;
+        if (APPLY) {
+            k1[j] = (float)sums[(size_t)c * 2] * inv_cnt;
+            k2[j] = (float)sums[(size_t)c * 2 + 1] * inv_cnt;
+        }
+    }
+    const int hw = t.HP * t.WP;
+    for (long u = t.u0 + threadIdx.x; u < t.u1; u += blockDim.x) {
+        const int s = (int)(u / hw), e = (int)(u - (long)s * hw);
+        const int py = e / t.WP, px = e - py * t.WP;
+        const long n = (long)v * n_per_view + s;
+        const long zoff = ((n * t.P + oct) * H + 2 * py) * W + 2 * px;
+        const uint4* zp = z8 + zoff;
+        float w[4][8], g[8];
+        unpack8(__ldg(zp), w[0]);
+        unpack8(__ldg(zp + 1), w[1]);
+        unpack8(__ldg(zp + W), w[2]);
+        unpack8(__ldg(zp + W + 1), w[3]);
+        if (dp_fmt) {
+            unpack8(__ldg(reinterpret_cast<const uint4*>(dp) + ((n * t.P + oct) * t.HP + py) * t.WP + px), g);
+        } else {
+            const float* gp = reinterpret_cast<const float*>(dp) + ((n * C + oct * 8) * t.HP + py) * t.WP + px;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = __ldg(gp + (long)j * hw);
+        }
+        float o[4][8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float m;
+            const int k = argmax4(fmaf(a[j], w[0][j], b[j]), fmaf(a[j], w[1][j], b[j]), fmaf(a[j], w[2][j], b[j]), fmaf(a[j], w[3][j], b[j]), m);
+            const float gj = (m > 0.f) ? g[j] : 0.f;
+            if (!APPLY) {
+                const float zk = (k == 0) ? w[0][j] : (k == 1) ? w[1][j] : (k == 2) ? w[2][j] : w[3][j];
+                s1[j] += gj;
+                s2[j] += gj * ((zk - mu[j]) * is[j]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float xh = (w[q][j] - mu[j]) * is[j];
+                    o[q][j] = a[j] * (((q == k) ? gj : 0.f) - k1[j] - xh * k2[j]);
+                }
+            }
+        }
+        if (APPLY) {
+            uint4* zo = dz8 + zoff;
+            zo[0] = pack8(o[0]);
+            zo[1] = pack8(o[1]);
+            zo[W] = pack8(o[2]);
+            zo[W + 1] = pack8(o[3]);
+        }
+    }
+    if (!APPLY) {
+        __shared__ float red[8][16];
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float x1 = warp_sum(s1[j]), x2 = warp_sum(s2[j]);
+            if (lane == 0) {
+                red[warp][j] = x1;
+                red[warp][8 + j] = x2;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 16) {
+            double acc = 0.0;
+            for (int wv = 0; wv < 8; ++wv) acc += (double)red[wv][threadIdx.x];
+            const int j = threadIdx.x & 7, which = threadIdx.x >> 3;
+            atomicAdd(&sums[((size_t)v * C + oct * 8 + j) * 2 + which], acc);
+        }
+    }
+}
+
+// bf16 act8 -> fp32 NCHW (tests / debugging)
+__global__ void unpack_act8_kernel(const uint4* __restrict__ x8, float* __restrict__ out, long n_units, int C, int HW) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_units) return;
+    const int pix = (int)(i % HW);
+    const long no = i / HW;
+    const int oct = (int)(no % (C / 8));
+    const long n = no / (C / 8);
+    float f[8];
+    unpack8(__ldg(x8 + i), f);
+    float* o = out + ((n * C + oct * 8) * (long)HW) + pix;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[(long)j * HW] = f[j];
+}
+
+dim3 tile_grid(int N, int n_per_view, int C, int H, int W) {
+    const int views = N / n_per_view, P = C / 8;
+    const long units = (long)n_per_view * (H / 2) * (W / 2);
+    long chunks = (8L * sm_count() + (long)views * P - 1) / ((long)views * P);
+    const long max_chunks = (units + 255) / 256;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    return dim3((unsigned)chunks, (unsigned)P, (unsigned)views);
+}
+
+int check_shape(const char* what, int N, int n_per_view, int C, int H, int W) {
+    B200_REQUIRE(N > 0 && n_per_view > 0 && N % n_per_view == 0, -2, "%s: N=%d must be a multiple of n_per_view=%d", what, N, n_per_view);
+    B200_REQUIRE(C % 8 == 0 && C > 0, -2, "%s: C=%d must be a multiple of 8", what, C);
+    B200_REQUIRE((H & 1) == 0 && (W & 1) == 0 && H > 0 && W > 0, -2, "%s: H=%d, W=%d must be even", what, H, W);
+    B200_REQUIRE(N / n_per_view <= 65535, -2, "%s: too many view-calls", what);
+    return 0;
+}
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_bn_relu_pool8_fwd(const void* z8, const float* scale, const float* shift, void* out, int N, int n_per_view, int C, int H, int W,
+                           int out_fmt, void* stream) {
+    B200_REQUIRE(z8 && scale && shift && out, -1, "bn_relu_pool8_fwd: null pointer");
+    int rc = check_shape("bn_relu_pool8_fwd", N, n_per_view, C, H, W);
+    if (rc) return rc;
+    bn_relu_pool8_fwd_kernel<<<tile_grid(N, n_per_view, C, H, W), 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(z8), scale, shift, out,
+                                                                                               n_per_view, C, H, W, out_fmt);
+    return launch_status("bn_relu_pool8_fwd_kernel");
+}
+
+int b200_bn_relu_pool8_bwd_reduce(const void* z8, const void* dp, const float* scale, const float* shift, const float* mean,
+                                  const float* invstd, double* sums, int N, int n_per_view, int C, int H, int W, int dp_fmt, void* stream) {
+    B200_REQUIRE(z8 && dp && scale && shift && mean && invstd && sums, -1, "bn_relu_pool8_bwd_reduce: null pointer");
+    int rc = check_shape("bn_relu_pool8_bwd_reduce", N, n_per_view, C, H, W);
+    if (rc) return rc;
+    bn_relu_pool8_bwd_kernel<false><<<tile_grid(N, n_per_view, C, H, W), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const uint4*>(z8), dp, scale, shift, mean, invstd, sums, nullptr, n_per_view, C, H, W, dp_fmt);
+    return launch_status("bn_relu_pool8_bwd_kernel<reduce>");
+}
+
+int b200_bn_relu_pool8_bwd_apply(const void* z8, const void* dp, const float* scale, const float* shift, const float* mean,
+                                 const float* invstd, const double* sums, void* dz8, int N, int n_per_view, int C, int H, int W, int dp_fmt,
+                                 void* stream) {
+    B200_REQUIRE(z8 && dp && scale && shift && mean && invstd && sums && dz8, -1, "bn_relu_pool8_bwd_apply: null pointer");
+    int rc = check_shape("bn_relu_pool8_bwd_apply", N, n_per_view, C, H, W);
+    if (rc) return rc;
+    bn_relu_pool8_bwd_kernel<true><<<tile_grid(N, n_per_view, C, H, W), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const uint4*>(z8), dp, scale, shift, mean, invstd, const_cast<double*>(sums), reinterpret_cast<uint4*>(dz8), n_per_view, C,
+        H, W, dp_fmt);
+    return launch_status("bn_relu_pool8_bwd_kernel<apply>");
+}
+
+int b200_unpack_act8(const void* x8, float* out, int N, int C, int H, int W, void* stream) {
+    B200_REQUIRE(x8 && out, -1, "unpack_act8: null pointer");
+    B200_REQUIRE(C % 8 == 0 && N > 0, -2, "unpack_act8: C must be a multiple of 8");
+    const long units = (long)N * (C / 8) * H * W;
+    unpack_act8_kernel<<<(unsigned)((units + 255) / 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(x8), out, units, C, H * W);
+    return launch_status("unpack_act8_kernel");
+}
+
+}  // extern "C"

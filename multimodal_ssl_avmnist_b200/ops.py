@@ -235,6 +235,36 @@ def conv_tc_wgrad(x8, dz8, dw, db, work, pad):
                                           _ptr(work, F32), N, Cin, Cout, H, W, K, pad, _stream()), "conv_tc_wgrad")
 
 
+def unpack_act8(x8, out):
+    N, P, H, W, _ = x8.shape
+    _lib.check(_lib_().b200_unpack_act8(_ptr(x8, BF16), _ptr(out, F32), N, P * 8, H, W, _stream()), "unpack_act8")
+
+
+def _fmt(t):
+    return 1 if t.dtype == BF16 else 0
+
+
+def bn_relu_pool8_fwd(z8, scale, shift, out, n_per_view):
+    """z8 bf16 act8 [N, C/8, H, W, 8] -> out: fp32 NCHW [N, C, H/2, W/2] or bf16 act8 [N, C/8, H/2, W/2, 8] (by dtype)."""
+    N, P, H, W, _ = z8.shape
+    _lib.check(_lib_().b200_bn_relu_pool8_fwd(_ptr(z8, BF16), _ptr(scale, F32), _ptr(shift, F32), _ptr(out), N, n_per_view, P * 8, H, W,
+                                              _fmt(out), _stream()), "bn_relu_pool8_fwd")
+
+
+def bn_relu_pool8_bwd_reduce(z8, dp, scale, shift, mean, invstd, sums, n_per_view):
+    N, P, H, W, _ = z8.shape
+    _lib.check(_lib_().b200_bn_relu_pool8_bwd_reduce(_ptr(z8, BF16), _ptr(dp), _ptr(scale, F32), _ptr(shift, F32), _ptr(mean, F32),
+                                                     _ptr(invstd, F32), _ptr(sums, F64), N, n_per_view, P * 8, H, W, _fmt(dp), _stream()),
+               "bn_relu_pool8_bwd_reduce")
+
+
+def bn_relu_pool8_bwd_apply(z8, dp, scale, shift, mean, invstd, sums, dz8, n_per_view):
+    N, P, H, W, _ = z8.shape
+    _lib.check(_lib_().b200_bn_relu_pool8_bwd_apply(_ptr(z8, BF16), _ptr(dp), _ptr(scale, F32), _ptr(shift, F32), _ptr(mean, F32),
+                                                    _ptr(invstd, F32), _ptr(sums, F64), _ptr(dz8, BF16), N, n_per_view, P * 8, H, W, _fmt(dp),
+                                                    _stream()), "bn_relu_pool8_bwd_apply")
+
+
 def bn_finalize(stats, gamma, beta, running_mean, running_var, nbt, scale, shift, mean, invstd, n_views, count, train=True,
                 momentum=0.1, eps=1e-5):
     Cc = gamma.numel()

@@ -113,3 +113,58 @@ def test_conv_tc_weight_gradient(geom, N):
     assert err <= 3e-5 * scale, (geom, N, err, scale)
     errb = float((db.double() - bd.grad).abs().max())
     assert errb <= 3e-5 * float(bd.grad.abs().max()), (geom, N, errb)
+
+
+def _pack8(x):
+    N, C, H, W = x.shape
+    out = torch.empty(N, C // 8, H, W, 8, dtype=torch.bfloat16, device=DEV)
+    ops.pack_act8(x.contiguous(), out)
+    return out
+
+
+@pytest.mark.parametrize("C,H,views,B", [(16, 56, 2, 3), (32, 28, 3, 5), (64, 14, 7, 9), (64, 10, 1, 40), (8, 112, 2, 2)])
+def test_bn_relu_pool8(C, H, views, B):
+    """act8 BN-apply/ReLU/pool forward and backward against a torch fp32 restatement on the same bf16 z / dp."""
+    g = torch.Generator().manual_seed(C + H)
+    N = views * B
+    z = _bf(torch.randn(N, C, H, H, generator=g)).to(DEV)
+    scale = (torch.randn(views, C, generator=g) * 0.5 + 1.0).to(DEV)       # includes negative gammas
+    shift = (torch.randn(views, C, generator=g) * 0.3).to(DEV)
+    mean = (torch.randn(views, C, generator=g) * 0.2).to(DEV)
+    invstd = (torch.rand(views, C, generator=g) + 0.5).to(DEV)
+    dp = _bf(torch.randn(N, C, H // 2, H // 2, generator=g)).to(DEV)
+    z8 = _pack8(z)
+    a = scale.repeat_interleave(B, 0)[:, :, None, None]
+    b = shift.repeat_interleave(B, 0)[:, :, None, None]
+    mu = mean.repeat_interleave(B, 0)[:, :, None, None]
+    istd = invstd.repeat_interleave(B, 0)[:, :, None, None]
+    y = a * z + b
+    pooled, idx = F.max_pool2d(y, 2, return_indices=True)
+    want_p = pooled.clamp_min(0)
+    # forward, both output formats
+    out32 = torch.full((N, C, H // 2, H // 2), float("nan"), device=DEV)
+    ops.bn_relu_pool8_fwd(z8, scale, shift, out32, B)
+    assert float((out32 - want_p).abs().max()) <= 1e-5 * float(want_p.abs().max())
+    out8 = torch.empty(N, C // 8, H // 2, H // 2, 8, dtype=torch.bfloat16, device=DEV)
+    ops.bn_relu_pool8_fwd(z8, scale, shift, out8, B)
+    assert torch.equal(_unpack8(out8), _bf(out32))
+    chk = torch.empty_like(out32)
+    ops.unpack_act8(out8, chk)
+    assert torch.equal(chk, _bf(out32))
+    # backward
+    gsel = dp * (pooled > 0)
+    dy = F.max_unpool2d(gsel, idx, 2, output_size=(H, H))
+    xh = (z - mu) * istd
+    s_want = torch.stack([dy.view(views, B, C, -1).double().sum(dim=(1, 3)), (dy * xh).view(views, B, C, -1).double().sum(dim=(1, 3))], -1)
+    cnt = B * H * H
+    k1 = (s_want[..., 0] / cnt).float().repeat_interleave(B, 0)[:, :, None, None]
+    k2 = (s_want[..., 1] / cnt).float().repeat_interleave(B, 0)[:, :, None, None]
+    want_dz = a * (dy - k1 - xh * k2)
+    for dpt in (dp, _pack8(dp)):
+        sums = torch.zeros(views, C, 2, dtype=torch.float64, device=DEV)
+        ops.bn_relu_pool8_bwd_reduce(z8, dpt, scale, shift, mean, invstd, sums, B)
+        assert float(((sums - s_want).abs() / (s_want.abs() + 1.0)).max()) < 1e-5
+        dz8 = torch.empty_like(z8)
+        ops.bn_relu_pool8_bwd_apply(z8, dpt, scale, shift, mean, invstd, s_want.contiguous(), dz8, B)
+        got = _unpack8(dz8)
+        assert float((got - want_dz).abs().max()) <= 8e-3 * float(want_dz.abs().max())
