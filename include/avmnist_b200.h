@@ -135,7 +135,7 @@ int b200_conv_bwd_data(const float* dz, const float* w, float* dx, int N, int Ci
 /* ---- tensor-core path (tcgen05 + TMEM + TMA) for the C_in >= 8 convolutions: same call sites as above ----
  * Activations are bf16 in the "act8" layout [N][C/8][H][W][8] (channel octets are planes; a pixel of a plane is one
  * 16-byte unit); accumulation is fp32.  b200_conv_tc computes z = conv(x, w) (+ bias and the BatchNorm partial
- * statistics when bias != NULL) and writes either fp32 NCHW (out_bf16 = 0) or bf16 act8 (out_bf16 = 1).  The data
+ * statistics when bias != NULL) and writes fp32 NCHW (out_bf16 = 0), bf16 act8 (1) or fp16 act8 (2).  The data
  * gradient of a convolution is the same call with (Cin, Cout) swapped, pad' = K-1-pad, H/W those of dz, and weights
  * prepared with flip = 1.  wprep: b200_conv_tc_weight_bytes(Cin, Cout, K) bytes filled by b200_conv_tc_prep_weights
  * from the fp32 OIHW weight (for flip = 1: `w` is the FORWARD weight [Cin][Cout][K][K]). */
@@ -150,17 +150,17 @@ int64_t b200_conv_tc_wgrad_work_floats(int N, int Cin, int Cout, int H, int W, i
 int b200_conv_tc_wgrad(const void* x_act8, const void* dz_act8, float* dw, float* db, float* work, int N, int Cin,
                        int Cout, int H, int W, int K, int pad, void* stream);
 /* BatchNorm-apply + ReLU + MaxPool2 on bf16 act8 activations (same reference call sites as b200_bn_relu_pool_*):
- *   z8 [N][C/8][H][W][8] bf16 (H, W even); scale/shift/mean/invstd [views][C] from b200_bn_finalize;
+ *   z8 [N][C/8][H][W][8] bf16 (z_f16 = 0) or fp16 (z_f16 = 1) (H, W even); scale/shift/mean/invstd [views][C] from b200_bn_finalize;
  *   out_fmt / dp_fmt: 0 = fp32 NCHW [N][C][H/2][W/2], 1 = bf16 act8 [N][C/8][H/2][W/2][8];
  *   sums: double [views][C][2] = {sum g, sum g*xhat} (zeroed by the caller before _bwd_reduce); dz8: bf16 act8 like z8. */
 int b200_bn_relu_pool8_fwd(const void* z8, const float* scale, const float* shift, void* out, int N, int n_per_view,
-                           int C, int H, int W, int out_fmt, void* stream);
+                           int C, int H, int W, int z_f16, int out_fmt, void* stream);
 int b200_bn_relu_pool8_bwd_reduce(const void* z8, const void* dp, const float* scale, const float* shift,
                                   const float* mean, const float* invstd, double* sums, int N, int n_per_view, int C,
-                                  int H, int W, int dp_fmt, void* stream);
+                                  int H, int W, int z_f16, int dp_fmt, void* stream);
 int b200_bn_relu_pool8_bwd_apply(const void* z8, const void* dp, const float* scale, const float* shift,
                                  const float* mean, const float* invstd, const double* sums, void* dz8, int N,
-                                 int n_per_view, int C, int H, int W, int dp_fmt, void* stream);
+                                 int n_per_view, int C, int H, int W, int z_f16, int dp_fmt, void* stream);
 /* bf16 act8 -> fp32 NCHW */
 int b200_unpack_act8(const void* x8, float* out, int N, int C, int H, int W, void* stream);
 /* fp32 NCHW -> bf16 act8 */

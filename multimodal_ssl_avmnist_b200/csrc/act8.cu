@@ -7,6 +7,7 @@
 // one (view-call, octet) pair, so the 8 (scale, shift, mean, invstd) tuples are block-uniform and the backward
 // reductions are per-thread registers -> warp shuffles -> one double atomicAdd per block and channel.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -18,6 +19,20 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xFFFF0000u);
     f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xFFFF0000u);
     f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xFFFF0000u);
+}
+__device__ __forceinline__ void unpack8h(const uint4& u, float (&f)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 v = __half22float2(h[i]);
+        f[2 * i] = v.x;
+        f[2 * i + 1] = v.y;
+    }
+}
+template <bool F16>
+__device__ __forceinline__ void unpackz(const uint4& u, float (&f)[8]) {
+    if (F16) unpack8h(u, f);
+    else unpack8(u, f);
 }
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -41,6 +56,7 @@ __device__ __forceinline__ Tile make_tile(int n_per_view, int C, int H, int W) {
 }
 
 // out_fmt 0: fp32 NCHW [N][C][HP][WP]; 1: bf16 act8 [N][C/8][HP][WP][8]
+template <bool ZF16>
 __global__ void __launch_bounds__(256) bn_relu_pool8_fwd_kernel(const uint4* __restrict__ z8, const float* __restrict__ scale,
                                                                 const float* __restrict__ shift, void* __restrict__ out, int n_per_view,
                                                                 int C, int H, int W, int out_fmt) {
@@ -59,10 +75,10 @@ __global__ void __launch_bounds__(256) bn_relu_pool8_fwd_kernel(const uint4* __r
         const long n = (long)v * n_per_view + s;
         const uint4* zp = z8 + ((n * t.P + oct) * H + 2 * py) * W + 2 * px;
         float w0[8], w1[8], w2[8], w3[8], m[8];
-        unpack8(__ldg(zp), w0);
-        unpack8(__ldg(zp + 1), w1);
-        unpack8(__ldg(zp + W), w2);
-        unpack8(__ldg(zp + W + 1), w3);
+        unpackz<ZF16>(__ldg(zp), w0);
+        unpackz<ZF16>(__ldg(zp + 1), w1);
+        unpackz<ZF16>(__ldg(zp + W), w2);
+        unpackz<ZF16>(__ldg(zp + W + 1), w3);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float y = fmaxf(fmaxf(fmaf(a[j], w0[j], b[j]), fmaf(a[j], w1[j], b[j])), fmaxf(fmaf(a[j], w2[j], b[j]), fmaf(a[j], w3[j], b[j])));
@@ -90,7 +106,7 @@ __device__ __forceinline__ int argmax4(float y0, float y1, float y2, float y3, f
 
 // dp_fmt 0: fp32 NCHW [N][C][HP][WP]; 1: bf16 act8.  APPLY = false: sums[view][c] += {sum g, sum g*xhat};
 // APPLY = true: dz8 = a*(g_at_argmax - mean(g) - xhat*mean(g*xhat)) for all four window positions.
-template <bool APPLY>
+template <bool APPLY, bool ZF16>
 __global__ void __launch_bounds__(256) bn_relu_pool8_bwd_kernel(const uint4* __restrict__ z8, const void* __restrict__ dp,
                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -118,10 +134,10 @@ __global__ void __launch_bounds__(256) bn_relu_pool8_bwd_kernel(const uint4* __r
         const long zoff = ((n * t.P + oct) * H + 2 * py) * W + 2 * px;
         const uint4* zp = z8 + zoff;
         float w[4][8], g[8];
-        unpack8(__ldg(zp), w[0]);
-        unpack8(__ldg(zp + 1), w[1]);
-        unpack8(__ldg(zp + W), w[2]);
-        unpack8(__ldg(zp + W + 1), w[3]);
+        unpackz<ZF16>(__ldg(zp), w[0]);
+        unpackz<ZF16>(__ldg(zp + 1), w[1]);
+        unpackz<ZF16>(__ldg(zp + W), w[2]);
+        unpackz<ZF16>(__ldg(zp + W + 1), w[3]);
         if (dp_fmt) {
             unpack8(__ldg(reinterpret_cast<const uint4*>(dp) + ((n * t.P + oct) * t.HP + py) * t.WP + px), g);
         } else {
@@ -217,34 +233,48 @@ using namespace b200;
 extern "C" {
 
 int b200_bn_relu_pool8_fwd(const void* z8, const float* scale, const float* shift, void* out, int N, int n_per_view, int C, int H, int W,
-                           int out_fmt, void* stream) {
+                           int z_f16, int out_fmt, void* stream) {
     B200_REQUIRE(z8 && scale && shift && out, -1, "bn_relu_pool8_fwd: null pointer");
     int rc = check_shape("bn_relu_pool8_fwd", N, n_per_view, C, H, W);
     if (rc) return rc;
-    bn_relu_pool8_fwd_kernel<<<tile_grid(N, n_per_view, C, H, W), 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(z8), scale, shift, out,
-                                                                                               n_per_view, C, H, W, out_fmt);
+    if (z_f16)
+        bn_relu_pool8_fwd_kernel<true><<<tile_grid(N, n_per_view, C, H, W), 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(z8), scale,
+                                                                                                         shift, out, n_per_view, C, H, W, out_fmt);
+    else
+        bn_relu_pool8_fwd_kernel<false><<<tile_grid(N, n_per_view, C, H, W), 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(z8), scale,
+                                                                                                          shift, out, n_per_view, C, H, W, out_fmt);
     return launch_status("bn_relu_pool8_fwd_kernel");
 }
 
 int b200_bn_relu_pool8_bwd_reduce(const void* z8, const void* dp, const float* scale, const float* shift, const float* mean,
-                                  const float* invstd, double* sums, int N, int n_per_view, int C, int H, int W, int dp_fmt, void* stream) {
+                                  const float* invstd, double* sums, int N, int n_per_view, int C, int H, int W, int z_f16, int dp_fmt,
+                                  void* stream) {
     B200_REQUIRE(z8 && dp && scale && shift && mean && invstd && sums, -1, "bn_relu_pool8_bwd_reduce: null pointer");
     int rc = check_shape("bn_relu_pool8_bwd_reduce", N, n_per_view, C, H, W);
     if (rc) return rc;
-    bn_relu_pool8_bwd_kernel<false><<<tile_grid(N, n_per_view, C, H, W), 256, 0, as_stream(stream)>>>(
-        reinterpret_cast<const uint4*>(z8), dp, scale, shift, mean, invstd, sums, nullptr, n_per_view, C, H, W, dp_fmt);
+    if (z_f16)
+        bn_relu_pool8_bwd_kernel<false, true><<<tile_grid(N, n_per_view, C, H, W), 256, 0, as_stream(stream)>>>(
+            reinterpret_cast<const uint4*>(z8), dp, scale, shift, mean, invstd, sums, nullptr, n_per_view, C, H, W, dp_fmt);
+    else
+        bn_relu_pool8_bwd_kernel<false, false><<<tile_grid(N, n_per_view, C, H, W), 256, 0, as_stream(stream)>>>(
+            reinterpret_cast<const uint4*>(z8), dp, scale, shift, mean, invstd, sums, nullptr, n_per_view, C, H, W, dp_fmt);
     return launch_status("bn_relu_pool8_bwd_kernel<reduce>");
 }
 
 int b200_bn_relu_pool8_bwd_apply(const void* z8, const void* dp, const float* scale, const float* shift, const float* mean,
-                                 const float* invstd, const double* sums, void* dz8, int N, int n_per_view, int C, int H, int W, int dp_fmt,
-                                 void* stream) {
+                                 const float* invstd, const double* sums, void* dz8, int N, int n_per_view, int C, int H, int W, int z_f16,
+                                 int dp_fmt, void* stream) {
     B200_REQUIRE(z8 && dp && scale && shift && mean && invstd && sums && dz8, -1, "bn_relu_pool8_bwd_apply: null pointer");
     int rc = check_shape("bn_relu_pool8_bwd_apply", N, n_per_view, C, H, W);
     if (rc) return rc;
-    bn_relu_pool8_bwd_kernel<true><<<tile_grid(N, n_per_view, C, H, W), 256, 0, as_stream(stream)>>>(
-        reinterpret_cast<const uint4*>(z8), dp, scale, shift, mean, invstd, const_cast<double*>(sums), reinterpret_cast<uint4*>(dz8), n_per_view, C,
-        H, W, dp_fmt);
+    if (z_f16)
+        bn_relu_pool8_bwd_kernel<true, true><<<tile_grid(N, n_per_view, C, H, W), 256, 0, as_stream(stream)>>>(
+            reinterpret_cast<const uint4*>(z8), dp, scale, shift, mean, invstd, const_cast<double*>(sums), reinterpret_cast<uint4*>(dz8), n_per_view,
+            C, H, W, dp_fmt);
+    else
+        bn_relu_pool8_bwd_kernel<true, false><<<tile_grid(N, n_per_view, C, H, W), 256, 0, as_stream(stream)>>>(
+            reinterpret_cast<const uint4*>(z8), dp, scale, shift, mean, invstd, const_cast<double*>(sums), reinterpret_cast<uint4*>(dz8), n_per_view,
+            C, H, W, dp_fmt);
     return launch_status("bn_relu_pool8_bwd_kernel<apply>");
 }
 

@@ -85,7 +85,8 @@ struct TcCfg {
     static_assert(P * PLANE_BYTES < (1 << 18) && PLANE_BYTES % 16 == 0, "descriptor range");
 };
 
-// out: fp32 NCHW [N][COUT][HO][WO] (out_bf16 == 0) or bf16 act8 [N][COUT/8][HO][WO][8] (out_bf16 == 1).
+// out: fp32 NCHW [N][COUT][HO][WO] (out_bf16 == 0), bf16 act8 [N][COUT/8][HO][WO][8] (1) or the same in fp16 (2: the pre-BatchNorm
+// z, which is never an MMA operand -- 11 mantissa bits keep max-pool arg-max ties as rare as on the reference's fp16 autocast path).
 // bias may be null (no bias, no statistics); stats: double [views][COUT][2] (sum, sum of squares), accumulated.
 template <class C>
 __global__ void __launch_bounds__(192, 1)
@@ -238,10 +239,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
                                 const int oct = cc * 2 + o;
                                 if (oct * 8 < C::COUT) {
                                     uint4 pk;
-                                    pk.x = pack_bf16(f[o * 8 + 0], f[o * 8 + 1]);
-                                    pk.y = pack_bf16(f[o * 8 + 2], f[o * 8 + 3]);
-                                    pk.z = pack_bf16(f[o * 8 + 4], f[o * 8 + 5]);
-                                    pk.w = pack_bf16(f[o * 8 + 6], f[o * 8 + 7]);
+                                    if (out_bf16 == 2) {
+                                        pk.x = pack_f16(f[o * 8 + 0], f[o * 8 + 1]);
+                                        pk.y = pack_f16(f[o * 8 + 2], f[o * 8 + 3]);
+                                        pk.z = pack_f16(f[o * 8 + 4], f[o * 8 + 5]);
+                                        pk.w = pack_f16(f[o * 8 + 6], f[o * 8 + 7]);
+                                    } else {
+                                        pk.x = pack_bf16(f[o * 8 + 0], f[o * 8 + 1]);
+                                        pk.y = pack_bf16(f[o * 8 + 2], f[o * 8 + 3]);
+                                        pk.z = pack_bf16(f[o * 8 + 4], f[o * 8 + 5]);
+                                        pk.w = pack_bf16(f[o * 8 + 6], f[o * 8 + 7]);
+                                    }
                                     uint4* dst = reinterpret_cast<uint4*>(out) + (((long)n * (C::COUT / 8) + oct) * C::HO + yy) * C::WO + x;
                                     *dst = pk;
                                 }

@@ -139,13 +139,16 @@ class DinoStepEngine:
     def __init__(self, kind="multi_central", mode="default", encoder_output_dim=256, output_dim=256, projection_dim=128,
                  n_global_views=2, n_local_views=4, momentum=0.996, center_momentum=0.9, student_temperature=0.1,
                  teacher_temperature=0.04, learning_rate=1e-4, weight_decay=1e-6, dropout=0.3, fusion_dropout=0.3, alpha=1.0,
-                 cosine_loss_alpha=0.0, augment_values=None, seed=0, device=None, process_group=None, data_parallel=None):
+                 cosine_loss_alpha=0.0, augment_values=None, seed=0, device=None, process_group=None, data_parallel=None,
+                 precision="bf16"):
         if not torch.cuda.is_available():
             raise ops._lib.B200Error("DinoStepEngine needs a CUDA device: the hot path has no CPU fallback")
         ops._lib.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         assert kind in ("multi_central", "image_simple")
         assert mode == "default" or kind == "multi_central"
+        assert precision in ("bf16", "fp32")
+        self.precision = precision
         self.kind, self.mode = kind, mode
         self.E, self.O, self.P = encoder_output_dim, output_dim, projection_dim
         self.Vg, self.Vl = n_global_views, n_local_views
@@ -197,6 +200,18 @@ class DinoStepEngine:
         for m in ("aux_image", "aux_audio"):
             if aux:
                 self.bn_s[f"{m}.mlp.1"] = _BN(512, self.device)
+        # tensor-core layers (tcgen05, bf16 act8 activations, fp32 accumulate): every C_in >= 8 convolution the library supports
+        self.tc = {}
+        for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers)):
+            self.tc[mod] = [precision == "bf16" and ops.conv_tc_supported(ci, co, hw, hw, k, pad) and ops.conv_tc_supported(co, ci, hw + 2 * pad - k + 1, hw + 2 * pad - k + 1, k, k - 1 - pad)
+                            for (conv, bn, ci, co, hw, k, pad) in layers]
+        self._tcw = {}
+        for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers)):
+            for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers):
+                if self.tc[mod][li]:
+                    for role in ("s", "t"):
+                        self._tcw[(role, mod, li)] = torch.empty(ops.conv_tc_weight_bytes(ci, co, k), dtype=torch.uint8, device=self.device)
+                    self._tcw[("flip", mod, li)] = torch.empty(ops.conv_tc_weight_bytes(co, ci, k), dtype=torch.uint8, device=self.device)
         self._ws = {}
         self._init_parameters()
         self.set_augmentation(augment_values)
@@ -264,22 +279,37 @@ class DinoStepEngine:
         if self.aud_layers:
             w["x_aud"] = e(Ns, 1, 112, 112)
         wg_work = 0
+        zmax = pmax = z8max = 0
+        BF = torch.bfloat16
         for role, N in (("s", Ns), ("t", Nt)):
             for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers)):
                 for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers):
                     ho = hw + 2 * pad - k + 1
                     nv = N // B
-                    w[f"{role}.{mod}.z{li}"] = e(N, co, ho, ho)
-                    w[f"{role}.{mod}.p{li}"] = e(N, co, ho // 2, ho // 2)
+                    tc = self.tc[mod][li]
+                    next_tc = li + 1 < len(layers) and self.tc[mod][li + 1]
+                    if tc:
+                        w[f"{role}.{mod}.z{li}"] = e(N, co // 8, ho, ho, 8, dtype=torch.float16)   # act8 layout, fp16: never an MMA operand
+                    else:
+                        w[f"{role}.{mod}.z{li}"] = e(N, co, ho, ho)
+                    if next_tc:
+                        w[f"{role}.{mod}.p8{li}"] = e(N, co // 8, ho // 2, ho // 2, 8, dtype=BF)
+                    if not next_tc or not tc:
+                        w[f"{role}.{mod}.p{li}"] = e(N, co, ho // 2, ho // 2)
                     w[f"{role}.{mod}.stats{li}"] = torch.zeros(nv, co, 2, dtype=torch.float64, device=dev)
                     for nm in ("scale", "shift", "mean", "invstd"):
                         w[f"{role}.{mod}.{nm}{li}"] = e(nv, co)
                     if role == "s":
                         w[f"s.{mod}.sums{li}"] = torch.zeros(nv, co, 2, dtype=torch.float64, device=dev)
-                        wg_work = max(wg_work, ops.conv_bwd_weight_work_floats(N, ci, co, hw, hw, k, pad))
-        zmax = max([w[k].numel() for k in w if isinstance(w[k], torch.Tensor) and k.startswith("s.") and ".z" in k])
-        pmax = max([w[k].numel() for k in w if isinstance(w[k], torch.Tensor) and k.startswith("s.") and ".p" in k])
-        w["dz"] = e(zmax)
+                        if tc:
+                            wg_work = max(wg_work, ops.conv_tc_wgrad_work_floats(N, ci, co, hw, hw, k, pad))
+                            z8max = max(z8max, N * co * ho * ho)
+                        else:
+                            wg_work = max(wg_work, ops.conv_bwd_weight_work_floats(N, ci, co, hw, hw, k, pad))
+                            zmax = max(zmax, N * co * ho * ho)
+                        pmax = max(pmax, N * co * (ho // 2) * (ho // 2), N * ci * hw * hw if li > 0 else 0)
+        w["dz"] = e(max(zmax, 4))
+        w["dz8"] = e(max(z8max, 8), dtype=BF)
         w["dp_a"], w["dp_b"] = e(pmax), e(pmax)
         w["wg_work"] = e(max(wg_work, 4))
         E, O, P = self.E, self.O, self.P
@@ -357,20 +387,43 @@ class DinoStepEngine:
     # ------------------------------------------------------------------------------------------------------
     # forward building blocks
     # ------------------------------------------------------------------------------------------------------
+    def _prep_tc_weights(self, role, P):
+        """fp32 conv weights -> the bf16 operand images of the tensor-core convolutions (weights change every step)."""
+        for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers)):
+            for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers):
+                if self.tc[mod][li]:
+                    ops.conv_tc_prep_weights(P["enc." + conv + ".weight"], self._tcw[(role, mod, li)])
+                    if role == "s":
+                        ops.conv_tc_prep_weights(P["enc." + conv + ".weight"], self._tcw[("flip", mod, li)], flip=True)
+
     def _conv_stack(self, w, role, mod, layers, x, N, B, P, bns, train=True):
+        """conv -> BatchNorm(batch statistics per view-call) -> ReLU -> MaxPool2 for every layer; tensor-core layers keep
+        z and the pooled activation in bf16 act8, the others in fp32 NCHW.  Returns the last pooled activation (fp32)."""
         nv = N // B
         cur = x
         for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers):
-            z, p, stats = w[f"{role}.{mod}.z{li}"], w[f"{role}.{mod}.p{li}"], w[f"{role}.{mod}.stats{li}"]
+            z, stats = w[f"{role}.{mod}.z{li}"], w[f"{role}.{mod}.stats{li}"]
+            tc = self.tc[mod][li]
+            next_tc = li + 1 < len(layers) and self.tc[mod][li + 1]
             stats.zero_()
-            ops.conv_fwd(cur.view(N, ci, hw, hw), P["enc." + conv + ".weight"], P["enc." + conv + ".bias"], z, stats, B, pad)
+            if tc:
+                ops.conv_tc(cur, self._tcw[(role, mod, li)], P["enc." + conv + ".bias"], z, stats, B, co, k, pad)
+            else:
+                ops.conv_fwd(cur.view(N, ci, hw, hw), P["enc." + conv + ".weight"], P["enc." + conv + ".bias"], z, stats, B, pad)
             b = bns["enc." + bn]
-            ho = z.shape[-1]
+            ho = hw + 2 * pad - k + 1
+            sc, sh = w[f"{role}.{mod}.scale{li}"], w[f"{role}.{mod}.shift{li}"]
             ops.bn_finalize(stats, P["enc." + bn + ".weight"], P["enc." + bn + ".bias"], b.running_mean, b.running_var,
-                            b.num_batches_tracked, w[f"{role}.{mod}.scale{li}"], w[f"{role}.{mod}.shift{li}"],
-                            w[f"{role}.{mod}.mean{li}"], w[f"{role}.{mod}.invstd{li}"], nv, B * ho * ho, train=train)
-            ops.bn_relu_pool_fwd(z, w[f"{role}.{mod}.scale{li}"], w[f"{role}.{mod}.shift{li}"], p, B)
-            cur = p
+                            b.num_batches_tracked, sc, sh, w[f"{role}.{mod}.mean{li}"], w[f"{role}.{mod}.invstd{li}"], nv, B * ho * ho, train=train)
+            if tc:
+                cur = w[f"{role}.{mod}.p8{li}"] if next_tc else w[f"{role}.{mod}.p{li}"]
+                ops.bn_relu_pool8_fwd(z, sc, sh, cur, B)
+            else:
+                cur = w[f"{role}.{mod}.p{li}"]
+                ops.bn_relu_pool_fwd(z, sc, sh, cur, B)
+                if next_tc:
+                    ops.pack_act8(cur, w[f"{role}.{mod}.p8{li}"])
+                    cur = w[f"{role}.{mod}.p8{li}"]
         return cur
 
     def _head_fwd(self, w, role, prefix, P, bn, x, out, hh, g, mask, drop_p, tag=""):
@@ -417,25 +470,45 @@ class DinoStepEngine:
         return w[f"{role}.feat"]
 
     def _conv_stack_bwd(self, w, mod, layers, x, d_top, N, B):
-        """Backward through a conv stack; d_top = gradient w.r.t. the last pooled activation (any shape, N*C*h*w)."""
+        """Backward through a conv stack; d_top = gradient w.r.t. the last pooled activation (fp32, any shape, N*C*h*w)."""
         S, G = self.S, self.G
         d_p = d_top
+        BF = torch.bfloat16
         for li in range(len(layers) - 1, -1, -1):
             conv, bn, ci, co, hw, k, pad = layers[li]
+            ho = hw + 2 * pad - k + 1
+            tc = self.tc[mod][li]
             z = w[f"s.{mod}.z{li}"]
             sums = w[f"s.{mod}.sums{li}"]
             sums.zero_()
             sc, sh, mu, inv = (w[f"s.{mod}.{n}{li}"] for n in ("scale", "shift", "mean", "invstd"))
-            dz = w["dz"][:z.numel()].view_as(z)
-            ops.bn_relu_pool_bwd_reduce(z, d_p, sc, sh, mu, inv, sums, B)
-            ops.bn_relu_pool_bwd_apply(z, d_p, sc, sh, mu, inv, sums, dz, B)
+            if tc:
+                if d_p.dtype != BF:
+                    d_p = d_p.view(N, co, ho // 2, ho // 2)
+                dz = w["dz8"][:z.numel()].view_as(z)
+                ops.bn_relu_pool8_bwd_reduce(z, d_p, sc, sh, mu, inv, sums, B)
+                ops.bn_relu_pool8_bwd_apply(z, d_p, sc, sh, mu, inv, sums, dz, B)
+            else:
+                dz = w["dz"][:z.numel()].view_as(z)
+                ops.bn_relu_pool_bwd_reduce(z, d_p, sc, sh, mu, inv, sums, B)
+                ops.bn_relu_pool_bwd_apply(z, d_p, sc, sh, mu, inv, sums, dz, B)
             ops.bn_param_grads(sums, G["enc." + bn + ".weight"], G["enc." + bn + ".bias"], N // B)
-            xin = x if li == 0 else w[f"s.{mod}.p{li - 1}"]
-            ops.conv_bwd_weight(xin.view(N, ci, hw, hw), dz, G["enc." + conv + ".weight"], G["enc." + conv + ".bias"], w["wg_work"], pad)
+            if tc:
+                ops.conv_tc_wgrad(w[f"s.{mod}.p8{li - 1}"], dz, G["enc." + conv + ".weight"], G["enc." + conv + ".bias"], w["wg_work"], pad)
+            else:
+                xin = x if li == 0 else w[f"s.{mod}.p{li - 1}"]
+                ops.conv_bwd_weight(xin.view(N, ci, hw, hw), dz, G["enc." + conv + ".weight"], G["enc." + conv + ".bias"], w["wg_work"], pad)
             if li > 0:
                 nxt = w["dp_a"] if d_p.data_ptr() != w["dp_a"].data_ptr() else w["dp_b"]
-                d_in = nxt[:N * ci * hw * hw].view(N, ci, hw, hw)
-                ops.conv_bwd_data(dz, S["enc." + conv + ".weight"], d_in, pad)
+                if tc:
+                    if self.tc[mod][li - 1]:          # the consumer is an act8 layer: bf16 act8 gradient
+                        d_in = nxt.view(BF)[:N * ci * hw * hw].view(N, ci // 8, hw, hw, 8)
+                    else:
+                        d_in = nxt[:N * ci * hw * hw].view(N, ci, hw, hw)
+                    ops.conv_tc(dz, self._tcw[("flip", mod, li)], None, d_in, None, N, ci, k, k - 1 - pad)
+                else:
+                    d_in = nxt[:N * ci * hw * hw].view(N, ci, hw, hw)
+                    ops.conv_bwd_data(dz, S["enc." + conv + ".weight"], d_in, pad)
                 d_p = d_in
 
     # ------------------------------------------------------------------------------------------------------
@@ -474,6 +547,9 @@ class DinoStepEngine:
                 ops.dropout_mask(w["t.fmask"], self.fusion_dropout, self.seed + 1, base + 1)
             if self.dropout > 0:
                 ops.dropout_mask(w["s.hmask"], self.dropout, self.seed + 1, base + 2)
+        if self._tcw:
+            self._prep_tc_weights("s", S)
+            self._prep_tc_weights("t", T)
         feat_s = self._encode(w, "s", S, self.bn_s, xi, xa, Ns, B, Nv, w.get("s.fmask"))
         feat_t = self._encode(w, "t", T, self.bn_t, xi[:Nt], xa[:Nt] if multi else None, Nt, B, Nt, w.get("t.fmask"))
         self._head_fwd(w, "s", "head.", S, self.bn_s["head.mlp.1"], feat_s, w["s.proj"], w["s.hh"], w["s.g"], w["s.hmask"], self.dropout)

@@ -215,9 +215,10 @@ def conv_tc(x8, wprep, bias, out, stats, n_per_view, Cout, K, pad):
     """x8: bf16 act8 [N, Cin/8, H, W, 8]; out: fp32 NCHW [N, Cout, Ho, Wo] or bf16 act8 [N, Cout/8, Ho, Wo, 8];
     bias/stats may be None (data-gradient use)."""
     N, P, H, W, _ = x8.shape
+    fmt = 1 if out.dtype == BF16 else 2 if out.dtype == torch.float16 else 0
     _lib.check(_lib_().b200_conv_tc(_ptr(x8, BF16), _ptr(wprep), _ptr(bias, F32) if bias is not None else None, _ptr(out),
                                     _ptr(stats, F64) if stats is not None else None, N, n_per_view, P * 8, Cout, H, W, K, pad,
-                                    1 if out.dtype == BF16 else 0, _stream()), "conv_tc")
+                                    fmt, _stream()), "conv_tc")
 
 
 def conv_tc_wgrad_work_floats(N, Cin, Cout, H, W, K, pad):
@@ -244,25 +245,31 @@ def _fmt(t):
     return 1 if t.dtype == BF16 else 0
 
 
+def _zf16(z8):
+    if z8.dtype not in (BF16, torch.float16):
+        raise _lib.B200Error(f"act8 z must be bf16 or fp16, got {z8.dtype}")
+    return 1 if z8.dtype == torch.float16 else 0
+
+
 def bn_relu_pool8_fwd(z8, scale, shift, out, n_per_view):
     """z8 bf16 act8 [N, C/8, H, W, 8] -> out: fp32 NCHW [N, C, H/2, W/2] or bf16 act8 [N, C/8, H/2, W/2, 8] (by dtype)."""
     N, P, H, W, _ = z8.shape
-    _lib.check(_lib_().b200_bn_relu_pool8_fwd(_ptr(z8, BF16), _ptr(scale, F32), _ptr(shift, F32), _ptr(out), N, n_per_view, P * 8, H, W,
-                                              _fmt(out), _stream()), "bn_relu_pool8_fwd")
+    _lib.check(_lib_().b200_bn_relu_pool8_fwd(_ptr(z8), _ptr(scale, F32), _ptr(shift, F32), _ptr(out), N, n_per_view, P * 8, H, W,
+                                              _zf16(z8), _fmt(out), _stream()), "bn_relu_pool8_fwd")
 
 
 def bn_relu_pool8_bwd_reduce(z8, dp, scale, shift, mean, invstd, sums, n_per_view):
     N, P, H, W, _ = z8.shape
-    _lib.check(_lib_().b200_bn_relu_pool8_bwd_reduce(_ptr(z8, BF16), _ptr(dp), _ptr(scale, F32), _ptr(shift, F32), _ptr(mean, F32),
-                                                     _ptr(invstd, F32), _ptr(sums, F64), N, n_per_view, P * 8, H, W, _fmt(dp), _stream()),
+    _lib.check(_lib_().b200_bn_relu_pool8_bwd_reduce(_ptr(z8), _ptr(dp), _ptr(scale, F32), _ptr(shift, F32), _ptr(mean, F32),
+                                                     _ptr(invstd, F32), _ptr(sums, F64), N, n_per_view, P * 8, H, W, _zf16(z8), _fmt(dp), _stream()),
                "bn_relu_pool8_bwd_reduce")
 
 
 def bn_relu_pool8_bwd_apply(z8, dp, scale, shift, mean, invstd, sums, dz8, n_per_view):
     N, P, H, W, _ = z8.shape
-    _lib.check(_lib_().b200_bn_relu_pool8_bwd_apply(_ptr(z8, BF16), _ptr(dp), _ptr(scale, F32), _ptr(shift, F32), _ptr(mean, F32),
-                                                    _ptr(invstd, F32), _ptr(sums, F64), _ptr(dz8, BF16), N, n_per_view, P * 8, H, W, _fmt(dp),
-                                                    _stream()), "bn_relu_pool8_bwd_apply")
+    _lib.check(_lib_().b200_bn_relu_pool8_bwd_apply(_ptr(z8), _ptr(dp), _ptr(scale, F32), _ptr(shift, F32), _ptr(mean, F32),
+                                                    _ptr(invstd, F32), _ptr(sums, F64), _ptr(dz8, BF16), N, n_per_view, P * 8, H, W, _zf16(z8),
+                                                    _fmt(dp), _stream()), "bn_relu_pool8_bwd_apply")
 
 
 def bn_finalize(stats, gamma, beta, running_mean, running_var, nbt, scale, shift, mean, invstd, n_views, count, train=True,

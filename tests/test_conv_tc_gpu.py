@@ -46,16 +46,16 @@ def test_conv_tc_forward(geom, views, B):
     want = F.conv2d(_bf(x).double(), _bf(w).double(), b.double(), padding=pad).float()   # fp64: no TF32 / FFT algorithms
     Ho = want.shape[-1]
     wp = _prep(w)
-    for out_bf16 in (False, True):
+    for out_bf16 in (False, torch.bfloat16, torch.float16):
         stats = torch.zeros(views, Cout, 2, dtype=torch.float64, device=DEV)
         if out_bf16:
-            out = torch.full((N, Cout // 8, Ho, Ho, 8), float("nan"), dtype=torch.bfloat16, device=DEV)
+            out = torch.full((N, Cout // 8, Ho, Ho, 8), float("nan"), dtype=out_bf16, device=DEV)
         else:
             out = torch.full((N, Cout, Ho, Ho), float("nan"), device=DEV)
         ops.conv_tc(x8, wp, b, out, stats, B, Cout, K, pad)
         torch.cuda.synchronize()
         got = _unpack8(out) if out_bf16 else out
-        tol = (8e-3 if out_bf16 else 2e-5) * float(want.abs().max())
+        tol = (8e-3 if out_bf16 == torch.bfloat16 else 1e-3 if out_bf16 else 2e-5) * float(want.abs().max())
         err = float((got - want).abs().max())
         assert err <= tol, (geom, out_bf16, err, tol)
         wv = want.view(views, B, Cout, Ho, Ho).double()
@@ -122,18 +122,23 @@ def _pack8(x):
     return out
 
 
+@pytest.mark.parametrize("zdt", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("C,H,views,B", [(16, 56, 2, 3), (32, 28, 3, 5), (64, 14, 7, 9), (64, 10, 1, 40), (8, 112, 2, 2)])
-def test_bn_relu_pool8(C, H, views, B):
+def test_bn_relu_pool8(C, H, views, B, zdt):
     """act8 BN-apply/ReLU/pool forward and backward against a torch fp32 restatement on the same bf16 z / dp."""
     g = torch.Generator().manual_seed(C + H)
     N = views * B
-    z = _bf(torch.randn(N, C, H, H, generator=g)).to(DEV)
+    z = torch.randn(N, C, H, H, generator=g)
+    z = (_bf(z) if zdt == torch.bfloat16 else z.half().float()).to(DEV)
     scale = (torch.randn(views, C, generator=g) * 0.5 + 1.0).to(DEV)       # includes negative gammas
     shift = (torch.randn(views, C, generator=g) * 0.3).to(DEV)
     mean = (torch.randn(views, C, generator=g) * 0.2).to(DEV)
     invstd = (torch.rand(views, C, generator=g) + 0.5).to(DEV)
     dp = _bf(torch.randn(N, C, H // 2, H // 2, generator=g)).to(DEV)
-    z8 = _pack8(z)
+    if zdt == torch.float16:
+        z8 = z.view(N, C // 8, 8, H, H).permute(0, 1, 3, 4, 2).contiguous().half()
+    else:
+        z8 = _pack8(z)
     a = scale.repeat_interleave(B, 0)[:, :, None, None]
     b = shift.repeat_interleave(B, 0)[:, :, None, None]
     mu = mean.repeat_interleave(B, 0)[:, :, None, None]
@@ -164,7 +169,7 @@ def test_bn_relu_pool8(C, H, views, B):
         sums = torch.zeros(views, C, 2, dtype=torch.float64, device=DEV)
         ops.bn_relu_pool8_bwd_reduce(z8, dpt, scale, shift, mean, invstd, sums, B)
         assert float(((sums - s_want).abs() / (s_want.abs() + 1.0)).max()) < 1e-5
-        dz8 = torch.empty_like(z8)
+        dz8 = torch.empty(z8.shape, dtype=torch.bfloat16, device=DEV)
         ops.bn_relu_pool8_bwd_apply(z8, dpt, scale, shift, mean, invstd, s_want.contiguous(), dz8, B)
         got = _unpack8(dz8)
         assert float((got - want_dz).abs().max()) <= 8e-3 * float(want_dz.abs().max())
