@@ -144,11 +144,15 @@ int64_t b200_conv_tc_weight_bytes(int Cin, int Cout, int K);
 int b200_conv_tc_prep_weights(const float* w, void* wprep, int Cin, int Cout, int K, int flip, void* stream);
 int b200_conv_tc(const void* x_act8, const void* wprep, const float* bias, void* out, double* stats, int N,
                  int n_per_view, int Cin, int Cout, int H, int W, int K, int pad, int out_bf16, void* stream);
-/* dw [Cout][Cin][K][K] = sum_n corr(x_n, dz_n), db [Cout] = sum dz (db may be NULL); x and dz bf16 act8, fp32 accumulate
- * in TMEM; per-CTA partials in work (float[b200_conv_tc_wgrad_work_floats(...)]) reduced in a fixed order. */
+/* dw [Cout][Cin][K][K] = sum_n corr(x_n, dz_n); x and dz bf16 act8, fp32 accumulate in TMEM; per-CTA partials in work
+ * (float[b200_conv_tc_wgrad_work_floats(...)]) reduced in a fixed order.  (The bias gradient sum(dz) comes from
+ * b200_bn_relu_pool8_bwd_apply's dbsum.)
+ * First layers (Cin = 1): b200_conv_tc / b200_conv_tc_wgrad take the "shift8" image bf16 [N][H][W+pad][8] written by
+ * b200_pack_shift8 (unit (y,xs) = x[y][xs-pad .. xs-pad+7], zero outside the row) instead of an act8 tensor. */
 int64_t b200_conv_tc_wgrad_work_floats(int N, int Cin, int Cout, int H, int W, int K, int pad);
-int b200_conv_tc_wgrad(const void* x_act8, const void* dz_act8, float* dw, float* db, float* work, int N, int Cin,
-                       int Cout, int H, int W, int K, int pad, void* stream);
+int b200_conv_tc_wgrad(const void* x_act8, const void* dz_act8, float* dw, float* work, int N, int Cin, int Cout, int H,
+                       int W, int K, int pad, void* stream);
+int b200_pack_shift8(const float* x, void* out, int N, int H, int W, int pad, void* stream);
 /* BatchNorm-apply + ReLU + MaxPool2 on bf16 act8 activations (same reference call sites as b200_bn_relu_pool_*):
  *   z8 [N][C/8][H][W][8] bf16 (z_f16 = 0) or fp16 (z_f16 = 1) (H, W even); scale/shift/mean/invstd [views][C] from b200_bn_finalize;
  *   out_fmt / dp_fmt: 0 = fp32 NCHW [N][C][H/2][W/2], 1 = bf16 act8 [N][C/8][H/2][W/2][8];
@@ -159,8 +163,10 @@ int b200_bn_relu_pool8_bwd_reduce(const void* z8, const void* dp, const float* s
                                   const float* mean, const float* invstd, double* sums, int N, int n_per_view, int C,
                                   int H, int W, int z_f16, int dp_fmt, void* stream);
 int b200_bn_relu_pool8_bwd_apply(const void* z8, const void* dp, const float* scale, const float* shift,
-                                 const float* mean, const float* invstd, const double* sums, void* dz8, int N,
-                                 int n_per_view, int C, int H, int W, int z_f16, int dp_fmt, void* stream);
+                                 const float* mean, const float* invstd, const double* sums, void* dz8, double* dbsum,
+                                 int N, int n_per_view, int C, int H, int W, int z_f16, int dp_fmt, void* stream);
+/* dbsum: double [C] (zeroed by the caller, may be NULL) += sum of dz per channel = the convolution's bias gradient */
+int b200_bias_grad_finalize(const double* dbsum, float* db, int C, void* stream);
 /* bf16 act8 -> fp32 NCHW */
 int b200_unpack_act8(const void* x8, float* out, int N, int C, int H, int W, void* stream);
 /* fp32 NCHW -> bf16 act8 */

@@ -110,8 +110,8 @@ template <bool APPLY, bool ZF16>
 __global__ void __launch_bounds__(256) bn_relu_pool8_bwd_kernel(const uint4* __restrict__ z8, const void* __restrict__ dp,
                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                                double* __restrict__ sums, uint4* __restrict__ dz8, int n_per_view, int C, int H,
-                                                                int W, int dp_fmt) {
+                                                                double* __restrict__ sums, uint4* __restrict__ dz8, double* __restrict__ dbsum,
+                                                                int n_per_view, int C, int H, int W, int dp_fmt) {
     const Tile t = make_tile(n_per_view, C, H, W);
     const int oct = blockIdx.y, v = blockIdx.z;
     float a[8], b[8], mu[8], is[8], k1[8], k2[8], s1[8], s2[8];
@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(256) bn_relu_pool8_bwd_kernel(const uint4* __r
                 for (int q = 0; q < 4; ++q) {
                     const float xh = (w[q][j] - mu[j]) * is[j];
                     o[q][j] = a[j] * (((q == k) ? gj : 0.f) - k1[j] - xh * k2[j]);
+                    s1[j] += o[q][j];
                 }
             }
         }
@@ -171,7 +172,23 @@ __global__ void __launch_bounds__(256) bn_relu_pool8_bwd_kernel(const uint4* __r
             zo[W + 1] = pack8(o[3]);
         }
     }
-    if (!APPLY) {
+    if (APPLY) {
+        if (dbsum != nullptr) {        // conv bias gradient = sum of dz over the view-call (block-uniform branch)
+            __shared__ float redb[8][8];
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float x1 = warp_sum(s1[j]);
+                if (lane == 0) redb[warp][j] = x1;
+            }
+            __syncthreads();
+            if (threadIdx.x < 8) {
+                double acc = 0.0;
+                for (int wv = 0; wv < 8; ++wv) acc += (double)redb[wv][threadIdx.x];
+                atomicAdd(&dbsum[oct * 8 + threadIdx.x], acc);
+            }
+        }
+    } else {
         __shared__ float red[8][16];
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -190,6 +207,11 @@ __global__ void __launch_bounds__(256) bn_relu_pool8_bwd_kernel(const uint4* __r
             atomicAdd(&sums[((size_t)v * C + oct * 8 + j) * 2 + which], acc);
         }
     }
+}
+
+__global__ void bias_grad_finalize_kernel(const double* __restrict__ dbsum, float* __restrict__ db, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) db[c] = (float)dbsum[c];
 }
 
 // bf16 act8 -> fp32 NCHW (tests / debugging)
@@ -254,28 +276,34 @@ int b200_bn_relu_pool8_bwd_reduce(const void* z8, const void* dp, const float* s
     if (rc) return rc;
     if (z_f16)
         bn_relu_pool8_bwd_kernel<false, true><<<tile_grid(N, n_per_view, C, H, W), 256, 0, as_stream(stream)>>>(
-            reinterpret_cast<const uint4*>(z8), dp, scale, shift, mean, invstd, sums, nullptr, n_per_view, C, H, W, dp_fmt);
+            reinterpret_cast<const uint4*>(z8), dp, scale, shift, mean, invstd, sums, nullptr, nullptr, n_per_view, C, H, W, dp_fmt);
     else
         bn_relu_pool8_bwd_kernel<false, false><<<tile_grid(N, n_per_view, C, H, W), 256, 0, as_stream(stream)>>>(
-            reinterpret_cast<const uint4*>(z8), dp, scale, shift, mean, invstd, sums, nullptr, n_per_view, C, H, W, dp_fmt);
+            reinterpret_cast<const uint4*>(z8), dp, scale, shift, mean, invstd, sums, nullptr, nullptr, n_per_view, C, H, W, dp_fmt);
     return launch_status("bn_relu_pool8_bwd_kernel<reduce>");
 }
 
 int b200_bn_relu_pool8_bwd_apply(const void* z8, const void* dp, const float* scale, const float* shift, const float* mean,
-                                 const float* invstd, const double* sums, void* dz8, int N, int n_per_view, int C, int H, int W, int z_f16,
-                                 int dp_fmt, void* stream) {
+                                 const float* invstd, const double* sums, void* dz8, double* dbsum, int N, int n_per_view, int C, int H, int W,
+                                 int z_f16, int dp_fmt, void* stream) {
     B200_REQUIRE(z8 && dp && scale && shift && mean && invstd && sums && dz8, -1, "bn_relu_pool8_bwd_apply: null pointer");
     int rc = check_shape("bn_relu_pool8_bwd_apply", N, n_per_view, C, H, W);
     if (rc) return rc;
     if (z_f16)
         bn_relu_pool8_bwd_kernel<true, true><<<tile_grid(N, n_per_view, C, H, W), 256, 0, as_stream(stream)>>>(
-            reinterpret_cast<const uint4*>(z8), dp, scale, shift, mean, invstd, const_cast<double*>(sums), reinterpret_cast<uint4*>(dz8), n_per_view,
-            C, H, W, dp_fmt);
+            reinterpret_cast<const uint4*>(z8), dp, scale, shift, mean, invstd, const_cast<double*>(sums), reinterpret_cast<uint4*>(dz8), dbsum,
+            n_per_view, C, H, W, dp_fmt);
     else
         bn_relu_pool8_bwd_kernel<true, false><<<tile_grid(N, n_per_view, C, H, W), 256, 0, as_stream(stream)>>>(
-            reinterpret_cast<const uint4*>(z8), dp, scale, shift, mean, invstd, const_cast<double*>(sums), reinterpret_cast<uint4*>(dz8), n_per_view,
-            C, H, W, dp_fmt);
+            reinterpret_cast<const uint4*>(z8), dp, scale, shift, mean, invstd, const_cast<double*>(sums), reinterpret_cast<uint4*>(dz8), dbsum,
+            n_per_view, C, H, W, dp_fmt);
     return launch_status("bn_relu_pool8_bwd_kernel<apply>");
+}
+
+int b200_bias_grad_finalize(const double* dbsum, float* db, int C, void* stream) {
+    B200_REQUIRE(dbsum && db && C > 0, -1, "bias_grad_finalize: bad arguments");
+    bias_grad_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(dbsum, db, C);
+    return launch_status("bias_grad_finalize_kernel");
 }
 
 int b200_unpack_act8(const void* x8, float* out, int N, int C, int H, int W, void* stream) {

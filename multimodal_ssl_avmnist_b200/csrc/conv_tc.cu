@@ -59,7 +59,8 @@ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ?
 template <int CIN_, int COUT_, int NPAD_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_>
 struct TcCfg {
     static constexpr int CIN = CIN_, COUT = COUT_, NPAD = NPAD_, HIN = HIN_, WIN = WIN_, KS = KS_, PAD = PAD_, BANDS = BANDS_, SLOTS = SLOTS_;
-    static constexpr int P = CIN / 8;                           // channel planes of the input
+    static constexpr bool L0 = (CIN == 1);                      // first layer: input is the "shift8" image (unit = x[q..q+7])
+    static constexpr int P = L0 ? 1 : CIN / 8;                  // channel planes of the input
     static constexpr int WP = WIN + 2 * PAD;                    // padded pitch (pixels)
     static constexpr int HO = HIN + 2 * PAD - KS + 1, WO = WP - KS + 1;
     static constexpr int HB = HO / BANDS;                       // output rows per band
@@ -70,15 +71,15 @@ struct TcCfg {
     static constexpr int SLOT_BYTES = round_up(P * PLANE_BYTES, 128);
     static constexpr int NJ = (KS + 1) / 2;                     // kw pairs when CIN == 8
     static constexpr int PH = P / 2;                            // plane pairs when CIN >= 16
-    static constexpr int NMMA = (CIN == 8) ? KS * NJ : KS * KS * PH;
+    static constexpr int NMMA = L0 ? NJ : (CIN == 8) ? KS * NJ : KS * KS * PH;
     static constexpr int W_BYTES = round_up(NMMA * NPAD * 32, 128);
-    static constexpr int MAXPIX = TILES * 128 + (KS - 1) * WP + KS + 1;       // exclusive bound of pixels a tile may touch
+    static constexpr int MAXPIX = TILES * 128 + (L0 ? KS : KS - 1) * WP + KS + 1;   // exclusive bound of pixels a tile may touch
     static constexpr int TAIL = round_up((MAXPIX > HPB * WP ? (MAXPIX - HPB * WP) : 0) * 16, 128) + 128;
     static constexpr int IMG_BYTES = SLOTS * SLOT_BYTES + TAIL;
     static constexpr int BAR_OFF = W_BYTES + IMG_BYTES;
     static constexpr int SMEM = BAR_OFF + 256 + NPAD * 4;
     static constexpr int TMEM_COLS = pow2_cols(2 * NPAD);
-    static_assert(CIN % 8 == 0 && (CIN == 8 || CIN % 16 == 0), "C_in must be 8 or a multiple of 16");
+    static_assert(CIN == 1 || (CIN % 8 == 0 && (CIN == 8 || CIN % 16 == 0)), "C_in must be 1, 8 or a multiple of 16");
     static_assert(NPAD % 16 == 0 && NPAD >= 16 && NPAD <= 64 && COUT <= NPAD && COUT % 8 == 0, "N tile");
     static_assert(HO % BANDS == 0, "bands must divide the output height");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
@@ -147,7 +148,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
                 mbar_wait(empty_bar(slot), (use & 1) ^ 1);
                 mbar_expect_tx(full_bar(slot), C::P * C::PLANE_BYTES);
                 const int n = view * n_per_view + i / C::BANDS, band = i % C::BANDS;
-                tma_load_4d(img_addr + slot * C::SLOT_BYTES, &tmap, full_bar(slot), 0, -C::PAD, band * C::HB - C::PAD, n * C::P);
+                tma_load_4d(img_addr + slot * C::SLOT_BYTES, &tmap, full_bar(slot), 0, C::L0 ? 0 : -C::PAD, band * C::HB - C::PAD, n * C::P);
             }
         }
     } else if (warp == 1) {
@@ -167,6 +168,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
                     const uint32_t d = tmem_base + buf * C::NPAD;
                     const uint32_t a0 = slot_addr + t * 2048;
                     int idx = 0;
+                    if constexpr (C::L0) {
+                        // K = (2 rows kh, kh+1) x (8 shifts = kw taps): one MMA per row pair, second K chunk = next image row
+#pragma unroll
+                        for (int j = 0; j < C::NJ; ++j, ++idx) {
+                            const uint64_t ad = smem_desc(a0 + (2 * j * C::WP) * 16, C::WP * 16, 128);
+                            const uint64_t bd = smem_desc(w_addr + idx * C::NPAD * 32, C::NPAD * 16, 128);
+                            mma_bf16(d, ad, bd, idesc, idx > 0);
+                        }
+                    } else {
 #pragma unroll
                     for (int kh = 0; kh < C::KS; ++kh) {
                         if constexpr (C::CIN == 8) {
@@ -187,6 +197,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
                                 }
                             }
                         }
+                    }
                     }
                     mma_commit(tfull_bar(buf));
                 }
@@ -296,7 +307,15 @@ __global__ void conv_tc_prep_weights_kernel(const float* __restrict__ w, __nv_bf
     const int ng = (e >> 6) % NG, c = (e / (64 * NG)) & 1, m = e / (128 * NG);
     const int co = ng * 8 + r;
     int kh, kw, ci;
-    if (CIN == 8) {
+    if (CIN == 1) {                 // shift8 first layer: chunk c of MMA m is image row kh = 2m + c, k8 is the kw tap
+        kh = 2 * m + c;
+        kw = k8;
+        ci = 0;
+        float v1 = 0.f;
+        if (kh < KS && kw < KS && co < COUT) v1 = w[(co * KS + kh) * KS + kw];
+        out[e] = __float2bfloat16_rn(v1);
+        return;
+    } else if (CIN == 8) {
         const int NJ = (KS + 1) / 2;
         kh = m / NJ;
         kw = 2 * (m % NJ) + c;
@@ -331,6 +350,25 @@ __global__ void pack_act8_kernel(const float* __restrict__ x, uint4* __restrict_
     out[i] = pk;
 }
 
+// fp32 [N][H][W] -> bf16 shift8 [N][H][W+pad][8]: unit (y, xs) = x[y][xs-pad .. xs-pad+7] (zero outside the row): the
+// 16-byte "pixel" of the first-layer tensor-core convolutions, whose kw taps are the K dimension.  The left padding
+// columns are materialised (their units reach into the row); right / top / bottom padding is TMA zero fill.
+__global__ void pack_shift8_kernel(const float* __restrict__ x, uint4* __restrict__ out, long n_units, int W, int pad) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_units) return;
+    const int WT = W + pad;
+    const int xs = (int)(i % WT);
+    const long row = i / WT;
+    const float* r = x + row * W;
+    float f[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int xc = xs - pad + c;
+        f[c] = (xc >= 0 && xc < W) ? __ldg(r + xc) : 0.f;
+    }
+    out[i] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
 template <class C>
 int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* out, double* stats, int N, int n_per_view, int out_bf16,
                    cudaStream_t st) {
@@ -344,8 +382,9 @@ int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* ou
         configured = true;
     }
     CUtensorMap tm;
-    const uint64_t dims[4] = {8, (uint64_t)C::WIN, (uint64_t)C::HIN, (uint64_t)N * C::P};
-    const uint64_t strides[3] = {16, (uint64_t)C::WIN * 16, (uint64_t)C::WIN * C::HIN * 16};
+    constexpr uint64_t WT = C::L0 ? C::WIN + C::PAD : C::WIN;      // the shift8 image carries its left padding columns
+    const uint64_t dims[4] = {8, WT, (uint64_t)C::HIN, (uint64_t)N * C::P};
+    const uint64_t strides[3] = {16, WT * 16, WT * C::HIN * 16};
     const uint32_t box[4] = {8, (uint32_t)C::WP, (uint32_t)C::HPB, (uint32_t)C::P};
     int rc = encode_tmap_bf16_4d(&tm, x, dims, strides, box);
     if (rc) return rc;
@@ -366,8 +405,10 @@ int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* ou
 //               moved by kh*WP pixels -> rows (kw', ci) of the accumulator, kw' < K are the real taps;
 //   B (N = C_out): the dz image, N units = channel planes (SBO = plane stride); dz is loaded with the PADDED pitch, its
 //               junk columns are TMA zero fill, so junk pixels contribute nothing.
-// One TMEM accumulator [64 x C_out] per (kh, x plane) lives for the whole kernel; a last accumulator multiplies dz by a
-// block of ones = the bias gradient.  Per-CTA partials go to `work`, reduced in a fixed order by wgrad_reduce_kernel.
+// One TMEM accumulator [64 x C_out] per (kh, x plane) lives for the whole kernel.  Per-CTA partials go to `work`, reduced
+// in a fixed order by wgrad_reduce_kernel.  (The bias gradient sum(dz) is produced by the BatchNorm-backward kernel that
+// writes dz.)  First layers (C_in = 1) read the shift8 image: the 8 M units are the image rows kh (SBO = one row) and the 8
+// elements of a unit are the kw shifts, so ONE accumulator holds all K*K taps.
 constexpr int hbz_for(int hb, int wp) {
     int h = hb;
     while ((h * wp) % 16) ++h;
@@ -377,7 +418,8 @@ constexpr int hbz_for(int hb, int wp) {
 template <int CIN_, int COUT_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int PSPLIT_>
 struct TcWgCfg {
     static constexpr int CIN = CIN_, COUT = COUT_, HIN = HIN_, WIN = WIN_, KS = KS_, PAD = PAD_, BANDS = BANDS_, SLOTS = SLOTS_, PSPLIT = PSPLIT_;
-    static constexpr int P_IN = CIN / 8, P_OUT = COUT / 8, PI = P_IN / PSPLIT;
+    static constexpr bool L0 = (CIN == 1);                       // first layer over the shift8 image: rows = (kh, kw) in ONE accumulator
+    static constexpr int P_IN = L0 ? 1 : CIN / 8, P_OUT = COUT / 8, PI = P_IN / PSPLIT;
     static constexpr int WP = WIN + 2 * PAD;
     static constexpr int HO = HIN + 2 * PAD - KS + 1, WO = WP - KS + 1;
     static constexpr int HB = HO / BANDS, HPB = HB + KS - 1;
@@ -386,18 +428,18 @@ struct TcWgCfg {
     static constexpr int PLANE_X = HPB * WP * 16, PLANE_Z = HBZ * WP * 16;
     static constexpr int X_BYTES = round_up(PI * PLANE_X, 128), Z_BYTES = round_up(P_OUT * PLANE_Z, 128);
     static constexpr int SLOT_BYTES = X_BYTES + Z_BYTES;
-    static constexpr int NACC = KS * PI + 1;
+    static constexpr int NACC = L0 ? 1 : KS * PI;
     static constexpr int TMEM_COLS = pow2_cols(NACC * COUT);
     static constexpr int ONES_OFF = SLOTS * SLOT_BYTES;
-    static constexpr int BAR_OFF = ONES_OFF + 2048;
+    static constexpr int BAR_OFF = ONES_OFF;
     static constexpr int SMEM = BAR_OFF + 256;
     static constexpr int DW = COUT * CIN * KS * KS;
-    static constexpr int PART = DW + COUT;                          // floats per CTA partial
+    static constexpr int PART = DW;                                 // floats per CTA partial
     static_assert(P_IN % PSPLIT == 0 && HO % BANDS == 0, "splits");
     static_assert(BANDS == 1 || HBZ == HB, "row bands need HB*WP to be a multiple of 16");
     static_assert(NACC * COUT <= 512, "TMEM columns");
     static_assert(KS <= 8 && COUT % 8 == 0 && COUT >= 8 && COUT <= 256, "shape");
-    static_assert((KSTEPS * 16 + (KS - 1) * WP + 8 - HPB * WP) * 16 <= Z_BYTES, "x overrun must stay inside the slot");
+    static_assert((KSTEPS * 16 + (L0 ? 7 : KS - 1) * WP + 8 - HPB * WP) * 16 <= Z_BYTES, "x overrun must stay inside the slot");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -418,8 +460,6 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     {
         uint4* z = reinterpret_cast<uint4*>(smem);
         for (int i = threadIdx.x; i < C::ONES_OFF / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
-        uint32_t* o = reinterpret_cast<uint32_t*>(smem + C::ONES_OFF);
-        for (int i = threadIdx.x; i < 512; i += blockDim.x) o[i] = 0x3F803F80u;      // bf16 1.0 pairs
         fence_proxy_async_smem();
     }
     if (warp == 0 && lane == 0) {
@@ -447,14 +487,13 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 mbar_expect_tx(full_bar(slot), C::PI * C::PLANE_X + C::P_OUT * C::PLANE_Z);
                 const int n = i / C::BANDS, band = i % C::BANDS;
                 const uint32_t sa = smem0 + slot * C::SLOT_BYTES;
-                tma_load_4d(sa, &tmap_x, full_bar(slot), 0, -C::PAD, band * C::HB - C::PAD, n * C::P_IN + split * C::PI);
+                tma_load_4d(sa, &tmap_x, full_bar(slot), 0, C::L0 ? 0 : -C::PAD, band * C::HB - C::PAD, n * C::P_IN + split * C::PI);
                 tma_load_4d(sa + C::X_BYTES, &tmap_z, full_bar(slot), 0, 0, band * C::HB, n * C::P_OUT);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = idesc_bf16(C::COUT, true, true, 64);
-            const uint64_t ones_desc = smem_desc(smem0 + C::ONES_OFF, 1024, 128);
             for (int i = i0; i < i1; ++i) {
                 const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
                 mbar_wait(full_bar(slot), use & 1);
@@ -463,15 +502,20 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 for (int ks = 0; ks < C::KSTEPS; ++ks) {
                     const uint32_t acc = (i > i0 || ks > 0) ? 1u : 0u;
                     const uint64_t bd = smem_desc(za + ks * 256, 128, C::PLANE_Z);
+                    if constexpr (C::L0) {
+                        // M units = 8 image rows kh (SBO = one row), the 8 elements of a unit = the kw shifts
+                        const uint64_t ad = smem_desc(xa + ks * 256, 128, C::WP * 16);
+                        mma_bf16(tmem_base, ad, bd, idesc, acc);
+                    } else {
 #pragma unroll
-                    for (int kh = 0; kh < C::KS; ++kh) {
+                        for (int kh = 0; kh < C::KS; ++kh) {
 #pragma unroll
-                        for (int pl = 0; pl < C::PI; ++pl) {
-                            const uint64_t ad = smem_desc(xa + pl * C::PLANE_X + (ks * 16 + kh * C::WP) * 16, 128, 16);
-                            mma_bf16(tmem_base + (kh * C::PI + pl) * C::COUT, ad, bd, idesc, acc);
+                            for (int pl = 0; pl < C::PI; ++pl) {
+                                const uint64_t ad = smem_desc(xa + pl * C::PLANE_X + (ks * 16 + kh * C::WP) * 16, 128, 16);
+                                mma_bf16(tmem_base + (kh * C::PI + pl) * C::COUT, ad, bd, idesc, acc);
+                            }
                         }
                     }
-                    mma_bf16(tmem_base + (C::KS * C::PI) * C::COUT, ones_desc, bd, idesc, acc);
                 }
                 mma_commit(empty_bar(slot));
             }
@@ -488,9 +532,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             tc_fence_after_sync();
         }
 #pragma unroll 1
-        for (int a = 0; a <= C::KS * C::PI; ++a) {
+        for (int a = 0; a < C::NACC; ++a) {
             const int kh = a / C::PI, pl = a % C::PI;
-            const bool is_bias = (a == C::KS * C::PI);
 #pragma unroll
             for (int cc = 0; cc < (C::COUT + 15) / 16; ++cc) {
                 uint32_t v[16];
@@ -505,8 +548,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 for (int t = 0; t < 16; ++t) {
                     const int co = cc * 16 + t;
                     if (co < C::COUT) {
-                        if (is_bias) {
-                            if (m == 0 && lane < 16 && split == 0) part[C::DW + co] = __uint_as_float(v[t]);
+                        if constexpr (C::L0) {      // row m = (kh = j, kw = ci8)
+                            if (lane < 16 && j < C::KS && ci8 < C::KS) part[(co * C::KS + j) * C::KS + ci8] = __uint_as_float(v[t]);
                         } else if (rowok) {
                             const int ci = (split * C::PI + pl) * 8 + ci8;
                             part[((co * C::CIN + ci) * C::KS + kh) * C::KS + j] = __uint_as_float(v[t]);
@@ -524,15 +567,13 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     }
 }
 
-// dw[e] (+)= sum over CTA partials in a fixed order (deterministic); the last COUT entries of a partial are the bias gradient
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ work, int n_parts, int part, int dw_n,
-                                                           float* __restrict__ dw, float* __restrict__ db) {
+// dw[e] = sum over CTA partials in a fixed order (deterministic)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ work, int n_parts, int part, float* __restrict__ dw) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= part) return;
     float acc = 0.f;
     for (int p = 0; p < n_parts; ++p) acc += work[(long)p * part + e];
-    if (e < dw_n) dw[e] = acc;
-    else if (db != nullptr) db[e - dw_n] = acc;
+    dw[e] = acc;
 }
 
 template <class C>
@@ -544,7 +585,7 @@ int wgrad_ctas(int N) {
 }
 
 template <class C>
-int launch_conv_tc_wgrad(const void* x, const void* dz, float* dw, float* db, float* work, int N, cudaStream_t st, int64_t* need) {
+int launch_conv_tc_wgrad(const void* x, const void* dz, float* dw, float* work, int N, cudaStream_t st, int64_t* need) {
     const int G = wgrad_ctas<C>(N);
     if (need) {
         *need = (int64_t)G * C::PART;
@@ -561,8 +602,9 @@ int launch_conv_tc_wgrad(const void* x, const void* dz, float* dw, float* db, fl
     }
     CUtensorMap tx, tz;
     {
-        const uint64_t dims[4] = {8, (uint64_t)C::WIN, (uint64_t)C::HIN, (uint64_t)N * C::P_IN};
-        const uint64_t strides[3] = {16, (uint64_t)C::WIN * 16, (uint64_t)C::WIN * C::HIN * 16};
+        constexpr uint64_t WT = C::L0 ? C::WIN + C::PAD : C::WIN;
+        const uint64_t dims[4] = {8, WT, (uint64_t)C::HIN, (uint64_t)N * C::P_IN};
+        const uint64_t strides[3] = {16, WT * 16, WT * C::HIN * 16};
         const uint32_t box[4] = {8, (uint32_t)C::WP, (uint32_t)C::HPB, (uint32_t)C::PI};
         int rc = encode_tmap_bf16_4d(&tx, x, dims, strides, box);
         if (rc) return rc;
@@ -577,7 +619,7 @@ int launch_conv_tc_wgrad(const void* x, const void* dz, float* dw, float* db, fl
     conv_tc_wgrad_kernel<C><<<dim3(G, 1, C::PSPLIT), 192, C::SMEM, st>>>(tx, tz, work, N);
     int rc = launch_status("conv_tc_wgrad_kernel");
     if (rc) return rc;
-    wgrad_reduce_kernel<<<(C::PART + 255) / 256, 256, 0, st>>>(work, G, C::PART, C::DW, dw, db);
+    wgrad_reduce_kernel<<<(C::PART + 255) / 256, 256, 0, st>>>(work, G, C::PART, dw);
     return launch_status("wgrad_reduce_kernel");
 }
 
@@ -587,6 +629,9 @@ using WgA2 = TcWgCfg<16, 32, 28, 28, 5, 2, 1, 2, 1>;
 using WgA3 = TcWgCfg<32, 64, 14, 14, 5, 2, 1, 3, 4>;
 using WgI1 = TcWgCfg<32, 64, 14, 14, 5, 0, 1, 4, 4>;
 using WgS1 = TcWgCfg<32, 64, 14, 14, 3, 1, 1, 3, 2>;
+using WgA0 = TcWgCfg<1, 8, 112, 112, 5, 2, 7, 3, 1>;      // first layers (shift8 image)
+using WgI0 = TcWgCfg<1, 32, 28, 28, 5, 2, 1, 3, 1>;
+using WgS0 = TcWgCfg<1, 32, 28, 28, 3, 1, 1, 3, 1>;
 
 //                         CIN COUT NPAD HIN  WIN KS PAD BANDS SLOTS
 using CfgA1 = TcCfg<8, 16, 16, 56, 56, 5, 2, 2, 4>;      // audio conv2 forward
@@ -597,6 +642,9 @@ using CfgA1d = TcCfg<16, 8, 16, 56, 56, 5, 2, 2, 3>;     // data gradients (C_in
 using CfgA2d = TcCfg<32, 16, 16, 28, 28, 5, 2, 1, 2>;
 using CfgA3d = TcCfg<64, 32, 32, 14, 14, 5, 2, 1, 2>;
 using CfgI1d = TcCfg<64, 32, 32, 10, 10, 5, 4, 1, 2>;
+using CfgA0 = TcCfg<1, 8, 16, 112, 112, 5, 2, 4, 3>;     // first layers on the shift8 image: audio conv1
+using CfgI0 = TcCfg<1, 32, 32, 28, 28, 5, 2, 1, 4>;      //   image conv1
+using CfgS0 = TcCfg<1, 32, 32, 28, 28, 3, 1, 1, 4>;      //   image_simple conv1
 using CfgS1 = TcCfg<32, 64, 64, 14, 14, 3, 1, 1, 4>;     // image_simple conv2 forward / its data gradient
 using CfgS1d = TcCfg<64, 32, 32, 14, 14, 3, 1, 1, 4>;
 
@@ -610,20 +658,21 @@ extern "C" {
 int b200_conv_tc_supported(int Cin, int Cout, int H, int W, int K, int pad) {
 #define TC_MATCH(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) return 1;
     TC_MATCH(CfgA1) TC_MATCH(CfgA2) TC_MATCH(CfgA3) TC_MATCH(CfgI1) TC_MATCH(CfgA1d) TC_MATCH(CfgA2d) TC_MATCH(CfgA3d) TC_MATCH(CfgI1d)
-    TC_MATCH(CfgS1) TC_MATCH(CfgS1d)
+    TC_MATCH(CfgS1) TC_MATCH(CfgS1d) TC_MATCH(CfgA0) TC_MATCH(CfgI0) TC_MATCH(CfgS0)
 #undef TC_MATCH
     return 0;
 }
 
 int64_t b200_conv_tc_weight_bytes(int Cin, int Cout, int K) {
     const int npad = (Cout + 15) / 16 * 16;
-    const int nmma = (Cin == 8) ? K * ((K + 1) / 2) : K * K * (Cin / 16);
+    const int nmma = (Cin == 1) ? (K + 1) / 2 : (Cin == 8) ? K * ((K + 1) / 2) : K * K * (Cin / 16);
     return (int64_t)nmma * npad * 32;
 }
 
 int b200_conv_tc_prep_weights(const float* w, void* out, int Cin, int Cout, int K, int flip, void* stream) {
     B200_REQUIRE(w && out, -1, "conv_tc_prep_weights: null pointer");
-    B200_REQUIRE(Cin == 8 || (Cin % 16 == 0 && Cin > 0), -2, "conv_tc_prep_weights: C_in must be 8 or a multiple of 16 (got %d)", Cin);
+    B200_REQUIRE(Cin == 1 || Cin == 8 || (Cin % 16 == 0 && Cin > 0), -2, "conv_tc_prep_weights: C_in must be 1, 8 or a multiple of 16 (got %d)", Cin);
+    B200_REQUIRE(!(Cin == 1 && flip), -2, "conv_tc_prep_weights: the first layer has no data gradient");
     B200_REQUIRE(Cout % 8 == 0 && Cout > 0 && Cout <= 64, -2, "conv_tc_prep_weights: C_out must be a multiple of 8, <= 64 (got %d)", Cout);
     const int npad = (Cout + 15) / 16 * 16;
     const int total = (int)(b200_conv_tc_weight_bytes(Cin, Cout, K) / 2);
@@ -632,11 +681,11 @@ int b200_conv_tc_prep_weights(const float* w, void* out, int Cin, int Cout, int 
     return launch_status("conv_tc_prep_weights_kernel");
 }
 
-static int wgrad_tc_dispatch(const void* x, const void* dz, float* dw, float* db, float* work, int N, int Cin, int Cout, int H, int W,
+static int wgrad_tc_dispatch(const void* x, const void* dz, float* dw, float* work, int N, int Cin, int Cout, int H, int W,
                              int K, int pad, cudaStream_t st, int64_t* need) {
 #define WG_RUN(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) \
-        return launch_conv_tc_wgrad<CFG>(x, dz, dw, db, work, N, st, need);
-    WG_RUN(WgA1) WG_RUN(WgA2) WG_RUN(WgA3) WG_RUN(WgI1) WG_RUN(WgS1)
+        return launch_conv_tc_wgrad<CFG>(x, dz, dw, work, N, st, need);
+    WG_RUN(WgA1) WG_RUN(WgA2) WG_RUN(WgA3) WG_RUN(WgI1) WG_RUN(WgS1) WG_RUN(WgA0) WG_RUN(WgI0) WG_RUN(WgS0)
 #undef WG_RUN
     set_error("conv_tc_wgrad: unsupported geometry Cin=%d Cout=%d H=%d W=%d K=%d pad=%d", Cin, Cout, H, W, K, pad);
     return -4;
@@ -644,16 +693,24 @@ static int wgrad_tc_dispatch(const void* x, const void* dz, float* dw, float* db
 
 int64_t b200_conv_tc_wgrad_work_floats(int N, int Cin, int Cout, int H, int W, int K, int pad) {
     int64_t need = 0;
-    int rc = wgrad_tc_dispatch(nullptr, nullptr, nullptr, nullptr, nullptr, N, Cin, Cout, H, W, K, pad, nullptr, &need);
+    int rc = wgrad_tc_dispatch(nullptr, nullptr, nullptr, nullptr, N, Cin, Cout, H, W, K, pad, nullptr, &need);
     return rc ? -1 : need;
 }
 
-int b200_conv_tc_wgrad(const void* x_act8, const void* dz_act8, float* dw, float* db, float* work, int N, int Cin, int Cout, int H, int W,
+int b200_conv_tc_wgrad(const void* x_act8, const void* dz_act8, float* dw, float* work, int N, int Cin, int Cout, int H, int W,
                        int K, int pad, void* stream) {
     B200_REQUIRE(x_act8 && dz_act8 && dw && work, -1, "conv_tc_wgrad: null pointer");
     B200_REQUIRE(N > 0, -2, "conv_tc_wgrad: N must be positive");
     B200_REQUIRE(((uintptr_t)x_act8 & 15) == 0 && ((uintptr_t)dz_act8 & 15) == 0, -3, "conv_tc_wgrad: pointers must be 16-byte aligned");
-    return wgrad_tc_dispatch(x_act8, dz_act8, dw, db, work, N, Cin, Cout, H, W, K, pad, as_stream(stream), nullptr);
+    return wgrad_tc_dispatch(x_act8, dz_act8, dw, work, N, Cin, Cout, H, W, K, pad, as_stream(stream), nullptr);
+}
+
+int b200_pack_shift8(const float* x, void* out, int N, int H, int W, int pad, void* stream) {
+    B200_REQUIRE(x && out, -1, "pack_shift8: null pointer");
+    B200_REQUIRE(N > 0 && H > 0 && W > 0 && pad >= 0, -2, "pack_shift8: bad shape");
+    const long px = (long)N * H * (W + pad);
+    pack_shift8_kernel<<<(unsigned)((px + 255) / 256), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<uint4*>(out), px, W, pad);
+    return launch_status("pack_shift8_kernel");
 }
 
 int b200_pack_act8(const float* x, void* out, int N, int C, int H, int W, void* stream) {
@@ -672,7 +729,7 @@ int b200_conv_tc(const void* x_act8, const void* wprep, const float* bias, void*
     cudaStream_t st = as_stream(stream);
 #define TC_RUN(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) \
         return launch_conv_tc<CFG>(x_act8, wprep, bias, out, stats, N, n_per_view, out_bf16, st);
-    TC_RUN(CfgA1) TC_RUN(CfgA2) TC_RUN(CfgA3) TC_RUN(CfgI1) TC_RUN(CfgA1d) TC_RUN(CfgA2d) TC_RUN(CfgA3d) TC_RUN(CfgI1d) TC_RUN(CfgS1) TC_RUN(CfgS1d)
+    TC_RUN(CfgA1) TC_RUN(CfgA2) TC_RUN(CfgA3) TC_RUN(CfgI1) TC_RUN(CfgA1d) TC_RUN(CfgA2d) TC_RUN(CfgA3d) TC_RUN(CfgI1d) TC_RUN(CfgS1) TC_RUN(CfgS1d) TC_RUN(CfgA0) TC_RUN(CfgI0) TC_RUN(CfgS0)
 #undef TC_RUN
     set_error("conv_tc: unsupported geometry Cin=%d Cout=%d H=%d W=%d K=%d pad=%d", Cin, Cout, H, W, K, pad);
     return -4;

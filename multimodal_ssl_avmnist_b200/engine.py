@@ -203,7 +203,8 @@ class DinoStepEngine:
         # tensor-core layers (tcgen05, bf16 act8 activations, fp32 accumulate): every C_in >= 8 convolution the library supports
         self.tc = {}
         for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers)):
-            self.tc[mod] = [precision == "bf16" and ops.conv_tc_supported(ci, co, hw, hw, k, pad) and ops.conv_tc_supported(co, ci, hw + 2 * pad - k + 1, hw + 2 * pad - k + 1, k, k - 1 - pad)
+            self.tc[mod] = [precision == "bf16" and ops.conv_tc_supported(ci, co, hw, hw, k, pad) and
+                            (ci == 1 or ops.conv_tc_supported(co, ci, hw + 2 * pad - k + 1, hw + 2 * pad - k + 1, k, k - 1 - pad))
                             for (conv, bn, ci, co, hw, k, pad) in layers]
         self._tcw = {}
         for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers)):
@@ -211,7 +212,8 @@ class DinoStepEngine:
                 if self.tc[mod][li]:
                     for role in ("s", "t"):
                         self._tcw[(role, mod, li)] = torch.empty(ops.conv_tc_weight_bytes(ci, co, k), dtype=torch.uint8, device=self.device)
-                    self._tcw[("flip", mod, li)] = torch.empty(ops.conv_tc_weight_bytes(co, ci, k), dtype=torch.uint8, device=self.device)
+                    if ci > 1:
+                        self._tcw[("flip", mod, li)] = torch.empty(ops.conv_tc_weight_bytes(co, ci, k), dtype=torch.uint8, device=self.device)
         self._ws = {}
         self._init_parameters()
         self.set_augmentation(augment_values)
@@ -288,6 +290,8 @@ class DinoStepEngine:
                     nv = N // B
                     tc = self.tc[mod][li]
                     next_tc = li + 1 < len(layers) and self.tc[mod][li + 1]
+                    if tc and ci == 1 and role == "s":
+                        w[f"{mod}.xs8"] = e(N, hw, hw + pad, 8, dtype=BF)       # first-layer input, shift8 (shared by the teacher)
                     if tc:
                         w[f"{role}.{mod}.z{li}"] = e(N, co // 8, ho, ho, 8, dtype=torch.float16)   # act8 layout, fp16: never an MMA operand
                     else:
@@ -310,6 +314,7 @@ class DinoStepEngine:
                         pmax = max(pmax, N * co * (ho // 2) * (ho // 2), N * ci * hw * hw if li > 0 else 0)
         w["dz"] = e(max(zmax, 4))
         w["dz8"] = e(max(z8max, 8), dtype=BF)
+        w["dbsum"] = torch.zeros(8, 128, dtype=torch.float64, device=dev)
         w["dp_a"], w["dp_b"] = e(pmax), e(pmax)
         w["wg_work"] = e(max(wg_work, 4))
         E, O, P = self.E, self.O, self.P
@@ -393,7 +398,7 @@ class DinoStepEngine:
             for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers):
                 if self.tc[mod][li]:
                     ops.conv_tc_prep_weights(P["enc." + conv + ".weight"], self._tcw[(role, mod, li)])
-                    if role == "s":
+                    if role == "s" and ci > 1:
                         ops.conv_tc_prep_weights(P["enc." + conv + ".weight"], self._tcw[("flip", mod, li)], flip=True)
 
     def _conv_stack(self, w, role, mod, layers, x, N, B, P, bns, train=True):
@@ -406,7 +411,12 @@ class DinoStepEngine:
             tc = self.tc[mod][li]
             next_tc = li + 1 < len(layers) and self.tc[mod][li + 1]
             stats.zero_()
-            if tc:
+            if tc and ci == 1:
+                xs8 = w[f"{mod}.xs8"]
+                if role == "s":
+                    ops.pack_shift8(cur.view(N, hw, hw), xs8, pad)
+                ops.conv_tc(xs8[:N], self._tcw[(role, mod, li)], P["enc." + conv + ".bias"], z, stats, B, co, k, pad)
+            elif tc:
                 ops.conv_tc(cur, self._tcw[(role, mod, li)], P["enc." + conv + ".bias"], z, stats, B, co, k, pad)
             else:
                 ops.conv_fwd(cur.view(N, ci, hw, hw), P["enc." + conv + ".weight"], P["enc." + conv + ".bias"], z, stats, B, pad)
@@ -474,6 +484,8 @@ class DinoStepEngine:
         S, G = self.S, self.G
         d_p = d_top
         BF = torch.bfloat16
+        if any(self.tc[mod]):
+            w["dbsum"].zero_()
         for li in range(len(layers) - 1, -1, -1):
             conv, bn, ci, co, hw, k, pad = layers[li]
             ho = hw + 2 * pad - k + 1
@@ -487,14 +499,16 @@ class DinoStepEngine:
                     d_p = d_p.view(N, co, ho // 2, ho // 2)
                 dz = w["dz8"][:z.numel()].view_as(z)
                 ops.bn_relu_pool8_bwd_reduce(z, d_p, sc, sh, mu, inv, sums, B)
-                ops.bn_relu_pool8_bwd_apply(z, d_p, sc, sh, mu, inv, sums, dz, B)
+                ops.bn_relu_pool8_bwd_apply(z, d_p, sc, sh, mu, inv, sums, dz, B, dbsum=w["dbsum"][li])
+                ops.bias_grad_finalize(w["dbsum"][li], G["enc." + conv + ".bias"])
             else:
                 dz = w["dz"][:z.numel()].view_as(z)
                 ops.bn_relu_pool_bwd_reduce(z, d_p, sc, sh, mu, inv, sums, B)
                 ops.bn_relu_pool_bwd_apply(z, d_p, sc, sh, mu, inv, sums, dz, B)
             ops.bn_param_grads(sums, G["enc." + bn + ".weight"], G["enc." + bn + ".bias"], N // B)
             if tc:
-                ops.conv_tc_wgrad(w[f"s.{mod}.p8{li - 1}"], dz, G["enc." + conv + ".weight"], G["enc." + conv + ".bias"], w["wg_work"], pad)
+                xin8 = w[f"{mod}.xs8"] if ci == 1 else w[f"s.{mod}.p8{li - 1}"]
+                ops.conv_tc_wgrad(xin8, dz, G["enc." + conv + ".weight"], w["wg_work"], pad)
             else:
                 xin = x if li == 0 else w[f"s.{mod}.p{li - 1}"]
                 ops.conv_bwd_weight(xin.view(N, ci, hw, hw), dz, G["enc." + conv + ".weight"], G["enc." + conv + ".bias"], w["wg_work"], pad)

@@ -212,12 +212,17 @@ def pack_act8(x, out):
 
 
 def conv_tc(x8, wprep, bias, out, stats, n_per_view, Cout, K, pad):
-    """x8: bf16 act8 [N, Cin/8, H, W, 8]; out: fp32 NCHW [N, Cout, Ho, Wo] or bf16 act8 [N, Cout/8, Ho, Wo, 8];
-    bias/stats may be None (data-gradient use)."""
-    N, P, H, W, _ = x8.shape
+    """x8: bf16 act8 [N, Cin/8, H, W, 8] (or the shift8 image [N, H, W, 8] of a first layer, Cin = 1); out: fp32 NCHW
+    [N, Cout, Ho, Wo] or bf16 / fp16 act8 [N, Cout/8, Ho, Wo, 8]; bias/stats may be None (data-gradient use)."""
+    if x8.dim() == 4:
+        N, H, W, _ = x8.shape
+        W -= pad
+        P = 0.125
+    else:
+        N, P, H, W, _ = x8.shape
     fmt = 1 if out.dtype == BF16 else 2 if out.dtype == torch.float16 else 0
     _lib.check(_lib_().b200_conv_tc(_ptr(x8, BF16), _ptr(wprep), _ptr(bias, F32) if bias is not None else None, _ptr(out),
-                                    _ptr(stats, F64) if stats is not None else None, N, n_per_view, P * 8, Cout, H, W, K, pad,
+                                    _ptr(stats, F64) if stats is not None else None, N, n_per_view, int(P * 8), Cout, H, W, K, pad,
                                     fmt, _stream()), "conv_tc")
 
 
@@ -228,12 +233,25 @@ def conv_tc_wgrad_work_floats(N, Cin, Cout, H, W, K, pad):
     return n
 
 
-def conv_tc_wgrad(x8, dz8, dw, db, work, pad):
-    """x8 [N, Cin/8, H, W, 8], dz8 [N, Cout/8, Ho, Wo, 8] bf16 act8 -> dw [Cout, Cin, K, K], db [Cout] (fp32)."""
-    N, P, H, W, _ = x8.shape
+def conv_tc_wgrad(x8, dz8, dw, work, pad):
+    """x8 [N, Cin/8, H, W, 8] (Cin = 1: the shift8 image [N, H, W, 8]), dz8 [N, Cout/8, Ho, Wo, 8] bf16 act8 -> dw [Cout, Cin, K, K]."""
+    N, H, W = x8.shape[0], x8.shape[-3], x8.shape[-2]
     Cout, Cin, K, _ = dw.shape
-    _lib.check(_lib_().b200_conv_tc_wgrad(_ptr(x8, BF16), _ptr(dz8, BF16), _ptr(dw, F32), _ptr(db, F32) if db is not None else None,
-                                          _ptr(work, F32), N, Cin, Cout, H, W, K, pad, _stream()), "conv_tc_wgrad")
+    if Cin == 1:
+        W -= pad
+    _lib.check(_lib_().b200_conv_tc_wgrad(_ptr(x8, BF16), _ptr(dz8, BF16), _ptr(dw, F32), _ptr(work, F32), N, Cin, Cout, H, W, K, pad,
+                                          _stream()), "conv_tc_wgrad")
+
+
+def pack_shift8(x, out, pad):
+    """fp32 [N, H, W] (or [N, 1, H, W]) -> bf16 shift8 [N, H, W + pad, 8] (pad = the convolution's padding)"""
+    N, H, W = x.shape[0], x.shape[-2], x.shape[-1]
+    assert tuple(out.shape) == (N, H, W + pad, 8)
+    _lib.check(_lib_().b200_pack_shift8(_ptr(x, F32), _ptr(out, BF16), N, H, W, pad, _stream()), "pack_shift8")
+
+
+def bias_grad_finalize(dbsum, db):
+    _lib.check(_lib_().b200_bias_grad_finalize(_ptr(dbsum, F64), _ptr(db, F32), db.numel(), _stream()), "bias_grad_finalize")
 
 
 def unpack_act8(x8, out):
@@ -265,10 +283,11 @@ def bn_relu_pool8_bwd_reduce(z8, dp, scale, shift, mean, invstd, sums, n_per_vie
                "bn_relu_pool8_bwd_reduce")
 
 
-def bn_relu_pool8_bwd_apply(z8, dp, scale, shift, mean, invstd, sums, dz8, n_per_view):
+def bn_relu_pool8_bwd_apply(z8, dp, scale, shift, mean, invstd, sums, dz8, n_per_view, dbsum=None):
     N, P, H, W, _ = z8.shape
     _lib.check(_lib_().b200_bn_relu_pool8_bwd_apply(_ptr(z8), _ptr(dp), _ptr(scale, F32), _ptr(shift, F32), _ptr(mean, F32),
-                                                    _ptr(invstd, F32), _ptr(sums, F64), _ptr(dz8, BF16), N, n_per_view, P * 8, H, W, _zf16(z8),
+                                                    _ptr(invstd, F32), _ptr(sums, F64), _ptr(dz8, BF16),
+                                                    _ptr(dbsum, F64) if dbsum is not None else None, N, n_per_view, P * 8, H, W, _zf16(z8),
                                                     _fmt(dp), _stream()), "bn_relu_pool8_bwd_apply")
 
 
@@ -425,6 +444,7 @@ def _wrap(name, fn):
         out = fn(*args, **kwargs)
         b.record()
         meta = tuple(tuple(t.shape) for t in args[:4] if isinstance(t, torch.Tensor))
+        meta = meta + (("i",) + tuple(int(v) for v in args if isinstance(v, int) and not isinstance(v, bool)),)
         _PROFILE.append((name, a, b, meta))
         return out
 

@@ -105,14 +105,11 @@ def test_conv_tc_weight_gradient(geom, N):
     ops.pack_act8(dz, dz8)
     work = torch.empty(ops.conv_tc_wgrad_work_floats(N, Cin, Cout, H, W, K, pad), device=DEV)
     dw = torch.full((Cout, Cin, K, K), float("nan"), device=DEV)
-    db = torch.full((Cout,), float("nan"), device=DEV)
-    ops.conv_tc_wgrad(x8, dz8, dw, db, work, pad)
+    ops.conv_tc_wgrad(x8, dz8, dw, work, pad)
     torch.cuda.synchronize()
     scale = float(wd.grad.abs().max())
     err = float((dw.double() - wd.grad).abs().max())
     assert err <= 3e-5 * scale, (geom, N, err, scale)
-    errb = float((db.double() - bd.grad).abs().max())
-    assert errb <= 3e-5 * float(bd.grad.abs().max()), (geom, N, errb)
 
 
 def _pack8(x):
@@ -170,6 +167,53 @@ def test_bn_relu_pool8(C, H, views, B, zdt):
         ops.bn_relu_pool8_bwd_reduce(z8, dpt, scale, shift, mean, invstd, sums, B)
         assert float(((sums - s_want).abs() / (s_want.abs() + 1.0)).max()) < 1e-5
         dz8 = torch.empty(z8.shape, dtype=torch.bfloat16, device=DEV)
-        ops.bn_relu_pool8_bwd_apply(z8, dpt, scale, shift, mean, invstd, s_want.contiguous(), dz8, B)
+        dbsum = torch.zeros(C, dtype=torch.float64, device=DEV)
+        ops.bn_relu_pool8_bwd_apply(z8, dpt, scale, shift, mean, invstd, s_want.contiguous(), dz8, B, dbsum=dbsum)
         got = _unpack8(dz8)
         assert float((got - want_dz).abs().max()) <= 8e-3 * float(want_dz.abs().max())
+        db_want = want_dz.double().sum(dim=(0, 2, 3))
+        db = torch.empty(C, device=DEV)
+        ops.bias_grad_finalize(dbsum, db)
+        assert float((db.double() - db_want).abs().max()) <= 1e-4 * float(want_dz.abs().sum(dim=(0, 2, 3)).max())
+
+
+# first layers (C_in = 1) on the shift8 image: (Cout, H, K, pad)
+FIRST = [(8, 112, 5, 2), (32, 28, 5, 2), (32, 28, 3, 1)]
+
+
+@pytest.mark.parametrize("geom", FIRST)
+@pytest.mark.parametrize("views,B", [(1, 2), (3, 5), (7, 12)])
+def test_first_layer_shift8_forward_and_weight_gradient(geom, views, B):
+    Cout, H, K, pad = geom
+    assert ops.conv_tc_supported(1, Cout, H, H, K, pad)
+    g = torch.Generator().manual_seed(Cout + H + views)
+    N = views * B
+    x = torch.rand(N, 1, H, H, generator=g).to(DEV)
+    w = (torch.randn(Cout, 1, K, K, generator=g) / K).to(DEV)
+    b = torch.randn(Cout, generator=g).to(DEV)
+    x8 = torch.empty(N, H, H + pad, 8, dtype=torch.bfloat16, device=DEV)
+    ops.pack_shift8(x, x8, pad)
+    xb = _bf(x)
+    assert torch.equal(x8[:, :, pad:, 0].float(), xb[:, 0]) and float(x8[:, :, :pad, 0].abs().max()) == 0.0
+    assert torch.equal(x8[:, :, :H - 3 + pad, 3].float(), xb[:, 0, :, 3 - pad:]) and float(x8[:, :, H - 3 + pad:, 3].abs().max()) == 0.0
+    want = F.conv2d(xb.double(), _bf(w).double(), b.double(), padding=pad).float()
+    wp = torch.empty(ops.conv_tc_weight_bytes(1, Cout, K), dtype=torch.uint8, device=DEV)
+    ops.conv_tc_prep_weights(w, wp)
+    stats = torch.zeros(views, Cout, 2, dtype=torch.float64, device=DEV)
+    z = torch.full((N, Cout // 8, H, H, 8), float("nan"), dtype=torch.float16, device=DEV)
+    ops.conv_tc(x8, wp, b, z, stats, B, Cout, K, pad)
+    torch.cuda.synchronize()
+    assert float((_unpack8(z) - want).abs().max()) <= 1e-3 * float(want.abs().max())
+    wv = want.view(views, B, Cout, H, H).double()
+    s_want = torch.stack([wv.sum(dim=(1, 3, 4)), (wv * wv).sum(dim=(1, 3, 4))], dim=-1)
+    assert float(((stats - s_want).abs() / (s_want.abs() + 1.0)).max()) < 1e-5
+    # weight gradient
+    dz = torch.randn(N, Cout, H, H, generator=g).to(DEV)
+    wd = torch.zeros(Cout, 1, K, K, dtype=torch.float64, device=DEV, requires_grad=True)
+    F.conv2d(xb.double(), wd, None, padding=pad).backward(_bf(dz).double())
+    dz8 = _pack8(dz)
+    work = torch.empty(ops.conv_tc_wgrad_work_floats(N, 1, Cout, H, H, K, pad), device=DEV)
+    dw = torch.full((Cout, 1, K, K), float("nan"), device=DEV)
+    ops.conv_tc_wgrad(x8, dz8, dw, work, pad)
+    torch.cuda.synchronize()
+    assert float((dw.double() - wd.grad).abs().max()) <= 3e-5 * float(wd.grad.abs().max())

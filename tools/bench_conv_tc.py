@@ -41,13 +41,12 @@ def main():
         zf = torch.empty(N, Cout, Ho, Ho, device=DEV)
         dx8 = torch.empty(N, Cin // 8, H, H, 8, dtype=torch.bfloat16, device=DEV)
         dw = torch.empty(Cout, Cin, K, K, device=DEV)
-        db = torch.empty(Cout, device=DEV)
         work = torch.empty(ops.conv_tc_wgrad_work_floats(N, Cin, Cout, H, H, K, pad), device=DEV)
         fl = 2.0 * N * Cout * Ho * Ho * Cin * K * K
         t_f8 = timeit(lambda: ops.conv_tc(x8, wp, b, z8, stats, B, Cout, K, pad))
         t_ff = timeit(lambda: ops.conv_tc(x8, wp, b, zf, stats, B, Cout, K, pad))
         t_d = timeit(lambda: ops.conv_tc(dz8, wpf, None, dx8, None, N, Cin, K, K - 1 - pad))
-        t_w = timeit(lambda: ops.conv_tc_wgrad(x8, dz8, dw, db, work, pad))
+        t_w = timeit(lambda: ops.conv_tc_wgrad(x8, dz8, dw, work, pad))
         by_f = x8.numel() * 2 + z8.numel() * 2
         rows.append({"layer": name, "N": N, "gflop": fl / 1e9, "fwd_bf16_ms": t_f8, "fwd_f32out_ms": t_ff, "dgrad_ms": t_d, "wgrad_ms": t_w,
                      "fwd_tflops": fl / t_f8 / 1e9, "fwd_gbs": by_f / t_f8 / 1e6, "dgrad_tflops": fl / t_d / 1e9, "wgrad_tflops": fl / t_w / 1e9,
