@@ -107,23 +107,30 @@ __device__ __forceinline__ int argmax4(float y0, float y1, float y2, float y3, f
 // dp_fmt 0: fp32 NCHW [N][C][HP][WP]; 1: bf16 act8.  APPLY = false: sums[view][c] += {sum g, sum g*xhat};
 // APPLY = true: dz8 = a*(g_at_argmax - mean(g) - xhat*mean(g*xhat)) for all four window positions.
 template <bool APPLY, bool ZF16>
-__global__ void __launch_bounds__(256) bn_relu_pool8_bwd_kernel(const uint4* __restrict__ z8, const void* __restrict__ dp,
+__global__ void __launch_bounds__(256, 3) bn_relu_pool8_bwd_kernel(const uint4* __restrict__ z8, const void* __restrict__ dp,
                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                 double* __restrict__ sums, uint4* __restrict__ dz8, double* __restrict__ dbsum,
                                                                 int n_per_view, int C, int H, int W, int dp_fmt) {
     const Tile t = make_tile(n_per_view, C, H, W);
     const int oct = blockIdx.y, v = blockIdx.z;
-    float a[8], b[8], mu[8], is[8], k1[8], k2[8], s1[8], s2[8];
+    // per-channel constants: y = a*z + b decides arg-max / ReLU; reduce: xhat = z*is + nm (nm = -mu*is);
+    // apply: dz = a*(dy - k1 - xhat*k2) = ca*z + cb + (a*g at the arg-max), ca = -a*is*k2, cb = -a*(k1 + nm*k2)
+    float a[8], b[8], c0[8], c1[8], s1[8], s2[8];
     const float inv_cnt = 1.0f / ((float)n_per_view * (float)H * (float)W);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = v * C + oct * 8 + j;
-        a[j] = __ldg(scale + c); b[j] = __ldg(shift + c); mu[j] = __ldg(mean + c); is[j] = __ldg(invstd + c);
+        a[j] = __ldg(scale + c); b[j] = __ldg(shift + c);
+        const float is = __ldg(invstd + c), nm = -__ldg(mean + c) * is;
         s1[j] = s2[j] = 0.f;
         if (APPLY) {
-            k1[j] = (float)sums[(size_t)c * 2] * inv_cnt;
-            k2[j] = (float)sums[(size_t)c * 2 + 1] * inv_cnt;
+            const float k1 = (float)sums[(size_t)c * 2] * inv_cnt, k2 = (float)sums[(size_t)c * 2 + 1] * inv_cnt;
+            c0[j] = -a[j] * is * k2;
+            c1[j] = -a[j] * (k1 + nm * k2);
+        } else {
+            c0[j] = is;
+            c1[j] = nm;
         }
     }
     const int hw = t.HP * t.WP;
@@ -145,7 +152,6 @@ __global__ void __launch_bounds__(256) bn_relu_pool8_bwd_kernel(const uint4* __r
 #pragma unroll
             for (int j = 0; j < 8; ++j) g[j] = __ldg(gp + (long)j * hw);
         }
-        float o[4][8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float m;
@@ -154,22 +160,22 @@ __global__ void __launch_bounds__(256) bn_relu_pool8_bwd_kernel(const uint4* __r
             if (!APPLY) {
                 const float zk = (k == 0) ? w[0][j] : (k == 1) ? w[1][j] : (k == 2) ? w[2][j] : w[3][j];
                 s1[j] += gj;
-                s2[j] += gj * ((zk - mu[j]) * is[j]);
+                s2[j] += gj * fmaf(zk, c0[j], c1[j]);
             } else {
+                const float ag = a[j] * gj;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float xh = (w[q][j] - mu[j]) * is[j];
-                    o[q][j] = a[j] * (((q == k) ? gj : 0.f) - k1[j] - xh * k2[j]);
-                    s1[j] += o[q][j];
+                    w[q][j] = fmaf(c0[j], w[q][j], c1[j]) + ((q == k) ? ag : 0.f);      // dz overwrites z in registers
+                    s1[j] += w[q][j];
                 }
             }
         }
         if (APPLY) {
             uint4* zo = dz8 + zoff;
-            zo[0] = pack8(o[0]);
-            zo[1] = pack8(o[1]);
-            zo[W] = pack8(o[2]);
-            zo[W + 1] = pack8(o[3]);
+            zo[0] = pack8(w[0]);
+            zo[1] = pack8(w[1]);
+            zo[W] = pack8(w[2]);
+            zo[W + 1] = pack8(w[3]);
         }
     }
     if (APPLY) {

@@ -355,21 +355,23 @@ __device__ int sample_chain(const int32_t* spec, int S, Draw& d, int32_t* rec /*
 }
 
 constexpr int NGROUPS = 784;
-__global__ void __launch_bounds__(128) aug_sample_kernel(const int32_t* __restrict__ spec, int B, int Vg, int Vl, uint64_t seed,
-                                                         uint64_t step, int32_t* __restrict__ img_ops, int32_t* __restrict__ aud_ops,
-                                                         uint32_t* __restrict__ group_bits) {
+__global__ void __launch_bounds__(32) aug_sample_kernel(const int32_t* __restrict__ spec, int B, int Vg, int Vl, uint64_t seed,
+                                                        uint64_t step, int32_t* __restrict__ img_ops, int32_t* __restrict__ aud_ops,
+                                                        uint32_t* __restrict__ group_bits) {
+    // one warp per (sample, view) record: lane 0 replays the two op chains (sequential by nature) and draws the grouped-masking
+    // subset with a partial Fisher-Yates shuffle (gc draws instead of ranking 784 random keys); the warp stages and copies.
     __shared__ int32_t sspec[4 * B200_AUG_MAX_OPS * 8];
     __shared__ int32_t rec_i[B200_AUG_MAX_OPS * 8], rec_a[B200_AUG_MAX_OPS * 8];
-    __shared__ int gcount;
-    __shared__ uint32_t keys[NGROUPS];
+    __shared__ uint16_t perm[NGROUPS];
     __shared__ uint32_t bits[B200_AUG_GROUP_WORDS];
     const int V = Vg + Vl;
     const int b = blockIdx.x / V, v = blockIdx.x - b * V;
     const size_t rec = (size_t)b * V + v;
     const int tid = threadIdx.x;
-    for (int i = tid; i < 4 * B200_AUG_MAX_OPS * 8; i += blockDim.x) sspec[i] = __ldg(spec + i);
+    for (int i = tid; i < 4 * B200_AUG_MAX_OPS * 8; i += 32) sspec[i] = __ldg(spec + i);
+    for (int i = tid; i < NGROUPS; i += 32) perm[i] = (uint16_t)i;
     if (tid < B200_AUG_GROUP_WORDS) bits[tid] = 0u;
-    __syncthreads();
+    __syncwarp();
     const bool local = v >= Vg;
     const uint64_t stream = (step << 36) ^ ((uint64_t)rec << 4);
     if (tid == 0) {
@@ -377,27 +379,21 @@ __global__ void __launch_bounds__(128) aug_sample_kernel(const int32_t* __restri
         int gc;
         sample_chain(sspec + (local ? 1 : 0) * B200_AUG_MAX_OPS * 8, 28, di, rec_i, &gc);
         sample_chain(sspec + (local ? 3 : 2) * B200_AUG_MAX_OPS * 8, 112, da, rec_a, &gc);
-        gcount = gc;
-    }
-    __syncthreads();
-    const int gc = gcount;
-    if (gc > 0) {
-        // uniformly random subset of gc groups: rank of a random key (ties broken by index) < gc
+        if (gc > NGROUPS) gc = NGROUPS;
         Philox rng(seed);
-        for (int g = tid; g < NGROUPS; g += blockDim.x) keys[g] = rng((uint64_t)g, stream | 4).x;
-        __syncthreads();
-        for (int g = tid; g < NGROUPS; g += blockDim.x) {
-            const uint32_t kg = keys[g];
-            int rank = 0;
-            for (int h = 0; h < NGROUPS; ++h) {
-                const uint32_t kh = keys[h];
-                rank += (kh < kg) || (kh == kg && h < g);
-            }
-            if (rank < gc) atomicOr(&bits[g >> 5], 1u << (g & 31));
+        uint4 r = make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < gc; ++i) {           // uniformly random subset of gc groups
+            if ((i & 3) == 0) r = rng((uint64_t)(i >> 2), stream | 4);
+            const uint32_t u = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
+            const int j = i + (int)(((uint64_t)u * (uint32_t)(NGROUPS - i)) >> 32);
+            const uint16_t pj = perm[j];
+            perm[j] = perm[i];
+            perm[i] = pj;
+            bits[pj >> 5] |= 1u << (pj & 31);
         }
-        __syncthreads();
     }
-    for (int i = tid; i < B200_AUG_MAX_OPS * 8; i += blockDim.x) {
+    __syncwarp();
+    for (int i = tid; i < B200_AUG_MAX_OPS * 8; i += 32) {
         img_ops[rec * (B200_AUG_MAX_OPS * 8) + i] = rec_i[i];
         aud_ops[rec * (B200_AUG_MAX_OPS * 8) + i] = rec_a[i];
     }
@@ -439,7 +435,7 @@ int b200_aug_sample(const int32_t* spec, int B, int Vg, int Vl, uint64_t seed, u
                     int32_t* aud_ops, uint32_t* group_bits, void* stream) {
     B200_REQUIRE(spec && img_ops && aud_ops && group_bits && B > 0 && Vg >= 0 && Vl >= 0 && Vg + Vl > 0, B200_E_ARG,
                  "aug_sample: bad arguments");
-    aug_sample_kernel<<<B * (Vg + Vl), 128, 0, as_stream(stream)>>>(spec, B, Vg, Vl, seed, step, img_ops, aud_ops, group_bits);
+    aug_sample_kernel<<<B * (Vg + Vl), 32, 0, as_stream(stream)>>>(spec, B, Vg, Vl, seed, step, img_ops, aud_ops, group_bits);
     return launch_status("aug_sample");
 }
 

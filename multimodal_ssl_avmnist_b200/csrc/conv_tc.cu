@@ -54,11 +54,13 @@ namespace {
 using namespace umma;
 
 constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
+constexpr int SMEM_EST(int nmma, int npad, int slots, int slot_bytes, int tail) { return round_up(nmma * npad * 32, 128) + slots * slot_bytes + tail + 256 + npad * 4; }
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
-template <int CIN_, int COUT_, int NPAD_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_>
+template <int CIN_, int COUT_, int NPAD_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int CTAS_ = 1>
 struct TcCfg {
     static constexpr int CIN = CIN_, COUT = COUT_, NPAD = NPAD_, HIN = HIN_, WIN = WIN_, KS = KS_, PAD = PAD_, BANDS = BANDS_, SLOTS = SLOTS_;
+    static constexpr int CTAS = CTAS_;                          // resident CTAs per SM (independent MMA streams hide the per-UMMA fixed cost)
     static constexpr bool L0 = (CIN == 1);                      // first layer: input is the "shift8" image (unit = x[q..q+7])
     static constexpr int P = L0 ? 1 : CIN / 8;                  // channel planes of the input
     static constexpr int WP = WIN + 2 * PAD;                    // padded pitch (pixels)
@@ -78,7 +80,11 @@ struct TcCfg {
     static constexpr int IMG_BYTES = SLOTS * SLOT_BYTES + TAIL;
     static constexpr int BAR_OFF = W_BYTES + IMG_BYTES;
     static constexpr int SMEM = BAR_OFF + 256 + NPAD * 4;
-    static constexpr int TMEM_COLS = pow2_cols(2 * NPAD);
+    static constexpr int NBUF = (NPAD <= 32 ? 8 : 4) / (CTAS > 2 ? 2 : 1);   // TMEM accumulator stages
+    static constexpr int TMEM_COLS = pow2_cols(NBUF * NPAD);
+    static_assert(TMEM_COLS * CTAS <= 512, "TMEM columns per SM");
+    static_assert((SMEM_EST(NMMA, NPAD, SLOTS, SLOT_BYTES, TAIL) + 1024) * CTAS <= 227 * 1024, "shared memory per SM");
+    static_assert(2 * SLOTS + 2 * NBUF <= 24, "barrier area");
     static_assert(CIN == 1 || (CIN % 8 == 0 && (CIN == 8 || CIN % 16 == 0)), "C_in must be 1, 8 or a multiple of 16");
     static_assert(NPAD % 16 == 0 && NPAD >= 16 && NPAD <= 64 && COUT <= NPAD && COUT % 8 == 0, "N tile");
     static_assert(HO % BANDS == 0, "bands must divide the output height");
@@ -90,14 +96,14 @@ struct TcCfg {
 // z, which is never an MMA operand -- 11 mantissa bits keep max-pool arg-max ties as rare as on the reference's fp16 autocast path).
 // bias may be null (no bias, no statistics); stats: double [views][COUT][2] (sum, sum of squares), accumulated.
 template <class C>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, C::CTAS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict__ wprep, const float* __restrict__ bias,
                void* __restrict__ out, double* __restrict__ stats, int n_per_view, int out_bf16) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_s = smem;
     uint8_t* img_s = smem + C::W_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);   // full[SLOTS], empty[SLOTS], tfull[2], tempty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::BAR_OFF + 192);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);   // full[SLOTS], empty[SLOTS], tfull[NBUF], tempty[NBUF]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::BAR_OFF + 200);
     float* bias_s = reinterpret_cast<float*>(smem + C::BAR_OFF + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,7 +115,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (C::SLOTS + s); };
     auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * C::SLOTS + b); };
-    auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * C::SLOTS + 2 + b); };
+    auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * C::SLOTS + C::NBUF + b); };
 
     // ---- one-time setup: weights -> smem, zero the image slots (+tail), barriers, TMEM ----
     {
@@ -127,7 +133,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < C::NBUF; ++b) {
             mbar_init(tfull_bar(b), 1);
             mbar_init(tempty_bar(b), 4);
         }
@@ -162,7 +168,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
                 tc_fence_after_sync();
                 const uint32_t slot_addr = img_addr + slot * C::SLOT_BYTES;
                 for (int t = 0; t < C::TILES; ++t, ++tcount) {
-                    const uint32_t buf = tcount & 1, u = tcount >> 1;
+                    const uint32_t buf = tcount % C::NBUF, u = tcount / C::NBUF;
                     mbar_wait(tempty_bar(buf), (u & 1) ^ 1);
                     tc_fence_after_sync();
                     const uint32_t d = tmem_base + buf * C::NPAD;
@@ -215,7 +221,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
         for (int i = i0; i < i1; ++i) {
             const int n = view * n_per_view + i / C::BANDS, band = i % C::BANDS;
             for (int t = 0; t < C::TILES; ++t, ++tcount) {
-                const uint32_t buf = tcount & 1, u = tcount >> 1;
+                const uint32_t buf = tcount % C::NBUF, u = tcount / C::NBUF;
                 mbar_wait(tfull_bar(buf), u & 1);
                 tc_fence_after_sync();
                 const int q = t * 128 + row;
@@ -389,7 +395,7 @@ int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* ou
     int rc = encode_tmap_bf16_4d(&tm, x, dims, strides, box);
     if (rc) return rc;
     const int views = N / n_per_view;
-    int G = sm_count() / views;
+    int G = sm_count() * C::CTAS / views;
     if (G < 1) G = 1;
     const long items = (long)n_per_view * C::BANDS;
     if (G > items) G = (int)items;
@@ -415,8 +421,9 @@ constexpr int hbz_for(int hb, int wp) {
     return h;
 }
 
-template <int CIN_, int COUT_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int PSPLIT_>
+template <int CIN_, int COUT_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int PSPLIT_, int CTAS_ = 1>
 struct TcWgCfg {
+    static constexpr int CTAS = CTAS_;                           // resident CTAs per SM
     static constexpr int CIN = CIN_, COUT = COUT_, HIN = HIN_, WIN = WIN_, KS = KS_, PAD = PAD_, BANDS = BANDS_, SLOTS = SLOTS_, PSPLIT = PSPLIT_;
     static constexpr bool L0 = (CIN == 1);                       // first layer over the shift8 image: rows = (kh, kw) in ONE accumulator
     static constexpr int P_IN = L0 ? 1 : CIN / 8, P_OUT = COUT / 8, PI = P_IN / PSPLIT;
@@ -437,14 +444,15 @@ struct TcWgCfg {
     static constexpr int PART = DW;                                 // floats per CTA partial
     static_assert(P_IN % PSPLIT == 0 && HO % BANDS == 0, "splits");
     static_assert(BANDS == 1 || HBZ == HB, "row bands need HB*WP to be a multiple of 16");
-    static_assert(NACC * COUT <= 512, "TMEM columns");
+    static_assert(NACC * COUT <= 512 && TMEM_COLS * CTAS <= 512, "TMEM columns");
+    static_assert((SMEM + 1024) * CTAS <= 227 * 1024, "shared memory per SM");
     static_assert(KS <= 8 && COUT % 8 == 0 && COUT >= 8 && COUT <= 256, "shape");
     static_assert((KSTEPS * 16 + (L0 ? 7 : KS - 1) * WP + 8 - HPB * WP) * 16 <= Z_BYTES, "x overrun must stay inside the slot");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
 template <class C>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, C::CTAS)
 conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_z, float* __restrict__ work, int N) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);     // full[SLOTS], empty[SLOTS], done
@@ -578,7 +586,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 
 template <class C>
 int wgrad_ctas(int N) {
-    int G = sm_count() / C::PSPLIT;
+    int G = sm_count() * C::CTAS / C::PSPLIT;
     const long items = (long)N * C::BANDS;
     if (G > items) G = (int)items;
     return G < 1 ? 1 : G;
@@ -624,25 +632,25 @@ int launch_conv_tc_wgrad(const void* x, const void* dz, float* dw, float* work, 
 }
 
 //                           CIN COUT HIN WIN KS PAD BANDS SLOTS PSPLIT
-using WgA1 = TcWgCfg<8, 16, 56, 56, 5, 2, 2, 2, 1>;
-using WgA2 = TcWgCfg<16, 32, 28, 28, 5, 2, 1, 2, 1>;
+using WgA1 = TcWgCfg<8, 16, 56, 56, 5, 2, 7, 2, 1, 4>;
+using WgA2 = TcWgCfg<16, 32, 28, 28, 5, 2, 1, 1, 2, 2>;
 using WgA3 = TcWgCfg<32, 64, 14, 14, 5, 2, 1, 3, 4>;
 using WgI1 = TcWgCfg<32, 64, 14, 14, 5, 0, 1, 4, 4>;
 using WgS1 = TcWgCfg<32, 64, 14, 14, 3, 1, 1, 3, 2>;
-using WgA0 = TcWgCfg<1, 8, 112, 112, 5, 2, 7, 3, 1>;      // first layers (shift8 image)
+using WgA0 = TcWgCfg<1, 8, 112, 112, 5, 2, 7, 1, 1, 3>;   // first layers (shift8 image)
 using WgI0 = TcWgCfg<1, 32, 28, 28, 5, 2, 1, 3, 1>;
 using WgS0 = TcWgCfg<1, 32, 28, 28, 3, 1, 1, 3, 1>;
 
 //                         CIN COUT NPAD HIN  WIN KS PAD BANDS SLOTS
-using CfgA1 = TcCfg<8, 16, 16, 56, 56, 5, 2, 2, 4>;      // audio conv2 forward
-using CfgA2 = TcCfg<16, 32, 32, 28, 28, 5, 2, 1, 4>;     // audio conv3 forward
+using CfgA1 = TcCfg<8, 16, 16, 56, 56, 5, 2, 2, 2, 3>;   // audio conv2 forward
+using CfgA2 = TcCfg<16, 32, 32, 28, 28, 5, 2, 1, 2, 2>;  // audio conv3 forward
 using CfgA3 = TcCfg<32, 64, 64, 14, 14, 5, 2, 1, 4>;     // audio conv4 forward
 using CfgI1 = TcCfg<32, 64, 64, 14, 14, 5, 0, 1, 4>;     // image conv2 forward (no padding)
-using CfgA1d = TcCfg<16, 8, 16, 56, 56, 5, 2, 2, 3>;     // data gradients (C_in/C_out swapped, pad' = K-1-pad)
-using CfgA2d = TcCfg<32, 16, 16, 28, 28, 5, 2, 1, 2>;
+using CfgA1d = TcCfg<16, 8, 16, 56, 56, 5, 2, 4, 2, 2>;  // data gradients (C_in/C_out swapped, pad' = K-1-pad)
+using CfgA2d = TcCfg<32, 16, 16, 28, 28, 5, 2, 2, 2, 2>;
 using CfgA3d = TcCfg<64, 32, 32, 14, 14, 5, 2, 1, 2>;
 using CfgI1d = TcCfg<64, 32, 32, 10, 10, 5, 4, 1, 2>;
-using CfgA0 = TcCfg<1, 8, 16, 112, 112, 5, 2, 4, 3>;     // first layers on the shift8 image: audio conv1
+using CfgA0 = TcCfg<1, 8, 16, 112, 112, 5, 2, 8, 2, 3>;  // first layers on the shift8 image: audio conv1
 using CfgI0 = TcCfg<1, 32, 32, 28, 28, 5, 2, 1, 4>;      //   image conv1
 using CfgS0 = TcCfg<1, 32, 32, 28, 28, 3, 1, 1, 4>;      //   image_simple conv1
 using CfgS1 = TcCfg<32, 64, 64, 14, 14, 3, 1, 1, 4>;     // image_simple conv2 forward / its data gradient

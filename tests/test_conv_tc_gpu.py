@@ -165,7 +165,7 @@ def test_bn_relu_pool8(C, H, views, B, zdt):
     for dpt in (dp, _pack8(dp)):
         sums = torch.zeros(views, C, 2, dtype=torch.float64, device=DEV)
         ops.bn_relu_pool8_bwd_reduce(z8, dpt, scale, shift, mean, invstd, sums, B)
-        assert float(((sums - s_want).abs() / (s_want.abs() + 1.0)).max()) < 1e-5
+        assert float(((sums - s_want).abs() / (s_want.abs() + 1.0)).max()) < 1e-4
         dz8 = torch.empty(z8.shape, dtype=torch.bfloat16, device=DEV)
         dbsum = torch.zeros(C, dtype=torch.float64, device=DEV)
         ops.bn_relu_pool8_bwd_apply(z8, dpt, scale, shift, mean, invstd, s_want.contiguous(), dz8, B, dbsum=dbsum)
