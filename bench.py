@@ -201,11 +201,13 @@ def op_cost(name, meta):
     if name == "linear_bwd_weight" and len(meta) >= 2:
         (M, N), (_, K) = meta[0], meta[1]
         return 2.0 * M * N * K, 0.0
-    if name == "aug_apply_audio":        # src u8 [B,112,112] read once (+L2 re-reads) + [V,B,112,112] fp32 written
-        out = meta[-1] if len(meta[-1]) == 4 else meta[0]
-        return 0.0, numel(meta[0]) * 1.0 + numel(out) * 4.0
-    if name == "aug_apply_image":
-        return 0.0, numel(meta[0]) * 4.0 + numel(meta[-1]) * 4.0
+    if name in ("aug_apply_audio", "aug_apply_image"):
+        # source read once (re-reads by the other views hit L2) + every view written once: fp32 [V,B,S,S] or bf16 shift8 [V,B,S,S+pad,8]
+        src = meta[0]
+        out8 = [m for m in meta[1:] if len(m) == 5]                    # bf16 shift8 [V,B,S,S+pad,8]
+        out32 = [m for m in meta[1:] if len(m) == 4 and m[-1] == m[-2]]  # fp32 [V,B,S,S]
+        out_bytes = sum(numel(m) * 2.0 for m in out8) + sum(numel(m) * 4.0 for m in out32)
+        return 0.0, numel(src) * (1.0 if name == "aug_apply_audio" else 4.0) + out_bytes
     if name == "ema_flat":
         return 0.0, 12.0 * numel(meta[0])
     if name == "adam_flat":

@@ -106,12 +106,16 @@ int b200_cosine_consistency_fwd_bwd(const float* emb, int V, int B, int D, float
 #define B200_AUG_MAX_OPS 8
 #define B200_AUG_GROUP_WORDS 28
 
-/* image: src float [B,28,28] in [0,1] (src_u8 == 0) or uint8 [B,28,28] scaled by 1/255 (src_u8 == 1) */
-int b200_aug_apply_image(const void* src, int src_u8, const int32_t* ops, float* out, int B, int V, void* stream);
+/* Outputs (either may be NULL, not both): out fp32 [V,B,S,S]; out_shift8 bf16 [V,B,S,S+pad,8], the first-layer input
+ * image of the tensor-core convolutions (unit (y,xs) = x[y][xs-pad .. xs-pad+7], zero outside the row).
+ * image: src float [B,28,28] in [0,1] (src_u8 == 0) or uint8 [B,28,28] scaled by 1/255 (src_u8 == 1) */
+int b200_aug_apply_image(const void* src, int src_u8, const int32_t* ops, float* out, void* out_shift8, int pad, int B,
+                         int V, void* stream);
 /* audio: src uint8 [B,112,112] (scaled by 1/255, utils/get_data.py:467) or float; noise: optional injected N(0,1)
  * field [B,V,112,112] (parity mode), NULL -> Philox(seed, sample*V+view) in-kernel */
 int b200_aug_apply_audio(const void* src, int src_u8, const int32_t* ops, const uint32_t* group_bits,
-                         const float* noise, uint64_t seed, float* out, int B, int V, void* stream);
+                         const float* noise, uint64_t seed, float* out, void* out_shift8, int pad, int B, int V,
+                         void* stream);
 /* device-side parameter sampling: spec tables int32 [4][B200_AUG_MAX_OPS][8] in the order
  * image-global, image-local, audio-global, audio-local (kind, p, a0..a5 as float bits; see augment.py pack_spec);
  * fills img_ops/aud_ops/group_bits for B samples x (Vg+Vl) views from Philox(seed, step). */

@@ -9,6 +9,8 @@
 //   * antialiased bilinear resize: ATen's separable weight tables (fp32 weights, double index math), FMA sums;
 //   * time warp: linear interpolation of |x| at torch.arange(0, W, rate) time steps (vectorised-arange rounding);
 //   * frequency/time masks, grouped 4x4 masking, erasing, additive gaussian noise.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -65,7 +67,7 @@ __device__ __forceinline__ float arange_f32(int k, int n, double step) {
 template <int S, int T>
 __global__ void __launch_bounds__(T) aug_apply_kernel(const void* __restrict__ src, int src_u8, const int32_t* __restrict__ ops,
                                                       const uint32_t* __restrict__ group_bits, const float* __restrict__ noise,
-                                                      uint64_t seed, float* __restrict__ out, int B, int V) {
+                                                      uint64_t seed, float* __restrict__ out, uint4* __restrict__ out8, int pad8, int B, int V) {
     constexpr int NPIX = S * S;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* bufA = reinterpret_cast<float*>(smem_raw);
@@ -224,8 +226,29 @@ __global__ void __launch_bounds__(T) aug_apply_kernel(const void* __restrict__ s
         }
     }
     // ---- write the finished view (view-major layout [V,B,S,S]) ----
-    float4* o4 = reinterpret_cast<float4*>(out + ((size_t)v * B + b) * NPIX);
-    for (int i = tid; i < NPIX / 4; i += T) o4[i] = reinterpret_cast<const float4*>(cur)[i];
+    if (out != nullptr) {
+        float4* o4 = reinterpret_cast<float4*>(out + ((size_t)v * B + b) * NPIX);
+        for (int i = tid; i < NPIX / 4; i += T) o4[i] = reinterpret_cast<const float4*>(cur)[i];
+    }
+    // ---- and / or the bf16 "shift8" image of the first-layer tensor-core convolution: [V,B,S,S+pad,8], unit (y, xs) =
+    //      x[y][xs-pad .. xs-pad+7] (zero outside the row); see conv_tc.cu ----
+    if (out8 != nullptr) {
+        const int WT = S + pad8;
+        uint4* o8 = out8 + ((size_t)v * B + b) * S * WT;
+        for (int i = tid; i < S * WT; i += T) {
+            const int y = i / WT, xs = i - y * WT;
+            const float* r = cur + y * S;
+            uint32_t pk[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const int x0 = xs - pad8 + 2 * h, x1 = x0 + 1;
+                const float f0 = (x0 >= 0 && x0 < S) ? r[x0] : 0.f, f1 = (x1 >= 0 && x1 < S) ? r[x1] : 0.f;
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(f0, f1);
+                pk[h] = *reinterpret_cast<uint32_t*>(&t2);
+            }
+            o8[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -406,20 +429,20 @@ using namespace b200;
 
 extern "C" {
 
-int b200_aug_apply_image(const void* src, int src_u8, const int32_t* ops, float* out, int B, int V, void* stream) {
-    B200_REQUIRE(src && ops && out && B > 0 && V > 0, B200_E_ARG, "aug_apply_image: bad arguments");
-    B200_REQUIRE((((uintptr_t)src | (uintptr_t)out) & 15) == 0, B200_E_ARG, "aug_apply_image: pointers must be 16-byte aligned");
+int b200_aug_apply_image(const void* src, int src_u8, const int32_t* ops, float* out, void* out_shift8, int pad, int B, int V, void* stream) {
+    B200_REQUIRE(src && ops && (out || out_shift8) && B > 0 && V > 0 && pad >= 0, B200_E_ARG, "aug_apply_image: bad arguments");
+    B200_REQUIRE((((uintptr_t)src | (uintptr_t)out | (uintptr_t)out_shift8) & 15) == 0, B200_E_ARG, "aug_apply_image: pointers must be 16-byte aligned");
     constexpr int S = 28, T = 128;
     const size_t smem = 2 * S * S * sizeof(float) + 2 * S * sizeof(AATable);
-    aug_apply_kernel<S, T><<<B * V, T, smem, as_stream(stream)>>>(src, src_u8, ops, nullptr, nullptr, 0, out, B, V);
+    aug_apply_kernel<S, T><<<B * V, T, smem, as_stream(stream)>>>(src, src_u8, ops, nullptr, nullptr, 0, out, reinterpret_cast<uint4*>(out_shift8), pad, B, V);
     return launch_status("aug_apply_image");
 }
 
 int b200_aug_apply_audio(const void* src, int src_u8, const int32_t* ops, const uint32_t* group_bits, const float* noise,
-                         uint64_t seed, float* out, int B, int V, void* stream) {
-    B200_REQUIRE(src && ops && group_bits && out && B > 0 && V > 0, B200_E_ARG, "aug_apply_audio: bad arguments");
-    B200_REQUIRE((((uintptr_t)src | (uintptr_t)out) & 15) == 0, B200_E_ARG, "aug_apply_audio: pointers must be 16-byte aligned");
-    constexpr int S = 112, T = 256;
+                         uint64_t seed, float* out, void* out_shift8, int pad, int B, int V, void* stream) {
+    B200_REQUIRE(src && ops && group_bits && (out || out_shift8) && B > 0 && V > 0 && pad >= 0, B200_E_ARG, "aug_apply_audio: bad arguments");
+    B200_REQUIRE((((uintptr_t)src | (uintptr_t)out | (uintptr_t)out_shift8) & 15) == 0, B200_E_ARG, "aug_apply_audio: pointers must be 16-byte aligned");
+    constexpr int S = 112, T = 512;
     const size_t smem = 2 * S * S * sizeof(float) + 2 * S * sizeof(AATable);
     static bool attr_done = false;
     if (!attr_done) {
@@ -427,7 +450,7 @@ int b200_aug_apply_audio(const void* src, int src_u8, const int32_t* ops, const 
         B200_REQUIRE(e == cudaSuccess, B200_E_SMEM, "aug_apply_audio: cannot reserve %zu B of shared memory", smem);
         attr_done = true;
     }
-    aug_apply_kernel<S, T><<<B * V, T, smem, as_stream(stream)>>>(src, src_u8, ops, group_bits, noise, seed, out, B, V);
+    aug_apply_kernel<S, T><<<B * V, T, smem, as_stream(stream)>>>(src, src_u8, ops, group_bits, noise, seed, out, reinterpret_cast<uint4*>(out_shift8), pad, B, V);
     return launch_status("aug_apply_audio");
 }
 

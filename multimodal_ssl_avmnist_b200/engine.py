@@ -368,25 +368,38 @@ class DinoStepEngine:
     # ------------------------------------------------------------------------------------------------------
     # augmentation
     # ------------------------------------------------------------------------------------------------------
-    def augment(self, images, audios, B=None):
+    def augment(self, images, audios, B=None, direct=False):
         """Device-sampled multi-crop views of a raw batch: images [B,28,28] (fp32 in [0,1] or uint8),
         audios [B,112,112] (uint8 or fp32).  Returns view-major tensors ([V,B,28,28], [V,B,112,112])."""
         B = images.shape[0]
         w = self._workspace(B)
         ops.aug_sample(self.aug_spec, B, self.Vg, self.Vl, self.seed, self.rng_step, w["img_ops"], w["aud_ops"], w["group_bits"])
-        return self.augment_with_params(images, audios, w["img_ops"], w["aud_ops"], w["group_bits"], None)
+        return self.augment_with_params(images, audios, w["img_ops"], w["aud_ops"], w["group_bits"], None, direct=direct)
 
-    def augment_with_params(self, images, audios, img_ops, aud_ops, group_bits, noise):
+    def augment_with_params(self, images, audios, img_ops, aud_ops, group_bits, noise, direct=False):
+        """Applies the op records.  direct=False: fp32 views ([V,B,28,28], [V,B,112,112]).  direct=True (tensor-core path
+        only): the kernels write the first-layer shift8 images straight into the workspace (no fp32 round trip); the
+        returned bf16 tensors are those workspace buffers and are recognised by forward_pass."""
         B = images.shape[0]
         w = self._workspace(B)
         V = self.V
+        seed = (self.seed * 1000003 + self.rng_step) & 0xFFFFFFFFFFFF
+        if direct and self.tc["img"][0] and (not self.aud_layers or self.tc["aud"][0]):
+            pi = self.img_layers[0][6]
+            xi = w["img.xs8"][:V * B].view(V, B, 28, 28 + pi, 8)
+            ops.aug_apply_image(images.reshape(B, 28, 28), img_ops, None, out8=xi, pad=pi)
+            xa = None
+            if self.aud_layers and audios is not None:
+                pa = self.aud_layers[0][6]
+                xa = w["aud.xs8"][:V * B].view(V, B, 112, 112 + pa, 8)
+                ops.aug_apply_audio(audios.reshape(B, 112, 112), aud_ops, group_bits, None, noise=noise, seed=seed, out8=xa, pad=pa)
+            return xi, xa
         xi = w["x_img"][:V * B].view(V, B, 28, 28)
         ops.aug_apply_image(images.reshape(B, 28, 28), img_ops, xi)
         xa = None
         if self.aud_layers and audios is not None:
             xa = w["x_aud"][:V * B].view(V, B, 112, 112)
-            ops.aug_apply_audio(audios.reshape(B, 112, 112), aud_ops, group_bits, xa, noise=noise,
-                                seed=(self.seed * 1000003 + self.rng_step) & 0xFFFFFFFFFFFF)
+            ops.aug_apply_audio(audios.reshape(B, 112, 112), aud_ops, group_bits, xa, noise=noise, seed=seed)
         return xi, xa
 
     # ------------------------------------------------------------------------------------------------------
@@ -413,7 +426,7 @@ class DinoStepEngine:
             stats.zero_()
             if tc and ci == 1:
                 xs8 = w[f"{mod}.xs8"]
-                if role == "s":
+                if role == "s" and not w.get("packed", False):
                     ops.pack_shift8(cur.view(N, hw, hw), xs8, pad)
                 ops.conv_tc(xs8[:N], self._tcw[(role, mod, li)], P["enc." + conv + ".bias"], z, stats, B, co, k, pad)
             elif tc:
@@ -539,16 +552,23 @@ class DinoStepEngine:
         S, T = self.S, self.T
         multi = self.kind == "multi_central"
         xi = w["x_img"]
-        if x_img.data_ptr() != xi.data_ptr():
-            xi[:Nv].copy_(x_img.reshape(Nv, 1, 28, 28))
-        xa = None
-        if multi:
-            xa = w["x_aud"]
-            if x_aud.data_ptr() != xa.data_ptr():
+        xa = w["x_aud"] if multi else None
+        packed = x_img.dtype == torch.bfloat16          # augment(direct=True): the shift8 workspace images are already filled
+        w["packed"] = packed
+        if packed:
+            if x_img.data_ptr() != w["img.xs8"].data_ptr() or (multi and x_aud.data_ptr() != w["aud.xs8"].data_ptr()):
+                raise ops._lib.B200Error("bf16 inputs must be the workspace shift8 images returned by augment(direct=True)")
+            if self.mode != "default":
+                ops.pack_shift8(raw[0].reshape(B, 28, 28), w["img.xs8"][Nv:], self.img_layers[0][6])
+                ops.pack_shift8(raw[1].reshape(B, 112, 112), w["aud.xs8"][Nv:], self.aud_layers[0][6])
+        else:
+            if x_img.data_ptr() != xi.data_ptr():
+                xi[:Nv].copy_(x_img.reshape(Nv, 1, 28, 28))
+            if multi and x_aud.data_ptr() != xa.data_ptr():
                 xa[:Nv].copy_(x_aud.reshape(Nv, 1, 112, 112))
-        if self.mode != "default":
-            xi[Nv:].copy_(raw[0].reshape(B, 1, 28, 28))
-            xa[Nv:].copy_(raw[1].reshape(B, 1, 112, 112))
+            if self.mode != "default":
+                xi[Nv:].copy_(raw[0].reshape(B, 1, 28, 28))
+                xa[Nv:].copy_(raw[1].reshape(B, 1, 112, 112))
         if masks is not None:
             if multi:
                 w["s.fmask"].copy_(masks["student_fusion"].reshape(Nv, E))
@@ -702,7 +722,7 @@ class DinoStepEngine:
     def train_step(self, images, audios=None, labels=None):
         """Whole step from a raw device batch: images [B,28,28] fp32 in [0,1] or uint8; audios [B,112,112] uint8 (or fp32);
         labels int64 [B] (semi_supervised).  Returns the device loss tensor [4] (dino, aux, cosine, total)."""
-        xi, xa = self.augment(images, audios)
+        xi, xa = self.augment(images, audios, direct=True)
         raw = None
         if self.mode != "default":
             img_f = images.float() / 255.0 if images.dtype == torch.uint8 else images

@@ -136,16 +136,24 @@ def cosine_consistency_fwd_bwd(emb, grad_emb, loss_out, grad_scale=1.0):
 
 
 # ---- augmentation ------------------------------------------------------------------------------------------
-def aug_apply_image(src, ops, out):
-    V, B = out.shape[0], out.shape[1]
-    _lib.check(_lib_().b200_aug_apply_image(_ptr(src), 1 if src.dtype == U8 else 0, _ptr(ops, I32), _ptr(out, F32), B, V, _stream()),
+def _aug_outs(out, out8, pad):
+    ref = out if out is not None else out8
+    if ref is None:
+        raise _lib.B200Error("augmentation needs an fp32 and / or a shift8 output")
+    return ref.shape[0], ref.shape[1], (_ptr(out, F32) if out is not None else None), (_ptr(out8, torch.bfloat16) if out8 is not None else None)
+
+
+def aug_apply_image(src, ops, out, out8=None, pad=0):
+    """out: fp32 [V, B, 28, 28] and / or out8: bf16 shift8 [V, B, 28, 28 + pad, 8] (first-layer tensor-core input)."""
+    V, B, po, p8 = _aug_outs(out, out8, pad)
+    _lib.check(_lib_().b200_aug_apply_image(_ptr(src), 1 if src.dtype == U8 else 0, _ptr(ops, I32), po, p8, pad, B, V, _stream()),
                "aug_apply_image")
 
 
-def aug_apply_audio(src, ops, group_bits, out, noise=None, seed=0):
-    V, B = out.shape[0], out.shape[1]
+def aug_apply_audio(src, ops, group_bits, out, noise=None, seed=0, out8=None, pad=0):
+    V, B, po, p8 = _aug_outs(out, out8, pad)
     _lib.check(_lib_().b200_aug_apply_audio(_ptr(src), 1 if src.dtype == U8 else 0, _ptr(ops, I32), _ptr(group_bits, I32),
-                                            _ptr(noise, F32), seed, _ptr(out, F32), B, V, _stream()), "aug_apply_audio")
+                                            _ptr(noise, F32), seed, po, p8, pad, B, V, _stream()), "aug_apply_audio")
 
 
 def aug_sample(spec, B, Vg, Vl, seed, step, img_ops, aud_ops, group_bits):
@@ -443,7 +451,7 @@ def _wrap(name, fn):
         a.record()
         out = fn(*args, **kwargs)
         b.record()
-        meta = tuple(tuple(t.shape) for t in args[:4] if isinstance(t, torch.Tensor))
+        meta = tuple(tuple(t.shape) for t in list(args[:4]) + list(kwargs.values()) if isinstance(t, torch.Tensor))
         meta = meta + (("i",) + tuple(int(v) for v in args if isinstance(v, int) and not isinstance(v, bool)),)
         _PROFILE.append((name, a, b, meta))
         return out

@@ -217,3 +217,24 @@ def test_first_layer_shift8_forward_and_weight_gradient(geom, views, B):
     ops.conv_tc_wgrad(x8, dz8, dw, work, pad)
     torch.cuda.synchronize()
     assert float((dw.double() - wd.grad).abs().max()) <= 3e-5 * float(wd.grad.abs().max())
+
+
+def test_augmentation_direct_shift8_output_matches_pack():
+    """The augmentation kernels' direct bf16 shift8 output == pack_shift8(fp32 output) bit for bit (same op records)."""
+    from multimodal_ssl_avmnist_b200.engine import DinoStepEngine
+    eng = DinoStepEngine(kind="multi_central", device=DEV, precision="bf16", seed=5)
+    B = 6
+    img = torch.rand(B, 28, 28, device=DEV)
+    aud = torch.randint(0, 256, (B, 112, 112), dtype=torch.uint8, device=DEV)
+    xi, xa = eng.augment(img, aud)                      # fp32 views
+    xi, xa = xi.clone(), xa.clone()
+    xi8, xa8 = eng.augment(img, aud, direct=True)       # same rng_step -> same op records and noise
+    for x, x8, pad in ((xi, xi8, 2), (xa, xa8, 2)):
+        V, Bb, S, _ = x.shape
+        want = torch.empty(V * Bb, S, S + pad, 8, dtype=torch.bfloat16, device=DEV)
+        ops.pack_shift8(x.reshape(V * Bb, S, S).contiguous(), want, pad)
+        assert torch.equal(x8.reshape(want.shape), want)
+    # and the whole step runs from it
+    l1 = eng.train_step(img, aud).clone()
+    torch.cuda.synchronize()
+    assert 3.0 < float(l1[0]) < 6.0

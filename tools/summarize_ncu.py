@@ -18,8 +18,14 @@ METRICS = ["gpu__time_duration.sum", "sm__throughput.avg.pct_of_peak_sustained_e
 
 def short(name):
     name = re.sub(r"^void ", "", name)
-    m = re.match(r"(b200::)?(\w+)(<[^>]*>)?", name)
-    return (m.group(2) + (m.group(3) or "")) if m else name[:60]
+    name = re.sub(r"\(unsigned char\)|\(int\)|\(bool\)", "", name)
+    name = name.replace("b200::", "").replace("<unnamed>::", "").replace("(anonymous namespace)::", "")
+    name = re.sub(r"^unnamed>::", "", name)
+    m = re.match(r"(\w+)(<.*>)?\(", name)
+    if m:
+        return m.group(1) + (m.group(2) or "")
+    m = re.match(r"(\w+)(<[^(]*>)?", name)
+    return (m.group(1) + (m.group(2) or "")) if m else name[:80]
 
 
 def launches(path, out, per_step=None):
