@@ -223,6 +223,18 @@ int b200_linear_bwd_data(const float* dy, int64_t lddy, const float* w, float* d
 int64_t b200_linear_bwd_weight_work_floats(int M, int N, int K);
 int b200_linear_bwd_weight(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dw, float* db, float* work,
                            int M, int N, int K, int accumulate, void* stream);
+/* tensor-core variants (tcgen05 kind::tf32, TMA-staged fp32 operands, fp32 TMEM accumulators): same results up to tf32
+ * operand rounding; operands that TMA cannot address (row pitch not a multiple of 16 bytes) run on the SIMT kernels.
+ * kind::tf32 needs K-major operands, so the two backward GEMMs transpose W (resp. dy and x) into `work` first:
+ * work is REQUIRED, float[b200_linear_bwd_{data,weight}_tc_work_floats(M, N, K)], 16-byte aligned. */
+int b200_linear_fwd_tc(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t ldy, int M, int N,
+                       int K, int act, const uint8_t* mask, float drop_p, void* stream);
+int64_t b200_linear_bwd_data_tc_work_floats(int M, int N, int K);
+int b200_linear_bwd_data_tc(const float* dy, int64_t lddy, const float* w, float* dx, int64_t lddx, float* work, int M, int N,
+                            int K, void* stream);
+int64_t b200_linear_bwd_weight_tc_work_floats(int M, int N, int K);
+int b200_linear_bwd_weight_tc(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dw, float* db, float* work,
+                              int M, int N, int K, int accumulate, void* stream);
 int b200_act_bwd(float* dy, const float* y, const uint8_t* mask, float drop_p, int64_t n, void* stream);
 /* BatchNorm1d statistics over the rows of h[M,C] (double sums, zeroed by the caller): stats[c] = {sum, sum^2} */
 int b200_colstats(const float* h, double* stats, int M, int C, void* stream);

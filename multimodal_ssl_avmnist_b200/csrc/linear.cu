@@ -4,6 +4,13 @@
 
 namespace b200 {
 
+// tensor-core GEMM (gemm_tc.cu)
+bool gemm_tc_usable(const void* A, int64_t lda, const void* Bm, int64_t ldb);
+int launch_gemm_tc(const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc, int M, int N, int K, int splits, int epi,
+                   const float* bias, const uint8_t* mask, float keep_scale, cudaStream_t st);
+int launch_transpose_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int R, int Cc, cudaStream_t st);
+int gemm_tc_splits(int M, int N, int K);
+
 constexpr int BM = 64, BN = 64, BK = 16, GT = 256, LDS_PAD = 4;
 
 // C[m,n] (+)= sum_k A(m,k) * B(n,k)
@@ -152,6 +159,24 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
 #pragma unroll
         for (int r = 0; r < 8; ++r) s += red[r][threadIdx.x & 31];
         out[col] = accumulate ? out[col] + s : s;
+    }
+}
+
+// partial column sums: part[blockIdx.y][col] = sum over this block's row slice (reduced in fixed order by reduce_splits_kernel)
+__global__ void __launch_bounds__(256) colsum_part_kernel(const float* __restrict__ dy, int64_t ld, int M, int N, float* __restrict__ part) {
+    __shared__ float red[8][33];
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+    const int rows = (M + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * rows, r1 = min(M, r0 + rows);
+    float a = 0.f;
+    if (col < N)
+        for (int m = r0 + rl; m < r1; m += 8) a += __ldg(dy + (int64_t)m * ld + col);
+    red[rl][threadIdx.x & 31] = a;
+    __syncthreads();
+    if (rl == 0 && col < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) s += red[r][threadIdx.x & 31];
+        part[(int64_t)blockIdx.y * N + col] = s;
     }
 }
 
@@ -325,6 +350,81 @@ int b200_linear_bwd_weight(const float* dy, int64_t lddy, const float* x, int64_
     if (rc || !db) return rc;
     colsum_kernel<<<(N + 31) / 32, 256, 0, st>>>(dy, lddy, M, N, db, accumulate);
     return launch_status("linear_bwd_bias");
+}
+
+// ---- tensor-core (tcgen05, tf32) variants: same arguments and results up to tf32 operand rounding; operands that TMA cannot
+//      address (row pitch not a multiple of 16 bytes, e.g. the 10-way classifier outputs) run on the SIMT kernels ----
+static int colsum_splits(int M) {
+    int rs = (M + 511) / 512;
+    return rs < 1 ? 1 : (rs > 64 ? 64 : rs);
+}
+
+int b200_linear_fwd_tc(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t ldy, int M, int N, int K,
+                       int act, const uint8_t* mask, float drop_p, void* stream) {
+    B200_REQUIRE(x && w && y && M > 0 && N > 0 && K > 0 && ldx >= K && ldy >= N, B200_E_ARG, "linear_fwd_tc: bad arguments");
+    B200_REQUIRE(act >= 0 && act <= 2 && (act != 2 || (mask && drop_p >= 0.f && drop_p < 1.f)), B200_E_ARG, "linear_fwd_tc: bad activation");
+    if (!gemm_tc_usable(x, ldx, w, K)) return b200_linear_fwd(x, ldx, w, bias, y, ldy, M, N, K, act, mask, drop_p, stream);
+    return launch_gemm_tc(x, ldx, w, K, y, ldy, M, N, K, 1, act + 1, bias, mask, 1.0f / (1.0f - drop_p), as_stream(stream));
+}
+
+static int64_t pad4(int64_t n) { return (n + 3) / 4 * 4; }
+
+int64_t b200_linear_bwd_data_tc_work_floats(int M, int N, int K) {
+    (void)M;
+    return (N > 0 && K > 0) ? (int64_t)K * pad4(N) : 0;
+}
+
+int b200_linear_bwd_data_tc(const float* dy, int64_t lddy, const float* w, float* dx, int64_t lddx, float* work, int M, int N, int K,
+                            void* stream) {
+    B200_REQUIRE(dy && w && dx && work && M > 0 && N > 0 && K > 0 && lddy >= N && lddx >= K, B200_E_ARG, "linear_bwd_data_tc: bad arguments");
+    if (!gemm_tc_usable(dy, lddy, work, 4)) return b200_linear_bwd_data(dy, lddy, w, dx, lddx, M, N, K, stream);
+    cudaStream_t st = as_stream(stream);
+    // dx[m,k] = sum_n dy[m,n] w[n,k] = sum_n dy[m,n] wT[k,n]:  B = w^T [K][N] (K-major in the reduction index n)
+    const int64_t ldt = pad4(N);
+    int rc = launch_transpose_f32(w, K, work, ldt, N, K, st);
+    if (rc) return rc;
+    return launch_gemm_tc(dy, lddy, work, ldt, dx, lddx, M, K, N, 1, 0, nullptr, nullptr, 1.f, st);
+}
+
+int64_t b200_linear_bwd_weight_tc_work_floats(int M, int N, int K) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    const int64_t simt = b200_linear_bwd_weight_work_floats(M, N, K);
+    const int64_t tc = (int64_t)gemm_tc_splits(N, K, M) * N * K + (int64_t)colsum_splits(M) * N + (int64_t)(N + K) * pad4(M);
+    return simt > tc ? simt : tc;
+}
+
+int b200_linear_bwd_weight_tc(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dw, float* db, float* work, int M, int N,
+                              int K, int accumulate, void* stream) {
+    B200_REQUIRE(dy && x && dw && work && M > 0 && N > 0 && K > 0 && lddy >= N && ldx >= K, B200_E_ARG, "linear_bwd_weight_tc: bad arguments");
+    if ((reinterpret_cast<uintptr_t>(work) & 15) != 0) return b200_linear_bwd_weight(dy, lddy, x, ldx, dw, db, work, M, N, K, accumulate, stream);
+    cudaStream_t st = as_stream(stream);
+    // dw[n,k] = sum_m dy[m,n] x[m,k] = sum_m dyT[n,m] xT[k,m]: both transposed copies are K-major in the reduction index m
+    const int splits = gemm_tc_splits(N, K, M);
+    const int64_t nk = (int64_t)N * K, ldt = pad4(M);
+    float* part = work + (int64_t)splits * nk;                 // colsum partials
+    const int rs = colsum_splits(M);
+    float* dyT = part + (int64_t)rs * N;
+    dyT += (4 - ((dyT - work) & 3)) & 3;                      // keep 16-byte alignment
+    float* xT = dyT + (int64_t)N * ldt;
+    int rc = launch_transpose_f32(dy, lddy, dyT, ldt, M, N, st);
+    if (rc) return rc;
+    rc = launch_transpose_f32(x, ldx, xT, ldt, M, K, st);
+    if (rc) return rc;
+    if (splits == 1 && !accumulate) {
+        rc = launch_gemm_tc(dyT, ldt, xT, ldt, dw, K, N, K, M, 1, 0, nullptr, nullptr, 1.f, st);
+    } else {
+        rc = launch_gemm_tc(dyT, ldt, xT, ldt, work, K, N, K, M, splits, 4, nullptr, nullptr, 1.f, st);
+        if (rc) return rc;
+        const int kps = ((M + splits - 1) / splits + 31) / 32 * 32;
+        const int eff = (M + kps - 1) / kps;
+        reduce_splits_kernel<<<(int)((nk + 1023) / 1024 < sm_count() * 8 ? (nk + 1023) / 1024 : sm_count() * 8), 256, 0, st>>>(work, eff, nk, dw,
+                                                                                                                            accumulate);
+        rc = launch_status("linear_bwd_weight_tc reduce");
+    }
+    if (rc || !db) return rc;
+    colsum_part_kernel<<<dim3((N + 31) / 32, rs), 256, 0, st>>>(dy, lddy, M, N, part);
+    reduce_splits_kernel<<<(N + 255) / 256, 256, 0, st>>>(part, rs, N, db, accumulate);
+    return launch_status("linear_bwd_bias_tc");
 }
 
 int b200_act_bwd(float* dy, const float* y, const uint8_t* mask, float drop_p, int64_t n, void* stream) {

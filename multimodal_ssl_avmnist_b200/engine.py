@@ -149,6 +149,7 @@ class DinoStepEngine:
         assert mode == "default" or kind == "multi_central"
         assert precision in ("bf16", "fp32")
         self.precision = precision
+        self.lin_tc = precision == "bf16"          # linear layers on the tensor cores (tcgen05 kind::tf32)
         self.kind, self.mode = kind, mode
         self.E, self.O, self.P = encoder_output_dim, output_dim, projection_dim
         self.Vg, self.Vl = n_global_views, n_local_views
@@ -451,27 +452,27 @@ class DinoStepEngine:
 
     def _head_fwd(self, w, role, prefix, P, bn, x, out, hh, g, mask, drop_p, tag=""):
         M = x.shape[0]
-        ops.linear_fwd(x, P[prefix + "mlp.0.weight"], P[prefix + "mlp.0.bias"], hh)
+        ops.linear_fwd(x, P[prefix + "mlp.0.weight"], P[prefix + "mlp.0.bias"], hh, tc=self.lin_tc)
         st = w[f"{role}.{tag}hstats"]
         st.zero_()
         ops.colstats(hh, st)
         ops.bn_finalize(st, P[prefix + "mlp.1.weight"], P[prefix + "mlp.1.bias"], bn.running_mean, bn.running_var, bn.num_batches_tracked,
                         w[f"{role}.{tag}hscale"], w[f"{role}.{tag}hshift"], w[f"{role}.{tag}hmean"], w[f"{role}.{tag}hinvstd"], 1, M)
         ops.bn1d_gelu_drop_fwd(hh, w[f"{role}.{tag}hscale"], w[f"{role}.{tag}hshift"], mask, drop_p, g)
-        ops.linear_fwd(g, P[prefix + "mlp.4.weight"], P[prefix + "mlp.4.bias"], out)
+        ops.linear_fwd(g, P[prefix + "mlp.4.weight"], P[prefix + "mlp.4.bias"], out, tc=self.lin_tc)
 
     def _head_bwd(self, w, role, prefix, x, d_out, hh, g, d_g, d_hh, d_x, mask, drop_p, tag=""):
         S, G = self.S, self.G
-        ops.linear_bwd_weight(d_out, g, G[prefix + "mlp.4.weight"], G[prefix + "mlp.4.bias"])
-        ops.linear_bwd_data(d_out, S[prefix + "mlp.4.weight"], d_g)
+        ops.linear_bwd_weight(d_out, g, G[prefix + "mlp.4.weight"], G[prefix + "mlp.4.bias"], tc=self.lin_tc)
+        ops.linear_bwd_data(d_out, S[prefix + "mlp.4.weight"], d_g, tc=self.lin_tc)
         sums = w[f"{role}.{tag}hsums"]
         sums.zero_()
         sc, sh, mu, inv = (w[f"{role}.{tag}h{n}"] for n in ("scale", "shift", "mean", "invstd"))
         ops.bn1d_gelu_drop_bwd_reduce(hh, d_g, sc, sh, mu, inv, mask, drop_p, sums)
         ops.bn1d_gelu_drop_bwd_apply(hh, d_g, sc, sh, mu, inv, mask, drop_p, sums, d_hh)
         ops.bn_param_grads(sums, G[prefix + "mlp.1.weight"], G[prefix + "mlp.1.bias"], 1)
-        ops.linear_bwd_weight(d_hh, x, G[prefix + "mlp.0.weight"], G[prefix + "mlp.0.bias"])
-        ops.linear_bwd_data(d_hh, S[prefix + "mlp.0.weight"], d_x)
+        ops.linear_bwd_weight(d_hh, x, G[prefix + "mlp.0.weight"], G[prefix + "mlp.0.bias"], tc=self.lin_tc)
+        ops.linear_bwd_data(d_hh, S[prefix + "mlp.0.weight"], d_x, tc=self.lin_tc)
 
     def _encode(self, w, role, P, bns, x_img, x_aud, N, B, n_fusion, fmask):
         """Encoder forward for N = n_views*B samples; fusion only over the first n_fusion rows."""
@@ -479,17 +480,17 @@ class DinoStepEngine:
             E = self.E
             cat = w[f"{role}.cat"]
             pi = self._conv_stack(w, role, "img", self.img_layers, x_img, N, B, P, bns)
-            ops.linear_fwd(pi.view(N, 1600), P["enc.image_encoder.1.weight"], P["enc.image_encoder.1.bias"], cat[:, :E])
+            ops.linear_fwd(pi.view(N, 1600), P["enc.image_encoder.1.weight"], P["enc.image_encoder.1.bias"], cat[:, :E], tc=self.lin_tc)
             pa = self._conv_stack(w, role, "aud", self.aud_layers, x_aud, N, B, P, bns)
-            ops.linear_fwd(pa.view(N, 3136), P["enc.audio_encoder.1.weight"], P["enc.audio_encoder.1.bias"], cat[:, E:])
+            ops.linear_fwd(pa.view(N, 3136), P["enc.audio_encoder.1.weight"], P["enc.audio_encoder.1.bias"], cat[:, E:], tc=self.lin_tc)
             h1, feat = w[f"{role}.h1"], w[f"{role}.feat"]
-            ops.linear_fwd(cat[:n_fusion], P["enc.fusion.0.weight"], P["enc.fusion.0.bias"], h1, act=2, mask=fmask, drop_p=self.fusion_dropout)
-            ops.linear_fwd(h1, P["enc.fusion.3.weight"], P["enc.fusion.3.bias"], feat)
+            ops.linear_fwd(cat[:n_fusion], P["enc.fusion.0.weight"], P["enc.fusion.0.bias"], h1, act=2, mask=fmask, drop_p=self.fusion_dropout, tc=self.lin_tc)
+            ops.linear_fwd(h1, P["enc.fusion.3.weight"], P["enc.fusion.3.bias"], feat, tc=self.lin_tc)
             return feat
         pi = self._conv_stack(w, role, "img", self.img_layers, x_img, N, B, P, bns)      # [N,128,3,3]
         ops.avgpool_fwd(pi, w[f"{role}.pool"])
-        ops.linear_fwd(w[f"{role}.pool"], P["enc.encoder.14.weight"], P["enc.encoder.14.bias"], w[f"{role}.e14"])
-        ops.linear_fwd(w[f"{role}.e14"], P["enc.projection.0.weight"], P["enc.projection.0.bias"], w[f"{role}.feat"])
+        ops.linear_fwd(w[f"{role}.pool"], P["enc.encoder.14.weight"], P["enc.encoder.14.bias"], w[f"{role}.e14"], tc=self.lin_tc)
+        ops.linear_fwd(w[f"{role}.e14"], P["enc.projection.0.weight"], P["enc.projection.0.bias"], w[f"{role}.feat"], tc=self.lin_tc)
         return w[f"{role}.feat"]
 
     def _conv_stack_bwd(self, w, mod, layers, x, d_top, N, B):
@@ -645,11 +646,11 @@ class DinoStepEngine:
             d_feat.add_(w["d.emb"])
         if multi:
             d_cat, d_h1 = w["d.cat"], w["d.h1"]
-            ops.linear_bwd_weight(d_feat, w["s.h1"], G["enc.fusion.3.weight"], G["enc.fusion.3.bias"])
-            ops.linear_bwd_data(d_feat, S["enc.fusion.3.weight"], d_h1)
+            ops.linear_bwd_weight(d_feat, w["s.h1"], G["enc.fusion.3.weight"], G["enc.fusion.3.bias"], tc=self.lin_tc)
+            ops.linear_bwd_data(d_feat, S["enc.fusion.3.weight"], d_h1, tc=self.lin_tc)
             ops.act_bwd(d_h1, w["s.h1"], self.fusion_dropout)
-            ops.linear_bwd_weight(d_h1, w["s.cat"][:Nv], G["enc.fusion.0.weight"], G["enc.fusion.0.bias"])
-            ops.linear_bwd_data(d_h1, S["enc.fusion.0.weight"], d_cat[:Nv])
+            ops.linear_bwd_weight(d_h1, w["s.cat"][:Nv], G["enc.fusion.0.weight"], G["enc.fusion.0.bias"], tc=self.lin_tc)
+            ops.linear_bwd_data(d_h1, S["enc.fusion.0.weight"], d_cat[:Nv], tc=self.lin_tc)
             if self.mode != "default":
                 for i, (m, sl) in enumerate((("aux_image", slice(0, E)), ("aux_audio", slice(E, 2 * E)))):
                     d_out = w[f"{m}.d.out"] if d_aux is None else d_aux[i]
@@ -658,15 +659,15 @@ class DinoStepEngine:
             for mod, layers, sl, nflat, lin, x in (("img", self.img_layers, slice(0, E), 1600, "enc.image_encoder.1", xi),
                                                    ("aud", self.aud_layers, slice(E, 2 * E), 3136, "enc.audio_encoder.1", xa)):
                 p_last = w[f"s.{mod}.p{len(layers) - 1}"].view(Ns, nflat)
-                ops.linear_bwd_weight(d_cat[:, sl], p_last, G[lin + ".weight"], G[lin + ".bias"])
+                ops.linear_bwd_weight(d_cat[:, sl], p_last, G[lin + ".weight"], G[lin + ".bias"], tc=self.lin_tc)
                 d_p = w["dp_a"][:Ns * nflat].view(Ns, nflat)
-                ops.linear_bwd_data(d_cat[:, sl], S[lin + ".weight"], d_p)
+                ops.linear_bwd_data(d_cat[:, sl], S[lin + ".weight"], d_p, tc=self.lin_tc)
                 self._conv_stack_bwd(w, mod, layers, x, d_p, Ns, B)
         else:
-            ops.linear_bwd_weight(d_feat, w["s.e14"], G["enc.projection.0.weight"], G["enc.projection.0.bias"])
-            ops.linear_bwd_data(d_feat, S["enc.projection.0.weight"], w["d.e14"])
-            ops.linear_bwd_weight(w["d.e14"], w["s.pool"], G["enc.encoder.14.weight"], G["enc.encoder.14.bias"])
-            ops.linear_bwd_data(w["d.e14"], S["enc.encoder.14.weight"], w["d.pool"])
+            ops.linear_bwd_weight(d_feat, w["s.e14"], G["enc.projection.0.weight"], G["enc.projection.0.bias"], tc=self.lin_tc)
+            ops.linear_bwd_data(d_feat, S["enc.projection.0.weight"], w["d.e14"], tc=self.lin_tc)
+            ops.linear_bwd_weight(w["d.e14"], w["s.pool"], G["enc.encoder.14.weight"], G["enc.encoder.14.bias"], tc=self.lin_tc)
+            ops.linear_bwd_data(w["d.e14"], S["enc.encoder.14.weight"], w["d.pool"], tc=self.lin_tc)
             d_p = w["dp_a"][:Ns * 128 * 9].view(Ns, 128, 3, 3)
             ops.avgpool_bwd(w["d.pool"], d_p)
             self._conv_stack_bwd(w, "img", self.img_layers, xi, d_p, Ns, B)

@@ -350,38 +350,49 @@ def _rows(t):
     return t.data_ptr(), t.stride(0)
 
 
-def linear_fwd(x, w, bias, y, act=0, mask=None, drop_p=0.0):
+def linear_fwd(x, w, bias, y, act=0, mask=None, drop_p=0.0, tc=False):
+    """y = act(x w^T + bias); tc=True: tcgen05 tf32 tensor-core GEMM, else the exact fp32 SIMT kernel."""
     M, K = x.shape
     N = w.shape[0]
     xp, ldx = _rows(x)
     yp, ldy = _rows(y)
-    _lib.check(_lib_().b200_linear_fwd(xp, ldx, _ptr(w, F32), _ptr(bias, F32), yp, ldy, M, N, K, act, _ptr(mask, U8), drop_p, _stream()),
-               "linear_fwd")
-
-
-def linear_bwd_data(dy, w, dx):
-    M, N = dy.shape
-    K = w.shape[1]
-    dyp, lddy = _rows(dy)
-    dxp, lddx = _rows(dx)
-    _lib.check(_lib_().b200_linear_bwd_data(dyp, lddy, _ptr(w, F32), dxp, lddx, M, N, K, _stream()), "linear_bwd_data")
+    fn = _lib_().b200_linear_fwd_tc if tc else _lib_().b200_linear_fwd
+    _lib.check(fn(xp, ldx, _ptr(w, F32), _ptr(bias, F32), yp, ldy, M, N, K, act, _ptr(mask, U8), drop_p, _stream()), "linear_fwd")
 
 
 _LINEAR_WORK = {}
 
 
-def linear_bwd_weight(dy, x, dw, db, accumulate=False, work=None):
+def _linear_work(device, need):
+    work = _LINEAR_WORK.get(device)         # one cached scratch per device, grown on demand
+    if work is None or work.numel() < need:
+        work = _LINEAR_WORK[device] = torch.empty(max(need, 4), dtype=F32, device=device)
+    return work
+
+
+def linear_bwd_data(dy, w, dx, tc=False):
+    M, N = dy.shape
+    K = w.shape[1]
+    dyp, lddy = _rows(dy)
+    dxp, lddx = _rows(dx)
+    if tc:
+        work = _linear_work(dy.device, _lib_().b200_linear_bwd_data_tc_work_floats(M, N, K))
+        _lib.check(_lib_().b200_linear_bwd_data_tc(dyp, lddy, _ptr(w, F32), dxp, lddx, _ptr(work, F32), M, N, K, _stream()), "linear_bwd_data")
+    else:
+        _lib.check(_lib_().b200_linear_bwd_data(dyp, lddy, _ptr(w, F32), dxp, lddx, M, N, K, _stream()), "linear_bwd_data")
+
+
+def linear_bwd_weight(dy, x, dw, db, accumulate=False, work=None, tc=False):
     M, N = dy.shape
     K = x.shape[1]
     dyp, lddy = _rows(dy)
     xp, ldx = _rows(x)
-    need = _lib_().b200_linear_bwd_weight_work_floats(M, N, K)
-    if work is None and need > 0:          # one cached split-K scratch per device, grown on demand
-        work = _LINEAR_WORK.get(dy.device)
-        if work is None or work.numel() < need:
-            work = _LINEAR_WORK[dy.device] = torch.empty(need, dtype=F32, device=dy.device)
-    _lib.check(_lib_().b200_linear_bwd_weight(dyp, lddy, xp, ldx, _ptr(dw, F32), _ptr(db, F32), _ptr(work, F32), M, N, K,
-                                              1 if accumulate else 0, _stream()), "linear_bwd_weight")
+    need = (_lib_().b200_linear_bwd_weight_tc_work_floats if tc else _lib_().b200_linear_bwd_weight_work_floats)(M, N, K)
+    if work is None and need > 0:
+        work = _linear_work(dy.device, need)
+    fn = _lib_().b200_linear_bwd_weight_tc if tc else _lib_().b200_linear_bwd_weight
+    _lib.check(fn(dyp, lddy, xp, ldx, _ptr(dw, F32), _ptr(db, F32), _ptr(work, F32), M, N, K, 1 if accumulate else 0, _stream()),
+               "linear_bwd_weight")
 
 
 def act_bwd(dy, y, drop_p=0.0):

@@ -238,3 +238,45 @@ def test_augmentation_direct_shift8_output_matches_pack():
     l1 = eng.train_step(img, aud).clone()
     torch.cuda.synchronize()
     assert 3.0 < float(l1[0]) < 6.0
+
+
+# (M, N, K): encoder FCs, fusion, projection head, ragged sizes (partial tiles in every dimension)
+LIN = [(6144, 256, 3136), (48, 256, 1600), (300, 512, 256), (130, 128, 512), (77, 10, 512), (1000, 256, 512)]
+
+
+@pytest.mark.parametrize("M,N,K", LIN)
+def test_linear_tensor_core_tf32(M, N, K):
+    """tcgen05 kind::tf32 GEMMs (fwd K-major x K-major, data gradient K-major x MN-major, weight gradient MN-major x MN-major
+    with split-K) against fp64 on the same fp32 tensors: tolerance 2e-3 of the output scale (tf32 operand rounding)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    dy = torch.randn(M, N, generator=g).to(DEV)
+    mask = (torch.rand(M, N, generator=g) > 0.3).to(torch.uint8).to(DEV)
+    want = x.double() @ w.double().t() + b.double()
+    for act in (0, 1, 2):
+        y = torch.full((M, N), float("nan"), device=DEV)
+        ops.linear_fwd(x, w, b, y, act=act, mask=mask if act == 2 else None, drop_p=0.3 if act == 2 else 0.0, tc=True)
+        ref = want if act == 0 else want.clamp_min(0)
+        if act == 2:
+            ref = ref * mask.double() / 0.7
+        assert float((y.double() - ref).abs().max()) <= 2e-3 * float(want.abs().max()), (M, N, K, act)
+    # strided output / input (column slices of a wider matrix, as the engine's cat buffer)
+    wide = torch.zeros(M, 2 * N + 4, device=DEV)
+    ops.linear_fwd(x, w, b, wide[:, N + 4:], tc=True)
+    assert float((wide[:, N + 4:].double() - want).abs().max()) <= 2e-3 * float(want.abs().max())
+    assert float(wide[:, :N + 4].abs().max()) == 0.0
+    dx = torch.full((M, K), float("nan"), device=DEV)
+    ops.linear_bwd_data(dy, w, dx, tc=True)
+    ref = dy.double() @ w.double()
+    assert float((dx.double() - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+    dw = torch.full((N, K), float("nan"), device=DEV)
+    db = torch.full((N,), float("nan"), device=DEV)
+    ops.linear_bwd_weight(dy, x, dw, db, tc=True)
+    ref = dy.double().t() @ x.double()
+    assert float((dw.double() - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+    assert float((db.double() - dy.double().sum(0)).abs().max()) <= 1e-4 * float(dy.double().abs().sum(0).max())
+    dw2 = dw.clone()
+    ops.linear_bwd_weight(dy, x, dw2, db, accumulate=True, tc=True)
+    assert float((dw2.double() - 2 * ref).abs().max()) <= 4e-3 * float(ref.abs().max())
