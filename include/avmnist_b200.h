@@ -169,6 +169,11 @@ int b200_bn_relu_pool8_bwd_reduce(const void* z8, const void* dp, const float* s
 int b200_bn_relu_pool8_bwd_apply(const void* z8, const void* dp, const float* scale, const float* shift,
                                  const float* mean, const float* invstd, const double* sums, void* dz8, double* dbsum,
                                  int N, int n_per_view, int C, int H, int W, int z_f16, int dp_fmt, void* stream);
+/* The same statistics as _bwd_reduce from the POOLED tensors only (no read of z): wherever the pooled output p is > 0 it
+ * equals gamma*xhat + beta at the arg-max, elsewhere the gradient is zero.  p, dp: [N][C][HP][WP] fp32 (fmt 0) or bf16 act8
+ * (fmt 1); gamma, beta: the BatchNorm weight / bias [C]. */
+int b200_bn_pool8_bwd_reduce_p(const void* p, const void* dp, const float* gamma, const float* beta, double* sums, int N,
+                               int n_per_view, int C, int HP, int WP, int p_fmt, int dp_fmt, void* stream);
 /* dbsum: double [C] (zeroed by the caller, may be NULL) += sum of dz per channel = the convolution's bias gradient */
 int b200_bias_grad_finalize(const double* dbsum, float* db, int C, void* stream);
 /* bf16 act8 -> fp32 NCHW */

@@ -215,6 +215,70 @@ __global__ void __launch_bounds__(256, 3) bn_relu_pool8_bwd_kernel(const uint4* 
     }
 }
 
+// BatchNorm-backward statistics from the POOLED tensors only.  At the arg-max position a*z+b = gamma*xhat + beta equals the
+// pooled output p wherever ReLU let it through (p > 0), and the gradient is zero elsewhere, so
+//     sum g = sum_{p>0} dp          sum g*xhat = sum_{p>0} dp * (p - beta) / gamma
+// -- no read of the 4x larger pre-BatchNorm tensor z and no arg-max search.  p / dp: fp32 NCHW (fmt 0) or bf16 act8 (fmt 1).
+__global__ void __launch_bounds__(256) bn_pool8_bwd_reduce_p_kernel(const void* __restrict__ p, const void* __restrict__ dp,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   double* __restrict__ sums, int n_per_view, int C, int HP, int WP, int p_fmt,
+                                                                   int dp_fmt) {
+    const int oct = blockIdx.y, v = blockIdx.z, P = C >> 3;
+    const int hw = HP * WP;
+    const long units = (long)n_per_view * hw;
+    const long u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
+    float ig[8], be[8], s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float gj = __ldg(gamma + oct * 8 + j);
+        ig[j] = gj != 0.f ? 1.0f / gj : 0.f;
+        be[j] = __ldg(beta + oct * 8 + j);
+        s1[j] = s2[j] = 0.f;
+    }
+    for (long u = u0 + threadIdx.x; u < u1; u += blockDim.x) {
+        const int s = (int)(u / hw), e = (int)(u - (long)s * hw);
+        const long n = (long)v * n_per_view + s;
+        float pv[8], g[8];
+        if (p_fmt) {
+            unpack8(__ldg(reinterpret_cast<const uint4*>(p) + (n * P + oct) * hw + e), pv);
+        } else {
+            const float* pp = reinterpret_cast<const float*>(p) + (n * C + oct * 8) * hw + e;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pv[j] = __ldg(pp + (long)j * hw);
+        }
+        if (dp_fmt) {
+            unpack8(__ldg(reinterpret_cast<const uint4*>(dp) + (n * P + oct) * hw + e), g);
+        } else {
+            const float* gp = reinterpret_cast<const float*>(dp) + (n * C + oct * 8) * hw + e;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = __ldg(gp + (long)j * hw);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float gj = pv[j] > 0.f ? g[j] : 0.f;
+            s1[j] += gj;
+            s2[j] += gj * ((pv[j] - be[j]) * ig[j]);
+        }
+    }
+    __shared__ float red[8][16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float x1 = warp_sum(s1[j]), x2 = warp_sum(s2[j]);
+        if (lane == 0) {
+            red[warp][j] = x1;
+            red[warp][8 + j] = x2;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        double acc = 0.0;
+        for (int wv = 0; wv < 8; ++wv) acc += (double)red[wv][threadIdx.x];
+        const int j = threadIdx.x & 7, which = threadIdx.x >> 3;
+        atomicAdd(&sums[((size_t)v * C + oct * 8 + j) * 2 + which], acc);
+    }
+}
+
 __global__ void bias_grad_finalize_kernel(const double* __restrict__ dbsum, float* __restrict__ db, int C) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) db[c] = (float)dbsum[c];
@@ -304,6 +368,21 @@ int b200_bn_relu_pool8_bwd_apply(const void* z8, const void* dp, const float* sc
             reinterpret_cast<const uint4*>(z8), dp, scale, shift, mean, invstd, const_cast<double*>(sums), reinterpret_cast<uint4*>(dz8), dbsum,
             n_per_view, C, H, W, dp_fmt);
     return launch_status("bn_relu_pool8_bwd_kernel<apply>");
+}
+
+int b200_bn_pool8_bwd_reduce_p(const void* p, const void* dp, const float* gamma, const float* beta, double* sums, int N, int n_per_view,
+                               int C, int HP, int WP, int p_fmt, int dp_fmt, void* stream) {
+    B200_REQUIRE(p && dp && gamma && beta && sums, -1, "bn_pool8_bwd_reduce_p: null pointer");
+    B200_REQUIRE(N > 0 && n_per_view > 0 && N % n_per_view == 0 && C % 8 == 0 && C > 0 && HP > 0 && WP > 0, -2, "bn_pool8_bwd_reduce_p: bad shape");
+    const int views = N / n_per_view, P = C / 8;
+    const long units = (long)n_per_view * HP * WP;
+    long chunks = (8L * sm_count() + (long)views * P - 1) / ((long)views * P);
+    const long max_chunks = (units + 511) / 512;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    bn_pool8_bwd_reduce_p_kernel<<<dim3((unsigned)chunks, (unsigned)P, (unsigned)views), 256, 0, as_stream(stream)>>>(p, dp, gamma, beta, sums,
+                                                                                                                  n_per_view, C, HP, WP, p_fmt, dp_fmt);
+    return launch_status("bn_pool8_bwd_reduce_p_kernel");
 }
 
 int b200_bias_grad_finalize(const double* dbsum, float* db, int C, void* stream) {

@@ -512,7 +512,8 @@ class DinoStepEngine:
                 if d_p.dtype != BF:
                     d_p = d_p.view(N, co, ho // 2, ho // 2)
                 dz = w["dz8"][:z.numel()].view_as(z)
-                ops.bn_relu_pool8_bwd_reduce(z, d_p, sc, sh, mu, inv, sums, B)
+                p_out = w[f"s.{mod}.p8{li}"] if f"s.{mod}.p8{li}" in w else w[f"s.{mod}.p{li}"]
+                ops.bn_pool8_bwd_reduce_p(p_out, d_p, S["enc." + bn + ".weight"], S["enc." + bn + ".bias"], sums, B)
                 ops.bn_relu_pool8_bwd_apply(z, d_p, sc, sh, mu, inv, sums, dz, B, dbsum=w["dbsum"][li])
                 ops.bias_grad_finalize(w["dbsum"][li], G["enc." + conv + ".bias"])
             else:

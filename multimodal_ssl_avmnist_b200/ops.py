@@ -291,6 +291,17 @@ def bn_relu_pool8_bwd_reduce(z8, dp, scale, shift, mean, invstd, sums, n_per_vie
                "bn_relu_pool8_bwd_reduce")
 
 
+def bn_pool8_bwd_reduce_p(p, dp, gamma, beta, sums, n_per_view):
+    """BatchNorm-backward sums {sum g, sum g*xhat} from the pooled output p and its gradient dp only (fp32 NCHW or bf16 act8 each)."""
+    if p.dim() == 5:
+        N, P, HP, WP, _ = p.shape
+        Cc = P * 8
+    else:
+        N, Cc, HP, WP = p.shape
+    _lib.check(_lib_().b200_bn_pool8_bwd_reduce_p(_ptr(p), _ptr(dp), _ptr(gamma, F32), _ptr(beta, F32), _ptr(sums, F64), N, n_per_view, Cc,
+                                                  HP, WP, _fmt(p), _fmt(dp), _stream()), "bn_pool8_bwd_reduce_p")
+
+
 def bn_relu_pool8_bwd_apply(z8, dp, scale, shift, mean, invstd, sums, dz8, n_per_view, dbsum=None):
     N, P, H, W, _ = z8.shape
     _lib.check(_lib_().b200_bn_relu_pool8_bwd_apply(_ptr(z8), _ptr(dp), _ptr(scale, F32), _ptr(shift, F32), _ptr(mean, F32),

@@ -280,3 +280,32 @@ def test_linear_tensor_core_tf32(M, N, K):
     dw2 = dw.clone()
     ops.linear_bwd_weight(dy, x, dw2, db, accumulate=True, tc=True)
     assert float((dw2.double() - 2 * ref).abs().max()) <= 4e-3 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("C,H,views,B", [(16, 56, 2, 3), (64, 10, 3, 7), (8, 112, 2, 2)])
+def test_bn_backward_statistics_from_pooled_tensors(C, H, views, B):
+    """b200_bn_pool8_bwd_reduce_p (reads only p and dp) == b200_bn_relu_pool8_bwd_reduce (reads z) up to the rounding of p."""
+    g = torch.Generator().manual_seed(C * 3 + H)
+    N = views * B
+    z = torch.randn(N, C, H, H, generator=g).half().float().to(DEV)
+    gamma = (torch.randn(C, generator=g) * 0.3 + 1.0).to(DEV)
+    gamma[1] = -0.7                                            # a negative BatchNorm weight (arg-max becomes arg-min of z)
+    beta = (torch.randn(C, generator=g) * 0.2).to(DEV)
+    zv = z.view(views, B, C, -1)
+    mean = zv.mean(dim=(1, 3))
+    invstd = (zv.var(dim=(1, 3), unbiased=False) + 1e-5).rsqrt()
+    scale = (gamma[None] * invstd).contiguous()
+    shift = (beta[None] - mean * scale).contiguous()
+    dp = _bf(torch.randn(N, C, H // 2, H // 2, generator=g)).to(DEV)
+    z8 = z.view(N, C // 8, 8, H, H).permute(0, 1, 3, 4, 2).contiguous().half()
+    want = torch.zeros(views, C, 2, dtype=torch.float64, device=DEV)
+    ops.bn_relu_pool8_bwd_reduce(z8, dp, scale, shift, mean.contiguous(), invstd.contiguous(), want, B)
+    p32 = torch.empty(N, C, H // 2, H // 2, device=DEV)
+    ops.bn_relu_pool8_fwd(z8, scale, shift, p32, B)
+    p8 = torch.empty(N, C // 8, H // 2, H // 2, 8, dtype=torch.bfloat16, device=DEV)
+    ops.bn_relu_pool8_fwd(z8, scale, shift, p8, B)
+    ref_scale = want.abs().max(dim=1, keepdim=True).values + 1e-9
+    for pt, dpt, tol in ((p32, dp, 1e-4), (p8, _pack8(dp), 5e-3), (p8, dp, 5e-3)):
+        got = torch.zeros_like(want)
+        ops.bn_pool8_bwd_reduce_p(pt, dpt, gamma, beta, got, B)
+        assert float(((got - want).abs() / ref_scale).max()) < tol, (pt.dtype, dpt.dtype)
