@@ -223,13 +223,13 @@ def op_cost(name, meta):
     return 0.0, 0.0
 
 
-def profile_ops(engine, images, audios, steps=2):
+def profile_ops(engine, images, audios, steps=2, labels=None):
     """Per-op CUDA-event timing of `steps` whole steps (events on the launching stream)."""
     import torch
     from multimodal_ssl_avmnist_b200 import ops
     rec = ops.start_profile()
     for _ in range(steps):
-        engine.train_step(images, audios)
+        engine.train_step(images, audios, labels)
     torch.cuda.synchronize()
     ops.stop_profile()
     agg = {}
@@ -267,11 +267,13 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
-    eng = DinoStepEngine(kind="multi_central", mode="default", augment_values=augment_values(), seed=1 + rank, device=dev)
+    eng = DinoStepEngine(kind="multi_central", mode=args.mode, augment_values=augment_values(), seed=1 + rank, device=dev)
     g = torch.Generator().manual_seed(1 + rank)
     img_h = torch.rand(B, 28, 28, generator=g).pin_memory()
     aud_h = torch.randint(0, 256, (B, 112, 112), generator=g, dtype=torch.uint8).pin_memory()
     img_d, aud_d = img_h.to(dev), aud_h.to(dev)
+    lab_h = torch.randint(0, 10, (B,), generator=g).pin_memory() if args.mode == "semi_supervised" else None
+    lab_d = lab_h.to(dev) if lab_h is not None else None
 
     def barrier():
         if world > 1:
@@ -280,7 +282,7 @@ def run_ours(args):
 
     # ---- warm-up (also sizes the workspaces) ----
     for _ in range(max(args.warmup, 3)):
-        eng.train_step(img_d, aud_d)
+        eng.train_step(img_d, aud_d, lab_d)
     barrier()
     # ---- timed region 1: inputs resident in HBM ----
     clocks = ClockSampler(local) if rank == 0 else None
@@ -289,20 +291,20 @@ def run_ours(args):
     barrier()
     e0.record()
     for _ in range(args.steps):
-        loss = eng.train_step(img_d, aud_d)
+        loss = eng.train_step(img_d, aud_d, lab_d)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
     launches = (ops.launch_count() - l0) // args.steps
     # ---- timed region 2: end to end through the host-facing call (pinned host buffers in, loss out) ----
     for _ in range(2):
-        eng.train_step_host(img_h, aud_h)
+        eng.train_step_host(img_h, aud_h, lab_h)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     last = None
     for _ in range(args.steps):
-        last = eng.train_step_host(img_h, aud_h)
+        last = eng.train_step_host(img_h, aud_h, lab_h)
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3) / args.steps
@@ -311,7 +313,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
-    rows = profile_ops(eng, img_d, aud_d, steps=2)       # every rank runs it (the step contains collectives when N > 1)
+    rows = profile_ops(eng, img_d, aud_d, steps=2, labels=lab_d)       # every rank runs it (the step contains collectives when N > 1)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -351,7 +353,8 @@ def run_ours(args):
     out_dir = os.path.join(ROOT, "gpurun_out")
     try:
         os.makedirs(out_dir, exist_ok=True)
-        with open(os.path.join(out_dir, f"bench_ops_n{world}_b{B}.json"), "w") as f:
+        tag = "" if args.mode == "default" else "_" + args.mode
+        with open(os.path.join(out_dir, f"bench_ops_n{world}_b{B}{tag}.json"), "w") as f:
             json.dump({"ms_per_step": ms, "profiled_ms_per_step": step_ms_prof, "ops": rows}, f, indent=1)
     except Exception:
         pass
@@ -363,7 +366,7 @@ def run_ours(args):
     h2d = img_h.numel() * 4 + aud_h.numel()
     line = {"metric": METRIC, "value": B * world / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+            "config": {"workload": WORKLOAD if args.mode == "default" else WORKLOAD.replace("default mode", args.mode + " mode"), "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations) is several GB, far larger than the 126 MB L2",
                        "precision": "bf16 tensor-core convolutions (fp16 pre-BatchNorm z, bf16 activations / gradients), fp32 accumulate, "
                                     "statistics, linears, losses, EMA, Adam"},
@@ -383,6 +386,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="default", choices=["default", "semi_supervised", "infonce", "mse"],
+                    help="training mode (BASELINE.json configs 2-5); the headline line is --mode default")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
