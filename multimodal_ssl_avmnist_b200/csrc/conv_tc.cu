@@ -57,8 +57,11 @@ constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
 constexpr int SMEM_EST(int nmma, int npad, int slots, int slot_bytes, int tail) { return round_up(nmma * npad * 32, 128) + slots * slot_bytes + tail + 256 + npad * 4; }
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
-template <int CIN_, int COUT_, int NPAD_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int CTAS_ = 1>
+template <int CIN_, int COUT_, int NPAD_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int CTAS_ = 1, int NSPLIT_ = 1>
 struct TcCfg {
+    static constexpr int NSPLIT = NSPLIT_;                      // output channels split over gridDim.z (halves the smem weight image)
+    static constexpr int NPADL = NPAD_ / NSPLIT_, COUTL = COUT_ / NSPLIT_;
+    static_assert(NSPLIT_ == 1 || (COUT_ == NPAD_ && NPADL % 16 == 0), "N split needs C_out == NPAD and 16-channel slices");
     static constexpr int CIN = CIN_, COUT = COUT_, NPAD = NPAD_, HIN = HIN_, WIN = WIN_, KS = KS_, PAD = PAD_, BANDS = BANDS_, SLOTS = SLOTS_;
     static constexpr int CTAS = CTAS_;                          // resident CTAs per SM (independent MMA streams hide the per-UMMA fixed cost)
     static constexpr bool L0 = (CIN == 1);                      // first layer: input is the "shift8" image (unit = x[q..q+7])
@@ -74,16 +77,16 @@ struct TcCfg {
     static constexpr int NJ = (KS + 1) / 2;                     // kw pairs when CIN == 8
     static constexpr int PH = P / 2;                            // plane pairs when CIN >= 16
     static constexpr int NMMA = L0 ? NJ : (CIN == 8) ? KS * NJ : KS * KS * PH;
-    static constexpr int W_BYTES = round_up(NMMA * NPAD * 32, 128);
+    static constexpr int W_BYTES = round_up(NMMA * NPADL * 32, 128);
     static constexpr int MAXPIX = TILES * 128 + (L0 ? KS : KS - 1) * WP + KS + 1;   // exclusive bound of pixels a tile may touch
     static constexpr int TAIL = round_up((MAXPIX > HPB * WP ? (MAXPIX - HPB * WP) : 0) * 16, 128) + 128;
     static constexpr int IMG_BYTES = SLOTS * SLOT_BYTES + TAIL;
     static constexpr int BAR_OFF = W_BYTES + IMG_BYTES;
-    static constexpr int SMEM = BAR_OFF + 256 + NPAD * 4;
-    static constexpr int NBUF = (NPAD <= 32 ? 8 : 4) / (CTAS > 2 ? 2 : 1);   // TMEM accumulator stages
-    static constexpr int TMEM_COLS = pow2_cols(NBUF * NPAD);
+    static constexpr int SMEM = BAR_OFF + 256 + NPADL * 4;
+    static constexpr int NBUF = (NPADL <= 32 ? 8 : 4) / (CTAS > 2 ? 2 : 1);   // TMEM accumulator stages
+    static constexpr int TMEM_COLS = pow2_cols(NBUF * NPADL);
     static_assert(TMEM_COLS * CTAS <= 512, "TMEM columns per SM");
-    static_assert((SMEM_EST(NMMA, NPAD, SLOTS, SLOT_BYTES, TAIL) + 1024) * CTAS <= 227 * 1024, "shared memory per SM");
+    static_assert((SMEM_EST(NMMA, NPADL, SLOTS, SLOT_BYTES, TAIL) + 1024) * CTAS <= 227 * 1024, "shared memory per SM");
     static_assert(2 * SLOTS + 2 * NBUF <= 24, "barrier area");
     static_assert(CIN == 1 || (CIN % 8 == 0 && (CIN == 8 || CIN % 16 == 0)), "C_in must be 1, 8 or a multiple of 16");
     static_assert(NPAD % 16 == 0 && NPAD >= 16 && NPAD <= 64 && COUT <= NPAD && COUT % 8 == 0, "N tile");
@@ -121,10 +124,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
     {
         const uint4* src = wprep;
         uint4* dst = reinterpret_cast<uint4*>(w_s);
-        for (int i = threadIdx.x; i < C::NMMA * C::NPAD * 2; i += blockDim.x) dst[i] = src[i];
+        constexpr int NGL = C::NPADL / 8, NG = C::NPAD / 8;          // 8-row groups (128 B = 8 uint4) per K chunk: local / whole
+        for (int i = threadIdx.x; i < C::NMMA * 2 * NGL * 8; i += blockDim.x) {
+            const int q = i & 7, gl = (i >> 3) % NGL, mc = (i >> 3) / NGL;
+            dst[i] = src[(mc * NG + blockIdx.z * NGL + gl) * 8 + q];
+        }
         uint4* z = reinterpret_cast<uint4*>(img_s);
         for (int i = threadIdx.x; i < C::IMG_BYTES / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
-        for (int i = threadIdx.x; i < C::NPAD; i += blockDim.x) bias_s[i] = (bias != nullptr && i < C::COUT) ? bias[i] : 0.f;
+        for (int i = threadIdx.x; i < C::NPADL; i += blockDim.x) bias_s[i] = (bias != nullptr && i < C::COUTL) ? bias[blockIdx.z * C::COUTL + i] : 0.f;
         fence_proxy_async_smem();
     }
     if (warp == 0 && lane == 0) {
@@ -160,7 +167,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            constexpr uint32_t idesc = idesc_bf16(C::NPAD);
+            constexpr uint32_t idesc = idesc_bf16(C::NPADL);
             uint32_t tcount = 0;
             for (int i = i0; i < i1; ++i) {
                 const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
@@ -171,7 +178,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
                     const uint32_t buf = tcount % C::NBUF, u = tcount / C::NBUF;
                     mbar_wait(tempty_bar(buf), (u & 1) ^ 1);
                     tc_fence_after_sync();
-                    const uint32_t d = tmem_base + buf * C::NPAD;
+                    const uint32_t d = tmem_base + buf * C::NPADL;
                     const uint32_t a0 = slot_addr + t * 2048;
                     int idx = 0;
                     if constexpr (C::L0) {
@@ -179,7 +186,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
 #pragma unroll
                         for (int j = 0; j < C::NJ; ++j, ++idx) {
                             const uint64_t ad = smem_desc(a0 + (2 * j * C::WP) * 16, C::WP * 16, 128);
-                            const uint64_t bd = smem_desc(w_addr + idx * C::NPAD * 32, C::NPAD * 16, 128);
+                            const uint64_t bd = smem_desc(w_addr + idx * C::NPADL * 32, C::NPADL * 16, 128);
                             mma_bf16(d, ad, bd, idesc, idx > 0);
                         }
                     } else {
@@ -189,7 +196,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
 #pragma unroll
                             for (int j = 0; j < C::NJ; ++j, ++idx) {
                                 const uint64_t ad = smem_desc(a0 + (kh * C::WP + 2 * j) * 16, 16, 128);
-                                const uint64_t bd = smem_desc(w_addr + idx * C::NPAD * 32, C::NPAD * 16, 128);
+                                const uint64_t bd = smem_desc(w_addr + idx * C::NPADL * 32, C::NPADL * 16, 128);
                                 mma_bf16(d, ad, bd, idesc, idx > 0);
                             }
                         } else {
@@ -198,7 +205,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
 #pragma unroll
                                 for (int pp = 0; pp < C::PH; ++pp, ++idx) {
                                     const uint64_t ad = smem_desc(a0 + (kh * C::WP + kw) * 16 + pp * 2 * C::PLANE_BYTES, C::PLANE_BYTES, 128);
-                                    const uint64_t bd = smem_desc(w_addr + idx * C::NPAD * 32, C::NPAD * 16, 128);
+                                    const uint64_t bd = smem_desc(w_addr + idx * C::NPADL * 32, C::NPADL * 16, 128);
                                     mma_bf16(d, ad, bd, idesc, idx > 0);
                                 }
                             }
@@ -213,9 +220,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
     } else {
         // ===== epilogue warps (TMEM lane quadrant = warp % 4) =====
         const int quad = warp & 3, row = quad * 32 + lane;
-        float s1[C::COUT], s2[C::COUT];
+        float s1[C::COUTL], s2[C::COUTL];
 #pragma unroll
-        for (int c = 0; c < C::COUT; ++c) s1[c] = s2[c] = 0.f;
+        for (int c = 0; c < C::COUTL; ++c) s1[c] = s2[c] = 0.f;
+        const int co0 = blockIdx.z * C::COUTL;                  // first output channel of this CTA's slice
         const bool do_stats = (bias != nullptr) && (stats != nullptr);
         uint32_t tcount = 0;
         for (int i = i0; i < i1; ++i) {
@@ -228,13 +236,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
                 const int y = q / C::WP, x = q - y * C::WP;
                 const bool valid = (y < C::HB) && (x < C::WO);
                 const int yy = band * C::HB + y;
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * C::NPAD;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * C::NPADL;
 #pragma unroll
-                for (int cc = 0; cc < C::NPAD / 16; ++cc) {
+                for (int cc = 0; cc < C::NPADL / 16; ++cc) {
                     uint32_t v[16];
                     tmem_ld16(taddr + cc * 16, v);
                     tmem_ld_wait();
-                    if (cc == C::NPAD / 16 - 1) {                 // accumulator drained: hand the TMEM buffer back
+                    if (cc == C::NPADL / 16 - 1) {                // accumulator drained: hand the TMEM buffer back
                         tc_fence_before_sync();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty_bar(buf));
@@ -244,9 +252,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
                     for (int j = 0; j < 16; ++j) {
                         const int ch = cc * 16 + j;
                         f[j] = __uint_as_float(v[j]) + bias_s[ch];
-                        if (ch < C::COUT && valid) {
-                            s1[ch < C::COUT ? ch : 0] += f[j];
-                            s2[ch < C::COUT ? ch : 0] += f[j] * f[j];
+                        if (ch < C::COUTL && valid) {
+                            s1[ch < C::COUTL ? ch : 0] += f[j];
+                            s2[ch < C::COUTL ? ch : 0] += f[j] * f[j];
                         }
                     }
                     if (valid) {
@@ -254,7 +262,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
 #pragma unroll
                             for (int o = 0; o < 2; ++o) {
                                 const int oct = cc * 2 + o;
-                                if (oct * 8 < C::COUT) {
+                                if (oct * 8 < C::COUTL) {
                                     uint4 pk;
                                     if (out_bf16 == 2) {
                                         pk.x = pack_f16(f[o * 8 + 0], f[o * 8 + 1]);
@@ -267,16 +275,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
                                         pk.z = pack_bf16(f[o * 8 + 4], f[o * 8 + 5]);
                                         pk.w = pack_bf16(f[o * 8 + 6], f[o * 8 + 7]);
                                     }
-                                    uint4* dst = reinterpret_cast<uint4*>(out) + (((long)n * (C::COUT / 8) + oct) * C::HO + yy) * C::WO + x;
+                                    uint4* dst = reinterpret_cast<uint4*>(out) + (((long)n * (C::COUT / 8) + co0 / 8 + oct) * C::HO + yy) * C::WO + x;
                                     *dst = pk;
                                 }
                             }
                         } else {
-                            float* dst = reinterpret_cast<float*>(out) + (((long)n * C::COUT) * C::HO + yy) * C::WO + x;
+                            float* dst = reinterpret_cast<float*>(out) + (((long)n * C::COUT + co0) * C::HO + yy) * C::WO + x;
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
                                 const int ch = cc * 16 + j;
-                                if (ch < C::COUT) dst[(long)ch * C::HO * C::WO] = f[j];
+                                if (ch < C::COUTL) dst[(long)ch * C::HO * C::WO] = f[j];
                             }
                         }
                     }
@@ -285,11 +293,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
         }
         if (do_stats) {
 #pragma unroll
-            for (int c = 0; c < C::COUT; ++c) {
+            for (int c = 0; c < C::COUTL; ++c) {
                 const double a = warp_sum((double)s1[c]), b = warp_sum((double)s2[c]);
                 if (lane == 0) {
-                    atomicAdd(&stats[((long)view * C::COUT + c) * 2 + 0], a);
-                    atomicAdd(&stats[((long)view * C::COUT + c) * 2 + 1], b);
+                    atomicAdd(&stats[((long)view * C::COUT + co0 + c) * 2 + 0], a);
+                    atomicAdd(&stats[((long)view * C::COUT + co0 + c) * 2 + 1], b);
                 }
             }
         }
@@ -395,11 +403,11 @@ int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* ou
     int rc = encode_tmap_bf16_4d(&tm, x, dims, strides, box);
     if (rc) return rc;
     const int views = N / n_per_view;
-    int G = sm_count() * C::CTAS / views;
+    int G = sm_count() * C::CTAS / (views * C::NSPLIT);
     if (G < 1) G = 1;
     const long items = (long)n_per_view * C::BANDS;
     if (G > items) G = (int)items;
-    conv_tc_kernel<C><<<dim3(G, views), 192, C::SMEM, st>>>(tm, reinterpret_cast<const uint4*>(wprep), bias, out, stats, n_per_view, out_bf16);
+    conv_tc_kernel<C><<<dim3(G, views, C::NSPLIT), 192, C::SMEM, st>>>(tm, reinterpret_cast<const uint4*>(wprep), bias, out, stats, n_per_view, out_bf16);
     return launch_status("conv_tc_kernel");
 }
 
@@ -421,22 +429,23 @@ constexpr int hbz_for(int hb, int wp) {
     return h;
 }
 
-template <int CIN_, int COUT_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int PSPLIT_, int CTAS_ = 1>
+template <int CIN_, int COUT_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int PSPLIT_, int CTAS_ = 1, int NSPLIT_ = 1>
 struct TcWgCfg {
+    static constexpr int NSPLIT = NSPLIT_, COUTL = COUT_ / NSPLIT_;     // dz channel planes split over CTAs (fewer TMEM columns per CTA)
     static constexpr int CTAS = CTAS_;                           // resident CTAs per SM
     static constexpr int CIN = CIN_, COUT = COUT_, HIN = HIN_, WIN = WIN_, KS = KS_, PAD = PAD_, BANDS = BANDS_, SLOTS = SLOTS_, PSPLIT = PSPLIT_;
     static constexpr bool L0 = (CIN == 1);                       // first layer over the shift8 image: rows = (kh, kw) in ONE accumulator
-    static constexpr int P_IN = L0 ? 1 : CIN / 8, P_OUT = COUT / 8, PI = P_IN / PSPLIT;
+    static constexpr int P_IN = L0 ? 1 : CIN / 8, P_OUT = COUT / 8, P_OUTL = COUTL / 8, PI = P_IN / PSPLIT;
     static constexpr int WP = WIN + 2 * PAD;
     static constexpr int HO = HIN + 2 * PAD - KS + 1, WO = WP - KS + 1;
     static constexpr int HB = HO / BANDS, HPB = HB + KS - 1;
     static constexpr int HBZ = hbz_for(HB, WP);
     static constexpr int KSTEPS = HBZ * WP / 16;
     static constexpr int PLANE_X = HPB * WP * 16, PLANE_Z = HBZ * WP * 16;
-    static constexpr int X_BYTES = round_up(PI * PLANE_X, 128), Z_BYTES = round_up(P_OUT * PLANE_Z, 128);
+    static constexpr int X_BYTES = round_up(PI * PLANE_X, 128), Z_BYTES = round_up(P_OUTL * PLANE_Z, 128);
     static constexpr int SLOT_BYTES = X_BYTES + Z_BYTES;
     static constexpr int NACC = L0 ? 1 : KS * PI;
-    static constexpr int TMEM_COLS = pow2_cols(NACC * COUT);
+    static constexpr int TMEM_COLS = pow2_cols(NACC * COUTL);
     static constexpr int ONES_OFF = SLOTS * SLOT_BYTES;
     static constexpr int BAR_OFF = ONES_OFF;
     static constexpr int SMEM = BAR_OFF + 256;
@@ -444,7 +453,7 @@ struct TcWgCfg {
     static constexpr int PART = DW;                                 // floats per CTA partial
     static_assert(P_IN % PSPLIT == 0 && HO % BANDS == 0, "splits");
     static_assert(BANDS == 1 || HBZ == HB, "row bands need HB*WP to be a multiple of 16");
-    static_assert(NACC * COUT <= 512 && TMEM_COLS * CTAS <= 512, "TMEM columns");
+    static_assert(NACC * COUTL <= 512 && TMEM_COLS * CTAS <= 512 && COUTL % 8 == 0, "TMEM columns");
     static_assert((SMEM + 1024) * CTAS <= 227 * 1024, "shared memory per SM");
     static_assert(KS <= 8 && COUT % 8 == 0 && COUT >= 8 && COUT <= 256, "shape");
     static_assert((KSTEPS * 16 + (L0 ? 7 : KS - 1) * WP + 8 - HPB * WP) * 16 <= Z_BYTES, "x overrun must stay inside the slot");
@@ -458,7 +467,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);     // full[SLOTS], empty[SLOTS], done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::BAR_OFF + 192);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int G = gridDim.x, g = blockIdx.x, split = blockIdx.z;
+    const int G = gridDim.x, g = blockIdx.x, split = blockIdx.z % C::PSPLIT, ns = blockIdx.z / C::PSPLIT;
     const long items = (long)N * C::BANDS;
     const int i0 = (int)(items * g / G), i1 = (int)(items * (g + 1) / G);
     const uint32_t bar0 = smem_u32(bars);
@@ -492,16 +501,16 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             for (int i = i0; i < i1; ++i) {
                 const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
                 mbar_wait(empty_bar(slot), (use & 1) ^ 1);
-                mbar_expect_tx(full_bar(slot), C::PI * C::PLANE_X + C::P_OUT * C::PLANE_Z);
+                mbar_expect_tx(full_bar(slot), C::PI * C::PLANE_X + C::P_OUTL * C::PLANE_Z);
                 const int n = i / C::BANDS, band = i % C::BANDS;
                 const uint32_t sa = smem0 + slot * C::SLOT_BYTES;
                 tma_load_4d(sa, &tmap_x, full_bar(slot), 0, C::L0 ? 0 : -C::PAD, band * C::HB - C::PAD, n * C::P_IN + split * C::PI);
-                tma_load_4d(sa + C::X_BYTES, &tmap_z, full_bar(slot), 0, 0, band * C::HB, n * C::P_OUT);
+                tma_load_4d(sa + C::X_BYTES, &tmap_z, full_bar(slot), 0, 0, band * C::HB, n * C::P_OUT + ns * C::P_OUTL);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = idesc_bf16(C::COUT, true, true, 64);
+            constexpr uint32_t idesc = idesc_bf16(C::COUTL, true, true, 64);
             for (int i = i0; i < i1; ++i) {
                 const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
                 mbar_wait(full_bar(slot), use & 1);
@@ -520,7 +529,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 #pragma unroll
                             for (int pl = 0; pl < C::PI; ++pl) {
                                 const uint64_t ad = smem_desc(xa + pl * C::PLANE_X + (ks * 16 + kh * C::WP) * 16, 128, 16);
-                                mma_bf16(tmem_base + (kh * C::PI + pl) * C::COUT, ad, bd, idesc, acc);
+                                mma_bf16(tmem_base + (kh * C::PI + pl) * C::COUTL, ad, bd, idesc, acc);
                             }
                         }
                     }
@@ -543,10 +552,10 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         for (int a = 0; a < C::NACC; ++a) {
             const int kh = a / C::PI, pl = a % C::PI;
 #pragma unroll
-            for (int cc = 0; cc < (C::COUT + 15) / 16; ++cc) {
+            for (int cc = 0; cc < (C::COUTL + 15) / 16; ++cc) {
                 uint32_t v[16];
                 if (i1 > i0) {
-                    tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + a * C::COUT + cc * 16, v);
+                    tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + a * C::COUTL + cc * 16, v);
                     tmem_ld_wait();
                 } else {
 #pragma unroll
@@ -554,8 +563,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 }
 #pragma unroll
                 for (int t = 0; t < 16; ++t) {
-                    const int co = cc * 16 + t;
-                    if (co < C::COUT) {
+                    const int co = ns * C::COUTL + cc * 16 + t;
+                    if (cc * 16 + t < C::COUTL) {
                         if constexpr (C::L0) {      // row m = (kh = j, kw = ci8)
                             if (lane < 16 && j < C::KS && ci8 < C::KS) part[(co * C::KS + j) * C::KS + ci8] = __uint_as_float(v[t]);
                         } else if (rowok) {
@@ -586,7 +595,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 
 template <class C>
 int wgrad_ctas(int N) {
-    int G = sm_count() * C::CTAS / C::PSPLIT;
+    int G = sm_count() * C::CTAS / (C::PSPLIT * C::NSPLIT);
     const long items = (long)N * C::BANDS;
     if (G > items) G = (int)items;
     return G < 1 ? 1 : G;
@@ -620,11 +629,11 @@ int launch_conv_tc_wgrad(const void* x, const void* dz, float* dw, float* work, 
     {
         const uint64_t dims[4] = {8, (uint64_t)C::WO, (uint64_t)C::HO, (uint64_t)N * C::P_OUT};
         const uint64_t strides[3] = {16, (uint64_t)C::WO * 16, (uint64_t)C::WO * C::HO * 16};
-        const uint32_t box[4] = {8, (uint32_t)C::WP, (uint32_t)C::HBZ, (uint32_t)C::P_OUT};
+        const uint32_t box[4] = {8, (uint32_t)C::WP, (uint32_t)C::HBZ, (uint32_t)C::P_OUTL};
         int rc = encode_tmap_bf16_4d(&tz, dz, dims, strides, box);
         if (rc) return rc;
     }
-    conv_tc_wgrad_kernel<C><<<dim3(G, 1, C::PSPLIT), 192, C::SMEM, st>>>(tx, tz, work, N);
+    conv_tc_wgrad_kernel<C><<<dim3(G, 1, C::PSPLIT * C::NSPLIT), 192, C::SMEM, st>>>(tx, tz, work, N);
     int rc = launch_status("conv_tc_wgrad_kernel");
     if (rc) return rc;
     wgrad_reduce_kernel<<<(C::PART + 255) / 256, 256, 0, st>>>(work, G, C::PART, dw);
@@ -644,7 +653,7 @@ using WgS0 = TcWgCfg<1, 32, 28, 28, 3, 1, 1, 3, 1>;
 //                         CIN COUT NPAD HIN  WIN KS PAD BANDS SLOTS
 using CfgA1 = TcCfg<8, 16, 16, 56, 56, 5, 2, 2, 2, 3>;   // audio conv2 forward
 using CfgA2 = TcCfg<16, 32, 32, 28, 28, 5, 2, 1, 2, 2>;  // audio conv3 forward
-using CfgA3 = TcCfg<32, 64, 64, 14, 14, 5, 2, 1, 4>;     // audio conv4 forward
+using CfgA3 = TcCfg<32, 64, 64, 14, 14, 5, 2, 1, 4>;     // audio conv4 forward (an N split over 2 CTAs/SM measured slower: N = 64 MMAs amortise the fixed cost)
 using CfgI1 = TcCfg<32, 64, 64, 14, 14, 5, 0, 1, 4>;     // image conv2 forward (no padding)
 using CfgA1d = TcCfg<16, 8, 16, 56, 56, 5, 2, 4, 2, 2>;  // data gradients (C_in/C_out swapped, pad' = K-1-pad)
 using CfgA2d = TcCfg<32, 16, 16, 28, 28, 5, 2, 2, 2, 2>;
