@@ -241,7 +241,7 @@ class MultiModalDINO(_DinoBase):
             eng.set_augmentation(augment_values)
         img = images.to(dev).reshape(-1, 28, 28).contiguous()
         aud = audios.to(dev).reshape(-1, 112, 112).contiguous()
-        xi, xa = eng.augment(img, aud)
+        xi, xa = eng.augment(img, aud, direct=True)      # views go straight into the first conv's operand format
         raw = None
         if with_raw:
             raw = (img.float() / 255.0 if img.dtype == torch.uint8 else img, aud.float() / 255.0 if aud.dtype == torch.uint8 else aud)

@@ -1,0 +1,133 @@
+"""GPU: the reference-shaped API (AVMNIST_Experiments mirror) drives the CUDA step: training_step -> loss.backward() ->
+optimizer.step() through the Lightning modules, all four training modes + the unimodal model, and a short Trainer.fit on
+synthetic AVMNIST files; the module path must agree with the bare engine on the same weights and views."""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MIRROR = os.path.join(ROOT, "multimodal_ssl_avmnist_b200", "AVMNIST_Experiments")
+sys.path.insert(0, MIRROR)
+
+import models.dino as md  # noqa: E402
+import utils.get_data as gd  # noqa: E402
+from oracle.fixtures import synth_raw, synth_views  # noqa: E402
+
+DEV = "cuda"
+KW = dict(data_dir="x/", data_augmentation="burst_noise", dino_model=None, encoder_class=md.CentralMultiModalEncoder, encoder_kwargs=None,
+          projection_dim=128, output_dim=256, encoder_output_dim=256, momentum=0.996, center_momentum=0.9, student_temperature=0.1,
+          teacher_temperature=0.04, learning_rate=1e-3, use_mixed_precision=True, num_epochs=100, weight_decay=1e-6, dropout=0.3)
+WRAPPERS = {"default": md.MultiModalDINOLightning, "semi_supervised": md.MultiModalDINOSemiSupervisedLightning,
+            "infonce": md.MultiModalDINOWithINFONCELightning, "mse": md.MultiModalDINOWithMSELightning}
+
+
+def _batch(mode, B, seed):
+    gi, ga, li, la = synth_views(B, seed=seed)          # [B, V, 1, H, W] like the reference's collated batch
+    views = tuple(t.to(DEV) for t in (gi, ga, li, la))
+    if mode == "default":
+        return views
+    image, audio, labels = synth_raw(B, seed=seed + 1)
+    return image.to(DEV), audio.to(DEV), labels.to(DEV), views
+
+
+@pytest.mark.parametrize("mode", list(WRAPPERS))
+def test_training_step_backward_optimizer(mode):
+    torch.manual_seed(0)
+    lit = WRAPPERS[mode](**KW).to(DEV)
+    opt = lit.configure_optimizers()["optimizer"]
+    B = 8
+    before = {k: v.detach().clone() for k, v in lit.model.student.state_dict().items() if v.dtype == torch.float32}
+    teacher0 = lit.model.teacher.fusion[0].weight.detach().clone()
+    losses = []
+    for it in range(3):
+        opt.zero_grad(set_to_none=True)
+        loss = lit.training_step(_batch(mode, B, 10 + it), it)
+        assert loss.requires_grad and loss.dim() == 0
+        loss.backward()
+        g = lit.model.student.audio_encoder[0].conv2.weight.grad
+        assert g is not None and float(g.abs().sum()) > 0
+        assert lit.model.student.image_encoder[0].fc1.weight.grad is None or float(lit.model.student.image_encoder[0].fc1.weight.grad.abs().sum()) == 0
+        opt.step()
+        losses.append(float(loss))
+    torch.cuda.synchronize()
+    assert all(l == l and 3.0 < l < 12.0 for l in losses), losses
+    moved = max(float((lit.model.student.state_dict()[k] - v).abs().max()) for k, v in before.items() if "fc1" not in k and "fc2" not in k)
+    assert moved > 1e-4
+    assert float((lit.model.teacher.fusion[0].weight - teacher0).abs().max()) > 0          # EMA follows the student
+    assert float(lit.model.center.abs().max()) > 0
+    # parameters still alias the engine arenas and the state_dict has the reference's keys
+    eng = lit.model.engine
+    assert lit.model.student.fusion[0].weight.data_ptr() == eng.S["enc.fusion.0.weight"].data_ptr()
+    sd = lit.state_dict()
+    assert "model.student.audio_encoder.0.conv4.weight" in sd and "model.center" in sd and "model.teacher_projection.mlp.4.bias" in sd
+
+
+def test_module_path_matches_the_bare_engine():
+    """Same weights, same views, dropout disabled: MultiModalDINOLightning.training_step == DinoStepEngine loss / gradients."""
+    from multimodal_ssl_avmnist_b200.engine import DinoStepEngine
+    torch.manual_seed(1)
+    kw = dict(KW, dropout=0.0)
+    lit = md.MultiModalDINOLightning(**kw).to(DEV)
+    B = 8
+    views = _batch("default", B, 50)
+    loss = lit.training_step(views, 0)
+    loss.backward()
+    meng = lit.model.engine
+    eng = DinoStepEngine(kind="multi_central", device=DEV, dropout=0.0, fusion_dropout=meng.fusion_dropout, seed=meng.seed,
+                         precision=meng.precision)
+    # the module ran update_teacher() already; copy the PRE-step weights: student is unchanged by training_step
+    eng.student.flat.copy_(meng.student.flat)
+    eng.sync_teacher()
+    gi, ga, li, la = views
+    xi = torch.cat([gi, li], 1).permute(1, 0, 2, 3, 4)[:, :, 0].contiguous()
+    xa = torch.cat([ga, la], 1).permute(1, 0, 2, 3, 4)[:, :, 0].contiguous()
+    eng.rng_step = 0
+    if meng.fusion_dropout == 0:
+        l2 = eng.forward_backward(xi, xa)
+        torch.cuda.synchronize()
+        assert abs(float(loss) - float(l2[0])) < 1e-5 * abs(float(l2[0]))
+        n = eng.n_trainable_prefix
+        assert float((eng.grad[:n] - meng.grad[:n]).abs().max()) <= 1e-6 * float(eng.grad[:n].abs().max()) + 1e-12
+    else:       # fusion dropout is active in student and teacher (reference semantics): same Philox stream -> same masks
+        l2 = eng.forward_backward(xi, xa)
+        torch.cuda.synchronize()
+        assert abs(float(loss) - float(l2[0])) < 1e-5 * abs(float(l2[0]))
+
+
+def test_unimodal_training_step():
+    torch.manual_seed(2)
+    lit = md.UniModalDINOLightning(encoder_class=md.ImageEncoder, data_dir="x/", dropout=0.3, learning_rate=1e-3, projection_dim=128,
+                                   output_dim=256, momentum=0.996, center_momentum=0.9, teacher_temperature=0.04, weight_decay=1e-6,
+                                   cosine_loss_alpha=0, num_epochs=10, data_augmentation="burst_noise").to(DEV)
+    opt = lit.configure_optimizers()["optimizer"]
+    for it in range(2):
+        opt.zero_grad(set_to_none=True)
+        loss = lit.training_step(_batch("default", 8, 70 + it), it)
+        loss.backward()
+        opt.step()
+    torch.cuda.synchronize()
+    assert 3.0 < float(loss) < 6.0
+
+
+def test_trainer_fit_on_synthetic_files(tmp_path):
+    """The run_dino.py flow in miniature: data module on synthetic files, Trainer(max_epochs) from the Lightning-surface
+    shim (or real Lightning when installed), CSV logger, checkpoint, reload."""
+    from _compat import pl, ModelCheckpoint, CSVLogger
+    d = str(tmp_path) + "/"
+    gd.write_synthetic_avmnist(d, n_train=64, n_test=16)
+    dm = gd.AVMNISTDinoDataModule(data_dir=d, batch_size=16, num_workers=0, type="burst_noise")
+    lit = md.MultiModalDINOLightning(**dict(KW, data_dir=d))
+    ckpt = ModelCheckpoint(dirpath=str(tmp_path), monitor="train_loss_epoch", mode="min")
+    tr = pl.Trainer(max_epochs=2, logger=CSVLogger(str(tmp_path), name="logs"), callbacks=[ckpt], log_every_n_steps=1, devices=1,
+                    accelerator="gpu")
+    tr.fit(lit, datamodule=dm)
+    assert tr.global_step >= 4 and "train_loss_epoch" in tr.callback_metrics
+    assert 3.0 < float(tr.callback_metrics["train_loss_epoch"]) < 6.0
+    assert os.path.exists(ckpt.best_model_path)
+    again = md.MultiModalDINOLightning.load_from_checkpoint(ckpt.best_model_path)
+    a, b = again.state_dict(), lit.state_dict()
+    assert set(a) == set(b) and all(a[k].shape == b[k].shape for k in a)
