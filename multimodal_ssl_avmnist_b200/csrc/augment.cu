@@ -76,6 +76,9 @@ __global__ void __launch_bounds__(T) aug_apply_kernel(const void* __restrict__ s
     AATable* ytab = xtab + S;
     __shared__ int32_t sops[B200_AUG_MAX_OPS * 8];
     __shared__ uint32_t sbits[B200_AUG_GROUP_WORDS];
+    __shared__ float u8lut[256];          // v / 255 exactly as the reference computes it (float64 division, rounded to fp32)
+    __shared__ float tw_alpha[S];         // time-warp per-column tables
+    __shared__ int tw_i0[S];
 
     const int tid = threadIdx.x;
     const int b = blockIdx.x / V, v = blockIdx.x - b * V;
@@ -85,13 +88,12 @@ __global__ void __launch_bounds__(T) aug_apply_kernel(const void* __restrict__ s
 
     // ---- stage the source (coalesced, vectorised) ----
     if (src_u8) {
+        for (int i = tid; i < 256; i += T) u8lut[i] = (float)((double)i / 255.0);
+        __syncthreads();
         const uint32_t* s4 = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(src) + (size_t)b * NPIX);
         for (int i = tid; i < NPIX / 4; i += T) {
-            uint32_t w = __ldg(s4 + i);
-            bufA[4 * i + 0] = __fdiv_rn((float)(w & 0xff), 255.0f);
-            bufA[4 * i + 1] = __fdiv_rn((float)((w >> 8) & 0xff), 255.0f);
-            bufA[4 * i + 2] = __fdiv_rn((float)((w >> 16) & 0xff), 255.0f);
-            bufA[4 * i + 3] = __fdiv_rn((float)(w >> 24), 255.0f);
+            const uint32_t w = __ldg(s4 + i);
+            reinterpret_cast<float4*>(bufA)[i] = make_float4(u8lut[w & 0xff], u8lut[(w >> 8) & 0xff], u8lut[(w >> 16) & 0xff], u8lut[w >> 24]);
         }
     } else {
         const float4* s4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + (size_t)b * NPIX);
@@ -148,8 +150,8 @@ __global__ void __launch_bounds__(T) aug_apply_kernel(const void* __restrict__ s
                 const float xs = (float)x + off, ys = (float)y + off;
                 const float gx = __fadd_rn(__fmaf_rn(ys, r10, __fmul_rn(xs, r00)), r20);
                 const float gy = __fadd_rn(__fmaf_rn(ys, r11, __fmul_rn(xs, r01)), r21);
-                const float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), (float)S), 1.0f), 2.0f);
-                const float iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), (float)S), 1.0f), 2.0f);
+                const float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), (float)S), 1.0f), 0.5f);     // x/2 == x*0.5 exactly
+                const float iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), (float)S), 1.0f), 0.5f);
                 const float fx = rintf(ix), fy = rintf(iy);
                 float val = 0.f;
                 if (fx >= 0.f && fx < (float)S && fy >= 0.f && fy < (float)S) val = cur[(int)fy * S + (int)fx];
@@ -208,13 +210,18 @@ __global__ void __launch_bounds__(T) aug_apply_kernel(const void* __restrict__ s
         } else if (kind == OP_TIME_WARP) {
             const double rate = __hiloint2double(p[1], p[0]);
             const int n_frames = (int)ceil((double)S / rate);
+            for (int kx = tid; kx < S; kx += T) {            // the interpolation position depends on the column only
+                const float ts = kx < n_frames ? arange_f32(kx, n_frames, rate) : 0.f;
+                tw_alpha[kx] = fmodf(ts, 1.0f);
+                tw_i0[kx] = kx < n_frames ? (int)ts : -1;
+            }
+            __syncthreads();
             for (int e = tid; e < NPIX; e += T) {
                 const int y = e / S, kx = e - y * S;
                 float val = 0.f;
-                if (kx < n_frames) {
-                    const float ts = arange_f32(kx, n_frames, rate);
-                    const float alpha = fmodf(ts, 1.0f);
-                    const int i0 = (int)ts;
+                const int i0 = tw_i0[kx];
+                if (i0 >= 0) {
+                    const float alpha = tw_alpha[kx];
                     const float n0 = i0 < S ? fabsf(cur[y * S + i0]) : 0.f;
                     const float n1 = (i0 + 1) < S ? fabsf(cur[y * S + i0 + 1]) : 0.f;
                     val = __fadd_rn(__fmul_rn(alpha, n1), __fmul_rn(__fsub_rn(1.0f, alpha), n0));
@@ -233,20 +240,30 @@ __global__ void __launch_bounds__(T) aug_apply_kernel(const void* __restrict__ s
     // ---- and / or the bf16 "shift8" image of the first-layer tensor-core convolution: [V,B,S,S+pad,8], unit (y, xs) =
     //      x[y][xs-pad .. xs-pad+7] (zero outside the row); see conv_tc.cu ----
     if (out8 != nullptr) {
-        const int WT = S + pad8;
+        const int WT = S + pad8, QW = (WT + 3) / 4;            // a thread writes 4 consecutive units of a row from 11 values
         uint4* o8 = out8 + ((size_t)v * B + b) * S * WT;
-        for (int i = tid; i < S * WT; i += T) {
-            const int y = i / WT, xs = i - y * WT;
+        for (int i = tid; i < S * QW; i += T) {
+            const int y = i / QW, xs = (i - y * QW) * 4;
             const float* r = cur + y * S;
-            uint32_t pk[4];
+            float f[11];
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                const int x0 = xs - pad8 + 2 * h, x1 = x0 + 1;
-                const float f0 = (x0 >= 0 && x0 < S) ? r[x0] : 0.f, f1 = (x1 >= 0 && x1 < S) ? r[x1] : 0.f;
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(f0, f1);
-                pk[h] = *reinterpret_cast<uint32_t*>(&t2);
+            for (int c = 0; c < 11; ++c) {
+                const int xc = xs - pad8 + c;
+                f[c] = (xc >= 0 && xc < S) ? r[xc] : 0.f;
             }
-            o8[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            uint32_t ev[5], od[5];                             // bf16 pairs starting at even / odd offsets
+#pragma unroll
+            for (int h = 0; h < 5; ++h) {
+                __nv_bfloat162 a2 = __floats2bfloat162_rn(f[2 * h], f[2 * h + 1]);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * h + 1], f[2 * h + 2]);
+                ev[h] = *reinterpret_cast<uint32_t*>(&a2);
+                od[h] = *reinterpret_cast<uint32_t*>(&b2);
+            }
+            uint4* dst = o8 + (size_t)y * WT + xs;
+            dst[0] = make_uint4(ev[0], ev[1], ev[2], ev[3]);
+            if (xs + 1 < WT) dst[1] = make_uint4(od[0], od[1], od[2], od[3]);
+            if (xs + 2 < WT) dst[2] = make_uint4(ev[1], ev[2], ev[3], ev[4]);
+            if (xs + 3 < WT) dst[3] = make_uint4(od[1], od[2], od[3], od[4]);
         }
     }
 }

@@ -18,6 +18,7 @@ so the teacher EMA is ONE flat kernel over the common prefix and Adam is one fla
 prefix (plus one over the mode heads); the unused CentralNet classifier heads (models/unimodal.py:121-125,
 179-183) are EMA'd and check-pointed like in the reference but never receive gradients.
 """
+import contextlib
 import math
 
 import numpy as np
@@ -215,6 +216,8 @@ class DinoStepEngine:
                         self._tcw[(role, mod, li)] = torch.empty(ops.conv_tc_weight_bytes(ci, co, k), dtype=torch.uint8, device=self.device)
                     if ci > 1:
                         self._tcw[("flip", mod, li)] = torch.empty(ops.conv_tc_weight_bytes(co, ci, k), dtype=torch.uint8, device=self.device)
+        self.overlap_teacher = True
+        self._side_stream = torch.cuda.Stream(device=self.device)
         self._ws = {}
         self._init_parameters()
         self.set_augmentation(augment_values)
@@ -281,8 +284,7 @@ class DinoStepEngine:
         w["x_img"] = e(Ns, 1, 28, 28)
         if self.aud_layers:
             w["x_aud"] = e(Ns, 1, 112, 112)
-        wg_work = 0
-        zmax = pmax = z8max = 0
+        scr = {m: dict(wg=0, z=0, p=0, z8=0) for m in ("img", "aud")}       # backward scratch sizes per modality stack
         BF = torch.bfloat16
         for role, N in (("s", Ns), ("t", Nt)):
             for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers)):
@@ -306,18 +308,22 @@ class DinoStepEngine:
                         w[f"{role}.{mod}.{nm}{li}"] = e(nv, co)
                     if role == "s":
                         w[f"s.{mod}.sums{li}"] = torch.zeros(nv, co, 2, dtype=torch.float64, device=dev)
+                        sc = scr[mod]
                         if tc:
-                            wg_work = max(wg_work, ops.conv_tc_wgrad_work_floats(N, ci, co, hw, hw, k, pad))
-                            z8max = max(z8max, N * co * ho * ho)
+                            sc["wg"] = max(sc["wg"], ops.conv_tc_wgrad_work_floats(N, ci, co, hw, hw, k, pad))
+                            sc["z8"] = max(sc["z8"], N * co * ho * ho)
                         else:
-                            wg_work = max(wg_work, ops.conv_bwd_weight_work_floats(N, ci, co, hw, hw, k, pad))
-                            zmax = max(zmax, N * co * ho * ho)
-                        pmax = max(pmax, N * co * (ho // 2) * (ho // 2), N * ci * hw * hw if li > 0 else 0)
-        w["dz"] = e(max(zmax, 4))
-        w["dz8"] = e(max(z8max, 8), dtype=BF)
-        w["dbsum"] = torch.zeros(8, 128, dtype=torch.float64, device=dev)
-        w["dp_a"], w["dp_b"] = e(pmax), e(pmax)
-        w["wg_work"] = e(max(wg_work, 4))
+                            sc["wg"] = max(sc["wg"], ops.conv_bwd_weight_work_floats(N, ci, co, hw, hw, k, pad))
+                            sc["z"] = max(sc["z"], N * co * ho * ho)
+                        sc["p"] = max(sc["p"], N * co * (ho // 2) * (ho // 2), N * ci * hw * hw if li > 0 else 0)
+        for m, sc in scr.items():           # one scratch set per stack: the two stacks' backward passes run on different streams
+            if sc["p"] == 0:
+                continue
+            w[f"{m}.dz"] = e(max(sc["z"], 4))
+            w[f"{m}.dz8"] = e(max(sc["z8"], 8), dtype=BF)
+            w[f"{m}.dbsum"] = torch.zeros(8, 128, dtype=torch.float64, device=dev)
+            w[f"{m}.dp_a"], w[f"{m}.dp_b"] = e(sc["p"]), e(sc["p"])
+            w[f"{m}.wg_work"] = e(max(sc["wg"], 4))
         E, O, P = self.E, self.O, self.P
         Nv = V * B
         if self.kind == "multi_central":
@@ -499,7 +505,7 @@ class DinoStepEngine:
         d_p = d_top
         BF = torch.bfloat16
         if any(self.tc[mod]):
-            w["dbsum"].zero_()
+            w[f"{mod}.dbsum"].zero_()
         for li in range(len(layers) - 1, -1, -1):
             conv, bn, ci, co, hw, k, pad = layers[li]
             ho = hw + 2 * pad - k + 1
@@ -511,24 +517,24 @@ class DinoStepEngine:
             if tc:
                 if d_p.dtype != BF:
                     d_p = d_p.view(N, co, ho // 2, ho // 2)
-                dz = w["dz8"][:z.numel()].view_as(z)
+                dz = w[f"{mod}.dz8"][:z.numel()].view_as(z)
                 p_out = w[f"s.{mod}.p8{li}"] if f"s.{mod}.p8{li}" in w else w[f"s.{mod}.p{li}"]
                 ops.bn_pool8_bwd_reduce_p(p_out, d_p, S["enc." + bn + ".weight"], S["enc." + bn + ".bias"], sums, B)
-                ops.bn_relu_pool8_bwd_apply(z, d_p, sc, sh, mu, inv, sums, dz, B, dbsum=w["dbsum"][li])
-                ops.bias_grad_finalize(w["dbsum"][li], G["enc." + conv + ".bias"])
+                ops.bn_relu_pool8_bwd_apply(z, d_p, sc, sh, mu, inv, sums, dz, B, dbsum=w[f"{mod}.dbsum"][li])
+                ops.bias_grad_finalize(w[f"{mod}.dbsum"][li], G["enc." + conv + ".bias"])
             else:
-                dz = w["dz"][:z.numel()].view_as(z)
+                dz = w[f"{mod}.dz"][:z.numel()].view_as(z)
                 ops.bn_relu_pool_bwd_reduce(z, d_p, sc, sh, mu, inv, sums, B)
                 ops.bn_relu_pool_bwd_apply(z, d_p, sc, sh, mu, inv, sums, dz, B)
             ops.bn_param_grads(sums, G["enc." + bn + ".weight"], G["enc." + bn + ".bias"], N // B)
             if tc:
                 xin8 = w[f"{mod}.xs8"] if ci == 1 else w[f"s.{mod}.p8{li - 1}"]
-                ops.conv_tc_wgrad(xin8, dz, G["enc." + conv + ".weight"], w["wg_work"], pad)
+                ops.conv_tc_wgrad(xin8, dz, G["enc." + conv + ".weight"], w[f"{mod}.wg_work"], pad)
             else:
                 xin = x if li == 0 else w[f"s.{mod}.p{li - 1}"]
-                ops.conv_bwd_weight(xin.view(N, ci, hw, hw), dz, G["enc." + conv + ".weight"], G["enc." + conv + ".bias"], w["wg_work"], pad)
+                ops.conv_bwd_weight(xin.view(N, ci, hw, hw), dz, G["enc." + conv + ".weight"], G["enc." + conv + ".bias"], w[f"{mod}.wg_work"], pad)
             if li > 0:
-                nxt = w["dp_a"] if d_p.data_ptr() != w["dp_a"].data_ptr() else w["dp_b"]
+                nxt = w[f"{mod}.dp_a"] if d_p.data_ptr() != w[f"{mod}.dp_a"].data_ptr() else w[f"{mod}.dp_b"]
                 if tc:
                     if self.tc[mod][li - 1]:          # the consumer is an act8 layer: bf16 act8 gradient
                         d_in = nxt.view(BF)[:N * ci * hw * hw].view(N, ci // 8, hw, hw, 8)
@@ -586,10 +592,29 @@ class DinoStepEngine:
         if self._tcw:
             self._prep_tc_weights("s", S)
             self._prep_tc_weights("t", T)
+        # first-layer operand images for both roles (the teacher reads a prefix of the student's)
+        if not packed:
+            for mod, layers, x in (("img", self.img_layers, xi), ("aud", self.aud_layers, xa)):
+                if layers and self.tc[mod][0]:
+                    hw, pad = layers[0][4], layers[0][6]
+                    ops.pack_shift8(x.view(Ns, hw, hw), w[f"{mod}.xs8"], pad)
+            w["packed"] = True
+        # the teacher forward is independent of the student forward: it runs on a side stream so that its CTAs fill the SMs the
+        # student's thin kernels leave idle (separate activation buffers; joined before the loss)
+        main = torch.cuda.current_stream()
+        side = self._side_stream if self.overlap_teacher else None
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                feat_t = self._encode(w, "t", T, self.bn_t, xi[:Nt], xa[:Nt] if multi else None, Nt, B, Nt, w.get("t.fmask"))
+                self._head_fwd(w, "t", "head.", T, self.bn_t["head.mlp.1"], feat_t, w["t.proj"], w["t.hh"], w["t.g"], None, 0.0)
         feat_s = self._encode(w, "s", S, self.bn_s, xi, xa, Ns, B, Nv, w.get("s.fmask"))
-        feat_t = self._encode(w, "t", T, self.bn_t, xi[:Nt], xa[:Nt] if multi else None, Nt, B, Nt, w.get("t.fmask"))
         self._head_fwd(w, "s", "head.", S, self.bn_s["head.mlp.1"], feat_s, w["s.proj"], w["s.hh"], w["s.g"], w["s.hmask"], self.dropout)
-        self._head_fwd(w, "t", "head.", T, self.bn_t["head.mlp.1"], feat_t, w["t.proj"], w["t.hh"], w["t.g"], None, 0.0)
+        if side is not None:
+            main.wait_stream(side)
+        else:
+            feat_t = self._encode(w, "t", T, self.bn_t, xi[:Nt], xa[:Nt] if multi else None, Nt, B, Nt, w.get("t.fmask"))
+            self._head_fwd(w, "t", "head.", T, self.bn_t["head.mlp.1"], feat_t, w["t.proj"], w["t.hh"], w["t.g"], None, 0.0)
         if self.mode != "default":
             cat = w["s.cat"]
             for m, sl in (("aux_image", slice(0, E)), ("aux_audio", slice(E, 2 * E))):
@@ -657,19 +682,28 @@ class DinoStepEngine:
                     d_out = w[f"{m}.d.out"] if d_aux is None else d_aux[i]
                     self._head_bwd(w, m, m + ".", w["s.cat"][Nv:, sl], d_out, w[f"{m}.hh"], w[f"{m}.g"], w[f"{m}.d.g"],
                                    w[f"{m}.d.hh"], d_cat[Nv:, sl], None, 0.0)
+            # the image and the audio stacks are independent from here on: the (small) image stack runs on the side stream
+            main = torch.cuda.current_stream()
+            side = self._side_stream if self.overlap_teacher else None
             for mod, layers, sl, nflat, lin, x in (("img", self.img_layers, slice(0, E), 1600, "enc.image_encoder.1", xi),
                                                    ("aud", self.aud_layers, slice(E, 2 * E), 3136, "enc.audio_encoder.1", xa)):
-                p_last = w[f"s.{mod}.p{len(layers) - 1}"].view(Ns, nflat)
-                ops.linear_bwd_weight(d_cat[:, sl], p_last, G[lin + ".weight"], G[lin + ".bias"], tc=self.lin_tc)
-                d_p = w["dp_a"][:Ns * nflat].view(Ns, nflat)
-                ops.linear_bwd_data(d_cat[:, sl], S[lin + ".weight"], d_p, tc=self.lin_tc)
-                self._conv_stack_bwd(w, mod, layers, x, d_p, Ns, B)
+                ctx = torch.cuda.stream(side) if (side is not None and mod == "img") else contextlib.nullcontext()
+                if side is not None and mod == "img":
+                    side.wait_stream(main)
+                with ctx:
+                    p_last = w[f"s.{mod}.p{len(layers) - 1}"].view(Ns, nflat)
+                    ops.linear_bwd_weight(d_cat[:, sl], p_last, G[lin + ".weight"], G[lin + ".bias"], tc=self.lin_tc)
+                    d_p = w[f"{mod}.dp_a"][:Ns * nflat].view(Ns, nflat)
+                    ops.linear_bwd_data(d_cat[:, sl], S[lin + ".weight"], d_p, tc=self.lin_tc)
+                    self._conv_stack_bwd(w, mod, layers, x, d_p, Ns, B)
+            if side is not None:
+                main.wait_stream(side)
         else:
             ops.linear_bwd_weight(d_feat, w["s.e14"], G["enc.projection.0.weight"], G["enc.projection.0.bias"], tc=self.lin_tc)
             ops.linear_bwd_data(d_feat, S["enc.projection.0.weight"], w["d.e14"], tc=self.lin_tc)
             ops.linear_bwd_weight(w["d.e14"], w["s.pool"], G["enc.encoder.14.weight"], G["enc.encoder.14.bias"], tc=self.lin_tc)
             ops.linear_bwd_data(w["d.e14"], S["enc.encoder.14.weight"], w["d.pool"], tc=self.lin_tc)
-            d_p = w["dp_a"][:Ns * 128 * 9].view(Ns, 128, 3, 3)
+            d_p = w["img.dp_a"][:Ns * 128 * 9].view(Ns, 128, 3, 3)
             ops.avgpool_bwd(w["d.pool"], d_p)
             self._conv_stack_bwd(w, "img", self.img_layers, xi, d_p, Ns, B)
         if self.world > 1:

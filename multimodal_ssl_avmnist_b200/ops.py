@@ -375,9 +375,10 @@ _LINEAR_WORK = {}
 
 
 def _linear_work(device, need):
-    work = _LINEAR_WORK.get(device)         # one cached scratch per device, grown on demand
+    key = (device, _stream())               # one cached scratch per device AND stream (concurrent streams must not share it)
+    work = _LINEAR_WORK.get(key)
     if work is None or work.numel() < need:
-        work = _LINEAR_WORK[device] = torch.empty(max(need, 4), dtype=F32, device=device)
+        work = _LINEAR_WORK[key] = torch.empty(max(need, 4), dtype=F32, device=device)
     return work
 
 
