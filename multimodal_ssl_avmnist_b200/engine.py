@@ -218,6 +218,7 @@ class DinoStepEngine:
                         self._tcw[("flip", mod, li)] = torch.empty(ops.conv_tc_weight_bytes(co, ci, k), dtype=torch.uint8, device=self.device)
         self.overlap_teacher = True
         self._side_stream = torch.cuda.Stream(device=self.device)
+        self._side_stream2 = torch.cuda.Stream(device=self.device)
         self._ws = {}
         self._init_parameters()
         self.set_augmentation(augment_values)
@@ -485,9 +486,17 @@ class DinoStepEngine:
         if self.kind == "multi_central":
             E = self.E
             cat = w[f"{role}.cat"]
-            pi = self._conv_stack(w, role, "img", self.img_layers, x_img, N, B, P, bns)
-            ops.linear_fwd(pi.view(N, 1600), P["enc.image_encoder.1.weight"], P["enc.image_encoder.1.bias"], cat[:, :E], tc=self.lin_tc)
+            # the student's image stack runs beside its audio stack on a second side stream (independent until the fusion MLP)
+            main = torch.cuda.current_stream()
+            side = self._side_stream2 if (self.overlap_teacher and role == "s") else None
+            if side is not None:
+                side.wait_stream(main)
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                pi = self._conv_stack(w, role, "img", self.img_layers, x_img, N, B, P, bns)
+                ops.linear_fwd(pi.view(N, 1600), P["enc.image_encoder.1.weight"], P["enc.image_encoder.1.bias"], cat[:, :E], tc=self.lin_tc)
             pa = self._conv_stack(w, role, "aud", self.aud_layers, x_aud, N, B, P, bns)
+            if side is not None:
+                main.wait_stream(side)
             ops.linear_fwd(pa.view(N, 3136), P["enc.audio_encoder.1.weight"], P["enc.audio_encoder.1.bias"], cat[:, E:], tc=self.lin_tc)
             h1, feat = w[f"{role}.h1"], w[f"{role}.feat"]
             ops.linear_fwd(cat[:n_fusion], P["enc.fusion.0.weight"], P["enc.fusion.0.bias"], h1, act=2, mask=fmask, drop_p=self.fusion_dropout, tc=self.lin_tc)
