@@ -219,6 +219,7 @@ class DinoStepEngine:
         self.overlap_teacher = True
         self._side_stream = torch.cuda.Stream(device=self.device)
         self._side_stream2 = torch.cuda.Stream(device=self.device)
+        self._wgrad_streams = {m: torch.cuda.Stream(device=self.device) for m in ("img", "aud")}
         self._ws = {}
         self._init_parameters()
         self.set_augmentation(augment_values)
@@ -322,9 +323,11 @@ class DinoStepEngine:
                 continue
             w[f"{m}.dz"] = e(max(sc["z"], 4))
             w[f"{m}.dz8"] = e(max(sc["z8"], 8), dtype=BF)
+            w[f"{m}.dz8b"] = e(max(sc["z8"], 8), dtype=BF)      # second buffer: the weight gradient of layer l overlaps layer l-1
             w[f"{m}.dbsum"] = torch.zeros(8, 128, dtype=torch.float64, device=dev)
             w[f"{m}.dp_a"], w[f"{m}.dp_b"] = e(sc["p"]), e(sc["p"])
             w[f"{m}.wg_work"] = e(max(sc["wg"], 4))
+            w[f"{m}.wg_work_b"] = e(max(sc["wg"], 4))
         E, O, P = self.E, self.O, self.P
         Nv = V * B
         if self.kind == "multi_central":
@@ -515,6 +518,11 @@ class DinoStepEngine:
         BF = torch.bfloat16
         if any(self.tc[mod]):
             w[f"{mod}.dbsum"].zero_()
+        # weight gradients (UMMA-issue bound, little HBM traffic) run on their own stream beside the data gradient and the next
+        # layer's HBM-bound BatchNorm kernels; dz and the wgrad scratch are double-buffered, an event guards their reuse
+        main = torch.cuda.current_stream()
+        wside = self._wgrad_streams[mod] if self.overlap_teacher else None
+        busy = {}                                               # buffer parity -> event of the wgrad that still reads it
         for li in range(len(layers) - 1, -1, -1):
             conv, bn, ci, co, hw, k, pad = layers[li]
             ho = hw + 2 * pad - k + 1
@@ -526,7 +534,10 @@ class DinoStepEngine:
             if tc:
                 if d_p.dtype != BF:
                     d_p = d_p.view(N, co, ho // 2, ho // 2)
-                dz = w[f"{mod}.dz8"][:z.numel()].view_as(z)
+                par = li & 1
+                if par in busy:
+                    main.wait_event(busy.pop(par))
+                dz = w[f"{mod}.dz8" if par == 0 else f"{mod}.dz8b"][:z.numel()].view_as(z)
                 p_out = w[f"s.{mod}.p8{li}"] if f"s.{mod}.p8{li}" in w else w[f"s.{mod}.p{li}"]
                 ops.bn_pool8_bwd_reduce_p(p_out, d_p, S["enc." + bn + ".weight"], S["enc." + bn + ".bias"], sums, B)
                 ops.bn_relu_pool8_bwd_apply(z, d_p, sc, sh, mu, inv, sums, dz, B, dbsum=w[f"{mod}.dbsum"][li])
@@ -538,7 +549,16 @@ class DinoStepEngine:
             ops.bn_param_grads(sums, G["enc." + bn + ".weight"], G["enc." + bn + ".bias"], N // B)
             if tc:
                 xin8 = w[f"{mod}.xs8"] if ci == 1 else w[f"s.{mod}.p8{li - 1}"]
-                ops.conv_tc_wgrad(xin8, dz, G["enc." + conv + ".weight"], w[f"{mod}.wg_work"], pad)
+                wk = w[f"{mod}.wg_work" if (li & 1) == 0 else f"{mod}.wg_work_b"]
+                if wside is not None:
+                    wside.wait_stream(main)
+                    with torch.cuda.stream(wside):
+                        ops.conv_tc_wgrad(xin8, dz, G["enc." + conv + ".weight"], wk, pad)
+                        ev = torch.cuda.Event()
+                        ev.record(wside)
+                    busy[li & 1] = ev
+                else:
+                    ops.conv_tc_wgrad(xin8, dz, G["enc." + conv + ".weight"], wk, pad)
             else:
                 xin = x if li == 0 else w[f"s.{mod}.p{li - 1}"]
                 ops.conv_bwd_weight(xin.view(N, ci, hw, hw), dz, G["enc." + conv + ".weight"], G["enc." + conv + ".bias"], w[f"{mod}.wg_work"], pad)
@@ -554,6 +574,8 @@ class DinoStepEngine:
                     d_in = nxt[:N * ci * hw * hw].view(N, ci, hw, hw)
                     ops.conv_bwd_data(dz, S["enc." + conv + ".weight"], d_in, pad)
                 d_p = d_in
+        if wside is not None:
+            main.wait_stream(wside)
 
     # ------------------------------------------------------------------------------------------------------
     # the step
