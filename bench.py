@@ -283,6 +283,7 @@ def run_ours(args):
     # ---- warm-up (also sizes the workspaces) ----
     for _ in range(max(args.warmup, 3)):
         eng.train_step(img_d, aud_d, lab_d)
+        eng.prefetch_augment(img_d, aud_d)
     barrier()
     # ---- timed region 1: inputs resident in HBM ----
     clocks = ClockSampler(local) if rank == 0 else None
@@ -292,19 +293,22 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         loss = eng.train_step(img_d, aud_d, lab_d)
+        eng.prefetch_augment(img_d, aud_d)      # the next step's views, on the augmentation stream (input pipeline overlap)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
     launches = (ops.launch_count() - l0) // args.steps
-    # ---- timed region 2: end to end through the host-facing call (pinned host buffers in, loss out) ----
+    # ---- timed region 2: end to end through the host-facing call (pinned host buffers in, loss out); every step copies its
+    #      batch host->device and reads its loss back; the NEXT batch's copy + augmentation are enqueued before the read-back ----
+    nxt = (img_h, aud_h) + ((lab_h,) if lab_h is not None else ())
     for _ in range(2):
-        eng.train_step_host(img_h, aud_h, lab_h)
+        eng.train_step_host(img_h, aud_h, lab_h, next_batch=nxt)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     last = None
     for _ in range(args.steps):
-        last = eng.train_step_host(img_h, aud_h, lab_h)
+        last = eng.train_step_host(img_h, aud_h, lab_h, next_batch=nxt)
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3) / args.steps

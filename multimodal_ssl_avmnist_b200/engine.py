@@ -220,6 +220,8 @@ class DinoStepEngine:
         self._side_stream = torch.cuda.Stream(device=self.device)
         self._side_stream2 = torch.cuda.Stream(device=self.device)
         self._wgrad_streams = {m: torch.cuda.Stream(device=self.device) for m in ("img", "aud")}
+        self._aug_stream = torch.cuda.Stream(device=self.device)
+        self._prefetch, self._step_done, self._step_done_prev = None, None, None
         self._ws = {}
         self._init_parameters()
         self.set_augmentation(augment_values)
@@ -283,6 +285,8 @@ class DinoStepEngine:
         w["img_ops"] = torch.zeros(B, V, A.MAX_OPS, A.OP_WORDS, dtype=torch.int32, device=dev)
         w["aud_ops"] = torch.zeros(B, V, A.MAX_OPS, A.OP_WORDS, dtype=torch.int32, device=dev)
         w["group_bits"] = torch.zeros(B, V, A.GROUP_WORDS, dtype=torch.int32, device=dev)
+        for nm in ("img_ops", "aud_ops", "group_bits"):
+            w[nm + "_b"] = torch.zeros_like(w[nm])
         w["x_img"] = e(Ns, 1, 28, 28)
         if self.aud_layers:
             w["x_aud"] = e(Ns, 1, 112, 112)
@@ -297,6 +301,7 @@ class DinoStepEngine:
                     next_tc = li + 1 < len(layers) and self.tc[mod][li + 1]
                     if tc and ci == 1 and role == "s":
                         w[f"{mod}.xs8"] = e(N, hw, hw + pad, 8, dtype=BF)       # first-layer input, shift8 (shared by the teacher)
+                        w[f"{mod}.xs8_b"] = e(N, hw, hw + pad, 8, dtype=BF)     # ... and the slot the next step's views are prefetched into
                     if tc:
                         w[f"{role}.{mod}.z{li}"] = e(N, co // 8, ho, ho, 8, dtype=torch.float16)   # act8 layout, fp16: never an MMA operand
                     else:
@@ -379,6 +384,48 @@ class DinoStepEngine:
     # ------------------------------------------------------------------------------------------------------
     # augmentation
     # ------------------------------------------------------------------------------------------------------
+    def prefetch_augment(self, images, audios):
+        """Enqueue the NEXT step's sampling + augmentation on the augmentation stream, into the spare first-layer buffers, so
+        that it overlaps the tail of the current step (its last weight gradient, EMA, Adam).  The next train_step() on the
+        same tensors picks the views up instead of augmenting again.  Tensor-core path only; a no-op otherwise."""
+        if not (self.tc["img"][0] and (not self.aud_layers or self.tc["aud"][0])):
+            return False
+        B = images.shape[0]
+        w = self._workspace(B)
+        main, st = torch.cuda.current_stream(), self._aug_stream
+        if self._step_done_prev is not None:
+            st.wait_event(self._step_done_prev)       # the spare slot was last read by the step BEFORE the one in flight
+        with torch.cuda.stream(st):
+            ops.aug_sample(self.aug_spec, B, self.Vg, self.Vl, self.seed, self.rng_step, w["img_ops_b"], w["aud_ops_b"], w["group_bits_b"])
+            seed = (self.seed * 1000003 + self.rng_step) & 0xFFFFFFFFFFFF
+            V = self.V
+            pi = self.img_layers[0][6]
+            ops.aug_apply_image(images.reshape(B, 28, 28), w["img_ops_b"], None, out8=w["img.xs8_b"][:V * B].view(V, B, 28, 28 + pi, 8), pad=pi)
+            if self.aud_layers and audios is not None:
+                pa = self.aud_layers[0][6]
+                ops.aug_apply_audio(audios.reshape(B, 112, 112), w["aud_ops_b"], w["group_bits_b"], None, seed=seed,
+                                    out8=w["aud.xs8_b"][:V * B].view(V, B, 112, 112 + pa, 8), pad=pa)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        self._prefetch = {"key": (images.data_ptr(), None if audios is None else audios.data_ptr(), B, self.rng_step), "event": ev}
+        return True
+
+    def _take_prefetched(self, images, audios):
+        """If the views of this batch were prefetched for this rng position: swap the buffer slots and return them."""
+        pf, self._prefetch = self._prefetch, None
+        B = images.shape[0]
+        if pf is None or pf["key"] != (images.data_ptr(), None if audios is None else audios.data_ptr(), B, self.rng_step):
+            return None
+        w = self._workspace(B)
+        torch.cuda.current_stream().wait_event(pf["event"])
+        for nm in ("img.xs8", "aud.xs8", "img_ops", "aud_ops", "group_bits"):
+            if nm in w:
+                w[nm], w[nm + "_b"] = w[nm + "_b"], w[nm]
+        V = self.V
+        xi = w["img.xs8"][:V * B].view(V, B, 28, 28 + self.img_layers[0][6], 8)
+        xa = w["aud.xs8"][:V * B].view(V, B, 112, 112 + self.aud_layers[0][6], 8) if self.aud_layers else None
+        return xi, xa
+
     def augment(self, images, audios, B=None, direct=False):
         """Device-sampled multi-crop views of a raw batch: images [B,28,28] (fp32 in [0,1] or uint8),
         audios [B,112,112] (uint8 or fp32).  Returns view-major tensors ([V,B,28,28], [V,B,112,112])."""
@@ -789,29 +836,57 @@ class DinoStepEngine:
     def train_step(self, images, audios=None, labels=None):
         """Whole step from a raw device batch: images [B,28,28] fp32 in [0,1] or uint8; audios [B,112,112] uint8 (or fp32);
         labels int64 [B] (semi_supervised).  Returns the device loss tensor [4] (dino, aux, cosine, total)."""
-        xi, xa = self.augment(images, audios, direct=True)
+        got = self._take_prefetched(images, audios)
+        xi, xa = got if got is not None else self.augment(images, audios, direct=True)
         raw = None
         if self.mode != "default":
             img_f = images.float() / 255.0 if images.dtype == torch.uint8 else images
             aud_f = audios.float() / 255.0 if audios.dtype == torch.uint8 else audios
             raw = (img_f, aud_f)
-        return self.train_step_views(xi, xa, raw=raw, labels=labels)
+        loss = self.train_step_views(xi, xa, raw=raw, labels=labels)
+        self._step_done_prev, self._step_done = self._step_done, torch.cuda.Event()
+        self._step_done.record()
+        return loss
 
-    def train_step_host(self, images_host, audios_host=None, labels_host=None):
+    def train_step_host(self, images_host, audios_host=None, labels_host=None, next_batch=None):
         """The host-facing call: raw batch in (pinned) host memory -> H2D copies -> whole step -> the total loss as a Python
-        float (D2H read).  This is what `e2e` in bench.py times."""
+        float (D2H read).  This is what `e2e` in bench.py times.  next_batch = (images_host, audios_host[, labels_host]) of
+        the FOLLOWING call, if known: its H2D copy and augmentation are enqueued on the augmentation stream before this
+        step's loss is read back, so the input pipeline overlaps the step (what the reference's DataLoader workers do)."""
         B = images_host.shape[0]
         buf = self._ws.setdefault(("host", B, images_host.dtype, None if audios_host is None else audios_host.dtype), {})
         if not buf:
-            buf["img"] = torch.empty(images_host.shape, dtype=images_host.dtype, device=self.device)
+            for tag in ("", "_b"):
+                buf["img" + tag] = torch.empty(images_host.shape, dtype=images_host.dtype, device=self.device)
+                if audios_host is not None:
+                    buf["aud" + tag] = torch.empty(audios_host.shape, dtype=audios_host.dtype, device=self.device)
+                if labels_host is not None:
+                    buf["lab" + tag] = torch.empty(labels_host.shape, dtype=labels_host.dtype, device=self.device)
+            buf["staged"] = None
+        if buf["staged"] is not None and buf["staged"] == (images_host.data_ptr(), None if audios_host is None else audios_host.data_ptr()):
+            for k in ("img", "aud", "lab"):                       # this batch was staged by the previous call: swap the slots
+                if k in buf:
+                    buf[k], buf[k + "_b"] = buf[k + "_b"], buf[k]
+        else:
+            self._prefetch = None
+            buf["img"].copy_(images_host, non_blocking=True)
             if audios_host is not None:
-                buf["aud"] = torch.empty(audios_host.shape, dtype=audios_host.dtype, device=self.device)
+                buf["aud"].copy_(audios_host, non_blocking=True)
             if labels_host is not None:
-                buf["lab"] = torch.empty(labels_host.shape, dtype=labels_host.dtype, device=self.device)
-        buf["img"].copy_(images_host, non_blocking=True)
-        if audios_host is not None:
-            buf["aud"].copy_(audios_host, non_blocking=True)
-        if labels_host is not None:
-            buf["lab"].copy_(labels_host, non_blocking=True)
+                buf["lab"].copy_(labels_host, non_blocking=True)
+        buf["staged"] = None
         loss = self.train_step(buf["img"], buf.get("aud"), buf.get("lab"))
+        if next_batch is not None:
+            nimg, naud = next_batch[0], (next_batch[1] if len(next_batch) > 1 else None)
+            nlab = next_batch[2] if len(next_batch) > 2 else None
+            with torch.cuda.stream(self._aug_stream):
+                if self._step_done_prev is not None:
+                    self._aug_stream.wait_event(self._step_done_prev)      # the spare raw buffers were last read one step back
+                buf["img_b"].copy_(nimg, non_blocking=True)
+                if naud is not None:
+                    buf["aud_b"].copy_(naud, non_blocking=True)
+                if nlab is not None:
+                    buf["lab_b"].copy_(nlab, non_blocking=True)
+            if self.prefetch_augment(buf["img_b"], buf.get("aud_b")):
+                buf["staged"] = (nimg.data_ptr(), None if naud is None else naud.data_ptr())
         return float(loss[3].item())

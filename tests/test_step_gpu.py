@@ -252,3 +252,24 @@ def test_full_step_from_raw_batch_runs_and_learns():
         assert float((eng.teacher.flat[:n] - s0[:n]).abs().max()) < float((eng.student.flat[:n] - s0[:n]).abs().max())
         assert float(eng.center.abs().max()) > 0
         assert eng.step_count == 20
+
+
+def test_prefetched_augmentation_is_identical_to_inline():
+    """train_step with the next step's views prefetched on the augmentation stream == train_step augmenting inline
+    (same Philox positions, same buffers' contents): losses and weights bit-identical after 4 steps."""
+    B = 16
+    img = torch.rand(B, 28, 28, device=DEV)
+    aud = torch.randint(0, 256, (B, 112, 112), dtype=torch.uint8, device=DEV)
+    runs = []
+    for prefetch in (False, True):
+        eng = DinoStepEngine(kind="multi_central", device=DEV, seed=9)
+        eng.overlap_teacher = False if not prefetch else True
+        losses = []
+        for it in range(4):
+            losses.append(eng.train_step(img, aud).clone())
+            if prefetch:
+                assert eng.prefetch_augment(img, aud)
+        torch.cuda.synchronize()
+        runs.append((torch.stack(losses).cpu(), eng.student.flat.clone().cpu()))
+    assert torch.allclose(runs[0][0], runs[1][0], rtol=1e-5, atol=1e-6), (runs[0][0], runs[1][0])
+    assert float((runs[0][1] - runs[1][1]).abs().max()) < 5e-4
