@@ -223,15 +223,33 @@ def op_cost(name, meta):
     return 0.0, 0.0
 
 
+def ncu_traffic(row, B):
+    """dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
+    (profiles/ncu_traffic.json, taken at per-GPU batch 1024; scaled linearly to B), or None if it was not captured."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        return None
+    ints = [s_ for s_ in row["shapes"] if s_ and s_[0] == "i"]
+    key = row["op"] + ":" + "x".join(str(v) for v in row["shapes"][0]) + (":" + "x".join(str(v) for v in ints[0][1:]) if ints else "")
+    ent = table.get("launches", {}).get(key)
+    if ent is None:
+        return None
+    return ent["dram_bytes"] * B / table.get("per_gpu_batch", 1024)
+
+
 def profile_ops(engine, images, audios, steps=2, labels=None):
     """Per-op CUDA-event timing of `steps` whole steps (events on the launching stream)."""
     import torch
     from multimodal_ssl_avmnist_b200 import ops
+    overlap, engine.overlap_teacher = engine.overlap_teacher, False      # per-kernel times: no concurrent streams while profiling
+    torch.cuda.synchronize()
     rec = ops.start_profile()
     for _ in range(steps):
         engine.train_step(images, audios, labels)
     torch.cuda.synchronize()
     ops.stop_profile()
+    engine.overlap_teacher = overlap
     agg = {}
     for name, a, b, meta in rec:
         ms = a.elapsed_time(b)
@@ -326,7 +344,12 @@ def run_ours(args):
     step_ms_prof = sum(r["ms_per_step"] for r in rows)
     # dominant kernel = the op launch with the largest share of the step (algorithmic flops / bytes from op_cost)
     costed = [r for r in rows if r["flops"] > 0 or r["bytes"] > 0]
-    top = max(costed, key=lambda r: r["ms_per_step"])
+    # dominant kernel = the largest launch of the kernel family with the largest share of the step
+    fam = {}
+    for r in costed:
+        fam[r["op"]] = fam.get(r["op"], 0.0) + r["ms_per_step"]
+    top_op = max(fam, key=fam.get)
+    top = max((r for r in costed if r["op"] == top_op), key=lambda r: r["ms_per_step"])
     shapes = [s_ for s_ in top["shapes"] if not (s_ and s_[0] == "i")][:3]
     # the binding roofline of a kernel = whichever of (FLOPs / tensor peak, bytes / HBM peak) takes longer
     t_tensor = top["flops"] / (peaks["tflops"] * 1e9)          # ms
@@ -344,6 +367,8 @@ def run_ours(args):
             roof["tflops"] = top["tflops"]
             roof["note"] = ("tcgen05 implicit-GEMM convolution whose FLOPs need less time at the tensor peak than its act8 bytes need at the "
                             "HBM peak: HBM is the binding roofline")
+    roof["family_share_of_step"] = fam[top_op] / step_ms_prof
+    roof["traffic"] = ncu_traffic(top, B)
     tc_rows = [r for r in rows if r["op"] in ("conv_tc", "conv_tc_wgrad")]
     if tc_rows:
         tc_ms = sum(r["ms_per_step"] for r in tc_rows)

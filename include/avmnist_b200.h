@@ -87,6 +87,11 @@ int b200_ce_fwd_bwd(const float* logits, const int64_t* labels, int B, int C, fl
 int64_t b200_infonce_work_floats(int B, int D);
 int b200_infonce_fwd_bwd(const float* a, const float* b, int B, int D, float temperature, float grad_scale,
                          float* grad_a, float* grad_b, float* loss_out, float* work, void* stream);
+/* the same loss and gradients on the tensor cores: tcgen05 tf32 similarity GEMM with an exp / row-sum epilogue (E = exp(sim)
+ * kept once in bf16), bf16 tcgen05 GEMMs for the gradients.  work: float[b200_infonce_tc_work_floats(B, D)], 16-byte aligned. */
+int64_t b200_infonce_tc_work_floats(int B, int D);
+int b200_infonce_fwd_bwd_tc(const float* a, const float* b, int B, int D, float temperature, float grad_scale, float* grad_a,
+                            float* grad_b, float* loss_out, float* work, void* stream);
 /* UniModalDINOLightning._cosine_consistency_loss, models/dino.py:1575-1594: emb [V,B,D] */
 int b200_cosine_consistency_fwd_bwd(const float* emb, int V, int B, int D, float grad_scale, float* grad_emb,
                                     float* loss_out, void* stream);

@@ -231,17 +231,49 @@ class AVMNISTDataModule(BaseAVMNISTDataModule):
     pass
 
 
+class DeviceResidentLoader:
+    """The whole training split resident in HBM: image fp32 [N,1,28,28] as stored on disk / 255, audio kept as the
+    on-disk uint8 [N,1,112,112] (0.75 GB for 60k samples; the /255 of utils/get_data.py:467 happens inside the augmentation
+    kernel), labels int64.  An epoch is a device-side permutation; a batch is one gather.  Yields (image, audio[, label]) device
+    tensors -- the raw-batch form the training_step augments on the GPU -- so no DataLoader worker, pinned buffer or H2D copy
+    sits on the step's critical path."""
+
+    def __init__(self, dataset, indices, batch_size, device, shuffle=True, drop_last=True, with_labels=False, seed=0):
+        base = dataset
+        idx = np.sort(np.asarray(indices)) if indices is not None else np.arange(len(base))
+        img = np.asarray(base.image_data[idx], dtype=np.float32).reshape(-1, 1, 28, 28)
+        self.image = torch.from_numpy(img / 255.0 if base.normalize_image else img).to(device)
+        self.audio = torch.from_numpy(np.ascontiguousarray(base.audio_data[idx])).reshape(-1, 1, 112, 112).to(device)      # uint8
+        self.labels = torch.from_numpy(base.labels[idx].astype(np.int64)).to(device)
+        self.batch_size, self.shuffle, self.drop_last, self.with_labels = batch_size, shuffle, drop_last, with_labels
+        self.gen = torch.Generator(device=device).manual_seed(seed)
+        self.device = device
+
+    def __len__(self):
+        n = self.image.shape[0]
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        n = self.image.shape[0]
+        perm = torch.randperm(n, device=self.device, generator=self.gen) if self.shuffle else torch.arange(n, device=self.device)
+        for b in range(len(self)):
+            sel = perm[b * self.batch_size:(b + 1) * self.batch_size]
+            batch = (self.image.index_select(0, sel), self.audio.index_select(0, sel))
+            yield batch + ((self.labels.index_select(0, sel),) if self.with_labels else ())
+
+
 class AVMNISTDinoDataModule(BaseAVMNISTDataModule):
     """device_augmentation=True (default): batches are the un-augmented (image, audio) pairs and the multi-crop views are
     made on the GPU inside the training step; False: the reference's collated 4-tuple of views (needs num_workers=0)."""
     EXTENDED = False
 
     def __init__(self, data_dir, batch_size=32, num_workers=4, n_global_views=2, n_local_views=4, type="burst_noise", augmentations=None,
-                 device_augmentation=True):
+                 device_augmentation=True, device_resident=False):
         super().__init__(data_dir=data_dir, batch_size=batch_size, num_workers=num_workers, type=type)
         self.n_global_views, self.n_local_views = n_global_views, n_local_views
         self.augmentations = augmentations if augmentations is not None else MultiModalAugmentation(n_global_views, n_local_views)
         self.device_augmentation = device_augmentation
+        self.device_resident = device_resident          # keep the training split in HBM (DeviceResidentLoader)
         if not device_augmentation and num_workers != 0:
             raise ValueError("per-sample CUDA augmentation in the dataset needs num_workers=0")
 
@@ -251,6 +283,13 @@ class AVMNISTDinoDataModule(BaseAVMNISTDataModule):
 
     def get_view_config(self):
         return {"n_global_views": self.n_global_views, "n_local_views": self.n_local_views}
+
+    def train_dataloader(self):
+        if self.device_resident and self.device_augmentation and torch.cuda.is_available():
+            sub = self.train_dataset
+            return DeviceResidentLoader(sub.dataset, sub.indices, self.batch_size, torch.device("cuda", torch.cuda.current_device()),
+                                        shuffle=self.train_shuffle, with_labels=self.EXTENDED)
+        return super().train_dataloader()
 
 
 class AVMNISTDinoDataModuleExtended(AVMNISTDinoDataModule):

@@ -37,11 +37,15 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
         : "memory");
 }
 
-// epi: 0 store, 1 +bias, 2 +bias,ReLU, 3 +bias,ReLU,dropout(mask), 4 split-K partial (C holds [splits][M][ldc])
+// epi: 0 store, 1 +bias, 2 +bias,ReLU, 3 +bias,ReLU,dropout(mask), 4 split-K partial (C holds [splits][M][ldc]),
+//      5 InfoNCE: e = exp(x*fparam - fparam) stored as bf16 into C (ldc in bf16 elements) + per-(column tile, row) sums of e in aux
+// BF16 = true: bf16 operands (kind::f16, UMMA K = 16, 64-element k-blocks); false: fp32 operands consumed as tf32.
+template <bool BF16>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C, int64_t ldc, int M, int N,
                int K, int k_per_split, int epi, const float* __restrict__ bias, const uint8_t* __restrict__ mask,
-               float keep_scale) {
+               float keep_scale, float* __restrict__ aux, float fparam) {
+    constexpr int GBKE = BF16 ? 64 : 32;                                 // k-block in elements (always 128 bytes)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                      // swizzle atoms need 1024-byte alignment
@@ -56,7 +60,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
     const int kbeg = blockIdx.z * k_per_split, kend = min(K, kbeg + k_per_split);
-    const int nkb = (kend - kbeg + GBK - 1) / GBK;
+    const int nkb = (kend - kbeg + GBKE - 1) / GBKE;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
@@ -81,14 +85,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(empty_bar(s), (use & 1) ^ 1);
                 mbar_expect_tx(full_bar(s), G_STAGE);
                 const uint32_t sa = base + s * G_STAGE, sb = sa + G_A_BYTES;
-                const int k = kbeg + kb * GBK;
+                const int k = kbeg + kb * GBKE;
                 tma_load_2d(sa, &tmA, full_bar(s), k, m0);             // box (32 k, 128 rows), 128-byte swizzle
                 tma_load_2d(sb, &tmB, full_bar(s), k, n0);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = idesc_tf32(GBN, false, false);
+            const uint32_t idesc = BF16 ? idesc_bf16(GBN) : idesc_tf32(GBN, false, false);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % G_STAGES, use = kb / G_STAGES;
                 mbar_wait(full_bar(s), use & 1);
@@ -113,6 +117,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after_sync();
         }
         float* crow = C + (epi == 4 ? (int64_t)blockIdx.z * M * ldc : 0) + (int64_t)gm * ldc;
+        float esum = 0.f;
         const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll 1
         for (int cc = 0; cc < GBN / 16; ++cc) {
@@ -126,6 +131,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             const int gn0 = n0 + cc * 16;
             if (gm >= M || gn0 >= N) continue;
+            if (epi == 5) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float e0 = (gn0 + 2 * j < N) ? expf(__uint_as_float(v[2 * j]) * fparam - fparam) : 0.f;
+                    const float e1 = (gn0 + 2 * j + 1 < N) ? expf(__uint_as_float(v[2 * j + 1]) * fparam - fparam) : 0.f;
+                    esum += e0 + e1;
+                    pk[j] = pack_bf16(e0, e1);
+                }
+                __nv_bfloat16* erow = reinterpret_cast<__nv_bfloat16*>(C) + (int64_t)gm * ldc + gn0;
+                if (gn0 + 16 <= N && (ldc & 7) == 0) {
+                    reinterpret_cast<uint4*>(erow)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    reinterpret_cast<uint4*>(erow)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (gn0 + j < N) reinterpret_cast<uint16_t*>(erow)[j] = (uint16_t)((j & 1) ? (pk[j >> 1] >> 16) : (pk[j >> 1] & 0xFFFFu));
+                }
+                continue;
+            }
             float f[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -145,6 +170,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (gn0 + j < N) crow[gn0 + j] = f[j];
             }
         }
+        if (epi == 5 && gm < M) aux[(int64_t)blockIdx.x * M + gm] = esum;
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -155,7 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 int encode_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems, uint32_t box_inner,
-                       uint32_t box_outer, bool swizzle128 = true) {
+                       uint32_t box_outer, bool swizzle128 = true, bool bf16 = false) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -171,10 +197,11 @@ int encode_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t inner, uint6
         fn = (EncodeFn)p;
     }
     cuuint64_t d[2] = {inner, outer};
-    cuuint64_t s[1] = {ld_elems * 4};
+    cuuint64_t s[1] = {ld_elems * (bf16 ? 2 : 4)};
     cuuint32_t b[2] = {box_inner, box_outer};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = fn(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), d, s, b, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -191,29 +218,42 @@ bool gemm_tc_usable(const void* A, int64_t lda, const void* Bm, int64_t ldb) {
     return ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bm)) & 15) == 0 && (lda & 3) == 0 && (ldb & 3) == 0;
 }
 
-// C[M,N] = A x B^T with the operand conventions above.  splits > 1: C must hold [splits][M][ldc] partials (epi is forced to 4).
-int launch_gemm_tc(const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc, int M, int N, int K, int splits, int epi,
-                   const float* bias, const uint8_t* mask, float keep_scale, cudaStream_t st) {
+// C[M,N] = A x B^T, both operands K-major.  splits > 1: C must hold [splits][M][ldc] partials (epi is forced to 4).
+// bf16 = 1: A and B are bf16 (lda / ldb in bf16 elements, multiples of 8); aux / fparam: see epi 5.
+int launch_gemm_tc_ex(const void* A, int64_t lda, const void* Bm, int64_t ldb, void* C, int64_t ldc, int M, int N, int K, int splits, int epi,
+                      const float* bias, const uint8_t* mask, float keep_scale, float* aux, float fparam, int bf16, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
         if (e != cudaSuccess) {
             set_error("gemm_tc: cannot set %d bytes of shared memory: %s", G_SMEM, cudaGetErrorString(e));
             return (int)e;
         }
         configured = true;
     }
+    const int gbke = bf16 ? 64 : 32;
     CUtensorMap ta, tb;
-    int rc = encode_tmap_f32_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GBK, GBM);
+    int rc = encode_tmap_f32_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, gbke, GBM, true, bf16 != 0);
     if (rc) return rc;
-    rc = encode_tmap_f32_2d(&tb, Bm, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GBK, GBN);
+    rc = encode_tmap_f32_2d(&tb, Bm, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, gbke, GBN, true, bf16 != 0);
     if (rc) return rc;
     if (splits < 1) splits = 1;
-    int kps = ((K + splits - 1) / splits + GBK - 1) / GBK * GBK;
+    int kps = ((K + splits - 1) / splits + gbke - 1) / gbke * gbke;
     splits = (K + kps - 1) / kps;
     dim3 grid((N + GBN - 1) / GBN, (M + GBM - 1) / GBM, splits);
-    gemm_tc_kernel<<<grid, 192, G_SMEM, st>>>(ta, tb, C, ldc, M, N, K, kps, splits > 1 ? 4 : epi, bias, mask, keep_scale);
+    if (bf16)
+        gemm_tc_kernel<true><<<grid, 192, G_SMEM, st>>>(ta, tb, reinterpret_cast<float*>(C), ldc, M, N, K, kps, splits > 1 ? 4 : epi, bias, mask,
+                                                        keep_scale, aux, fparam);
+    else
+        gemm_tc_kernel<false><<<grid, 192, G_SMEM, st>>>(ta, tb, reinterpret_cast<float*>(C), ldc, M, N, K, kps, splits > 1 ? 4 : epi, bias, mask,
+                                                         keep_scale, aux, fparam);
     return launch_status("gemm_tc_kernel");
+}
+
+int launch_gemm_tc(const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc, int M, int N, int K, int splits, int epi,
+                   const float* bias, const uint8_t* mask, float keep_scale, cudaStream_t st) {
+    return launch_gemm_tc_ex(A, lda, Bm, ldb, C, ldc, M, N, K, splits, epi, bias, mask, keep_scale, nullptr, 0.f, 0, st);
 }
 
 // dst[c*ldd + r] = src[r*lds + c], 32 x 32 tiles through shared memory (coalesced both ways)

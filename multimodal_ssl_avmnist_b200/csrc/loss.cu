@@ -2,6 +2,8 @@
 // MSE alignment, 10-way CE, InfoNCE (tiled, the [B,B] matrix never reaches HBM), cosine consistency.
 // All reductions inside a row are warp shuffles; cross-CTA reductions go through per-CTA partials that are
 // summed in a fixed order (deterministic).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -392,6 +394,80 @@ __global__ void __launch_bounds__(256) normalize_bwd_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// InfoNCE on the tensor cores (csrc/gemm_tc.cu): S = Ah Bh^T as a tcgen05 tf32 GEMM whose epilogue turns every tile into
+// e = exp(S/temp - 1/temp), stores it as bf16 and emits per-(column tile, row) partial sums (-> rowsum, fixed order);
+// the same call with swapped operands gives E^T and the column sums.  The gradients are then plain bf16 tensor-core
+// GEMMs   T = E [Bh | Bh/colsum]   and   T' = E^T [Ah | Ah/rowsum]   followed by an element-wise combine:
+//     dAh_i = (0.5/B (T1_i / rowsum_i + T2_i) - Bh_i / B) / temp.
+// E is B x B bf16 (134 MB at B = 8192): written once, read once per side; 3 x 2 B^2 D FLOP on the tensor cores replace the
+// 6 x 2 B^2 D FLOP of recomputing SIMT tiles.
+// ---------------------------------------------------------------------------------------------------------
+int launch_gemm_tc_ex(const void* A, int64_t lda, const void* Bm, int64_t ldb, void* C, int64_t ldc, int M, int N, int K, int splits, int epi,
+                      const float* bias, const uint8_t* mask, float keep_scale, float* aux, float fparam, int bf16, cudaStream_t st);
+
+// tf32 keeps 10 mantissa bits: at 1/temp = 14 that is a 4e-3 error on the logits.  Split x = hi + lo (hi = x with the low 13
+// mantissa bits cleared: exact in tf32; lo = x - hi: exact in fp32) and lay the pieces out along K so that ONE tf32 GEMM
+// computes  a_hi b_hi + a_hi b_lo + a_lo b_hi  (the 3xTF32 scheme, error ~2^-21):  X1 = [hi | hi | lo],  X2 = [hi | lo | hi].
+__global__ void __launch_bounds__(256) infonce_split3_kernel(const float* __restrict__ xh, int B, int D, float* __restrict__ x1,
+                                                             float* __restrict__ x2) {
+    const size_t n = (size_t)B * D;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = e / D;
+        const int d = (int)(e - i * D);
+        const float x = xh[e];
+        const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u), lo = x - hi;
+        float* r1 = x1 + i * 3 * D;
+        float* r2 = x2 + i * 3 * D;
+        r1[d] = hi; r1[D + d] = hi; r1[2 * D + d] = lo;
+        r2[d] = hi; r2[D + d] = lo; r2[2 * D + d] = hi;
+    }
+}
+
+__global__ void __launch_bounds__(256) sum_parts_kernel(const float* __restrict__ part, int n_parts, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a = 0.f;
+    for (int p = 0; p < n_parts; ++p) a += part[(size_t)p * n + i];
+    out[i] = a;
+}
+
+// YT bf16 [2D][ld]: YT[d][j] = xh[j][d], YT[D+d][j] = xh[j][d] / s[j]   (K-major B operand of the gradient GEMM)
+__global__ void __launch_bounds__(256) infonce_build_yt_kernel(const float* __restrict__ xh, const float* __restrict__ s, int B, int D, int ld,
+                                                               __nv_bfloat16* __restrict__ yt) {
+    __shared__ float tile[32][33];
+    const int j0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int j = j0 + ty + 8 * i, d = d0 + tx;
+        tile[ty + 8 * i][tx] = (j < B && d < D) ? __ldg(xh + (size_t)j * D + d) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int d = d0 + ty + 8 * i, j = j0 + tx;
+        if (d < D && j < B) {
+            const float v = tile[tx][ty + 8 * i];
+            yt[(size_t)d * ld + j] = __float2bfloat16_rn(v);
+            yt[(size_t)(D + d) * ld + j] = __float2bfloat16_rn(v / __ldg(s + j));
+        }
+    }
+}
+
+// dxh[i][d] = inv_temp * (0.5*coef*(T[i][d] / own[i] + T[i][D+d]) - coef * other_h[i][d])
+__global__ void __launch_bounds__(256) infonce_combine_kernel(const float* __restrict__ T, const float* __restrict__ own,
+                                                              const float* __restrict__ other_h, int B, int D, float inv_temp, float coef,
+                                                              float* __restrict__ dxh) {
+    const size_t n = (size_t)B * D;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = e / D;
+        const int d = (int)(e - i * D);
+        const float t1 = T[i * 2 * D + d], t2 = T[i * 2 * D + D + d];
+        dxh[e] = inv_temp * (0.5f * coef * (t1 / __ldg(own + i) + t2) - coef * __ldg(other_h + e));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Cosine consistency (unimodal): mean over pairs i<j of mean_b (1 - <e_i, e_j>)^2, e = normalize(emb).
 // One CTA (128 threads) per sample; the V normalised vectors sit in shared memory.
 // ---------------------------------------------------------------------------------------------------------
@@ -563,6 +639,73 @@ int b200_infonce_fwd_bwd(const float* a, const float* b, int B, int D, float tem
     normalize_bwd_kernel<<<rg, 256, 0, st>>>(ah, dah, dena, B, D, grad_scale, grad_a);
     normalize_bwd_kernel<<<rg, 256, 0, st>>>(bh, dbh, denb, B, D, grad_scale, grad_b);
     return launch_status("infonce_fwd_bwd");
+}
+
+static int64_t pad4l(int64_t n) { return (n + 3) / 4 * 4; }
+
+int64_t b200_infonce_tc_work_floats(int B, int D) {
+    if (B <= 0 || D <= 0) return 0;
+    const int64_t nt = (B + 127) / 128, ldE = (B + 7) / 8 * 8;
+    return pad4l(4LL * B * D) + pad4l(4LL * B) + pad4l(2 * nt * B) + pad4l(2LL * B * 2 * D) + pad4l(4LL * B * 3 * D) +
+           pad4l((2LL * B * ldE + 2LL * 2 * D * ldE) / 2 + 8) + 64;
+}
+
+int b200_infonce_fwd_bwd_tc(const float* a, const float* b, int B, int D, float temperature, float grad_scale, float* grad_a,
+                            float* grad_b, float* loss_out, float* work, void* stream) {
+    B200_REQUIRE(a && b && grad_a && grad_b && loss_out && work && B > 0, B200_E_ARG, "infonce_tc: bad arguments");
+    B200_REQUIRE(D % 32 == 0 && D >= 32 && D <= 1024, B200_E_SHAPE, "infonce_tc: D=%d must be a multiple of 32", D);
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(work) & 15) == 0, B200_E_ARG, "infonce_tc: work must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const int64_t nt = (B + 127) / 128, ldE = (B + 7) / 8 * 8;
+    float* ah = work;
+    float* bh = ah + (size_t)B * D;
+    float* dah = bh + (size_t)B * D;
+    float* dbh = dah + (size_t)B * D;
+    float* dena = work + pad4l(4LL * B * D);
+    float* denb = dena + B;
+    float* rowsum = denb + B;
+    float* colsum = rowsum + B;
+    float* rowpart = dena + pad4l(4LL * B);
+    float* colpart = rowpart + nt * B;
+    float* Ta = rowpart + pad4l(2 * nt * B);
+    float* Tb = Ta + (size_t)B * 2 * D;
+    float* a1 = Ta + pad4l(2LL * B * 2 * D);             // [hi | hi | lo] / [hi | lo | hi] splits of ah and bh, [B][3D] each
+    float* a2 = a1 + (size_t)B * 3 * D;
+    float* b1 = a2 + (size_t)B * 3 * D;
+    float* b2 = b1 + (size_t)B * 3 * D;
+    __nv_bfloat16* E = reinterpret_cast<__nv_bfloat16*>(a1 + pad4l(4LL * B * 3 * D));
+    __nv_bfloat16* ET = E + (size_t)B * ldE;
+    __nv_bfloat16* YTa = ET + (size_t)B * ldE;          // built from ah / rowsum: B operand of the dBh GEMM
+    __nv_bfloat16* YTb = YTa + (size_t)2 * D * ldE;     // built from bh / colsum: B operand of the dAh GEMM
+    const float inv_temp = 1.0f / temperature;
+    const int rg = rows_grid(B);
+    cudaMemsetAsync(loss_out, 0, sizeof(float), st);
+    normalize_rows_kernel<<<rg, 256, 0, st>>>(a, B, D, ah, dena);
+    normalize_rows_kernel<<<rg, 256, 0, st>>>(b, B, D, bh, denb);
+    const int sg = (int)(((size_t)B * D + 255) / 256 < (size_t)sm_count() * 8 ? ((size_t)B * D + 255) / 256 : (size_t)sm_count() * 8);
+    infonce_split3_kernel<<<sg, 256, 0, st>>>(ah, B, D, a1, a2);
+    infonce_split3_kernel<<<sg, 256, 0, st>>>(bh, B, D, b1, b2);
+    int rc = launch_gemm_tc_ex(a1, 3 * D, b2, 3 * D, E, ldE, B, B, 3 * D, 1, 5, nullptr, nullptr, 1.f, rowpart, inv_temp, 0, st);
+    if (rc) return rc;
+    rc = launch_gemm_tc_ex(b1, 3 * D, a2, 3 * D, ET, ldE, B, B, 3 * D, 1, 5, nullptr, nullptr, 1.f, colpart, inv_temp, 0, st);
+    if (rc) return rc;
+    sum_parts_kernel<<<(B + 255) / 256, 256, 0, st>>>(rowpart, (int)nt, B, rowsum);
+    sum_parts_kernel<<<(B + 255) / 256, 256, 0, st>>>(colpart, (int)nt, B, colsum);
+    infonce_loss_kernel<<<rg, 256, 0, st>>>(ah, bh, rowsum, colsum, B, D, inv_temp, loss_out);
+    const dim3 tg((B + 31) / 32, (D + 31) / 32);
+    infonce_build_yt_kernel<<<tg, 256, 0, st>>>(ah, rowsum, B, D, (int)ldE, YTa);
+    infonce_build_yt_kernel<<<tg, 256, 0, st>>>(bh, colsum, B, D, (int)ldE, YTb);
+    rc = launch_gemm_tc_ex(E, ldE, YTb, ldE, Ta, 2 * D, B, 2 * D, B, 1, 0, nullptr, nullptr, 1.f, nullptr, 0.f, 1, st);
+    if (rc) return rc;
+    rc = launch_gemm_tc_ex(ET, ldE, YTa, ldE, Tb, 2 * D, B, 2 * D, B, 1, 0, nullptr, nullptr, 1.f, nullptr, 0.f, 1, st);
+    if (rc) return rc;
+    const float coef = 1.0f / (float)B;
+    const int cg = (int)(((size_t)B * D + 255) / 256 < (size_t)sm_count() * 8 ? ((size_t)B * D + 255) / 256 : (size_t)sm_count() * 8);
+    infonce_combine_kernel<<<cg, 256, 0, st>>>(Ta, rowsum, bh, B, D, inv_temp, coef, dah);
+    infonce_combine_kernel<<<cg, 256, 0, st>>>(Tb, colsum, ah, B, D, inv_temp, coef, dbh);
+    normalize_bwd_kernel<<<rg, 256, 0, st>>>(ah, dah, dena, B, D, grad_scale, grad_a);
+    normalize_bwd_kernel<<<rg, 256, 0, st>>>(bh, dbh, denb, B, D, grad_scale, grad_b);
+    return launch_status("infonce_fwd_bwd_tc");
 }
 
 int b200_cosine_consistency_fwd_bwd(const float* emb, int V, int B, int D, float grad_scale, float* grad_emb, float* loss_out,

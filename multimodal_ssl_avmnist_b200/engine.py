@@ -375,7 +375,7 @@ class DinoStepEngine:
                 for nm in ("hscale", "hshift", "hmean", "hinvstd"):
                     w[f"{m}.{nm}"] = e(1, 512)
             if self.mode == "infonce":
-                w["infonce_work"] = e(ops.infonce_work_floats(B, P))
+                w["infonce_work"] = e(ops.infonce_work_floats(B, P, tc=self.lin_tc))
         if self.cosine_loss_alpha > 0:
             w["d.emb"] = e(Nv, O)
         self._ws[B] = w
@@ -728,7 +728,7 @@ class DinoStepEngine:
             loss[1:2].add_(loss[2:3])
             loss[2:3].zero_()
         elif self.mode == "infonce":
-            ops.infonce_fwd_bwd(oi, oa, w["aux_image.d.out"], w["aux_audio.d.out"], loss[1:2], w["infonce_work"], grad_scale=self.alpha)
+            ops.infonce_fwd_bwd(oi, oa, w["aux_image.d.out"], w["aux_audio.d.out"], loss[1:2], w["infonce_work"], grad_scale=self.alpha, tc=self.lin_tc)
         elif self.mode == "mse":
             ops.mse_align_fwd_bwd(oi, oa, w["aux_image.d.out"], w["aux_audio.d.out"], loss[1:2], grad_scale=self.alpha)
 

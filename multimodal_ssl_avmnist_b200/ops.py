@@ -119,14 +119,16 @@ def ce_fwd_bwd(logits, labels, grad_logits, loss_out, grad_scale=1.0):
                                        _ptr(loss_out, F32), _stream()), "ce_fwd_bwd")
 
 
-def infonce_work_floats(B, D):
-    return _lib_().b200_infonce_work_floats(B, D)
+def infonce_work_floats(B, D, tc=False):
+    return (_lib_().b200_infonce_tc_work_floats if tc else _lib_().b200_infonce_work_floats)(B, D)
 
 
-def infonce_fwd_bwd(a, b, grad_a, grad_b, loss_out, work, temperature=0.07, grad_scale=1.0):
+def infonce_fwd_bwd(a, b, grad_a, grad_b, loss_out, work, temperature=0.07, grad_scale=1.0, tc=False):
+    """InfoNCE loss + gradients; tc=True: tensor-core similarity / gradient GEMMs (work sized with infonce_work_floats(tc=True))."""
     B, D = a.shape
-    _lib.check(_lib_().b200_infonce_fwd_bwd(_ptr(a, F32), _ptr(b, F32), B, D, temperature, grad_scale, _ptr(grad_a, F32),
-                                            _ptr(grad_b, F32), _ptr(loss_out, F32), _ptr(work, F32), _stream()), "infonce_fwd_bwd")
+    fn = _lib_().b200_infonce_fwd_bwd_tc if tc else _lib_().b200_infonce_fwd_bwd
+    _lib.check(fn(_ptr(a, F32), _ptr(b, F32), B, D, temperature, grad_scale, _ptr(grad_a, F32), _ptr(grad_b, F32), _ptr(loss_out, F32),
+                  _ptr(work, F32), _stream()), "infonce_fwd_bwd")
 
 
 def cosine_consistency_fwd_bwd(emb, grad_emb, loss_out, grad_scale=1.0):

@@ -131,3 +131,31 @@ def test_trainer_fit_on_synthetic_files(tmp_path):
     again = md.MultiModalDINOLightning.load_from_checkpoint(ckpt.best_model_path)
     a, b = again.state_dict(), lit.state_dict()
     assert set(a) == set(b) and all(a[k].shape == b[k].shape for k in a)
+
+
+def test_device_resident_loader_feeds_the_step(tmp_path):
+    """the training split lives in HBM (audio as the on-disk uint8), batches are device gathers and the /255
+    normalisation happens inside the augmentation kernel; same samples as the DataLoader path."""
+    d = str(tmp_path) + "/"
+    gd.write_synthetic_avmnist(d, n_train=96, n_test=16)
+    dm = gd.AVMNISTDinoDataModuleExtended(data_dir=d, batch_size=16, num_workers=0, type="burst_noise", device_resident=True)
+    dm.setup("fit")
+    dl = dm.train_dataloader()
+    assert isinstance(dl, gd.DeviceResidentLoader) and len(dl) == len(dm.train_dataset) // 16
+    image, audio, label = next(iter(dl))
+    assert image.is_cuda and audio.dtype == torch.uint8 and image.shape == (16, 1, 28, 28) and audio.shape == (16, 1, 112, 112)
+    # the resident tensors hold exactly the samples of the subset (the host dataset divides the audio by 255)
+    sub = dm.train_dataset
+    k = int(sorted(sub.indices)[3])
+    himg, haud, hlab = sub.dataset[k]
+    assert torch.allclose(dl.image[3].cpu(), himg.float(), atol=1e-7) and int(dl.labels[3]) == int(hlab)
+    assert torch.allclose(dl.audio[3].cpu().float() / 255.0, haud.float(), atol=1e-7)
+    lit = md.MultiModalDINOSemiSupervisedLightning(**dict(KW, data_dir=d)).to(DEV)
+    opt = lit.configure_optimizers()["optimizer"]
+    for it, batch in enumerate(dl):
+        opt.zero_grad(set_to_none=True)
+        loss = lit.training_step(batch, it)
+        loss.backward()
+        opt.step()
+    torch.cuda.synchronize()
+    assert 3.0 < float(loss) < 12.0

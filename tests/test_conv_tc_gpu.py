@@ -309,3 +309,26 @@ def test_bn_backward_statistics_from_pooled_tensors(C, H, views, B):
         got = torch.zeros_like(want)
         ops.bn_pool8_bwd_reduce_p(pt, dpt, gamma, beta, got, B)
         assert float(((got - want).abs() / ref_scale).max()) < tol, (pt.dtype, dpt.dtype)
+
+
+@pytest.mark.parametrize("B,D", [(64, 128), (300, 128), (1024, 128), (2500, 64)])
+def test_infonce_tensor_core(B, D):
+    """Tensor-core InfoNCE (tf32 similarity GEMM + exp/row-sum epilogue, bf16 E, bf16 gradient GEMMs) against the fp64 formula
+    (models/dino.py:1091-1128): loss 1e-3 relative, gradients 2e-2 of their scale."""
+    g = torch.Generator().manual_seed(B + D)
+    a = torch.randn(B, D, generator=g).to(DEV)
+    b = (0.5 * a.cpu() + torch.randn(B, D, generator=g)).to(DEV)
+    ad, bd = a.double().requires_grad_(True), b.double().requires_grad_(True)
+    sim = F.normalize(ad, dim=1) @ F.normalize(bd, dim=1).t() / 0.07
+    lab = torch.arange(B, device=DEV)
+    want = 0.5 * (F.cross_entropy(sim, lab) + F.cross_entropy(sim.t(), lab))
+    want.backward()
+    ga, gb, lo = torch.empty_like(a), torch.empty_like(b), torch.empty(1, device=DEV)
+    work = torch.empty(ops.infonce_work_floats(B, D, tc=True), device=DEV)
+    ops.infonce_fwd_bwd(a, b, ga, gb, lo, work, temperature=0.07, tc=True)
+    torch.cuda.synchronize()
+    assert abs(float(lo) - float(want)) < 1e-3 * float(want), (float(lo), float(want))
+    for got, ref in ((ga, ad.grad), (gb, bd.grad)):
+        assert float((got.double() - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
+        cos = float((got.double().flatten() @ ref.flatten()) / (got.double().norm() * ref.norm()))
+        assert cos > 0.9995, cos
