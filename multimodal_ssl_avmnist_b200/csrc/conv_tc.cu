@@ -85,6 +85,11 @@ struct TcCfg {
     static constexpr int SMEM = BAR_OFF + 256 + NPADL * 4;
     static constexpr int NBUF = (NPADL <= 32 ? 8 : 4) / (CTAS > 2 ? 2 : 1);   // TMEM accumulator stages
     static constexpr int TMEM_COLS = pow2_cols(NBUF * NPADL);
+    // One issuing thread sustains only ~1 UMMA per 140 cycles at these tile shapes (measured, tools/umma_probe.cu); four
+    // concurrent issue streams per SM -- CTAs or warps -- reach the shared-memory operand bandwidth (39-48 cycles per UMMA).
+    static constexpr int ISS = CTAS >= 3 ? 1 : (CTAS == 2 ? 2 : 4);     // MMA-issuer warps per CTA
+    static constexpr int THREADS = 32 * (1 + ISS + 4);
+    static_assert(NBUF % ISS == 0, "a TMEM stage must always be filled by the same issuer");
     static_assert(TMEM_COLS * CTAS <= 512, "TMEM columns per SM");
     static_assert((SMEM_EST(NMMA, NPADL, SLOTS, SLOT_BYTES, TAIL) + 1024) * CTAS <= 227 * 1024, "shared memory per SM");
     static_assert(2 * SLOTS + 2 * NBUF <= 24, "barrier area");
@@ -99,7 +104,7 @@ struct TcCfg {
 // z, which is never an MMA operand -- 11 mantissa bits keep max-pool arg-max ties as rare as on the reference's fp16 autocast path).
 // bias may be null (no bias, no statistics); stats: double [views][COUT][2] (sum, sum of squares), accumulated.
 template <class C>
-__global__ void __launch_bounds__(192, C::CTAS)
+__global__ void __launch_bounds__(C::THREADS, C::CTAS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict__ wprep, const float* __restrict__ bias,
                void* __restrict__ out, double* __restrict__ stats, int n_per_view, int out_bf16) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -138,7 +143,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
         prefetch_tmap(&tmap);
         for (int s = 0; s < C::SLOTS; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), C::ISS);
         }
         for (int b = 0; b < C::NBUF; ++b) {
             mbar_init(tfull_bar(b), 1);
@@ -164,17 +169,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
                 tma_load_4d(img_addr + slot * C::SLOT_BYTES, &tmap, full_bar(slot), 0, C::L0 ? 0 : -C::PAD, band * C::HB - C::PAD, n * C::P);
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
+    } else if (warp <= C::ISS) {
+        // ===== MMA issuers: warp w takes the tiles t == w-1 (mod ISS) of every item =====
         if (lane == 0) {
             constexpr uint32_t idesc = idesc_bf16(C::NPADL);
-            uint32_t tcount = 0;
             for (int i = i0; i < i1; ++i) {
                 const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
                 mbar_wait(full_bar(slot), use & 1);
                 tc_fence_after_sync();
                 const uint32_t slot_addr = img_addr + slot * C::SLOT_BYTES;
-                for (int t = 0; t < C::TILES; ++t, ++tcount) {
+                for (int t = warp - 1; t < C::TILES; t += C::ISS) {
+                    const uint32_t tcount = (uint32_t)k * C::TILES + t;
                     const uint32_t buf = tcount % C::NBUF, u = tcount / C::NBUF;
                     mbar_wait(tempty_bar(buf), (u & 1) ^ 1);
                     tc_fence_after_sync();
@@ -219,7 +224,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
         }
     } else {
         // ===== epilogue warps (TMEM lane quadrant = warp % 4) =====
-        const int quad = warp & 3, row = quad * 32 + lane;
+        const int quad = warp & 3, row = quad * 32 + lane;      // the 4 epilogue warps have consecutive ids: all quadrants covered
         float s1[C::COUTL], s2[C::COUTL];
 #pragma unroll
         for (int c = 0; c < C::COUTL; ++c) s1[c] = s2[c] = 0.f;
@@ -407,7 +412,7 @@ int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* ou
     if (G < 1) G = 1;
     const long items = (long)n_per_view * C::BANDS;
     if (G > items) G = (int)items;
-    conv_tc_kernel<C><<<dim3(G, views, C::NSPLIT), 192, C::SMEM, st>>>(tm, reinterpret_cast<const uint4*>(wprep), bias, out, stats, n_per_view, out_bf16);
+    conv_tc_kernel<C><<<dim3(G, views, C::NSPLIT), C::THREADS, C::SMEM, st>>>(tm, reinterpret_cast<const uint4*>(wprep), bias, out, stats, n_per_view, out_bf16);
     return launch_status("conv_tc_kernel");
 }
 
@@ -453,6 +458,8 @@ struct TcWgCfg {
     static constexpr int PART = DW;                                 // floats per CTA partial
     static_assert(P_IN % PSPLIT == 0 && HO % BANDS == 0, "splits");
     static_assert(BANDS == 1 || HBZ == HB, "row bands need HB*WP to be a multiple of 16");
+    static constexpr int ISS = (L0 || NACC < 4) ? 1 : (CTAS >= 3 ? 1 : (CTAS == 2 ? 2 : 4));   // MMA-issuer warps (accumulators split among them)
+    static constexpr int THREADS = 32 * (1 + ISS + 4);
     static_assert(NACC * COUTL <= 512 && TMEM_COLS * CTAS <= 512 && COUTL % 8 == 0, "TMEM columns");
     static_assert((SMEM + 1024) * CTAS <= 227 * 1024, "shared memory per SM");
     static_assert(KS <= 8 && COUT % 8 == 0 && COUT >= 8 && COUT <= 256, "shape");
@@ -461,7 +468,7 @@ struct TcWgCfg {
 };
 
 template <class C>
-__global__ void __launch_bounds__(192, C::CTAS)
+__global__ void __launch_bounds__(C::THREADS, C::CTAS)
 conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_z, float* __restrict__ work, int N) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);     // full[SLOTS], empty[SLOTS], done
@@ -484,9 +491,9 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         prefetch_tmap(&tmap_z);
         for (int s = 0; s < C::SLOTS; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), C::ISS);
         }
-        mbar_init(done_bar, 1);
+        mbar_init(done_bar, C::ISS);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<C::TMEM_COLS>(smem_u32(tmem_slot));
@@ -508,8 +515,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 tma_load_4d(sa + C::X_BYTES, &tmap_z, full_bar(slot), 0, 0, band * C::HB, n * C::P_OUT + ns * C::P_OUTL);
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
+    } else if (warp <= C::ISS) {
+        if (lane == 0) {                     // issuer w owns the accumulators a == w-1 (mod ISS)
             constexpr uint32_t idesc = idesc_bf16(C::COUTL, true, true, 64);
             for (int i = i0; i < i1; ++i) {
                 const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
@@ -528,6 +535,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                         for (int kh = 0; kh < C::KS; ++kh) {
 #pragma unroll
                             for (int pl = 0; pl < C::PI; ++pl) {
+                                if ((kh * C::PI + pl) % C::ISS != warp - 1) continue;
                                 const uint64_t ad = smem_desc(xa + pl * C::PLANE_X + (ks * 16 + kh * C::WP) * 16, 128, 16);
                                 mma_bf16(tmem_base + (kh * C::PI + pl) * C::COUTL, ad, bd, idesc, acc);
                             }
@@ -633,7 +641,7 @@ int launch_conv_tc_wgrad(const void* x, const void* dz, float* dw, float* work, 
         int rc = encode_tmap_bf16_4d(&tz, dz, dims, strides, box);
         if (rc) return rc;
     }
-    conv_tc_wgrad_kernel<C><<<dim3(G, 1, C::PSPLIT * C::NSPLIT), 192, C::SMEM, st>>>(tx, tz, work, N);
+    conv_tc_wgrad_kernel<C><<<dim3(G, 1, C::PSPLIT * C::NSPLIT), C::THREADS, C::SMEM, st>>>(tx, tz, work, N);
     int rc = launch_status("conv_tc_wgrad_kernel");
     if (rc) return rc;
     wgrad_reduce_kernel<<<(C::PART + 255) / 256, 256, 0, st>>>(work, G, C::PART, dw);
