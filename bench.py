@@ -285,11 +285,12 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
-    eng = DinoStepEngine(kind="multi_central", mode=args.mode, augment_values=augment_values(), seed=1 + rank, device=dev)
+    eng = DinoStepEngine(kind=args.kind, mode=args.mode, augment_values=augment_values() if args.kind == "multi_central" else None,
+                         seed=1 + rank, device=dev)
     g = torch.Generator().manual_seed(1 + rank)
     img_h = torch.rand(B, 28, 28, generator=g).pin_memory()
-    aud_h = torch.randint(0, 256, (B, 112, 112), generator=g, dtype=torch.uint8).pin_memory()
-    img_d, aud_d = img_h.to(dev), aud_h.to(dev)
+    aud_h = torch.randint(0, 256, (B, 112, 112), generator=g, dtype=torch.uint8).pin_memory() if args.kind == "multi_central" else None
+    img_d, aud_d = img_h.to(dev), (aud_h.to(dev) if aud_h is not None else None)
     lab_h = torch.randint(0, 10, (B,), generator=g).pin_memory() if args.mode == "semi_supervised" else None
     lab_d = lab_h.to(dev) if lab_h is not None else None
 
@@ -318,7 +319,7 @@ def run_ours(args):
     launches = (ops.launch_count() - l0) // args.steps
     # ---- timed region 2: end to end through the host-facing call (pinned host buffers in, loss out); every step copies its
     #      batch host->device and reads its loss back; the NEXT batch's copy + augmentation are enqueued before the read-back ----
-    nxt = (img_h, aud_h) + ((lab_h,) if lab_h is not None else ())
+    nxt = ((img_h, aud_h) + ((lab_h,) if lab_h is not None else ())) if aud_h is not None else (img_h,)
     for _ in range(2):
         eng.train_step_host(img_h, aud_h, lab_h, next_batch=nxt)
     barrier()
@@ -386,20 +387,21 @@ def run_ours(args):
     out_dir = os.path.join(ROOT, "gpurun_out")
     try:
         os.makedirs(out_dir, exist_ok=True)
-        tag = "" if args.mode == "default" else "_" + args.mode
+        tag = ("" if args.mode == "default" else "_" + args.mode) + ("" if args.kind == "multi_central" else "_" + args.kind)
         with open(os.path.join(out_dir, f"bench_ops_n{world}_b{B}{tag}.json"), "w") as f:
             json.dump({"ms_per_step": ms, "profiled_ms_per_step": step_ms_prof, "ops": rows}, f, indent=1)
     except Exception:
         pass
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.kind == "multi_central" and args.mode == "default":
         cores = os.cpu_count() or 1
         rate, _, desc = cpu_reference(64, 2, 1, cores)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
-    h2d = img_h.numel() * 4 + aud_h.numel()
+    h2d = img_h.numel() * 4 + (aud_h.numel() if aud_h is not None else 0)
     line = {"metric": METRIC, "value": B * world / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD if args.mode == "default" else WORKLOAD.replace("default mode", args.mode + " mode"), "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+            "config": {"workload": (WORKLOAD if args.mode == "default" else WORKLOAD.replace("default mode", args.mode + " mode")) if args.kind == "multi_central"
+                       else "image_simple unimodal DINO step (2 global + 4 local views of 28x28 images, O=256, P=128)", "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations) is several GB, far larger than the 126 MB L2",
                        "precision": "bf16 tensor-core convolutions (fp16 pre-BatchNorm z, bf16 activations / gradients), fp32 accumulate, "
                                     "statistics, linears, losses, EMA, Adam"},
@@ -419,6 +421,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kind", default="multi_central", choices=["multi_central", "image_simple"],
+                    help="image_simple = BASELINE.json configs[0] (unimodal image DINO); the headline line is multi_central")
     ap.add_argument("--mode", default="default", choices=["default", "semi_supervised", "infonce", "mse"],
                     help="training mode (BASELINE.json configs 2-5); the headline line is --mode default")
     args = ap.parse_args()

@@ -178,6 +178,29 @@ __global__ void __launch_bounds__(256, 3) bn_relu_pool8_bwd_kernel(const uint4* 
             zo[W + 1] = pack8(w[3]);
         }
     }
+    if (APPLY && ((H | W) & 1)) {
+        // odd planes (7x7 -> floor-pooled 3x3): the last row / column is in no pooling window but still receives the dense
+        // BatchNorm terms dz = ca*z + cb
+        const int ex = ((W & 1) ? H : 0) + ((H & 1) ? W : 0) - (((H & 1) && (W & 1)) ? 1 : 0);     // positions per (sample, octet)
+        const long units = (long)n_per_view * ex;
+        const long e0 = units * blockIdx.x / gridDim.x, e1 = units * (blockIdx.x + 1) / gridDim.x;
+        for (long u = e0 + threadIdx.x; u < e1; u += blockDim.x) {
+            const int s = (int)(u / ex);
+            int e = (int)(u - (long)s * ex), y, x;
+            if ((W & 1) && e < H) { y = e; x = W - 1; }
+            else { e -= (W & 1) ? H : 0; y = H - 1; x = e; }          // last row (without the corner already covered above)
+            const long n = (long)v * n_per_view + s;
+            const long off = ((n * t.P + oct) * H + y) * W + x;
+            float zz[8];
+            unpackz<ZF16>(__ldg(z8 + off), zz);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                zz[j] = fmaf(c0[j], zz[j], c1[j]);
+                s1[j] += zz[j];
+            }
+            dz8[off] = pack8(zz);
+        }
+    }
     if (APPLY) {
         if (dbsum != nullptr) {        // conv bias gradient = sum of dz over the view-call (block-uniform branch)
             __shared__ float redb[8][8];
@@ -312,7 +335,7 @@ dim3 tile_grid(int N, int n_per_view, int C, int H, int W) {
 int check_shape(const char* what, int N, int n_per_view, int C, int H, int W) {
     B200_REQUIRE(N > 0 && n_per_view > 0 && N % n_per_view == 0, -2, "%s: N=%d must be a multiple of n_per_view=%d", what, N, n_per_view);
     B200_REQUIRE(C % 8 == 0 && C > 0, -2, "%s: C=%d must be a multiple of 8", what, C);
-    B200_REQUIRE((H & 1) == 0 && (W & 1) == 0 && H > 0 && W > 0, -2, "%s: H=%d, W=%d must be even", what, H, W);
+    B200_REQUIRE(H > 1 && W > 1, -2, "%s: H=%d, W=%d must be at least 2 (odd sizes floor-pool like nn.MaxPool2d)", what, H, W);
     B200_REQUIRE(N / n_per_view <= 65535, -2, "%s: too many view-calls", what);
     return 0;
 }

@@ -94,7 +94,7 @@ struct TcCfg {
     static_assert((SMEM_EST(NMMA, NPADL, SLOTS, SLOT_BYTES, TAIL) + 1024) * CTAS <= 227 * 1024, "shared memory per SM");
     static_assert(2 * SLOTS + 2 * NBUF <= 24, "barrier area");
     static_assert(CIN == 1 || (CIN % 8 == 0 && (CIN == 8 || CIN % 16 == 0)), "C_in must be 1, 8 or a multiple of 16");
-    static_assert(NPAD % 16 == 0 && NPAD >= 16 && NPAD <= 64 && COUT <= NPAD && COUT % 8 == 0, "N tile");
+    static_assert(NPAD % 16 == 0 && NPAD >= 16 && NPADL <= 64 && COUT <= NPAD && COUT % 8 == 0, "N tile");
     static_assert(HO % BANDS == 0, "bands must divide the output height");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
     static_assert(P * PLANE_BYTES < (1 << 18) && PLANE_BYTES % 16 == 0, "descriptor range");
@@ -657,6 +657,7 @@ using WgS1 = TcWgCfg<32, 64, 14, 14, 3, 1, 1, 3, 2>;
 using WgA0 = TcWgCfg<1, 8, 112, 112, 5, 2, 7, 1, 1, 3>;   // first layers (shift8 image)
 using WgI0 = TcWgCfg<1, 32, 28, 28, 5, 2, 1, 3, 1>;
 using WgS0 = TcWgCfg<1, 32, 28, 28, 3, 1, 1, 3, 1>;
+using WgS2 = TcWgCfg<64, 128, 7, 7, 3, 1, 1, 3, 4, 1, 2>;
 
 //                         CIN COUT NPAD HIN  WIN KS PAD BANDS SLOTS
 using CfgA1 = TcCfg<8, 16, 16, 56, 56, 5, 2, 2, 2, 3>;   // audio conv2 forward
@@ -670,6 +671,8 @@ using CfgI1d = TcCfg<64, 32, 32, 10, 10, 5, 4, 1, 2>;
 using CfgA0 = TcCfg<1, 8, 16, 112, 112, 5, 2, 8, 2, 3>;  // first layers on the shift8 image: audio conv1
 using CfgI0 = TcCfg<1, 32, 32, 28, 28, 5, 2, 1, 4>;      //   image conv1
 using CfgS0 = TcCfg<1, 32, 32, 28, 28, 3, 1, 1, 4>;      //   image_simple conv1
+using CfgS2 = TcCfg<64, 128, 128, 7, 7, 3, 1, 1, 3, 2, 2>;   // image_simple conv3 forward (two 64-channel slices) / data gradient
+using CfgS2d = TcCfg<128, 64, 64, 7, 7, 3, 1, 1, 2, 1, 1>;
 using CfgS1 = TcCfg<32, 64, 64, 14, 14, 3, 1, 1, 4>;     // image_simple conv2 forward / its data gradient
 using CfgS1d = TcCfg<64, 32, 32, 14, 14, 3, 1, 1, 4>;
 
@@ -683,7 +686,7 @@ extern "C" {
 int b200_conv_tc_supported(int Cin, int Cout, int H, int W, int K, int pad) {
 #define TC_MATCH(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) return 1;
     TC_MATCH(CfgA1) TC_MATCH(CfgA2) TC_MATCH(CfgA3) TC_MATCH(CfgI1) TC_MATCH(CfgA1d) TC_MATCH(CfgA2d) TC_MATCH(CfgA3d) TC_MATCH(CfgI1d)
-    TC_MATCH(CfgS1) TC_MATCH(CfgS1d) TC_MATCH(CfgA0) TC_MATCH(CfgI0) TC_MATCH(CfgS0)
+    TC_MATCH(CfgS1) TC_MATCH(CfgS1d) TC_MATCH(CfgA0) TC_MATCH(CfgI0) TC_MATCH(CfgS0) TC_MATCH(CfgS2) TC_MATCH(CfgS2d)
 #undef TC_MATCH
     return 0;
 }
@@ -698,7 +701,7 @@ int b200_conv_tc_prep_weights(const float* w, void* out, int Cin, int Cout, int 
     B200_REQUIRE(w && out, -1, "conv_tc_prep_weights: null pointer");
     B200_REQUIRE(Cin == 1 || Cin == 8 || (Cin % 16 == 0 && Cin > 0), -2, "conv_tc_prep_weights: C_in must be 1, 8 or a multiple of 16 (got %d)", Cin);
     B200_REQUIRE(!(Cin == 1 && flip), -2, "conv_tc_prep_weights: the first layer has no data gradient");
-    B200_REQUIRE(Cout % 8 == 0 && Cout > 0 && Cout <= 64, -2, "conv_tc_prep_weights: C_out must be a multiple of 8, <= 64 (got %d)", Cout);
+    B200_REQUIRE(Cout % 8 == 0 && Cout > 0 && Cout <= 128, -2, "conv_tc_prep_weights: C_out must be a multiple of 8, <= 128 (got %d)", Cout);
     const int npad = (Cout + 15) / 16 * 16;
     const int total = (int)(b200_conv_tc_weight_bytes(Cin, Cout, K) / 2);
     conv_tc_prep_weights_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(out), Cin, Cout, npad, K,
@@ -710,7 +713,7 @@ static int wgrad_tc_dispatch(const void* x, const void* dz, float* dw, float* wo
                              int K, int pad, cudaStream_t st, int64_t* need) {
 #define WG_RUN(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) \
         return launch_conv_tc_wgrad<CFG>(x, dz, dw, work, N, st, need);
-    WG_RUN(WgA1) WG_RUN(WgA2) WG_RUN(WgA3) WG_RUN(WgI1) WG_RUN(WgS1) WG_RUN(WgA0) WG_RUN(WgI0) WG_RUN(WgS0)
+    WG_RUN(WgA1) WG_RUN(WgA2) WG_RUN(WgA3) WG_RUN(WgI1) WG_RUN(WgS1) WG_RUN(WgA0) WG_RUN(WgI0) WG_RUN(WgS0) WG_RUN(WgS2)
 #undef WG_RUN
     set_error("conv_tc_wgrad: unsupported geometry Cin=%d Cout=%d H=%d W=%d K=%d pad=%d", Cin, Cout, H, W, K, pad);
     return -4;
@@ -754,7 +757,7 @@ int b200_conv_tc(const void* x_act8, const void* wprep, const float* bias, void*
     cudaStream_t st = as_stream(stream);
 #define TC_RUN(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) \
         return launch_conv_tc<CFG>(x_act8, wprep, bias, out, stats, N, n_per_view, out_bf16, st);
-    TC_RUN(CfgA1) TC_RUN(CfgA2) TC_RUN(CfgA3) TC_RUN(CfgI1) TC_RUN(CfgA1d) TC_RUN(CfgA2d) TC_RUN(CfgA3d) TC_RUN(CfgI1d) TC_RUN(CfgS1) TC_RUN(CfgS1d) TC_RUN(CfgA0) TC_RUN(CfgI0) TC_RUN(CfgS0)
+    TC_RUN(CfgA1) TC_RUN(CfgA2) TC_RUN(CfgA3) TC_RUN(CfgI1) TC_RUN(CfgA1d) TC_RUN(CfgA2d) TC_RUN(CfgA3d) TC_RUN(CfgI1d) TC_RUN(CfgS1) TC_RUN(CfgS1d) TC_RUN(CfgA0) TC_RUN(CfgI0) TC_RUN(CfgS0) TC_RUN(CfgS2) TC_RUN(CfgS2d)
 #undef TC_RUN
     set_error("conv_tc: unsupported geometry Cin=%d Cout=%d H=%d W=%d K=%d pad=%d", Cin, Cout, H, W, K, pad);
     return -4;

@@ -10,7 +10,8 @@ from multimodal_ssl_avmnist_b200 import ops
 
 DEV = "cuda"
 # (Cin, Cout, H, W, K, pad) forward geometries of the encoders (models/unimodal.py:129-140, 186-208; dino.py:20-30)
-FWD = [(8, 16, 56, 56, 5, 2), (16, 32, 28, 28, 5, 2), (32, 64, 14, 14, 5, 2), (32, 64, 14, 14, 5, 0), (32, 64, 14, 14, 3, 1)]
+FWD = [(8, 16, 56, 56, 5, 2), (16, 32, 28, 28, 5, 2), (32, 64, 14, 14, 5, 2), (32, 64, 14, 14, 5, 0), (32, 64, 14, 14, 3, 1),
+       (64, 128, 7, 7, 3, 1)]
 
 
 def _bf(x):
@@ -120,7 +121,7 @@ def _pack8(x):
 
 
 @pytest.mark.parametrize("zdt", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("C,H,views,B", [(16, 56, 2, 3), (32, 28, 3, 5), (64, 14, 7, 9), (64, 10, 1, 40), (8, 112, 2, 2)])
+@pytest.mark.parametrize("C,H,views,B", [(16, 56, 2, 3), (32, 28, 3, 5), (64, 14, 7, 9), (64, 10, 1, 40), (8, 112, 2, 2), (128, 7, 3, 5)])
 def test_bn_relu_pool8(C, H, views, B, zdt):
     """act8 BN-apply/ReLU/pool forward and backward against a torch fp32 restatement on the same bf16 z / dp."""
     g = torch.Generator().manual_seed(C + H)

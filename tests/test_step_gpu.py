@@ -212,7 +212,7 @@ def test_step_bf16_tensor_core_path_vs_oracle(mode, golden):
 
 def test_unimodal_image_simple_bf16_runs():
     eng = DinoStepEngine(kind="image_simple", device=DEV, precision="bf16")
-    assert eng.tc["img"] == [True, True, False]
+    assert eng.tc["img"] == [True, True, True]
     e32 = DinoStepEngine(kind="image_simple", device=DEV, precision="fp32")
     e32.student.flat.copy_(eng.student.flat)
     e32.sync_teacher()
