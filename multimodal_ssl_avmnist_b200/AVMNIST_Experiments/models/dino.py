@@ -312,6 +312,47 @@ class UniModalDINO(_DinoBase):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# Downstream models (reference models/dino.py:1764-1850): frozen-encoder features through the CUDA encoder forward
+# ------------------------------------------------------------------------------------------------------------
+class FeatureExtractor(nn.Module):
+    """Frozen student-encoder features of un-augmented batches.  The reference deep-copies the encoder; here the features
+    come from the live student weights through DinoStepEngine.encode_features (identical while nothing trains in between).
+    train()/eval() select BatchNorm batch / running statistics exactly like the copy's mode would."""
+
+    def __init__(self, pretrained_model, is_dino_based=True):
+        super().__init__()
+        if not is_dino_based or not hasattr(pretrained_model, "_b200"):
+            raise NotImplementedError("only DINO models with a compiled B200 step have a CUDA feature path")
+        self._dino = [pretrained_model]                      # not registered: the encoder stays owned by the DINO model
+        self.is_unimodal = hasattr(pretrained_model.student, "modality")
+        self.modality = getattr(pretrained_model.student, "modality", None)
+        self.output_dim = pretrained_model.student.output_dim
+
+    @torch.no_grad()
+    def forward(self, images, spectrograms=None):
+        dino = self._dino[0]
+        eng = dino._b200.ensure(dino.center.device)
+        img = images.to(eng.device).reshape(-1, 28, 28).contiguous()
+        aud = None if (self.is_unimodal or spectrograms is None) else spectrograms.to(eng.device).reshape(-1, 112, 112).contiguous()
+        return eng.encode_features(img, aud, train=self.training).clone()
+
+
+class DownstreamClassifier(nn.Module):
+    """Frozen encoder + Linear(output_dim, 128) -> ReLU -> Linear(128, num_classes) (reference models/dino.py:1764-1815)."""
+
+    def __init__(self, pretrained_model, num_classes=10, trainable_encoder=False, is_dino_based=True):
+        super().__init__()
+        if trainable_encoder:
+            raise NotImplementedError("fine-tuning the encoder through the probe is outside the B200 hot-path scope")
+        self.encoder = FeatureExtractor(pretrained_model, is_dino_based=is_dino_based)
+        self.is_unimodal, self.modality = self.encoder.is_unimodal, self.encoder.modality
+        self.classifier = nn.Sequential(nn.Linear(self.encoder.output_dim, 128), nn.ReLU(), nn.Linear(128, num_classes))
+
+    def forward(self, images, spectrograms=None):
+        return self.classifier(self.encoder(images, spectrograms))
+
+
+# ------------------------------------------------------------------------------------------------------------
 # Lightning modules
 # ------------------------------------------------------------------------------------------------------------
 class _DinoLightningBase(pl.LightningModule):
@@ -339,9 +380,46 @@ class _DinoLightningBase(pl.LightningModule):
         sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=self.num_epochs)
         return {"optimizer": opt, "lr_scheduler": {"scheduler": sched}}
 
+    def probe_accuracy(self, train_loader, val_loader, max_batches=None):
+        """The reference's per-epoch linear probe (models/dino.py:878-951): a fresh 2-layer MLP on frozen student features,
+        one epoch of AdamW(lr) on train-mode features, then accuracy on eval-mode features.  Returns (val_loss, mlp_acc %).
+        The encoder forward runs on the CUDA kernels; the 33k-parameter probe itself is plain torch."""
+        dev = self.model.center.device
+        probe = DownstreamClassifier(self.model, trainable_encoder=False).to(dev)
+        opt = torch.optim.AdamW(probe.classifier.parameters(), lr=self.learning_rate)
+        crit = nn.CrossEntropyLoss()
+        probe.train()
+        total, nb = 0.0, 0
+        for bi, batch in enumerate(train_loader):
+            if max_batches is not None and bi >= max_batches:
+                break
+            images, audios, labels = batch[0].to(dev), batch[1].to(dev), batch[2].to(dev)
+            opt.zero_grad()
+            loss = crit(probe(images, audios), labels)
+            loss.backward()
+            opt.step()
+            total, nb = total + float(loss), nb + 1
+        probe.eval()
+        correct = count = 0
+        with torch.no_grad():
+            for bi, batch in enumerate(val_loader):
+                if max_batches is not None and bi >= max_batches:
+                    break
+                images, audios, labels = batch[0].to(dev), batch[1].to(dev), batch[2].to(dev)
+                correct += int((probe(images, audios).argmax(1) == labels).sum())
+                count += int(labels.numel())
+        return total / max(nb, 1), 100.0 * correct / max(count, 1)
+
     def on_train_epoch_end(self):
-        """The reference trains a linear probe here to log `mlp_acc` (models/dino.py:878-951); evaluation is outside the
-        hot-path scope, so only the epoch's training loss is available as a checkpoint metric."""
+        """Logs `val_loss` / `mlp_acc` like the reference (models/dino.py:878-951) when the trainer's data module provides
+        labelled loaders (`probe_dataloaders()` -> (train, val)); otherwise only the training loss is available."""
+        dm = getattr(getattr(self, "trainer", None), "datamodule", None)
+        get = getattr(dm, "probe_dataloaders", None)
+        if get is None:
+            return None
+        val_loss, acc = self.probe_accuracy(*get())
+        self.log("val_loss", val_loss)
+        self.log("mlp_acc", acc, on_epoch=True, prog_bar=True)
         return None
 
 

@@ -284,6 +284,20 @@ class AVMNISTDinoDataModule(BaseAVMNISTDataModule):
     def get_view_config(self):
         return {"n_global_views": self.n_global_views, "n_local_views": self.n_local_views}
 
+    def probe_dataloaders(self):
+        """Labelled (image, audio, label) loaders over the train / validation subsets for the per-epoch linear probe."""
+        def labelled(sub):
+            ds = AVMNISTDataset.__new__(AVMNISTDataset)
+            ds.__dict__.update(sub.dataset.__dict__)
+            return torch.utils.data.Subset(ds, sub.indices)
+
+        def collate(items):
+            img = torch.tensor(np.stack([i[0] for i in items]), dtype=torch.float32)
+            aud = torch.tensor(np.stack([i[1] for i in items]), dtype=torch.float32)
+            return img, aud, torch.stack([i[2] for i in items])
+        mk = lambda sub, sh: DataLoader(labelled(sub), batch_size=self.batch_size, shuffle=sh, num_workers=0, collate_fn=collate)
+        return mk(self.train_dataset, True), mk(self.val_dataset, False)
+
     def train_dataloader(self):
         if self.device_resident and self.device_augmentation and torch.cuda.is_available():
             sub = self.train_dataset

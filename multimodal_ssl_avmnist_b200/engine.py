@@ -222,6 +222,7 @@ class DinoStepEngine:
         self._wgrad_streams = {m: torch.cuda.Stream(device=self.device) for m in ("img", "aud")}
         self._aug_stream = torch.cuda.Stream(device=self.device)
         self._prefetch, self._step_done, self._step_done_prev = None, None, None
+        self._eval_wrole = "s"
         self._ws = {}
         self._init_parameters()
         self.set_augmentation(augment_values)
@@ -482,13 +483,14 @@ class DinoStepEngine:
             tc = self.tc[mod][li]
             next_tc = li + 1 < len(layers) and self.tc[mod][li + 1]
             stats.zero_()
+            wrole = role if role in ("s", "t") else self._eval_wrole      # the evaluation role "e" borrows a role's weight images
             if tc and ci == 1:
                 xs8 = w[f"{mod}.xs8"]
                 if role == "s" and not w.get("packed", False):
                     ops.pack_shift8(cur.view(N, hw, hw), xs8, pad)
-                ops.conv_tc(xs8[:N], self._tcw[(role, mod, li)], P["enc." + conv + ".bias"], z, stats, B, co, k, pad)
+                ops.conv_tc(xs8[:N], self._tcw[(wrole, mod, li)], P["enc." + conv + ".bias"], z, stats, B, co, k, pad)
             elif tc:
-                ops.conv_tc(cur, self._tcw[(role, mod, li)], P["enc." + conv + ".bias"], z, stats, B, co, k, pad)
+                ops.conv_tc(cur, self._tcw[(wrole, mod, li)], P["enc." + conv + ".bias"], z, stats, B, co, k, pad)
             else:
                 ops.conv_fwd(cur.view(N, ci, hw, hw), P["enc." + conv + ".weight"], P["enc." + conv + ".bias"], z, stats, B, pad)
             b = bns["enc." + bn]
@@ -531,7 +533,7 @@ class DinoStepEngine:
         ops.linear_bwd_weight(d_hh, x, G[prefix + "mlp.0.weight"], G[prefix + "mlp.0.bias"], tc=self.lin_tc)
         ops.linear_bwd_data(d_hh, S[prefix + "mlp.0.weight"], d_x, tc=self.lin_tc)
 
-    def _encode(self, w, role, P, bns, x_img, x_aud, N, B, n_fusion, fmask):
+    def _encode(self, w, role, P, bns, x_img, x_aud, N, B, n_fusion, fmask, train=True):
         """Encoder forward for N = n_views*B samples; fusion only over the first n_fusion rows."""
         if self.kind == "multi_central":
             E = self.E
@@ -542,17 +544,20 @@ class DinoStepEngine:
             if side is not None:
                 side.wait_stream(main)
             with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
-                pi = self._conv_stack(w, role, "img", self.img_layers, x_img, N, B, P, bns)
+                pi = self._conv_stack(w, role, "img", self.img_layers, x_img, N, B, P, bns, train=train)
                 ops.linear_fwd(pi.view(N, 1600), P["enc.image_encoder.1.weight"], P["enc.image_encoder.1.bias"], cat[:, :E], tc=self.lin_tc)
-            pa = self._conv_stack(w, role, "aud", self.aud_layers, x_aud, N, B, P, bns)
+            pa = self._conv_stack(w, role, "aud", self.aud_layers, x_aud, N, B, P, bns, train=train)
             if side is not None:
                 main.wait_stream(side)
             ops.linear_fwd(pa.view(N, 3136), P["enc.audio_encoder.1.weight"], P["enc.audio_encoder.1.bias"], cat[:, E:], tc=self.lin_tc)
             h1, feat = w[f"{role}.h1"], w[f"{role}.feat"]
-            ops.linear_fwd(cat[:n_fusion], P["enc.fusion.0.weight"], P["enc.fusion.0.bias"], h1, act=2, mask=fmask, drop_p=self.fusion_dropout, tc=self.lin_tc)
+            if fmask is None:        # evaluation mode: no dropout
+                ops.linear_fwd(cat[:n_fusion], P["enc.fusion.0.weight"], P["enc.fusion.0.bias"], h1, act=1, tc=self.lin_tc)
+            else:
+                ops.linear_fwd(cat[:n_fusion], P["enc.fusion.0.weight"], P["enc.fusion.0.bias"], h1, act=2, mask=fmask, drop_p=self.fusion_dropout, tc=self.lin_tc)
             ops.linear_fwd(h1, P["enc.fusion.3.weight"], P["enc.fusion.3.bias"], feat, tc=self.lin_tc)
             return feat
-        pi = self._conv_stack(w, role, "img", self.img_layers, x_img, N, B, P, bns)      # [N,128,3,3]
+        pi = self._conv_stack(w, role, "img", self.img_layers, x_img, N, B, P, bns, train=train)      # [N,128,3,3]
         ops.avgpool_fwd(pi, w[f"{role}.pool"])
         ops.linear_fwd(w[f"{role}.pool"], P["enc.encoder.14.weight"], P["enc.encoder.14.bias"], w[f"{role}.e14"], tc=self.lin_tc)
         ops.linear_fwd(w[f"{role}.e14"], P["enc.projection.0.weight"], P["enc.projection.0.bias"], w[f"{role}.feat"], tc=self.lin_tc)
@@ -623,6 +628,79 @@ class DinoStepEngine:
                 d_p = d_in
         if wside is not None:
             main.wait_stream(wside)
+
+    # ------------------------------------------------------------------------------------------------------
+    # evaluation-side encoder forward (linear-probe / kNN features; models/dino.py:1764-1850)
+    # ------------------------------------------------------------------------------------------------------
+    def _eval_workspace(self, B):
+        key = ("eval", B)
+        if key in self._ws:
+            return self._ws[key]
+        dev, BF = self.device, torch.bfloat16
+        w = {"B": B}
+
+        def e(*shape, dtype=F32):
+            return torch.empty(*shape, dtype=dtype, device=dev)
+
+        w["x_img"] = e(B, 1, 28, 28)
+        if self.aud_layers:
+            w["x_aud"] = e(B, 1, 112, 112)
+        for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers)):
+            for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers):
+                ho = hw + 2 * pad - k + 1
+                tc = self.tc[mod][li]
+                next_tc = li + 1 < len(layers) and self.tc[mod][li + 1]
+                if tc and ci == 1:
+                    w[f"{mod}.xs8"] = e(B, hw, hw + pad, 8, dtype=BF)
+                w[f"e.{mod}.z{li}"] = e(B, co // 8, ho, ho, 8, dtype=torch.float16) if tc else e(B, co, ho, ho)
+                if next_tc:
+                    w[f"e.{mod}.p8{li}"] = e(B, co // 8, ho // 2, ho // 2, 8, dtype=BF)
+                if not next_tc or not tc:
+                    w[f"e.{mod}.p{li}"] = e(B, co, ho // 2, ho // 2)
+                w[f"e.{mod}.stats{li}"] = torch.zeros(1, co, 2, dtype=torch.float64, device=dev)
+                for nm in ("scale", "shift", "mean", "invstd"):
+                    w[f"e.{mod}.{nm}{li}"] = e(1, co)
+        E, O = self.E, self.O
+        if self.kind == "multi_central":
+            w["e.cat"], w["e.h1"], w["e.feat"] = e(B, 2 * E), e(B, E), e(B, O)
+            w["e.fmask"] = torch.ones(B, E, dtype=torch.uint8, device=dev)
+        else:
+            w["e.pool"], w["e.e14"], w["e.feat"] = e(B, 128), e(B, 512), e(B, O)
+        self._ws[key] = w
+        return w
+
+    @torch.no_grad()
+    def encode_features(self, images, audios=None, train=False, teacher=False):
+        """Encoder features [B, O] of an UN-augmented batch (images [B,28,28] fp32 in [0,1] or uint8, audios [B,112,112] fp32 in
+        [0,1] or uint8), as DownstreamClassifier / FeatureExtractor of the reference use them (models/dino.py:1764-1850).
+        train=False: BatchNorm with the running statistics, no dropout (module.eval()); train=True: batch statistics and an
+        active fusion dropout, like the reference's probe training on a train()-mode copy -- the copy's running statistics are
+        scratch, the live ones are never touched."""
+        B = images.shape[0]
+        w = self._eval_workspace(B)
+        P = self.T if teacher else self.S
+        bns = self.bn_t if teacher else self.bn_s
+        if train:       # scratch running statistics
+            bns = {k: _BN(v.C, self.device) for k, v in bns.items()}
+        xi = w["x_img"]
+        xi.copy_((images.float() / 255.0 if images.dtype == torch.uint8 else images).reshape(B, 1, 28, 28))
+        xa = None
+        if self.aud_layers:
+            xa = w["x_aud"]
+            xa.copy_((audios.float() / 255.0 if audios.dtype == torch.uint8 else audios).reshape(B, 1, 112, 112))
+        w["packed"] = False
+        if self._tcw:
+            self._prep_tc_weights("t" if teacher else "s", P)
+        for mod, layers, x in (("img", self.img_layers, xi), ("aud", self.aud_layers, xa)):
+            if layers and self.tc[mod][0]:
+                ops.pack_shift8(x.view(B, layers[0][4], layers[0][4]), w[f"{mod}.xs8"], layers[0][6])
+        w["packed"] = True
+        fmask = None
+        if train and self.kind == "multi_central" and self.fusion_dropout > 0:
+            fmask = w["e.fmask"]
+            ops.dropout_mask(fmask, self.fusion_dropout, self.seed + 17, self.rng_step * 4 + 3)
+        self._eval_wrole = "t" if teacher else "s"
+        return self._encode(w, "e", P, bns, xi, xa, B, B, B, fmask, train=train)
 
     # ------------------------------------------------------------------------------------------------------
     # the step

@@ -250,6 +250,7 @@ class Trainer:
     def fit(self, model, datamodule=None, train_dataloaders=None):
         self.model = model
         model._trainer = self
+        self.datamodule = datamodule
         self._pending_step, self._pending_epoch = {}, {}
         if datamodule is not None:
             datamodule.prepare_data()

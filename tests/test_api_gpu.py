@@ -159,3 +159,39 @@ def test_device_resident_loader_feeds_the_step(tmp_path):
         opt.step()
     torch.cuda.synchronize()
     assert 3.0 < float(loss) < 12.0
+
+
+def test_feature_path_and_linear_probe(tmp_path):
+    """eval-mode encoder features through the CUDA kernels match the fp32 oracle encoder on the same weights
+    (running statistics), train-mode features use batch statistics, and the per-epoch probe logs mlp_acc through Trainer.fit."""
+    from oracle import dino_ref as R
+    from _compat import pl, CSVLogger
+    torch.manual_seed(3)
+    lit = md.MultiModalDINOLightning(**KW).to(DEV)
+    B = 16
+    loss = lit.training_step(_batch("default", B, 90), 0)        # one step so that the running statistics are not the initial ones
+    fx = md.FeatureExtractor(lit.model).eval()
+    image, audio, _ = synth_raw(B, seed=91)
+    feats = fx(image.to(DEV), audio.to(DEV))
+    assert feats.shape == (B, 256) and torch.isfinite(feats).all()
+    # oracle: eval-mode CentralMultiModalEncoder with the same parameters and buffers
+    sd = {k: v.detach().cpu().float() for k, v in lit.model.student.state_dict().items()}
+    p = {k: v for k, v in sd.items() if "running" not in k and "num_batches" not in k}
+    buf = {k: v for k, v in sd.items() if "running" in k or "num_batches" in k}
+    fi = R.central_image_features(image, p, buf, train=False)
+    fa = R.central_audio_features(audio, p, buf, train=False)
+    h = torch.relu(torch.cat([fi, fa], 1) @ p["fusion.0.weight"].t() + p["fusion.0.bias"])
+    want = h @ p["fusion.3.weight"].t() + p["fusion.3.bias"]
+    assert float((feats.cpu() - want).abs().max()) < 3e-2 * float(want.abs().max())
+    ftrain = md.FeatureExtractor(lit.model).train()(image.to(DEV), audio.to(DEV))
+    assert float((ftrain - feats).abs().max()) > 1e-3            # batch statistics + dropout differ from the eval path
+    sd2 = lit.model.student.state_dict()
+    assert all(torch.equal(sd2[k].cpu().float(), sd[k]) for k in sd if "running" in k), "feature passes must not touch the running statistics"
+    # the probe through the trainer
+    d = str(tmp_path) + "/"
+    gd.write_synthetic_avmnist(d, n_train=64, n_test=16)
+    dm = gd.AVMNISTDinoDataModule(data_dir=d, batch_size=16, num_workers=0, type="burst_noise")
+    lit2 = md.MultiModalDINOLightning(**dict(KW, data_dir=d))
+    tr = pl.Trainer(max_epochs=1, logger=CSVLogger(str(tmp_path), name="logs"), log_every_n_steps=1, devices=1, accelerator="gpu")
+    tr.fit(lit2, datamodule=dm)
+    assert "mlp_acc" in tr.callback_metrics and 0.0 <= float(tr.callback_metrics["mlp_acc"]) <= 100.0
