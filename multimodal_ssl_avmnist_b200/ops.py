@@ -464,12 +464,17 @@ def stop_profile():
     return rec
 
 
+# tensor-core variants of the linear / InfoNCE wrappers issue more kernels (transposes, split-K and partial-sum reductions)
+_LAUNCHES_TC = {"linear_bwd_weight": 6, "linear_bwd_data": 2, "infonce_fwd_bwd": 19}
+
+
 def _wrap(name, fn):
     n_launch = _LAUNCHES.get(name, 1)
+    n_launch_tc = _LAUNCHES_TC.get(name, n_launch)
 
     def wrapped(*args, **kwargs):
         global LAUNCH_COUNT
-        LAUNCH_COUNT += n_launch
+        LAUNCH_COUNT += n_launch_tc if kwargs.get("tc") else n_launch
         if _PROFILE is None:
             return fn(*args, **kwargs)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
