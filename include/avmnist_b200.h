@@ -162,6 +162,14 @@ int64_t b200_conv_tc_wgrad_work_floats(int N, int Cin, int Cout, int H, int W, i
 int b200_conv_tc_wgrad(const void* x_act8, const void* dz_act8, float* dw, float* work, int N, int Cin, int Cout, int H,
                        int W, int K, int pad, void* stream);
 int b200_pack_shift8(const float* x, void* out, int N, int H, int W, int pad, void* stream);
+/* First layers, fused backward: b200_bn_relu_pool8_bwd_apply + b200_conv_tc_wgrad in one kernel (the first layer needs no data
+ * gradient, so dz never has to exist in HBM): z8 fp16 act8 [N][Cout/8][H][W][8], dp8 bf16 act8 [N][Cout/8][H/2][W/2][8],
+ * scale/shift/mean/invstd [views][Cout], sums double [views][Cout][2] (from b200_bn_pool8_bwd_reduce_p) -> dw [Cout][1][K][K],
+ * dbsum double [Cout] += sum(dz) (may be NULL).  work: float[b200_conv_tc_wgrad_l0_fused_work_floats(...)], 16-byte aligned. */
+int64_t b200_conv_tc_wgrad_l0_fused_work_floats(int N, int n_per_view, int Cout, int H, int W, int K, int pad);
+int b200_conv_tc_wgrad_l0_fused(const void* x_shift8, const void* z8, const void* dp8, const float* scale, const float* shift,
+                                const float* mean, const float* invstd, const double* sums, float* dw, double* dbsum,
+                                float* work, int N, int n_per_view, int Cout, int H, int W, int K, int pad, void* stream);
 /* BatchNorm-apply + ReLU + MaxPool2 on bf16 act8 activations (same reference call sites as b200_bn_relu_pool_*):
  *   z8 [N][C/8][H][W][8] bf16 (z_f16 = 0) or fp16 (z_f16 = 1) (H, W even); scale/shift/mean/invstd [views][C] from b200_bn_finalize;
  *   out_fmt / dp_fmt: 0 = fp32 NCHW [N][C][H/2][W/2], 1 = bf16 act8 [N][C/8][H/2][W/2][8];

@@ -188,6 +188,9 @@ class _DinoBase(nn.Module):
                   teacher_temperature=self.teacher_temperature, n_global_views=self.n_global_views, n_local_views=self.n_local_views)
         if hasattr(self, "encoder_output_dim"):
             hp["encoder_output_dim"] = self.encoder_output_dim
+        # use_mixed_precision (the reference trains with precision='16-mixed', run_dino.py:360) selects the tensor-core path
+        # (bf16 / fp16 activations, tf32 linears, fp32 accumulation); False runs the exact fp32 kernels
+        hp["precision"] = "bf16" if getattr(self, "use_mixed_precision", True) else "fp32"
         return hp
 
     @property
@@ -370,6 +373,7 @@ class _DinoLightningBase(pl.LightningModule):
     def _sync_hparams(self):
         m = self.model
         m.student_temperature, m.teacher_temperature = self.student_temperature, self.teacher_temperature
+        m.use_mixed_precision = bool(getattr(self, "use_mixed_precision", True))
         if m.engine is not None:
             m.engine.tau_s, m.engine.tau_t = self.student_temperature, self.teacher_temperature
 
@@ -435,7 +439,7 @@ class MultiModalDINOLightning(_DinoLightningBase):
         self.output_dim, self.encoder_output_dim, self.projection_dim = output_dim, encoder_output_dim, projection_dim
         self.learning_rate, self.weight_decay, self.num_epochs = learning_rate, weight_decay, num_epochs
         self.student_temperature, self.teacher_temperature = student_temperature, teacher_temperature
-        self.use_mixed_precision = use_mixed_precision          # kept for signature compatibility: the step computes in fp32
+        self.use_mixed_precision = use_mixed_precision          # True: tensor-core path (bf16/fp16/tf32 operands); False: exact fp32 kernels
         self.momentum, self.center_momentum, self.dropout = momentum, center_momentum, dropout
         self.data_dir, self.data_augmentation = data_dir, data_augmentation
         if dino_model is None:

@@ -648,6 +648,278 @@ int launch_conv_tc_wgrad(const void* x, const void* dz, float* dw, float* work, 
     return launch_status("wgrad_reduce_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// First layer, fused backward: BatchNorm-apply / ReLU / max-pool backward + weight gradient in ONE kernel.  The first layer
+// needs no data gradient, so its dz (the largest tensor of the backward pass) has a single consumer: instead of writing it
+// to HBM and reading it back, the pre-BatchNorm z tile (fp16 act8) is TMA-loaded straight into the position of the dz MMA
+// operand (padded pitch, zero-filled junk columns), four warps transform it IN PLACE into dz = ca*z + cb + [arg-max] a*g
+// (bf16) from the pooled gradient tile, fence it to the async proxy, and the MMA warp accumulates dW exactly as in
+// conv_tc_wgrad_kernel.  The same warps accumulate the conv bias gradient sum(dz).
+//   cst: per (view, channel) constants float4 {a, b, ca, cb} prepared by wgrad_l0_consts_kernel from the BatchNorm tensors.
+template <class C>
+__global__ void __launch_bounds__(192, C::CTAS)
+conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_z,
+                              const __grid_constant__ CUtensorMap tmap_g, const float4* __restrict__ cst, float* __restrict__ work,
+                              double* __restrict__ dbsum, int N, int n_per_view) {
+    static_assert(C::L0 && C::PSPLIT == 1 && C::NSPLIT == 1 && (C::HB % 2) == 0 && (C::WO % 2) == 0, "first-layer geometry");
+    constexpr int HBP = C::HB / 2, WOP = C::WO / 2;                      // pooled rows / columns of a band
+    constexpr int G_BYTES = round_up(C::P_OUT * HBP * WOP * 16, 128);    // pooled-gradient tile
+    constexpr int SLOT = C::X_BYTES + C::Z_BYTES + G_BYTES;
+    constexpr int CST_OFF = C::SLOTS * SLOT, BAR_OFF = CST_OFF + C::COUT * 16 + C::COUT * 4;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float4* cst_s = reinterpret_cast<float4*>(smem + CST_OFF);
+    float* db_s = reinterpret_cast<float*>(smem + CST_OFF + C::COUT * 16);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);        // full[S], ready[S], empty[S], done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 200);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = gridDim.x, g = blockIdx.x;
+    const long items = (long)N * C::BANDS;
+    const int i0 = (int)(items * g / G), i1 = (int)(items * (g + 1) / G);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto ready_bar = [&](int s) { return bar0 + 8u * (C::SLOTS + s); };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (2 * C::SLOTS + s); };
+    const uint32_t done_bar = bar0 + 8u * (3 * C::SLOTS);
+    {
+        uint4* z = reinterpret_cast<uint4*>(smem);
+        for (int i = threadIdx.x; i < CST_OFF / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < C::COUT; i += blockDim.x) db_s[i] = 0.f;
+        fence_proxy_async_smem();
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        prefetch_tmap(&tmap_z);
+        prefetch_tmap(&tmap_g);
+        for (int s = 0; s < C::SLOTS; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(ready_bar(s), 128);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(done_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<C::TMEM_COLS>(smem_u32(tmem_slot));
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem0 = smem_u32(smem);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = i0; i < i1; ++i) {
+                const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
+                mbar_wait(empty_bar(slot), (use & 1) ^ 1);
+                mbar_expect_tx(full_bar(slot), C::PLANE_X + C::P_OUT * C::PLANE_Z + C::P_OUT * HBP * WOP * 16);
+                const int n = i / C::BANDS, band = i % C::BANDS;
+                const uint32_t sa = smem0 + slot * SLOT;
+                tma_load_4d(sa, &tmap_x, full_bar(slot), 0, 0, band * C::HB - C::PAD, n);
+                tma_load_4d(sa + C::X_BYTES, &tmap_z, full_bar(slot), 0, 0, band * C::HB, n * C::P_OUT);
+                tma_load_4d(sa + C::X_BYTES + C::Z_BYTES, &tmap_g, full_bar(slot), 0, 0, band * HBP, n * C::P_OUT);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_bf16(C::COUT, true, true, 64);
+            for (int i = i0; i < i1; ++i) {
+                const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
+                mbar_wait(ready_bar(slot), use & 1);
+                tc_fence_after_sync();
+                const uint32_t xa = smem0 + slot * SLOT, za = xa + C::X_BYTES;
+                for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                    const uint64_t bd = smem_desc(za + ks * 256, 128, C::PLANE_Z);
+                    const uint64_t ad = smem_desc(xa + ks * 256, 128, C::WP * 16);
+                    mma_bf16(tmem_base, ad, bd, idesc, (i > i0 || ks > 0) ? 1u : 0u);
+                }
+                mma_commit(empty_bar(slot));
+            }
+            mma_commit(done_bar);
+        }
+    } else {
+        // ===== transform warps: z -> dz in place (then the end-of-kernel epilogue) =====
+        const int t = threadIdx.x - 64;                                  // 0..127
+        int cur_view = -1;
+        for (int i = i0; i < i1; ++i) {
+            const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
+            const int n = i / C::BANDS, view = n / n_per_view;
+            if (view != cur_view) {                                      // uniform over the four warps
+                asm volatile("bar.sync 1, 128;" ::: "memory");           // nobody still reads the previous view's constants
+                if (t < C::COUT) cst_s[t] = __ldg(cst + (size_t)view * C::COUT + t);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                cur_view = view;
+            }
+            mbar_wait(full_bar(slot), use & 1);
+            uint8_t* zimg = smem + slot * SLOT + C::X_BYTES;
+            const uint4* gimg = reinterpret_cast<const uint4*>(smem + slot * SLOT + C::X_BYTES + C::Z_BYTES);
+#pragma unroll 1
+            for (int o = 0; o < C::P_OUT; ++o) {
+                float4 c4[8];
+                float acc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    c4[j] = cst_s[o * 8 + j];
+                    acc[j] = 0.f;
+                }
+                for (int e = t; e < HBP * WOP; e += 128) {
+                    const int py = e / WOP, px = e - py * WOP;
+                    uint4* zp = reinterpret_cast<uint4*>(zimg + (size_t)o * C::PLANE_Z) + (2 * py) * C::WP + 2 * px;
+                    const uint4 raw[4] = {zp[0], zp[1], zp[C::WP], zp[C::WP + 1]};
+                    const uint4 graw = gimg[o * (HBP * WOP) + e];
+                    uint32_t outw[4][4];
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {                        // channel pairs of the octet
+                        const uint32_t gw = (&graw.x)[h];
+                        float res[4][2];
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const float4 cc = c4[2 * h + half];
+                            float zv[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t zw = (&raw[q].x)[h];
+                                const __half2 hz = *reinterpret_cast<const __half2*>(&zw);
+                                zv[q] = half ? __high2float(hz) : __low2float(hz);
+                            }
+                            const float gv = __uint_as_float(half ? (gw & 0xFFFF0000u) : (gw << 16));
+                            int kk = 0;
+                            float m = fmaf(cc.x, zv[0], cc.y);
+#pragma unroll
+                            for (int q = 1; q < 4; ++q) {
+                                const float y = fmaf(cc.x, zv[q], cc.y);
+                                if (y > m) { m = y; kk = q; }
+                            }
+                            const float ag = (m > 0.f) ? cc.x * gv : 0.f;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                res[q][half] = fmaf(cc.z, zv[q], cc.w) + ((q == kk) ? ag : 0.f);
+                                acc[2 * h + half] += res[q][half];
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) outw[q][h] = pack_bf16(res[q][0], res[q][1]);
+                    }
+                    zp[0] = make_uint4(outw[0][0], outw[0][1], outw[0][2], outw[0][3]);
+                    zp[1] = make_uint4(outw[1][0], outw[1][1], outw[1][2], outw[1][3]);
+                    zp[C::WP] = make_uint4(outw[2][0], outw[2][1], outw[2][2], outw[2][3]);
+                    zp[C::WP + 1] = make_uint4(outw[3][0], outw[3][1], outw[3][2], outw[3][3]);
+                }
+                if (dbsum != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float v = acc[j];
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                        if (lane == 0) atomicAdd(&db_s[o * 8 + j], v);
+                    }
+                }
+            }
+            fence_proxy_async_smem();                                    // generic-proxy writes -> visible to the tensor core
+            mbar_arrive(ready_bar(slot));
+        }
+        // ---- end of kernel: bias-gradient sums and the dW partial of this CTA ----
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (t < C::COUT && dbsum != nullptr) atomicAdd(&dbsum[t], (double)db_s[t]);
+        const int quad = warp & 3;
+        const int m = quad * 16 + (lane & 15), j = m >> 3, ci8 = m & 7;
+        float* part = work + (long)g * C::PART;
+        if (i1 > i0) {
+            mbar_wait(done_bar, 0);
+            tc_fence_after_sync();
+        }
+#pragma unroll
+        for (int cc = 0; cc < (C::COUT + 15) / 16; ++cc) {
+            uint32_t v[16];
+            if (i1 > i0) {
+                tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + cc * 16, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int co = cc * 16 + q;
+                if (co < C::COUT && lane < 16 && j < C::KS && ci8 < C::KS) part[(co * C::KS + j) * C::KS + ci8] = __uint_as_float(v[q]);
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    }
+}
+
+// {a, b, ca, cb} per (view, channel): y = a*z + b decides arg-max / ReLU; dz = ca*z + cb + [arg-max] a*g
+__global__ void wgrad_l0_consts_kernel(const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, const double* __restrict__ sums, float inv_cnt, int n,
+                                       float4* __restrict__ cst) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const float a = scale[c], is = invstd[c], nm = -mean[c] * is;
+    const float k1 = (float)sums[(size_t)c * 2] * inv_cnt, k2 = (float)sums[(size_t)c * 2 + 1] * inv_cnt;
+    cst[c] = make_float4(a, shift[c], -a * is * k2, -a * (k1 + nm * k2));
+}
+
+template <class C>
+int launch_conv_tc_wgrad_l0_fused(const void* x, const void* z, const void* dp, const float* scale, const float* shift, const float* mean,
+                                  const float* invstd, const double* sums, float* dw, double* dbsum, float* work, int N, int n_per_view,
+                                  cudaStream_t st, int64_t* need) {
+    constexpr int HBP = C::HB / 2, WOP = C::WO / 2;
+    constexpr int G_BYTES = round_up(C::P_OUT * HBP * WOP * 16, 128);
+    constexpr int SLOT = C::X_BYTES + C::Z_BYTES + G_BYTES;
+    constexpr int SMEM = C::SLOTS * SLOT + C::COUT * 20 + 256;
+    static_assert((SMEM + 1024) * C::CTAS <= 227 * 1024, "shared memory per SM");
+    const int G = wgrad_ctas<C>(N);
+    const int views = N / n_per_view;
+    const int64_t cst_floats = (int64_t)views * C::COUT * 4;
+    if (need) {
+        *need = (int64_t)G * C::PART + cst_floats + 8;
+        return 0;
+    }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_l0_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) {
+            set_error("conv_tc_wgrad_l0_fused: cannot set %d bytes of shared memory: %s", SMEM, cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured = true;
+    }
+    float4* cst = reinterpret_cast<float4*>(work + (((int64_t)G * C::PART + 3) / 4) * 4);
+    wgrad_l0_consts_kernel<<<(views * C::COUT + 127) / 128, 128, 0, st>>>(scale, shift, mean, invstd, sums,
+                                                                          1.0f / ((float)n_per_view * C::HO * C::WO), views * C::COUT, cst);
+    CUtensorMap tx, tz, tg;
+    {
+        constexpr uint64_t WT = C::WIN + C::PAD;
+        const uint64_t dims[4] = {8, WT, (uint64_t)C::HIN, (uint64_t)N};
+        const uint64_t strides[3] = {16, WT * 16, WT * C::HIN * 16};
+        const uint32_t box[4] = {8, (uint32_t)C::WP, (uint32_t)C::HPB, 1};
+        int rc = encode_tmap_bf16_4d(&tx, x, dims, strides, box);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[4] = {8, (uint64_t)C::WO, (uint64_t)C::HO, (uint64_t)N * C::P_OUT};
+        const uint64_t strides[3] = {16, (uint64_t)C::WO * 16, (uint64_t)C::WO * C::HO * 16};
+        const uint32_t box[4] = {8, (uint32_t)C::WP, (uint32_t)C::HBZ, (uint32_t)C::P_OUT};
+        int rc = encode_tmap_bf16_4d(&tz, z, dims, strides, box);          // fp16 data: same 2-byte elements, no conversion
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[4] = {8, (uint64_t)WOP * 1, (uint64_t)(C::HO / 2), (uint64_t)N * C::P_OUT};
+        const uint64_t strides[3] = {16, (uint64_t)WOP * 16, (uint64_t)WOP * (C::HO / 2) * 16};
+        const uint32_t box[4] = {8, (uint32_t)WOP, (uint32_t)HBP, (uint32_t)C::P_OUT};
+        int rc = encode_tmap_bf16_4d(&tg, dp, dims, strides, box);
+        if (rc) return rc;
+    }
+    conv_tc_wgrad_l0_fused_kernel<C><<<G, 192, SMEM, st>>>(tx, tz, tg, cst, work, dbsum, N, n_per_view);
+    int rc = launch_status("conv_tc_wgrad_l0_fused_kernel");
+    if (rc) return rc;
+    wgrad_reduce_kernel<<<(C::PART + 255) / 256, 256, 0, st>>>(work, G, C::PART, dw);
+    return launch_status("wgrad_reduce_kernel");
+}
+
 //                           CIN COUT HIN WIN KS PAD BANDS SLOTS PSPLIT
 using WgA1 = TcWgCfg<8, 16, 56, 56, 5, 2, 7, 2, 1, 4>;
 using WgA2 = TcWgCfg<16, 32, 28, 28, 5, 2, 1, 1, 2, 2>;
@@ -717,6 +989,41 @@ static int wgrad_tc_dispatch(const void* x, const void* dz, float* dw, float* wo
 #undef WG_RUN
     set_error("conv_tc_wgrad: unsupported geometry Cin=%d Cout=%d H=%d W=%d K=%d pad=%d", Cin, Cout, H, W, K, pad);
     return -4;
+}
+
+// fused first-layer backward (Cin = 1): geometries of the first layers of the three encoders
+using WgF_A0 = TcWgCfg<1, 8, 112, 112, 5, 2, 7, 1, 1, 3>;
+using WgF_I0 = TcWgCfg<1, 32, 28, 28, 5, 2, 1, 1, 1, 2>;
+using WgF_S0 = TcWgCfg<1, 32, 28, 28, 3, 1, 1, 1, 1, 2>;
+
+static int wgrad_l0_dispatch(const void* x, const void* z, const void* dp, const float* scale, const float* shift, const float* mean,
+                             const float* invstd, const double* sums, float* dw, double* dbsum, float* work, int N, int n_per_view, int Cout,
+                             int H, int W, int K, int pad, cudaStream_t st, int64_t* need) {
+#define WF_RUN(CFG) if (Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) \
+        return launch_conv_tc_wgrad_l0_fused<CFG>(x, z, dp, scale, shift, mean, invstd, sums, dw, dbsum, work, N, n_per_view, st, need);
+    WF_RUN(WgF_A0) WF_RUN(WgF_I0) WF_RUN(WgF_S0)
+#undef WF_RUN
+    set_error("conv_tc_wgrad_l0_fused: unsupported geometry Cout=%d H=%d W=%d K=%d pad=%d", Cout, H, W, K, pad);
+    return -4;
+}
+
+int64_t b200_conv_tc_wgrad_l0_fused_work_floats(int N, int n_per_view, int Cout, int H, int W, int K, int pad) {
+    int64_t need = 0;
+    if (N <= 0 || n_per_view <= 0 || N % n_per_view) return -1;
+    int rc = wgrad_l0_dispatch(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, N, n_per_view, Cout, H, W,
+                               K, pad, nullptr, &need);
+    return rc ? -1 : need;
+}
+
+int b200_conv_tc_wgrad_l0_fused(const void* x_shift8, const void* z8, const void* dp8, const float* scale, const float* shift,
+                                const float* mean, const float* invstd, const double* sums, float* dw, double* dbsum, float* work, int N,
+                                int n_per_view, int Cout, int H, int W, int K, int pad, void* stream) {
+    B200_REQUIRE(x_shift8 && z8 && dp8 && scale && shift && mean && invstd && sums && dw && work, -1, "conv_tc_wgrad_l0_fused: null pointer");
+    B200_REQUIRE(N > 0 && n_per_view > 0 && N % n_per_view == 0, -2, "conv_tc_wgrad_l0_fused: N=%d must be a multiple of n_per_view=%d", N, n_per_view);
+    B200_REQUIRE(((reinterpret_cast<uintptr_t>(x_shift8) | reinterpret_cast<uintptr_t>(z8) | reinterpret_cast<uintptr_t>(dp8) |
+                   reinterpret_cast<uintptr_t>(work)) & 15) == 0, -3, "conv_tc_wgrad_l0_fused: pointers must be 16-byte aligned");
+    return wgrad_l0_dispatch(x_shift8, z8, dp8, scale, shift, mean, invstd, sums, dw, dbsum, work, N, n_per_view, Cout, H, W, K, pad,
+                             as_stream(stream), nullptr);
 }
 
 int64_t b200_conv_tc_wgrad_work_floats(int N, int Cin, int Cout, int H, int W, int K, int pad) {

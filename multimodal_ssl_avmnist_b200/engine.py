@@ -22,6 +22,8 @@ import contextlib
 import math
 
 import numpy as np
+import os
+
 import torch
 
 from . import augment as A
@@ -150,6 +152,8 @@ class DinoStepEngine:
         assert mode == "default" or kind == "multi_central"
         assert precision in ("bf16", "fp32")
         self.precision = precision
+        # first layers: BatchNorm/ReLU/pool backward-apply fused into the weight-gradient kernel (dz stays in shared memory)
+        self.fuse_l0_bwd = precision == "bf16" and os.environ.get("B200_FUSE_L0_BWD", "1") != "0"
         self.lin_tc = precision == "bf16"          # linear layers on the tensor cores (tcgen05 kind::tf32)
         self.kind, self.mode = kind, mode
         self.E, self.O, self.P = encoder_output_dim, output_dim, projection_dim
@@ -319,7 +323,11 @@ class DinoStepEngine:
                         sc = scr[mod]
                         if tc:
                             sc["wg"] = max(sc["wg"], ops.conv_tc_wgrad_work_floats(N, ci, co, hw, hw, k, pad))
-                            sc["z8"] = max(sc["z8"], N * co * ho * ho)
+                            if ci == 1 and self.fuse_l0_bwd and next_tc:
+                                # fused apply + weight gradient: this layer's dz never exists in HBM
+                                sc["wg"] = max(sc["wg"], ops.conv_tc_wgrad_l0_fused_work_floats(N, B, co, hw, hw, k, pad))
+                            else:
+                                sc["z8"] = max(sc["z8"], N * co * ho * ho)
                         else:
                             sc["wg"] = max(sc["wg"], ops.conv_bwd_weight_work_floats(N, ci, co, hw, hw, k, pad))
                             sc["z"] = max(sc["z"], N * co * ho * ho)
@@ -589,11 +597,14 @@ class DinoStepEngine:
                 par = li & 1
                 if par in busy:
                     main.wait_event(busy.pop(par))
-                dz = w[f"{mod}.dz8" if par == 0 else f"{mod}.dz8b"][:z.numel()].view_as(z)
+                fused = ci == 1 and self.fuse_l0_bwd and d_p.dtype == BF
+                if not fused:
+                    dz = w[f"{mod}.dz8" if par == 0 else f"{mod}.dz8b"][:z.numel()].view_as(z)
                 p_out = w[f"s.{mod}.p8{li}"] if f"s.{mod}.p8{li}" in w else w[f"s.{mod}.p{li}"]
                 ops.bn_pool8_bwd_reduce_p(p_out, d_p, S["enc." + bn + ".weight"], S["enc." + bn + ".bias"], sums, B)
-                ops.bn_relu_pool8_bwd_apply(z, d_p, sc, sh, mu, inv, sums, dz, B, dbsum=w[f"{mod}.dbsum"][li])
-                ops.bias_grad_finalize(w[f"{mod}.dbsum"][li], G["enc." + conv + ".bias"])
+                if not fused:
+                    ops.bn_relu_pool8_bwd_apply(z, d_p, sc, sh, mu, inv, sums, dz, B, dbsum=w[f"{mod}.dbsum"][li])
+                    ops.bias_grad_finalize(w[f"{mod}.dbsum"][li], G["enc." + conv + ".bias"])
             else:
                 dz = w[f"{mod}.dz"][:z.numel()].view_as(z)
                 ops.bn_relu_pool_bwd_reduce(z, d_p, sc, sh, mu, inv, sums, B)
@@ -602,15 +613,24 @@ class DinoStepEngine:
             if tc:
                 xin8 = w[f"{mod}.xs8"] if ci == 1 else w[f"s.{mod}.p8{li - 1}"]
                 wk = w[f"{mod}.wg_work" if (li & 1) == 0 else f"{mod}.wg_work_b"]
+
+                def wgrad():
+                    if fused:       # BatchNorm / ReLU / pool backward-apply happens inside the weight-gradient kernel
+                        ops.conv_tc_wgrad_l0_fused(xin8, z, d_p, sc, sh, mu, inv, sums, G["enc." + conv + ".weight"], w[f"{mod}.dbsum"][li], wk,
+                                                   B, pad)
+                        ops.bias_grad_finalize(w[f"{mod}.dbsum"][li], G["enc." + conv + ".bias"])
+                    else:
+                        ops.conv_tc_wgrad(xin8, dz, G["enc." + conv + ".weight"], wk, pad)
+
                 if wside is not None:
                     wside.wait_stream(main)
                     with torch.cuda.stream(wside):
-                        ops.conv_tc_wgrad(xin8, dz, G["enc." + conv + ".weight"], wk, pad)
+                        wgrad()
                         ev = torch.cuda.Event()
                         ev.record(wside)
                     busy[li & 1] = ev
                 else:
-                    ops.conv_tc_wgrad(xin8, dz, G["enc." + conv + ".weight"], wk, pad)
+                    wgrad()
             else:
                 xin = x if li == 0 else w[f"s.{mod}.p{li - 1}"]
                 ops.conv_bwd_weight(xin.view(N, ci, hw, hw), dz, G["enc." + conv + ".weight"], G["enc." + conv + ".bias"], w[f"{mod}.wg_work"], pad)

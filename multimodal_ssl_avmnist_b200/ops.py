@@ -253,6 +253,23 @@ def conv_tc_wgrad(x8, dz8, dw, work, pad):
                                           _stream()), "conv_tc_wgrad")
 
 
+def conv_tc_wgrad_l0_fused_work_floats(N, n_per_view, Cout, H, W, K, pad):
+    n = int(_lib_().b200_conv_tc_wgrad_l0_fused_work_floats(N, n_per_view, Cout, H, W, K, pad))
+    if n < 0:
+        raise _lib.B200Error(f"conv_tc_wgrad_l0_fused: unsupported geometry {(Cout, H, W, K, pad)}")
+    return n
+
+
+def conv_tc_wgrad_l0_fused(xs8, z8, dp8, scale, shift, mean, invstd, sums, dw, dbsum, work, n_per_view, pad):
+    """First-layer backward in one kernel: BN/ReLU/pool backward-apply (z8 fp16 act8, dp8 bf16 act8) + weight gradient."""
+    N, P, H, W, _ = z8.shape
+    Cout, _, K, _ = dw.shape
+    _lib.check(_lib_().b200_conv_tc_wgrad_l0_fused(_ptr(xs8, BF16), _ptr(z8, torch.float16), _ptr(dp8, BF16), _ptr(scale, F32), _ptr(shift, F32),
+                                                   _ptr(mean, F32), _ptr(invstd, F32), _ptr(sums, F64), _ptr(dw, F32),
+                                                   _ptr(dbsum, F64) if dbsum is not None else None, _ptr(work, F32), N, n_per_view, Cout, H, W,
+                                                   K, pad, _stream()), "conv_tc_wgrad_l0_fused")
+
+
 def pack_shift8(x, out, pad):
     """fp32 [N, H, W] (or [N, 1, H, W]) -> bf16 shift8 [N, H, W + pad, 8] (pad = the convolution's padding)"""
     N, H, W = x.shape[0], x.shape[-2], x.shape[-1]
@@ -440,8 +457,8 @@ def bn1d_gelu_drop_bwd_apply(h, dg, scale, shift, mean, invstd, mask, drop_p, su
 
 # ---- launch accounting and optional per-op timing ------------------------------------------------------------
 # Every wrapper above issues a fixed number of kernel launches; the table lists the ones that issue more than one.
-_LAUNCHES = {"conv_tc_wgrad": 2, "conv_bwd_weight": 3, "linear_bwd_weight": 3, "infonce_fwd_bwd": 9}
-_NOT_KERNELS = {"conv_tc_wgrad_work_floats", "conv_tc_supported", "conv_tc_weight_bytes", "dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
+_LAUNCHES = {"conv_tc_wgrad_l0_fused": 3, "conv_tc_wgrad": 2, "conv_bwd_weight": 3, "linear_bwd_weight": 3, "infonce_fwd_bwd": 9}
+_NOT_KERNELS = {"conv_tc_wgrad_l0_fused_work_floats", "conv_tc_wgrad_work_floats", "conv_tc_supported", "conv_tc_weight_bytes", "dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
 LAUNCH_COUNT = 0
 _PROFILE = None          # None, or a list receiving (name, start_event, end_event, meta)
 

@@ -220,6 +220,51 @@ def test_first_layer_shift8_forward_and_weight_gradient(geom, views, B):
     assert float((dw.double() - wd.grad).abs().max()) <= 3e-5 * float(wd.grad.abs().max())
 
 
+@pytest.mark.parametrize("geom", FIRST)
+@pytest.mark.parametrize("views,B", [(1, 2), (3, 5), (7, 12), (2, 160)])
+def test_first_layer_fused_backward_matches_apply_then_wgrad(geom, views, B):
+    """b200_conv_tc_wgrad_l0_fused == b200_bn_relu_pool8_bwd_apply followed by b200_conv_tc_wgrad: the dz tile is produced
+    in shared memory with the same arithmetic and bf16 rounding, so dW agrees to accumulation order and the bias-gradient
+    sums to fp32 summation order."""
+    Cout, H, K, pad = geom
+    g = torch.Generator().manual_seed(11 * Cout + H + views + B)
+    N = views * B
+    x = torch.rand(N, 1, H, H, generator=g).to(DEV)
+    x8 = torch.empty(N, H, H + pad, 8, dtype=torch.bfloat16, device=DEV)
+    ops.pack_shift8(x, x8, pad)
+    z8 = torch.randn(N, Cout // 8, H, H, 8, generator=g).to(DEV).to(torch.float16)
+    dp8 = torch.randn(N, Cout // 8, H // 2, H // 2, 8, generator=g).to(DEV).to(torch.bfloat16)
+    scale = (torch.rand(views, Cout, generator=g) + 0.5).to(DEV)
+    scale[:, 1] *= -1.0                                   # negative BatchNorm scale flips the arg-max
+    shift = (torch.randn(views, Cout, generator=g) * 0.3).to(DEV)
+    mean = (torch.randn(views, Cout, generator=g) * 0.1).to(DEV)
+    invstd = (torch.rand(views, Cout, generator=g) + 0.5).to(DEV)
+    sums = torch.zeros(views, Cout, 2, dtype=torch.float64, device=DEV)
+    ops.bn_relu_pool8_bwd_reduce(z8, dp8, scale, shift, mean, invstd, sums, B)
+    # two-kernel path
+    dz8 = torch.empty(N, Cout // 8, H, H, 8, dtype=torch.bfloat16, device=DEV)
+    db_a = torch.zeros(Cout, dtype=torch.float64, device=DEV)
+    ops.bn_relu_pool8_bwd_apply(z8, dp8, scale, shift, mean, invstd, sums, dz8, B, dbsum=db_a)
+    work = torch.empty(ops.conv_tc_wgrad_work_floats(N, 1, Cout, H, H, K, pad), device=DEV)
+    dw_a = torch.full((Cout, 1, K, K), float("nan"), device=DEV)
+    ops.conv_tc_wgrad(x8, dz8, dw_a, work, pad)
+    # fused
+    z_keep = z8.clone()
+    work2 = torch.empty(ops.conv_tc_wgrad_l0_fused_work_floats(N, B, Cout, H, H, K, pad), device=DEV)
+    dw_b = torch.full((Cout, 1, K, K), float("nan"), device=DEV)
+    db_b = torch.zeros(Cout, dtype=torch.float64, device=DEV)
+    ops.conv_tc_wgrad_l0_fused(x8, z8, dp8, scale, shift, mean, invstd, sums, dw_b, db_b, work2, B, pad)
+    torch.cuda.synchronize()
+    assert torch.equal(z8, z_keep)                       # inputs untouched
+    ref = float(dw_a.abs().max())
+    assert float((dw_a - dw_b).abs().max()) <= 2e-5 * ref + 1e-6
+    assert float((db_a - db_b).abs().max()) <= 1e-4 * float(dz8.float().abs().sum(dim=(0, 2, 3)).max())
+    # and against an fp64 convolution weight gradient of the unpacked dz
+    wd = torch.zeros(Cout, 1, K, K, dtype=torch.float64, device=DEV, requires_grad=True)
+    F.conv2d(_bf(x).double(), wd, None, padding=pad).backward(_unpack8(dz8).double())
+    assert float((dw_b.double() - wd.grad).abs().max()) <= 3e-5 * float(wd.grad.abs().max())
+
+
 def test_augmentation_direct_shift8_output_matches_pack():
     """The augmentation kernels' direct bf16 shift8 output == pack_shift8(fp32 output) bit for bit (same op records)."""
     from multimodal_ssl_avmnist_b200.engine import DinoStepEngine
