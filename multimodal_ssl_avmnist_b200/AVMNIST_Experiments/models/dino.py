@@ -567,10 +567,19 @@ class UniModalDINOLightning(_DinoLightningBase):
         self._sync_hparams()
         student_out, teacher_out, embeddings = self.model(batch)
         loss = self.dino_loss(student_out, teacher_out)
+        cosine_loss = None
         if self.cosine_loss_alpha > 0:
-            # the consistency term back-propagates into the encoder output: give the embeddings the engine's grad path
-            raise NotImplementedError("cosine_loss_alpha > 0 is available through DinoStepEngine(cosine_loss_alpha=...); the YAML "
-                                      "configs of the reference set it to 0")
+            # total = dino + alpha * cosine (reference models/dino.py:1651-1656).  The value comes from the fused kernel here;
+            # its gradient w.r.t. the embeddings is added by the engine's backward pass (engine.cosine_loss_alpha), so the
+            # term enters the autograd graph as a constant and is not counted twice
+            eng = self.model.engine
+            eng.cosine_loss_alpha = float(self.cosine_loss_alpha)
+            cosine_loss = self._cosine_consistency_loss(embeddings).detach()
+            loss = loss + self.cosine_loss_alpha * cosine_loss
+        elif self.model.engine is not None:
+            self.model.engine.cosine_loss_alpha = 0.0
         self.model.update_teacher()
         self.log("train_loss", loss, on_step=True, on_epoch=True, prog_bar=True)
+        if cosine_loss is not None:
+            self.log("cosine_loss", cosine_loss, on_step=True, on_epoch=True, prog_bar=True)
         return loss

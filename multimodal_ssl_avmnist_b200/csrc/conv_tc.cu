@@ -665,7 +665,7 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
     constexpr int HBP = C::HB / 2, WOP = C::WO / 2;                      // pooled rows / columns of a band
     constexpr int G_BYTES = round_up(C::P_OUT * HBP * WOP * 16, 128);    // pooled-gradient tile
     constexpr int SLOT = C::X_BYTES + C::Z_BYTES + G_BYTES;
-    constexpr int CST_OFF = C::SLOTS * SLOT, BAR_OFF = CST_OFF + C::COUT * 16 + C::COUT * 4;
+    constexpr int CST_OFF = C::SLOTS * SLOT, BAR_OFF = CST_OFF + C::COUT * 16 + 4 * C::COUT * 4;
     extern __shared__ __align__(1024) uint8_t smem[];
     float4* cst_s = reinterpret_cast<float4*>(smem + CST_OFF);
     float* db_s = reinterpret_cast<float*>(smem + CST_OFF + C::COUT * 16);
@@ -683,7 +683,7 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
     {
         uint4* z = reinterpret_cast<uint4*>(smem);
         for (int i = threadIdx.x; i < CST_OFF / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
-        for (int i = threadIdx.x; i < C::COUT; i += blockDim.x) db_s[i] = 0.f;
+        for (int i = threadIdx.x; i < 4 * C::COUT; i += blockDim.x) db_s[i] = 0.f;       // [transform warp][channel]
         fence_proxy_async_smem();
     }
     if (warp == 0 && lane == 0) {
@@ -809,7 +809,7 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
                         float v = acc[j];
 #pragma unroll
                         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                        if (lane == 0) atomicAdd(&db_s[o * 8 + j], v);
+                        if (lane == 0) db_s[(warp - 2) * C::COUT + o * 8 + j] += v;      // single writer per slot: deterministic
                     }
                 }
             }
@@ -818,7 +818,8 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
         }
         // ---- end of kernel: bias-gradient sums and the dW partial of this CTA ----
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (t < C::COUT && dbsum != nullptr) atomicAdd(&dbsum[t], (double)db_s[t]);
+        if (t < C::COUT && dbsum != nullptr)
+            atomicAdd(&dbsum[t], (double)db_s[t] + (double)db_s[C::COUT + t] + (double)db_s[2 * C::COUT + t] + (double)db_s[3 * C::COUT + t]);
         const int quad = warp & 3;
         const int m = quad * 16 + (lane & 15), j = m >> 3, ci8 = m & 7;
         float* part = work + (long)g * C::PART;
@@ -869,7 +870,7 @@ int launch_conv_tc_wgrad_l0_fused(const void* x, const void* z, const void* dp, 
     constexpr int HBP = C::HB / 2, WOP = C::WO / 2;
     constexpr int G_BYTES = round_up(C::P_OUT * HBP * WOP * 16, 128);
     constexpr int SLOT = C::X_BYTES + C::Z_BYTES + G_BYTES;
-    constexpr int SMEM = C::SLOTS * SLOT + C::COUT * 20 + 256;
+    constexpr int SMEM = C::SLOTS * SLOT + C::COUT * 32 + 256;
     static_assert((SMEM + 1024) * C::CTAS <= 227 * 1024, "shared memory per SM");
     const int G = wgrad_ctas<C>(N);
     const int views = N / n_per_view;

@@ -385,8 +385,8 @@ class DinoStepEngine:
                     w[f"{m}.{nm}"] = e(1, 512)
             if self.mode == "infonce":
                 w["infonce_work"] = e(ops.infonce_work_floats(B, P, tc=self.lin_tc))
-        if self.cosine_loss_alpha > 0:
-            w["d.emb"] = e(Nv, O)
+        if self.kind != "multi_central" or self.cosine_loss_alpha > 0:
+            w["d.emb"] = e(Nv, O)          # cosine-consistency gradient (UniModalDINO, cosine_loss_alpha may be switched on later)
         self._ws[B] = w
         return w
 
@@ -899,7 +899,8 @@ class DinoStepEngine:
             self.aux_loss_pass(w, labels)
         self.backward_pass(w)
         loss = w["loss"]
-        loss[3:4].copy_(loss[0:1] + loss[1:2] + loss[2:3])
+        # the loss kernels report UNSCALED values (their gradients carry the weights): total = dino + alpha*aux + alpha_cos*cosine
+        loss[3:4].copy_(loss[0:1] + float(getattr(self, "alpha", 1.0)) * loss[1:2] + float(self.cosine_loss_alpha) * loss[2:3])
         return loss
 
     def allreduce_gradients(self):

@@ -217,7 +217,7 @@ def step_fixture(mode, B=4, seed=5, n_steps=2):
     return out
 
 
-def unimodal_fixture(B=4, seed=9):
+def unimodal_fixture(B=4, seed=9, alpha=0):
     spec = R.image_simple_spec(256)
     hs = R.head_spec(256, 128)
     sp = R.make_params(spec, seed)
@@ -234,7 +234,7 @@ def unimodal_fixture(B=4, seed=9):
             md.pl.LightningModule.__init__(self)
             self.model = m
             self.student_temperature, self.teacher_temperature = 0.1, 0.04
-            self.cosine_loss_alpha = 0
+            self.cosine_loss_alpha = alpha
 
     lit = L(model)
     lit.train()
@@ -277,6 +277,7 @@ if __name__ == "__main__":
     fx = {"losses": losses_kat(), "augment": augment_fixtures()}
     fx["steps"] = {m: step_fixture(m) for m in ("default", "semi_supervised", "infonce", "mse")}
     fx["unimodal_image_simple"] = unimodal_fixture()
+    fx["unimodal_image_simple_cosine"] = unimodal_fixture(alpha=0.3)          # + cosine consistency term (models/dino.py:1651-1656)
     fx["versions"] = {"torch": torch.__version__}
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(fx, f, indent=1)

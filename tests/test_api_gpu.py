@@ -113,6 +113,37 @@ def test_unimodal_training_step():
     assert 3.0 < float(loss) < 6.0
 
 
+def test_unimodal_training_step_with_cosine_consistency_matches_engine():
+    """cosine_loss_alpha > 0 (the reference's constructor default is 0.3): training_step returns dino + alpha * cosine and
+    backward() carries the consistency gradient into the encoder - identical to the bare engine with the same weights."""
+    from multimodal_ssl_avmnist_b200.engine import DinoStepEngine
+    torch.manual_seed(4)
+    lit = md.UniModalDINOLightning(encoder_class=md.ImageEncoder, data_dir="x/", dropout=0.0, learning_rate=1e-3, projection_dim=128,
+                                   output_dim=256, cosine_loss_alpha=0.3, num_epochs=10, use_mixed_precision=False).to(DEV)
+    views = _batch("default", 8, 90)
+    loss = lit.training_step(views, 0)
+    loss.backward()
+    meng = lit.model.engine
+    assert meng.precision == "fp32" and meng.cosine_loss_alpha == 0.3
+    eng = DinoStepEngine(kind="image_simple", device=DEV, dropout=0.0, seed=meng.seed, precision="fp32", cosine_loss_alpha=0.3)
+    eng.student.flat.copy_(meng.student.flat)
+    eng.sync_teacher()
+    gi, ga, li, la = views
+    xi = torch.cat([gi, li], 1).permute(1, 0, 2, 3, 4)[:, :, 0].contiguous()
+    l2 = eng.forward_backward(xi, None)
+    torch.cuda.synchronize()
+    assert float(l2[2]) > 0 and abs(float(l2[3]) - (float(l2[0]) + 0.3 * float(l2[2]))) < 1e-6
+    assert abs(float(loss) - float(l2[3])) < 1e-5 * abs(float(l2[3]))
+    n = eng.n_trainable_prefix
+    assert float((eng.grad[:n] - meng.grad[:n]).abs().max()) <= 1e-6 * float(eng.grad[:n].abs().max()) + 1e-12
+    # and the term matters: without it the gradient differs
+    eng0 = DinoStepEngine(kind="image_simple", device=DEV, dropout=0.0, seed=meng.seed, precision="fp32", cosine_loss_alpha=0.0)
+    eng0.student.flat.copy_(meng.student.flat)
+    eng0.sync_teacher()
+    eng0.forward_backward(xi, None)
+    assert float((eng0.grad[:n] - eng.grad[:n]).abs().max()) > 0
+
+
 def test_trainer_fit_on_synthetic_files(tmp_path):
     """The run_dino.py flow in miniature: data module on synthetic files, Trainer(max_epochs) from the Lightning-surface
     shim (or real Lightning when installed), CSV logger, checkpoint, reload."""

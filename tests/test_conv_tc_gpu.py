@@ -262,7 +262,10 @@ def test_first_layer_fused_backward_matches_apply_then_wgrad(geom, views, B):
     # and against an fp64 convolution weight gradient of the unpacked dz
     wd = torch.zeros(Cout, 1, K, K, dtype=torch.float64, device=DEV, requires_grad=True)
     F.conv2d(_bf(x).double(), wd, None, padding=pad).backward(_unpack8(dz8).double())
-    assert float((dw_b.double() - wd.grad).abs().max()) <= 3e-5 * float(wd.grad.abs().max())
+    # the tensor core accumulates ~N*H*W products per tap in fp32 (truncating adds): the bound is relative to sum |x|*|dz|
+    wa = torch.zeros(Cout, 1, K, K, dtype=torch.float64, device=DEV, requires_grad=True)
+    F.conv2d(_bf(x).double(), wa, None, padding=pad).backward(_unpack8(dz8).double().abs())
+    assert float(((dw_b.double() - wd.grad).abs() / wa.grad).max()) <= 3e-6
 
 
 def test_augmentation_direct_shift8_output_matches_pack():

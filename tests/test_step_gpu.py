@@ -107,12 +107,15 @@ def test_step_vs_oracle_and_reference(mode, golden):
         assert _rel(eng.bn_s["head.mlp.1"].running_var, st.student_head_buf["mlp.1.running_var"]) < btol
 
 
-def test_unimodal_image_simple_step(golden):
-    fx = golden["unimodal_image_simple"]
+@pytest.mark.parametrize("key,alpha", [("unimodal_image_simple", 0.0), ("unimodal_image_simple_cosine", 0.3)])
+def test_unimodal_image_simple_step(golden, key, alpha):
+    """UniModalDINOLightning.training_step of the imported reference (golden), without and with the cosine-consistency term
+    (total = dino + alpha * cosine, models/dino.py:1651-1656)."""
+    fx = golden[key]
     B = fx["B"]
     sp = R.make_params(R.image_simple_spec(256), fx["seed"])
     hp = R.make_params(R.head_spec(256, 128), fx["seed"] + 1)
-    eng = DinoStepEngine(kind="image_simple", device=DEV, precision="fp32")
+    eng = DinoStepEngine(kind="image_simple", device=DEV, precision="fp32", cosine_loss_alpha=alpha)
     eng.load_named(student=sp, teacher=sp, student_head=hp, teacher_head=hp)
     gi, ga, li, la = synth_views(B, seed=100)
     img, _ = views_to_vb(gi, ga, li, la)
