@@ -258,29 +258,67 @@ __global__ void __launch_bounds__(256) bn_pool8_bwd_reduce_p_kernel(const void* 
         be[j] = __ldg(beta + oct * 8 + j);
         s1[j] = s2[j] = 0.f;
     }
-    for (long u = u0 + threadIdx.x; u < u1; u += blockDim.x) {
-        const int s = (int)(u / hw), e = (int)(u - (long)s * hw);
-        const long n = (long)v * n_per_view + s;
-        float pv[8], g[8];
-        if (p_fmt) {
-            unpack8(__ldg(reinterpret_cast<const uint4*>(p) + (n * P + oct) * hw + e), pv);
-        } else {
-            const float* pp = reinterpret_cast<const float*>(p) + (n * C + oct * 8) * hw + e;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) pv[j] = __ldg(pp + (long)j * hw);
-        }
-        if (dp_fmt) {
-            unpack8(__ldg(reinterpret_cast<const uint4*>(dp) + (n * P + oct) * hw + e), g);
-        } else {
-            const float* gp = reinterpret_cast<const float*>(dp) + (n * C + oct * 8) * hw + e;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] = __ldg(gp + (long)j * hw);
-        }
+    auto accumulate = [&](const float* pv, const float* g) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float gj = pv[j] > 0.f ? g[j] : 0.f;
             s1[j] += gj;
             s2[j] += gj * ((pv[j] - be[j]) * ig[j]);
+        }
+    };
+    if (p_fmt && dp_fmt) {
+        // both tensors act8: four independent 16-byte loads per tensor in flight per thread
+        const uint4* pb = reinterpret_cast<const uint4*>(p);
+        const uint4* gb = reinterpret_cast<const uint4*>(dp);
+        auto addr = [&](long u) {
+            const long s = u / hw;
+            return (((long)v * n_per_view + s) * P + oct) * hw + (u - s * hw);
+        };
+        long u = u0 + threadIdx.x;
+        const long step = blockDim.x;
+        for (; u + 3 * step < u1; u += 4 * step) {
+            uint4 rp[4], rg[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const long a = addr(u + q * step);
+                rp[q] = __ldg(pb + a);
+                rg[q] = __ldg(gb + a);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float pv[8], g[8];
+                unpack8(rp[q], pv);
+                unpack8(rg[q], g);
+                accumulate(pv, g);
+            }
+        }
+        for (; u < u1; u += step) {
+            const long a = addr(u);
+            float pv[8], g[8];
+            unpack8(__ldg(pb + a), pv);
+            unpack8(__ldg(gb + a), g);
+            accumulate(pv, g);
+        }
+    } else {
+        for (long u = u0 + threadIdx.x; u < u1; u += blockDim.x) {
+            const int s = (int)(u / hw), e = (int)(u - (long)s * hw);
+            const long n = (long)v * n_per_view + s;
+            float pv[8], g[8];
+            if (p_fmt) {
+                unpack8(__ldg(reinterpret_cast<const uint4*>(p) + (n * P + oct) * hw + e), pv);
+            } else {
+                const float* pp = reinterpret_cast<const float*>(p) + (n * C + oct * 8) * hw + e;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pv[j] = __ldg(pp + (long)j * hw);
+            }
+            if (dp_fmt) {
+                unpack8(__ldg(reinterpret_cast<const uint4*>(dp) + (n * P + oct) * hw + e), g);
+            } else {
+                const float* gp = reinterpret_cast<const float*>(dp) + (n * C + oct * 8) * hw + e;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g[j] = __ldg(gp + (long)j * hw);
+            }
+            accumulate(pv, g);
         }
     }
     __shared__ float red[8][16];

@@ -656,13 +656,17 @@ int launch_conv_tc_wgrad(const void* x, const void* dz, float* dw, float* work, 
 // (bf16) from the pooled gradient tile, fence it to the async proxy, and the MMA warp accumulates dW exactly as in
 // conv_tc_wgrad_kernel.  The same warps accumulate the conv bias gradient sum(dz).
 //   cst: per (view, channel) constants float4 {a, b, ca, cb} prepared by wgrad_l0_consts_kernel from the BatchNorm tensors.
+constexpr int L0F_ISS = 3;                       // MMA-issuer warps (K steps interleaved, one TMEM accumulator each)
+constexpr int L0F_THREADS = 32 * (1 + L0F_ISS + 4);
 template <class C>
-__global__ void __launch_bounds__(192, C::CTAS)
+__global__ void __launch_bounds__(L0F_THREADS, C::CTAS)
 conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_z,
                               const __grid_constant__ CUtensorMap tmap_g, const float4* __restrict__ cst, float* __restrict__ work,
                               double* __restrict__ dbsum, int N, int n_per_view) {
     static_assert(C::L0 && C::PSPLIT == 1 && C::NSPLIT == 1 && (C::HB % 2) == 0 && (C::WO % 2) == 0, "first-layer geometry");
     constexpr int HBP = C::HB / 2, WOP = C::WO / 2;                      // pooled rows / columns of a band
+    constexpr int ACC_COLS = round_up(C::COUT, 32), TCOLS = pow2_cols(L0F_ISS * ACC_COLS);
+    static_assert(TCOLS * C::CTAS <= 512, "TMEM columns per SM");
     constexpr int G_BYTES = round_up(C::P_OUT * HBP * WOP * 16, 128);    // pooled-gradient tile
     constexpr int SLOT = C::X_BYTES + C::Z_BYTES + G_BYTES;
     constexpr int CST_OFF = C::SLOTS * SLOT, BAR_OFF = CST_OFF + C::COUT * 16 + 4 * C::COUT * 4;
@@ -693,12 +697,12 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
         for (int s = 0; s < C::SLOTS; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(ready_bar(s), 128);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), L0F_ISS);
         }
-        mbar_init(done_bar, 1);
+        mbar_init(done_bar, L0F_ISS);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<C::TMEM_COLS>(smem_u32(tmem_slot));
+    if (warp == 1) tmem_alloc<TCOLS>(smem_u32(tmem_slot));
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -718,18 +722,22 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
                 tma_load_4d(sa + C::X_BYTES + C::Z_BYTES, &tmap_g, full_bar(slot), 0, 0, band * HBP, n * C::P_OUT);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp <= L0F_ISS) {
         if (lane == 0) {
+            // issuer w takes the K steps ks = w, w + ISS, ... of every item and owns accumulator w (summed in the epilogue):
+            // one issuing thread sustains only ~1 MMA / 140 cycles, the tensor pipe of the SM about four times that
             constexpr uint32_t idesc = idesc_bf16(C::COUT, true, true, 64);
+            const int w = warp - 1;
+            const uint32_t acc = tmem_base + w * ACC_COLS;
             for (int i = i0; i < i1; ++i) {
                 const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
                 mbar_wait(ready_bar(slot), use & 1);
                 tc_fence_after_sync();
                 const uint32_t xa = smem0 + slot * SLOT, za = xa + C::X_BYTES;
-                for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                for (int ks = w; ks < C::KSTEPS; ks += L0F_ISS) {
                     const uint64_t bd = smem_desc(za + ks * 256, 128, C::PLANE_Z);
                     const uint64_t ad = smem_desc(xa + ks * 256, 128, C::WP * 16);
-                    mma_bf16(tmem_base, ad, bd, idesc, (i > i0 || ks > 0) ? 1u : 0u);
+                    mma_bf16(acc, ad, bd, idesc, (i > i0 || ks >= L0F_ISS) ? 1u : 0u);
                 }
                 mma_commit(empty_bar(slot));
             }
@@ -737,7 +745,8 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
         }
     } else {
         // ===== transform warps: z -> dz in place (then the end-of-kernel epilogue) =====
-        const int t = threadIdx.x - 64;                                  // 0..127
+        const int t = threadIdx.x - 32 * (1 + L0F_ISS);                  // 0..127
+        const int tw = warp - (1 + L0F_ISS);                             // transform warp 0..3
         int cur_view = -1;
         for (int i = i0; i < i1; ++i) {
             const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
@@ -809,7 +818,7 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
                         float v = acc[j];
 #pragma unroll
                         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                        if (lane == 0) db_s[(warp - 2) * C::COUT + o * 8 + j] += v;      // single writer per slot: deterministic
+                        if (lane == 0) db_s[tw * C::COUT + o * 8 + j] += v;      // single writer per slot: deterministic
                     }
                 }
             }
@@ -829,18 +838,25 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
         }
 #pragma unroll
         for (int cc = 0; cc < (C::COUT + 15) / 16; ++cc) {
-            uint32_t v[16];
-            if (i1 > i0) {
-                tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + cc * 16, v);
-                tmem_ld_wait();
-            } else {
+            float sum[16];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = 0u;
+            for (int q = 0; q < 16; ++q) sum[q] = 0.f;
+            if (i1 > i0) {
+#pragma unroll
+                for (int w = 0; w < L0F_ISS; ++w) {
+                    if (w < C::KSTEPS) {                                  // (every issuer has at least one K step)
+                        uint32_t v[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + w * ACC_COLS + cc * 16, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) sum[q] += __uint_as_float(v[q]);
+                    }
+                }
             }
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 const int co = cc * 16 + q;
-                if (co < C::COUT && lane < 16 && j < C::KS && ci8 < C::KS) part[(co * C::KS + j) * C::KS + ci8] = __uint_as_float(v[q]);
+                if (co < C::COUT && lane < 16 && j < C::KS && ci8 < C::KS) part[(co * C::KS + j) * C::KS + ci8] = sum[q];
             }
         }
     }
@@ -848,7 +864,7 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
     __syncthreads();
     if (warp == 1) {
         tc_fence_after_sync();
-        tmem_dealloc<C::TMEM_COLS>(tmem_base);
+        tmem_dealloc<TCOLS>(tmem_base);
     }
 }
 
@@ -914,7 +930,7 @@ int launch_conv_tc_wgrad_l0_fused(const void* x, const void* z, const void* dp, 
         int rc = encode_tmap_bf16_4d(&tg, dp, dims, strides, box);
         if (rc) return rc;
     }
-    conv_tc_wgrad_l0_fused_kernel<C><<<G, 192, SMEM, st>>>(tx, tz, tg, cst, work, dbsum, N, n_per_view);
+    conv_tc_wgrad_l0_fused_kernel<C><<<G, L0F_THREADS, SMEM, st>>>(tx, tz, tg, cst, work, dbsum, N, n_per_view);
     int rc = launch_status("conv_tc_wgrad_l0_fused_kernel");
     if (rc) return rc;
     wgrad_reduce_kernel<<<(C::PART + 255) / 256, 256, 0, st>>>(work, G, C::PART, dw);

@@ -256,15 +256,15 @@ def test_first_layer_fused_backward_matches_apply_then_wgrad(geom, views, B):
     ops.conv_tc_wgrad_l0_fused(x8, z8, dp8, scale, shift, mean, invstd, sums, dw_b, db_b, work2, B, pad)
     torch.cuda.synchronize()
     assert torch.equal(z8, z_keep)                       # inputs untouched
-    ref = float(dw_a.abs().max())
-    assert float((dw_a - dw_b).abs().max()) <= 2e-5 * ref + 1e-6
+    # fp32 tensor-core accumulation (truncating adds, split over two accumulators in the fused kernel): bounds are relative
+    # to sum |x|*|dz| per tap
+    wa = torch.zeros(Cout, 1, K, K, dtype=torch.float64, device=DEV, requires_grad=True)
+    F.conv2d(_bf(x).double(), wa, None, padding=pad).backward(_unpack8(dz8).double().abs())
+    assert float(((dw_a - dw_b).abs().double() / wa.grad).max()) <= 3e-6
     assert float((db_a - db_b).abs().max()) <= 1e-4 * float(dz8.float().abs().sum(dim=(0, 2, 3)).max())
     # and against an fp64 convolution weight gradient of the unpacked dz
     wd = torch.zeros(Cout, 1, K, K, dtype=torch.float64, device=DEV, requires_grad=True)
     F.conv2d(_bf(x).double(), wd, None, padding=pad).backward(_unpack8(dz8).double())
-    # the tensor core accumulates ~N*H*W products per tap in fp32 (truncating adds): the bound is relative to sum |x|*|dz|
-    wa = torch.zeros(Cout, 1, K, K, dtype=torch.float64, device=DEV, requires_grad=True)
-    F.conv2d(_bf(x).double(), wa, None, padding=pad).backward(_unpack8(dz8).double().abs())
     assert float(((dw_b.double() - wd.grad).abs() / wa.grad).max()) <= 3e-6
 
 
