@@ -57,11 +57,28 @@ constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
 constexpr int SMEM_EST(int nmma, int npad, int slots, int slot_bytes, int tail) { return round_up(nmma * npad * 32, 128) + slots * slot_bytes + tail + 256 + npad * 4; }
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
+// Output-pixel phases packed into the MMA N dimension.  At these channel counts an MMA costs the same ~40-48 cycles of
+// shared-memory operand fetch whether N is 16 or 64, so XPH adjacent output pixels x = XPH*xq + ph share ONE pass over the
+// input: column (ph, co) of the accumulator is output pixel phase ph, the x taps become kw' = ph + kw in [0, K + XPH - 1)
+// (weights zero where kw' - ph is no tap), and row m of a tile is the pixel group xq.  The input slab is therefore held
+// de-interleaved in shared memory -- one plane per x phase, loaded by one strided TMA map each -- so that consecutive
+// rows m are again consecutive 16-byte units.  5x5, 8 -> 16 channels: 20 MMAs (N = 64) per 512 outputs instead of 60.
+// A function of the layer shape only, because the weight image (b200_conv_tc_prep_weights) depends on it.
+constexpr int xph_for(int cin, int cout, int ks) {
+    return (ks == 5 && ((cin == 8 && cout == 16) || (cin == 16 && cout == 8))) ? 4
+         : (ks == 5 && ((cin == 16 && cout == 32) || (cin == 32 && cout == 16))) ? 2 : 1;
+}
+
+struct TMaps {
+    CUtensorMap m[4];                                           // one per x phase (residue of the global column)
+};
+
 template <int CIN_, int COUT_, int NPAD_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int CTAS_ = 1, int NSPLIT_ = 1>
 struct TcCfg {
     static constexpr int NSPLIT = NSPLIT_;                      // output channels split over gridDim.z (halves the smem weight image)
-    static constexpr int NPADL = NPAD_ / NSPLIT_, COUTL = COUT_ / NSPLIT_;
-    static_assert(NSPLIT_ == 1 || (COUT_ == NPAD_ && NPADL % 16 == 0), "N split needs C_out == NPAD and 16-channel slices");
+    static constexpr int XPH = xph_for(CIN_, COUT_, KS_);       // output x phases packed into N
+    static constexpr int NPADL = XPH == 1 ? NPAD_ / NSPLIT_ : round_up(XPH * COUT_, 16), COUTL = COUT_ / NSPLIT_;
+    static_assert(NSPLIT_ == 1 || (XPH == 1 && COUT_ == NPAD_ && NPADL % 16 == 0), "N split needs C_out == NPAD and 16-channel slices");
     static constexpr int CIN = CIN_, COUT = COUT_, NPAD = NPAD_, HIN = HIN_, WIN = WIN_, KS = KS_, PAD = PAD_, BANDS = BANDS_, SLOTS = SLOTS_;
     static constexpr int CTAS = CTAS_;                          // resident CTAs per SM (independent MMA streams hide the per-UMMA fixed cost)
     static constexpr bool L0 = (CIN == 1);                      // first layer: input is the "shift8" image (unit = x[q..q+7])
@@ -70,16 +87,21 @@ struct TcCfg {
     static constexpr int HO = HIN + 2 * PAD - KS + 1, WO = WP - KS + 1;
     static constexpr int HB = HO / BANDS;                       // output rows per band
     static constexpr int HPB = HB + KS - 1;                     // input rows per band slab
-    static constexpr int Q = (HB - 1) * WP + WO;                // flat outputs per band (incl. junk columns)
+    static constexpr int KWX = KS + XPH - 1;                    // x taps including the phase shifts
+    static constexpr int WQ = (WP + XPH - 1) / XPH;             // pitch of one phase plane = row pitch of the flat tile index
+    static constexpr int WOQ = WO / XPH;                        // valid pixel groups per output row
+    static constexpr int Q = (HB - 1) * WQ + WOQ;               // flat tile rows per band (incl. junk columns)
     static constexpr int TILES = (Q + 127) / 128;
-    static constexpr int PLANE_BYTES = HPB * WP * 16;
-    static constexpr int SLOT_BYTES = round_up(P * PLANE_BYTES, 128);
-    static constexpr int NJ = (KS + 1) / 2;                     // kw pairs when CIN == 8
+    static constexpr int PLANE_BYTES = HPB * WQ * 16;           // one (x phase, channel plane)
+    static constexpr int PHASE_BYTES = P * PLANE_BYTES;
+    static constexpr int SLOT_BYTES = round_up(XPH * PHASE_BYTES, 128);
+    static constexpr int NJ = (KWX + 1) / 2;                    // kw' pairs when CIN == 8
     static constexpr int PH = P / 2;                            // plane pairs when CIN >= 16
-    static constexpr int NMMA = L0 ? NJ : (CIN == 8) ? KS * NJ : KS * KS * PH;
+    static constexpr int NMMA = L0 ? (KS + 1) / 2 : (CIN == 8) ? KS * NJ : KS * KWX * PH;
     static constexpr int W_BYTES = round_up(NMMA * NPADL * 32, 128);
-    static constexpr int MAXPIX = TILES * 128 + (L0 ? KS : KS - 1) * WP + KS + 1;   // exclusive bound of pixels a tile may touch
-    static constexpr int TAIL = round_up((MAXPIX > HPB * WP ? (MAXPIX - HPB * WP) : 0) * 16, 128) + 128;
+    static constexpr int MAXPIX = TILES * 128 + (L0 ? KS : KS - 1) * WQ + (KWX - 1) / XPH + 2;   // exclusive bound of units a tile may touch
+    static constexpr int TAIL = round_up((MAXPIX > HPB * WQ ? (MAXPIX - HPB * WQ) : 0) * 16, 128) + 128;
+    static_assert(XPH == 1 || (!L0 && WO % XPH == 0 && WIN % XPH == 0 && XPH <= 4 && (CIN != 8 || (XPH % 2 == 0 && KWX % 2 == 0))), "x phases");
     static constexpr int IMG_BYTES = SLOTS * SLOT_BYTES + TAIL;
     static constexpr int BAR_OFF = W_BYTES + IMG_BYTES;
     static constexpr int SMEM = BAR_OFF + 256 + NPADL * 4;
@@ -97,7 +119,7 @@ struct TcCfg {
     static_assert(NPAD % 16 == 0 && NPAD >= 16 && NPADL <= 64 && COUT <= NPAD && COUT % 8 == 0, "N tile");
     static_assert(HO % BANDS == 0, "bands must divide the output height");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
-    static_assert(P * PLANE_BYTES < (1 << 18) && PLANE_BYTES % 16 == 0, "descriptor range");
+    static_assert(XPH * P * PLANE_BYTES < (1 << 18) && PLANE_BYTES % 16 == 0, "descriptor range");
 };
 
 // out: fp32 NCHW [N][COUT][HO][WO] (out_bf16 == 0), bf16 act8 [N][COUT/8][HO][WO][8] (1) or the same in fp16 (2: the pre-BatchNorm
@@ -105,7 +127,7 @@ struct TcCfg {
 // bias may be null (no bias, no statistics); stats: double [views][COUT][2] (sum, sum of squares), accumulated.
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict__ wprep, const float* __restrict__ bias,
+conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wprep, const float* __restrict__ bias,
                void* __restrict__ out, double* __restrict__ stats, int n_per_view, int out_bf16) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_s = smem;
@@ -129,18 +151,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
     {
         const uint4* src = wprep;
         uint4* dst = reinterpret_cast<uint4*>(w_s);
-        constexpr int NGL = C::NPADL / 8, NG = C::NPAD / 8;          // 8-row groups (128 B = 8 uint4) per K chunk: local / whole
+        constexpr int NGL = C::NPADL / 8, NG = NGL * C::NSPLIT;       // 8-row groups (128 B = 8 uint4) per K chunk: local / whole
         for (int i = threadIdx.x; i < C::NMMA * 2 * NGL * 8; i += blockDim.x) {
             const int q = i & 7, gl = (i >> 3) % NGL, mc = (i >> 3) / NGL;
             dst[i] = src[(mc * NG + blockIdx.z * NGL + gl) * 8 + q];
         }
         uint4* z = reinterpret_cast<uint4*>(img_s);
         for (int i = threadIdx.x; i < C::IMG_BYTES / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
-        for (int i = threadIdx.x; i < C::NPADL; i += blockDim.x) bias_s[i] = (bias != nullptr && i < C::COUTL) ? bias[blockIdx.z * C::COUTL + i] : 0.f;
+        for (int i = threadIdx.x; i < C::NPADL; i += blockDim.x)     // column (phase, channel): the bias repeats per phase
+            bias_s[i] = (bias != nullptr && i < C::XPH * C::COUTL) ? bias[blockIdx.z * C::COUTL + i % C::COUTL] : 0.f;
         fence_proxy_async_smem();
     }
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tmap);
+        for (int r = 0; r < C::XPH; ++r) prefetch_tmap(&tmaps.m[r]);
         for (int s = 0; s < C::SLOTS; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), C::ISS);
@@ -164,9 +187,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
             for (int i = i0; i < i1; ++i) {
                 const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
                 mbar_wait(empty_bar(slot), (use & 1) ^ 1);
-                mbar_expect_tx(full_bar(slot), C::P * C::PLANE_BYTES);
+                mbar_expect_tx(full_bar(slot), C::XPH * C::PHASE_BYTES);
                 const int n = view * n_per_view + i / C::BANDS, band = i % C::BANDS;
-                tma_load_4d(img_addr + slot * C::SLOT_BYTES, &tmap, full_bar(slot), 0, C::L0 ? 0 : -C::PAD, band * C::HB - C::PAD, n * C::P);
+#pragma unroll
+                for (int rp = 0; rp < C::XPH; ++rp) {
+                    // phase plane rp holds the padded columns x' = XPH*i + rp, i.e. the global columns x' - PAD = XPH*(i + a) + r
+                    constexpr int X = C::XPH;
+                    const int r = ((rp - C::PAD) % X + X) % X, a = (rp - C::PAD - r) / X;
+                    tma_load_4d(img_addr + slot * C::SLOT_BYTES + rp * C::PHASE_BYTES, &tmaps.m[r], full_bar(slot), 0, C::L0 ? 0 : a,
+                                band * C::HB - C::PAD, n * C::P);
+                }
             }
         }
     } else if (warp <= C::ISS) {
@@ -199,17 +229,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
                     for (int kh = 0; kh < C::KS; ++kh) {
                         if constexpr (C::CIN == 8) {
 #pragma unroll
-                            for (int j = 0; j < C::NJ; ++j, ++idx) {
-                                const uint64_t ad = smem_desc(a0 + (kh * C::WP + 2 * j) * 16, 16, 128);
+                            for (int j = 0; j < C::NJ; ++j, ++idx) {     // K = taps kw' = 2j, 2j+1: next unit, or the next phase plane
+                                const uint64_t ad = smem_desc(a0 + ((2 * j) % C::XPH) * C::PHASE_BYTES + (kh * C::WQ + (2 * j) / C::XPH) * 16,
+                                                              C::XPH == 1 ? 16 : C::PHASE_BYTES, 128);
                                 const uint64_t bd = smem_desc(w_addr + idx * C::NPADL * 32, C::NPADL * 16, 128);
                                 mma_bf16(d, ad, bd, idesc, idx > 0);
                             }
                         } else {
 #pragma unroll
-                            for (int kw = 0; kw < C::KS; ++kw) {
+                            for (int kw = 0; kw < C::KWX; ++kw) {
 #pragma unroll
                                 for (int pp = 0; pp < C::PH; ++pp, ++idx) {
-                                    const uint64_t ad = smem_desc(a0 + (kh * C::WP + kw) * 16 + pp * 2 * C::PLANE_BYTES, C::PLANE_BYTES, 128);
+                                    const uint64_t ad = smem_desc(a0 + (kw % C::XPH) * C::PHASE_BYTES + (kh * C::WQ + kw / C::XPH) * 16 +
+                                                                      pp * 2 * C::PLANE_BYTES, C::PLANE_BYTES, 128);
                                     const uint64_t bd = smem_desc(w_addr + idx * C::NPADL * 32, C::NPADL * 16, 128);
                                     mma_bf16(d, ad, bd, idesc, idx > 0);
                                 }
@@ -238,8 +270,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
                 mbar_wait(tfull_bar(buf), u & 1);
                 tc_fence_after_sync();
                 const int q = t * 128 + row;
-                const int y = q / C::WP, x = q - y * C::WP;
-                const bool valid = (y < C::HB) && (x < C::WO);
+                const int y = q / C::WQ, xq = q - y * C::WQ;
+                const bool valid = (y < C::HB) && (xq < C::WOQ);
                 const int yy = band * C::HB + y;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * C::NPADL;
 #pragma unroll
@@ -255,19 +287,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
                     float f[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int ch = cc * 16 + j;
-                        f[j] = __uint_as_float(v[j]) + bias_s[ch];
-                        if (ch < C::COUTL && valid) {
-                            s1[ch < C::COUTL ? ch : 0] += f[j];
-                            s2[ch < C::COUTL ? ch : 0] += f[j] * f[j];
+                        const int col = cc * 16 + j, ch = col % C::COUTL;
+                        f[j] = __uint_as_float(v[j]) + bias_s[col];
+                        if (col < C::XPH * C::COUTL && valid) {
+                            s1[ch] += f[j];
+                            s2[ch] += f[j] * f[j];
                         }
                     }
                     if (valid) {
                         if (out_bf16) {
 #pragma unroll
                             for (int o = 0; o < 2; ++o) {
-                                const int oct = cc * 2 + o;
-                                if (oct * 8 < C::COUTL) {
+                                const int col0 = cc * 16 + o * 8, ph = col0 / C::COUTL, oct = (col0 % C::COUTL) / 8;
+                                if (ph < C::XPH) {
                                     uint4 pk;
                                     if (out_bf16 == 2) {
                                         pk.x = pack_f16(f[o * 8 + 0], f[o * 8 + 1]);
@@ -280,16 +312,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
                                         pk.z = pack_bf16(f[o * 8 + 4], f[o * 8 + 5]);
                                         pk.w = pack_bf16(f[o * 8 + 6], f[o * 8 + 7]);
                                     }
-                                    uint4* dst = reinterpret_cast<uint4*>(out) + (((long)n * (C::COUT / 8) + co0 / 8 + oct) * C::HO + yy) * C::WO + x;
+                                    uint4* dst = reinterpret_cast<uint4*>(out) + (((long)n * (C::COUT / 8) + co0 / 8 + oct) * C::HO + yy) * C::WO +
+                                                 xq * C::XPH + ph;
                                     *dst = pk;
                                 }
                             }
                         } else {
-                            float* dst = reinterpret_cast<float*>(out) + (((long)n * C::COUT + co0) * C::HO + yy) * C::WO + x;
+                            float* dst = reinterpret_cast<float*>(out) + (((long)n * C::COUT + co0) * C::HO + yy) * C::WO + xq * C::XPH;
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
-                                const int ch = cc * 16 + j;
-                                if (ch < C::COUTL) dst[(long)ch * C::HO * C::WO] = f[j];
+                                const int col = cc * 16 + j, ph = col / C::COUTL, ch = col % C::COUTL;
+                                if (ph < C::XPH) dst[(long)ch * C::HO * C::WO + ph] = f[j];
                             }
                         }
                     }
@@ -319,34 +352,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict
 // fp32 OIHW weights -> the bf16 byte image the MMA issuer expects: [mma][k chunk (2)][n group][8 rows][8 k].
 // flip = 1 prepares the data-gradient convolution: w is the forward weight [CIN][COUT][KS][KS] and the taps are mirrored.
 __global__ void conv_tc_prep_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int CIN, int COUT, int NPAD,
-                                            int KS, int flip, int total) {
+                                            int KS, int XPH, int flip, int total) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const int k8 = e & 7, r = (e >> 3) & 7, NG = NPAD / 8;
     const int ng = (e >> 6) % NG, c = (e / (64 * NG)) & 1, m = e / (128 * NG);
-    const int co = ng * 8 + r;
+    const int col = ng * 8 + r, ph = col / COUT, co = col % COUT;      // accumulator column = (x phase, output channel)
+    const int KWX = KS + XPH - 1;
     int kh, kw, ci;
     if (CIN == 1) {                 // shift8 first layer: chunk c of MMA m is image row kh = 2m + c, k8 is the kw tap
         kh = 2 * m + c;
         kw = k8;
         ci = 0;
         float v1 = 0.f;
-        if (kh < KS && kw < KS && co < COUT) v1 = w[(co * KS + kh) * KS + kw];
+        if (kh < KS && kw < KS && col < COUT) v1 = w[(co * KS + kh) * KS + kw];
         out[e] = __float2bfloat16_rn(v1);
         return;
     } else if (CIN == 8) {
-        const int NJ = (KS + 1) / 2;
+        const int NJ = (KWX + 1) / 2;
         kh = m / NJ;
-        kw = 2 * (m % NJ) + c;
+        kw = 2 * (m % NJ) + c - ph;
         ci = k8;
     } else {
         const int PH = CIN / 16;
-        kh = m / (KS * PH);
-        kw = (m / PH) % KS;
+        kh = m / (KWX * PH);
+        kw = (m / PH) % KWX - ph;
         ci = (2 * (m % PH) + c) * 8 + k8;
     }
     float v = 0.f;
-    if (kw < KS && co < COUT) {
+    if (kw >= 0 && kw < KS && ph < XPH) {
         v = flip ? w[((ci * COUT + co) * KS + (KS - 1 - kh)) * KS + (KS - 1 - kw)] : w[((co * CIN + ci) * KS + kh) * KS + kw];
     }
     out[e] = __float2bfloat16_rn(v);
@@ -400,13 +434,16 @@ int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* ou
         }
         configured = true;
     }
-    CUtensorMap tm;
+    TMaps tm;
     constexpr uint64_t WT = C::L0 ? C::WIN + C::PAD : C::WIN;      // the shift8 image carries its left padding columns
-    const uint64_t dims[4] = {8, WT, (uint64_t)C::HIN, (uint64_t)N * C::P};
-    const uint64_t strides[3] = {16, WT * 16, WT * C::HIN * 16};
-    const uint32_t box[4] = {8, (uint32_t)C::WP, (uint32_t)C::HPB, (uint32_t)C::P};
-    int rc = encode_tmap_bf16_4d(&tm, x, dims, strides, box);
-    if (rc) return rc;
+    for (int r = 0; r < C::XPH; ++r) {                             // map r: the columns x = XPH*i + r of every row
+        const uint64_t dims[4] = {8, WT / C::XPH, (uint64_t)C::HIN, (uint64_t)N * C::P};
+        const uint64_t strides[3] = {16 * (uint64_t)C::XPH, WT * 16, WT * C::HIN * 16};
+        const uint32_t box[4] = {8, (uint32_t)C::WQ, (uint32_t)C::HPB, (uint32_t)C::P};
+        int rc = encode_tmap_bf16_4d(&tm.m[r], reinterpret_cast<const uint8_t*>(x) + 16 * r, dims, strides, box);
+        if (rc) return rc;
+    }
+    for (int r = C::XPH; r < 4; ++r) tm.m[r] = tm.m[0];
     const int views = N / n_per_view;
     int G = sm_count() * C::CTAS / (views * C::NSPLIT);
     if (G < 1) G = 1;
@@ -949,12 +986,12 @@ using WgS0 = TcWgCfg<1, 32, 28, 28, 3, 1, 1, 3, 1>;
 using WgS2 = TcWgCfg<64, 128, 7, 7, 3, 1, 1, 3, 4, 1, 2>;
 
 //                         CIN COUT NPAD HIN  WIN KS PAD BANDS SLOTS
-using CfgA1 = TcCfg<8, 16, 16, 56, 56, 5, 2, 2, 2, 3>;   // audio conv2 forward
-using CfgA2 = TcCfg<16, 32, 32, 28, 28, 5, 2, 1, 2, 2>;  // audio conv3 forward
+using CfgA1 = TcCfg<8, 16, 16, 56, 56, 5, 2, 2, 2, 2>;   // audio conv2 forward (4 x phases: N = 64)
+using CfgA2 = TcCfg<16, 32, 32, 28, 28, 5, 2, 1, 2, 1>;  // audio conv3 forward (2 x phases: N = 64)
 using CfgA3 = TcCfg<32, 64, 64, 14, 14, 5, 2, 1, 4>;     // audio conv4 forward (an N split over 2 CTAs/SM measured slower: N = 64 MMAs amortise the fixed cost)
 using CfgI1 = TcCfg<32, 64, 64, 14, 14, 5, 0, 1, 4>;     // image conv2 forward (no padding)
-using CfgA1d = TcCfg<16, 8, 16, 56, 56, 5, 2, 4, 2, 2>;  // data gradients (C_in/C_out swapped, pad' = K-1-pad)
-using CfgA2d = TcCfg<32, 16, 16, 28, 28, 5, 2, 2, 2, 2>;
+using CfgA1d = TcCfg<16, 8, 16, 56, 56, 5, 2, 2, 2, 1>;  // data gradients (C_in/C_out swapped, pad' = K-1-pad); 4 x phases: N = 32
+using CfgA2d = TcCfg<32, 16, 16, 28, 28, 5, 2, 1, 2, 1>;  // 2 x phases: N = 32
 using CfgA3d = TcCfg<64, 32, 32, 14, 14, 5, 2, 1, 2>;
 using CfgI1d = TcCfg<64, 32, 32, 10, 10, 5, 4, 1, 2>;
 using CfgA0 = TcCfg<1, 8, 16, 112, 112, 5, 2, 8, 2, 3>;  // first layers on the shift8 image: audio conv1
@@ -981,8 +1018,9 @@ int b200_conv_tc_supported(int Cin, int Cout, int H, int W, int K, int pad) {
 }
 
 int64_t b200_conv_tc_weight_bytes(int Cin, int Cout, int K) {
-    const int npad = (Cout + 15) / 16 * 16;
-    const int nmma = (Cin == 1) ? (K + 1) / 2 : (Cin == 8) ? K * ((K + 1) / 2) : K * K * (Cin / 16);
+    const int xph = Cin == 1 ? 1 : xph_for(Cin, Cout, K), kwx = K + xph - 1;
+    const int npad = (xph * Cout + 15) / 16 * 16;
+    const int nmma = (Cin == 1) ? (K + 1) / 2 : (Cin == 8) ? K * ((kwx + 1) / 2) : K * kwx * (Cin / 16);
     return (int64_t)nmma * npad * 32;
 }
 
@@ -991,10 +1029,11 @@ int b200_conv_tc_prep_weights(const float* w, void* out, int Cin, int Cout, int 
     B200_REQUIRE(Cin == 1 || Cin == 8 || (Cin % 16 == 0 && Cin > 0), -2, "conv_tc_prep_weights: C_in must be 1, 8 or a multiple of 16 (got %d)", Cin);
     B200_REQUIRE(!(Cin == 1 && flip), -2, "conv_tc_prep_weights: the first layer has no data gradient");
     B200_REQUIRE(Cout % 8 == 0 && Cout > 0 && Cout <= 128, -2, "conv_tc_prep_weights: C_out must be a multiple of 8, <= 128 (got %d)", Cout);
-    const int npad = (Cout + 15) / 16 * 16;
+    const int xph = Cin == 1 ? 1 : xph_for(Cin, Cout, K);
+    const int npad = (xph * Cout + 15) / 16 * 16;
     const int total = (int)(b200_conv_tc_weight_bytes(Cin, Cout, K) / 2);
     conv_tc_prep_weights_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(out), Cin, Cout, npad, K,
-                                                                                      flip, total);
+                                                                                      xph, flip, total);
     return launch_status("conv_tc_prep_weights_kernel");
 }
 
