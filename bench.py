@@ -153,11 +153,11 @@ def op_cost(name, meta):
     if meta and meta[-1] and meta[-1][0] == "i":
         ints, meta = meta[-1][1:], meta[:-1]
     if name == "conv_tc" and len(meta) >= 3 and len(ints) >= 4:
-        # (x8 | shift8, wprep, [bias], out) + (n_per_view, Cout, K, pad): tcgen05 implicit GEMM, bf16 operands, fp32 accumulate
+        # (x8 | quad8, wprep, [bias], out) + (n_per_view, Cout, K, pad): tcgen05 implicit GEMM, bf16 operands, fp32 accumulate
         x, out = meta[0], meta[-1]
         n_per_view, Cout, K, pad = ints[:4]
-        if len(x) == 4:
-            N, H, W, Cin = x[0], x[1], x[2] - pad, 1
+        if len(x) == 4:               # first layer: quad8 image [N, H, ceil((W + 2 pad) / 4), 8]; square inputs
+            N, H, W, Cin = x[0], x[1], x[1], 1
         else:
             N, H, W, Cin = x[0], x[2], x[3], x[1] * 8
         Ho, Wo = H + 2 * pad - K + 1, W + 2 * pad - K + 1
@@ -173,7 +173,12 @@ def op_cost(name, meta):
         return 0.0, numel(meta[0]) * 2.0 + numel(meta[1]) * (2.0 if len(meta[1]) == 5 else 4.0)
     if name == "bn_relu_pool8_bwd_apply" and len(meta) >= 2:
         return 0.0, numel(meta[0]) * 4.0 + numel(meta[1]) * (2.0 if len(meta[1]) == 5 else 4.0)
-    if name == "pack_shift8" and len(meta) >= 2:
+    if name == "conv_tc_wgrad_l0_fused" and len(meta) >= 3:
+        # (quad8 x, z8 fp16, dp8 bf16, ...): BatchNorm-apply + weight gradient, every operand read once; dz never leaves the SM
+        x, z, dp = meta[0], meta[1], meta[2]
+        K = 5 if x[2] * 4 - x[1] >= 4 else 3
+        return 2.0 * z[0] * z[1] * 8 * z[2] * z[3] * K * K, (numel(x) + numel(z) + numel(dp)) * 2.0
+    if name in ("pack_shift8", "pack_quad8") and len(meta) >= 2:
         return 0.0, numel(meta[0]) * 4.0 + numel(meta[1]) * 2.0
     if name in ("conv_fwd", "conv_bwd_data", "conv_bwd_weight") and len(meta) >= 2:
         if name == "conv_fwd":
@@ -202,9 +207,9 @@ def op_cost(name, meta):
         (M, N), (_, K) = meta[0], meta[1]
         return 2.0 * M * N * K, 0.0
     if name in ("aug_apply_audio", "aug_apply_image"):
-        # source read once (re-reads by the other views hit L2) + every view written once: fp32 [V,B,S,S] or bf16 shift8 [V,B,S,S+pad,8]
+        # source read once (re-reads by the other views hit L2) + every view written once: fp32 [V,B,S,S] or bf16 quad8 [V,B,S,ceil((S+2pad)/4),8]
         src = meta[0]
-        out8 = [m for m in meta[1:] if len(m) == 5]                    # bf16 shift8 [V,B,S,S+pad,8]
+        out8 = [m for m in meta[1:] if len(m) == 5]                    # bf16 quad8
         out32 = [m for m in meta[1:] if len(m) == 4 and m[-1] == m[-2]]  # fp32 [V,B,S,S]
         out_bytes = sum(numel(m) * 2.0 for m in out8) + sum(numel(m) * 4.0 for m in out32)
         return 0.0, numel(src) * (1.0 if name == "aug_apply_audio" else 4.0) + out_bytes

@@ -111,15 +111,15 @@ int b200_cosine_consistency_fwd_bwd(const float* emb, int V, int B, int D, float
 #define B200_AUG_MAX_OPS 8
 #define B200_AUG_GROUP_WORDS 28
 
-/* Outputs (either may be NULL, not both): out fp32 [V,B,S,S]; out_shift8 bf16 [V,B,S,S+pad,8], the first-layer input
- * image of the tensor-core convolutions (unit (y,xs) = x[y][xs-pad .. xs-pad+7], zero outside the row).
+/* Outputs (either may be NULL, not both): out fp32 [V,B,S,S]; out_quad8 bf16 [V,B,S,ceil((S+2 pad)/4),8], the first-layer
+ * input image of the tensor-core convolutions (see b200_pack_quad8; pad = that convolution's padding).
  * image: src float [B,28,28] in [0,1] (src_u8 == 0) or uint8 [B,28,28] scaled by 1/255 (src_u8 == 1) */
-int b200_aug_apply_image(const void* src, int src_u8, const int32_t* ops, float* out, void* out_shift8, int pad, int B,
+int b200_aug_apply_image(const void* src, int src_u8, const int32_t* ops, float* out, void* out_quad8, int pad, int B,
                          int V, void* stream);
 /* audio: src uint8 [B,112,112] (scaled by 1/255, utils/get_data.py:467) or float; noise: optional injected N(0,1)
  * field [B,V,112,112] (parity mode), NULL -> Philox(seed, sample*V+view) in-kernel */
 int b200_aug_apply_audio(const void* src, int src_u8, const int32_t* ops, const uint32_t* group_bits,
-                         const float* noise, uint64_t seed, float* out, void* out_shift8, int pad, int B, int V,
+                         const float* noise, uint64_t seed, float* out, void* out_quad8, int pad, int B, int V,
                          void* stream);
 /* device-side parameter sampling: spec tables int32 [4][B200_AUG_MAX_OPS][8] in the order
  * image-global, image-local, audio-global, audio-local (kind, p, a0..a5 as float bits; see augment.py pack_spec);
@@ -156,18 +156,23 @@ int b200_conv_tc(const void* x_act8, const void* wprep, const float* bias, void*
 /* dw [Cout][Cin][K][K] = sum_n corr(x_n, dz_n); x and dz bf16 act8, fp32 accumulate in TMEM; per-CTA partials in work
  * (float[b200_conv_tc_wgrad_work_floats(...)]) reduced in a fixed order.  (The bias gradient sum(dz) comes from
  * b200_bn_relu_pool8_bwd_apply's dbsum.)
- * First layers (Cin = 1): b200_conv_tc / b200_conv_tc_wgrad take the "shift8" image bf16 [N][H][W+pad][8] written by
- * b200_pack_shift8 (unit (y,xs) = x[y][xs-pad .. xs-pad+7], zero outside the row) instead of an act8 tensor. */
+ * First layers (Cin = 1): b200_conv_tc takes the "quad8" image (b200_pack_quad8); the stand-alone b200_conv_tc_wgrad takes the
+ * "shift8" image bf16 [N][H][W+pad][8] written by b200_pack_shift8 (unit (y,xs) = x[y][xs-pad .. xs-pad+7], zero outside the
+ * row) -- the training step uses b200_conv_tc_wgrad_l0_fused (quad8) instead. */
 int64_t b200_conv_tc_wgrad_work_floats(int N, int Cin, int Cout, int H, int W, int K, int pad);
 int b200_conv_tc_wgrad(const void* x_act8, const void* dz_act8, float* dw, float* work, int N, int Cin, int Cout, int H,
                        int W, int K, int pad, void* stream);
 int b200_pack_shift8(const float* x, void* out, int N, int H, int W, int pad, void* stream);
+/* fp32 [N][H][W] -> bf16 "quad8" [N][H][WQ][8], WQ = ceil((W + 2 pad) / 4): unit (y, xq) = the 8 zero-padded-row pixels
+ * 4 xq .. 4 xq + 7 (padded column c = image column c - pad).  The first-layer input of b200_conv_tc (C_in = 1) and of
+ * b200_conv_tc_wgrad_l0_fused: four adjacent output pixels share one unit, whose 8 elements are all their kw taps. */
+int b200_pack_quad8(const float* x, void* out, int N, int H, int W, int pad, void* stream);
 /* First layers, fused backward: b200_bn_relu_pool8_bwd_apply + b200_conv_tc_wgrad in one kernel (the first layer needs no data
- * gradient, so dz never has to exist in HBM): z8 fp16 act8 [N][Cout/8][H][W][8], dp8 bf16 act8 [N][Cout/8][H/2][W/2][8],
+ * gradient, so dz never has to exist in HBM): x_quad8 from b200_pack_quad8 / the augmentation kernels, z8 fp16 act8 [N][Cout/8][H][W][8], dp8 bf16 act8 [N][Cout/8][H/2][W/2][8],
  * scale/shift/mean/invstd [views][Cout], sums double [views][Cout][2] (from b200_bn_pool8_bwd_reduce_p) -> dw [Cout][1][K][K],
  * dbsum double [Cout] += sum(dz) (may be NULL).  work: float[b200_conv_tc_wgrad_l0_fused_work_floats(...)], 16-byte aligned. */
 int64_t b200_conv_tc_wgrad_l0_fused_work_floats(int N, int n_per_view, int Cout, int H, int W, int K, int pad);
-int b200_conv_tc_wgrad_l0_fused(const void* x_shift8, const void* z8, const void* dp8, const float* scale, const float* shift,
+int b200_conv_tc_wgrad_l0_fused(const void* x_quad8, const void* z8, const void* dp8, const float* scale, const float* shift,
                                 const float* mean, const float* invstd, const double* sums, float* dw, double* dbsum,
                                 float* work, int N, int n_per_view, int Cout, int H, int W, int K, int pad, void* stream);
 /* BatchNorm-apply + ReLU + MaxPool2 on bf16 act8 activations (same reference call sites as b200_bn_relu_pool_*):

@@ -237,33 +237,24 @@ __global__ void __launch_bounds__(T) aug_apply_kernel(const void* __restrict__ s
         float4* o4 = reinterpret_cast<float4*>(out + ((size_t)v * B + b) * NPIX);
         for (int i = tid; i < NPIX / 4; i += T) o4[i] = reinterpret_cast<const float4*>(cur)[i];
     }
-    // ---- and / or the bf16 "shift8" image of the first-layer tensor-core convolution: [V,B,S,S+pad,8], unit (y, xs) =
-    //      x[y][xs-pad .. xs-pad+7] (zero outside the row); see conv_tc.cu ----
+    // ---- and / or the bf16 "quad8" image of the first-layer tensor-core convolution: [V,B,S,WQ,8], WQ = ceil((S + 2 pad) / 4),
+    //      unit (y, xq) = the zero-padded row's pixels 4xq .. 4xq+7 (padded column c = image column c - pad); see conv_tc.cu ----
     if (out8 != nullptr) {
-        const int WT = S + pad8, QW = (WT + 3) / 4;            // a thread writes 4 consecutive units of a row from 11 values
-        uint4* o8 = out8 + ((size_t)v * B + b) * S * WT;
-        for (int i = tid; i < S * QW; i += T) {
-            const int y = i / QW, xs = (i - y * QW) * 4;
+        const int WQ = (S + 2 * pad8 + 3) / 4;
+        uint4* o8 = out8 + ((size_t)v * B + b) * S * WQ;
+        for (int i = tid; i < S * WQ; i += T) {
+            const int y = i / WQ, xq = i - y * WQ;
             const float* r = cur + y * S;
-            float f[11];
+            float f[8];
 #pragma unroll
-            for (int c = 0; c < 11; ++c) {
-                const int xc = xs - pad8 + c;
+            for (int c = 0; c < 8; ++c) {
+                const int xc = 4 * xq - pad8 + c;
                 f[c] = (xc >= 0 && xc < S) ? r[xc] : 0.f;
             }
-            uint32_t ev[5], od[5];                             // bf16 pairs starting at even / odd offsets
-#pragma unroll
-            for (int h = 0; h < 5; ++h) {
-                __nv_bfloat162 a2 = __floats2bfloat162_rn(f[2 * h], f[2 * h + 1]);
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * h + 1], f[2 * h + 2]);
-                ev[h] = *reinterpret_cast<uint32_t*>(&a2);
-                od[h] = *reinterpret_cast<uint32_t*>(&b2);
-            }
-            uint4* dst = o8 + (size_t)y * WT + xs;
-            dst[0] = make_uint4(ev[0], ev[1], ev[2], ev[3]);
-            if (xs + 1 < WT) dst[1] = make_uint4(od[0], od[1], od[2], od[3]);
-            if (xs + 2 < WT) dst[2] = make_uint4(ev[1], ev[2], ev[3], ev[4]);
-            if (xs + 3 < WT) dst[3] = make_uint4(od[1], od[2], od[3], od[4]);
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
+            o8[i] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2),
+                               *reinterpret_cast<uint32_t*>(&p3));
         }
     }
 }
@@ -446,19 +437,19 @@ using namespace b200;
 
 extern "C" {
 
-int b200_aug_apply_image(const void* src, int src_u8, const int32_t* ops, float* out, void* out_shift8, int pad, int B, int V, void* stream) {
-    B200_REQUIRE(src && ops && (out || out_shift8) && B > 0 && V > 0 && pad >= 0, B200_E_ARG, "aug_apply_image: bad arguments");
-    B200_REQUIRE((((uintptr_t)src | (uintptr_t)out | (uintptr_t)out_shift8) & 15) == 0, B200_E_ARG, "aug_apply_image: pointers must be 16-byte aligned");
+int b200_aug_apply_image(const void* src, int src_u8, const int32_t* ops, float* out, void* out_quad8, int pad, int B, int V, void* stream) {
+    B200_REQUIRE(src && ops && (out || out_quad8) && B > 0 && V > 0 && pad >= 0, B200_E_ARG, "aug_apply_image: bad arguments");
+    B200_REQUIRE((((uintptr_t)src | (uintptr_t)out | (uintptr_t)out_quad8) & 15) == 0, B200_E_ARG, "aug_apply_image: pointers must be 16-byte aligned");
     constexpr int S = 28, T = 128;
     const size_t smem = 2 * S * S * sizeof(float) + 2 * S * sizeof(AATable);
-    aug_apply_kernel<S, T><<<B * V, T, smem, as_stream(stream)>>>(src, src_u8, ops, nullptr, nullptr, 0, out, reinterpret_cast<uint4*>(out_shift8), pad, B, V);
+    aug_apply_kernel<S, T><<<B * V, T, smem, as_stream(stream)>>>(src, src_u8, ops, nullptr, nullptr, 0, out, reinterpret_cast<uint4*>(out_quad8), pad, B, V);
     return launch_status("aug_apply_image");
 }
 
 int b200_aug_apply_audio(const void* src, int src_u8, const int32_t* ops, const uint32_t* group_bits, const float* noise,
-                         uint64_t seed, float* out, void* out_shift8, int pad, int B, int V, void* stream) {
-    B200_REQUIRE(src && ops && group_bits && (out || out_shift8) && B > 0 && V > 0 && pad >= 0, B200_E_ARG, "aug_apply_audio: bad arguments");
-    B200_REQUIRE((((uintptr_t)src | (uintptr_t)out | (uintptr_t)out_shift8) & 15) == 0, B200_E_ARG, "aug_apply_audio: pointers must be 16-byte aligned");
+                         uint64_t seed, float* out, void* out_quad8, int pad, int B, int V, void* stream) {
+    B200_REQUIRE(src && ops && group_bits && (out || out_quad8) && B > 0 && V > 0 && pad >= 0, B200_E_ARG, "aug_apply_audio: bad arguments");
+    B200_REQUIRE((((uintptr_t)src | (uintptr_t)out | (uintptr_t)out_quad8) & 15) == 0, B200_E_ARG, "aug_apply_audio: pointers must be 16-byte aligned");
     constexpr int S = 112, T = 512;
     const size_t smem = 2 * S * S * sizeof(float) + 2 * S * sizeof(AATable);
     static bool attr_done = false;
@@ -467,7 +458,7 @@ int b200_aug_apply_audio(const void* src, int src_u8, const int32_t* ops, const 
         B200_REQUIRE(e == cudaSuccess, B200_E_SMEM, "aug_apply_audio: cannot reserve %zu B of shared memory", smem);
         attr_done = true;
     }
-    aug_apply_kernel<S, T><<<B * V, T, smem, as_stream(stream)>>>(src, src_u8, ops, group_bits, noise, seed, out, reinterpret_cast<uint4*>(out_shift8), pad, B, V);
+    aug_apply_kernel<S, T><<<B * V, T, smem, as_stream(stream)>>>(src, src_u8, ops, group_bits, noise, seed, out, reinterpret_cast<uint4*>(out_quad8), pad, B, V);
     return launch_status("aug_apply_audio");
 }
 

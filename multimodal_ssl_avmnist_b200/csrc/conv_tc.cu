@@ -76,7 +76,10 @@ struct TMaps {
 template <int CIN_, int COUT_, int NPAD_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int CTAS_ = 1, int NSPLIT_ = 1>
 struct TcCfg {
     static constexpr int NSPLIT = NSPLIT_;                      // output channels split over gridDim.z (halves the smem weight image)
-    static constexpr int XPH = xph_for(CIN_, COUT_, KS_);       // output x phases packed into N
+    // First layers (C_in = 1) read the "quad8" image: unit (y, xq) = the 8 padded-row pixels 4*xq .. 4*xq+7, which are exactly
+    // the taps kw' = ph + kw < 8 of the four output phases -- only that one plane exists (no other phase planes to load)
+    static constexpr int XPH = CIN_ == 1 ? 4 : xph_for(CIN_, COUT_, KS_);       // output x phases packed into N
+    static constexpr int XPL = CIN_ == 1 ? 1 : XPH;             // phase planes of the input slab in shared memory
     static constexpr int NPADL = XPH == 1 ? NPAD_ / NSPLIT_ : round_up(XPH * COUT_, 16), COUTL = COUT_ / NSPLIT_;
     static_assert(NSPLIT_ == 1 || (XPH == 1 && COUT_ == NPAD_ && NPADL % 16 == 0), "N split needs C_out == NPAD and 16-channel slices");
     static constexpr int CIN = CIN_, COUT = COUT_, NPAD = NPAD_, HIN = HIN_, WIN = WIN_, KS = KS_, PAD = PAD_, BANDS = BANDS_, SLOTS = SLOTS_;
@@ -94,14 +97,15 @@ struct TcCfg {
     static constexpr int TILES = (Q + 127) / 128;
     static constexpr int PLANE_BYTES = HPB * WQ * 16;           // one (x phase, channel plane)
     static constexpr int PHASE_BYTES = P * PLANE_BYTES;
-    static constexpr int SLOT_BYTES = round_up(XPH * PHASE_BYTES, 128);
+    static constexpr int SLOT_BYTES = round_up(XPL * PHASE_BYTES, 128);
     static constexpr int NJ = (KWX + 1) / 2;                    // kw' pairs when CIN == 8
     static constexpr int PH = P / 2;                            // plane pairs when CIN >= 16
     static constexpr int NMMA = L0 ? (KS + 1) / 2 : (CIN == 8) ? KS * NJ : KS * KWX * PH;
     static constexpr int W_BYTES = round_up(NMMA * NPADL * 32, 128);
     static constexpr int MAXPIX = TILES * 128 + (L0 ? KS : KS - 1) * WQ + (KWX - 1) / XPH + 2;   // exclusive bound of units a tile may touch
     static constexpr int TAIL = round_up((MAXPIX > HPB * WQ ? (MAXPIX - HPB * WQ) : 0) * 16, 128) + 128;
-    static_assert(XPH == 1 || (!L0 && WO % XPH == 0 && WIN % XPH == 0 && XPH <= 4 && (CIN != 8 || (XPH % 2 == 0 && KWX % 2 == 0))), "x phases");
+    static_assert(XPH == 1 || (WO % XPH == 0 && WIN % XPH == 0 && XPH <= 4 && (CIN != 8 || (XPH % 2 == 0 && KWX % 2 == 0))), "x phases");
+    static_assert(!L0 || KWX <= 8, "first layer: all taps of all phases must lie inside one 8-pixel unit");
     static constexpr int IMG_BYTES = SLOTS * SLOT_BYTES + TAIL;
     static constexpr int BAR_OFF = W_BYTES + IMG_BYTES;
     static constexpr int SMEM = BAR_OFF + 256 + NPADL * 4;
@@ -116,10 +120,10 @@ struct TcCfg {
     static_assert((SMEM_EST(NMMA, NPADL, SLOTS, SLOT_BYTES, TAIL) + 1024) * CTAS <= 227 * 1024, "shared memory per SM");
     static_assert(2 * SLOTS + 2 * NBUF <= 24, "barrier area");
     static_assert(CIN == 1 || (CIN % 8 == 0 && (CIN == 8 || CIN % 16 == 0)), "C_in must be 1, 8 or a multiple of 16");
-    static_assert(NPAD % 16 == 0 && NPAD >= 16 && NPADL <= 64 && COUT <= NPAD && COUT % 8 == 0, "N tile");
+    static_assert(NPAD % 16 == 0 && NPAD >= 16 && NPADL <= 128 && COUT <= NPAD && COUT % 8 == 0, "N tile");
     static_assert(HO % BANDS == 0, "bands must divide the output height");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
-    static_assert(XPH * P * PLANE_BYTES < (1 << 18) && PLANE_BYTES % 16 == 0, "descriptor range");
+    static_assert(XPL * P * PLANE_BYTES < (1 << 18) && PLANE_BYTES % 16 == 0, "descriptor range");
 };
 
 // out: fp32 NCHW [N][COUT][HO][WO] (out_bf16 == 0), bf16 act8 [N][COUT/8][HO][WO][8] (1) or the same in fp16 (2: the pre-BatchNorm
@@ -163,7 +167,7 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
         fence_proxy_async_smem();
     }
     if (warp == 0 && lane == 0) {
-        for (int r = 0; r < C::XPH; ++r) prefetch_tmap(&tmaps.m[r]);
+        for (int r = 0; r < C::XPL; ++r) prefetch_tmap(&tmaps.m[r]);
         for (int s = 0; s < C::SLOTS; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), C::ISS);
@@ -187,10 +191,10 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
             for (int i = i0; i < i1; ++i) {
                 const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
                 mbar_wait(empty_bar(slot), (use & 1) ^ 1);
-                mbar_expect_tx(full_bar(slot), C::XPH * C::PHASE_BYTES);
+                mbar_expect_tx(full_bar(slot), C::XPL * C::PHASE_BYTES);
                 const int n = view * n_per_view + i / C::BANDS, band = i % C::BANDS;
 #pragma unroll
-                for (int rp = 0; rp < C::XPH; ++rp) {
+                for (int rp = 0; rp < C::XPL; ++rp) {
                     // phase plane rp holds the padded columns x' = XPH*i + rp, i.e. the global columns x' - PAD = XPH*(i + a) + r
                     constexpr int X = C::XPH;
                     const int r = ((rp - C::PAD) % X + X) % X, a = (rp - C::PAD - r) / X;
@@ -219,8 +223,8 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
                     if constexpr (C::L0) {
                         // K = (2 rows kh, kh+1) x (8 shifts = kw taps): one MMA per row pair, second K chunk = next image row
 #pragma unroll
-                        for (int j = 0; j < C::NJ; ++j, ++idx) {
-                            const uint64_t ad = smem_desc(a0 + (2 * j * C::WP) * 16, C::WP * 16, 128);
+                        for (int j = 0; j < C::NMMA; ++j, ++idx) {         // (K + 1) / 2 row pairs
+                            const uint64_t ad = smem_desc(a0 + (2 * j * C::WQ) * 16, C::WQ * 16, 128);
                             const uint64_t bd = smem_desc(w_addr + idx * C::NPADL * 32, C::NPADL * 16, 128);
                             mma_bf16(d, ad, bd, idesc, idx > 0);
                         }
@@ -360,12 +364,12 @@ __global__ void conv_tc_prep_weights_kernel(const float* __restrict__ w, __nv_bf
     const int col = ng * 8 + r, ph = col / COUT, co = col % COUT;      // accumulator column = (x phase, output channel)
     const int KWX = KS + XPH - 1;
     int kh, kw, ci;
-    if (CIN == 1) {                 // shift8 first layer: chunk c of MMA m is image row kh = 2m + c, k8 is the kw tap
+    if (CIN == 1) {                 // quad8 first layer: chunk c of MMA m is image row kh = 2m + c, k8 is the tap kw' = ph + kw
         kh = 2 * m + c;
-        kw = k8;
+        kw = k8 - ph;
         ci = 0;
         float v1 = 0.f;
-        if (kh < KS && kw < KS && col < COUT) v1 = w[(co * KS + kh) * KS + kw];
+        if (kh < KS && kw >= 0 && kw < KS && ph < XPH) v1 = w[(co * KS + kh) * KS + kw];
         out[e] = __float2bfloat16_rn(v1);
         return;
     } else if (CIN == 8) {
@@ -422,6 +426,23 @@ __global__ void pack_shift8_kernel(const float* __restrict__ x, uint4* __restric
     out[i] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
 
+// fp32 [N][H][W] -> bf16 quad8 [N][H][WQ][8], WQ = ceil((W + 2 pad) / 4): unit (y, xq) = padded-row pixels 4*xq .. 4*xq+7
+// (padded column c is image column c - pad, zero outside the row).  Each pixel appears in two units: 4 bytes per pixel.
+__global__ void pack_quad8_kernel(const float* __restrict__ x, uint4* __restrict__ out, long n_units, int W, int WQ, int pad) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_units) return;
+    const int xq = (int)(i % WQ);
+    const long row = i / WQ;
+    const float* r = x + row * W;
+    float f[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int xc = 4 * xq - pad + c;
+        f[c] = (xc >= 0 && xc < W) ? __ldg(r + xc) : 0.f;
+    }
+    out[i] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
 template <class C>
 int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* out, double* stats, int N, int n_per_view, int out_bf16,
                    cudaStream_t st) {
@@ -435,15 +456,15 @@ int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* ou
         configured = true;
     }
     TMaps tm;
-    constexpr uint64_t WT = C::L0 ? C::WIN + C::PAD : C::WIN;      // the shift8 image carries its left padding columns
-    for (int r = 0; r < C::XPH; ++r) {                             // map r: the columns x = XPH*i + r of every row
-        const uint64_t dims[4] = {8, WT / C::XPH, (uint64_t)C::HIN, (uint64_t)N * C::P};
-        const uint64_t strides[3] = {16 * (uint64_t)C::XPH, WT * 16, WT * C::HIN * 16};
+    constexpr uint64_t WT = C::L0 ? C::WQ : C::WIN;                // quad8 image: WQ units per row, left padding materialised
+    for (int r = 0; r < C::XPL; ++r) {                             // map r: the columns x = XPH*i + r of every row
+        const uint64_t dims[4] = {8, WT / C::XPL, (uint64_t)C::HIN, (uint64_t)N * C::P};
+        const uint64_t strides[3] = {16 * (uint64_t)C::XPL, WT * 16, WT * C::HIN * 16};
         const uint32_t box[4] = {8, (uint32_t)C::WQ, (uint32_t)C::HPB, (uint32_t)C::P};
         int rc = encode_tmap_bf16_4d(&tm.m[r], reinterpret_cast<const uint8_t*>(x) + 16 * r, dims, strides, box);
         if (rc) return rc;
     }
-    for (int r = C::XPH; r < 4; ++r) tm.m[r] = tm.m[0];
+    for (int r = C::XPL; r < 4; ++r) tm.m[r] = tm.m[0];
     const int views = N / n_per_view;
     int G = sm_count() * C::CTAS / (views * C::NSPLIT);
     if (G < 1) G = 1;
@@ -495,7 +516,9 @@ struct TcWgCfg {
     static constexpr int PART = DW;                                 // floats per CTA partial
     static_assert(P_IN % PSPLIT == 0 && HO % BANDS == 0, "splits");
     static_assert(BANDS == 1 || HBZ == HB, "row bands need HB*WP to be a multiple of 16");
-    static constexpr int ISS = (L0 || NACC < 4) ? 1 : (CTAS >= 3 ? 1 : (CTAS == 2 ? 2 : 4));   // MMA-issuer warps (accumulators split among them)
+    // MMA-issuer warps; the accumulators (kh, x plane) are dealt out among them, so the count divides NACC where it can: 5
+    // accumulators on 4 issuers would leave three of them idle half of the time
+    static constexpr int ISS = (L0 || NACC < 4 || CTAS >= 3) ? 1 : (NACC <= 6 ? NACC : 4);
     static constexpr int THREADS = 32 * (1 + ISS + 4);
     static_assert(NACC * COUTL <= 512 && TMEM_COLS * CTAS <= 512 && COUTL % 8 == 0, "TMEM columns");
     static_assert((SMEM + 1024) * CTAS <= 227 * 1024, "shared memory per SM");
@@ -689,29 +712,58 @@ int launch_conv_tc_wgrad(const void* x, const void* dz, float* dw, float* work, 
 // First layer, fused backward: BatchNorm-apply / ReLU / max-pool backward + weight gradient in ONE kernel.  The first layer
 // needs no data gradient, so its dz (the largest tensor of the backward pass) has a single consumer: instead of writing it
 // to HBM and reading it back, the pre-BatchNorm z tile (fp16 act8) is TMA-loaded straight into the position of the dz MMA
-// operand (padded pitch, zero-filled junk columns), four warps transform it IN PLACE into dz = ca*z + cb + [arg-max] a*g
-// (bf16) from the pooled gradient tile, fence it to the async proxy, and the MMA warp accumulates dW exactly as in
-// conv_tc_wgrad_kernel.  The same warps accumulate the conv bias gradient sum(dz).
+// operand, four warps transform it IN PLACE into dz = ca*z + cb + [arg-max] a*g (bf16) from the pooled gradient tile, fence
+// it to the async proxy, and the MMA warps accumulate dW.  The same warps accumulate the conv bias gradient sum(dz).
+//
+// Operands (both MN-major, K = flat index of PIXEL GROUPS xq over the pitch WQ of the quad8 image, 4 pixels per group):
+//   A (M = 64): the quad8 x slab; M units = 8 image rows kh (SBO = one row), the 8 elements of a unit = taps kw' = ph + kw;
+//   B (N = 4*C_out): dz de-interleaved by output phase ph = x mod 4 (one strided TMA map per phase, like the forward
+//               convolution's input planes): N units = (ph, channel octet) planes, SBO = plane stride.
+//   D[(kh, kw')][(ph, co)] = sum_xq x[.., 4xq + kw'] dz[co][.., 4xq + ph]   =>   dW[co][kh][kw] = sum_ph D[(kh, kw + ph)][(ph, co)]
+// -- a quarter of the K steps of the one-pixel-per-row formulation, at N = 32 / 128 instead of 8 / 32.
 //   cst: per (view, channel) constants float4 {a, b, ca, cb} prepared by wgrad_l0_consts_kernel from the BatchNorm tensors.
 constexpr int L0F_ISS = 3;                       // MMA-issuer warps (K steps interleaved, one TMEM accumulator each)
 constexpr int L0F_THREADS = 32 * (1 + L0F_ISS + 4);
+
+template <int COUT_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int CTAS_>
+struct L0FCfg {
+    static constexpr int COUT = COUT_, HIN = HIN_, WIN = WIN_, KS = KS_, PAD = PAD_, BANDS = BANDS_, SLOTS = SLOTS_, CTAS = CTAS_;
+    static constexpr int P_OUT = COUT / 8, NTOT = 4 * COUT;
+    static constexpr int WP = WIN + 2 * PAD, WQ = (WP + 3) / 4;                  // quad8 units per row
+    static constexpr int HO = HIN + 2 * PAD - KS + 1, WO = WP - KS + 1;
+    static constexpr int HB = HO / BANDS, HPB = HB + KS - 1, HBZ = hbz_for(HB, WQ);
+    static constexpr int KSTEPS = HBZ * WQ / 16;
+    static constexpr int PLANE_X = HPB * WQ * 16, PLANE_Z = HBZ * WQ * 16;       // x slab; one (phase, octet) dz plane
+    static constexpr int X_BYTES = round_up(PLANE_X, 128), Z_BYTES = round_up(4 * P_OUT * PLANE_Z, 128);
+    static constexpr int HBP = HB / 2, WOP = WO / 2;                             // pooled rows / columns of a band
+    static constexpr int G_BYTES = round_up(P_OUT * HBP * WOP * 16, 128);
+    static constexpr int SLOT = X_BYTES + Z_BYTES + G_BYTES;
+    static constexpr int STAGE_BYTES = 4 * COUT * KS * KS * 4;                   // end-of-kernel staging of the phase terms
+    static constexpr int CST_OFF = SLOTS * SLOT, BAR_OFF = CST_OFF + COUT * 16 + 4 * COUT * 4;
+    static constexpr int SMEM = BAR_OFF + 256;
+    static constexpr int ACC_COLS = round_up(NTOT, 32), TCOLS = pow2_cols(L0F_ISS * ACC_COLS);
+    static constexpr int PART = COUT * KS * KS;
+    static_assert(HO == HIN && WO == WIN && HO % BANDS == 0 && HB % 2 == 0 && WO % 4 == 0 && COUT % 8 == 0, "geometry");
+    static_assert(KS + 3 <= 8, "all taps of all phases must lie inside one 8-pixel unit");
+    static_assert(BANDS == 1 || HBZ == HB, "row bands need HB*WQ to be a multiple of 16");
+    static_assert(TCOLS * CTAS <= 512 && NTOT <= 256 && NTOT % 16 == 0, "TMEM columns / N");
+    static_assert((SMEM + 1024) * CTAS <= 227 * 1024, "shared memory per SM");
+    static_assert(STAGE_BYTES <= SLOT, "staging reuses the first slot");
+    static_assert((KSTEPS * 16 + 7 * WQ + 8 - HPB * WQ) * 16 <= Z_BYTES, "x overrun must stay inside the slot");
+    static_assert(KSTEPS >= L0F_ISS, "every issuer needs a K step");
+};
+
 template <class C>
 __global__ void __launch_bounds__(L0F_THREADS, C::CTAS)
-conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_z,
+conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ TMaps tmaps_z,
                               const __grid_constant__ CUtensorMap tmap_g, const float4* __restrict__ cst, float* __restrict__ work,
                               double* __restrict__ dbsum, int N, int n_per_view) {
-    static_assert(C::L0 && C::PSPLIT == 1 && C::NSPLIT == 1 && (C::HB % 2) == 0 && (C::WO % 2) == 0, "first-layer geometry");
-    constexpr int HBP = C::HB / 2, WOP = C::WO / 2;                      // pooled rows / columns of a band
-    constexpr int ACC_COLS = round_up(C::COUT, 32), TCOLS = pow2_cols(L0F_ISS * ACC_COLS);
-    static_assert(TCOLS * C::CTAS <= 512, "TMEM columns per SM");
-    constexpr int G_BYTES = round_up(C::P_OUT * HBP * WOP * 16, 128);    // pooled-gradient tile
-    constexpr int SLOT = C::X_BYTES + C::Z_BYTES + G_BYTES;
-    constexpr int CST_OFF = C::SLOTS * SLOT, BAR_OFF = CST_OFF + C::COUT * 16 + 4 * C::COUT * 4;
+    constexpr int HBP = C::HBP, WOP = C::WOP, SLOT = C::SLOT;
     extern __shared__ __align__(1024) uint8_t smem[];
-    float4* cst_s = reinterpret_cast<float4*>(smem + CST_OFF);
-    float* db_s = reinterpret_cast<float*>(smem + CST_OFF + C::COUT * 16);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);        // full[S], ready[S], empty[S], done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 200);
+    float4* cst_s = reinterpret_cast<float4*>(smem + C::CST_OFF);
+    float* db_s = reinterpret_cast<float*>(smem + C::CST_OFF + C::COUT * 16);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);     // full[S], ready[S], empty[S], done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::BAR_OFF + 200);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, g = blockIdx.x;
     const long items = (long)N * C::BANDS;
@@ -723,13 +775,13 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
     const uint32_t done_bar = bar0 + 8u * (3 * C::SLOTS);
     {
         uint4* z = reinterpret_cast<uint4*>(smem);
-        for (int i = threadIdx.x; i < CST_OFF / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < C::CST_OFF / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
         for (int i = threadIdx.x; i < 4 * C::COUT; i += blockDim.x) db_s[i] = 0.f;       // [transform warp][channel]
         fence_proxy_async_smem();
     }
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_x);
-        prefetch_tmap(&tmap_z);
+        for (int r = 0; r < 4; ++r) prefetch_tmap(&tmaps_z.m[r]);
         prefetch_tmap(&tmap_g);
         for (int s = 0; s < C::SLOTS; ++s) {
             mbar_init(full_bar(s), 1);
@@ -739,7 +791,7 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
         mbar_init(done_bar, L0F_ISS);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<TCOLS>(smem_u32(tmem_slot));
+    if (warp == 1) tmem_alloc<C::TCOLS>(smem_u32(tmem_slot));
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -751,11 +803,13 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
             for (int i = i0; i < i1; ++i) {
                 const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
                 mbar_wait(empty_bar(slot), (use & 1) ^ 1);
-                mbar_expect_tx(full_bar(slot), C::PLANE_X + C::P_OUT * C::PLANE_Z + C::P_OUT * HBP * WOP * 16);
+                mbar_expect_tx(full_bar(slot), C::PLANE_X + 4 * C::P_OUT * C::PLANE_Z + C::P_OUT * HBP * WOP * 16);
                 const int n = i / C::BANDS, band = i % C::BANDS;
                 const uint32_t sa = smem0 + slot * SLOT;
                 tma_load_4d(sa, &tmap_x, full_bar(slot), 0, 0, band * C::HB - C::PAD, n);
-                tma_load_4d(sa + C::X_BYTES, &tmap_z, full_bar(slot), 0, 0, band * C::HB, n * C::P_OUT);
+#pragma unroll
+                for (int ph = 0; ph < 4; ++ph)      // columns x = 4*xq + ph of every z row -> plane group ph
+                    tma_load_4d(sa + C::X_BYTES + ph * C::P_OUT * C::PLANE_Z, &tmaps_z.m[ph], full_bar(slot), 0, 0, band * C::HB, n * C::P_OUT);
                 tma_load_4d(sa + C::X_BYTES + C::Z_BYTES, &tmap_g, full_bar(slot), 0, 0, band * HBP, n * C::P_OUT);
             }
         }
@@ -763,9 +817,9 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
         if (lane == 0) {
             // issuer w takes the K steps ks = w, w + ISS, ... of every item and owns accumulator w (summed in the epilogue):
             // one issuing thread sustains only ~1 MMA / 140 cycles, the tensor pipe of the SM about four times that
-            constexpr uint32_t idesc = idesc_bf16(C::COUT, true, true, 64);
+            constexpr uint32_t idesc = idesc_bf16(C::NTOT, true, true, 64);
             const int w = warp - 1;
-            const uint32_t acc = tmem_base + w * ACC_COLS;
+            const uint32_t acc = tmem_base + w * C::ACC_COLS;
             for (int i = i0; i < i1; ++i) {
                 const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
                 mbar_wait(ready_bar(slot), use & 1);
@@ -773,7 +827,7 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
                 const uint32_t xa = smem0 + slot * SLOT, za = xa + C::X_BYTES;
                 for (int ks = w; ks < C::KSTEPS; ks += L0F_ISS) {
                     const uint64_t bd = smem_desc(za + ks * 256, 128, C::PLANE_Z);
-                    const uint64_t ad = smem_desc(xa + ks * 256, 128, C::WP * 16);
+                    const uint64_t ad = smem_desc(xa + ks * 256, 128, C::WQ * 16);
                     mma_bf16(acc, ad, bd, idesc, (i > i0 || ks >= L0F_ISS) ? 1u : 0u);
                 }
                 mma_commit(empty_bar(slot));
@@ -808,8 +862,11 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
                 }
                 for (int e = t; e < HBP * WOP; e += 128) {
                     const int py = e / WOP, px = e - py * WOP;
-                    uint4* zp = reinterpret_cast<uint4*>(zimg + (size_t)o * C::PLANE_Z) + (2 * py) * C::WP + 2 * px;
-                    const uint4 raw[4] = {zp[0], zp[1], zp[C::WP], zp[C::WP + 1]};
+                    // pooling window: rows 2py, 2py+1; columns 2px, 2px+1 = pixel group px/2, phases 2(px&1) and 2(px&1)+1
+                    const int ph0 = 2 * (px & 1);
+                    uint4* zp0 = reinterpret_cast<uint4*>(zimg + (size_t)(ph0 * C::P_OUT + o) * C::PLANE_Z) + (2 * py) * C::WQ + (px >> 1);
+                    uint4* zp1 = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(zp0) + (size_t)C::P_OUT * C::PLANE_Z);
+                    const uint4 raw[4] = {zp0[0], zp1[0], zp0[C::WQ], zp1[C::WQ]};
                     const uint4 graw = gimg[o * (HBP * WOP) + e];
                     uint32_t outw[4][4];
 #pragma unroll
@@ -844,10 +901,10 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
 #pragma unroll
                         for (int q = 0; q < 4; ++q) outw[q][h] = pack_bf16(res[q][0], res[q][1]);
                     }
-                    zp[0] = make_uint4(outw[0][0], outw[0][1], outw[0][2], outw[0][3]);
-                    zp[1] = make_uint4(outw[1][0], outw[1][1], outw[1][2], outw[1][3]);
-                    zp[C::WP] = make_uint4(outw[2][0], outw[2][1], outw[2][2], outw[2][3]);
-                    zp[C::WP + 1] = make_uint4(outw[3][0], outw[3][1], outw[3][2], outw[3][3]);
+                    zp0[0] = make_uint4(outw[0][0], outw[0][1], outw[0][2], outw[0][3]);
+                    zp1[0] = make_uint4(outw[1][0], outw[1][1], outw[1][2], outw[1][3]);
+                    zp0[C::WQ] = make_uint4(outw[2][0], outw[2][1], outw[2][2], outw[2][3]);
+                    zp1[C::WQ] = make_uint4(outw[3][0], outw[3][1], outw[3][2], outw[3][3]);
                 }
                 if (dbsum != nullptr) {
 #pragma unroll
@@ -867,41 +924,48 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
         if (t < C::COUT && dbsum != nullptr)
             atomicAdd(&dbsum[t], (double)db_s[t] + (double)db_s[C::COUT + t] + (double)db_s[2 * C::COUT + t] + (double)db_s[3 * C::COUT + t]);
         const int quad = warp & 3;
-        const int m = quad * 16 + (lane & 15), j = m >> 3, ci8 = m & 7;
+        const int m = quad * 16 + (lane & 15), j = m >> 3, e8 = m & 7;   // accumulator row = (image row kh = j, tap kw' = e8)
         float* part = work + (long)g * C::PART;
+        float* stage = reinterpret_cast<float*>(smem);                   // [ph][co][kh][kw]: every MMA has completed (done_bar)
         if (i1 > i0) {
             mbar_wait(done_bar, 0);
             tc_fence_after_sync();
-        }
+#pragma unroll 1
+            for (int cc = 0; cc < C::NTOT / 16; ++cc) {
+                float sum[16];
 #pragma unroll
-        for (int cc = 0; cc < (C::COUT + 15) / 16; ++cc) {
-            float sum[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) sum[q] = 0.f;
-            if (i1 > i0) {
+                for (int q = 0; q < 16; ++q) sum[q] = 0.f;
 #pragma unroll
                 for (int w = 0; w < L0F_ISS; ++w) {
-                    if (w < C::KSTEPS) {                                  // (every issuer has at least one K step)
-                        uint32_t v[16];
-                        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + w * ACC_COLS + cc * 16, v);
-                        tmem_ld_wait();
+                    uint32_t v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + w * C::ACC_COLS + cc * 16, v);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) sum[q] += __uint_as_float(v[q]);
-                    }
+                    for (int q = 0; q < 16; ++q) sum[q] += __uint_as_float(v[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int col = cc * 16 + q, ph = col / C::COUT, co = col % C::COUT;
+                    const int kw = e8 - ph;
+                    if (lane < 16 && j < C::KS && kw >= 0 && kw < C::KS) stage[((ph * C::COUT + co) * C::KS + j) * C::KS + kw] = sum[q];
                 }
             }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int idx = t; idx < C::PART; idx += 128) {                   // fixed summation order over the four phases
+            float v = 0.f;
+            if (i1 > i0) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const int co = cc * 16 + q;
-                if (co < C::COUT && lane < 16 && j < C::KS && ci8 < C::KS) part[(co * C::KS + j) * C::KS + ci8] = sum[q];
+                for (int ph = 0; ph < 4; ++ph) v += stage[ph * C::PART + idx];
             }
+            part[idx] = v;
         }
     }
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after_sync();
-        tmem_dealloc<TCOLS>(tmem_base);
+        tmem_dealloc<C::TCOLS>(tmem_base);
     }
 }
 
@@ -920,12 +984,10 @@ template <class C>
 int launch_conv_tc_wgrad_l0_fused(const void* x, const void* z, const void* dp, const float* scale, const float* shift, const float* mean,
                                   const float* invstd, const double* sums, float* dw, double* dbsum, float* work, int N, int n_per_view,
                                   cudaStream_t st, int64_t* need) {
-    constexpr int HBP = C::HB / 2, WOP = C::WO / 2;
-    constexpr int G_BYTES = round_up(C::P_OUT * HBP * WOP * 16, 128);
-    constexpr int SLOT = C::X_BYTES + C::Z_BYTES + G_BYTES;
-    constexpr int SMEM = C::SLOTS * SLOT + C::COUT * 32 + 256;
-    static_assert((SMEM + 1024) * C::CTAS <= 227 * 1024, "shared memory per SM");
-    const int G = wgrad_ctas<C>(N);
+    int G = sm_count() * C::CTAS;
+    const long items = (long)N * C::BANDS;
+    if (G > items) G = (int)items;
+    if (G < 1) G = 1;
     const int views = N / n_per_view;
     const int64_t cst_floats = (int64_t)views * C::COUT * 4;
     if (need) {
@@ -934,9 +996,9 @@ int launch_conv_tc_wgrad_l0_fused(const void* x, const void* z, const void* dp, 
     }
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_l0_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_l0_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) {
-            set_error("conv_tc_wgrad_l0_fused: cannot set %d bytes of shared memory: %s", SMEM, cudaGetErrorString(e));
+            set_error("conv_tc_wgrad_l0_fused: cannot set %d bytes of shared memory: %s", C::SMEM, cudaGetErrorString(e));
             return (int)e;
         }
         configured = true;
@@ -944,30 +1006,30 @@ int launch_conv_tc_wgrad_l0_fused(const void* x, const void* z, const void* dp, 
     float4* cst = reinterpret_cast<float4*>(work + (((int64_t)G * C::PART + 3) / 4) * 4);
     wgrad_l0_consts_kernel<<<(views * C::COUT + 127) / 128, 128, 0, st>>>(scale, shift, mean, invstd, sums,
                                                                           1.0f / ((float)n_per_view * C::HO * C::WO), views * C::COUT, cst);
-    CUtensorMap tx, tz, tg;
+    CUtensorMap tx, tg;
+    TMaps tz;
     {
-        constexpr uint64_t WT = C::WIN + C::PAD;
-        const uint64_t dims[4] = {8, WT, (uint64_t)C::HIN, (uint64_t)N};
-        const uint64_t strides[3] = {16, WT * 16, WT * C::HIN * 16};
-        const uint32_t box[4] = {8, (uint32_t)C::WP, (uint32_t)C::HPB, 1};
+        const uint64_t dims[4] = {8, (uint64_t)C::WQ, (uint64_t)C::HIN, (uint64_t)N};
+        const uint64_t strides[3] = {16, (uint64_t)C::WQ * 16, (uint64_t)C::WQ * C::HIN * 16};
+        const uint32_t box[4] = {8, (uint32_t)C::WQ, (uint32_t)C::HPB, 1};
         int rc = encode_tmap_bf16_4d(&tx, x, dims, strides, box);
         if (rc) return rc;
     }
-    {
-        const uint64_t dims[4] = {8, (uint64_t)C::WO, (uint64_t)C::HO, (uint64_t)N * C::P_OUT};
-        const uint64_t strides[3] = {16, (uint64_t)C::WO * 16, (uint64_t)C::WO * C::HO * 16};
-        const uint32_t box[4] = {8, (uint32_t)C::WP, (uint32_t)C::HBZ, (uint32_t)C::P_OUT};
-        int rc = encode_tmap_bf16_4d(&tz, z, dims, strides, box);          // fp16 data: same 2-byte elements, no conversion
+    for (int ph = 0; ph < 4; ++ph) {        // fp16 data: same 2-byte elements, no conversion; columns 4*i + ph
+        const uint64_t dims[4] = {8, (uint64_t)C::WO / 4, (uint64_t)C::HO, (uint64_t)N * C::P_OUT};
+        const uint64_t strides[3] = {64, (uint64_t)C::WO * 16, (uint64_t)C::WO * C::HO * 16};
+        const uint32_t box[4] = {8, (uint32_t)C::WQ, (uint32_t)C::HBZ, (uint32_t)C::P_OUT};
+        int rc = encode_tmap_bf16_4d(&tz.m[ph], reinterpret_cast<const uint8_t*>(z) + 16 * ph, dims, strides, box);
         if (rc) return rc;
     }
     {
-        const uint64_t dims[4] = {8, (uint64_t)WOP * 1, (uint64_t)(C::HO / 2), (uint64_t)N * C::P_OUT};
-        const uint64_t strides[3] = {16, (uint64_t)WOP * 16, (uint64_t)WOP * (C::HO / 2) * 16};
-        const uint32_t box[4] = {8, (uint32_t)WOP, (uint32_t)HBP, (uint32_t)C::P_OUT};
+        const uint64_t dims[4] = {8, (uint64_t)C::WOP, (uint64_t)(C::HO / 2), (uint64_t)N * C::P_OUT};
+        const uint64_t strides[3] = {16, (uint64_t)C::WOP * 16, (uint64_t)C::WOP * (C::HO / 2) * 16};
+        const uint32_t box[4] = {8, (uint32_t)C::WOP, (uint32_t)C::HBP, (uint32_t)C::P_OUT};
         int rc = encode_tmap_bf16_4d(&tg, dp, dims, strides, box);
         if (rc) return rc;
     }
-    conv_tc_wgrad_l0_fused_kernel<C><<<G, L0F_THREADS, SMEM, st>>>(tx, tz, tg, cst, work, dbsum, N, n_per_view);
+    conv_tc_wgrad_l0_fused_kernel<C><<<G, L0F_THREADS, C::SMEM, st>>>(tx, tz, tg, cst, work, dbsum, N, n_per_view);
     int rc = launch_status("conv_tc_wgrad_l0_fused_kernel");
     if (rc) return rc;
     wgrad_reduce_kernel<<<(C::PART + 255) / 256, 256, 0, st>>>(work, G, C::PART, dw);
@@ -994,7 +1056,7 @@ using CfgA1d = TcCfg<16, 8, 16, 56, 56, 5, 2, 2, 2, 1>;  // data gradients (C_in
 using CfgA2d = TcCfg<32, 16, 16, 28, 28, 5, 2, 1, 2, 1>;  // 2 x phases: N = 32
 using CfgA3d = TcCfg<64, 32, 32, 14, 14, 5, 2, 1, 2>;
 using CfgI1d = TcCfg<64, 32, 32, 10, 10, 5, 4, 1, 2>;
-using CfgA0 = TcCfg<1, 8, 16, 112, 112, 5, 2, 8, 2, 3>;  // first layers on the shift8 image: audio conv1
+using CfgA0 = TcCfg<1, 8, 16, 112, 112, 5, 2, 2, 2, 3>;  // first layers on the quad8 image (4 x phases: N = 32 / 128): audio conv1
 using CfgI0 = TcCfg<1, 32, 32, 28, 28, 5, 2, 1, 4>;      //   image conv1
 using CfgS0 = TcCfg<1, 32, 32, 28, 28, 3, 1, 1, 4>;      //   image_simple conv1
 using CfgS2 = TcCfg<64, 128, 128, 7, 7, 3, 1, 1, 3, 2, 2>;   // image_simple conv3 forward (two 64-channel slices) / data gradient
@@ -1018,7 +1080,7 @@ int b200_conv_tc_supported(int Cin, int Cout, int H, int W, int K, int pad) {
 }
 
 int64_t b200_conv_tc_weight_bytes(int Cin, int Cout, int K) {
-    const int xph = Cin == 1 ? 1 : xph_for(Cin, Cout, K), kwx = K + xph - 1;
+    const int xph = Cin == 1 ? 4 : xph_for(Cin, Cout, K), kwx = K + xph - 1;
     const int npad = (xph * Cout + 15) / 16 * 16;
     const int nmma = (Cin == 1) ? (K + 1) / 2 : (Cin == 8) ? K * ((kwx + 1) / 2) : K * kwx * (Cin / 16);
     return (int64_t)nmma * npad * 32;
@@ -1029,7 +1091,7 @@ int b200_conv_tc_prep_weights(const float* w, void* out, int Cin, int Cout, int 
     B200_REQUIRE(Cin == 1 || Cin == 8 || (Cin % 16 == 0 && Cin > 0), -2, "conv_tc_prep_weights: C_in must be 1, 8 or a multiple of 16 (got %d)", Cin);
     B200_REQUIRE(!(Cin == 1 && flip), -2, "conv_tc_prep_weights: the first layer has no data gradient");
     B200_REQUIRE(Cout % 8 == 0 && Cout > 0 && Cout <= 128, -2, "conv_tc_prep_weights: C_out must be a multiple of 8, <= 128 (got %d)", Cout);
-    const int xph = Cin == 1 ? 1 : xph_for(Cin, Cout, K);
+    const int xph = Cin == 1 ? 4 : xph_for(Cin, Cout, K);
     const int npad = (xph * Cout + 15) / 16 * 16;
     const int total = (int)(b200_conv_tc_weight_bytes(Cin, Cout, K) / 2);
     conv_tc_prep_weights_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(out), Cin, Cout, npad, K,
@@ -1048,9 +1110,10 @@ static int wgrad_tc_dispatch(const void* x, const void* dz, float* dw, float* wo
 }
 
 // fused first-layer backward (Cin = 1): geometries of the first layers of the three encoders
-using WgF_A0 = TcWgCfg<1, 8, 112, 112, 5, 2, 7, 1, 1, 3>;
-using WgF_I0 = TcWgCfg<1, 32, 28, 28, 5, 2, 1, 1, 1, 2>;
-using WgF_S0 = TcWgCfg<1, 32, 28, 28, 3, 1, 1, 1, 1, 2>;
+//                    COUT HIN  WIN KS PAD BANDS SLOTS CTAS
+using WgF_A0 = L0FCfg<8, 112, 112, 5, 2, 7, 2, 2>;
+using WgF_I0 = L0FCfg<32, 28, 28, 5, 2, 1, 2, 1>;
+using WgF_S0 = L0FCfg<32, 28, 28, 3, 1, 1, 2, 1>;
 
 static int wgrad_l0_dispatch(const void* x, const void* z, const void* dp, const float* scale, const float* shift, const float* mean,
                              const float* invstd, const double* sums, float* dw, double* dbsum, float* work, int N, int n_per_view, int Cout,
@@ -1071,14 +1134,14 @@ int64_t b200_conv_tc_wgrad_l0_fused_work_floats(int N, int n_per_view, int Cout,
     return rc ? -1 : need;
 }
 
-int b200_conv_tc_wgrad_l0_fused(const void* x_shift8, const void* z8, const void* dp8, const float* scale, const float* shift,
+int b200_conv_tc_wgrad_l0_fused(const void* x_quad8, const void* z8, const void* dp8, const float* scale, const float* shift,
                                 const float* mean, const float* invstd, const double* sums, float* dw, double* dbsum, float* work, int N,
                                 int n_per_view, int Cout, int H, int W, int K, int pad, void* stream) {
-    B200_REQUIRE(x_shift8 && z8 && dp8 && scale && shift && mean && invstd && sums && dw && work, -1, "conv_tc_wgrad_l0_fused: null pointer");
+    B200_REQUIRE(x_quad8 && z8 && dp8 && scale && shift && mean && invstd && sums && dw && work, -1, "conv_tc_wgrad_l0_fused: null pointer");
     B200_REQUIRE(N > 0 && n_per_view > 0 && N % n_per_view == 0, -2, "conv_tc_wgrad_l0_fused: N=%d must be a multiple of n_per_view=%d", N, n_per_view);
-    B200_REQUIRE(((reinterpret_cast<uintptr_t>(x_shift8) | reinterpret_cast<uintptr_t>(z8) | reinterpret_cast<uintptr_t>(dp8) |
+    B200_REQUIRE(((reinterpret_cast<uintptr_t>(x_quad8) | reinterpret_cast<uintptr_t>(z8) | reinterpret_cast<uintptr_t>(dp8) |
                    reinterpret_cast<uintptr_t>(work)) & 15) == 0, -3, "conv_tc_wgrad_l0_fused: pointers must be 16-byte aligned");
-    return wgrad_l0_dispatch(x_shift8, z8, dp8, scale, shift, mean, invstd, sums, dw, dbsum, work, N, n_per_view, Cout, H, W, K, pad,
+    return wgrad_l0_dispatch(x_quad8, z8, dp8, scale, shift, mean, invstd, sums, dw, dbsum, work, N, n_per_view, Cout, H, W, K, pad,
                              as_stream(stream), nullptr);
 }
 
@@ -1094,6 +1157,14 @@ int b200_conv_tc_wgrad(const void* x_act8, const void* dz_act8, float* dw, float
     B200_REQUIRE(N > 0, -2, "conv_tc_wgrad: N must be positive");
     B200_REQUIRE(((uintptr_t)x_act8 & 15) == 0 && ((uintptr_t)dz_act8 & 15) == 0, -3, "conv_tc_wgrad: pointers must be 16-byte aligned");
     return wgrad_tc_dispatch(x_act8, dz_act8, dw, work, N, Cin, Cout, H, W, K, pad, as_stream(stream), nullptr);
+}
+
+int b200_pack_quad8(const float* x, void* out, int N, int H, int W, int pad, void* stream) {
+    B200_REQUIRE(x && out && N > 0 && H > 0 && W > 0 && pad >= 0, -1, "pack_quad8: bad arguments");
+    const int WQ = (W + 2 * pad + 3) / 4;
+    const long units = (long)N * H * WQ;
+    pack_quad8_kernel<<<(unsigned)((units + 255) / 256), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<uint4*>(out), units, W, WQ, pad);
+    return launch_status("pack_quad8_kernel");
 }
 
 int b200_pack_shift8(const float* x, void* out, int N, int H, int W, int pad, void* stream) {

@@ -152,8 +152,6 @@ class DinoStepEngine:
         assert mode == "default" or kind == "multi_central"
         assert precision in ("bf16", "fp32")
         self.precision = precision
-        # first layers: BatchNorm/ReLU/pool backward-apply fused into the weight-gradient kernel (dz stays in shared memory)
-        self.fuse_l0_bwd = precision == "bf16" and os.environ.get("B200_FUSE_L0_BWD", "1") != "0"
         self.lin_tc = precision == "bf16"          # linear layers on the tensor cores (tcgen05 kind::tf32)
         self.kind, self.mode = kind, mode
         self.E, self.O, self.P = encoder_output_dim, output_dim, projection_dim
@@ -212,6 +210,11 @@ class DinoStepEngine:
             self.tc[mod] = [precision == "bf16" and ops.conv_tc_supported(ci, co, hw, hw, k, pad) and
                             (ci == 1 or ops.conv_tc_supported(co, ci, hw + 2 * pad - k + 1, hw + 2 * pad - k + 1, k, k - 1 - pad))
                             for (conv, bn, ci, co, hw, k, pad) in layers]
+        for mod in self.tc:
+            # a tensor-core first layer runs its backward fused into the weight-gradient kernel (dz stays in shared memory),
+            # which consumes the bf16 act8 pooled gradient written by the second layer's tensor-core data gradient
+            if self.tc[mod] and self.tc[mod][0] and not (len(self.tc[mod]) > 1 and self.tc[mod][1]):
+                self.tc[mod][0] = False
         self._tcw = {}
         for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers)):
             for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers):
@@ -305,8 +308,9 @@ class DinoStepEngine:
                     tc = self.tc[mod][li]
                     next_tc = li + 1 < len(layers) and self.tc[mod][li + 1]
                     if tc and ci == 1 and role == "s":
-                        w[f"{mod}.xs8"] = e(N, hw, hw + pad, 8, dtype=BF)       # first-layer input, shift8 (shared by the teacher)
-                        w[f"{mod}.xs8_b"] = e(N, hw, hw + pad, 8, dtype=BF)     # ... and the slot the next step's views are prefetched into
+                        wq = ops.quad8_width(hw, pad)
+                        w[f"{mod}.xs8"] = e(N, hw, wq, 8, dtype=BF)             # first-layer input, quad8 (shared by the teacher)
+                        w[f"{mod}.xs8_b"] = e(N, hw, wq, 8, dtype=BF)           # ... and the slot the next step's views are prefetched into
                     if tc:
                         w[f"{role}.{mod}.z{li}"] = e(N, co // 8, ho, ho, 8, dtype=torch.float16)   # act8 layout, fp16: never an MMA operand
                     else:
@@ -323,7 +327,7 @@ class DinoStepEngine:
                         sc = scr[mod]
                         if tc:
                             sc["wg"] = max(sc["wg"], ops.conv_tc_wgrad_work_floats(N, ci, co, hw, hw, k, pad))
-                            if ci == 1 and self.fuse_l0_bwd and next_tc:
+                            if ci == 1:
                                 # fused apply + weight gradient: this layer's dz never exists in HBM
                                 sc["wg"] = max(sc["wg"], ops.conv_tc_wgrad_l0_fused_work_floats(N, B, co, hw, hw, k, pad))
                             else:
@@ -409,11 +413,11 @@ class DinoStepEngine:
             seed = (self.seed * 1000003 + self.rng_step) & 0xFFFFFFFFFFFF
             V = self.V
             pi = self.img_layers[0][6]
-            ops.aug_apply_image(images.reshape(B, 28, 28), w["img_ops_b"], None, out8=w["img.xs8_b"][:V * B].view(V, B, 28, 28 + pi, 8), pad=pi)
+            ops.aug_apply_image(images.reshape(B, 28, 28), w["img_ops_b"], None, out8=w["img.xs8_b"][:V * B].view(V, B, 28, ops.quad8_width(28, pi), 8), pad=pi)
             if self.aud_layers and audios is not None:
                 pa = self.aud_layers[0][6]
                 ops.aug_apply_audio(audios.reshape(B, 112, 112), w["aud_ops_b"], w["group_bits_b"], None, seed=seed,
-                                    out8=w["aud.xs8_b"][:V * B].view(V, B, 112, 112 + pa, 8), pad=pa)
+                                    out8=w["aud.xs8_b"][:V * B].view(V, B, 112, ops.quad8_width(112, pa), 8), pad=pa)
             ev = torch.cuda.Event()
             ev.record(st)
         self._prefetch = {"key": (images.data_ptr(), None if audios is None else audios.data_ptr(), B, self.rng_step), "event": ev}
@@ -431,8 +435,8 @@ class DinoStepEngine:
             if nm in w:
                 w[nm], w[nm + "_b"] = w[nm + "_b"], w[nm]
         V = self.V
-        xi = w["img.xs8"][:V * B].view(V, B, 28, 28 + self.img_layers[0][6], 8)
-        xa = w["aud.xs8"][:V * B].view(V, B, 112, 112 + self.aud_layers[0][6], 8) if self.aud_layers else None
+        xi = w["img.xs8"][:V * B].view(V, B, 28, ops.quad8_width(28, self.img_layers[0][6]), 8)
+        xa = w["aud.xs8"][:V * B].view(V, B, 112, ops.quad8_width(112, self.aud_layers[0][6]), 8) if self.aud_layers else None
         return xi, xa
 
     def augment(self, images, audios, B=None, direct=False):
@@ -445,7 +449,7 @@ class DinoStepEngine:
 
     def augment_with_params(self, images, audios, img_ops, aud_ops, group_bits, noise, direct=False):
         """Applies the op records.  direct=False: fp32 views ([V,B,28,28], [V,B,112,112]).  direct=True (tensor-core path
-        only): the kernels write the first-layer shift8 images straight into the workspace (no fp32 round trip); the
+        only): the kernels write the first-layer quad8 images straight into the workspace (no fp32 round trip); the
         returned bf16 tensors are those workspace buffers and are recognised by forward_pass."""
         B = images.shape[0]
         w = self._workspace(B)
@@ -453,12 +457,12 @@ class DinoStepEngine:
         seed = (self.seed * 1000003 + self.rng_step) & 0xFFFFFFFFFFFF
         if direct and self.tc["img"][0] and (not self.aud_layers or self.tc["aud"][0]):
             pi = self.img_layers[0][6]
-            xi = w["img.xs8"][:V * B].view(V, B, 28, 28 + pi, 8)
+            xi = w["img.xs8"][:V * B].view(V, B, 28, ops.quad8_width(28, pi), 8)
             ops.aug_apply_image(images.reshape(B, 28, 28), img_ops, None, out8=xi, pad=pi)
             xa = None
             if self.aud_layers and audios is not None:
                 pa = self.aud_layers[0][6]
-                xa = w["aud.xs8"][:V * B].view(V, B, 112, 112 + pa, 8)
+                xa = w["aud.xs8"][:V * B].view(V, B, 112, ops.quad8_width(112, pa), 8)
                 ops.aug_apply_audio(audios.reshape(B, 112, 112), aud_ops, group_bits, None, noise=noise, seed=seed, out8=xa, pad=pa)
             return xi, xa
         xi = w["x_img"][:V * B].view(V, B, 28, 28)
@@ -495,7 +499,7 @@ class DinoStepEngine:
             if tc and ci == 1:
                 xs8 = w[f"{mod}.xs8"]
                 if role == "s" and not w.get("packed", False):
-                    ops.pack_shift8(cur.view(N, hw, hw), xs8, pad)
+                    ops.pack_quad8(cur.view(N, hw, hw), xs8, pad)
                 ops.conv_tc(xs8[:N], self._tcw[(wrole, mod, li)], P["enc." + conv + ".bias"], z, stats, B, co, k, pad)
             elif tc:
                 ops.conv_tc(cur, self._tcw[(wrole, mod, li)], P["enc." + conv + ".bias"], z, stats, B, co, k, pad)
@@ -597,7 +601,7 @@ class DinoStepEngine:
                 par = li & 1
                 if par in busy:
                     main.wait_event(busy.pop(par))
-                fused = ci == 1 and self.fuse_l0_bwd and d_p.dtype == BF
+                fused = ci == 1
                 if not fused:
                     dz = w[f"{mod}.dz8" if par == 0 else f"{mod}.dz8b"][:z.numel()].view_as(z)
                 p_out = w[f"s.{mod}.p8{li}"] if f"s.{mod}.p8{li}" in w else w[f"s.{mod}.p{li}"]
@@ -671,7 +675,7 @@ class DinoStepEngine:
                 tc = self.tc[mod][li]
                 next_tc = li + 1 < len(layers) and self.tc[mod][li + 1]
                 if tc and ci == 1:
-                    w[f"{mod}.xs8"] = e(B, hw, hw + pad, 8, dtype=BF)
+                    w[f"{mod}.xs8"] = e(B, hw, ops.quad8_width(hw, pad), 8, dtype=BF)
                 w[f"e.{mod}.z{li}"] = e(B, co // 8, ho, ho, 8, dtype=torch.float16) if tc else e(B, co, ho, ho)
                 if next_tc:
                     w[f"e.{mod}.p8{li}"] = e(B, co // 8, ho // 2, ho // 2, 8, dtype=BF)
@@ -713,7 +717,7 @@ class DinoStepEngine:
             self._prep_tc_weights("t" if teacher else "s", P)
         for mod, layers, x in (("img", self.img_layers, xi), ("aud", self.aud_layers, xa)):
             if layers and self.tc[mod][0]:
-                ops.pack_shift8(x.view(B, layers[0][4], layers[0][4]), w[f"{mod}.xs8"], layers[0][6])
+                ops.pack_quad8(x.view(B, layers[0][4], layers[0][4]), w[f"{mod}.xs8"], layers[0][6])
         w["packed"] = True
         fmask = None
         if train and self.kind == "multi_central" and self.fusion_dropout > 0:
@@ -737,14 +741,14 @@ class DinoStepEngine:
         multi = self.kind == "multi_central"
         xi = w["x_img"]
         xa = w["x_aud"] if multi else None
-        packed = x_img.dtype == torch.bfloat16          # augment(direct=True): the shift8 workspace images are already filled
+        packed = x_img.dtype == torch.bfloat16          # augment(direct=True): the quad8 workspace images are already filled
         w["packed"] = packed
         if packed:
             if x_img.data_ptr() != w["img.xs8"].data_ptr() or (multi and x_aud.data_ptr() != w["aud.xs8"].data_ptr()):
-                raise ops._lib.B200Error("bf16 inputs must be the workspace shift8 images returned by augment(direct=True)")
+                raise ops._lib.B200Error("bf16 inputs must be the workspace quad8 images returned by augment(direct=True)")
             if self.mode != "default":
-                ops.pack_shift8(raw[0].reshape(B, 28, 28), w["img.xs8"][Nv:], self.img_layers[0][6])
-                ops.pack_shift8(raw[1].reshape(B, 112, 112), w["aud.xs8"][Nv:], self.aud_layers[0][6])
+                ops.pack_quad8(raw[0].reshape(B, 28, 28), w["img.xs8"][Nv:], self.img_layers[0][6])
+                ops.pack_quad8(raw[1].reshape(B, 112, 112), w["aud.xs8"][Nv:], self.aud_layers[0][6])
         else:
             if x_img.data_ptr() != xi.data_ptr():
                 xi[:Nv].copy_(x_img.reshape(Nv, 1, 28, 28))
@@ -773,7 +777,7 @@ class DinoStepEngine:
             for mod, layers, x in (("img", self.img_layers, xi), ("aud", self.aud_layers, xa)):
                 if layers and self.tc[mod][0]:
                     hw, pad = layers[0][4], layers[0][6]
-                    ops.pack_shift8(x.view(Ns, hw, hw), w[f"{mod}.xs8"], pad)
+                    ops.pack_quad8(x.view(Ns, hw, hw), w[f"{mod}.xs8"], pad)
             w["packed"] = True
         # the teacher forward is independent of the student forward: it runs on a side stream so that its CTAs fill the SMs the
         # student's thin kernels leave idle (separate activation buffers; joined before the loss)

@@ -141,12 +141,12 @@ def cosine_consistency_fwd_bwd(emb, grad_emb, loss_out, grad_scale=1.0):
 def _aug_outs(out, out8, pad):
     ref = out if out is not None else out8
     if ref is None:
-        raise _lib.B200Error("augmentation needs an fp32 and / or a shift8 output")
+        raise _lib.B200Error("augmentation needs an fp32 and / or a quad8 output")
     return ref.shape[0], ref.shape[1], (_ptr(out, F32) if out is not None else None), (_ptr(out8, torch.bfloat16) if out8 is not None else None)
 
 
 def aug_apply_image(src, ops, out, out8=None, pad=0):
-    """out: fp32 [V, B, 28, 28] and / or out8: bf16 shift8 [V, B, 28, 28 + pad, 8] (first-layer tensor-core input)."""
+    """out: fp32 [V, B, 28, 28] and / or out8: bf16 quad8 [V, B, 28, ceil((28 + 2 pad) / 4), 8] (first-layer tensor-core input)."""
     V, B, po, p8 = _aug_outs(out, out8, pad)
     _lib.check(_lib_().b200_aug_apply_image(_ptr(src), 1 if src.dtype == U8 else 0, _ptr(ops, I32), po, p8, pad, B, V, _stream()),
                "aug_apply_image")
@@ -222,11 +222,13 @@ def pack_act8(x, out):
 
 
 def conv_tc(x8, wprep, bias, out, stats, n_per_view, Cout, K, pad):
-    """x8: bf16 act8 [N, Cin/8, H, W, 8] (or the shift8 image [N, H, W, 8] of a first layer, Cin = 1); out: fp32 NCHW
+    """x8: bf16 act8 [N, Cin/8, H, W, 8] (or the quad8 image [N, H, ceil((W + 2 pad) / 4), 8] of a first layer, Cin = 1); out: fp32 NCHW
     [N, Cout, Ho, Wo] or bf16 / fp16 act8 [N, Cout/8, Ho, Wo, 8]; bias/stats may be None (data-gradient use)."""
-    if x8.dim() == 4:
-        N, H, W, _ = x8.shape
-        W -= pad
+    if x8.dim() == 4:               # first layer: quad8 image [N, H, WQ, 8]; the width follows from the output
+        N, H, WQ, _ = x8.shape
+        W = out.shape[-1 if out.dim() == 4 else -2] - 2 * pad + K - 1
+        if WQ != quad8_width(W, pad):
+            raise _lib.B200Error(f"conv_tc: quad8 input of width {WQ} does not match W={W}, pad={pad}")
         P = 0.125
     else:
         N, P, H, W, _ = x8.shape
@@ -268,6 +270,18 @@ def conv_tc_wgrad_l0_fused(xs8, z8, dp8, scale, shift, mean, invstd, sums, dw, d
                                                    _ptr(mean, F32), _ptr(invstd, F32), _ptr(sums, F64), _ptr(dw, F32),
                                                    _ptr(dbsum, F64) if dbsum is not None else None, _ptr(work, F32), N, n_per_view, Cout, H, W,
                                                    K, pad, _stream()), "conv_tc_wgrad_l0_fused")
+
+
+def quad8_width(W, pad):
+    """units per row of the quad8 first-layer image"""
+    return (W + 2 * pad + 3) // 4
+
+
+def pack_quad8(x, out, pad):
+    """fp32 [N, H, W] (or [N, 1, H, W]) -> bf16 quad8 [N, H, ceil((W + 2 pad) / 4), 8] (pad = the convolution's padding)"""
+    N, H, W = x.shape[0], x.shape[-2], x.shape[-1]
+    assert tuple(out.shape) == (N, H, quad8_width(W, pad), 8)
+    _lib.check(_lib_().b200_pack_quad8(_ptr(x, F32), _ptr(out, BF16), N, H, W, pad, _stream()), "pack_quad8")
 
 
 def pack_shift8(x, out, pad):

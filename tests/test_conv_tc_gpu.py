@@ -202,7 +202,14 @@ def test_first_layer_shift8_forward_and_weight_gradient(geom, views, B):
     ops.conv_tc_prep_weights(w, wp)
     stats = torch.zeros(views, Cout, 2, dtype=torch.float64, device=DEV)
     z = torch.full((N, Cout // 8, H, H, 8), float("nan"), dtype=torch.float16, device=DEV)
-    ops.conv_tc(x8, wp, b, z, stats, B, Cout, K, pad)
+    # forward input: the quad8 image (unit = padded pixels 4xq .. 4xq+7: the taps of four adjacent outputs)
+    WQ = ops.quad8_width(H, pad)
+    xq8 = torch.empty(N, H, WQ, 8, dtype=torch.bfloat16, device=DEV)
+    ops.pack_quad8(x, xq8, pad)
+    xpad = F.pad(xb[:, 0], (pad, 4 * WQ + 8 - H - pad))
+    for e in (0, 3, 7):
+        assert torch.equal(xq8[:, :, :, e].float(), xpad[:, :, e:e + 4 * WQ:4])
+    ops.conv_tc(xq8, wp, b, z, stats, B, Cout, K, pad)
     torch.cuda.synchronize()
     assert float((_unpack8(z) - want).abs().max()) <= 1e-3 * float(want.abs().max())
     wv = want.view(views, B, Cout, H, H).double()
@@ -253,7 +260,9 @@ def test_first_layer_fused_backward_matches_apply_then_wgrad(geom, views, B):
     work2 = torch.empty(ops.conv_tc_wgrad_l0_fused_work_floats(N, B, Cout, H, H, K, pad), device=DEV)
     dw_b = torch.full((Cout, 1, K, K), float("nan"), device=DEV)
     db_b = torch.zeros(Cout, dtype=torch.float64, device=DEV)
-    ops.conv_tc_wgrad_l0_fused(x8, z8, dp8, scale, shift, mean, invstd, sums, dw_b, db_b, work2, B, pad)
+    xq8 = torch.empty(N, H, ops.quad8_width(H, pad), 8, dtype=torch.bfloat16, device=DEV)
+    ops.pack_quad8(x, xq8, pad)
+    ops.conv_tc_wgrad_l0_fused(xq8, z8, dp8, scale, shift, mean, invstd, sums, dw_b, db_b, work2, B, pad)
     torch.cuda.synchronize()
     assert torch.equal(z8, z_keep)                       # inputs untouched
     # fp32 tensor-core accumulation (truncating adds, split over two accumulators in the fused kernel): bounds are relative
@@ -268,8 +277,8 @@ def test_first_layer_fused_backward_matches_apply_then_wgrad(geom, views, B):
     assert float(((dw_b.double() - wd.grad).abs() / wa.grad).max()) <= 3e-6
 
 
-def test_augmentation_direct_shift8_output_matches_pack():
-    """The augmentation kernels' direct bf16 shift8 output == pack_shift8(fp32 output) bit for bit (same op records)."""
+def test_augmentation_direct_quad8_output_matches_pack():
+    """The augmentation kernels' direct bf16 quad8 output == pack_quad8(fp32 output) bit for bit (same op records)."""
     from multimodal_ssl_avmnist_b200.engine import DinoStepEngine
     eng = DinoStepEngine(kind="multi_central", device=DEV, precision="bf16", seed=5)
     B = 6
@@ -280,8 +289,8 @@ def test_augmentation_direct_shift8_output_matches_pack():
     xi8, xa8 = eng.augment(img, aud, direct=True)       # same rng_step -> same op records and noise
     for x, x8, pad in ((xi, xi8, 2), (xa, xa8, 2)):
         V, Bb, S, _ = x.shape
-        want = torch.empty(V * Bb, S, S + pad, 8, dtype=torch.bfloat16, device=DEV)
-        ops.pack_shift8(x.reshape(V * Bb, S, S).contiguous(), want, pad)
+        want = torch.empty(V * Bb, S, ops.quad8_width(S, pad), 8, dtype=torch.bfloat16, device=DEV)
+        ops.pack_quad8(x.reshape(V * Bb, S, S).contiguous(), want, pad)
         assert torch.equal(x8.reshape(want.shape), want)
     # and the whole step runs from it
     l1 = eng.train_step(img, aud).clone()

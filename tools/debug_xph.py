@@ -16,8 +16,21 @@ w = (torch.randn(Cout, Cin, K, K, generator=g) / (Cin * K * K) ** 0.5).to(DEV)
 if mode == "delta":
     x.zero_(); x[:, 0, 10, 10] = 1.0
 b = torch.zeros(Cout, device=DEV)
-x8 = torch.empty(N, Cin // 8, H, W, 8, dtype=torch.bfloat16, device=DEV)
-ops.pack_act8(x, x8)
+if Cin == 1:
+    x = x.abs()
+    if mode.startswith("delta"):
+        parts = mode.split(":")
+        dy, dx = (int(parts[1]), int(parts[2])) if len(parts) > 2 else (10, 10)
+        x.zero_(); x[:, 0, dy, dx] = 1.0
+    if mode == "row":
+        x.zero_(); x[:, 0, 10, :] = 1.0
+    if mode == "col":
+        x.zero_(); x[:, 0, :, 10] = 1.0
+    x8 = torch.empty(N, H, ops.quad8_width(W, pad), 8, dtype=torch.bfloat16, device=DEV)
+    ops.pack_quad8(x, x8, pad)
+else:
+    x8 = torch.empty(N, Cin // 8, H, W, 8, dtype=torch.bfloat16, device=DEV)
+    ops.pack_act8(x, x8)
 bf = lambda t: t.to(torch.bfloat16).float()
 want = F.conv2d(bf(x).double(), bf(w).double(), b.double(), padding=pad).float()
 Ho = want.shape[-1]
@@ -32,8 +45,18 @@ e = err[0]
 print("err by channel", [round(float(v), 3) for v in e.amax(dim=(1, 2))])
 print("err by x (first 16)", [round(float(v), 3) for v in e.amax(dim=(0, 1))[:16]])
 print("err by y (first 16)", [round(float(v), 3) for v in e.amax(dim=(0, 2))[:16]])
+if mode != "rand":
+    bad = (err[0, 0] > 1e-3).nonzero()
+    print("bad positions ch0 (first 40):", bad[:40].tolist(), "count", len(bad))
+    for (yy, xx) in bad[:6].tolist():
+        print("   at", yy, xx, "got", float(out[0, 0, yy, xx]), "want", float(want[0, 0, yy, xx]))
 if mode == "delta":
     nz = (out[0, 0].abs() > 1e-6).nonzero()
     print("nonzero got ch0:", nz[:30].tolist())
     nz = (want[0, 0].abs() > 1e-6).nonzero()
     print("nonzero want ch0:", nz[:30].tolist())
+if mode == "col":
+    torch.set_printoptions(linewidth=250, precision=3, sci_mode=False)
+    print("diff[0, :, 60, 4:20]"); print((out - want)[0, :, 60, 4:20])
+    print("diff[0, 0, 50:60, 4:20]"); print((out - want)[0, 0, 50:60, 4:20])
+    print("diff[0, 0, 104:112, 4:20]"); print((out - want)[0, 0, 104:112, 4:20])

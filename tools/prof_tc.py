@@ -46,10 +46,16 @@ def layer(Cin, Cout, H, K, pad):
         ops.bn_relu_pool8_fwd(z8, sc, sh, p8, B)
         ops.bn_relu_pool8_bwd_reduce(z8, dp8, sc, sh, mu, inv, sums, B)
         ops.bn_relu_pool8_bwd_apply(z8, dp8, sc, sh, mu, inv, sums, dz8, B)
+        ops.bn_pool8_bwd_reduce_p(p8, dp8, sc[0].contiguous(), sh[0].contiguous(), sums, B)
+    if Cin == 1:        # fused first-layer backward (BatchNorm-apply + weight gradient)
+        work2 = torch.empty(ops.conv_tc_wgrad_l0_fused_work_floats(N, B, Cout, H, H, K, pad), device=DEV)
+        for _ in range(reps):
+            ops.conv_tc_wgrad_l0_fused(x8, z8, dp8, sc, sh, mu, inv, sums, dw, None, work2, B, pad)
 
 
 layer(1, 8, 112, 5, 2)
 layer(8, 16, 56, 5, 2)
+layer(16, 32, 28, 5, 2)
 layer(32, 64, 14, 5, 2)
 torch.cuda.synchronize()
 print("ok")
