@@ -55,6 +55,11 @@ using namespace umma;
 
 constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
 constexpr int SMEM_EST(int nmma, int npad, int slots, int slot_bytes, int tail) { return round_up(nmma * npad * 32, 128) + slots * slot_bytes + tail + 256 + npad * 4; }
+constexpr int nbuf_for(int npadl, int ctas) {        // accumulator stages: as many as 512 TMEM columns per SM allow, at most 8 / 4
+    int n = (npadl <= 32 ? 8 : 4) / (ctas > 2 ? 2 : 1);
+    while (n > 1 && n * npadl * ctas > 512) n /= 2;
+    return n;
+}
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
 // Output-pixel phases packed into the MMA N dimension.  At these channel counts an MMA costs the same ~40-48 cycles of
@@ -109,7 +114,7 @@ struct TcCfg {
     static constexpr int IMG_BYTES = SLOTS * SLOT_BYTES + TAIL;
     static constexpr int BAR_OFF = W_BYTES + IMG_BYTES;
     static constexpr int SMEM = BAR_OFF + 256 + NPADL * 4;
-    static constexpr int NBUF = (NPADL <= 32 ? 8 : 4) / (CTAS > 2 ? 2 : 1);   // TMEM accumulator stages
+    static constexpr int NBUF = nbuf_for(NPADL, CTAS);          // TMEM accumulator stages
     static constexpr int TMEM_COLS = pow2_cols(NBUF * NPADL);
     // One issuing thread sustains only ~1 UMMA per 140 cycles at these tile shapes (measured, tools/umma_probe.cu); four
     // concurrent issue streams per SM -- CTAs or warps -- reach the shared-memory operand bandwidth (39-48 cycles per UMMA).
@@ -709,6 +714,205 @@ int launch_conv_tc_wgrad(const void* x, const void* dz, float* dw, float* work, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Weight gradient with output-pixel phases in N (small-channel layers, where the tensor pipe is saturated by N = 16 / 32
+// MMAs that do a fraction of its work).  K = flat index of PIXEL GROUPS (y, xq) over the pitch WQ, XPH pixels per group:
+//   B (N = XPH*C_out): dz de-interleaved by phase ph = x mod XPH (strided TMA maps), N units = (ph, channel octet) planes;
+//   A (M = 64): M units = the 8 taps kw' = ph + kw, elements = 8 input channels.  Unit plane u holds, at (row, xq), the padded
+//               pixel (row, XPH*xq + u): the phase plane (u mod XPH) of x shifted by u / XPH groups -- eight TMA loads with
+//               the shift in the start coordinate, so that consecutive K rows are consecutive 16-byte units in every plane;
+//   D(kh, plane)[(kw', ci)][(ph, co)]   =>   dW[co][ci][kh][kw] = sum_ph D[(kw + ph, ci)][(ph, co)]
+// The phase terms go to XPH separate partials per CTA; wgrad_reduce_kernel sums all of them in a fixed order.
+template <int CIN_, int COUT_, int HIN_, int WIN_, int KS_, int PAD_, int XPH_, int WQ_, int BANDS_, int SLOTS_, int PSPLIT_>
+struct WgPCfg {
+    static constexpr int CIN = CIN_, COUT = COUT_, HIN = HIN_, WIN = WIN_, KS = KS_, PAD = PAD_, XPH = XPH_, BANDS = BANDS_, SLOTS = SLOTS_;
+    static constexpr int PSPLIT = PSPLIT_, P_IN = CIN / 8, P_OUT = COUT / 8, PI = P_IN / PSPLIT, NTOT = XPH * COUT;
+    static constexpr int WP = WIN + 2 * PAD, HO = HIN + 2 * PAD - KS + 1, WO = WP - KS + 1, KWX = KS + XPH - 1;
+    static constexpr int WQ = WQ_ ? WQ_ : (WP + XPH - 1) / XPH;                  // pitch of every plane (units)
+    static constexpr int HB = HO / BANDS, HPB = HB + KS - 1, HBZ = hbz_for(HB, WQ);
+    static constexpr int KSTEPS = HBZ * WQ / 16;
+    static constexpr int PLANE_XU = HPB * WQ * 16, PLANE_Z = HBZ * WQ * 16;
+    static constexpr int X_BYTES = round_up(8 * PI * PLANE_XU, 128), Z_BYTES = round_up(XPH * P_OUT * PLANE_Z, 128);
+    static constexpr int SLOT = X_BYTES + Z_BYTES;
+    static constexpr int NACC = KS * PI, TCOLS = pow2_cols(NACC * NTOT);
+    static constexpr int ISS = NACC <= 6 ? NACC : 4;
+    static constexpr int THREADS = 32 * (1 + ISS + 4);
+    static constexpr int PART = COUT * CIN * KS * KS;
+    static constexpr int BAR_OFF = SLOTS * SLOT, SMEM = BAR_OFF + 256;
+    static_assert(CIN % 8 == 0 && COUT % 8 == 0 && P_IN % PSPLIT == 0 && HO % BANDS == 0 && WO % XPH == 0 && WIN % XPH == 0, "shape");
+    static_assert(KWX <= 8 && NTOT <= 256 && NTOT % 16 == 0 && TCOLS <= 512, "taps / N / TMEM");
+    static_assert(WQ * XPH >= WP && (BANDS == 1 || HBZ == HB), "pitch / bands");
+    static_assert((KSTEPS * 16 + (KS - 1) * WQ - HPB * WQ) * 16 <= Z_BYTES, "x overrun must stay inside the slot");
+    static_assert(SMEM + 1024 <= 227 * 1024 && 2 * SLOTS + 1 <= 24, "shared memory / barriers");
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1)
+conv_tc_wgrad_ph_kernel(const __grid_constant__ TMaps tmaps_x, const __grid_constant__ TMaps tmaps_z, float* __restrict__ work, int N) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);     // full[SLOTS], empty[SLOTS], done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::BAR_OFF + 200);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = gridDim.x, g = blockIdx.x, split = blockIdx.z;
+    const long items = (long)N * C::BANDS;
+    const int i0 = (int)(items * g / G), i1 = (int)(items * (g + 1) / G);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (C::SLOTS + s); };
+    const uint32_t done_bar = bar0 + 8u * (2 * C::SLOTS);
+    {
+        uint4* z = reinterpret_cast<uint4*>(smem);                       // unit planes u >= KWX are never loaded: they stay zero
+        for (int i = threadIdx.x; i < C::BAR_OFF / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async_smem();
+    }
+    if (warp == 0 && lane == 0) {
+        for (int r = 0; r < C::XPH; ++r) {
+            prefetch_tmap(&tmaps_x.m[r]);
+            prefetch_tmap(&tmaps_z.m[r]);
+        }
+        for (int s = 0; s < C::SLOTS; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), C::ISS);
+        }
+        mbar_init(done_bar, C::ISS);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<C::TCOLS>(smem_u32(tmem_slot));
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem0 = smem_u32(smem);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = i0; i < i1; ++i) {
+                const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
+                mbar_wait(empty_bar(slot), (use & 1) ^ 1);
+                mbar_expect_tx(full_bar(slot), C::KWX * C::PI * C::PLANE_XU + C::XPH * C::P_OUT * C::PLANE_Z);
+                const int n = i / C::BANDS, band = i % C::BANDS;
+                const uint32_t sa = smem0 + slot * C::SLOT;
+#pragma unroll
+                for (int u = 0; u < C::KWX; ++u) {   // padded column XPH*xq + u = global column XPH*(xq + a) + r
+                    constexpr int X = C::XPH;
+                    const int r = ((u - C::PAD) % X + X) % X, a = (u - C::PAD - r) / X;
+                    tma_load_4d(sa + u * C::PI * C::PLANE_XU, &tmaps_x.m[r], full_bar(slot), 0, a, band * C::HB - C::PAD,
+                                n * C::P_IN + split * C::PI);
+                }
+#pragma unroll
+                for (int ph = 0; ph < C::XPH; ++ph)
+                    tma_load_4d(sa + C::X_BYTES + ph * C::P_OUT * C::PLANE_Z, &tmaps_z.m[ph], full_bar(slot), 0, 0, band * C::HB, n * C::P_OUT);
+            }
+        }
+    } else if (warp <= C::ISS) {
+        if (lane == 0) {                     // issuer w owns the accumulators a == w-1 (mod ISS)
+            constexpr uint32_t idesc = idesc_bf16(C::NTOT, true, true, 64);
+            for (int i = i0; i < i1; ++i) {
+                const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
+                mbar_wait(full_bar(slot), use & 1);
+                tc_fence_after_sync();
+                const uint32_t xa = smem0 + slot * C::SLOT, za = xa + C::X_BYTES;
+                for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                    const uint32_t acc = (i > i0 || ks > 0) ? 1u : 0u;
+                    const uint64_t bd = smem_desc(za + ks * 256, 128, C::PLANE_Z);
+#pragma unroll
+                    for (int kh = 0; kh < C::KS; ++kh) {
+#pragma unroll
+                        for (int pl = 0; pl < C::PI; ++pl) {
+                            if ((kh * C::PI + pl) % C::ISS != warp - 1) continue;
+                            const uint64_t ad = smem_desc(xa + pl * C::PLANE_XU + (ks * 16 + kh * C::WQ) * 16, 128, C::PI * C::PLANE_XU);
+                            mma_bf16(tmem_base + (kh * C::PI + pl) * C::NTOT, ad, bd, idesc, acc);
+                        }
+                    }
+                }
+                mma_commit(empty_bar(slot));
+            }
+            mma_commit(done_bar);
+        }
+    } else {
+        // epilogue: M = 64 accumulators occupy lanes 0-15 of each 32-lane quadrant: row m = quad*16 + lane = (tap kw' = u, ci8)
+        const int quad = warp & 3;
+        const int m = quad * 16 + (lane & 15), u = m >> 3, ci8 = m & 7;
+        if (i1 > i0) {
+            mbar_wait(done_bar, 0);
+            tc_fence_after_sync();
+        }
+#pragma unroll 1
+        for (int a = 0; a < C::NACC; ++a) {
+            const int kh = a / C::PI, pl = a % C::PI;
+            const int ci = (split * C::PI + pl) * 8 + ci8;
+#pragma unroll 1
+            for (int cc = 0; cc < C::NTOT / 16; ++cc) {
+                uint32_t v[16];
+                if (i1 > i0) {
+                    tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + a * C::NTOT + cc * 16, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) v[t] = 0u;
+                }
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const int col = cc * 16 + t, ph = col / C::COUT, co = col % C::COUT;
+                    const int kw = u - ph;
+                    if (lane < 16 && kw >= 0 && kw < C::KS)
+                        work[((long)g * C::XPH + ph) * C::PART + ((co * C::CIN + ci) * C::KS + kh) * C::KS + kw] = __uint_as_float(v[t]);
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc<C::TCOLS>(tmem_base);
+    }
+}
+
+template <class C>
+int launch_conv_tc_wgrad_ph(const void* x, const void* dz, float* dw, float* work, int N, cudaStream_t st, int64_t* need) {
+    int G = sm_count() / C::PSPLIT;
+    const long items = (long)N * C::BANDS;
+    if (G > items) G = (int)items;
+    if (G < 1) G = 1;
+    if (need) {
+        *need = (int64_t)G * C::XPH * C::PART;
+        return 0;
+    }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_ph_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) {
+            set_error("conv_tc_wgrad: cannot set %d bytes of shared memory: %s", C::SMEM, cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured = true;
+    }
+    TMaps tx, tz;
+    for (int r = 0; r < 4; ++r) {
+        const int rr = r < C::XPH ? r : 0;
+        {
+            const uint64_t dims[4] = {8, (uint64_t)C::WIN / C::XPH, (uint64_t)C::HIN, (uint64_t)N * C::P_IN};
+            const uint64_t strides[3] = {16 * (uint64_t)C::XPH, (uint64_t)C::WIN * 16, (uint64_t)C::WIN * C::HIN * 16};
+            const uint32_t box[4] = {8, (uint32_t)C::WQ, (uint32_t)C::HPB, (uint32_t)C::PI};
+            int rc = encode_tmap_bf16_4d(&tx.m[r], reinterpret_cast<const uint8_t*>(x) + 16 * rr, dims, strides, box);
+            if (rc) return rc;
+        }
+        {
+            const uint64_t dims[4] = {8, (uint64_t)C::WO / C::XPH, (uint64_t)C::HO, (uint64_t)N * C::P_OUT};
+            const uint64_t strides[3] = {16 * (uint64_t)C::XPH, (uint64_t)C::WO * 16, (uint64_t)C::WO * C::HO * 16};
+            const uint32_t box[4] = {8, (uint32_t)C::WQ, (uint32_t)C::HBZ, (uint32_t)C::P_OUT};
+            int rc = encode_tmap_bf16_4d(&tz.m[r], reinterpret_cast<const uint8_t*>(dz) + 16 * rr, dims, strides, box);
+            if (rc) return rc;
+        }
+    }
+    conv_tc_wgrad_ph_kernel<C><<<dim3(G, 1, C::PSPLIT), C::THREADS, C::SMEM, st>>>(tx, tz, work, N);
+    int rc = launch_status("conv_tc_wgrad_ph_kernel");
+    if (rc) return rc;
+    wgrad_reduce_kernel<<<(C::PART + 255) / 256, 256, 0, st>>>(work, G * C::XPH, C::PART, dw);
+    return launch_status("wgrad_reduce_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // First layer, fused backward: BatchNorm-apply / ReLU / max-pool backward + weight gradient in ONE kernel.  The first layer
 // needs no data gradient, so its dz (the largest tensor of the backward pass) has a single consumer: instead of writing it
 // to HBM and reading it back, the pre-BatchNorm z tile (fp16 act8) is TMA-loaded straight into the position of the dz MMA
@@ -722,12 +926,17 @@ int launch_conv_tc_wgrad(const void* x, const void* dz, float* dw, float* work, 
 //   D[(kh, kw')][(ph, co)] = sum_xq x[.., 4xq + kw'] dz[co][.., 4xq + ph]   =>   dW[co][kh][kw] = sum_ph D[(kh, kw + ph)][(ph, co)]
 // -- a quarter of the K steps of the one-pixel-per-row formulation, at N = 32 / 128 instead of 8 / 32.
 //   cst: per (view, channel) constants float4 {a, b, ca, cb} prepared by wgrad_l0_consts_kernel from the BatchNorm tensors.
+// STAGED: the z tile is TMA-loaded densely (whole rows: the TMA engine moves strided 16-byte pieces at only ~16 B/clk per SM)
+// into a staging area and the transform warps scatter dz into the phase planes; otherwise z is loaded straight into the
+// phase planes by four strided maps and transformed in place.
 constexpr int L0F_ISS = 3;                       // MMA-issuer warps (K steps interleaved, one TMEM accumulator each)
-constexpr int L0F_THREADS = 32 * (1 + L0F_ISS + 4);
 
-template <int COUT_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int CTAS_>
+template <int COUT_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int CTAS_, bool STAGED_ = false>
 struct L0FCfg {
     static constexpr int COUT = COUT_, HIN = HIN_, WIN = WIN_, KS = KS_, PAD = PAD_, BANDS = BANDS_, SLOTS = SLOTS_, CTAS = CTAS_;
+    static constexpr bool STAGED = STAGED_;
+    static constexpr int TW = STAGED ? 8 : 4;                                    // transform warps
+    static constexpr int THREADS = 32 * (1 + L0F_ISS + TW);
     static constexpr int P_OUT = COUT / 8, NTOT = 4 * COUT;
     static constexpr int WP = WIN + 2 * PAD, WQ = (WP + 3) / 4;                  // quad8 units per row
     static constexpr int HO = HIN + 2 * PAD - KS + 1, WO = WP - KS + 1;
@@ -737,9 +946,10 @@ struct L0FCfg {
     static constexpr int X_BYTES = round_up(PLANE_X, 128), Z_BYTES = round_up(4 * P_OUT * PLANE_Z, 128);
     static constexpr int HBP = HB / 2, WOP = WO / 2;                             // pooled rows / columns of a band
     static constexpr int G_BYTES = round_up(P_OUT * HBP * WOP * 16, 128);
-    static constexpr int SLOT = X_BYTES + Z_BYTES + G_BYTES;
+    static constexpr int ZS_BYTES = STAGED ? round_up(P_OUT * HBZ * WO * 16, 128) : 0;   // dense z tile [octet][row][column]
+    static constexpr int SLOT = X_BYTES + ZS_BYTES + Z_BYTES + G_BYTES;
     static constexpr int STAGE_BYTES = 4 * COUT * KS * KS * 4;                   // end-of-kernel staging of the phase terms
-    static constexpr int CST_OFF = SLOTS * SLOT, BAR_OFF = CST_OFF + COUT * 16 + 4 * COUT * 4;
+    static constexpr int CST_OFF = SLOTS * SLOT, BAR_OFF = CST_OFF + COUT * 16 + TW * COUT * 4;
     static constexpr int SMEM = BAR_OFF + 256;
     static constexpr int ACC_COLS = round_up(NTOT, 32), TCOLS = pow2_cols(L0F_ISS * ACC_COLS);
     static constexpr int PART = COUT * KS * KS;
@@ -749,12 +959,13 @@ struct L0FCfg {
     static_assert(TCOLS * CTAS <= 512 && NTOT <= 256 && NTOT % 16 == 0, "TMEM columns / N");
     static_assert((SMEM + 1024) * CTAS <= 227 * 1024, "shared memory per SM");
     static_assert(STAGE_BYTES <= SLOT, "staging reuses the first slot");
-    static_assert((KSTEPS * 16 + 7 * WQ + 8 - HPB * WQ) * 16 <= Z_BYTES, "x overrun must stay inside the slot");
+    static_assert((KSTEPS * 16 + 7 * WQ + 8 - HPB * WQ) * 16 <= ZS_BYTES + Z_BYTES, "x overrun must stay inside the slot");
+    static_assert(!STAGED || HBZ == HB, "staged z tile: whole bands");
     static_assert(KSTEPS >= L0F_ISS, "every issuer needs a K step");
 };
 
 template <class C>
-__global__ void __launch_bounds__(L0F_THREADS, C::CTAS)
+__global__ void __launch_bounds__(C::THREADS, C::CTAS)
 conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ TMaps tmaps_z,
                               const __grid_constant__ CUtensorMap tmap_g, const float4* __restrict__ cst, float* __restrict__ work,
                               double* __restrict__ dbsum, int N, int n_per_view) {
@@ -776,7 +987,7 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
     {
         uint4* z = reinterpret_cast<uint4*>(smem);
         for (int i = threadIdx.x; i < C::CST_OFF / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
-        for (int i = threadIdx.x; i < 4 * C::COUT; i += blockDim.x) db_s[i] = 0.f;       // [transform warp][channel]
+        for (int i = threadIdx.x; i < C::TW * C::COUT; i += blockDim.x) db_s[i] = 0.f;   // [transform warp][channel]
         fence_proxy_async_smem();
     }
     if (warp == 0 && lane == 0) {
@@ -785,7 +996,7 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
         prefetch_tmap(&tmap_g);
         for (int s = 0; s < C::SLOTS; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(ready_bar(s), 128);
+            mbar_init(ready_bar(s), 32 * C::TW);
             mbar_init(empty_bar(s), L0F_ISS);
         }
         mbar_init(done_bar, L0F_ISS);
@@ -803,14 +1014,19 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
             for (int i = i0; i < i1; ++i) {
                 const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
                 mbar_wait(empty_bar(slot), (use & 1) ^ 1);
-                mbar_expect_tx(full_bar(slot), C::PLANE_X + 4 * C::P_OUT * C::PLANE_Z + C::P_OUT * HBP * WOP * 16);
+                mbar_expect_tx(full_bar(slot), C::PLANE_X + (C::STAGED ? C::P_OUT * C::HBZ * C::WO * 16 : 4 * C::P_OUT * C::PLANE_Z) +
+                                                   C::P_OUT * HBP * WOP * 16);
                 const int n = i / C::BANDS, band = i % C::BANDS;
                 const uint32_t sa = smem0 + slot * SLOT;
                 tma_load_4d(sa, &tmap_x, full_bar(slot), 0, 0, band * C::HB - C::PAD, n);
+                if constexpr (C::STAGED) {          // dense tile (map 0 is the plain act8 map)
+                    tma_load_4d(sa + C::X_BYTES, &tmaps_z.m[0], full_bar(slot), 0, 0, band * C::HB, n * C::P_OUT);
+                } else {
 #pragma unroll
-                for (int ph = 0; ph < 4; ++ph)      // columns x = 4*xq + ph of every z row -> plane group ph
-                    tma_load_4d(sa + C::X_BYTES + ph * C::P_OUT * C::PLANE_Z, &tmaps_z.m[ph], full_bar(slot), 0, 0, band * C::HB, n * C::P_OUT);
-                tma_load_4d(sa + C::X_BYTES + C::Z_BYTES, &tmap_g, full_bar(slot), 0, 0, band * HBP, n * C::P_OUT);
+                    for (int ph = 0; ph < 4; ++ph)  // columns x = 4*xq + ph of every z row -> plane group ph
+                        tma_load_4d(sa + C::X_BYTES + ph * C::P_OUT * C::PLANE_Z, &tmaps_z.m[ph], full_bar(slot), 0, 0, band * C::HB, n * C::P_OUT);
+                }
+                tma_load_4d(sa + C::X_BYTES + C::ZS_BYTES + C::Z_BYTES, &tmap_g, full_bar(slot), 0, 0, band * HBP, n * C::P_OUT);
             }
         }
     } else if (warp <= L0F_ISS) {
@@ -824,7 +1040,7 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
                 const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
                 mbar_wait(ready_bar(slot), use & 1);
                 tc_fence_after_sync();
-                const uint32_t xa = smem0 + slot * SLOT, za = xa + C::X_BYTES;
+                const uint32_t xa = smem0 + slot * SLOT, za = xa + C::X_BYTES + C::ZS_BYTES;
                 for (int ks = w; ks < C::KSTEPS; ks += L0F_ISS) {
                     const uint64_t bd = smem_desc(za + ks * 256, 128, C::PLANE_Z);
                     const uint64_t ad = smem_desc(xa + ks * 256, 128, C::WQ * 16);
@@ -836,21 +1052,23 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
         }
     } else {
         // ===== transform warps: z -> dz in place (then the end-of-kernel epilogue) =====
-        const int t = threadIdx.x - 32 * (1 + L0F_ISS);                  // 0..127
-        const int tw = warp - (1 + L0F_ISS);                             // transform warp 0..3
+        constexpr int NT = 32 * C::TW;                                   // transform threads
+        const int t = threadIdx.x - 32 * (1 + L0F_ISS);                  // 0..NT-1
+        const int tw = warp - (1 + L0F_ISS);                             // transform warp
         int cur_view = -1;
         for (int i = i0; i < i1; ++i) {
             const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
             const int n = i / C::BANDS, view = n / n_per_view;
             if (view != cur_view) {                                      // uniform over the four warps
-                asm volatile("bar.sync 1, 128;" ::: "memory");           // nobody still reads the previous view's constants
+                asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");    // nobody still reads the previous view's constants
                 if (t < C::COUT) cst_s[t] = __ldg(cst + (size_t)view * C::COUT + t);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
                 cur_view = view;
             }
             mbar_wait(full_bar(slot), use & 1);
-            uint8_t* zimg = smem + slot * SLOT + C::X_BYTES;
-            const uint4* gimg = reinterpret_cast<const uint4*>(smem + slot * SLOT + C::X_BYTES + C::Z_BYTES);
+            uint8_t* zimg = smem + slot * SLOT + C::X_BYTES + C::ZS_BYTES;
+            const uint4* zst = reinterpret_cast<const uint4*>(smem + slot * SLOT + C::X_BYTES);
+            const uint4* gimg = reinterpret_cast<const uint4*>(smem + slot * SLOT + C::X_BYTES + C::ZS_BYTES + C::Z_BYTES);
 #pragma unroll 1
             for (int o = 0; o < C::P_OUT; ++o) {
                 float4 c4[8];
@@ -860,13 +1078,19 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
                     c4[j] = cst_s[o * 8 + j];
                     acc[j] = 0.f;
                 }
-                for (int e = t; e < HBP * WOP; e += 128) {
+                for (int e = t; e < HBP * WOP; e += NT) {
                     const int py = e / WOP, px = e - py * WOP;
                     // pooling window: rows 2py, 2py+1; columns 2px, 2px+1 = pixel group px/2, phases 2(px&1) and 2(px&1)+1
                     const int ph0 = 2 * (px & 1);
                     uint4* zp0 = reinterpret_cast<uint4*>(zimg + (size_t)(ph0 * C::P_OUT + o) * C::PLANE_Z) + (2 * py) * C::WQ + (px >> 1);
                     uint4* zp1 = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(zp0) + (size_t)C::P_OUT * C::PLANE_Z);
-                    const uint4 raw[4] = {zp0[0], zp1[0], zp0[C::WQ], zp1[C::WQ]};
+                    uint4 raw[4];
+                    if constexpr (C::STAGED) {
+                        const uint4* zs = zst + ((size_t)o * C::HBZ + 2 * py) * C::WO + 2 * px;
+                        raw[0] = zs[0]; raw[1] = zs[1]; raw[2] = zs[C::WO]; raw[3] = zs[C::WO + 1];
+                    } else {
+                        raw[0] = zp0[0]; raw[1] = zp1[0]; raw[2] = zp0[C::WQ]; raw[3] = zp1[C::WQ];
+                    }
                     const uint4 graw = gimg[o * (HBP * WOP) + e];
                     uint32_t outw[4][4];
 #pragma unroll
@@ -920,14 +1144,18 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
             mbar_arrive(ready_bar(slot));
         }
         // ---- end of kernel: bias-gradient sums and the dW partial of this CTA ----
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (t < C::COUT && dbsum != nullptr)
-            atomicAdd(&dbsum[t], (double)db_s[t] + (double)db_s[C::COUT + t] + (double)db_s[2 * C::COUT + t] + (double)db_s[3 * C::COUT + t]);
+        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+        if (t < C::COUT && dbsum != nullptr) {
+            double v = 0.0;
+#pragma unroll
+            for (int q = 0; q < C::TW; ++q) v += (double)db_s[q * C::COUT + t];
+            atomicAdd(&dbsum[t], v);
+        }
         const int quad = warp & 3;
         const int m = quad * 16 + (lane & 15), j = m >> 3, e8 = m & 7;   // accumulator row = (image row kh = j, tap kw' = e8)
         float* part = work + (long)g * C::PART;
         float* stage = reinterpret_cast<float*>(smem);                   // [ph][co][kh][kw]: every MMA has completed (done_bar)
-        if (i1 > i0) {
+        if (i1 > i0 && tw < 4) {                                         // four warps cover the four TMEM lane quadrants
             mbar_wait(done_bar, 0);
             tc_fence_after_sync();
 #pragma unroll 1
@@ -951,8 +1179,8 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
                 }
             }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int idx = t; idx < C::PART; idx += 128) {                   // fixed summation order over the four phases
+        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+        for (int idx = t; idx < C::PART; idx += NT) {                    // fixed summation order over the four phases
             float v = 0.f;
             if (i1 > i0) {
 #pragma unroll
@@ -1015,12 +1243,20 @@ int launch_conv_tc_wgrad_l0_fused(const void* x, const void* z, const void* dp, 
         int rc = encode_tmap_bf16_4d(&tx, x, dims, strides, box);
         if (rc) return rc;
     }
-    for (int ph = 0; ph < 4; ++ph) {        // fp16 data: same 2-byte elements, no conversion; columns 4*i + ph
-        const uint64_t dims[4] = {8, (uint64_t)C::WO / 4, (uint64_t)C::HO, (uint64_t)N * C::P_OUT};
-        const uint64_t strides[3] = {64, (uint64_t)C::WO * 16, (uint64_t)C::WO * C::HO * 16};
-        const uint32_t box[4] = {8, (uint32_t)C::WQ, (uint32_t)C::HBZ, (uint32_t)C::P_OUT};
-        int rc = encode_tmap_bf16_4d(&tz.m[ph], reinterpret_cast<const uint8_t*>(z) + 16 * ph, dims, strides, box);
-        if (rc) return rc;
+    for (int ph = 0; ph < 4; ++ph) {        // fp16 data: same 2-byte elements, no conversion
+        if (C::STAGED) {                    // one dense map: whole rows of the act8 tensor
+            const uint64_t dims[4] = {8, (uint64_t)C::WO, (uint64_t)C::HO, (uint64_t)N * C::P_OUT};
+            const uint64_t strides[3] = {16, (uint64_t)C::WO * 16, (uint64_t)C::WO * C::HO * 16};
+            const uint32_t box[4] = {8, (uint32_t)C::WO, (uint32_t)C::HBZ, (uint32_t)C::P_OUT};
+            int rc = encode_tmap_bf16_4d(&tz.m[ph], z, dims, strides, box);
+            if (rc) return rc;
+        } else {                            // columns 4*i + ph
+            const uint64_t dims[4] = {8, (uint64_t)C::WO / 4, (uint64_t)C::HO, (uint64_t)N * C::P_OUT};
+            const uint64_t strides[3] = {64, (uint64_t)C::WO * 16, (uint64_t)C::WO * C::HO * 16};
+            const uint32_t box[4] = {8, (uint32_t)C::WQ, (uint32_t)C::HBZ, (uint32_t)C::P_OUT};
+            int rc = encode_tmap_bf16_4d(&tz.m[ph], reinterpret_cast<const uint8_t*>(z) + 16 * ph, dims, strides, box);
+            if (rc) return rc;
+        }
     }
     {
         const uint64_t dims[4] = {8, (uint64_t)C::WOP, (uint64_t)(C::HO / 2), (uint64_t)N * C::P_OUT};
@@ -1029,7 +1265,7 @@ int launch_conv_tc_wgrad_l0_fused(const void* x, const void* z, const void* dp, 
         int rc = encode_tmap_bf16_4d(&tg, dp, dims, strides, box);
         if (rc) return rc;
     }
-    conv_tc_wgrad_l0_fused_kernel<C><<<G, L0F_THREADS, C::SMEM, st>>>(tx, tz, tg, cst, work, dbsum, N, n_per_view);
+    conv_tc_wgrad_l0_fused_kernel<C><<<G, C::THREADS, C::SMEM, st>>>(tx, tz, tg, cst, work, dbsum, N, n_per_view);
     int rc = launch_status("conv_tc_wgrad_l0_fused_kernel");
     if (rc) return rc;
     wgrad_reduce_kernel<<<(C::PART + 255) / 256, 256, 0, st>>>(work, G, C::PART, dw);
@@ -1037,8 +1273,9 @@ int launch_conv_tc_wgrad_l0_fused(const void* x, const void* z, const void* dp, 
 }
 
 //                           CIN COUT HIN WIN KS PAD BANDS SLOTS PSPLIT
-using WgA1 = TcWgCfg<8, 16, 56, 56, 5, 2, 7, 2, 1, 4>;
-using WgA2 = TcWgCfg<16, 32, 28, 28, 5, 2, 1, 1, 2, 2>;
+//                   CIN COUT HIN WIN KS PAD XPH WQ BANDS SLOTS PSPLIT   (phases in N)
+using WgA1 = WgPCfg<8, 16, 56, 56, 5, 2, 4, 16, 4, 3, 1>;
+using WgA2 = WgPCfg<16, 32, 28, 28, 5, 2, 2, 16, 2, 3, 2>;
 using WgA3 = TcWgCfg<32, 64, 14, 14, 5, 2, 1, 3, 4>;
 using WgI1 = TcWgCfg<32, 64, 14, 14, 5, 0, 1, 4, 4>;
 using WgS1 = TcWgCfg<32, 64, 14, 14, 3, 1, 1, 3, 2>;
@@ -1103,7 +1340,11 @@ static int wgrad_tc_dispatch(const void* x, const void* dz, float* dw, float* wo
                              int K, int pad, cudaStream_t st, int64_t* need) {
 #define WG_RUN(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) \
         return launch_conv_tc_wgrad<CFG>(x, dz, dw, work, N, st, need);
-    WG_RUN(WgA1) WG_RUN(WgA2) WG_RUN(WgA3) WG_RUN(WgI1) WG_RUN(WgS1) WG_RUN(WgA0) WG_RUN(WgI0) WG_RUN(WgS0) WG_RUN(WgS2)
+#define WGP_RUN(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) \
+        return launch_conv_tc_wgrad_ph<CFG>(x, dz, dw, work, N, st, need);
+    WGP_RUN(WgA1) WGP_RUN(WgA2)
+#undef WGP_RUN
+    WG_RUN(WgA3) WG_RUN(WgI1) WG_RUN(WgS1) WG_RUN(WgA0) WG_RUN(WgI0) WG_RUN(WgS0) WG_RUN(WgS2)
 #undef WG_RUN
     set_error("conv_tc_wgrad: unsupported geometry Cin=%d Cout=%d H=%d W=%d K=%d pad=%d", Cin, Cout, H, W, K, pad);
     return -4;
@@ -1111,7 +1352,7 @@ static int wgrad_tc_dispatch(const void* x, const void* dz, float* dw, float* wo
 
 // fused first-layer backward (Cin = 1): geometries of the first layers of the three encoders
 //                    COUT HIN  WIN KS PAD BANDS SLOTS CTAS
-using WgF_A0 = L0FCfg<8, 112, 112, 5, 2, 7, 2, 2>;
+using WgF_A0 = L0FCfg<8, 112, 112, 5, 2, 7, 2, 2>;         // (STAGED, one CTA per SM with 8 transform warps: 0.73 ms vs 0.55 ms)
 using WgF_I0 = L0FCfg<32, 28, 28, 5, 2, 1, 2, 1>;
 using WgF_S0 = L0FCfg<32, 28, 28, 3, 1, 1, 2, 1>;
 

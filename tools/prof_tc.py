@@ -15,7 +15,7 @@ BF = torch.bfloat16
 def layer(Cin, Cout, H, K, pad):
     Ho = H + 2 * pad - K + 1
     if Cin == 1:
-        x8 = torch.rand(N, H, H + pad, 8, device=DEV).to(BF)
+        x8 = torch.rand(N, H, ops.quad8_width(H, pad), 8, device=DEV).to(BF)
     else:
         x8 = torch.randn(N, Cin // 8, H, H, 8, device=DEV).to(BF)
     dz8 = torch.randn(N, Cout // 8, Ho, Ho, 8, device=DEV).to(BF)
@@ -26,10 +26,11 @@ def layer(Cin, Cout, H, K, pad):
     stats = torch.zeros(views, Cout, 2, dtype=torch.float64, device=DEV)
     z8 = torch.empty(N, Cout // 8, Ho, Ho, 8, dtype=torch.float16, device=DEV)
     dw = torch.empty(Cout, Cin, K, K, device=DEV)
-    work = torch.empty(ops.conv_tc_wgrad_work_floats(N, Cin, Cout, H, H, K, pad), device=DEV)
+    work = torch.empty(ops.conv_tc_wgrad_work_floats(N, Cin, Cout, H, H, K, pad), device=DEV) if Cin > 1 else None
     for _ in range(reps):
         ops.conv_tc(x8, wp, b, z8, stats, B, Cout, K, pad)
-        ops.conv_tc_wgrad(x8, dz8, dw, work, pad)
+        if Cin > 1:
+            ops.conv_tc_wgrad(x8, dz8, dw, work, pad)
     if Cin > 1:
         wpf = torch.empty(ops.conv_tc_weight_bytes(Cout, Cin, K), dtype=torch.uint8, device=DEV)
         ops.conv_tc_prep_weights(w, wpf, flip=True)
@@ -54,6 +55,7 @@ def layer(Cin, Cout, H, K, pad):
 
 
 layer(1, 8, 112, 5, 2)
+layer(1, 32, 28, 5, 2)
 layer(8, 16, 56, 5, 2)
 layer(16, 32, 28, 5, 2)
 layer(32, 64, 14, 5, 2)
