@@ -37,24 +37,38 @@ def main():
             name = re.sub(r"\(int\)|\(bool\)", "", d[ik])
             grid = [int(x) for x in re.findall(r"\d+", d[ig])]
             traffic = (to_bytes(d[ir], units[ir]) + to_bytes(d[iw], units[iw])) * 1024 / b
+            def qw(w, pad):
+                return (w + 2 * pad + 3) // 4
             m = re.search(r"conv_tc_kernel<.*TcCfg<([\d, ]+)>", name)
+            m2 = re.search(r"conv_tc_wgrad_ph_kernel<.*WgPCfg<([\d, ]+)>", name)
+            m3 = re.search(r"conv_tc_wgrad_l0_fused_kernel<.*L0FCfg<([\d, ]+)", name)
+            m4 = re.search(r"conv_tc_wgrad_kernel<.*TcWgCfg<([\d, ]+)>", name)
             if m:
                 a = [int(x) for x in m.group(1).split(",")]
                 cin, cout, hin, win, ks, pad = a[0], a[1], a[3], a[4], a[5], a[6]
                 views = grid[1]
                 n = 1024 * (views if views > 1 else V_STUDENT)
                 npv = 1024 if views > 1 else n
-                shape = f"{n}x{hin}x{win + pad}x8" if cin == 1 else f"{n}x{cin // 8}x{hin}x{win}x8"
+                shape = f"{n}x{hin}x{qw(win, pad)}x8" if cin == 1 else f"{n}x{cin // 8}x{hin}x{win}x8"
                 key = f"conv_tc:{shape}:{npv}x{cout}x{ks}x{pad}"
-            else:
-                m = re.search(r"conv_tc_wgrad_kernel<.*TcWgCfg<([\d, ]+)>", name)
-                if not m:
-                    continue
-                a = [int(x) for x in m.group(1).split(",")]
+            elif m2:
+                a = [int(x) for x in m2.group(1).split(",")]
+                cin, hin, win, pad = a[0], a[2], a[3], a[5]
+                key = f"conv_tc_wgrad:{1024 * V_STUDENT}x{cin // 8}x{hin}x{win}x8:{pad}"
+            elif m3:
+                a = [int(x) for x in m3.group(1).split(",")]
+                hin, win, pad = a[1], a[2], a[4]
+                key = f"conv_tc_wgrad_l0_fused:{1024 * V_STUDENT}x{hin}x{qw(win, pad)}x8:1024x{pad}"
+            elif m4:
+                a = [int(x) for x in m4.group(1).split(",")]
                 cin, hin, win, pad = a[0], a[2], a[3], a[5]
                 n = 1024 * V_STUDENT
                 shape = f"{n}x{hin}x{win + pad}x8" if cin == 1 else f"{n}x{cin // 8}x{hin}x{win}x8"
                 key = f"conv_tc_wgrad:{shape}:{pad}"
+            else:
+                continue
+            if key in launches:           # the same kernel more than once in the capture: keep the first (student) launch
+                continue
             launches[key] = {"dram_bytes": traffic, "us_under_ncu": float(d[it].replace(",", "")) * (1024 / b if False else 1), "source": path.split("/")[-1],
                              "captured_at_batch": b}
     json.dump({"per_gpu_batch": 1024, "metric": "dram__bytes_read.sum + dram__bytes_write.sum (ncu --set full --clock-control none)",
