@@ -17,9 +17,10 @@ namespace {
 using namespace umma;
 
 constexpr int GBM = 128, GBN = 128, GBK = 32;            // tile (GBK fp32 = one 128-byte swizzle row)
-constexpr int G_STAGES = 6;
+// Two pipeline depths: 6 stages (one CTA per SM) for long reductions; 3 stages (two CTAs per SM) for K-per-split <= 1024, where
+// a tile is a handful of k-blocks and the second resident CTA hides the first one's pipeline fill and store epilogue.
 constexpr int G_A_BYTES = GBM * GBK * 4, G_B_BYTES = GBN * GBK * 4, G_STAGE = G_A_BYTES + G_B_BYTES;
-constexpr int G_SMEM = G_STAGES * G_STAGE + 1024 + 256;
+constexpr int g_smem(int stages) { return stages * G_STAGE + 1024 + 256; }
 
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return smem_desc(saddr, lbo_bytes, sbo_bytes) | (2ull << 61);      // layout type 2 = SWIZZLE_128B
@@ -40,8 +41,8 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
 // epi: 0 store, 1 +bias, 2 +bias,ReLU, 3 +bias,ReLU,dropout(mask), 4 split-K partial (C holds [splits][M][ldc]),
 //      5 InfoNCE: e = exp(x*fparam - fparam) stored as bf16 into C (ldc in bf16 elements) + per-(column tile, row) sums of e in aux
 // BF16 = true: bf16 operands (kind::f16, UMMA K = 16, 64-element k-blocks); false: fp32 operands consumed as tf32.
-template <bool BF16>
-__global__ void __launch_bounds__(192, 1)
+template <bool BF16, int G_STAGES>
+__global__ void __launch_bounds__(192, G_STAGES <= 3 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C, int64_t ldc, int M, int N,
                int K, int k_per_split, int epi, const float* __restrict__ bias, const uint8_t* __restrict__ mask,
                float keep_scale, float* __restrict__ aux, float fparam) {
@@ -224,10 +225,12 @@ int launch_gemm_tc_ex(const void* A, int64_t lda, const void* Bm, int64_t ldb, v
                       const float* bias, const uint8_t* mask, float keep_scale, float* aux, float fparam, int bf16, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem(6));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem(6));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem(3));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem(3));
         if (e != cudaSuccess) {
-            set_error("gemm_tc: cannot set %d bytes of shared memory: %s", G_SMEM, cudaGetErrorString(e));
+            set_error("gemm_tc: cannot set %d bytes of shared memory: %s", g_smem(6), cudaGetErrorString(e));
             return (int)e;
         }
         configured = true;
@@ -242,12 +245,17 @@ int launch_gemm_tc_ex(const void* A, int64_t lda, const void* Bm, int64_t ldb, v
     int kps = ((K + splits - 1) / splits + gbke - 1) / gbke * gbke;
     splits = (K + kps - 1) / kps;
     dim3 grid((N + GBN - 1) / GBN, (M + GBM - 1) / GBM, splits);
-    if (bf16)
-        gemm_tc_kernel<true><<<grid, 192, G_SMEM, st>>>(ta, tb, reinterpret_cast<float*>(C), ldc, M, N, K, kps, splits > 1 ? 4 : epi, bias, mask,
-                                                        keep_scale, aux, fparam);
+    const bool shallow = kps <= 1024 && (long)grid.x * grid.y * grid.z > sm_count();      // enough tiles for two CTAs per SM
+    const int e = splits > 1 ? 4 : epi;
+    float* Cf = reinterpret_cast<float*>(C);
+    if (bf16 && shallow)
+        gemm_tc_kernel<true, 3><<<grid, 192, g_smem(3), st>>>(ta, tb, Cf, ldc, M, N, K, kps, e, bias, mask, keep_scale, aux, fparam);
+    else if (bf16)
+        gemm_tc_kernel<true, 6><<<grid, 192, g_smem(6), st>>>(ta, tb, Cf, ldc, M, N, K, kps, e, bias, mask, keep_scale, aux, fparam);
+    else if (shallow)
+        gemm_tc_kernel<false, 3><<<grid, 192, g_smem(3), st>>>(ta, tb, Cf, ldc, M, N, K, kps, e, bias, mask, keep_scale, aux, fparam);
     else
-        gemm_tc_kernel<false><<<grid, 192, G_SMEM, st>>>(ta, tb, reinterpret_cast<float*>(C), ldc, M, N, K, kps, splits > 1 ? 4 : epi, bias, mask,
-                                                         keep_scale, aux, fparam);
+        gemm_tc_kernel<false, 6><<<grid, 192, g_smem(6), st>>>(ta, tb, Cf, ldc, M, N, K, kps, e, bias, mask, keep_scale, aux, fparam);
     return launch_status("gemm_tc_kernel");
 }
 
