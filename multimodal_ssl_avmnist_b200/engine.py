@@ -225,6 +225,8 @@ class DinoStepEngine:
                         self._tcw[("flip", mod, li)] = torch.empty(ops.conv_tc_weight_bytes(co, ci, k), dtype=torch.uint8, device=self.device)
         self.overlap_teacher = True
         self._side_stream = torch.cuda.Stream(device=self.device)
+        self._lin_wg_stream = torch.cuda.Stream(device=self.device)       # linear weight gradients
+        self._lin_wg_pending = False
         self._side_stream2 = torch.cuda.Stream(device=self.device)
         self._wgrad_streams = {m: torch.cuda.Stream(device=self.device) for m in ("img", "aud")}
         self._aug_stream = torch.cuda.Stream(device=self.device)
@@ -532,9 +534,21 @@ class DinoStepEngine:
         ops.bn1d_gelu_drop_fwd(hh, w[f"{role}.{tag}hscale"], w[f"{role}.{tag}hshift"], mask, drop_p, g)
         ops.linear_fwd(g, P[prefix + "mlp.4.weight"], P[prefix + "mlp.4.bias"], out, tc=self.lin_tc)
 
+    def _lin_wgrad(self, dy, x, gw, gb):
+        """Weight / bias gradient of a linear layer.  Nothing in the backward chain depends on it, so it runs on its own stream
+        beside the data gradients (dy and x are not written again in this step; backward_pass joins the stream at its end)."""
+        st = self._lin_wg_stream if self.overlap_teacher else None
+        if st is None:
+            ops.linear_bwd_weight(dy, x, gw, gb, tc=self.lin_tc)
+            return
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            ops.linear_bwd_weight(dy, x, gw, gb, tc=self.lin_tc)
+        self._lin_wg_pending = True
+
     def _head_bwd(self, w, role, prefix, x, d_out, hh, g, d_g, d_hh, d_x, mask, drop_p, tag=""):
         S, G = self.S, self.G
-        ops.linear_bwd_weight(d_out, g, G[prefix + "mlp.4.weight"], G[prefix + "mlp.4.bias"], tc=self.lin_tc)
+        self._lin_wgrad(d_out, g, G[prefix + "mlp.4.weight"], G[prefix + "mlp.4.bias"])
         ops.linear_bwd_data(d_out, S[prefix + "mlp.4.weight"], d_g, tc=self.lin_tc)
         sums = w[f"{role}.{tag}hsums"]
         sums.zero_()
@@ -542,7 +556,7 @@ class DinoStepEngine:
         ops.bn1d_gelu_drop_bwd_reduce(hh, d_g, sc, sh, mu, inv, mask, drop_p, sums)
         ops.bn1d_gelu_drop_bwd_apply(hh, d_g, sc, sh, mu, inv, mask, drop_p, sums, d_hh)
         ops.bn_param_grads(sums, G[prefix + "mlp.1.weight"], G[prefix + "mlp.1.bias"], 1)
-        ops.linear_bwd_weight(d_hh, x, G[prefix + "mlp.0.weight"], G[prefix + "mlp.0.bias"], tc=self.lin_tc)
+        self._lin_wgrad(d_hh, x, G[prefix + "mlp.0.weight"], G[prefix + "mlp.0.bias"])
         ops.linear_bwd_data(d_hh, S[prefix + "mlp.0.weight"], d_x, tc=self.lin_tc)
 
     def _encode(self, w, role, P, bns, x_img, x_aud, N, B, n_fusion, fmask, train=True):
@@ -852,10 +866,10 @@ class DinoStepEngine:
             d_feat.add_(w["d.emb"])
         if multi:
             d_cat, d_h1 = w["d.cat"], w["d.h1"]
-            ops.linear_bwd_weight(d_feat, w["s.h1"], G["enc.fusion.3.weight"], G["enc.fusion.3.bias"], tc=self.lin_tc)
+            self._lin_wgrad(d_feat, w["s.h1"], G["enc.fusion.3.weight"], G["enc.fusion.3.bias"])
             ops.linear_bwd_data(d_feat, S["enc.fusion.3.weight"], d_h1, tc=self.lin_tc)
             ops.act_bwd(d_h1, w["s.h1"], self.fusion_dropout)
-            ops.linear_bwd_weight(d_h1, w["s.cat"][:Nv], G["enc.fusion.0.weight"], G["enc.fusion.0.bias"], tc=self.lin_tc)
+            self._lin_wgrad(d_h1, w["s.cat"][:Nv], G["enc.fusion.0.weight"], G["enc.fusion.0.bias"])
             ops.linear_bwd_data(d_h1, S["enc.fusion.0.weight"], d_cat[:Nv], tc=self.lin_tc)
             if self.mode != "default":
                 for i, (m, sl) in enumerate((("aux_image", slice(0, E)), ("aux_audio", slice(E, 2 * E)))):
@@ -872,20 +886,23 @@ class DinoStepEngine:
                     side.wait_stream(main)
                 with ctx:
                     p_last = w[f"s.{mod}.p{len(layers) - 1}"].view(Ns, nflat)
-                    ops.linear_bwd_weight(d_cat[:, sl], p_last, G[lin + ".weight"], G[lin + ".bias"], tc=self.lin_tc)
+                    self._lin_wgrad(d_cat[:, sl], p_last, G[lin + ".weight"], G[lin + ".bias"])
                     d_p = w[f"{mod}.dp_a"][:Ns * nflat].view(Ns, nflat)
                     ops.linear_bwd_data(d_cat[:, sl], S[lin + ".weight"], d_p, tc=self.lin_tc)
                     self._conv_stack_bwd(w, mod, layers, x, d_p, Ns, B)
             if side is not None:
                 main.wait_stream(side)
         else:
-            ops.linear_bwd_weight(d_feat, w["s.e14"], G["enc.projection.0.weight"], G["enc.projection.0.bias"], tc=self.lin_tc)
+            self._lin_wgrad(d_feat, w["s.e14"], G["enc.projection.0.weight"], G["enc.projection.0.bias"])
             ops.linear_bwd_data(d_feat, S["enc.projection.0.weight"], w["d.e14"], tc=self.lin_tc)
-            ops.linear_bwd_weight(w["d.e14"], w["s.pool"], G["enc.encoder.14.weight"], G["enc.encoder.14.bias"], tc=self.lin_tc)
+            self._lin_wgrad(w["d.e14"], w["s.pool"], G["enc.encoder.14.weight"], G["enc.encoder.14.bias"])
             ops.linear_bwd_data(w["d.e14"], S["enc.encoder.14.weight"], w["d.pool"], tc=self.lin_tc)
             d_p = w["img.dp_a"][:Ns * 128 * 9].view(Ns, 128, 3, 3)
             ops.avgpool_bwd(w["d.pool"], d_p)
             self._conv_stack_bwd(w, "img", self.img_layers, xi, d_p, Ns, B)
+        if self._lin_wg_pending:
+            torch.cuda.current_stream().wait_stream(self._lin_wg_stream)
+            self._lin_wg_pending = False
         if self.world > 1:
             self.allreduce_gradients()
 
