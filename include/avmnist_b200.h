@@ -151,6 +151,9 @@ int b200_conv_bwd_data(const float* dz, const float* w, float* dx, int N, int Ci
 int b200_conv_tc_supported(int Cin, int Cout, int H, int W, int K, int pad);
 int64_t b200_conv_tc_weight_bytes(int Cin, int Cout, int K);
 int b200_conv_tc_prep_weights(const float* w, void* wprep, int Cin, int Cout, int K, int flip, void* stream);
+/* the same for n weight tensors in ONE launch: desc_dev = device array int64 [n][6] = {w pointer, out pointer, Cin, Cout, K, flip}
+ * (validated like b200_conv_tc_prep_weights by the caller: the kernel trusts the table) */
+int b200_conv_tc_prep_weights_multi(const int64_t* desc_dev, int n, void* stream);
 int b200_conv_tc(const void* x_act8, const void* wprep, const float* bias, void* out, double* stats, int N,
                  int n_per_view, int Cin, int Cout, int H, int W, int K, int pad, int out_bf16, void* stream);
 /* dw [Cout][Cin][K][K] = sum_n corr(x_n, dz_n); x and dz bf16 act8, fp32 accumulate in TMEM; per-CTA partials in work

@@ -69,7 +69,7 @@ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ?
 // de-interleaved in shared memory -- one plane per x phase, loaded by one strided TMA map each -- so that consecutive
 // rows m are again consecutive 16-byte units.  5x5, 8 -> 16 channels: 20 MMAs (N = 64) per 512 outputs instead of 60.
 // A function of the layer shape only, because the weight image (b200_conv_tc_prep_weights) depends on it.
-constexpr int xph_for(int cin, int cout, int ks) {
+__host__ __device__ constexpr int xph_for(int cin, int cout, int ks) {
     return (ks == 5 && ((cin == 8 && cout == 16) || (cin == 16 && cout == 8))) ? 4
          : (ks == 5 && ((cin == 16 && cout == 32) || (cin == 32 && cout == 16))) ? 2 : 1;
 }
@@ -360,10 +360,8 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
 
 // fp32 OIHW weights -> the bf16 byte image the MMA issuer expects: [mma][k chunk (2)][n group][8 rows][8 k].
 // flip = 1 prepares the data-gradient convolution: w is the forward weight [CIN][COUT][KS][KS] and the taps are mirrored.
-__global__ void conv_tc_prep_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int CIN, int COUT, int NPAD,
-                                            int KS, int XPH, int flip, int total) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= total) return;
+__device__ __forceinline__ void conv_tc_prep_element(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int CIN, int COUT, int NPAD,
+                                                     int KS, int XPH, int flip, int e) {
     const int k8 = e & 7, r = (e >> 3) & 7, NG = NPAD / 8;
     const int ng = (e >> 6) % NG, c = (e / (64 * NG)) & 1, m = e / (128 * NG);
     const int col = ng * 8 + r, ph = col / COUT, co = col % COUT;      // accumulator column = (x phase, output channel)
@@ -393,6 +391,33 @@ __global__ void conv_tc_prep_weights_kernel(const float* __restrict__ w, __nv_bf
         v = flip ? w[((ci * COUT + co) * KS + (KS - 1 - kh)) * KS + (KS - 1 - kw)] : w[((co * CIN + ci) * KS + kh) * KS + kw];
     }
     out[e] = __float2bfloat16_rn(v);
+}
+
+__global__ void conv_tc_prep_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int CIN, int COUT, int NPAD,
+                                            int KS, int XPH, int flip, int total) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < total) conv_tc_prep_element(w, out, CIN, COUT, NPAD, KS, XPH, flip, e);
+}
+
+__host__ __device__ inline void conv_tc_weight_geometry(int Cin, int Cout, int K, int* xph, int* npad, int* total) {
+    const int x = Cin == 1 ? 4 : xph_for(Cin, Cout, K), kwx = K + x - 1;
+    const int np = (x * Cout + 15) / 16 * 16;
+    const int nmma = (Cin == 1) ? (K + 1) / 2 : (Cin == 8) ? K * ((kwx + 1) / 2) : K * kwx * (Cin / 16);
+    *xph = x;
+    *npad = np;
+    *total = nmma * np * 16;                  // bf16 elements
+}
+
+// all weight images of a step in ONE launch: desc[i] = {w pointer, out pointer, Cin, Cout, K, flip} (int64 each), blockIdx.y = i
+__global__ void conv_tc_prep_weights_multi_kernel(const long long* __restrict__ desc) {
+    const long long* d = desc + 6 * blockIdx.y;
+    const int Cin = (int)d[2], Cout = (int)d[3], K = (int)d[4], flip = (int)d[5];
+    int xph, npad, total;
+    conv_tc_weight_geometry(Cin, Cout, K, &xph, &npad, &total);
+    const float* w = reinterpret_cast<const float*>(d[0]);
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d[1]);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x)
+        conv_tc_prep_element(w, out, Cin, Cout, npad, K, xph, flip, e);
 }
 
 // fp32 NCHW -> bf16 act8 (tests and the hand-over from the fp32 first layer)
@@ -1317,10 +1342,9 @@ int b200_conv_tc_supported(int Cin, int Cout, int H, int W, int K, int pad) {
 }
 
 int64_t b200_conv_tc_weight_bytes(int Cin, int Cout, int K) {
-    const int xph = Cin == 1 ? 4 : xph_for(Cin, Cout, K), kwx = K + xph - 1;
-    const int npad = (xph * Cout + 15) / 16 * 16;
-    const int nmma = (Cin == 1) ? (K + 1) / 2 : (Cin == 8) ? K * ((kwx + 1) / 2) : K * kwx * (Cin / 16);
-    return (int64_t)nmma * npad * 32;
+    int xph, npad, total;
+    conv_tc_weight_geometry(Cin, Cout, K, &xph, &npad, &total);
+    return (int64_t)total * 2;
 }
 
 int b200_conv_tc_prep_weights(const float* w, void* out, int Cin, int Cout, int K, int flip, void* stream) {
@@ -1334,6 +1358,12 @@ int b200_conv_tc_prep_weights(const float* w, void* out, int Cin, int Cout, int 
     conv_tc_prep_weights_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(out), Cin, Cout, npad, K,
                                                                                       xph, flip, total);
     return launch_status("conv_tc_prep_weights_kernel");
+}
+
+int b200_conv_tc_prep_weights_multi(const int64_t* desc_dev, int n, void* stream) {
+    B200_REQUIRE(desc_dev && n > 0 && n <= 65535, -1, "conv_tc_prep_weights_multi: bad arguments");
+    conv_tc_prep_weights_multi_kernel<<<dim3(16, (unsigned)n), 256, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(desc_dev));
+    return launch_status("conv_tc_prep_weights_multi_kernel");
 }
 
 static int wgrad_tc_dispatch(const void* x, const void* dz, float* dw, float* work, int N, int Cin, int Cout, int H, int W,

@@ -216,6 +216,7 @@ class DinoStepEngine:
             if self.tc[mod] and self.tc[mod][0] and not (len(self.tc[mod]) > 1 and self.tc[mod][1]):
                 self.tc[mod][0] = False
         self._tcw = {}
+        self._prep_desc = {}
         for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers)):
             for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers):
                 if self.tc[mod][li]:
@@ -479,13 +480,22 @@ class DinoStepEngine:
     # forward building blocks
     # ------------------------------------------------------------------------------------------------------
     def _prep_tc_weights(self, role, P):
-        """fp32 conv weights -> the bf16 operand images of the tensor-core convolutions (weights change every step)."""
-        for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers)):
-            for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers):
-                if self.tc[mod][li]:
-                    ops.conv_tc_prep_weights(P["enc." + conv + ".weight"], self._tcw[(role, mod, li)])
-                    if role == "s" and ci > 1:
-                        ops.conv_tc_prep_weights(P["enc." + conv + ".weight"], self._tcw[("flip", mod, li)], flip=True)
+        """fp32 conv weights -> the bf16 operand images of the tensor-core convolutions (weights change every step): ONE launch
+        over a device table of (weight, image, Cin, Cout, K, flip) records, built once per role (the arenas never move)."""
+        desc = self._prep_desc.get(role)
+        if desc is None:
+            rows = []
+            for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers)):
+                for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers):
+                    if self.tc[mod][li]:
+                        wt = P["enc." + conv + ".weight"]
+                        rows.append([wt.data_ptr(), self._tcw[(role, mod, li)].data_ptr(), ci, co, k, 0])
+                        if role == "s" and ci > 1:       # data gradient: channels swapped, taps mirrored
+                            rows.append([wt.data_ptr(), self._tcw[("flip", mod, li)].data_ptr(), co, ci, k, 1])
+            desc = torch.tensor(rows, dtype=torch.int64, device=self.device) if rows else False
+            self._prep_desc[role] = desc
+        if desc is not False:
+            ops.conv_tc_prep_weights_multi(desc)
 
     def _conv_stack(self, w, role, mod, layers, x, N, B, P, bns, train=True):
         """conv -> BatchNorm(batch statistics per view-call) -> ReLU -> MaxPool2 for every layer; tensor-core layers keep

@@ -238,6 +238,11 @@ def conv_tc(x8, wprep, bias, out, stats, n_per_view, Cout, K, pad):
                                     fmt, _stream()), "conv_tc")
 
 
+def conv_tc_prep_weights_multi(desc):
+    """desc: int64 CUDA tensor [n, 6] = (w data_ptr, out data_ptr, Cin, Cout, K, flip) per weight image; one launch for all"""
+    _lib.check(_lib_().b200_conv_tc_prep_weights_multi(_ptr(desc, torch.int64), desc.shape[0], _stream()), "conv_tc_prep_weights_multi")
+
+
 def conv_tc_wgrad_work_floats(N, Cin, Cout, H, W, K, pad):
     n = int(_lib_().b200_conv_tc_wgrad_work_floats(N, Cin, Cout, H, W, K, pad))
     if n < 0:
