@@ -292,6 +292,20 @@ class DinoStepEngine:
             return torch.empty(*shape, dtype=dtype, device=dev)
 
         w = {"B": B, "Ns": Ns, "Nt": Nt}
+        # every accumulator that must be zero when a step starts (BatchNorm statistics, backward sums, bias-gradient sums)
+        # lives in ONE float64 arena: one memset per step instead of two dozen
+        zarena = torch.zeros(1 << 17, dtype=torch.float64, device=dev)
+        zoff = [0]
+
+        def zalloc(*shape):
+            n = int(math.prod(shape))
+            o = zoff[0]
+            zoff[0] = o + (n + 1) // 2 * 2
+            if zoff[0] > zarena.numel():
+                raise ops._lib.B200Error("zero arena too small")
+            return zarena[o:o + n].view(*shape)
+
+        w["zarena"] = zarena
         # augmentation
         w["img_ops"] = torch.zeros(B, V, A.MAX_OPS, A.OP_WORDS, dtype=torch.int32, device=dev)
         w["aud_ops"] = torch.zeros(B, V, A.MAX_OPS, A.OP_WORDS, dtype=torch.int32, device=dev)
@@ -322,11 +336,11 @@ class DinoStepEngine:
                         w[f"{role}.{mod}.p8{li}"] = e(N, co // 8, ho // 2, ho // 2, 8, dtype=BF)
                     if not next_tc or not tc:
                         w[f"{role}.{mod}.p{li}"] = e(N, co, ho // 2, ho // 2)
-                    w[f"{role}.{mod}.stats{li}"] = torch.zeros(nv, co, 2, dtype=torch.float64, device=dev)
+                    w[f"{role}.{mod}.stats{li}"] = zalloc(nv, co, 2)
                     for nm in ("scale", "shift", "mean", "invstd"):
                         w[f"{role}.{mod}.{nm}{li}"] = e(nv, co)
                     if role == "s":
-                        w[f"s.{mod}.sums{li}"] = torch.zeros(nv, co, 2, dtype=torch.float64, device=dev)
+                        w[f"s.{mod}.sums{li}"] = zalloc(nv, co, 2)
                         sc = scr[mod]
                         if tc:
                             sc["wg"] = max(sc["wg"], ops.conv_tc_wgrad_work_floats(N, ci, co, hw, hw, k, pad))
@@ -345,7 +359,7 @@ class DinoStepEngine:
             w[f"{m}.dz"] = e(max(sc["z"], 4))
             w[f"{m}.dz8"] = e(max(sc["z8"], 8), dtype=BF)
             w[f"{m}.dz8b"] = e(max(sc["z8"], 8), dtype=BF)      # second buffer: the weight gradient of layer l overlaps layer l-1
-            w[f"{m}.dbsum"] = torch.zeros(8, 128, dtype=torch.float64, device=dev)
+            w[f"{m}.dbsum"] = zalloc(8, 128)
             w[f"{m}.dp_a"], w[f"{m}.dp_b"] = e(sc["p"]), e(sc["p"])
             w[f"{m}.wg_work"] = e(max(sc["wg"], 4))
             w[f"{m}.wg_work_b"] = e(max(sc["wg"], 4))
@@ -370,11 +384,11 @@ class DinoStepEngine:
             w[f"{role}.hh"] = e(N, 512)
             w[f"{role}.g"] = e(N, 512)
             w[f"{role}.proj"] = e(N, P)
-            w[f"{role}.hstats"] = torch.zeros(512, 2, dtype=torch.float64, device=dev)
+            w[f"{role}.hstats"] = zalloc(512, 2)
             for nm in ("hscale", "hshift", "hmean", "hinvstd"):
                 w[f"{role}.{nm}"] = e(1, 512)
         w["s.hmask"] = torch.ones(Nv, 512, dtype=torch.uint8, device=dev)
-        w["s.hsums"] = torch.zeros(512, 2, dtype=torch.float64, device=dev)
+        w["s.hsums"] = zalloc(512, 2)
         w["d.proj"], w["d.g"], w["d.hh"] = e(Nv, P), e(Nv, 512), e(Nv, 512)
         parts = ops.dino_loss_parts(B)
         w["part_loss"], w["part_colsum"] = e(parts), e(parts, P)
@@ -386,8 +400,8 @@ class DinoStepEngine:
             for m in ("aux_image", "aux_audio"):
                 w[f"{m}.hh"], w[f"{m}.g"], w[f"{m}.out"] = e(B, 512), e(B, 512), e(B, out)
                 w[f"{m}.d.out"], w[f"{m}.d.g"], w[f"{m}.d.hh"] = e(B, out), e(B, 512), e(B, 512)
-                w[f"{m}.hstats"] = torch.zeros(512, 2, dtype=torch.float64, device=dev)
-                w[f"{m}.hsums"] = torch.zeros(512, 2, dtype=torch.float64, device=dev)
+                w[f"{m}.hstats"] = zalloc(512, 2)
+                w[f"{m}.hsums"] = zalloc(512, 2)
                 for nm in ("hscale", "hshift", "hmean", "hinvstd"):
                     w[f"{m}.{nm}"] = e(1, 512)
             if self.mode == "infonce":
@@ -506,7 +520,8 @@ class DinoStepEngine:
             z, stats = w[f"{role}.{mod}.z{li}"], w[f"{role}.{mod}.stats{li}"]
             tc = self.tc[mod][li]
             next_tc = li + 1 < len(layers) and self.tc[mod][li + 1]
-            stats.zero_()
+            if "zarena" not in w:
+                stats.zero_()
             wrole = role if role in ("s", "t") else self._eval_wrole      # the evaluation role "e" borrows a role's weight images
             if tc and ci == 1:
                 xs8 = w[f"{mod}.xs8"]
@@ -537,7 +552,8 @@ class DinoStepEngine:
         M = x.shape[0]
         ops.linear_fwd(x, P[prefix + "mlp.0.weight"], P[prefix + "mlp.0.bias"], hh, tc=self.lin_tc)
         st = w[f"{role}.{tag}hstats"]
-        st.zero_()
+        if "zarena" not in w:
+            st.zero_()
         ops.colstats(hh, st)
         ops.bn_finalize(st, P[prefix + "mlp.1.weight"], P[prefix + "mlp.1.bias"], bn.running_mean, bn.running_var, bn.num_batches_tracked,
                         w[f"{role}.{tag}hscale"], w[f"{role}.{tag}hshift"], w[f"{role}.{tag}hmean"], w[f"{role}.{tag}hinvstd"], 1, M)
@@ -561,7 +577,8 @@ class DinoStepEngine:
         self._lin_wgrad(d_out, g, G[prefix + "mlp.4.weight"], G[prefix + "mlp.4.bias"])
         ops.linear_bwd_data(d_out, S[prefix + "mlp.4.weight"], d_g, tc=self.lin_tc)
         sums = w[f"{role}.{tag}hsums"]
-        sums.zero_()
+        if "zarena" not in w:
+            sums.zero_()
         sc, sh, mu, inv = (w[f"{role}.{tag}h{n}"] for n in ("scale", "shift", "mean", "invstd"))
         ops.bn1d_gelu_drop_bwd_reduce(hh, d_g, sc, sh, mu, inv, mask, drop_p, sums)
         ops.bn1d_gelu_drop_bwd_apply(hh, d_g, sc, sh, mu, inv, mask, drop_p, sums, d_hh)
@@ -604,7 +621,7 @@ class DinoStepEngine:
         S, G = self.S, self.G
         d_p = d_top
         BF = torch.bfloat16
-        if any(self.tc[mod]):
+        if any(self.tc[mod]) and "zarena" not in w:
             w[f"{mod}.dbsum"].zero_()
         # weight gradients (UMMA-issue bound, little HBM traffic) run on their own stream beside the data gradient and the next
         # layer's HBM-bound BatchNorm kernels; dz and the wgrad scratch are double-buffered, an event guards their reuse
@@ -617,7 +634,8 @@ class DinoStepEngine:
             tc = self.tc[mod][li]
             z = w[f"s.{mod}.z{li}"]
             sums = w[f"s.{mod}.sums{li}"]
-            sums.zero_()
+            if "zarena" not in w:
+                sums.zero_()
             sc, sh, mu, inv = (w[f"s.{mod}.{n}{li}"] for n in ("scale", "shift", "mean", "invstd"))
             if tc:
                 if d_p.dtype != BF:
@@ -765,6 +783,7 @@ class DinoStepEngine:
         multi = self.kind == "multi_central"
         xi = w["x_img"]
         xa = w["x_aud"] if multi else None
+        w["zarena"].zero_()                             # all statistics / backward-sum accumulators of this step
         packed = x_img.dtype == torch.bfloat16          # augment(direct=True): the quad8 workspace images are already filled
         w["packed"] = packed
         if packed:
