@@ -171,3 +171,19 @@ def test_trainer_shim_runs_a_toy_module(tmp_path):
     assert os.path.exists(os.path.join(tr.logger.log_dir, "metrics.csv"))
     again = Toy.load_from_checkpoint(ckpt.best_model_path)
     assert again.lr == 0.1
+
+
+def test_quad8_width_covers_every_tap_of_every_output_phase():
+    """The first-layer image has ceil((W + 2 pad) / 4) units per row: the last valid pixel group's taps kw' = ph + kw stay
+    inside its 8-pixel unit for the three first-layer geometries (host-side shape logic, no GPU)."""
+    import importlib
+    ops_src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "multimodal_ssl_avmnist_b200", "ops.py")).read()
+    ns = {}
+    start = ops_src.index("def quad8_width")
+    exec(ops_src[start:ops_src.index("\n\n\n", start)], ns)
+    for W, K, pad in ((112, 5, 2), (28, 5, 2), (28, 3, 1)):
+        wq = ns["quad8_width"](W, pad)
+        assert 4 * wq >= W + 2 * pad
+        last_group = W // 4 - 1                      # outputs 4*g .. 4*g+3
+        assert 3 + (K - 1) <= 7                      # kw' = ph + kw < 8
+        assert last_group < wq

@@ -65,6 +65,27 @@ def test_conv_tc_forward(geom, views, B):
         assert rel < 1e-5, (geom, "stats", rel)
 
 
+def test_prep_weights_multi_matches_single_launches():
+    """b200_conv_tc_prep_weights_multi (one launch over a device descriptor table) == the per-tensor launches, bit for bit,
+    for every layer shape incl. the first layers (4 phases), the phase-packed 8<->16 / 16<->32 layers and flipped images."""
+    g = torch.Generator().manual_seed(3)
+    shapes = [(8, 1, 5, False), (32, 1, 5, False), (32, 1, 3, False), (16, 8, 5, False), (16, 8, 5, True), (32, 16, 5, False),
+              (32, 16, 5, True), (64, 32, 5, False), (64, 32, 5, True), (64, 32, 3, True), (128, 64, 3, False)]
+    ws, singles, multis, rows = [], [], [], []
+    for co, ci, k, flip in shapes:
+        w = torch.randn(co, ci, k, k, generator=g).to(DEV)
+        cin, cout = (co, ci) if flip else (ci, co)
+        a = torch.zeros(ops.conv_tc_weight_bytes(cin, cout, k), dtype=torch.uint8, device=DEV)
+        b = torch.full_like(a, 0xAB)
+        ops.conv_tc_prep_weights(w, a, flip=flip)
+        ws.append(w); singles.append(a); multis.append(b)
+        rows.append([w.data_ptr(), b.data_ptr(), cin, cout, k, int(flip)])
+    ops.conv_tc_prep_weights_multi(torch.tensor(rows, dtype=torch.int64, device=DEV))
+    torch.cuda.synchronize()
+    for (co, ci, k, flip), a, b in zip(shapes, singles, multis):
+        assert torch.equal(a, b), (co, ci, k, flip)
+
+
 @pytest.mark.parametrize("geom", FWD)
 def test_conv_tc_data_gradient(geom):
     """dx of conv(x, w): the same kernel with swapped channels, pad' = K-1-pad and flipped weights."""
