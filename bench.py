@@ -309,6 +309,16 @@ def run_ours(args):
         eng.train_step(img_d, aud_d, lab_d)
         eng.prefetch_augment(img_d, aud_d)
     barrier()
+    use_graph = bool(args.graph) and world == 1
+    graph_launches = None
+    if use_graph:
+        eng._prefetch = None
+        lg = ops.launch_count()
+        eng.capture_train_step(B)               # 2 warm-up bodies + the captured one
+        graph_launches = (ops.launch_count() - lg) // 3
+        for _ in range(3):
+            eng.graph_step(img_d, aud_d, lab_d)
+        barrier()
     # ---- timed region 1: inputs resident in HBM ----
     clocks = ClockSampler(local) if rank == 0 else None
     l0 = ops.launch_count()
@@ -316,23 +326,36 @@ def run_ours(args):
     barrier()
     e0.record()
     for _ in range(args.steps):
-        loss = eng.train_step(img_d, aud_d, lab_d)
-        eng.prefetch_augment(img_d, aud_d)      # the next step's views, on the augmentation stream (input pipeline overlap)
+        if use_graph:
+            loss = eng.graph_step(img_d, aud_d, lab_d)
+        else:
+            loss = eng.train_step(img_d, aud_d, lab_d)
+            eng.prefetch_augment(img_d, aud_d)  # the next step's views, on the augmentation stream (input pipeline overlap)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
-    launches = (ops.launch_count() - l0) // args.steps
+    launches = graph_launches if use_graph else (ops.launch_count() - l0) // args.steps
     # ---- timed region 2: end to end through the host-facing call (pinned host buffers in, loss out); every step copies its
     #      batch host->device and reads its loss back; the NEXT batch's copy + augmentation are enqueued before the read-back ----
     nxt = ((img_h, aud_h) + ((lab_h,) if lab_h is not None else ())) if aud_h is not None else (img_h,)
+    def host_step():
+        if not use_graph:
+            return eng.train_step_host(img_h, aud_h, lab_h, next_batch=nxt)
+        img_d.copy_(img_h, non_blocking=True)   # H2D of this step's batch, graph replay, D2H of the loss
+        if aud_h is not None:
+            aud_d.copy_(aud_h, non_blocking=True)
+        if lab_h is not None:
+            lab_d.copy_(lab_h, non_blocking=True)
+        return float(eng.graph_step(img_d, aud_d, lab_d)[3].item())
+
     for _ in range(2):
-        eng.train_step_host(img_h, aud_h, lab_h, next_batch=nxt)
+        host_step()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     last = None
     for _ in range(args.steps):
-        last = eng.train_step_host(img_h, aud_h, lab_h, next_batch=nxt)
+        last = host_step()
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3) / args.steps
@@ -341,6 +364,8 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
+    if use_graph:
+        eng.release_graph()                     # the per-op profile below steps eagerly
     rows = profile_ops(eng, img_d, aud_d, steps=2, labels=lab_d)       # every rank runs it (the step contains collectives when N > 1)
     if rank != 0:
         if world > 1:
@@ -407,6 +432,7 @@ def run_ours(args):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": (WORKLOAD if args.mode == "default" else WORKLOAD.replace("default mode", args.mode + " mode")) if args.kind == "multi_central"
                        else "image_simple unimodal DINO step (2 global + 4 local views of 28x28 images, O=256, P=128)", "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "execution": "one CUDA graph replay per step (device-side step counters)" if use_graph else "eager launches on 6 streams",
                        "l2": "per-step working set (activations) is several GB, far larger than the 126 MB L2",
                        "precision": "bf16 tensor-core convolutions (fp16 pre-BatchNorm z, bf16 activations / gradients), fp32 accumulate, "
                                     "statistics, linears, losses, EMA, Adam"},
@@ -426,6 +452,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the whole step from one CUDA graph (single GPU; meant for small per-GPU batches, where the "
+                         "~165 host-side launches bound the step)")
     ap.add_argument("--kind", default="multi_central", choices=["multi_central", "image_simple"],
                     help="image_simple = BASELINE.json configs[0] (unimodal image DINO); the headline line is multi_central")
     ap.add_argument("--mode", default="default", choices=["default", "semi_supervised", "infonce", "mse"],

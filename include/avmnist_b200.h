@@ -126,6 +126,14 @@ int b200_aug_apply_audio(const void* src, int src_u8, const int32_t* ops, const 
  * fills img_ops/aud_ops/group_bits for B samples x (Vg+Vl) views from Philox(seed, step). */
 int b200_aug_sample(const int32_t* spec, int B, int Vg, int Vl, uint64_t seed, uint64_t step, int32_t* img_ops,
                     int32_t* aud_ops, uint32_t* group_bits, void* stream);
+/* CUDA-graph replay variants: the step counter lives in device memory (int64, advanced by b200_counters_advance inside the
+ * graph), so the captured launches need no per-step host arguments.  step_dev == NULL: identical to the plain calls.
+ * aug_sample: step + *step_dev; aug_apply_audio: noise seed (seed + *step_dev) & (2^48 - 1). */
+int b200_aug_sample_dev(const int32_t* spec, int B, int Vg, int Vl, uint64_t seed, uint64_t step, const int64_t* step_dev,
+                        int32_t* img_ops, int32_t* aud_ops, uint32_t* group_bits, void* stream);
+int b200_aug_apply_audio_dev(const void* src, int src_u8, const int32_t* ops, const uint32_t* group_bits,
+                             const float* noise, uint64_t seed, const int64_t* step_dev, float* out, void* out_quad8,
+                             int pad, int B, int V, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Encoder building blocks -- conv -> BatchNorm(train) -> ReLU -> MaxPool2 of CentralUnimodalImage/Audio
@@ -275,6 +283,9 @@ int b200_bn1d_gelu_drop_bwd_apply(const float* h, const float* dg, const float* 
                                   const double* sums, float* dh, int M, int C, void* stream);
 /* Bernoulli keep-mask from Philox(seed, offset): mask[i] = u >= p */
 int b200_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+/* offset + 4 * (*step_dev): the CUDA-graph replay variant (see b200_aug_sample_dev) */
+int b200_dropout_mask_dev(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, const int64_t* step_dev,
+                          void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Optimiser -- torch.optim.Adam(lr, weight_decay) as configured at models/dino.py:953-962, over one flat arena;
@@ -284,6 +295,13 @@ int b200_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t
 int b200_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                    float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
                    float bias_correction2_sqrt, float grad_scale, void* stream);
+/* CUDA-graph replay: bc_out[0] = 1 - beta1^t, bc_out[1] = sqrt(1 - beta2^t) for t = *step_dev + 1 (double arithmetic, rounded
+ * to fp32 like the host path); b200_adam_flat_dev reads them from device memory; b200_counters_advance adds 1 to n counters. */
+int b200_adam_bias_dev(const int64_t* step_dev, double beta1, double beta2, float* bc_out, void* stream);
+int b200_adam_flat_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, const float* bc_dev, float grad_scale,
+                       void* stream);
+int b200_counters_advance(int64_t* counters, int n, void* stream);
 /* y <- y * alpha (used to apply an upstream autograd scale / the 1/world_size of the gradient all-reduce) */
 int b200_scale_flat(float* y, int64_t n, float alpha, void* stream);
 

@@ -14,7 +14,7 @@ ABI_VERSION = 1
 _lib = None
 
 _CTYPES = {
-    "int": C.c_int, "int64_t": C.c_int64, "uint64_t": C.c_uint64, "float": C.c_float,
+    "int": C.c_int, "int64_t": C.c_int64, "uint64_t": C.c_uint64, "float": C.c_float, "double": C.c_double,
     "const char*": C.c_char_p,
 }
 

@@ -67,8 +67,10 @@ __device__ __forceinline__ float arange_f32(int k, int n, double step) {
 template <int S, int T>
 __global__ void __launch_bounds__(T) aug_apply_kernel(const void* __restrict__ src, int src_u8, const int32_t* __restrict__ ops,
                                                       const uint32_t* __restrict__ group_bits, const float* __restrict__ noise,
-                                                      uint64_t seed, float* __restrict__ out, uint4* __restrict__ out8, int pad8, int B, int V) {
+                                                      uint64_t seed, float* __restrict__ out, uint4* __restrict__ out8, int pad8, int B, int V,
+                                                      const int64_t* __restrict__ step_dev) {
     constexpr int NPIX = S * S;
+    if (step_dev != nullptr) seed = (seed + (uint64_t)__ldg(step_dev)) & 0xFFFFFFFFFFFFull;      // CUDA-graph replay: the step lives on the device
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* bufA = reinterpret_cast<float*>(smem_raw);
     float* bufB = bufA + NPIX;
@@ -388,7 +390,8 @@ __device__ int sample_chain(const int32_t* spec, int S, Draw& d, int32_t* rec /*
 constexpr int NGROUPS = 784;
 __global__ void __launch_bounds__(32) aug_sample_kernel(const int32_t* __restrict__ spec, int B, int Vg, int Vl, uint64_t seed,
                                                         uint64_t step, int32_t* __restrict__ img_ops, int32_t* __restrict__ aud_ops,
-                                                        uint32_t* __restrict__ group_bits) {
+                                                        uint32_t* __restrict__ group_bits, const int64_t* __restrict__ step_dev) {
+    if (step_dev != nullptr) step += (uint64_t)__ldg(step_dev);
     // one warp per (sample, view) record: lane 0 replays the two op chains (sequential by nature) and draws the grouped-masking
     // subset with a partial Fisher-Yates shuffle (gc draws instead of ranking 784 random keys); the warp stages and copies.
     __shared__ int32_t sspec[4 * B200_AUG_MAX_OPS * 8];
@@ -442,12 +445,18 @@ int b200_aug_apply_image(const void* src, int src_u8, const int32_t* ops, float*
     B200_REQUIRE((((uintptr_t)src | (uintptr_t)out | (uintptr_t)out_quad8) & 15) == 0, B200_E_ARG, "aug_apply_image: pointers must be 16-byte aligned");
     constexpr int S = 28, T = 128;
     const size_t smem = 2 * S * S * sizeof(float) + 2 * S * sizeof(AATable);
-    aug_apply_kernel<S, T><<<B * V, T, smem, as_stream(stream)>>>(src, src_u8, ops, nullptr, nullptr, 0, out, reinterpret_cast<uint4*>(out_quad8), pad, B, V);
+    aug_apply_kernel<S, T><<<B * V, T, smem, as_stream(stream)>>>(src, src_u8, ops, nullptr, nullptr, 0, out, reinterpret_cast<uint4*>(out_quad8), pad, B, V,
+                                                                  nullptr);
     return launch_status("aug_apply_image");
 }
 
 int b200_aug_apply_audio(const void* src, int src_u8, const int32_t* ops, const uint32_t* group_bits, const float* noise,
                          uint64_t seed, float* out, void* out_quad8, int pad, int B, int V, void* stream) {
+    return b200_aug_apply_audio_dev(src, src_u8, ops, group_bits, noise, seed, nullptr, out, out_quad8, pad, B, V, stream);
+}
+
+int b200_aug_apply_audio_dev(const void* src, int src_u8, const int32_t* ops, const uint32_t* group_bits, const float* noise,
+                             uint64_t seed, const int64_t* step_dev, float* out, void* out_quad8, int pad, int B, int V, void* stream) {
     B200_REQUIRE(src && ops && group_bits && (out || out_quad8) && B > 0 && V > 0 && pad >= 0, B200_E_ARG, "aug_apply_audio: bad arguments");
     B200_REQUIRE((((uintptr_t)src | (uintptr_t)out | (uintptr_t)out_quad8) & 15) == 0, B200_E_ARG, "aug_apply_audio: pointers must be 16-byte aligned");
     constexpr int S = 112, T = 512;
@@ -458,15 +467,21 @@ int b200_aug_apply_audio(const void* src, int src_u8, const int32_t* ops, const 
         B200_REQUIRE(e == cudaSuccess, B200_E_SMEM, "aug_apply_audio: cannot reserve %zu B of shared memory", smem);
         attr_done = true;
     }
-    aug_apply_kernel<S, T><<<B * V, T, smem, as_stream(stream)>>>(src, src_u8, ops, group_bits, noise, seed, out, reinterpret_cast<uint4*>(out_quad8), pad, B, V);
+    aug_apply_kernel<S, T><<<B * V, T, smem, as_stream(stream)>>>(src, src_u8, ops, group_bits, noise, seed, out, reinterpret_cast<uint4*>(out_quad8), pad, B, V,
+                                                                  step_dev);
     return launch_status("aug_apply_audio");
 }
 
 int b200_aug_sample(const int32_t* spec, int B, int Vg, int Vl, uint64_t seed, uint64_t step, int32_t* img_ops,
                     int32_t* aud_ops, uint32_t* group_bits, void* stream) {
+    return b200_aug_sample_dev(spec, B, Vg, Vl, seed, step, nullptr, img_ops, aud_ops, group_bits, stream);
+}
+
+int b200_aug_sample_dev(const int32_t* spec, int B, int Vg, int Vl, uint64_t seed, uint64_t step, const int64_t* step_dev, int32_t* img_ops,
+                        int32_t* aud_ops, uint32_t* group_bits, void* stream) {
     B200_REQUIRE(spec && img_ops && aud_ops && group_bits && B > 0 && Vg >= 0 && Vl >= 0 && Vg + Vl > 0, B200_E_ARG,
                  "aug_sample: bad arguments");
-    aug_sample_kernel<<<B * (Vg + Vl), 32, 0, as_stream(stream)>>>(spec, B, Vg, Vl, seed, step, img_ops, aud_ops, group_bits);
+    aug_sample_kernel<<<B * (Vg + Vl), 32, 0, as_stream(stream)>>>(spec, B, Vg, Vl, seed, step, img_ops, aud_ops, group_bits, step_dev);
     return launch_status("aug_sample");
 }
 

@@ -91,8 +91,12 @@ __global__ void __launch_bounds__(256) ema_multi_kernel(float* const* __restrict
 __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
                                                         float b1, float b2, float eps, float wd, float bc1, float bc2s,
-                                                        float gs) {
+                                                        float gs, const float* __restrict__ bc_dev) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (bc_dev != nullptr) {          // CUDA-graph replay: the bias corrections of this step were computed on the device
+        bc1 = __ldg(bc_dev);
+        bc2s = __ldg(bc_dev + 1);
+    }
     const float step = lr / bc1;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float pi = p[i];
@@ -111,8 +115,20 @@ __global__ void __launch_bounds__(256) scale_flat_kernel(float* __restrict__ y, 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] *= a;
 }
 
+// bias corrections of Adam step t = *step_dev + 1, in double like the host path (1 - beta^t, sqrt(1 - beta2^t)), rounded to fp32
+__global__ void adam_bias_kernel(const int64_t* __restrict__ step_dev, double b1, double b2, float* __restrict__ out) {
+    const double t = (double)(*step_dev + 1);
+    out[0] = (float)(1.0 - pow(b1, t));
+    out[1] = (float)sqrt(1.0 - pow(b2, t));
+}
+
+__global__ void counters_advance_kernel(int64_t* __restrict__ ctr, int n) {
+    if ((int)threadIdx.x < n) ctr[threadIdx.x] += 1;
+}
+
 __global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float p, uint64_t seed,
-                                                           uint64_t offset) {
+                                                           uint64_t offset, const int64_t* __restrict__ step_dev) {
+    if (step_dev != nullptr) offset += 4ull * (uint64_t)__ldg(step_dev);      // the engine's offsets are 4*step + k
     Philox rng(seed);
     const int64_t n4 = (n + 3) >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -171,8 +187,28 @@ int b200_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_a
     B200_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0, B200_E_ARG, "adam_flat: null pointer or n <= 0");
     adam_flat_kernel<<<flat_grid(n, 4), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                      eps, weight_decay, bias_correction1,
-                                                                     bias_correction2_sqrt, grad_scale);
+                                                                     bias_correction2_sqrt, grad_scale, nullptr);
     return launch_status("adam_flat");
+}
+
+int b200_adam_bias_dev(const int64_t* step_dev, double beta1, double beta2, float* bc_out, void* stream) {
+    B200_REQUIRE(step_dev && bc_out, B200_E_ARG, "adam_bias_dev: null pointer");
+    adam_bias_kernel<<<1, 1, 0, as_stream(stream)>>>(step_dev, beta1, beta2, bc_out);
+    return launch_status("adam_bias_dev");
+}
+
+int b200_adam_flat_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, const float* bc_dev, float grad_scale, void* stream) {
+    B200_REQUIRE(param && grad && exp_avg && exp_avg_sq && bc_dev && n > 0, B200_E_ARG, "adam_flat_dev: null pointer or n <= 0");
+    adam_flat_kernel<<<flat_grid(n, 4), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                     eps, weight_decay, 1.f, 1.f, grad_scale, bc_dev);
+    return launch_status("adam_flat_dev");
+}
+
+int b200_counters_advance(int64_t* counters, int n, void* stream) {
+    B200_REQUIRE(counters && n > 0 && n <= 32, B200_E_ARG, "counters_advance: bad arguments");
+    counters_advance_kernel<<<1, 32, 0, as_stream(stream)>>>(counters, n);
+    return launch_status("counters_advance");
 }
 
 int b200_scale_flat(float* y, int64_t n, float alpha, void* stream) {
@@ -182,8 +218,12 @@ int b200_scale_flat(float* y, int64_t n, float alpha, void* stream) {
 }
 
 int b200_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
+    return b200_dropout_mask_dev(mask, n, p, seed, offset, nullptr, stream);
+}
+
+int b200_dropout_mask_dev(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, const int64_t* step_dev, void* stream) {
     B200_REQUIRE(mask && n > 0 && p >= 0.f && p < 1.f, B200_E_ARG, "dropout_mask: bad arguments");
-    dropout_mask_kernel<<<flat_grid((n + 3) / 4, 4), 256, 0, as_stream(stream)>>>(mask, n, p, seed, offset);
+    dropout_mask_kernel<<<flat_grid((n + 3) / 4, 4), 256, 0, as_stream(stream)>>>(mask, n, p, seed, offset, step_dev);
     return launch_status("dropout_mask");
 }
 

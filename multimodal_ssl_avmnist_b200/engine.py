@@ -167,6 +167,9 @@ class DinoStepEngine:
         self.world = dp.world_size(process_group) if (data_parallel is None or data_parallel) else 1
         self.step_count = 0          # optimizer steps taken (Adam bias correction)
         self.rng_step = 0            # augmentation / dropout stream position
+        self._ctr = None             # CUDA-graph mode: device counters int64 [rng_step, adam step] read by the kernels
+        self._bc = None              #   ... and Adam's two bias corrections of the current step (device, fp32)
+        self._graph = None
 
         if kind == "multi_central":
             used, unused = central_encoder_params(self.E, self.O)
@@ -461,8 +464,14 @@ class DinoStepEngine:
         audios [B,112,112] (uint8 or fp32).  Returns view-major tensors ([V,B,28,28], [V,B,112,112])."""
         B = images.shape[0]
         w = self._workspace(B)
-        ops.aug_sample(self.aug_spec, B, self.Vg, self.Vl, self.seed, self.rng_step, w["img_ops"], w["aud_ops"], w["group_bits"])
+        step, step_dev = self._step_args()
+        ops.aug_sample(self.aug_spec, B, self.Vg, self.Vl, self.seed, step, w["img_ops"], w["aud_ops"], w["group_bits"], step_dev=step_dev)
         return self.augment_with_params(images, audios, w["img_ops"], w["aud_ops"], w["group_bits"], None, direct=direct)
+
+    def _step_args(self):
+        """(host step value, device step counter) for the kernels that consume the RNG stream position: eager mode passes the
+        host counter, CUDA-graph mode 0 + a pointer to the device counter (identical streams either way)."""
+        return (0, self._ctr[0:1]) if self._ctr is not None else (self.rng_step, None)
 
     def augment_with_params(self, images, audios, img_ops, aud_ops, group_bits, noise, direct=False):
         """Applies the op records.  direct=False: fp32 views ([V,B,28,28], [V,B,112,112]).  direct=True (tensor-core path
@@ -471,7 +480,8 @@ class DinoStepEngine:
         B = images.shape[0]
         w = self._workspace(B)
         V = self.V
-        seed = (self.seed * 1000003 + self.rng_step) & 0xFFFFFFFFFFFF
+        step, step_dev = self._step_args()
+        seed = (self.seed * 1000003 + step) & 0xFFFFFFFFFFFF
         if direct and self.tc["img"][0] and (not self.aud_layers or self.tc["aud"][0]):
             pi = self.img_layers[0][6]
             xi = w["img.xs8"][:V * B].view(V, B, 28, ops.quad8_width(28, pi), 8)
@@ -480,14 +490,15 @@ class DinoStepEngine:
             if self.aud_layers and audios is not None:
                 pa = self.aud_layers[0][6]
                 xa = w["aud.xs8"][:V * B].view(V, B, 112, ops.quad8_width(112, pa), 8)
-                ops.aug_apply_audio(audios.reshape(B, 112, 112), aud_ops, group_bits, None, noise=noise, seed=seed, out8=xa, pad=pa)
+                ops.aug_apply_audio(audios.reshape(B, 112, 112), aud_ops, group_bits, None, noise=noise, seed=seed, out8=xa, pad=pa,
+                                    step_dev=step_dev)
             return xi, xa
         xi = w["x_img"][:V * B].view(V, B, 28, 28)
         ops.aug_apply_image(images.reshape(B, 28, 28), img_ops, xi)
         xa = None
         if self.aud_layers and audios is not None:
             xa = w["x_aud"][:V * B].view(V, B, 112, 112)
-            ops.aug_apply_audio(audios.reshape(B, 112, 112), aud_ops, group_bits, xa, noise=noise, seed=seed)
+            ops.aug_apply_audio(audios.reshape(B, 112, 112), aud_ops, group_bits, xa, noise=noise, seed=seed, step_dev=step_dev)
         return xi, xa
 
     # ------------------------------------------------------------------------------------------------------
@@ -806,12 +817,13 @@ class DinoStepEngine:
                 w["t.fmask"].copy_(masks["teacher_fusion"].reshape(Nt, E))
             w["s.hmask"].copy_(masks["student_head"].reshape(Nv, 512))
         else:
-            base = self.rng_step * 4
+            step, step_dev = self._step_args()
+            base = step * 4
             if multi:
-                ops.dropout_mask(w["s.fmask"], self.fusion_dropout, self.seed + 1, base)
-                ops.dropout_mask(w["t.fmask"], self.fusion_dropout, self.seed + 1, base + 1)
+                ops.dropout_mask(w["s.fmask"], self.fusion_dropout, self.seed + 1, base, step_dev=step_dev)
+                ops.dropout_mask(w["t.fmask"], self.fusion_dropout, self.seed + 1, base + 1, step_dev=step_dev)
             if self.dropout > 0:
-                ops.dropout_mask(w["s.hmask"], self.dropout, self.seed + 1, base + 2)
+                ops.dropout_mask(w["s.hmask"], self.dropout, self.seed + 1, base + 2, step_dev=step_dev)
         if self._tcw:
             self._prep_tc_weights("s", S)
             self._prep_tc_weights("t", T)
@@ -967,12 +979,16 @@ class DinoStepEngine:
         self.step_count += 1
         gs = self._grad_scale if grad_scale is None else grad_scale
         n = self.n_trainable_prefix
-        ops.adam_flat(self.student.flat[:n], self.grad[:n], self.exp_avg[:n], self.exp_avg_sq[:n], self.step_count, self.lr,
-                      weight_decay=self.weight_decay, grad_scale=gs)
-        if self.aux_range is not None:
-            lo, hi = self.aux_range
-            ops.adam_flat(self.student.flat[lo:hi], self.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.step_count,
-                          self.lr, weight_decay=self.weight_decay, grad_scale=gs)
+        ranges = [(0, n)] + ([self.aux_range] if self.aux_range is not None else [])
+        if self._ctr is not None:       # CUDA-graph mode: the step number and its bias corrections live on the device
+            ops.adam_bias_dev(self._ctr[1:2], self._bc)
+        for lo, hi in ranges:
+            if self._ctr is not None:
+                ops.adam_flat_dev(self.student.flat[lo:hi], self.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self._bc, self.lr,
+                                  weight_decay=self.weight_decay, grad_scale=gs)
+            else:
+                ops.adam_flat(self.student.flat[lo:hi], self.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.step_count,
+                              self.lr, weight_decay=self.weight_decay, grad_scale=gs)
 
     def train_step_views(self, x_img, x_aud, masks=None, raw=None, labels=None):
         """Reference step order on given views: forward/loss/backward, EMA (before the optimizer, dino.py:871), Adam."""
@@ -980,6 +996,8 @@ class DinoStepEngine:
         self.update_teacher()
         self.optimizer_step()
         self.rng_step += 1
+        if self._ctr is not None:
+            ops.counters_advance(self._ctr)
         return loss
 
     def train_step(self, images, audios=None, labels=None):
@@ -996,6 +1014,83 @@ class DinoStepEngine:
         self._step_done_prev, self._step_done = self._step_done, torch.cuda.Event()
         self._step_done.record()
         return loss
+
+    # ------------------------------------------------------------------------------------------------------
+    # CUDA-graph replay of the whole step (small per-GPU batches are bound by the ~165 host-side launches)
+    # ------------------------------------------------------------------------------------------------------
+    def _state_tensors(self):
+        ts = [self.student.flat, self.teacher.flat, self.exp_avg, self.exp_avg_sq, self.center]
+        for table in (self.bn_s, self.bn_t):
+            for bn in table.values():
+                ts += [bn.running_mean, bn.running_var, bn.num_batches_tracked]
+        return ts
+
+    def capture_train_step(self, B, image_dtype=torch.float32, audio_dtype=torch.uint8):
+        """Captures train_step (sampling, augmentation, forward, losses, EMA, backward, Adam, all side streams) for per-GPU batch
+        B into ONE CUDA graph.  The per-step scalars (RNG stream position, Adam step) move to device counters that the graph
+        advances itself, so a replay needs no host arguments and reproduces the eager step bit for bit.  Single GPU; lr /
+        temperatures are baked in (re-capture after changing them).  Use graph_step() afterwards."""
+        if self.world > 1:
+            raise ops._lib.B200Error("capture_train_step: the data-parallel exchange is not captured; use train_step")
+        dev = self.device
+        g = {"B": B, "img": torch.zeros(B, 28, 28, dtype=image_dtype, device=dev)}
+        if self.aud_layers:
+            g["aud"] = torch.zeros(B, 112, 112, dtype=audio_dtype, device=dev)
+        if self.mode == "semi_supervised":
+            g["lab"] = torch.zeros(B, dtype=torch.int64, device=dev)
+        self._prefetch = None
+        state = self._state_tensors()
+        snap = [t.clone() for t in state]
+        host = (self.rng_step, self.step_count)
+        self._ctr = torch.tensor(host, dtype=torch.int64, device=dev)
+        self._bc = torch.zeros(2, device=dev)
+
+        def body():
+            return self.train_step(g["img"], g.get("aud"), g.get("lab"))
+
+        def restore():
+            for t, c in zip(state, snap):
+                t.copy_(c)
+            self.rng_step, self.step_count = host
+            self._ctr.copy_(torch.tensor(host, dtype=torch.int64))
+            self._step_done = self._step_done_prev = None
+
+        side = torch.cuda.Stream(device=dev)       # warm-up off the capture stream: workspaces, scratch, one-time attributes
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        restore()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            g["loss"] = body()
+        restore()
+        torch.cuda.synchronize()
+        g["graph"] = graph
+        self._graph = g
+        return g
+
+    def graph_step(self, images, audios=None, labels=None):
+        """One training step by replaying the captured graph on a raw device batch; returns the device loss tensor [4]."""
+        g = self._graph
+        if g is None or images.shape[0] != g["B"]:
+            raise ops._lib.B200Error("graph_step: call capture_train_step(B) for this batch size first")
+        g["img"].copy_(images.reshape(g["img"].shape))
+        if "aud" in g:
+            g["aud"].copy_(audios.reshape(g["aud"].shape))
+        if "lab" in g:
+            g["lab"].copy_(labels)
+        g["graph"].replay()
+        self.rng_step += 1
+        self.step_count += 1
+        return g["loss"]
+
+    def release_graph(self):
+        """Back to eager stepping (the host counters are authoritative again)."""
+        self._graph = None
+        self._ctr = self._bc = None
 
     def train_step_host(self, images_host, audios_host=None, labels_host=None, next_batch=None):
         """The host-facing call: raw batch in (pinned) host memory -> H2D copies -> whole step -> the total loss as a Python

@@ -83,8 +83,23 @@ def scale_flat(y, alpha):
     _lib.check(_lib_().b200_scale_flat(_ptr(y, F32), y.numel(), alpha, _stream()), "scale_flat")
 
 
-def dropout_mask(mask, p, seed, offset):
-    _lib.check(_lib_().b200_dropout_mask(_ptr(mask, U8), mask.numel(), p, seed, offset, _stream()), "dropout_mask")
+def dropout_mask(mask, p, seed, offset, step_dev=None):
+    """step_dev (int64 device scalar, CUDA-graph replay): the Philox offset becomes offset + 4 * *step_dev"""
+    _lib.check(_lib_().b200_dropout_mask_dev(_ptr(mask, U8), mask.numel(), p, seed, offset, _ptr(step_dev, I64), _stream()), "dropout_mask")
+
+
+def adam_bias_dev(step_dev, bc_out, beta1=0.9, beta2=0.999):
+    """bc_out[0:2] = (1 - beta1^t, sqrt(1 - beta2^t)) for t = *step_dev + 1, computed on the device (CUDA-graph replay)"""
+    _lib.check(_lib_().b200_adam_bias_dev(_ptr(step_dev, I64), beta1, beta2, _ptr(bc_out, F32), _stream()), "adam_bias_dev")
+
+
+def adam_flat_dev(param, grad, exp_avg, exp_avg_sq, bc_dev, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    _lib.check(_lib_().b200_adam_flat_dev(_ptr(param, F32), _ptr(grad, F32), _ptr(exp_avg, F32), _ptr(exp_avg_sq, F32), param.numel(),
+                                          lr, beta1, beta2, eps, weight_decay, _ptr(bc_dev, F32), grad_scale, _stream()), "adam_flat")
+
+
+def counters_advance(counters):
+    _lib.check(_lib_().b200_counters_advance(_ptr(counters, I64), counters.numel(), _stream()), "counters_advance")
 
 
 # ---- losses ------------------------------------------------------------------------------------------------
@@ -160,15 +175,17 @@ def aug_apply_image(src, ops, out, out8=None, pad=0):
                "aug_apply_image")
 
 
-def aug_apply_audio(src, ops, group_bits, out, noise=None, seed=0, out8=None, pad=0):
+def aug_apply_audio(src, ops, group_bits, out, noise=None, seed=0, out8=None, pad=0, step_dev=None):
+    """step_dev (int64 device scalar, CUDA-graph replay): the noise seed becomes (seed + *step_dev) mod 2^48"""
     V, B, po, p8 = _aug_outs(out, out8, pad)
-    _lib.check(_lib_().b200_aug_apply_audio(_ptr(src), 1 if src.dtype == U8 else 0, _ptr(ops, I32), _ptr(group_bits, I32),
-                                            _ptr(noise, F32), seed, po, p8, pad, B, V, _stream()), "aug_apply_audio")
+    _lib.check(_lib_().b200_aug_apply_audio_dev(_ptr(src), 1 if src.dtype == U8 else 0, _ptr(ops, I32), _ptr(group_bits, I32),
+                                                _ptr(noise, F32), seed, _ptr(step_dev, I64), po, p8, pad, B, V, _stream()), "aug_apply_audio")
 
 
-def aug_sample(spec, B, Vg, Vl, seed, step, img_ops, aud_ops, group_bits):
-    _lib.check(_lib_().b200_aug_sample(_ptr(spec, I32), B, Vg, Vl, seed, step, _ptr(img_ops, I32), _ptr(aud_ops, I32),
-                                       _ptr(group_bits, I32), _stream()), "aug_sample")
+def aug_sample(spec, B, Vg, Vl, seed, step, img_ops, aud_ops, group_bits, step_dev=None):
+    """step_dev (int64 device scalar, CUDA-graph replay): the Philox stream position is step + *step_dev"""
+    _lib.check(_lib_().b200_aug_sample_dev(_ptr(spec, I32), B, Vg, Vl, seed, step, _ptr(step_dev, I64), _ptr(img_ops, I32),
+                                           _ptr(aud_ops, I32), _ptr(group_bits, I32), _stream()), "aug_sample")
 
 
 # ---- encoder blocks ----------------------------------------------------------------------------------------

@@ -276,3 +276,43 @@ def test_prefetched_augmentation_is_identical_to_inline():
         runs.append((torch.stack(losses).cpu(), eng.student.flat.clone().cpu()))
     assert torch.allclose(runs[0][0], runs[1][0], rtol=1e-5, atol=1e-6), (runs[0][0], runs[1][0])
     assert float((runs[0][1] - runs[1][1]).abs().max()) < 5e-4
+
+
+@pytest.mark.parametrize("mode", ["default", "mse"])
+def test_cuda_graph_replay_reproduces_the_eager_step_bit_for_bit(mode):
+    """capture_train_step / graph_step: the whole step (sampling, augmentation, forward, losses, EMA, backward, Adam, side
+    streams) replayed from ONE CUDA graph, with the RNG position and the Adam step read from device counters.  Same seed, same
+    raw batches: parameters, teacher, Adam moments, BatchNorm buffers and losses equal the eager engine's exactly."""
+    B = 8
+    g = torch.Generator().manual_seed(77)
+    batches = [(torch.rand(B, 28, 28, generator=g).to(DEV), torch.randint(0, 256, (B, 112, 112), dtype=torch.uint8, generator=g).to(DEV))
+               for _ in range(4)]
+    engs = [DinoStepEngine(kind="multi_central", mode=mode, device=DEV, precision="bf16", seed=11) for _ in range(2)]
+    engs[1].student.flat.copy_(engs[0].student.flat)
+    engs[1].sync_teacher()
+    engs[0].sync_teacher()
+    eager, graph = engs
+    # one eager step on both first, so that the capture starts from a non-trivial state (step counters 1, Adam moments set)
+    l_e = [eager.train_step(*batches[0]).clone()]
+    l_g = [graph.train_step(*batches[0]).clone()]
+    graph.capture_train_step(B)
+    assert graph.rng_step == 1 and graph.step_count == 1          # capture (and its warm-up) left the state untouched
+    assert torch.equal(graph.student.flat, eager.student.flat)
+    for img, aud in batches[1:]:
+        l_e.append(eager.train_step(img, aud).clone())
+        l_g.append(graph.graph_step(img, aud).clone())
+    torch.cuda.synchronize()
+    for a, b in zip(l_e, l_g):
+        # (the alignment-loss VALUE is a float atomic sum over CTAs: last-bit run-to-run differences, eager or not)
+        assert torch.equal(a, b) if mode == "default" else torch.allclose(a, b, rtol=1e-6, atol=0), (a, b)
+    exact = {n: torch.equal(x, y) for n, x, y in (("student", graph.student.flat, eager.student.flat), ("teacher", graph.teacher.flat, eager.teacher.flat),
+                                                  ("adam v", graph.exp_avg_sq, eager.exp_avg_sq), ("centre", graph.center, eager.center))}
+    assert all(exact.values()), exact
+    assert graph.rng_step == eager.rng_step == 4 and graph.step_count == 4
+    # and back to eager stepping
+    graph.release_graph()
+    a = eager.train_step(*batches[0]).clone()
+    b = graph.train_step(*batches[0]).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) if mode == "default" else torch.allclose(a, b, rtol=1e-6, atol=0)
+    assert torch.equal(graph.student.flat, eager.student.flat)
