@@ -85,6 +85,10 @@ struct TcCfg {
     // the taps kw' = ph + kw < 8 of the four output phases -- only that one plane exists (no other phase planes to load)
     static constexpr int XPH = CIN_ == 1 ? 4 : xph_for(CIN_, COUT_, KS_);       // output x phases packed into N
     static constexpr int XPL = CIN_ == 1 ? 1 : XPH;             // phase planes of the input slab in shared memory
+    // accumulator column order: (channel octet, x phase, channel in octet) -- a 16-column chunk then holds two ADJACENT output
+    // pixels of one octet (XPH even), i.e. 32 contiguous bytes of the act8 output: one 256-bit store
+    __host__ __device__ static constexpr int col_phase(int col) { return (col / 8) % XPH; }
+    __host__ __device__ static constexpr int col_channel(int col) { return (col / 8) / XPH * 8 + col % 8; }   // within this CTA's slice
     static constexpr int NPADL = XPH == 1 ? NPAD_ / NSPLIT_ : round_up(XPH * COUT_, 16), COUTL = COUT_ / NSPLIT_;
     static_assert(NSPLIT_ == 1 || (XPH == 1 && COUT_ == NPAD_ && NPADL % 16 == 0), "N split needs C_out == NPAD and 16-channel slices");
     static constexpr int CIN = CIN_, COUT = COUT_, NPAD = NPAD_, HIN = HIN_, WIN = WIN_, KS = KS_, PAD = PAD_, BANDS = BANDS_, SLOTS = SLOTS_;
@@ -167,8 +171,8 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
         }
         uint4* z = reinterpret_cast<uint4*>(img_s);
         for (int i = threadIdx.x; i < C::IMG_BYTES / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
-        for (int i = threadIdx.x; i < C::NPADL; i += blockDim.x)     // column (phase, channel): the bias repeats per phase
-            bias_s[i] = (bias != nullptr && i < C::XPH * C::COUTL) ? bias[blockIdx.z * C::COUTL + i % C::COUTL] : 0.f;
+        for (int i = threadIdx.x; i < C::NPADL; i += blockDim.x)     // column (octet, phase, channel): the bias repeats per phase
+            bias_s[i] = (bias != nullptr && i < C::XPH * C::COUTL) ? bias[blockIdx.z * C::COUTL + C::col_channel(i)] : 0.f;
         fence_proxy_async_smem();
     }
     if (warp == 0 && lane == 0) {
@@ -296,7 +300,7 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
                     float f[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int col = cc * 16 + j, ch = col % C::COUTL;
+                        const int col = cc * 16 + j, ch = C::col_channel(col);
                         f[j] = __uint_as_float(v[j]) + bias_s[col];
                         if (col < C::XPH * C::COUTL && valid) {
                             s1[ch] += f[j];
@@ -305,33 +309,45 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
                     }
                     if (valid) {
                         if (out_bf16) {
+                            uint4 pk[2];
 #pragma unroll
                             for (int o = 0; o < 2; ++o) {
-                                const int col0 = cc * 16 + o * 8, ph = col0 / C::COUTL, oct = (col0 % C::COUTL) / 8;
-                                if (ph < C::XPH) {
-                                    uint4 pk;
-                                    if (out_bf16 == 2) {
-                                        pk.x = pack_f16(f[o * 8 + 0], f[o * 8 + 1]);
-                                        pk.y = pack_f16(f[o * 8 + 2], f[o * 8 + 3]);
-                                        pk.z = pack_f16(f[o * 8 + 4], f[o * 8 + 5]);
-                                        pk.w = pack_f16(f[o * 8 + 6], f[o * 8 + 7]);
-                                    } else {
-                                        pk.x = pack_bf16(f[o * 8 + 0], f[o * 8 + 1]);
-                                        pk.y = pack_bf16(f[o * 8 + 2], f[o * 8 + 3]);
-                                        pk.z = pack_bf16(f[o * 8 + 4], f[o * 8 + 5]);
-                                        pk.w = pack_bf16(f[o * 8 + 6], f[o * 8 + 7]);
+                                if (out_bf16 == 2) {
+                                    pk[o].x = pack_f16(f[o * 8 + 0], f[o * 8 + 1]);
+                                    pk[o].y = pack_f16(f[o * 8 + 2], f[o * 8 + 3]);
+                                    pk[o].z = pack_f16(f[o * 8 + 4], f[o * 8 + 5]);
+                                    pk[o].w = pack_f16(f[o * 8 + 6], f[o * 8 + 7]);
+                                } else {
+                                    pk[o].x = pack_bf16(f[o * 8 + 0], f[o * 8 + 1]);
+                                    pk[o].y = pack_bf16(f[o * 8 + 2], f[o * 8 + 3]);
+                                    pk[o].z = pack_bf16(f[o * 8 + 4], f[o * 8 + 5]);
+                                    pk[o].w = pack_bf16(f[o * 8 + 6], f[o * 8 + 7]);
+                                }
+                            }
+                            const int col0 = cc * 16, ph0 = C::col_phase(col0), oct0 = C::col_channel(col0) / 8;
+                            if constexpr (C::XPH % 2 == 0) {
+                                // the chunk = pixels (ph0, ph0 + 1) of octet oct0: 32 contiguous, 32-byte aligned bytes
+                                if (col0 < C::XPH * C::COUTL) {
+                                    uint4* dst = reinterpret_cast<uint4*>(out) + (((long)n * (C::COUT / 8) + co0 / 8 + oct0) * C::HO + yy) * C::WO +
+                                                 xq * C::XPH + ph0;
+                                    st_global_256(dst, pk[0], pk[1]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int o = 0; o < 2; ++o) {        // XPH == 1: two octets of the same pixel
+                                    const int oct = oct0 + o;
+                                    if (oct * 8 < C::COUTL) {
+                                        uint4* dst = reinterpret_cast<uint4*>(out) + (((long)n * (C::COUT / 8) + co0 / 8 + oct) * C::HO + yy) * C::WO + xq;
+                                        *dst = pk[o];
                                     }
-                                    uint4* dst = reinterpret_cast<uint4*>(out) + (((long)n * (C::COUT / 8) + co0 / 8 + oct) * C::HO + yy) * C::WO +
-                                                 xq * C::XPH + ph;
-                                    *dst = pk;
                                 }
                             }
                         } else {
                             float* dst = reinterpret_cast<float*>(out) + (((long)n * C::COUT + co0) * C::HO + yy) * C::WO + xq * C::XPH;
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
-                                const int col = cc * 16 + j, ph = col / C::COUTL, ch = col % C::COUTL;
-                                if (ph < C::XPH) dst[(long)ch * C::HO * C::WO + ph] = f[j];
+                                const int col = cc * 16 + j, ph = C::col_phase(col), ch = C::col_channel(col);
+                                if (col < C::XPH * C::COUTL) dst[(long)ch * C::HO * C::WO + ph] = f[j];
                             }
                         }
                     }
@@ -364,7 +380,7 @@ __device__ __forceinline__ void conv_tc_prep_element(const float* __restrict__ w
                                                      int KS, int XPH, int flip, int e) {
     const int k8 = e & 7, r = (e >> 3) & 7, NG = NPAD / 8;
     const int ng = (e >> 6) % NG, c = (e / (64 * NG)) & 1, m = e / (128 * NG);
-    const int col = ng * 8 + r, ph = col / COUT, co = col % COUT;      // accumulator column = (x phase, output channel)
+    const int ph = ng % XPH, co = ng / XPH * 8 + r;                     // accumulator column = (channel octet, x phase, channel in octet)
     const int KWX = KS + XPH - 1;
     int kh, kw, ci;
     if (CIN == 1) {                 // quad8 first layer: chunk c of MMA m is image row kh = 2m + c, k8 is the tap kw' = ph + kw
@@ -372,7 +388,7 @@ __device__ __forceinline__ void conv_tc_prep_element(const float* __restrict__ w
         kw = k8 - ph;
         ci = 0;
         float v1 = 0.f;
-        if (kh < KS && kw >= 0 && kw < KS && ph < XPH) v1 = w[(co * KS + kh) * KS + kw];
+        if (kh < KS && kw >= 0 && kw < KS && co < COUT) v1 = w[(co * KS + kh) * KS + kw];
         out[e] = __float2bfloat16_rn(v1);
         return;
     } else if (CIN == 8) {
@@ -387,7 +403,7 @@ __device__ __forceinline__ void conv_tc_prep_element(const float* __restrict__ w
         ci = (2 * (m % PH) + c) * 8 + k8;
     }
     float v = 0.f;
-    if (kw >= 0 && kw < KS && ph < XPH) {
+    if (kw >= 0 && kw < KS && co < COUT) {
         v = flip ? w[((ci * COUT + co) * KS + (KS - 1 - kh)) * KS + (KS - 1 - kw)] : w[((co * CIN + ci) * KS + kh) * KS + kw];
     }
     out[e] = __float2bfloat16_rn(v);
