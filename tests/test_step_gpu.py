@@ -304,7 +304,7 @@ def test_cuda_graph_replay_reproduces_the_eager_step_bit_for_bit(mode):
     torch.cuda.synchronize()
     for a, b in zip(l_e, l_g):
         # (the alignment-loss VALUE is a float atomic sum over CTAs: last-bit run-to-run differences, eager or not)
-        assert torch.equal(a, b) if mode == "default" else torch.allclose(a, b, rtol=1e-6, atol=0), (a, b)
+        assert torch.equal(a, b) if mode == "default" else torch.allclose(a, b, rtol=1e-5, atol=1e-7), (a, b)
     exact = {n: torch.equal(x, y) for n, x, y in (("student", graph.student.flat, eager.student.flat), ("teacher", graph.teacher.flat, eager.teacher.flat),
                                                   ("adam v", graph.exp_avg_sq, eager.exp_avg_sq), ("centre", graph.center, eager.center))}
     assert all(exact.values()), exact
@@ -314,5 +314,5 @@ def test_cuda_graph_replay_reproduces_the_eager_step_bit_for_bit(mode):
     a = eager.train_step(*batches[0]).clone()
     b = graph.train_step(*batches[0]).clone()
     torch.cuda.synchronize()
-    assert torch.equal(a, b) if mode == "default" else torch.allclose(a, b, rtol=1e-6, atol=0)
+    assert torch.equal(a, b) if mode == "default" else torch.allclose(a, b, rtol=1e-5, atol=1e-7)
     assert torch.equal(graph.student.flat, eager.student.flat)
