@@ -976,7 +976,7 @@ template <int COUT_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOT
 struct L0FCfg {
     static constexpr int COUT = COUT_, HIN = HIN_, WIN = WIN_, KS = KS_, PAD = PAD_, BANDS = BANDS_, SLOTS = SLOTS_, CTAS = CTAS_;
     static constexpr bool STAGED = STAGED_;
-    static constexpr int TW = STAGED ? 8 : 4;                                    // transform warps
+    static constexpr int TW = (STAGED && CTAS_ == 1) ? 8 : 4;                    // transform warps
     static constexpr int THREADS = 32 * (1 + L0F_ISS + TW);
     static constexpr int P_OUT = COUT / 8, NTOT = 4 * COUT;
     static constexpr int WP = WIN + 2 * PAD, WQ = (WP + 3) / 4;                  // quad8 units per row
@@ -1398,7 +1398,7 @@ static int wgrad_tc_dispatch(const void* x, const void* dz, float* dw, float* wo
 
 // fused first-layer backward (Cin = 1): geometries of the first layers of the three encoders
 //                    COUT HIN  WIN KS PAD BANDS SLOTS CTAS
-using WgF_A0 = L0FCfg<8, 112, 112, 5, 2, 7, 2, 2>;         // (STAGED, one CTA per SM with 8 transform warps: 0.73 ms vs 0.55 ms)
+using WgF_A0 = L0FCfg<8, 112, 112, 5, 2, 7, 2, 2>;         // (STAGED measured slower: 0.73 ms with one CTA / 8 transform warps, 0.83 ms with two CTAs, vs 0.55 ms)
 using WgF_I0 = L0FCfg<32, 28, 28, 5, 2, 1, 2, 1>;
 using WgF_S0 = L0FCfg<32, 28, 28, 3, 1, 1, 2, 1>;
 
