@@ -71,7 +71,8 @@ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ?
 // A function of the layer shape only, because the weight image (b200_conv_tc_prep_weights) depends on it.
 __host__ __device__ constexpr int xph_for(int cin, int cout, int ks) {
     return (ks == 5 && ((cin == 8 && cout == 16) || (cin == 16 && cout == 8))) ? 4
-         : (ks == 5 && ((cin == 16 && cout == 32) || (cin == 32 && cout == 16))) ? 2 : 1;
+         : (ks == 5 && ((cin == 16 && cout == 32) || (cin == 32 && cout == 16))) ? 2
+         : (ks == 3 && ((cin == 32 && cout == 64) || (cin == 64 && cout == 32))) ? 2 : 1;
 }
 
 struct TMaps {
