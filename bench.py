@@ -121,9 +121,64 @@ def cpu_reference(batch, steps, warmup, cores, with_aug=True):
     return rate, 1e3 * batch / rate, desc
 
 
+def run_reference_on_gpu(args):
+    """Library-kernel bar: the oracle's restatement of the reference step (the same torch calls as models/dino.py /
+    models/unimodal.py) moved to cuda:0 and run the way the reference runs on a GPU -- eager ATen / cuDNN / cuBLAS, fp16
+    autocast (run_dino.py:360) unless --reference-fp32.  Inputs are ALREADY-AUGMENTED views resident in HBM: the reference has
+    no GPU augmentation (its torchvision chains run in DataLoader workers), so this bar EXCLUDES the augmentation that our step
+    includes.  A reported baseline beside the CPU arm, never part of the product path."""
+    import torch
+    from oracle import dino_ref, fixtures
+
+    def to_cuda(obj):
+        if torch.is_tensor(obj):
+            return obj.cuda()
+        if isinstance(obj, dict):
+            return {k: to_cuda(v) for k, v in obj.items()}
+        if isinstance(obj, (list, tuple)):
+            return type(obj)(to_cuda(v) for v in obj)
+        return obj
+
+    torch.backends.cudnn.benchmark = True
+    B, V, Vg = args.batch, 6, 2
+    st = dino_ref.CentralDinoState(seed=0)
+    for name, val in list(vars(st).items()):
+        setattr(st, name, to_cuda(val))
+    g = torch.Generator(device="cuda").manual_seed(1)
+    img = torch.rand(V, B, 1, 28, 28, device="cuda", generator=g)
+    aud = torch.rand(V, B, 1, 112, 112, device="cuda", generator=g)
+    masks = to_cuda(fixtures.make_masks(3, V, Vg, B, st.E, 512))
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.float16, enabled=not args.reference_fp32):
+            return dino_ref.central_dino_step(st, img, aud, masks)["loss"]
+
+    for _ in range(max(args.warmup, 3)):
+        loss = step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    rate = B / ms * 1e3
+    prec = "fp32 (torch defaults)" if args.reference_fp32 else "fp16 autocast (run_dino.py:360)"
+    print(json.dumps({"metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+                      "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32" if args.reference_fp32 else "f16", "data": "synthetic",
+                      "config": {"workload": WORKLOAD, "per_gpu_batch": B, "inputs": "pre-augmented views resident in HBM (no augmentation timed)",
+                                 "execution": "stock PyTorch eager kernels (cuDNN / cuBLAS / ATen) on cuda:0, " + prec},
+                      "impl": "reference", "library_bar": True, "last_loss": float(loss),
+                      "torch": torch.__version__, "cudnn": torch.backends.cudnn.version()}))
+
+
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    if args.reference_device == "gpu":
+        return run_reference_on_gpu(args)
     cores = os.cpu_count() or 1
     # size the per-step sample so that the whole run stays within a couple of minutes
     import torch
@@ -452,6 +507,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-device", default="cpu", choices=["cpu", "gpu"],
+                    help="--impl reference only: 'gpu' times the same oracle step with stock PyTorch kernels on cuda:0 (library bar)")
+    ap.add_argument("--reference-fp32", action="store_true", help="library bar without fp16 autocast")
     ap.add_argument("--graph", action="store_true",
                     help="replay the whole step from one CUDA graph (single GPU; meant for small per-GPU batches, where the "
                          "~165 host-side launches bound the step)")

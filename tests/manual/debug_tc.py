@@ -1,5 +1,5 @@
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle.fixtures import make_masks, synth_views, views_to_vb
 from multimodal_ssl_avmnist_b200.engine import DinoStepEngine

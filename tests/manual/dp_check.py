@@ -1,11 +1,11 @@
 """Multi-GPU plumbing check (run under torchrun, N >= 2): every rank feeds the SAME views and dropout masks, so after the
 gradient / centre all-reduces each rank must reproduce the single-process step exactly (sum of N identical gradients
 times 1/N; mean over N identical row sets).  Also checks that ranks stay bit-identical with different per-rank data.
-    torchrun --nproc-per-node 2 --master-addr 127.0.0.1 tools/dp_check.py"""
+    torchrun --nproc-per-node 2 --master-addr 127.0.0.1 tests/manual/dp_check.py"""
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
 import torch.distributed as dist

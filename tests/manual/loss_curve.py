@@ -2,7 +2,7 @@
 the engine in both precisions, on identical per-step inputs (pre-augmented synthetic views, shared dropout masks) from
 identical initial weights.  Writes a JSON with the three curves and summary statistics.
 
-    python tools/loss_curve.py --steps 1000 --batch 16 --out profiles/r1b_loss_curve_1k.json
+    python tests/manual/loss_curve.py --steps 1000 --batch 16 --out profiles/r1b_loss_curve_1k.json
 """
 import argparse
 import json
@@ -10,7 +10,7 @@ import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import dino_ref as R
 from oracle.fixtures import make_masks, synth_views, views_to_vb
