@@ -283,6 +283,9 @@ def op_cost(name, meta):
     return 0.0, 0.0
 
 
+NCU_EXTRA = {}      # tensor-pipe / l1tex busy % of the roofline kernel from the same committed ncu capture
+
+
 def ncu_traffic(row, B):
     """dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
     (profiles/ncu_traffic.json, taken at per-GPU batch 1024; scaled linearly to B), or None if it was not captured."""
@@ -295,6 +298,7 @@ def ncu_traffic(row, B):
     ent = table.get("launches", {}).get(key)
     if ent is None:
         return None
+    NCU_EXTRA.update({k_: ent[k_] for k_ in ("tensor_pipe_busy_pct", "l1tex_pct") if k_ in ent})
     return ent["dram_bytes"] * B / table.get("per_gpu_batch", 1024)
 
 
@@ -455,6 +459,11 @@ def run_ours(args):
                             "HBM peak: HBM is the binding roofline")
     roof["family_share_of_step"] = fam[top_op] / step_ms_prof
     roof["traffic"] = ncu_traffic(top, B)
+    if NCU_EXTRA:       # from the same committed ncu --set full capture (profiles/ncu_traffic.json, profiles/r1d_ncu_kernels.md)
+        roof["ncu"] = dict(NCU_EXTRA)
+        if NCU_EXTRA.get("tensor_pipe_busy_pct", 0) > 80:
+            roof["note"] = (roof.get("note", "") + "; ncu: the tensor pipe is busy %.0f %% of the time (a UMMA occupies it for its shared-memory operand "
+                            "fetch whatever its N): the kernel's real ceiling" % NCU_EXTRA["tensor_pipe_busy_pct"]).lstrip("; ")
     tc_rows = [r for r in rows if r["op"] in ("conv_tc", "conv_tc_wgrad")]
     if tc_rows:
         tc_ms = sum(r["ms_per_step"] for r in tc_rows)

@@ -33,6 +33,8 @@ def main():
         hdr, units, data = rows[0], rows[1], rows[2:]
         ik, ig = hdr.index("Kernel Name"), hdr.index("Grid Size")
         it, ir, iw = col(hdr, "gpu__time_duration.sum"), col(hdr, "dram__bytes_read.sum"), col(hdr, "dram__bytes_write.sum")
+        itc = col(hdr, "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed")
+        il1 = col(hdr, "l1tex__throughput.avg.pct_of_peak_sustained_elapsed")
         for d in data:
             name = re.sub(r"\(int\)|\(bool\)", "", d[ik])
             grid = [int(x) for x in re.findall(r"\d+", d[ig])]
@@ -69,7 +71,7 @@ def main():
                 continue
             if key in launches:           # the same kernel more than once in the capture: keep the first (student) launch
                 continue
-            launches[key] = {"dram_bytes": traffic, "us_under_ncu": float(d[it].replace(",", "")) * (1024 / b if False else 1), "source": path.split("/")[-1],
+            launches[key] = {"tensor_pipe_busy_pct": float(d[itc]), "l1tex_pct": float(d[il1]), "dram_bytes": traffic, "us_under_ncu": float(d[it].replace(",", "")) * (1024 / b if False else 1), "source": path.split("/")[-1],
                              "captured_at_batch": b}
     json.dump({"per_gpu_batch": 1024, "metric": "dram__bytes_read.sum + dram__bytes_write.sum (ncu --set full --clock-control none)",
                "launches": launches}, open(out, "w"), indent=1)
