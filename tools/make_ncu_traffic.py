@@ -12,8 +12,10 @@ V_STUDENT, V_TEACHER = 6, 2
 
 
 def col(hdr, name):
+    if name in hdr:
+        return hdr.index(name)
     for i, h in enumerate(hdr):
-        if h == name or h.endswith(name):
+        if h.endswith(name):
             return i
     raise KeyError(name)
 
@@ -71,7 +73,7 @@ def main():
                 continue
             if key in launches:           # the same kernel more than once in the capture: keep the first (student) launch
                 continue
-            launches[key] = {"tensor_pipe_busy_pct": float(d[itc]), "l1tex_pct": float(d[il1]), "dram_bytes": traffic, "us_under_ncu": float(d[it].replace(",", "")) * (1024 / b if False else 1), "source": path.split("/")[-1],
+            launches[key] = {"tensor_pipe_busy_pct": float(d[itc] or 0), "l1tex_pct": float(d[il1] or 0), "dram_bytes": traffic, "us_under_ncu": float(d[it].replace(",", "")) * (1024 / b if False else 1), "source": path.split("/")[-1],
                              "captured_at_batch": b}
     json.dump({"per_gpu_batch": 1024, "metric": "dram__bytes_read.sum + dram__bytes_write.sum (ncu --set full --clock-control none)",
                "launches": launches}, open(out, "w"), indent=1)
