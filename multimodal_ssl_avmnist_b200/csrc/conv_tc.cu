@@ -1,18 +1,25 @@
-// Tensor-core convolutions for the C_in >= 8 layers of the AVMNIST encoders (models/unimodal.py:129-140, 186-208;
-// models/dino.py:20-30): tcgen05.mma with TMEM accumulators, operands staged by TMA, NO im2col.
+// Tensor-core convolutions of the AVMNIST encoders (models/unimodal.py:129-140, 186-208; models/dino.py:20-30):
+// tcgen05.mma with TMEM accumulators, operands staged by TMA, NO im2col.  Forward, data gradient, weight gradient; first
+// layers (C_in = 1) included; the first-layer backward is fused with its BatchNorm / ReLU / max-pool backward.
 //
 // Activation layout ("act8"): bf16 [N][C/8][H][W][8] -- channel octets are planes, a pixel of a plane is one 16-byte
 // unit.  A TMA box load of (8, W+2p, H'+K-1, C/8) starting at (-p, -p) drops a whole zero-padded image (or row band)
 // into shared memory (out-of-bounds = 0 is the convolution padding).  With output pixels numbered flat over the PADDED
-// pitch, q = y*(W+2p) + x, the input pixel of tap (kh,kw) is q + kh*(W+2p) + kw: for a tile of 128 consecutive q the A
+// pitch, q = y*pitch + x, the input pixel of tap (kh,kw) is q + kh*pitch + kw: for a tile of 128 consecutive q the A
 // operand of every tap is the SAME smem image at a shifted start address -- a K-major SWIZZLE_NONE UMMA descriptor
 // (8 consecutive pixels x 16 B = one core matrix, SBO = 128 B; the second K chunk is the next channel plane,
-// LBO = plane stride, or for C_in = 8 the next kw tap, LBO = 16 B).  Outputs at x >= W_out / y >= H_out are junk and
-// are masked in the epilogue (7-30 % of the MMA work, which is nowhere near the bound).
+// LBO = plane stride, or for C_in = 8 the next kw tap).  Outputs at x >= W_out / y >= H_out are junk and are masked in
+// the epilogue.
 //
-// Roles in a CTA (192 threads, one CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-5 =
-// epilogue (tcgen05.ld -> +bias -> BatchNorm partial statistics -> store), double-buffered TMEM accumulators.
-// The same kernel is the data-gradient convolution (flipped/transposed weights prepared by conv_tc_prep_weights).
+// A UMMA occupies the tensor pipe for its shared-memory operand fetch (26-48 cycles at these shapes) whatever its N, so
+// the kernels minimise the NUMBER of UMMAs: adjacent output pixels are packed into N ("x phases", see xph_for / TcCfg),
+// with the input slab de-interleaved by phase through strided TMA maps; first layers read the "quad8" image (8 consecutive
+// padded pixels per unit = all taps of four output pixels).  See DESIGN.md 4.1 for the measurements behind this.
+//
+// Kernels: conv_tc_kernel (forward / data gradient: warp 0 = TMA producer, 1-4 MMA-issuer warps, 4 epilogue warps,
+// 2-8 TMEM accumulator stages), conv_tc_wgrad_kernel / conv_tc_wgrad_ph_kernel (weight gradients, MN-major operands, one
+// TMEM accumulator per (kh, plane)), conv_tc_wgrad_l0_fused_kernel (first layer: BatchNorm-backward-apply in shared memory
+// + weight gradient), weight-image / input-image packing kernels.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
