@@ -191,3 +191,46 @@ def test_step_against_reference(mode, golden):
         _check_group(bn, rec["student_bn"], 1e-5, ba, "student_bn")
         _check_group(st.teacher_buf, rec["teacher_bn"], 1e-5, ba, "teacher_bn")
         _check_group(st.student_head_buf, rec["student_head_bn"], 1e-5, ba, "head_bn")
+
+
+@pytest.mark.parametrize("key,alpha", [("unimodal_image_simple", 0.0), ("unimodal_image_simple_cosine", 0.3)])
+def test_unimodal_step_loss_and_gradients_against_reference(key, alpha, golden):
+    """UniModalDINOLightning.training_step of the imported reference on ImageEncoder (BASELINE config 1), with and without the
+    cosine-consistency term: the oracle's pieces (image_simple_encoder, projection_head, dino_loss_unimodal,
+    cosine_consistency_loss) reproduce its loss and parameter gradients."""
+    fx = golden[key]
+    B = fx["B"]
+    spec, hspec = R.image_simple_spec(256), R.head_spec(256, 128)
+    sp = {k: v.clone().requires_grad_(True) for k, v in R.make_params(spec, fx["seed"]).items()}
+    hp = {k: v.clone().requires_grad_(True) for k, v in R.make_params(hspec, fx["seed"] + 1).items()}
+    bufs = [R.make_bn_buffers(spec, R.image_simple_bn_names()) for _ in range(2)] + [R.make_bn_buffers(hspec, ["mlp.1"]) for _ in range(2)]
+    gi, ga, li, la = synth_views(B, seed=100)
+    img, _ = views_to_vb(gi, ga, li, la)
+    m = make_masks(seed=200, V=6, Vg=2, B=B, E=256, hidden=512)
+    feats = torch.cat([R.image_simple_encoder(img[v], sp, bufs[0]) for v in range(6)])
+    with torch.no_grad():
+        tfeat = torch.cat([R.image_simple_encoder(img[v], {k: v_.detach() for k, v_ in sp.items()}, bufs[1]) for v in range(2)])
+        tproj = R.projection_head(tfeat, {k: v_.detach() for k, v_ in hp.items()}, bufs[3], None, 0.0)
+    sproj = R.projection_head(feats, hp, bufs[2], m["student_head"], 0.3)
+    loss = R.dino_loss_unimodal(sproj.view(6, B, -1), tproj.view(2, B, -1))        # centre is zero on the first step
+    if alpha > 0:
+        loss = loss + alpha * R.cosine_consistency_loss(feats.view(6, B, -1))
+    assert abs(float(loss.detach()) - fx["loss"]) < 1e-5 * fx["loss"], (float(loss.detach()), fx["loss"])
+    loss.backward()
+    checked = 0
+    for k, ref in fx["grads"].items():
+        if k.startswith("model.student_projection."):
+            g = hp[k[len("model.student_projection."):]].grad
+        elif k.startswith("model.student."):
+            g = sp[k[len("model.student."):]].grad
+        else:
+            continue
+        if g is None:
+            continue
+        ok, why = summaries_close(summarize(g), ref, 2e-4, 1e-7)
+        # conv biases in front of a train-mode BatchNorm: mathematically zero gradient, pure rounding noise on both sides
+        if not ok and k.endswith(".bias") and ref["abs_sum"] < 1e-4 * ref["n"]:
+            continue
+        assert ok, (k, why)
+        checked += 1
+    assert checked >= 10
