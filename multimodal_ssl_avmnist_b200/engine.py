@@ -167,6 +167,8 @@ class DinoStepEngine:
         self.world = dp.world_size(process_group) if (data_parallel is None or data_parallel) else 1
         self.step_count = 0          # optimizer steps taken (Adam bias correction)
         self.rng_step = 0            # augmentation / dropout stream position
+        self._loss_slots = [torch.zeros(1).pin_memory() for _ in range(2)]      # lagged loss read-back (train_step_host)
+        self._loss_flip, self._loss_pending = 0, None
         self._ctr = None             # CUDA-graph mode: device counters int64 [rng_step, adam step] read by the kernels
         self._bc = None              #   ... and Adam's two bias corrections of the current step (device, fp32)
         self._graph = None
@@ -1092,11 +1094,14 @@ class DinoStepEngine:
         self._graph = None
         self._ctr = self._bc = None
 
-    def train_step_host(self, images_host, audios_host=None, labels_host=None, next_batch=None):
+    def train_step_host(self, images_host, audios_host=None, labels_host=None, next_batch=None, lagged_loss=False):
         """The host-facing call: raw batch in (pinned) host memory -> H2D copies -> whole step -> the total loss as a Python
         float (D2H read).  This is what `e2e` in bench.py times.  next_batch = (images_host, audios_host[, labels_host]) of
         the FOLLOWING call, if known: its H2D copy and augmentation are enqueued on the augmentation stream before this
-        step's loss is read back, so the input pipeline overlaps the step (what the reference's DataLoader workers do)."""
+        step's loss is read back, so the input pipeline overlaps the step (what the reference's DataLoader workers do).
+        lagged_loss=True: every step's loss is still copied to (pinned) host memory, but the call returns the PREVIOUS step's
+        value (None on the first call; flush_loss() returns the last one) so that the host never waits for the step it has
+        just enqueued -- the usual way a training loop logs its loss."""
         B = images_host.shape[0]
         buf = self._ws.setdefault(("host", B, images_host.dtype, None if audios_host is None else audios_host.dtype), {})
         if not buf:
@@ -1133,4 +1138,22 @@ class DinoStepEngine:
                     buf["lab_b"].copy_(nlab, non_blocking=True)
             if self.prefetch_augment(buf["img_b"], buf.get("aud_b")):
                 buf["staged"] = (nimg.data_ptr(), None if naud is None else naud.data_ptr())
-        return float(loss[3].item())
+        if not lagged_loss:
+            return float(loss[3].item())
+        prev = self.flush_loss()
+        slot = self._loss_slots[self._loss_flip]
+        self._loss_flip ^= 1
+        slot.copy_(loss[3:4], non_blocking=True)              # D2H of this step's loss, read one call later
+        ev = torch.cuda.Event()
+        ev.record()
+        self._loss_pending = (slot, ev)
+        return prev
+
+    def flush_loss(self):
+        """The loss of the last train_step_host(lagged_loss=True) call whose value has not been returned yet (or None)."""
+        if self._loss_pending is None:
+            return None
+        slot, ev = self._loss_pending
+        self._loss_pending = None
+        ev.synchronize()
+        return float(slot[0])

@@ -316,3 +316,21 @@ def test_cuda_graph_replay_reproduces_the_eager_step_bit_for_bit(mode):
     torch.cuda.synchronize()
     assert torch.equal(a, b) if mode == "default" else torch.allclose(a, b, rtol=1e-5, atol=1e-7)
     assert torch.equal(graph.student.flat, eager.student.flat)
+
+
+def test_host_step_lagged_loss_returns_the_previous_steps_value():
+    """train_step_host(lagged_loss=True): same training trajectory, every step's loss still reaches the host, one call later."""
+    B = 8
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(B, 28, 28, generator=g).pin_memory()
+    aud = torch.randint(0, 256, (B, 112, 112), dtype=torch.uint8, generator=g).pin_memory()
+    a = DinoStepEngine(kind="multi_central", device=DEV, precision="bf16", seed=3)
+    b = DinoStepEngine(kind="multi_central", device=DEV, precision="bf16", seed=3)
+    b.student.flat.copy_(a.student.flat)
+    a.sync_teacher()
+    b.sync_teacher()
+    direct = [a.train_step_host(img, aud) for _ in range(4)]
+    lagged = [b.train_step_host(img, aud, lagged_loss=True) for _ in range(4)]
+    assert lagged[0] is None and lagged[1:] == direct[:3]
+    assert b.flush_loss() == direct[3] and b.flush_loss() is None
+    assert torch.equal(a.student.flat, b.student.flat)
