@@ -113,7 +113,7 @@ struct TcCfg {
     static constexpr int Q = (HB - 1) * WQ + WOQ;               // flat tile rows per band (incl. junk columns)
     static constexpr int TILES = (Q + 127) / 128;
     static constexpr int PLANE_BYTES = HPB * WQ * 16;           // one (x phase, channel plane)
-    static constexpr int PHASE_BYTES = P * PLANE_BYTES;
+    static constexpr int PHASE_BYTES = round_up(P * PLANE_BYTES, 128);   // stride of a phase-plane group: TMA destinations are 128-byte aligned
     static constexpr int SLOT_BYTES = round_up(XPL * PHASE_BYTES, 128);
     static constexpr int NJ = (KWX + 1) / 2;                    // kw' pairs when CIN == 8
     static constexpr int PH = P / 2;                            // plane pairs when CIN >= 16
@@ -140,7 +140,7 @@ struct TcCfg {
     static_assert(NPAD % 16 == 0 && NPAD >= 16 && NPADL <= 128 && COUT <= NPAD && COUT % 8 == 0, "N tile");
     static_assert(HO % BANDS == 0, "bands must divide the output height");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
-    static_assert(XPL * P * PLANE_BYTES < (1 << 18) && PLANE_BYTES % 16 == 0, "descriptor range");
+    static_assert(XPL * PHASE_BYTES < (1 << 18) && PLANE_BYTES % 16 == 0, "descriptor range");
 };
 
 // out: fp32 NCHW [N][COUT][HO][WO] (out_bf16 == 0), bf16 act8 [N][COUT/8][HO][WO][8] (1) or the same in fp16 (2: the pre-BatchNorm
@@ -208,7 +208,7 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
             for (int i = i0; i < i1; ++i) {
                 const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
                 mbar_wait(empty_bar(slot), (use & 1) ^ 1);
-                mbar_expect_tx(full_bar(slot), C::XPL * C::PHASE_BYTES);
+                mbar_expect_tx(full_bar(slot), C::XPL * C::P * C::PLANE_BYTES);
                 const int n = view * n_per_view + i / C::BANDS, band = i % C::BANDS;
 #pragma unroll
                 for (int rp = 0; rp < C::XPL; ++rp) {
@@ -791,6 +791,7 @@ struct WgPCfg {
     static_assert(KWX <= 8 && NTOT <= 256 && NTOT % 16 == 0 && TCOLS <= 512, "taps / N / TMEM");
     static_assert(WQ * XPH >= WP && (BANDS == 1 || HBZ == HB), "pitch / bands");
     static_assert((KSTEPS * 16 + (KS - 1) * WQ - HPB * WQ) * 16 <= Z_BYTES, "x overrun must stay inside the slot");
+    static_assert((PI * PLANE_XU) % 128 == 0 && (P_OUT * PLANE_Z) % 128 == 0, "TMA destinations (unit planes, phase planes) must be 128-byte aligned");
     static_assert(SMEM + 1024 <= 227 * 1024 && 2 * SLOTS + 1 <= 24, "shared memory / barriers");
 };
 
@@ -1010,6 +1011,7 @@ struct L0FCfg {
     static_assert(STAGE_BYTES <= SLOT, "staging reuses the first slot");
     static_assert((KSTEPS * 16 + 7 * WQ + 8 - HPB * WQ) * 16 <= ZS_BYTES + Z_BYTES, "x overrun must stay inside the slot");
     static_assert(!STAGED || HBZ == HB, "staged z tile: whole bands");
+    static_assert((P_OUT * PLANE_Z) % 128 == 0, "TMA destinations (phase planes) must be 128-byte aligned");
     static_assert(KSTEPS >= L0F_ISS, "every issuer needs a K step");
 };
 
