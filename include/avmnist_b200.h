@@ -92,6 +92,12 @@ int b200_infonce_fwd_bwd(const float* a, const float* b, int B, int D, float tem
 int64_t b200_infonce_tc_work_floats(int B, int D);
 int b200_infonce_fwd_bwd_tc(const float* a, const float* b, int B, int D, float temperature, float grad_scale, float* grad_a,
                             float* grad_b, float* loss_out, float* work, void* stream);
+/* SimCLR NT-Xent (other_ssl/multimodal_simclr/multimodal_simclr.py:74-89): reps [N = 2B, D] = cat([z1, z2]); row-normalised
+ * similarities / temperature, self-similarity masked, positive of row i = row (i + B) mod N, mean cross-entropy; forward and
+ * backward in one call on the InfoNCE tile kernels.  work: float[b200_ntxent_work_floats(N, D)]. */
+int64_t b200_ntxent_work_floats(int N, int D);
+int b200_ntxent_fwd_bwd(const float* reps, int N, int D, float temperature, float grad_scale, float* grad, float* loss_out,
+                        float* work, void* stream);
 /* UniModalDINOLightning._cosine_consistency_loss, models/dino.py:1575-1594: emb [V,B,D] */
 int b200_cosine_consistency_fwd_bwd(const float* emb, int V, int B, int D, float grad_scale, float* grad_emb,
                                     float* loss_out, void* stream);

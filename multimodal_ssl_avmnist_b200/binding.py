@@ -225,6 +225,16 @@ def standalone_pair_loss(kind, a, b, **kw):
     return fused_loss(lo[0], (a, b), (ga, gb))
 
 
+def standalone_ntxent_loss(reps, temperature=0.07):
+    """SimCLR NT-Xent of reps [2B, D] = cat([z1, z2]) (other_ssl/multimodal_simclr/multimodal_simclr.py:74-89) through the fused
+    kernel, differentiable w.r.t. reps (a drop-in for MultiModalSimCLRLightning.nt_xent_loss on CUDA tensors)."""
+    x = reps.detach().contiguous().float()
+    g, lo = torch.empty_like(x), torch.empty(1, device=x.device)
+    work = torch.empty(ops.ntxent_work_floats(*x.shape), device=x.device)
+    ops.ntxent_fwd_bwd(x, g, lo, work, temperature=temperature)
+    return fused_loss(lo[0], (reps,), (g,))
+
+
 def standalone_ce_loss(logits, labels):
     x = logits.detach().contiguous().float()
     g, lo = torch.empty_like(x), torch.empty(1, device=x.device)

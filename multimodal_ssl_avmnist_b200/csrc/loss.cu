@@ -240,7 +240,9 @@ template <bool GRAD>
 __global__ void __launch_bounds__(256) infonce_rows_kernel(const float* __restrict__ A, const float* __restrict__ Bm, int B, int D,
                                                            float inv_temp, const float* __restrict__ rowsum_in,
                                                            const float* __restrict__ colsum_in, float coef,
-                                                           float* __restrict__ out) {
+                                                           float* __restrict__ out, int partner_half) {
+    // partner_half > 0: NT-Xent on ONE set of 2*half rows (A == Bm): self-similarities are masked out of the sums and the
+    // positive of row i is row (i + half) mod B instead of the diagonal
     // smem: At[D][NT] (k-major), Bt[D][NT], Bs[NT][D] (row-major copy for the G*B product), G[NT][NT+1]
     extern __shared__ float sm[];
     float* At = sm;
@@ -295,12 +297,13 @@ __global__ void __launch_bounds__(256) infonce_rows_kernel(const float* __restri
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 int gi = i0 + ty * 4 + a, gj = j0 + tx * 4 + c;
-                float e = (gi < B && gj < B) ? expf(sacc[a][c] * inv_temp - inv_temp) : 0.f;
+                float e = (gi < B && gj < B && !(partner_half > 0 && gi == gj)) ? expf(sacc[a][c] * inv_temp - inv_temp) : 0.f;
                 if (!GRAD) {
                     rs[a] += e;
                 } else {
                     float csj = (gj < B) ? __ldg(colsum_in + gj) : 1.f;
-                    float g = (e / rsi[a] + e / csj) * (0.5f * coef) - ((gi == gj && gi < B) ? coef : 0.f);
+                    const int pos = partner_half > 0 ? (gi + partner_half) % B : gi;
+                    float g = (e / rsi[a] + e / csj) * (0.5f * coef) - ((gj == pos && gi < B) ? coef : 0.f);
                     G[(ty * 4 + a) * (NT + 1) + tx * 4 + c] = g;
                 }
             }
@@ -376,6 +379,21 @@ __global__ void __launch_bounds__(256) infonce_loss_kernel(const float* __restri
         if (lane == 0) acc += logf(rowsum[r]) + logf(colsum[r]) + 2.f * inv_temp - 2.f * d * inv_temp;
     }
     if (lane == 0) atomicAdd(loss_out, acc / (2.f * (float)B));
+}
+
+// NT-Xent: loss = sum_i [log rowsum_i + 1/temp - sim(i, partner(i))] / N  (rowsum excludes the self-similarity)
+__global__ void __launch_bounds__(256) ntxent_loss_kernel(const float* __restrict__ rh, const float* __restrict__ rowsum, int N, int D,
+                                                          float inv_temp, float* __restrict__ loss_out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = N / 2;
+    float acc = 0.f;
+    for (int r = blockIdx.x * 8 + warp; r < N; r += gridDim.x * 8) {
+        const int p = (r + half) % N;
+        float d = 0.f;
+        for (int k = lane; k < D; k += 32) d += __ldg(rh + (size_t)r * D + k) * __ldg(rh + (size_t)p * D + k);
+        d = warp_sum(d);
+        if (lane == 0) acc += logf(rowsum[r]) + inv_temp - d * inv_temp;
+    }
+    if (lane == 0) atomicAdd(loss_out, acc / (float)N);
 }
 
 // backward through the row normalisation: dx = (dxh - xh <xh, dxh>) / denom
@@ -630,18 +648,50 @@ int b200_infonce_fwd_bwd(const float* a, const float* b, int B, int D, float tem
     cudaMemsetAsync(loss_out, 0, sizeof(float), st);
     normalize_rows_kernel<<<rg, 256, 0, st>>>(a, B, D, ah, dena);
     normalize_rows_kernel<<<rg, 256, 0, st>>>(b, B, D, bh, denb);
-    infonce_rows_kernel<false><<<tg, 256, sm_f, st>>>(ah, bh, B, D, inv_temp, nullptr, nullptr, 0.f, rowsum);
-    infonce_rows_kernel<false><<<tg, 256, sm_f, st>>>(bh, ah, B, D, inv_temp, nullptr, nullptr, 0.f, colsum);
+    infonce_rows_kernel<false><<<tg, 256, sm_f, st>>>(ah, bh, B, D, inv_temp, nullptr, nullptr, 0.f, rowsum, 0);
+    infonce_rows_kernel<false><<<tg, 256, sm_f, st>>>(bh, ah, B, D, inv_temp, nullptr, nullptr, 0.f, colsum, 0);
     infonce_loss_kernel<<<rg, 256, 0, st>>>(ah, bh, rowsum, colsum, B, D, inv_temp, loss_out);
     const float coef = 1.0f / (float)B;
-    infonce_rows_kernel<true><<<tg, 256, sm_g, st>>>(ah, bh, B, D, inv_temp, rowsum, colsum, coef, dah);
-    infonce_rows_kernel<true><<<tg, 256, sm_g, st>>>(bh, ah, B, D, inv_temp, colsum, rowsum, coef, dbh);
+    infonce_rows_kernel<true><<<tg, 256, sm_g, st>>>(ah, bh, B, D, inv_temp, rowsum, colsum, coef, dah, 0);
+    infonce_rows_kernel<true><<<tg, 256, sm_g, st>>>(bh, ah, B, D, inv_temp, colsum, rowsum, coef, dbh, 0);
     normalize_bwd_kernel<<<rg, 256, 0, st>>>(ah, dah, dena, B, D, grad_scale, grad_a);
     normalize_bwd_kernel<<<rg, 256, 0, st>>>(bh, dbh, denb, B, D, grad_scale, grad_b);
     return launch_status("infonce_fwd_bwd");
 }
 
 static int64_t pad4l(int64_t n) { return (n + 3) / 4 * 4; }
+
+int64_t b200_ntxent_work_floats(int N, int D) { return (int64_t)2 * N * D + (int64_t)2 * N; }
+
+int b200_ntxent_fwd_bwd(const float* reps, int N, int D, float temperature, float grad_scale, float* grad, float* loss_out, float* work,
+                        void* stream) {
+    B200_REQUIRE(reps && grad && loss_out && work && N > 1 && N % 2 == 0, B200_E_ARG, "ntxent: bad arguments (N = 2B rows)");
+    B200_REQUIRE(D % 16 == 0 && D >= 16 && D <= 256, B200_E_SHAPE, "ntxent: D=%d must be a multiple of 16 in [16,256]", D);
+    B200_REQUIRE(temperature > 0.f, B200_E_ARG, "ntxent: temperature must be positive");
+    cudaStream_t st = as_stream(stream);
+    float* rh = work;
+    float* drh = rh + (size_t)N * D;
+    float* den = drh + (size_t)N * D;
+    float* rowsum = den + N;
+    const float inv_temp = 1.0f / temperature;
+    const int rg = rows_grid(N), tg = (N + NT - 1) / NT;
+    const size_t sm_f = (size_t)2 * D * NT * sizeof(float), sm_g = sm_f + ((size_t)NT * D + (size_t)NT * (NT + 1)) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(infonce_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(infonce_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr = true;
+    }
+    normalize_rows_kernel<<<rg, 256, 0, st>>>(reps, N, D, rh, den);
+    infonce_rows_kernel<false><<<tg, 256, sm_f, st>>>(rh, rh, N, D, inv_temp, nullptr, nullptr, 0.f, rowsum, N / 2);
+    cudaMemsetAsync(loss_out, 0, sizeof(float), st);
+    ntxent_loss_kernel<<<rg, 256, 0, st>>>(rh, rowsum, N, D, inv_temp, loss_out);
+    // dL/dS_ij = (e_ij / rowsum_i - [j == partner(i)]) / N, and S = R R^T is symmetric in R:
+    // dL/dR_hat = (H + H^T) R_hat / temp with (H + H^T)_ij = (e_ij/rs_i + e_ij/rs_j) / N - 2 [j == partner(i)] / N
+    infonce_rows_kernel<true><<<tg, 256, sm_g, st>>>(rh, rh, N, D, inv_temp, rowsum, rowsum, 2.0f / (float)N, drh, N / 2);
+    normalize_bwd_kernel<<<rg, 256, 0, st>>>(rh, drh, den, N, D, grad_scale, grad);
+    return launch_status("ntxent_fwd_bwd");
+}
 
 int64_t b200_infonce_tc_work_floats(int B, int D) {
     if (B <= 0 || D <= 0) return 0;

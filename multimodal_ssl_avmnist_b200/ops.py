@@ -154,6 +154,17 @@ def infonce_fwd_bwd(a, b, grad_a, grad_b, loss_out, work, temperature=0.07, grad
                   _ptr(work, F32), _stream()), "infonce_fwd_bwd")
 
 
+def ntxent_work_floats(N, D):
+    return int(_lib_().b200_ntxent_work_floats(N, D))
+
+
+def ntxent_fwd_bwd(reps, grad, loss_out, work, temperature=0.07, grad_scale=1.0):
+    """SimCLR NT-Xent on reps [2B, D] = cat([z1, z2]) (positives B rows apart, self-similarity masked): loss + d loss / d reps."""
+    N, D = reps.shape
+    _lib.check(_lib_().b200_ntxent_fwd_bwd(_ptr(reps, F32), N, D, temperature, grad_scale, _ptr(grad, F32), _ptr(loss_out, F32),
+                                           _ptr(work, F32), _stream()), "ntxent_fwd_bwd")
+
+
 def cosine_consistency_fwd_bwd(emb, grad_emb, loss_out, grad_scale=1.0):
     V, B, D = emb.shape
     _lib.check(_lib_().b200_cosine_consistency_fwd_bwd(_ptr(emb, F32), V, B, D, grad_scale, _ptr(grad_emb, F32), _ptr(loss_out, F32),
@@ -501,8 +512,8 @@ def bn1d_gelu_drop_bwd_apply(h, dg, scale, shift, mean, invstd, mask, drop_p, su
 
 # ---- launch accounting and optional per-op timing ------------------------------------------------------------
 # Every wrapper above issues a fixed number of kernel launches; the table lists the ones that issue more than one.
-_LAUNCHES = {"conv_tc_wgrad_l0_fused": 3, "conv_tc_wgrad": 2, "conv_bwd_weight": 3, "linear_bwd_weight": 3, "infonce_fwd_bwd": 9}
-_NOT_KERNELS = {"conv_tc_wgrad_l0_fused_work_floats", "conv_tc_wgrad_work_floats", "conv_tc_supported", "conv_tc_weight_bytes", "dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
+_LAUNCHES = {"ntxent_fwd_bwd": 5, "conv_tc_wgrad_l0_fused": 3, "conv_tc_wgrad": 2, "conv_bwd_weight": 3, "linear_bwd_weight": 3, "infonce_fwd_bwd": 9}
+_NOT_KERNELS = {"quad8_width", "ntxent_work_floats", "conv_tc_wgrad_l0_fused_work_floats", "conv_tc_wgrad_work_floats", "conv_tc_supported", "conv_tc_weight_bytes", "dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
 LAUNCH_COUNT = 0
 _PROFILE = None          # None, or a list receiving (name, start_event, end_event, meta)
 

@@ -216,6 +216,17 @@ def infonce_loss(a, b, temperature=0.07):
     return 0.5 * (F.cross_entropy(sim, lab) + F.cross_entropy(sim.T, lab))
 
 
+def ntxent_loss(reps, temperature=0.07):
+    """MultiModalSimCLRLightning.nt_xent_loss (other_ssl/multimodal_simclr/multimodal_simclr.py:74-89): reps = cat([z1, z2]),
+    self-similarities masked, positive of row i is row (i + B) mod 2B."""
+    r = F.normalize(reps, dim=1)
+    n = r.shape[0]
+    sim = (r @ r.T) / temperature
+    sim = sim.masked_fill(torch.eye(n, dtype=torch.bool, device=r.device), float("-inf"))
+    lab = (torch.arange(n, device=r.device) + n // 2) % n
+    return F.cross_entropy(sim, lab)
+
+
 def mse_align_loss(a, b):
     """MultiModalDINOWithMSELightning.mse_loss (models/dino.py:1193-1211)."""
     return ((F.normalize(a, p=2, dim=1) - F.normalize(b, p=2, dim=1)) ** 2).mean()

@@ -62,6 +62,14 @@ def losses_kat():
     labels = torch.tensor([3, 1, 4, 1])
     ce = torch.nn.CrossEntropyLoss()
     out["supervised"] = float(ce(logits_i, labels) + ce(logits_a, labels))
+    # SimCLR NT-Xent: the reference's own method on cat([z1, z2])
+    import other_ssl.multimodal_simclr.multimodal_simclr as simclr
+    reps = torch.cat([S[0], S[1]]).clone().requires_grad_(True)
+    nt = simclr.MultiModalSimCLRLightning.nt_xent_loss(None, reps)
+    nt.backward()
+    out["ntxent"] = float(nt)
+    out["ntxent_grad_abs_sum"] = float(reps.grad.abs().sum())
+    out["ntxent_grad_first8"] = reps.grad.flatten()[:8].tolist()
     # gradient KAT for the fused DINO loss backward
     Sg = S.clone().requires_grad_(True)
     M().dino_loss(Sg, T).backward()

@@ -227,3 +227,21 @@ def test_feature_path_and_linear_probe(tmp_path):
     tr = pl.Trainer(max_epochs=1, logger=CSVLogger(str(tmp_path), name="logs"), log_every_n_steps=1, devices=1, accelerator="gpu")
     tr.fit(lit2, datamodule=dm)
     assert "mlp_acc" in tr.callback_metrics and 0.0 <= float(tr.callback_metrics["mlp_acc"]) <= 100.0
+
+
+def test_standalone_ntxent_is_a_drop_in_for_the_reference_loss():
+    """binding.standalone_ntxent_loss: forward value and autograd gradient of the fused kernel == torch restatement of
+    MultiModalSimCLRLightning.nt_xent_loss on CUDA tensors that require grad."""
+    import torch.nn.functional as F
+    from multimodal_ssl_avmnist_b200 import binding as B
+    torch.manual_seed(3)
+    z = torch.randn(64, 128, device=DEV, requires_grad=True)
+    loss = B.standalone_ntxent_loss(z)
+    loss.backward()
+    z2 = z.detach().clone().double().requires_grad_(True)
+    r = F.normalize(z2, dim=1)
+    sim = (r @ r.T / 0.07).masked_fill(torch.eye(64, dtype=torch.bool, device=DEV), float("-inf"))
+    want = F.cross_entropy(sim, (torch.arange(64, device=DEV) + 32) % 64)
+    want.backward()
+    assert abs(float(loss) - float(want)) < 1e-5 * float(want)
+    assert float((z.grad - z2.grad.float()).abs().max()) <= 2e-5 * float(z2.grad.abs().max())

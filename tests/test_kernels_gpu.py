@@ -489,3 +489,28 @@ def test_adam_and_dropout_mask():
     assert torch.equal(mask, m2)
     ops.dropout_mask(m2, 0.3, 42, 8)
     assert not torch.equal(mask, m2)
+
+
+@pytest.mark.parametrize("B,D", [(4, 128), (37, 128), (300, 64), (1000, 256)])
+def test_ntxent_vs_oracle(B, D, golden):
+    """b200_ntxent_fwd_bwd (SimCLR NT-Xent on the InfoNCE tile kernels, self-similarity masked, positives B rows apart)
+    against the oracle's restatement of the reference; B = 4 is the reference's own known answer."""
+    if B == 4:
+        torch.manual_seed(7)
+        S = torch.randn(6, 4, 128)
+        reps = torch.cat([S[0], S[1]])
+    else:
+        reps = torch.randn(2 * B, D, generator=torch.Generator().manual_seed(B))
+    want_in = reps.clone().double().requires_grad_(True)
+    want = R.ntxent_loss(want_in)
+    want.backward()
+    x = reps.to(DEV)
+    grad, loss = torch.empty_like(x), torch.empty(1, device=DEV)
+    work = torch.empty(ops.ntxent_work_floats(2 * B, D), device=DEV)
+    ops.ntxent_fwd_bwd(x, grad, loss, work)
+    torch.cuda.synchronize()
+    if B == 4:
+        assert abs(float(loss) - golden["losses"]["ntxent"]) < 2e-6 * golden["losses"]["ntxent"] + 1e-6
+    assert abs(float(loss) - float(want)) < 1e-5 * abs(float(want)) + 1e-6
+    ref = want_in.grad.float()
+    assert float((grad.cpu() - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 1e-8

@@ -37,6 +37,17 @@ def test_loss_known_answers(golden):
     assert abs(g["infonce"] - 1.38977242) < 1e-6 and abs(g["mse"] - 0.01482718) < 1e-7
 
 
+def test_ntxent_known_answer(golden):
+    """SimCLR NT-Xent: the oracle's restatement against the reference's own nt_xent_loss on cat([S[0], S[1]])."""
+    S, _ = _kat_inputs()
+    reps = torch.cat([S[0], S[1]]).clone().requires_grad_(True)
+    loss = R.ntxent_loss(reps)
+    assert abs(float(loss.detach()) - golden["losses"]["ntxent"]) < 1e-6
+    loss.backward()
+    assert abs(float(reps.grad.abs().sum()) - golden["losses"]["ntxent_grad_abs_sum"]) < 1e-4 * golden["losses"]["ntxent_grad_abs_sum"]
+    assert torch.allclose(reps.grad.flatten()[:8], torch.tensor(golden["losses"]["ntxent_grad_first8"]), rtol=1e-4, atol=1e-7)
+
+
 def test_loss_gradient_known_answer(golden):
     S, T = _kat_inputs()
     Sg = S.clone().requires_grad_(True)
