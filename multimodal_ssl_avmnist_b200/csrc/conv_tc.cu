@@ -976,16 +976,14 @@ int launch_conv_tc_wgrad_ph(const void* x, const void* dz, float* dw, float* wor
 //   D[(kh, kw')][(ph, co)] = sum_xq x[.., 4xq + kw'] dz[co][.., 4xq + ph]   =>   dW[co][kh][kw] = sum_ph D[(kh, kw + ph)][(ph, co)]
 // -- a quarter of the K steps of the one-pixel-per-row formulation, at N = 32 / 128 instead of 8 / 32.
 //   cst: per (view, channel) constants float4 {a, b, ca, cb} prepared by wgrad_l0_consts_kernel from the BatchNorm tensors.
-// STAGED: the z tile is TMA-loaded densely (whole rows: the TMA engine moves strided 16-byte pieces at only ~16 B/clk per SM)
-// into a staging area and the transform warps scatter dz into the phase planes; otherwise z is loaded straight into the
-// phase planes by four strided maps and transformed in place.
+// (A variant that TMA-loads the z tile densely into a staging area and lets the transform warps scatter dz into the phase
+// planes was measured slower -- 0.73 ms with one CTA and 8 transform warps, 0.83 ms with two CTAs, against 0.55 ms -- and removed.)
 constexpr int L0F_ISS = 3;                       // MMA-issuer warps (K steps interleaved, one TMEM accumulator each)
 
-template <int COUT_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int CTAS_, bool STAGED_ = false>
+template <int COUT_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int CTAS_>
 struct L0FCfg {
     static constexpr int COUT = COUT_, HIN = HIN_, WIN = WIN_, KS = KS_, PAD = PAD_, BANDS = BANDS_, SLOTS = SLOTS_, CTAS = CTAS_;
-    static constexpr bool STAGED = STAGED_;
-    static constexpr int TW = (STAGED && CTAS_ == 1) ? 8 : 4;                    // transform warps
+    static constexpr int TW = 4;                                                 // transform warps
     static constexpr int THREADS = 32 * (1 + L0F_ISS + TW);
     static constexpr int P_OUT = COUT / 8, NTOT = 4 * COUT;
     static constexpr int WP = WIN + 2 * PAD, WQ = (WP + 3) / 4;                  // quad8 units per row
@@ -996,8 +994,7 @@ struct L0FCfg {
     static constexpr int X_BYTES = round_up(PLANE_X, 128), Z_BYTES = round_up(4 * P_OUT * PLANE_Z, 128);
     static constexpr int HBP = HB / 2, WOP = WO / 2;                             // pooled rows / columns of a band
     static constexpr int G_BYTES = round_up(P_OUT * HBP * WOP * 16, 128);
-    static constexpr int ZS_BYTES = STAGED ? round_up(P_OUT * HBZ * WO * 16, 128) : 0;   // dense z tile [octet][row][column]
-    static constexpr int SLOT = X_BYTES + ZS_BYTES + Z_BYTES + G_BYTES;
+    static constexpr int SLOT = X_BYTES + Z_BYTES + G_BYTES;
     static constexpr int STAGE_BYTES = 4 * COUT * KS * KS * 4;                   // end-of-kernel staging of the phase terms
     static constexpr int CST_OFF = SLOTS * SLOT, BAR_OFF = CST_OFF + COUT * 16 + TW * COUT * 4;
     static constexpr int SMEM = BAR_OFF + 256;
@@ -1009,8 +1006,7 @@ struct L0FCfg {
     static_assert(TCOLS * CTAS <= 512 && NTOT <= 256 && NTOT % 16 == 0, "TMEM columns / N");
     static_assert((SMEM + 1024) * CTAS <= 227 * 1024, "shared memory per SM");
     static_assert(STAGE_BYTES <= SLOT, "staging reuses the first slot");
-    static_assert((KSTEPS * 16 + 7 * WQ + 8 - HPB * WQ) * 16 <= ZS_BYTES + Z_BYTES, "x overrun must stay inside the slot");
-    static_assert(!STAGED || HBZ == HB, "staged z tile: whole bands");
+    static_assert((KSTEPS * 16 + 7 * WQ + 8 - HPB * WQ) * 16 <= Z_BYTES, "x overrun must stay inside the slot");
     static_assert((P_OUT * PLANE_Z) % 128 == 0, "TMA destinations (phase planes) must be 128-byte aligned");
     static_assert(KSTEPS >= L0F_ISS, "every issuer needs a K step");
 };
@@ -1065,19 +1061,14 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
             for (int i = i0; i < i1; ++i) {
                 const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
                 mbar_wait(empty_bar(slot), (use & 1) ^ 1);
-                mbar_expect_tx(full_bar(slot), C::PLANE_X + (C::STAGED ? C::P_OUT * C::HBZ * C::WO * 16 : 4 * C::P_OUT * C::PLANE_Z) +
-                                                   C::P_OUT * HBP * WOP * 16);
+                mbar_expect_tx(full_bar(slot), C::PLANE_X + 4 * C::P_OUT * C::PLANE_Z + C::P_OUT * HBP * WOP * 16);
                 const int n = i / C::BANDS, band = i % C::BANDS;
                 const uint32_t sa = smem0 + slot * SLOT;
                 tma_load_4d(sa, &tmap_x, full_bar(slot), 0, 0, band * C::HB - C::PAD, n);
-                if constexpr (C::STAGED) {          // dense tile (map 0 is the plain act8 map)
-                    tma_load_4d(sa + C::X_BYTES, &tmaps_z.m[0], full_bar(slot), 0, 0, band * C::HB, n * C::P_OUT);
-                } else {
 #pragma unroll
-                    for (int ph = 0; ph < 4; ++ph)  // columns x = 4*xq + ph of every z row -> plane group ph
-                        tma_load_4d(sa + C::X_BYTES + ph * C::P_OUT * C::PLANE_Z, &tmaps_z.m[ph], full_bar(slot), 0, 0, band * C::HB, n * C::P_OUT);
-                }
-                tma_load_4d(sa + C::X_BYTES + C::ZS_BYTES + C::Z_BYTES, &tmap_g, full_bar(slot), 0, 0, band * HBP, n * C::P_OUT);
+                for (int ph = 0; ph < 4; ++ph)      // columns x = 4*xq + ph of every z row -> plane group ph
+                    tma_load_4d(sa + C::X_BYTES + ph * C::P_OUT * C::PLANE_Z, &tmaps_z.m[ph], full_bar(slot), 0, 0, band * C::HB, n * C::P_OUT);
+                tma_load_4d(sa + C::X_BYTES + C::Z_BYTES, &tmap_g, full_bar(slot), 0, 0, band * HBP, n * C::P_OUT);
             }
         }
     } else if (warp <= L0F_ISS) {
@@ -1091,7 +1082,7 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
                 const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
                 mbar_wait(ready_bar(slot), use & 1);
                 tc_fence_after_sync();
-                const uint32_t xa = smem0 + slot * SLOT, za = xa + C::X_BYTES + C::ZS_BYTES;
+                const uint32_t xa = smem0 + slot * SLOT, za = xa + C::X_BYTES;
                 for (int ks = w; ks < C::KSTEPS; ks += L0F_ISS) {
                     const uint64_t bd = smem_desc(za + ks * 256, 128, C::PLANE_Z);
                     const uint64_t ad = smem_desc(xa + ks * 256, 128, C::WQ * 16);
@@ -1117,9 +1108,8 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
                 cur_view = view;
             }
             mbar_wait(full_bar(slot), use & 1);
-            uint8_t* zimg = smem + slot * SLOT + C::X_BYTES + C::ZS_BYTES;
-            const uint4* zst = reinterpret_cast<const uint4*>(smem + slot * SLOT + C::X_BYTES);
-            const uint4* gimg = reinterpret_cast<const uint4*>(smem + slot * SLOT + C::X_BYTES + C::ZS_BYTES + C::Z_BYTES);
+            uint8_t* zimg = smem + slot * SLOT + C::X_BYTES;
+            const uint4* gimg = reinterpret_cast<const uint4*>(smem + slot * SLOT + C::X_BYTES + C::Z_BYTES);
 #pragma unroll 1
             for (int o = 0; o < C::P_OUT; ++o) {
                 float4 c4[8];
@@ -1135,13 +1125,7 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
                     const int ph0 = 2 * (px & 1);
                     uint4* zp0 = reinterpret_cast<uint4*>(zimg + (size_t)(ph0 * C::P_OUT + o) * C::PLANE_Z) + (2 * py) * C::WQ + (px >> 1);
                     uint4* zp1 = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(zp0) + (size_t)C::P_OUT * C::PLANE_Z);
-                    uint4 raw[4];
-                    if constexpr (C::STAGED) {
-                        const uint4* zs = zst + ((size_t)o * C::HBZ + 2 * py) * C::WO + 2 * px;
-                        raw[0] = zs[0]; raw[1] = zs[1]; raw[2] = zs[C::WO]; raw[3] = zs[C::WO + 1];
-                    } else {
-                        raw[0] = zp0[0]; raw[1] = zp1[0]; raw[2] = zp0[C::WQ]; raw[3] = zp1[C::WQ];
-                    }
+                    const uint4 raw[4] = {zp0[0], zp1[0], zp0[C::WQ], zp1[C::WQ]};
                     const uint4 graw = gimg[o * (HBP * WOP) + e];
                     uint32_t outw[4][4];
 #pragma unroll
@@ -1295,19 +1279,12 @@ int launch_conv_tc_wgrad_l0_fused(const void* x, const void* z, const void* dp, 
         if (rc) return rc;
     }
     for (int ph = 0; ph < 4; ++ph) {        // fp16 data: same 2-byte elements, no conversion
-        if (C::STAGED) {                    // one dense map: whole rows of the act8 tensor
-            const uint64_t dims[4] = {8, (uint64_t)C::WO, (uint64_t)C::HO, (uint64_t)N * C::P_OUT};
-            const uint64_t strides[3] = {16, (uint64_t)C::WO * 16, (uint64_t)C::WO * C::HO * 16};
-            const uint32_t box[4] = {8, (uint32_t)C::WO, (uint32_t)C::HBZ, (uint32_t)C::P_OUT};
-            int rc = encode_tmap_bf16_4d(&tz.m[ph], z, dims, strides, box);
-            if (rc) return rc;
-        } else {                            // columns 4*i + ph
-            const uint64_t dims[4] = {8, (uint64_t)C::WO / 4, (uint64_t)C::HO, (uint64_t)N * C::P_OUT};
-            const uint64_t strides[3] = {64, (uint64_t)C::WO * 16, (uint64_t)C::WO * C::HO * 16};
-            const uint32_t box[4] = {8, (uint32_t)C::WQ, (uint32_t)C::HBZ, (uint32_t)C::P_OUT};
-            int rc = encode_tmap_bf16_4d(&tz.m[ph], reinterpret_cast<const uint8_t*>(z) + 16 * ph, dims, strides, box);
-            if (rc) return rc;
-        }
+        // columns 4*i + ph
+        const uint64_t dims[4] = {8, (uint64_t)C::WO / 4, (uint64_t)C::HO, (uint64_t)N * C::P_OUT};
+        const uint64_t strides[3] = {64, (uint64_t)C::WO * 16, (uint64_t)C::WO * C::HO * 16};
+        const uint32_t box[4] = {8, (uint32_t)C::WQ, (uint32_t)C::HBZ, (uint32_t)C::P_OUT};
+        int rc = encode_tmap_bf16_4d(&tz.m[ph], reinterpret_cast<const uint8_t*>(z) + 16 * ph, dims, strides, box);
+        if (rc) return rc;
     }
     {
         const uint64_t dims[4] = {8, (uint64_t)C::WOP, (uint64_t)(C::HO / 2), (uint64_t)N * C::P_OUT};
@@ -1408,7 +1385,7 @@ static int wgrad_tc_dispatch(const void* x, const void* dz, float* dw, float* wo
 
 // fused first-layer backward (Cin = 1): geometries of the first layers of the three encoders
 //                    COUT HIN  WIN KS PAD BANDS SLOTS CTAS
-using WgF_A0 = L0FCfg<8, 112, 112, 5, 2, 7, 2, 2>;         // (STAGED measured slower: 0.73 ms with one CTA / 8 transform warps, 0.83 ms with two CTAs, vs 0.55 ms)
+using WgF_A0 = L0FCfg<8, 112, 112, 5, 2, 7, 2, 2>;
 using WgF_I0 = L0FCfg<32, 28, 28, 5, 2, 1, 2, 1>;
 using WgF_S0 = L0FCfg<32, 28, 28, 3, 1, 1, 2, 1>;
 
