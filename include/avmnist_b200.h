@@ -78,12 +78,15 @@ int b200_center_apply(float* center, const float* colsum, int D, int64_t n_rows,
  *   b200_infonce_fwd_bwd   -- infoNCE_loss, models/dino.py:1091-1128: sim = normalize(a) normalize(b)^T / temp,
  *                             0.5*(CE(sim, I) + CE(sim^T, I)); the [B,B] matrix is never written to HBM.
  *                             work: float[b200_infonce_work_floats(B, D)].
- * loss_out[0] receives the scalar (written, not accumulated).
+ * loss_out[0] receives the scalar (written, not accumulated).  The scalar is a FIXED-ORDER sum (per-block partials added by
+ * block index by the last block to finish): bit-identical from run to run, like the reference's deterministic=True
+ * (run_dino.py:364).  work: float[b200_loss_work_floats(B)] scratch for those partials (contents irrelevant on entry).
  * ---------------------------------------------------------------------------------------------------------- */
+int64_t b200_loss_work_floats(int B);
 int b200_mse_align_fwd_bwd(const float* a, const float* b, int B, int D, float grad_scale, float* grad_a,
-                           float* grad_b, float* loss_out, void* stream);
+                           float* grad_b, float* loss_out, float* work, void* stream);
 int b200_ce_fwd_bwd(const float* logits, const int64_t* labels, int B, int C, float grad_scale, float* grad_logits,
-                    float* loss_out, void* stream);
+                    float* loss_out, float* work, void* stream);
 int64_t b200_infonce_work_floats(int B, int D);
 int b200_infonce_fwd_bwd(const float* a, const float* b, int B, int D, float temperature, float grad_scale,
                          float* grad_a, float* grad_b, float* loss_out, float* work, void* stream);
@@ -100,7 +103,7 @@ int b200_ntxent_fwd_bwd(const float* reps, int N, int D, float temperature, floa
                         float* work, void* stream);
 /* UniModalDINOLightning._cosine_consistency_loss, models/dino.py:1575-1594: emb [V,B,D] */
 int b200_cosine_consistency_fwd_bwd(const float* emb, int V, int B, int D, float grad_scale, float* grad_emb,
-                                    float* loss_out, void* stream);
+                                    float* loss_out, float* work, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Multi-crop augmentation  --  MultiModalAugmentation.__call__, utils/get_data.py:233-257 and its chains

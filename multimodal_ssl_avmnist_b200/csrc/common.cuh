@@ -48,6 +48,38 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// ---- fixed-order reductions of one float per warp / per block (run-to-run deterministic: no float atomics) ----
+// Sum of the warps' values (v: the warp's value, valid in lane 0); result valid in thread 0.  All threads of the block must call.
+__device__ __forceinline__ float block_sum_ordered(float v) {
+    __shared__ float s_warp[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) s_warp[warp] = v;
+    __syncthreads();
+    float a = 0.f;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < nw; ++w) a += s_warp[w];
+    __syncthreads();
+    return a;
+}
+// Grid-wide sum of one float per block (valid in thread 0) in BLOCK ORDER: every block stores its partial and draws a ticket; the
+// block that draws the last one adds the partials by index and writes out[0].  work[0] = ticket (unsigned, 0 at launch, left 0),
+// work[1 + b] = partial of block b: work needs 1 + gridDim.x floats.
+__device__ __forceinline__ void grid_sum_ordered(float block_partial, float* work, float* out) {
+    if (threadIdx.x == 0) {
+        volatile float* parts = work + 1;
+        parts[blockIdx.x] = block_partial;
+        __threadfence();
+        const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(work), 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            float a = 0.f;
+            for (unsigned b = 0; b < gridDim.x; ++b) a += parts[b];
+            out[0] = a;
+            *reinterpret_cast<volatile unsigned*>(work) = 0u;
+        }
+    }
+}
+
 // ---- Philox4x32-10 (counter-based RNG; same construction as curand/torch, used with our own key/counter map) ----
 struct Philox {
     uint32_t key[2];

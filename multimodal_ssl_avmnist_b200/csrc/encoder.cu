@@ -324,7 +324,7 @@ struct Wg1Cfg {
     static constexpr int TIW = NSTRIP * SX + K - 1;
     static constexpr int X_FLOATS = TIH * TIW;
     static constexpr int RED_FLOATS = COUT * (K * K + 1);
-    static constexpr size_t SMEM = (size_t)(X_FLOATS + RED_FLOATS) * sizeof(float);
+    static constexpr size_t SMEM = (size_t)(X_FLOATS + RED_FLOATS + THREADS) * sizeof(float);      // + one staging float per thread
 };
 
 template <int COUT, int H, int W, int K, int PAD, int TY, int SX>
@@ -378,13 +378,20 @@ conv_wgrad_c1_kernel(const float* __restrict__ x, const float* __restrict__ dz, 
         }
     }
     __syncthreads();
-    // block reduction: warp-level first (lanes of a warp mostly share `co`), then shared-memory atomics
-    if (active) {
+    // block reduction in a FIXED order (run-to-run deterministic, like the reference's deterministic=True): tap by tap every
+    // thread stages its accumulator, then one thread per output channel adds the NPOS positions in index order
+    float* s_stage = s_red + C::RED_FLOATS;
 #pragma unroll
-        for (int a = 0; a < K * K; ++a) atomicAdd(&s_red[co * (K * K + 1) + a], acc[a]);
-        atomicAdd(&s_red[co * (K * K + 1) + K * K], dbacc);
+    for (int a = 0; a <= K * K; ++a) {
+        s_stage[tid] = active ? (a < K * K ? acc[a < K * K ? a : 0] : dbacc) : 0.f;
+        __syncthreads();
+        if (tid < COUT) {
+            float sum = 0.f;
+            for (int p = 0; p < C::NPOS; ++p) sum += s_stage[tid * C::NPOS + p];
+            s_red[tid * (K * K + 1) + a] = sum;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     for (int i = tid; i < COUT * K * K; i += C::THREADS) {
         const int c = i / (K * K), a = i % (K * K);
         part[(size_t)blockIdx.x * COUT * K * K + i] = s_red[c * (K * K + 1) + a];

@@ -172,7 +172,7 @@ __global__ void center_update_kernel(float* __restrict__ center, const float* __
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mse_align_kernel(const float* __restrict__ a, const float* __restrict__ b, int B, int D,
                                                         float gscale, float* __restrict__ ga, float* __restrict__ gb,
-                                                        float* __restrict__ loss_out) {
+                                                        float* __restrict__ loss_out, float* __restrict__ work) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float inv_n = 1.0f / ((float)B * (float)D);
     float lacc = 0.f;
@@ -204,13 +204,13 @@ __global__ void __launch_bounds__(256) mse_align_kernel(const float* __restrict_
             gb[(size_t)r * D + k] = (-g - y * dotb) / db;
         }
     }
-    lacc = warp_sum(lacc);
-    if (lane == 0) atomicAdd(loss_out, lacc * inv_n);
+    grid_sum_ordered(block_sum_ordered(warp_sum(lacc) * inv_n), work, loss_out);
 }
 
 // 10-way (C <= 32) cross entropy, mean over rows; one thread per row.
 __global__ void __launch_bounds__(128) ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int B, int C,
-                                                 float gscale, float* __restrict__ g, float* __restrict__ loss_out) {
+                                                 float gscale, float* __restrict__ g, float* __restrict__ loss_out,
+                                                 float* __restrict__ work) {
     float lacc = 0.f;
     const float invB = 1.0f / (float)B;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < B; r += gridDim.x * blockDim.x) {
@@ -224,8 +224,7 @@ __global__ void __launch_bounds__(128) ce_kernel(const float* __restrict__ logit
         lacc += lse - __ldg(lp + y);
         for (int k = 0; k < C; ++k) g[(size_t)r * C + k] = (expf(__ldg(lp + k) - lse) - (k == y ? 1.f : 0.f)) * invB * gscale;
     }
-    lacc = warp_sum(lacc);
-    if ((threadIdx.x & 31) == 0) atomicAdd(loss_out, lacc * invB);
+    grid_sum_ordered(block_sum_ordered(warp_sum(lacc) * invB), work, loss_out);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -369,7 +368,7 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
 // loss = sum_i [log rowsum_i + log colsum_i + 2/temp - 2 sim_ii] / (2B);  one warp per row for the diagonal dot
 __global__ void __launch_bounds__(256) infonce_loss_kernel(const float* __restrict__ ah, const float* __restrict__ bh,
                                                            const float* __restrict__ rowsum, const float* __restrict__ colsum, int B,
-                                                           int D, float inv_temp, float* __restrict__ loss_out) {
+                                                           int D, float inv_temp, float* __restrict__ loss_out, float* __restrict__ work) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float acc = 0.f;
     for (int r = blockIdx.x * 8 + warp; r < B; r += gridDim.x * 8) {
@@ -378,12 +377,12 @@ __global__ void __launch_bounds__(256) infonce_loss_kernel(const float* __restri
         d = warp_sum(d);
         if (lane == 0) acc += logf(rowsum[r]) + logf(colsum[r]) + 2.f * inv_temp - 2.f * d * inv_temp;
     }
-    if (lane == 0) atomicAdd(loss_out, acc / (2.f * (float)B));
+    grid_sum_ordered(block_sum_ordered(acc / (2.f * (float)B)), work, loss_out);
 }
 
 // NT-Xent: loss = sum_i [log rowsum_i + 1/temp - sim(i, partner(i))] / N  (rowsum excludes the self-similarity)
 __global__ void __launch_bounds__(256) ntxent_loss_kernel(const float* __restrict__ rh, const float* __restrict__ rowsum, int N, int D,
-                                                          float inv_temp, float* __restrict__ loss_out) {
+                                                          float inv_temp, float* __restrict__ loss_out, float* __restrict__ work) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = N / 2;
     float acc = 0.f;
     for (int r = blockIdx.x * 8 + warp; r < N; r += gridDim.x * 8) {
@@ -393,7 +392,7 @@ __global__ void __launch_bounds__(256) ntxent_loss_kernel(const float* __restric
         d = warp_sum(d);
         if (lane == 0) acc += logf(rowsum[r]) + inv_temp - d * inv_temp;
     }
-    if (lane == 0) atomicAdd(loss_out, acc / (float)N);
+    grid_sum_ordered(block_sum_ordered(acc / (float)N), work, loss_out);
 }
 
 // backward through the row normalisation: dx = (dxh - xh <xh, dxh>) / denom
@@ -490,7 +489,8 @@ __global__ void __launch_bounds__(256) infonce_combine_kernel(const float* __res
 // One CTA (128 threads) per sample; the V normalised vectors sit in shared memory.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) cosine_consistency_kernel(const float* __restrict__ emb, int V, int B, int D, float gscale,
-                                                                 float* __restrict__ grad, float* __restrict__ loss_out) {
+                                                                 float* __restrict__ grad, float* __restrict__ loss_out,
+                                                                 float* __restrict__ work) {
     extern __shared__ float sm[];          // e[V][D], ge[V][D], den[V], simm[V*V]
     float* e = sm;
     float* ge = e + (size_t)V * D;
@@ -519,11 +519,12 @@ __global__ void __launch_bounds__(128) cosine_consistency_kernel(const float* __
         if (lane == 0) simm[pr] = d;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    {
         float l = 0.f;
-        for (int i = 0; i < V; ++i)
-            for (int j = i + 1; j < V; ++j) l += (1.f - simm[i * V + j]) * (1.f - simm[i * V + j]);
-        atomicAdd(loss_out, l * coef);
+        if (threadIdx.x == 0)
+            for (int i = 0; i < V; ++i)
+                for (int j = i + 1; j < V; ++j) l += (1.f - simm[i * V + j]) * (1.f - simm[i * V + j]);
+        grid_sum_ordered(l * coef, work, loss_out);
     }
     // d loss / d e_i = sum_{j != i} -2 (1 - s_ij) e_j * coef
     for (int v = warp; v < V; v += nw) {
@@ -601,22 +602,24 @@ int b200_center_apply(float* center, const float* colsum, int D, int64_t n_rows,
     return launch_status("center_apply");
 }
 
+int64_t b200_loss_work_floats(int B) { return (int64_t)(B > 0 ? B : 0) + 1025; }
+
 int b200_mse_align_fwd_bwd(const float* a, const float* b, int B, int D, float grad_scale, float* grad_a, float* grad_b,
-                           float* loss_out, void* stream) {
-    B200_REQUIRE(a && b && grad_a && grad_b && loss_out && B > 0 && D > 0, B200_E_ARG, "mse_align: bad arguments");
+                           float* loss_out, float* work, void* stream) {
+    B200_REQUIRE(a && b && grad_a && grad_b && loss_out && work && B > 0 && D > 0, B200_E_ARG, "mse_align: bad arguments");
     cudaStream_t st = as_stream(stream);
-    cudaMemsetAsync(loss_out, 0, sizeof(float), st);
-    mse_align_kernel<<<rows_grid(B), 256, 0, st>>>(a, b, B, D, grad_scale, grad_a, grad_b, loss_out);
+    cudaMemsetAsync(work, 0, sizeof(float), st);          // the ticket of the fixed-order grid sum
+    mse_align_kernel<<<rows_grid(B), 256, 0, st>>>(a, b, B, D, grad_scale, grad_a, grad_b, loss_out, work);
     return launch_status("mse_align_fwd_bwd");
 }
 
 int b200_ce_fwd_bwd(const float* logits, const int64_t* labels, int B, int C, float grad_scale, float* grad_logits,
-                    float* loss_out, void* stream) {
-    B200_REQUIRE(logits && labels && grad_logits && loss_out && B > 0 && C > 0, B200_E_ARG, "ce: bad arguments");
+                    float* loss_out, float* work, void* stream) {
+    B200_REQUIRE(logits && labels && grad_logits && loss_out && work && B > 0 && C > 0, B200_E_ARG, "ce: bad arguments");
     cudaStream_t st = as_stream(stream);
-    cudaMemsetAsync(loss_out, 0, sizeof(float), st);
+    cudaMemsetAsync(work, 0, sizeof(float), st);
     int grid = (B + 127) / 128;
-    ce_kernel<<<grid, 128, 0, st>>>(logits, labels, B, C, grad_scale, grad_logits, loss_out);
+    ce_kernel<<<grid, 128, 0, st>>>(logits, labels, B, C, grad_scale, grad_logits, loss_out, work);
     return launch_status("ce_fwd_bwd");
 }
 
@@ -645,12 +648,12 @@ int b200_infonce_fwd_bwd(const float* a, const float* b, int B, int D, float tem
         cudaFuncSetAttribute(infonce_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         attr_done = true;
     }
-    cudaMemsetAsync(loss_out, 0, sizeof(float), st);
+    cudaMemsetAsync(dah, 0, sizeof(float), st);           // dah is free until the gradient kernels: ticket + partials of the loss sum
     normalize_rows_kernel<<<rg, 256, 0, st>>>(a, B, D, ah, dena);
     normalize_rows_kernel<<<rg, 256, 0, st>>>(b, B, D, bh, denb);
     infonce_rows_kernel<false><<<tg, 256, sm_f, st>>>(ah, bh, B, D, inv_temp, nullptr, nullptr, 0.f, rowsum, 0);
     infonce_rows_kernel<false><<<tg, 256, sm_f, st>>>(bh, ah, B, D, inv_temp, nullptr, nullptr, 0.f, colsum, 0);
-    infonce_loss_kernel<<<rg, 256, 0, st>>>(ah, bh, rowsum, colsum, B, D, inv_temp, loss_out);
+    infonce_loss_kernel<<<rg, 256, 0, st>>>(ah, bh, rowsum, colsum, B, D, inv_temp, loss_out, dah);
     const float coef = 1.0f / (float)B;
     infonce_rows_kernel<true><<<tg, 256, sm_g, st>>>(ah, bh, B, D, inv_temp, rowsum, colsum, coef, dah, 0);
     infonce_rows_kernel<true><<<tg, 256, sm_g, st>>>(bh, ah, B, D, inv_temp, colsum, rowsum, coef, dbh, 0);
@@ -684,8 +687,8 @@ int b200_ntxent_fwd_bwd(const float* reps, int N, int D, float temperature, floa
     }
     normalize_rows_kernel<<<rg, 256, 0, st>>>(reps, N, D, rh, den);
     infonce_rows_kernel<false><<<tg, 256, sm_f, st>>>(rh, rh, N, D, inv_temp, nullptr, nullptr, 0.f, rowsum, N / 2);
-    cudaMemsetAsync(loss_out, 0, sizeof(float), st);
-    ntxent_loss_kernel<<<rg, 256, 0, st>>>(rh, rowsum, N, D, inv_temp, loss_out);
+    cudaMemsetAsync(drh, 0, sizeof(float), st);           // drh is free until the gradient kernel: ticket + partials of the loss sum
+    ntxent_loss_kernel<<<rg, 256, 0, st>>>(rh, rowsum, N, D, inv_temp, loss_out, drh);
     // dL/dS_ij = (e_ij / rowsum_i - [j == partner(i)]) / N, and S = R R^T is symmetric in R:
     // dL/dR_hat = (H + H^T) R_hat / temp with (H + H^T)_ij = (e_ij/rs_i + e_ij/rs_j) / N - 2 [j == partner(i)] / N
     infonce_rows_kernel<true><<<tg, 256, sm_g, st>>>(rh, rh, N, D, inv_temp, rowsum, rowsum, 2.0f / (float)N, drh, N / 2);
@@ -729,7 +732,7 @@ int b200_infonce_fwd_bwd_tc(const float* a, const float* b, int B, int D, float 
     __nv_bfloat16* YTb = YTa + (size_t)2 * D * ldE;     // built from bh / colsum: B operand of the dAh GEMM
     const float inv_temp = 1.0f / temperature;
     const int rg = rows_grid(B);
-    cudaMemsetAsync(loss_out, 0, sizeof(float), st);
+    cudaMemsetAsync(dah, 0, sizeof(float), st);           // dah is free until the combine kernels: ticket + partials of the loss sum
     normalize_rows_kernel<<<rg, 256, 0, st>>>(a, B, D, ah, dena);
     normalize_rows_kernel<<<rg, 256, 0, st>>>(b, B, D, bh, denb);
     const int sg = (int)(((size_t)B * D + 255) / 256 < (size_t)sm_count() * 8 ? ((size_t)B * D + 255) / 256 : (size_t)sm_count() * 8);
@@ -741,7 +744,7 @@ int b200_infonce_fwd_bwd_tc(const float* a, const float* b, int B, int D, float 
     if (rc) return rc;
     sum_parts_kernel<<<(B + 255) / 256, 256, 0, st>>>(rowpart, (int)nt, B, rowsum);
     sum_parts_kernel<<<(B + 255) / 256, 256, 0, st>>>(colpart, (int)nt, B, colsum);
-    infonce_loss_kernel<<<rg, 256, 0, st>>>(ah, bh, rowsum, colsum, B, D, inv_temp, loss_out);
+    infonce_loss_kernel<<<rg, 256, 0, st>>>(ah, bh, rowsum, colsum, B, D, inv_temp, loss_out, dah);
     const dim3 tg((B + 31) / 32, (D + 31) / 32);
     infonce_build_yt_kernel<<<tg, 256, 0, st>>>(ah, rowsum, B, D, (int)ldE, YTa);
     infonce_build_yt_kernel<<<tg, 256, 0, st>>>(bh, colsum, B, D, (int)ldE, YTb);
@@ -759,13 +762,13 @@ int b200_infonce_fwd_bwd_tc(const float* a, const float* b, int B, int D, float 
 }
 
 int b200_cosine_consistency_fwd_bwd(const float* emb, int V, int B, int D, float grad_scale, float* grad_emb, float* loss_out,
-                                    void* stream) {
-    B200_REQUIRE(emb && grad_emb && loss_out && V > 1 && V <= 16 && B > 0 && D > 0, B200_E_ARG, "cosine_consistency: bad arguments");
+                                    float* work, void* stream) {
+    B200_REQUIRE(emb && grad_emb && loss_out && work && V > 1 && V <= 16 && B > 0 && D > 0, B200_E_ARG, "cosine_consistency: bad arguments");
     cudaStream_t st = as_stream(stream);
     size_t smem = ((size_t)2 * V * D + V + (size_t)V * V) * sizeof(float);
     B200_REQUIRE(smem <= 48 * 1024, B200_E_SHAPE, "cosine_consistency: V*D too large");
-    cudaMemsetAsync(loss_out, 0, sizeof(float), st);
-    cosine_consistency_kernel<<<B, 128, smem, st>>>(emb, V, B, D, grad_scale, grad_emb, loss_out);
+    cudaMemsetAsync(work, 0, sizeof(float), st);
+    cosine_consistency_kernel<<<B, 128, smem, st>>>(emb, V, B, D, grad_scale, grad_emb, loss_out, work);
     return launch_status("cosine_consistency_fwd_bwd");
 }
 

@@ -400,6 +400,7 @@ class DinoStepEngine:
         w["t_colmean"] = e(Vg, P)
         w["colsum"] = e(P + 1)
         w["loss"] = torch.zeros(4, device=dev)             # [dino, aux, cosine, total]
+        w["loss_work"] = torch.zeros(int(ops._lib_().b200_loss_work_floats(B)), device=dev)    # partials of the fixed-order loss sums
         if self.mode != "default":
             out = 10 if self.mode == "semi_supervised" else P
             for m in ("aux_image", "aux_audio"):
@@ -882,14 +883,14 @@ class DinoStepEngine:
         loss = w["loss"]
         oi, oa = w["aux_image.out"], w["aux_audio.out"]
         if self.mode == "semi_supervised":
-            ops.ce_fwd_bwd(oi, labels, w["aux_image.d.out"], loss[1:2], grad_scale=self.alpha)
-            ops.ce_fwd_bwd(oa, labels, w["aux_audio.d.out"], loss[2:3], grad_scale=self.alpha)
+            ops.ce_fwd_bwd(oi, labels, w["aux_image.d.out"], loss[1:2], grad_scale=self.alpha, work=w["loss_work"])
+            ops.ce_fwd_bwd(oa, labels, w["aux_audio.d.out"], loss[2:3], grad_scale=self.alpha, work=w["loss_work"])
             loss[1:2].add_(loss[2:3])
             loss[2:3].zero_()
         elif self.mode == "infonce":
             ops.infonce_fwd_bwd(oi, oa, w["aux_image.d.out"], w["aux_audio.d.out"], loss[1:2], w["infonce_work"], grad_scale=self.alpha, tc=self.lin_tc)
         elif self.mode == "mse":
-            ops.mse_align_fwd_bwd(oi, oa, w["aux_image.d.out"], w["aux_audio.d.out"], loss[1:2], grad_scale=self.alpha)
+            ops.mse_align_fwd_bwd(oi, oa, w["aux_image.d.out"], w["aux_audio.d.out"], loss[1:2], grad_scale=self.alpha, work=w["loss_work"])
 
     def backward_pass(self, w, d_proj=None, d_aux=None):
         """Backward from the gradient w.r.t. the student projections (default: the fused loss's own w['d.proj']) and, in the
@@ -905,7 +906,8 @@ class DinoStepEngine:
         d_feat = w["d.feat"]
         self._head_bwd(w, "s", "head.", feat_s, d_proj, w["s.hh"], w["s.g"], w["d.g"], w["d.hh"], d_feat, w["s.hmask"], self.dropout)
         if self.cosine_loss_alpha > 0:
-            ops.cosine_consistency_fwd_bwd(feat_s.view(V, B, O), w["d.emb"].view(V, B, O), w["loss"][2:3], grad_scale=self.cosine_loss_alpha)
+            ops.cosine_consistency_fwd_bwd(feat_s.view(V, B, O), w["d.emb"].view(V, B, O), w["loss"][2:3], grad_scale=self.cosine_loss_alpha,
+                                           work=w["loss_work"])
             d_feat.add_(w["d.emb"])
         if multi:
             d_cat, d_h1 = w["d.cat"], w["d.h1"]

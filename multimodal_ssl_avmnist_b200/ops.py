@@ -130,16 +130,31 @@ def center_apply(center, colsum, n_rows, m_c):
     _lib.check(_lib_().b200_center_apply(_ptr(center, F32), _ptr(colsum, F32), colsum.numel(), n_rows, m_c, 1 - m_c, _stream()), "center_apply")
 
 
-def mse_align_fwd_bwd(a, b, grad_a, grad_b, loss_out, grad_scale=1.0):
+_LOSS_WORK = {}
+
+
+def _loss_work(device, B):
+    """Scratch for the fixed-order loss sums (per-block partials + ticket), one per device and stream."""
+    need = int(_lib_().b200_loss_work_floats(B))
+    key = (device, _stream())
+    work = _LOSS_WORK.get(key)
+    if work is None or work.numel() < need:
+        work = _LOSS_WORK[key] = torch.zeros(need, dtype=F32, device=device)
+    return work
+
+
+def mse_align_fwd_bwd(a, b, grad_a, grad_b, loss_out, grad_scale=1.0, work=None):
     B, D = a.shape
+    work = _loss_work(a.device, B) if work is None else work
     _lib.check(_lib_().b200_mse_align_fwd_bwd(_ptr(a, F32), _ptr(b, F32), B, D, grad_scale, _ptr(grad_a, F32), _ptr(grad_b, F32),
-                                              _ptr(loss_out, F32), _stream()), "mse_align_fwd_bwd")
+                                              _ptr(loss_out, F32), _ptr(work, F32), _stream()), "mse_align_fwd_bwd")
 
 
-def ce_fwd_bwd(logits, labels, grad_logits, loss_out, grad_scale=1.0):
+def ce_fwd_bwd(logits, labels, grad_logits, loss_out, grad_scale=1.0, work=None):
     B, Cc = logits.shape
+    work = _loss_work(logits.device, B) if work is None else work
     _lib.check(_lib_().b200_ce_fwd_bwd(_ptr(logits, F32), _ptr(labels, I64), B, Cc, grad_scale, _ptr(grad_logits, F32),
-                                       _ptr(loss_out, F32), _stream()), "ce_fwd_bwd")
+                                       _ptr(loss_out, F32), _ptr(work, F32), _stream()), "ce_fwd_bwd")
 
 
 def infonce_work_floats(B, D, tc=False):
@@ -165,10 +180,11 @@ def ntxent_fwd_bwd(reps, grad, loss_out, work, temperature=0.07, grad_scale=1.0)
                                            _ptr(work, F32), _stream()), "ntxent_fwd_bwd")
 
 
-def cosine_consistency_fwd_bwd(emb, grad_emb, loss_out, grad_scale=1.0):
+def cosine_consistency_fwd_bwd(emb, grad_emb, loss_out, grad_scale=1.0, work=None):
     V, B, D = emb.shape
+    work = _loss_work(emb.device, B) if work is None else work
     _lib.check(_lib_().b200_cosine_consistency_fwd_bwd(_ptr(emb, F32), V, B, D, grad_scale, _ptr(grad_emb, F32), _ptr(loss_out, F32),
-                                                       _stream()), "cosine_consistency_fwd_bwd")
+                                                       _ptr(work, F32), _stream()), "cosine_consistency_fwd_bwd")
 
 
 # ---- augmentation ------------------------------------------------------------------------------------------

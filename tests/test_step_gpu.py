@@ -1,10 +1,9 @@
 """GPU parity of the whole training step (engine -> C ABI -> CUDA) against the CPU oracle and against the
 golden numbers produced by the imported reference (tests/golden/golden.json).
 
-Tolerances: everything is fp32; the CUDA kernels sum in a different order than ATen, so step 0 is compared at
-2e-4 relative (gradients) / 1e-5 (loss, EMA, Adam); from step 1 on, max-pool arg-max flips triggered by the
-+-lr Adam noise on BatchNorm-cancelled biases allow 1e-2 on a few gradient tensors (same effect separates the
-oracle from the reference itself, see tests/test_oracle_golden.py)."""
+Tolerances: everything is fp32; the CUDA kernels sum in a different order than ATen, so every step is compared at
+3e-4 relative (gradients) / 1e-5 (loss, EMA, Adam) FROM IDENTICAL STATE (the engine is re-synchronised to the oracle
+between steps).  The unimodal and bf16 product-path tests come first so that they always run under `pytest -x`."""
 import re
 
 import pytest
@@ -35,76 +34,6 @@ def _load_state(eng, st):
 
 def _gpu_masks(m):
     return {k: v.to(torch.uint8).to(DEV) for k, v in m.items()}
-
-
-@pytest.mark.parametrize("mode", ["default", "semi_supervised", "infonce", "mse"])
-def test_step_vs_oracle_and_reference(mode, golden):
-    fx = golden["steps"][mode]
-    B = fx["B"]
-    st = R.CentralDinoState(seed=fx["seed"], mode=mode)
-    eng = DinoStepEngine(kind="multi_central", mode=mode, device=DEV, precision="fp32")
-    _load_state(eng, st)
-    for it, rec in enumerate(fx["steps"]):
-        img, aud = views_to_vb(*synth_views(B, seed=100 + it))
-        masks = make_masks(seed=200 + it, V=6, Vg=2, B=B, E=256, hidden=512)
-        raw = labels = None
-        graw = glabels = None
-        if mode != "default":
-            image, audio, labels = synth_raw(B, seed=300 + it)
-            raw = (image, audio)
-            graw, glabels = (image[:, 0].to(DEV).contiguous(), audio[:, 0].to(DEV).contiguous()), labels.to(DEV)
-        want = R.central_dino_step(st, img, aud, masks, raw=raw, labels=labels)
-        loss = eng.forward_backward(img[:, :, 0].to(DEV).contiguous(), aud[:, :, 0].to(DEV).contiguous(), masks=_gpu_masks(masks),
-                                    raw=graw, labels=glabels)
-        torch.cuda.synchronize()
-        total = float(loss[3])
-        assert abs(total - float(want["loss"])) < 1e-5 * max(1.0, abs(float(want["loss"]))), (mode, it, total, float(want["loss"]))
-        assert abs(total - rec["loss"]) < 2e-5 * max(1.0, abs(rec["loss"])), (mode, it, total, rec["loss"])     # the reference itself
-        # outputs
-        assert _rel(eng._ws[B]["s.proj"].view(6, B, -1), want["student_out"]) < (2e-5 if it == 0 else 2e-3)
-        # gradients
-        gtol = 3e-4 if it == 0 else 2e-2
-        groups = [("enc.", want["grads"]["student"], "model.student."), ("head.", want["grads"]["student_head"], "model.student_projection.")]
-        if mode != "default":
-            nm = ("image_classifier", "audio_classifier") if mode == "semi_supervised" else ("image_projection_head", "audio_projection_head")
-            groups += [("aux_image.", want["grads"]["image"], f"model.{nm[0]}."), ("aux_audio.", want["grads"]["audio"], f"model.{nm[1]}.")]
-        for prefix, gd, refprefix in groups:
-            for k, g in gd.items():
-                mine = eng.G[prefix + k]
-                if _cancelled(k):
-                    assert float(mine.abs().sum()) < 1e-3, (k, float(mine.abs().sum()))
-                    continue
-                assert _rel(mine, g) < gtol, (mode, it, k, _rel(mine, g))
-                ok, why = summaries_close(summarize(mine), rec["grads"][refprefix + k], gtol, 1e-7)
-                assert ok, (mode, it, k, why)
-        # EMA (before the optimizer) and Adam
-        eng.update_teacher()
-        eng.optimizer_step()
-        ttol = 1e-9 if it == 0 else 3e-6
-        for k, v in st.teacher.items():
-            d = float((eng.T["enc." + k].cpu() - v).abs().max())
-            assert d <= ttol, ("teacher", k, d)
-        if it == 0:        # identical inputs -> the EMA is bit-exact
-            for k, v in st.teacher_head.items():
-                assert torch.equal(eng.T["head." + k].cpu(), v), k
-        for k, v in st.student.items():
-            diff = (eng.S["enc." + k].cpu() - v).abs()
-            if _cancelled(k):
-                assert float(diff.max()) <= 2.5e-4 * (it + 1), ("student after adam", k, float(diff.max()))
-                continue
-            # Adam turns any gradient into a ~lr-sized step, so elements whose gradient is rounding noise (dead units)
-            # may differ by up to 2*lr; everything else must agree to fp32 rounding
-            assert float(diff.max()) <= 2.5e-4 * (it + 1), ("student after adam (max)", k, float(diff.max()))
-            assert float(diff.mean()) <= (2e-7 if it == 0 else 2e-5), ("student after adam (mean)", k, float(diff.mean()))
-        # centre and BatchNorm running statistics
-        assert _rel(eng.center, st.center) < 1e-5
-        btol = 1e-5 if it == 0 else 2e-3
-        for k in ("image_encoder.0.bn1", "image_encoder.0.bn2", "audio_encoder.0.bn1", "audio_encoder.0.bn4"):
-            assert _rel(eng.bn_s["enc." + k].running_mean, st.student_buf[k + ".running_mean"]) < btol, k
-            assert _rel(eng.bn_s["enc." + k].running_var, st.student_buf[k + ".running_var"]) < btol, k
-            assert _rel(eng.bn_t["enc." + k].running_var, st.teacher_buf[k + ".running_var"]) < btol, k
-            assert int(eng.bn_s["enc." + k].num_batches_tracked) == int(st.student_buf[k + ".num_batches_tracked"])
-        assert _rel(eng.bn_s["head.mlp.1"].running_var, st.student_head_buf["mlp.1.running_var"]) < btol
 
 
 @pytest.mark.parametrize("key,alpha", [("unimodal_image_simple", 0.0), ("unimodal_image_simple_cosine", 0.3)])
@@ -213,6 +142,129 @@ def test_step_bf16_tensor_core_path_vs_oracle(mode, golden):
         assert torch.equal(eng.T["head." + k].cpu(), v), k
 
 
+def _sync_engine_to_oracle(eng, st):
+    """Copies the oracle's COMPLETE training state into the engine: parameters, Adam moments + step, BatchNorm running statistics,
+    centre.  Used before every step after the first, so that each step is compared from identical state (a free-running
+    trajectory amplifies last-bit differences through max-pool arg-max flips and Adam's sign-like first steps)."""
+    _load_state(eng, st)
+    M, V = eng.student.views(eng.exp_avg), eng.student.views(eng.exp_avg_sq)
+    eng.exp_avg.zero_()
+    eng.exp_avg_sq.zero_()
+    for gname, prefix in (("student", "enc."), ("student_head", "head."), ("image", "aux_image."), ("audio", "aux_audio.")):
+        for key, val in st.adam.get(gname, {}).items():
+            if isinstance(key, tuple):
+                (M if key[0] == "m" else V)[prefix + key[1]].copy_(val.to(DEV))
+    eng.step_count = int(st.adam.get("step", 0))
+    eng.center.copy_(st.center.to(DEV))
+    tables = [(eng.bn_s, "enc.", st.student_buf), (eng.bn_t, "enc.", st.teacher_buf), (eng.bn_s, "head.", st.student_head_buf),
+              (eng.bn_t, "head.", st.teacher_head_buf)]
+    for m in ("image", "audio"):
+        if m + "_buf" in st.aux:
+            tables.append((eng.bn_s, f"aux_{m}.", st.aux[m + "_buf"]))
+    for table, prefix, buf in tables:
+        for k, v in buf.items():
+            base, attr = k.rsplit(".", 1)
+            getattr(table[prefix + base], attr).copy_(v.to(DEV))
+
+
+@pytest.mark.parametrize("mode", ["default", "semi_supervised", "infonce", "mse"])
+def test_step_vs_oracle_and_reference(mode, golden):
+    """Two consecutive steps, each compared at the SAME tight tolerances (gradients 3e-4 relative, loss 1e-5): before the second
+    step the engine is re-synchronised to the oracle's state after the first, so the comparison is per step and not along a
+    chaotic free-running trajectory.  Against the imported reference's own numbers (golden) the second step is bounded by what
+    separates the oracle from the reference there (1e-2, tests/test_oracle_golden.py) plus the engine-vs-oracle 3e-4."""
+    fx = golden["steps"][mode]
+    B = fx["B"]
+    st = R.CentralDinoState(seed=fx["seed"], mode=mode)
+    eng = DinoStepEngine(kind="multi_central", mode=mode, device=DEV, precision="fp32")
+    _load_state(eng, st)
+    for it, rec in enumerate(fx["steps"]):
+        if it > 0:
+            _sync_engine_to_oracle(eng, st)
+        img, aud = views_to_vb(*synth_views(B, seed=100 + it))
+        masks = make_masks(seed=200 + it, V=6, Vg=2, B=B, E=256, hidden=512)
+        raw = labels = None
+        graw = glabels = None
+        if mode != "default":
+            image, audio, labels = synth_raw(B, seed=300 + it)
+            raw = (image, audio)
+            graw, glabels = (image[:, 0].to(DEV).contiguous(), audio[:, 0].to(DEV).contiguous()), labels.to(DEV)
+        want = R.central_dino_step(st, img, aud, masks, raw=raw, labels=labels)
+        loss = eng.forward_backward(img[:, :, 0].to(DEV).contiguous(), aud[:, :, 0].to(DEV).contiguous(), masks=_gpu_masks(masks),
+                                    raw=graw, labels=glabels)
+        torch.cuda.synchronize()
+        total = float(loss[3])
+        assert abs(total - float(want["loss"])) < 1e-5 * max(1.0, abs(float(want["loss"]))), (mode, it, total, float(want["loss"]))
+        assert abs(total - rec["loss"]) < 2e-5 * max(1.0, abs(rec["loss"])), (mode, it, total, rec["loss"])     # the reference itself
+        # outputs
+        assert _rel(eng._ws[B]["s.proj"].view(6, B, -1), want["student_out"]) < 2e-5
+        # gradients: vs the oracle at 3e-4 in every step; vs the reference golden 3e-4 (step 0) / 1.2e-2 (step 1, see docstring)
+        gtol, rtol = 3e-4, (3e-4 if it == 0 else 1.2e-2)
+        groups = [("enc.", want["grads"]["student"], "model.student."), ("head.", want["grads"]["student_head"], "model.student_projection.")]
+        if mode != "default":
+            nm = ("image_classifier", "audio_classifier") if mode == "semi_supervised" else ("image_projection_head", "audio_projection_head")
+            groups += [("aux_image.", want["grads"]["image"], f"model.{nm[0]}."), ("aux_audio.", want["grads"]["audio"], f"model.{nm[1]}.")]
+        for prefix, gd, refprefix in groups:
+            for k, g in gd.items():
+                mine = eng.G[prefix + k]
+                if _cancelled(k):
+                    assert float(mine.abs().sum()) < 1e-3, (k, float(mine.abs().sum()))
+                    continue
+                assert _rel(mine, g) < gtol, (mode, it, k, _rel(mine, g))
+                ok, why = summaries_close(summarize(mine), rec["grads"][refprefix + k], rtol, 1e-7 if it == 0 else 1e-6)
+                assert ok, (mode, it, k, why)
+        # EMA (before the optimizer) and Adam
+        eng.update_teacher()
+        eng.optimizer_step()
+        for k, v in st.teacher.items():
+            d = float((eng.T["enc." + k].cpu() - v).abs().max())
+            assert d <= 1e-9, ("teacher", k, d)
+        for k, v in st.teacher_head.items():     # identical inputs -> the EMA is bit-exact
+            assert torch.equal(eng.T["head." + k].cpu(), v), k
+        for k, v in st.student.items():
+            diff = (eng.S["enc." + k].cpu() - v).abs()
+            # Adam turns any gradient into a ~lr-sized step, so elements whose gradient is rounding noise (dead units,
+            # BatchNorm-cancelled biases) may differ by up to 2*lr; everything else must agree to fp32 rounding
+            assert float(diff.max()) <= 2.5e-4, ("student after adam (max)", k, float(diff.max()))
+            if not _cancelled(k):
+                assert float(diff.mean()) <= 2e-7, ("student after adam (mean)", k, float(diff.mean()))
+        # centre and BatchNorm running statistics
+        assert _rel(eng.center, st.center) < 1e-5
+        for k in ("image_encoder.0.bn1", "image_encoder.0.bn2", "audio_encoder.0.bn1", "audio_encoder.0.bn4"):
+            assert _rel(eng.bn_s["enc." + k].running_mean, st.student_buf[k + ".running_mean"]) < 1e-5, k
+            assert _rel(eng.bn_s["enc." + k].running_var, st.student_buf[k + ".running_var"]) < 1e-5, k
+            assert _rel(eng.bn_t["enc." + k].running_var, st.teacher_buf[k + ".running_var"]) < 1e-5, k
+            assert int(eng.bn_s["enc." + k].num_batches_tracked) == int(st.student_buf[k + ".num_batches_tracked"])
+        assert _rel(eng.bn_s["head.mlp.1"].running_var, st.student_head_buf["mlp.1.running_var"]) < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["default", "semi_supervised", "infonce", "mse"])
+def test_fp32_step_is_run_to_run_deterministic(mode):
+    """The reference trains with deterministic=True (run_dino.py:364).  The exact-fp32 path has no order-dependent float
+    reduction: two engines fed the same inputs produce bit-identical losses, gradients, parameters and centre over two steps."""
+    B = 6
+    outs = []
+    for _ in range(2):
+        st = R.CentralDinoState(seed=3, mode=mode)
+        eng = DinoStepEngine(kind="multi_central", mode=mode, device=DEV, precision="fp32")
+        _load_state(eng, st)
+        rec = []
+        for it in range(2):
+            img, aud = views_to_vb(*synth_views(B, seed=100 + it))
+            masks = make_masks(seed=200 + it, V=6, Vg=2, B=B, E=256, hidden=512)
+            graw = glabels = None
+            if mode != "default":
+                image, audio, labels = synth_raw(B, seed=300 + it)
+                graw, glabels = (image[:, 0].to(DEV).contiguous(), audio[:, 0].to(DEV).contiguous()), labels.to(DEV)
+            loss = eng.train_step_views(img[:, :, 0].to(DEV).contiguous(), aud[:, :, 0].to(DEV).contiguous(), masks=_gpu_masks(masks),
+                                        raw=graw, labels=glabels)
+            rec += [loss.clone(), eng.grad.clone()]
+        torch.cuda.synchronize()
+        outs.append(rec + [eng.student.flat.clone(), eng.teacher.flat.clone(), eng.center.clone()])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b), float((a - b).abs().max())
+
+
 def test_unimodal_image_simple_bf16_runs():
     eng = DinoStepEngine(kind="image_simple", device=DEV, precision="bf16")
     assert eng.tc["img"] == [True, True, True]
@@ -303,8 +355,7 @@ def test_cuda_graph_replay_reproduces_the_eager_step_bit_for_bit(mode):
         l_g.append(graph.graph_step(img, aud).clone())
     torch.cuda.synchronize()
     for a, b in zip(l_e, l_g):
-        # (the alignment-loss VALUE is a float atomic sum over CTAs: last-bit run-to-run differences, eager or not)
-        assert torch.equal(a, b) if mode == "default" else torch.allclose(a, b, rtol=1e-5, atol=1e-7), (a, b)
+        assert torch.equal(a, b), (a, b)          # loss values are fixed-order sums: bit-identical, eager or replayed
     exact = {n: torch.equal(x, y) for n, x, y in (("student", graph.student.flat, eager.student.flat), ("teacher", graph.teacher.flat, eager.teacher.flat),
                                                   ("adam v", graph.exp_avg_sq, eager.exp_avg_sq), ("centre", graph.center, eager.center))}
     assert all(exact.values()), exact
@@ -314,7 +365,7 @@ def test_cuda_graph_replay_reproduces_the_eager_step_bit_for_bit(mode):
     a = eager.train_step(*batches[0]).clone()
     b = graph.train_step(*batches[0]).clone()
     torch.cuda.synchronize()
-    assert torch.equal(a, b) if mode == "default" else torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+    assert torch.equal(a, b)
     assert torch.equal(graph.student.flat, eager.student.flat)
 
 
