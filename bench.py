@@ -174,25 +174,47 @@ def run_reference_on_gpu(args):
                       "torch": torch.__version__, "cudnn": torch.backends.cudnn.version()}))
 
 
+REF_SAMPLE_BATCH = 64        # the CPU arm steps on a fixed 64-sample slice of the workload's batch (pinned: same B in every run)
+
+
+def workload_config(args, world):
+    """The `config` object of the JSON line -- identical for our arm and the reference arm."""
+    B = per_gpu_batch(args, world)
+    if args.kind == "multi_central":
+        wl = WORKLOAD if args.mode == "default" else WORKLOAD.replace("default mode", args.mode + " mode")
+    else:
+        wl = "image_simple unimodal DINO step (2 global + 4 local views of 28x28 images, O=256, P=128)"
+    return {"workload": wl, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+            "l2": "inputs larger than L2: the per-step working set (activations) is several GB against the 126 MB L2"}
+
+
+def per_gpu_batch(args, world):
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} GPUs")
+        return args.global_batch // world
+    return args.batch
+
+
 def run_reference(args):
+    """The reference's own CPU implementation of the path (oracle port; /root/reference does not exist on the GPU box) on all
+    host cores.  Same `config` as our arm; every step is a FIXED 64-sample slice of that workload's batch (a bounded sample:
+    the CPU rate is flat in B beyond a few dozen samples), steps / warm-up as asked."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     if args.reference_device == "gpu":
         return run_reference_on_gpu(args)
     cores = os.cpu_count() or 1
-    # size the per-step sample so that the whole run stays within a couple of minutes
     import torch
     torch.set_num_threads(cores)
-    t0 = time.perf_counter()
-    cpu_reference(8, 1, 1, cores, with_aug=False)
-    t8 = (time.perf_counter() - t0) / 2
-    budget = 100.0 / max(1, args.steps + args.warmup)
-    batch = int(max(8, min(256, 8 * budget / max(t8, 1e-3)))) // 8 * 8
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    batch = REF_SAMPLE_BATCH
     rate, ms, desc = cpu_reference(batch, args.steps, args.warmup, cores)
     line = {"metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_step_batch": batch, "inputs": "host"}, "impl": "reference",
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "impl": "reference",
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"each step = a {batch}-sample slice of the workload batch; " + desc},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -302,11 +324,17 @@ def ncu_traffic(row, B):
     return ent["dram_bytes"] * B / table.get("per_gpu_batch", 1024)
 
 
-def profile_ops(engine, images, audios, steps=2, labels=None):
-    """Per-op CUDA-event timing of `steps` whole steps (events on the launching stream)."""
+def profile_ops(engine, images, audios, steps=3, labels=None):
+    """Per-op CUDA-event timing (events on the launching stream, side streams switched off so that every op runs alone on the
+    current stream).  One un-recorded step first: switching the streams off moves ops onto streams whose scratch buffers do
+    not exist yet, and a first-use cudaMalloc between two events would be charged to that op (round 1's 6 ms
+    `linear_bwd_weight`).  Per op and shape the MEDIAN over the recorded calls is reported."""
+    import statistics
     import torch
     from multimodal_ssl_avmnist_b200 import ops
     overlap, engine.overlap_teacher = engine.overlap_teacher, False      # per-kernel times: no concurrent streams while profiling
+    engine._prefetch = None
+    engine.train_step(images, audios, labels)                            # un-recorded: allocates the per-stream scratch
     torch.cuda.synchronize()
     rec = ops.start_profile()
     for _ in range(steps):
@@ -316,20 +344,47 @@ def profile_ops(engine, images, audios, steps=2, labels=None):
     engine.overlap_teacher = overlap
     agg = {}
     for name, a, b, meta in rec:
-        ms = a.elapsed_time(b)
-        key = (name, meta)
-        d = agg.setdefault(key, {"ms": 0.0, "calls": 0})
-        d["ms"] += ms
-        d["calls"] += 1
+        agg.setdefault((name, meta), []).append(a.elapsed_time(b))
     rows = []
-    for (name, meta), d in agg.items():
+    for (name, meta), ts in agg.items():
         fl, by = op_cost(name, meta)
-        per = d["ms"] / d["calls"]
-        rows.append({"op": name, "shapes": [list(s) for s in meta], "calls_per_step": d["calls"] / steps, "ms_per_call": per,
-                     "ms_per_step": d["ms"] / steps, "flops": fl, "bytes": by,
+        calls = len(ts) / steps
+        per = statistics.median(ts)
+        rows.append({"op": name, "shapes": [list(s) for s in meta], "calls_per_step": calls, "ms_per_call": per,
+                     "ms_per_step": per * calls, "flops": fl, "bytes": by,
                      "tflops": fl / per / 1e9 if per > 0 else 0.0, "gbs": by / per / 1e6 if per > 0 else 0.0})
     rows.sort(key=lambda r: -r["ms_per_step"])
     return rows
+
+
+def step_work(kind, mode, B):
+    """Algorithmic work of ONE step on one GPU: (FLOPs, HBM bytes).  FLOPs: forward MACs x 2 x (6 student views x
+    3 [fwd, dgrad, wgrad] + 2 teacher views); the non-default modes add one un-augmented student pass through both conv
+    stacks + encoder linears + the two mode heads (x 3).  Bytes: augmentation 373,184 B/sample (21,952 image only), saved
+    pre-BatchNorm activations 2 B x (1 write + 1 read) x 6 views, DINO loss 7,168 B/sample, + per step the teacher EMA
+    (12 B/param) and Adam (28 B per trainable param)."""
+    head = 196_608
+    if kind == "multi_central":
+        enc, act_elems, aug = 39_770_624, 219_648, 373_184
+        n_ema, n_adam = 6_600_580, 1_728_368
+        raw_pass = 39_770_624 - 196_608                      # conv stacks + encoder linears, no fusion
+    else:
+        enc = 225_792 + 3_612_672 + 3_612_672 + 128 * 512 + 512 * 256       # 3 x conv3x3 + Linear(128,512) + Linear(512,256)
+        act_elems, aug = 32 * 28 * 28 + 64 * 14 * 14 + 128 * 7 * 7, 21_952
+        n_ema, n_adam = 488_768, 488_768
+        raw_pass = 0
+    macs = 20 * (enc + head)
+    extra_bytes = 0.0
+    if mode != "default":
+        out = 10 if mode == "semi_supervised" else 128
+        macs += 3 * (raw_pass + 2 * (256 * 512 + 512 * out))
+        n_adam += 2 * (256 * 512 + 512 + 1024 + 512 * out + out)
+        extra_bytes += act_elems * 4.0                       # the 7th view-call's saved activations
+        if mode == "infonce":
+            macs += 3 * B * 128                              # per sample: B x 128 similarity MACs, forward + two gradient GEMMs
+    flops = 2.0 * macs * B
+    byts = B * (aug + act_elems * 6 * 4.0 + 7168 + extra_bytes) + 12.0 * n_ema + 28.0 * n_adam
+    return flops, byts
 
 
 def run_ours(args):
@@ -348,7 +403,7 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
+    B = per_gpu_batch(args, world)
     eng = DinoStepEngine(kind=args.kind, mode=args.mode, augment_values=augment_values() if args.kind == "multi_central" else None,
                          seed=1 + rank, device=dev)
     g = torch.Generator().manual_seed(1 + rank)
@@ -427,21 +482,33 @@ def run_ours(args):
     ms, ms_e2e = float(t[0]), float(t[1])
     if use_graph:
         eng.release_graph()                     # the per-op profile below steps eagerly
-    rows = profile_ops(eng, img_d, aud_d, steps=2, labels=lab_d)       # every rank runs it (the step contains collectives when N > 1)
+    # per-op profile; every rank runs it (the step contains collectives when N > 1).  Consistency gate: with the side streams
+    # off the per-op times must add up to about the step time (<= 1.3 x: the overlapped step hides ~15 %); otherwise a stall sat
+    # between two events (allocation, clock ramp) and the profile is taken again.
+    for attempt in range(3):
+        rows = profile_ops(eng, img_d, aud_d, steps=3, labels=lab_d)
+        step_ms_prof = sum(r["ms_per_step"] for r in rows)
+        if step_ms_prof <= 1.3 * ms + 0.3:
+            break
+    profile_ok = step_ms_prof <= 1.3 * ms + 0.3
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peaks = load_peaks()
-    step_ms_prof = sum(r["ms_per_step"] for r in rows)
-    # dominant kernel = the op launch with the largest share of the step (algorithmic flops / bytes from op_cost)
+    # (i) the whole step against both rooflines (SURVEY 8d algorithmic work / the timed ms_per_step / measured peaks)
+    fl_step, by_step = step_work(args.kind, args.mode, B)
+    t_tensor_step, t_hbm_step = fl_step / (peaks["tflops"] * 1e9), by_step / (peaks["hbm_gbs"] * 1e6)       # ms
+    whole = {"algorithmic_tflop": fl_step / 1e12, "algorithmic_gb": by_step / 1e9, "tflops": fl_step / ms / 1e9, "gbs": by_step / ms / 1e6,
+             "frac_tensor": fl_step / ms / 1e9 / peaks["tflops"], "frac_hbm": by_step / ms / 1e6 / peaks["hbm_gbs"],
+             "ideal_ms": max(t_tensor_step, t_hbm_step), "achieved_over_ideal": max(t_tensor_step, t_hbm_step) / ms}
+    # (ii) the dominant kernel = the largest launch of the kernel family with the largest share of the step
     costed = [r for r in rows if r["flops"] > 0 or r["bytes"] > 0]
-    # dominant kernel = the largest launch of the kernel family with the largest share of the step
     fam = {}
     for r in costed:
         fam[r["op"]] = fam.get(r["op"], 0.0) + r["ms_per_step"]
     top_op = max(fam, key=fam.get)
-    top = max((r for r in costed if r["op"] == top_op), key=lambda r: r["ms_per_step"])
+    top = max((r for r in costed if r["op"] == top_op), key=lambda r: r["ms_per_call"])
     shapes = [s_ for s_ in top["shapes"] if not (s_ and s_[0] == "i")][:3]
     # the binding roofline of a kernel = whichever of (FLOPs / tensor peak, bytes / HBM peak) takes longer
     t_tensor = top["flops"] / (peaks["tflops"] * 1e9)          # ms
@@ -459,9 +526,12 @@ def run_ours(args):
             roof["tflops"] = top["tflops"]
             roof["note"] = ("tcgen05 implicit-GEMM convolution whose FLOPs need less time at the tensor peak than its act8 bytes need at the "
                             "HBM peak: HBM is the binding roofline")
+    roof["us_per_launch"] = 1e3 * top["ms_per_call"]
     roof["family_share_of_step"] = fam[top_op] / step_ms_prof
+    roof["profile"] = {"sum_of_op_ms": step_ms_prof, "ms_per_step": ms, "consistent": profile_ok}
+    roof["whole_step"] = whole
     roof["traffic"] = ncu_traffic(top, B)
-    if NCU_EXTRA:       # from the same committed ncu --set full capture (profiles/ncu_traffic.json, profiles/r1d_ncu_kernels.md)
+    if NCU_EXTRA:       # from the same committed ncu --set full capture (profiles/ncu_traffic.json)
         roof["ncu"] = dict(NCU_EXTRA)
         if NCU_EXTRA.get("tensor_pipe_busy_pct", 0) > 80:
             roof["note"] = (roof.get("note", "") + "; ncu: the tensor pipe is busy %.0f %% of the time (a UMMA occupies it for its shared-memory operand "
@@ -491,17 +561,17 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline and args.kind == "multi_central" and args.mode == "default":
         cores = os.cpu_count() or 1
-        rate, _, desc = cpu_reference(64, 2, 1, cores)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        rate, _, desc = cpu_reference(REF_SAMPLE_BATCH, 3, 1, cores)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"each step = a {REF_SAMPLE_BATCH}-sample slice of the workload batch; " + desc}
     h2d = img_h.numel() * 4 + (aud_h.numel() if aud_h is not None else 0)
     line = {"metric": METRIC, "value": B * world / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": (WORKLOAD if args.mode == "default" else WORKLOAD.replace("default mode", args.mode + " mode")) if args.kind == "multi_central"
-                       else "image_simple unimodal DINO step (2 global + 4 local views of 28x28 images, O=256, P=128)", "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "execution": "one CUDA graph replay per step (device-side step counters)" if use_graph else "eager launches on 6 streams",
-                       "l2": "per-step working set (activations) is several GB, far larger than the 126 MB L2",
-                       "precision": "bf16 tensor-core convolutions (fp16 pre-BatchNorm z, bf16 activations / gradients), fp32 accumulate, "
-                                    "statistics, linears, losses, EMA, Adam"},
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, world),
+            "details": {"execution": "one CUDA graph replay per step (device-side step counters)" if use_graph else "eager launches on 6 streams",
+                        "precision": "bf16 tensor-core convolutions (fp16 pre-BatchNorm z, bf16 activations / gradients), fp32 accumulate, "
+                                     "statistics, linears, losses, EMA, Adam"},
             "e2e": {"value": B * world / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e, "last_loss": last,
                     "note": "every step: H2D of its raw batch from pinned memory + D2H of its total loss (fp32 scalar, read back one "
@@ -519,6 +589,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="STRONG scaling: total batch over all GPUs (per-GPU batch = global / N); overrides --batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reference-device", default="cpu", choices=["cpu", "gpu"],
                     help="--impl reference only: 'gpu' times the same oracle step with stock PyTorch kernels on cuda:0 (library bar)")

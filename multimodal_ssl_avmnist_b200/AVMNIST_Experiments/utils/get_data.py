@@ -248,14 +248,26 @@ class DeviceResidentLoader:
         self.batch_size, self.shuffle, self.drop_last, self.with_labels = batch_size, shuffle, drop_last, with_labels
         self.gen = torch.Generator(device=device).manual_seed(seed)
         self.device = device
+        self.rank, self.world = 0, 1
+
+    def set_rank_shard(self, rank, world):
+        """Data parallel (what Lightning's DistributedSampler does for the reference under strategy='ddp', run_dino.py:359): every
+        rank draws the SAME epoch permutation (same generator seed) and takes the strided slice rank::world of it, truncated so
+        that all ranks see the same number of samples."""
+        self.rank, self.world = int(rank), int(world)
+
+    def _n_local(self):
+        return self.image.shape[0] // self.world
 
     def __len__(self):
-        n = self.image.shape[0]
+        n = self._n_local()
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
     def __iter__(self):
         n = self.image.shape[0]
         perm = torch.randperm(n, device=self.device, generator=self.gen) if self.shuffle else torch.arange(n, device=self.device)
+        if self.world > 1:
+            perm = perm[:self._n_local() * self.world][self.rank::self.world]
         for b in range(len(self)):
             sel = perm[b * self.batch_size:(b + 1) * self.batch_size]
             batch = (self.image.index_select(0, sel), self.audio.index_select(0, sel))
@@ -302,7 +314,8 @@ class AVMNISTDinoDataModule(BaseAVMNISTDataModule):
         if self.device_resident and self.device_augmentation and torch.cuda.is_available():
             sub = self.train_dataset
             return DeviceResidentLoader(sub.dataset, sub.indices, self.batch_size, torch.device("cuda", torch.cuda.current_device()),
-                                        shuffle=self.train_shuffle, with_labels=self.EXTENDED)
+                                        shuffle=self.train_shuffle, with_labels=self.EXTENDED,
+                                        seed=int(torch.initial_seed()) & 0x7FFFFFFF)       # the run's global seed: same permutation on every rank
         return super().train_dataloader()
 
 

@@ -20,11 +20,27 @@ from .engine import DinoStepEngine
 
 class B200Adam(torch.optim.Optimizer):
     """torch.optim.Adam-compatible front (param_groups, lr schedulers, state_dict) whose step() is ONE flat-arena CUDA
-    kernel over the parameters that received gradients (plus one for the mode heads)."""
+    kernel over the parameters that received gradients (plus one for the mode heads).
+
+    The moments and the step counter live in the engine's flat arenas, but they BELONG to this optimizer object: a new
+    B200Adam starts from zero moments and step 0 exactly like a new torch.optim.Adam (run_dino.py builds a fresh optimizer per
+    seed / per fit, run_dino.py:94-104), and state_dict() / load_state_dict() carry them through checkpoints."""
 
     def __init__(self, params, binding, lr=1e-4, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8):
         super().__init__(params, dict(lr=lr, weight_decay=weight_decay, betas=betas, eps=eps))
         self.binding = binding
+        self._fresh = True                 # the engine's moments still hold a previous optimizer's state
+        self._pending_state = None
+        binding.optimizer = self
+
+    def _claim_engine(self, eng):
+        """First contact with the engine: reset (or restore) the Adam state it holds."""
+        if self._fresh:
+            eng.reset_optimizer_state()
+            self._fresh = False
+        if self._pending_state is not None:
+            eng.load_optimizer_state(self._pending_state)
+            self._pending_state = None
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -32,10 +48,31 @@ class B200Adam(torch.optim.Optimizer):
         eng = self.binding.engine
         if eng is None:
             raise ops._lib.B200Error("B200Adam.step() before the first CUDA forward")
+        self._claim_engine(eng)
         g = self.param_groups[0]
         eng.lr, eng.weight_decay = g["lr"], g["weight_decay"]
         eng.optimizer_step()
         return loss
+
+    def state_dict(self):
+        sd = super().state_dict()
+        eng = self.binding.engine
+        if eng is not None and not self._fresh:
+            sd["b200_arena_state"] = eng.optimizer_state()
+        elif self._pending_state is not None:
+            sd["b200_arena_state"] = self._pending_state
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        arena = state_dict.pop("b200_arena_state", None)
+        super().load_state_dict(state_dict)
+        if arena is not None:
+            self._pending_state = arena
+            eng = self.binding.engine
+            if eng is not None:
+                self._fresh = False
+                self._claim_engine(eng)
 
 
 class _StudentOutputs(torch.autograd.Function):
@@ -119,6 +156,11 @@ class EngineBinding:
         mod = self.module
         if self.engine is None:
             hp = mod.b200_hparams()
+            # augmentation / dropout streams: the global torch seed (run_dino.py seeds it per run) + the rank, so that seeds and
+            # data-parallel ranks draw different views and masks
+            import os
+            rank = int(os.environ.get("RANK", "0")) if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+            hp.setdefault("seed", (int(torch.initial_seed()) + rank) & 0x7FFFFFFF)
             self.engine = DinoStepEngine(kind=self.kind, mode=self.mode, device=device, **hp)
             self._names = self._name_map()
         eng = self.engine

@@ -994,6 +994,27 @@ class DinoStepEngine:
                 ops.adam_flat(self.student.flat[lo:hi], self.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.step_count,
                               self.lr, weight_decay=self.weight_decay, grad_scale=gs)
 
+    def reset_optimizer_state(self):
+        """A fresh Adam: zero moments, step 0 (what constructing a new torch.optim.Adam gives the reference per fit)."""
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.step_count = 0
+        if self._ctr is not None:
+            self._ctr[1:2].zero_()
+
+    def optimizer_state(self):
+        """Adam state for checkpoints: the two moment arenas (CPU copies) + the step count."""
+        return {"exp_avg": self.exp_avg.detach().cpu().clone(), "exp_avg_sq": self.exp_avg_sq.detach().cpu().clone(), "step": int(self.step_count)}
+
+    def load_optimizer_state(self, state):
+        if state["exp_avg"].numel() != self.exp_avg.numel():
+            raise ops._lib.B200Error("load_optimizer_state: arena size mismatch (different model kind / mode)")
+        self.exp_avg.copy_(state["exp_avg"].to(self.device))
+        self.exp_avg_sq.copy_(state["exp_avg_sq"].to(self.device))
+        self.step_count = int(state["step"])
+        if self._ctr is not None:
+            self._ctr[1:2].fill_(self.step_count)
+
     def train_step_views(self, x_img, x_aud, masks=None, raw=None, labels=None):
         """Reference step order on given views: forward/loss/backward, EMA (before the optimizer, dino.py:871), Adam."""
         loss = self.forward_backward(x_img, x_aud, masks=masks, raw=raw, labels=labels)

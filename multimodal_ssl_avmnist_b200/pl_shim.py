@@ -216,6 +216,7 @@ class Trainer:
         self.world_size = int(os.environ.get("WORLD_SIZE", "1"))
         self._epoch_acc = {}
         self.model = None
+        self._dist_sampler = None
 
     # -- logging ------------------------------------------------------------------------------------------
     def _log(self, name, value, on_step=None, on_epoch=None):
@@ -246,24 +247,45 @@ class Trainer:
             self.logger.log_metrics({k: (float(v) if v is not None else None) for k, v in pending.items()}, self.global_step, self.current_epoch)
         pending.clear()
 
+    def _shard_loader(self, loader):
+        """strategy='ddp' under torchrun: every rank must train on its own shard (real Lightning injects a DistributedSampler,
+        run_dino.py:359).  Loaders that can shard themselves (DeviceResidentLoader.set_rank_shard) are told their rank; a plain
+        torch DataLoader is rebuilt around a DistributedSampler; anything else is refused rather than silently replicated."""
+        if self.world_size <= 1 or loader is None:
+            return loader
+        if hasattr(loader, "set_rank_shard"):
+            loader.set_rank_shard(self.global_rank, self.world_size)
+            return loader
+        if isinstance(loader, torch.utils.data.DataLoader):
+            if isinstance(loader.sampler, torch.utils.data.distributed.DistributedSampler):
+                return loader
+            shuffle = isinstance(loader.sampler, torch.utils.data.RandomSampler)
+            sampler = torch.utils.data.distributed.DistributedSampler(loader.dataset, num_replicas=self.world_size, rank=self.global_rank,
+                                                                      shuffle=shuffle, seed=int(os.environ.get("PL_GLOBAL_SEED", "0")))
+            self._dist_sampler = sampler
+            return torch.utils.data.DataLoader(loader.dataset, batch_size=loader.batch_size, sampler=sampler, num_workers=loader.num_workers,
+                                               collate_fn=loader.collate_fn, pin_memory=loader.pin_memory, drop_last=loader.drop_last)
+        raise RuntimeError("Trainer(strategy='ddp'): cannot shard this train loader over the ranks (no set_rank_shard, not a DataLoader)")
+
     # -- fit ----------------------------------------------------------------------------------------------
     def fit(self, model, datamodule=None, train_dataloaders=None):
         self.model = model
         model._trainer = self
         self.datamodule = datamodule
         self._pending_step, self._pending_epoch = {}, {}
+        if torch.cuda.is_available():         # before the loaders are built: a device-resident loader lives on THIS rank's GPU
+            dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+            torch.cuda.set_device(dev)
+            if self.strategy == "ddp" and self.world_size > 1 and not torch.distributed.is_initialized():
+                torch.distributed.init_process_group("nccl", device_id=dev)
+            model.to(dev)
         if datamodule is not None:
             datamodule.prepare_data()
             datamodule.setup("fit")
             loader = datamodule.train_dataloader()
         else:
             loader = train_dataloaders
-        if torch.cuda.is_available():
-            dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-            torch.cuda.set_device(dev)
-            if self.strategy == "ddp" and self.world_size > 1 and not torch.distributed.is_initialized():
-                torch.distributed.init_process_group("nccl", device_id=dev)
-            model.to(dev)
+        loader = self._shard_loader(loader)
         cfg = model.configure_optimizers()
         sched = None
         if isinstance(cfg, dict):
@@ -287,6 +309,8 @@ class Trainer:
             self._epoch_acc = {}
             for cb in self.callbacks:
                 cb.on_train_epoch_start(self, model)
+            if getattr(self, "_dist_sampler", None) is not None:
+                self._dist_sampler.set_epoch(epoch)
             for batch_idx, batch in enumerate(loader):
                 if self.limit_train_batches is not None and batch_idx >= self.limit_train_batches:
                     break

@@ -187,3 +187,32 @@ def test_quad8_width_covers_every_tap_of_every_output_phase():
         last_group = W // 4 - 1                      # outputs 4*g .. 4*g+3
         assert 3 + (K - 1) <= 7                      # kw' = ph + kw < 8
         assert last_group < wq
+
+
+def test_ddp_ranks_train_on_disjoint_shards(tmp_path, monkeypatch):
+    """strategy='ddp' (run_dino.py:359): real Lightning injects a DistributedSampler; the shim must shard too.  Device-resident
+    loader: same permutation on every rank, strided slices, disjoint and equally long; a plain DataLoader is rebuilt around a
+    DistributedSampler; an unshardable iterable is refused instead of being silently replicated."""
+    from multimodal_ssl_avmnist_b200 import pl_shim
+    gd.write_synthetic_avmnist(str(tmp_path) + "/", n_train=96, n_test=16)
+    dm = gd.AVMNISTDinoDataModule(str(tmp_path) + "/", batch_size=8, num_workers=0)
+    dm.setup("fit")
+    sub = dm.train_dataset
+    seen = []
+    for rank in range(2):
+        ld = gd.DeviceResidentLoader(sub.dataset, sub.indices, 8, torch.device("cpu"), shuffle=True, with_labels=True, seed=5)
+        ld.labels = torch.arange(ld.image.shape[0])           # sample ids, to see which samples a rank draws
+        ld.set_rank_shard(rank, 2)
+        ids = torch.cat([b[2] for b in ld])
+        assert len(ld) == ld.image.shape[0] // 2 // 8 and ids.numel() == len(ld) * 8
+        seen.append(set(ids.tolist()))
+    assert not (seen[0] & seen[1])
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setenv("RANK", "1")
+    tr = pl_shim.Trainer(strategy="ddp")
+    plain = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(torch.arange(40)), batch_size=4, shuffle=True)
+    sharded = tr._shard_loader(plain)
+    assert isinstance(sharded.sampler, torch.utils.data.distributed.DistributedSampler) and sharded.sampler.rank == 1
+    assert sum(b[0].numel() for b in sharded) == 20
+    with pytest.raises(RuntimeError):
+        tr._shard_loader([1, 2, 3])
