@@ -304,7 +304,7 @@ class CentralDinoState:
 
 def central_dino_step(st, img_views, aud_views, masks, n_global=2, tau_s=0.1, tau_t=0.04, momentum=0.996,
                       center_momentum=0.9, lr=1e-4, weight_decay=1e-6, dropout=0.3, raw=None, labels=None,
-                      alpha=1.0, do_adam=True):
+                      alpha=1.0, do_adam=True, loss_scale=1.0):
     """One reference training step in the live Lightning order: forward (student on all views,
     teacher on the global views, heads, centre update), loss, teacher EMA, backward, Adam.
 
@@ -312,6 +312,8 @@ def central_dino_step(st, img_views, aud_views, masks, n_global=2, tau_s=0.1, ta
     masks: dict with keep-masks 'student_fusion' [V,B,E], 'teacher_fusion' [Vg,B,E], 'student_head' [V*B,512]
     (+ 'aux_image_head'/'aux_audio_head' are never needed: the mode heads use dropout 0).
     raw = (image [B,1,28,28], audio [B,1,112,112]) for the non-default modes.
+    loss_scale: static GradScaler stand-in for runs under fp16 autocast (Lightning's precision='16-mixed', run_dino.py:360):
+    the backward runs on loss * loss_scale, gradients are unscaled, and a step with non-finite gradients skips Adam.
     Returns dict(loss, grads{student,student_head,aux...}, student_out, teacher_out)."""
     V, B = img_views.shape[0], img_views.shape[1]
     S = {k: v.clone().requires_grad_(True) for k, v in st.student.items()}
@@ -354,11 +356,14 @@ def central_dino_step(st, img_views, aud_views, masks, n_global=2, tau_s=0.1, ta
     ema_update(st.teacher, st.student, momentum)
     ema_update(st.teacher_head, st.student_head, momentum)
 
-    loss.backward()
-    grads = {"student": {k: v.grad for k, v in S.items() if v.grad is not None},
-             "student_head": {k: v.grad for k, v in SH.items() if v.grad is not None}}
+    (loss * loss_scale if loss_scale != 1.0 else loss).backward()
+    unscale = (lambda g: g / loss_scale) if loss_scale != 1.0 else (lambda g: g)
+    grads = {"student": {k: unscale(v.grad) for k, v in S.items() if v.grad is not None},
+             "student_head": {k: unscale(v.grad) for k, v in SH.items() if v.grad is not None}}
     for m in AUX:
-        grads[m] = {k: v.grad for k, v in AUX[m].items() if v.grad is not None}
+        grads[m] = {k: unscale(v.grad) for k, v in AUX[m].items() if v.grad is not None}
+    if loss_scale != 1.0 and not all(bool(torch.isfinite(g).all()) for gd in grads.values() for g in gd.values()):
+        do_adam = False          # GradScaler: skip the optimizer step on overflow
     if do_adam:
         # one optimizer over all parameters: shared step counter
         step = st.adam.get("step", 0)
