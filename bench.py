@@ -387,6 +387,64 @@ def step_work(kind, mode, B):
     return flops, byts
 
 
+def run_module_path(args, B, steps, warmup):
+    """Throughput of the DROP-IN path (reference flow run_dino.py:356-373): `Trainer.fit(MultiModalDINOLightning,
+    AVMNISTDinoDataModule)` from the API mirror -- training_step -> loss.backward() -> B200Adam.step() per batch, batches
+    gathered from the HBM-resident split (DeviceResidentLoader), augmentation on the device.  Timed with CUDA events recorded
+    from a Trainer callback after `warmup` batches.  Returns a dict for the JSON line."""
+    import shutil
+    import tempfile
+    import torch
+    mirror = os.path.join(ROOT, "multimodal_ssl_avmnist_b200", "AVMNIST_Experiments")
+    if mirror not in sys.path:
+        sys.path.insert(0, mirror)
+    import models.dino as md
+    import utils.get_data as gd
+    from _compat import pl
+    Callback = pl.Callback
+    tmp = tempfile.mkdtemp(prefix="avmnist_bench_") + "/"
+    try:
+        n_batches = warmup + steps
+        n_train = (n_batches * B * 12 + 10) // 11 + B          # the data module keeps 55000/60000 of the train file for training
+        gd.write_synthetic_avmnist(tmp, n_train=n_train, n_test=16)
+        aug = gd.MultiModalAugmentation(2, 4, augment_values=augment_values())
+        dm = gd.AVMNISTDinoDataModule(data_dir=tmp, batch_size=B, num_workers=0, type="burst_noise", augmentations=aug, device_resident=True)
+        dm.probe_dataloaders = None            # no per-epoch linear probe here: only the training steps are timed
+        lit = md.MultiModalDINOLightning(data_dir=tmp, encoder_class=md.CentralMultiModalEncoder, projection_dim=128, output_dim=256,
+                                         encoder_output_dim=256, learning_rate=1e-4, num_epochs=1, weight_decay=1e-6, dropout=0.3)
+
+        class Timer(Callback):
+            def __init__(self):
+                self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                self.n = 0
+
+            def on_train_batch_start(self, trainer, pl_module, batch, batch_idx):
+                if batch_idx == warmup:
+                    torch.cuda.synchronize()
+                    self.e0.record()
+
+            def on_train_batch_end(self, trainer, pl_module, outputs, batch, batch_idx):
+                if batch_idx >= warmup:
+                    self.n += 1
+                if batch_idx == warmup + steps - 1:
+                    self.e1.record()
+
+        timer = Timer()
+        tr = pl.Trainer(max_epochs=1, limit_train_batches=n_batches, callbacks=[timer], logger=None, log_every_n_steps=10 ** 9,
+                        devices=1, accelerator="gpu", precision="16-mixed")
+        tr.fit(lit, datamodule=dm)
+        torch.cuda.synchronize()
+        if timer.n != steps:
+            return {"error": f"module path ran {timer.n} timed steps, wanted {steps}"}
+        ms = timer.e0.elapsed_time(timer.e1) / steps
+        return {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warmup, "per_gpu_batch": B,
+                "api": "Trainer.fit(MultiModalDINOLightning(CentralMultiModalEncoder), AVMNISTDinoDataModule(device_resident=True)): "
+                       "training_step -> loss.backward() -> B200Adam.step(), reference flow run_dino.py:356-373",
+                "last_loss": float(tr.callback_metrics.get("train_loss", float("nan")))}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -564,6 +622,14 @@ def run_ours(args):
         rate, _, desc = cpu_reference(REF_SAMPLE_BATCH, 3, 1, cores)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"each step = a {REF_SAMPLE_BATCH}-sample slice of the workload batch; " + desc}
+    drop_in = None
+    if world == 1 and args.kind == "multi_central" and args.mode == "default" and not args.no_module_path:
+        try:
+            del eng
+            torch.cuda.empty_cache()
+            drop_in = run_module_path(args, B, min(args.steps, 20), 3)
+        except Exception as exc:        # reported, never hidden: the engine numbers above stand on their own
+            drop_in = {"error": f"{type(exc).__name__}: {exc}"}
     h2d = img_h.numel() * 4 + (aud_h.numel() if aud_h is not None else 0)
     line = {"metric": METRIC, "value": B * world / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
@@ -576,7 +642,8 @@ def run_ours(args):
                     "ms_per_step": ms_e2e, "last_loss": last,
                     "note": "every step: H2D of its raw batch from pinned memory + D2H of its total loss (fp32 scalar, read back one "
                             "call later so that the host never waits for the step it has just enqueued)"},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "hbm_kernels": hbm, "cpu_baseline": cpu, "impl": "ours"}
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "hbm_kernels": hbm, "cpu_baseline": cpu, "drop_in_module_path": drop_in,
+            "impl": "ours"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -592,6 +659,7 @@ def main():
     ap.add_argument("--global-batch", type=int, default=0,
                     help="STRONG scaling: total batch over all GPUs (per-GPU batch = global / N); overrides --batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-module-path", action="store_true", help="skip the Trainer.fit (drop-in module path) throughput measurement")
     ap.add_argument("--reference-device", default="cpu", choices=["cpu", "gpu"],
                     help="--impl reference only: 'gpu' times the same oracle step with stock PyTorch kernels on cuda:0 (library bar)")
     ap.add_argument("--reference-fp32", action="store_true", help="library bar without fp16 autocast")

@@ -122,8 +122,13 @@ def _bn_eval(z, p, buf, bn):
                         training=False, eps=1e-5)
 
 
+TRACE = None        # tests may set this to a dict: conv name -> list of pre-BatchNorm outputs z, one per call (view-call order)
+
+
 def _block(x, p, buf, conv, bn, pad, train=True):
     z = F.conv2d(x, p[f"{conv}.weight"], p[f"{conv}.bias"], padding=pad)
+    if TRACE is not None:
+        TRACE.setdefault(conv, []).append(z.detach())
     y = _bn_train(z, p, buf, bn) if train else _bn_eval(z, p, buf, bn)
     return F.max_pool2d(F.relu(y), 2)
 
