@@ -314,6 +314,20 @@ int b200_counters_advance(int64_t* counters, int n, void* stream);
 /* y <- y * alpha (used to apply an upstream autograd scale / the 1/world_size of the gradient all-reduce) */
 int b200_scale_flat(float* y, int64_t n, float alpha, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * kNN evaluation of frozen encoder features -- train_knn_classifier,
+ * training_structures/dino_train.py:349-368: sklearn KNeighborsClassifier(n_neighbors=5) = Euclidean distance, uniform
+ * weights, majority vote, vote ties -> smallest class label.
+ *   ||a - b||^2 = ||a||^2 - 2 (a.b - ||b||^2 / 2): score(i, j) = a_i . b_j - ||b_j||^2 / 2 is ONE exact-fp32 GEMM with a bias
+ *   (b200_linear_fwd with x = test features [M,D], w = train features [N,D], bias = b200_knn_neg_half_sqnorm(train));
+ *   b200_knn_topk_vote picks the k largest scores of every row (equal scores -> smaller train index) and votes.
+ *   scores [M, lds >= N] fp32; labels int64 [N] in [0, n_classes), n_classes <= 32; k <= 16; pred int64 [M];
+ *   neighbours (optional, may be NULL) int32 [M, k] = train indices, nearest first.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200_knn_neg_half_sqnorm(const float* x, int64_t ldx, int N, int D, float* out, void* stream);
+int b200_knn_topk_vote(const float* scores, int64_t lds, const int64_t* labels, int M, int N, int k, int n_classes,
+                       int64_t* pred, int32_t* neighbours, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

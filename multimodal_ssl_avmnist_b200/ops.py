@@ -526,10 +526,32 @@ def bn1d_gelu_drop_bwd_apply(h, dg, scale, shift, mean, invstd, mask, drop_p, su
                                                      _stream()), "bn1d_gelu_drop_bwd_apply")
 
 
+# ---- kNN evaluation of frozen features -----------------------------------------------------------------
+def knn_predict(train_feats, train_labels, test_feats, k=5, n_classes=10, return_neighbours=False, chunk=2048):
+    """sklearn KNeighborsClassifier(n_neighbors=k).fit(train).predict(test) on device features (training_structures/dino_train.py:
+    349-368): exact-fp32 score GEMM (a.b - |b|^2/2, larger = nearer) + per-row top-k + majority vote, `chunk` test rows at a time."""
+    N, D = train_feats.shape
+    M = test_feats.shape[0]
+    dev = train_feats.device
+    bias = torch.empty(N, dtype=F32, device=dev)
+    tp, ldt = _rows(train_feats)
+    _lib.check(_lib_().b200_knn_neg_half_sqnorm(tp, ldt, N, D, _ptr(bias, F32), _stream()), "knn_neg_half_sqnorm")
+    pred = torch.empty(M, dtype=I64, device=dev)
+    nbr = torch.empty(M, k, dtype=I32, device=dev) if return_neighbours else None
+    scores = torch.empty(min(chunk, M), N, dtype=F32, device=dev)
+    labels = train_labels.to(I64).contiguous()
+    for lo in range(0, M, chunk):
+        hi = min(M, lo + chunk)
+        linear_fwd(test_feats[lo:hi], train_feats, bias, scores[:hi - lo])
+        _lib.check(_lib_().b200_knn_topk_vote(_ptr(scores, F32), N, _ptr(labels, I64), hi - lo, N, k, n_classes, pred[lo:hi].data_ptr(),
+                                              nbr[lo:hi].data_ptr() if nbr is not None else None, _stream()), "knn_topk_vote")
+    return (pred, nbr) if return_neighbours else pred
+
+
 # ---- launch accounting and optional per-op timing ------------------------------------------------------------
 # Every wrapper above issues a fixed number of kernel launches; the table lists the ones that issue more than one.
 _LAUNCHES = {"ntxent_fwd_bwd": 5, "conv_tc_wgrad_l0_fused": 3, "conv_tc_wgrad": 2, "conv_bwd_weight": 3, "linear_bwd_weight": 3, "infonce_fwd_bwd": 9}
-_NOT_KERNELS = {"quad8_width", "ntxent_work_floats", "conv_tc_wgrad_l0_fused_work_floats", "conv_tc_wgrad_work_floats", "conv_tc_supported", "conv_tc_weight_bytes", "dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
+_NOT_KERNELS = {"knn_predict", "quad8_width", "ntxent_work_floats", "conv_tc_wgrad_l0_fused_work_floats", "conv_tc_wgrad_work_floats", "conv_tc_supported", "conv_tc_weight_bytes", "dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
 LAUNCH_COUNT = 0
 _PROFILE = None          # None, or a list receiving (name, start_event, end_event, meta)
 

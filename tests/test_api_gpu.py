@@ -227,6 +227,20 @@ def test_feature_path_and_linear_probe(tmp_path):
     tr = pl.Trainer(max_epochs=1, logger=CSVLogger(str(tmp_path), name="logs"), log_every_n_steps=1, devices=1, accelerator="gpu")
     tr.fit(lit2, datamodule=dm)
     assert "mlp_acc" in tr.callback_metrics and 0.0 <= float(tr.callback_metrics["mlp_acc"]) <= 100.0
+    # kNN evaluation of the frozen encoder (training_structures/dino_train.py:349-368) on the CUDA feature + kNN kernels
+    from training_structures.dino_train import train_knn_classifier
+    from sklearn.neighbors import KNeighborsClassifier
+    train_loader, val_loader = dm.probe_dataloaders()
+    knn, acc = train_knn_classifier(lit2.model, train_loader, val_loader, n_neighbors=5, device=DEV)
+    assert 0.0 <= acc <= 100.0 and knn.train_features.shape[1] == 256 and knn.train_features.is_cuda
+    fx2 = md.FeatureExtractor(lit2.model).eval()
+    xs, ys = [], []
+    for b in val_loader:
+        xs.append(fx2(b[0].to(DEV), b[1].to(DEV)).cpu())
+        ys.append(b[2])
+    xs, ys = torch.cat(xs), torch.cat(ys)
+    sk = KNeighborsClassifier(n_neighbors=5).fit(knn.train_features.cpu().numpy(), knn.train_labels.cpu().numpy())
+    assert abs(100.0 * sk.score(xs.numpy(), ys.numpy()) - acc) <= 100.0 / len(ys) + 1e-6      # same features -> same accuracy (one near-tie allowed)
 
 
 def test_standalone_ntxent_is_a_drop_in_for_the_reference_loss():

@@ -514,3 +514,33 @@ def test_ntxent_vs_oracle(B, D, golden):
     assert abs(float(loss) - float(want)) < 1e-5 * abs(float(want)) + 1e-6
     ref = want_in.grad.float()
     assert float((grad.cpu() - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 1e-8
+
+
+def test_knn_matches_sklearn_and_fp64_brute_force():
+    """train_knn_classifier (training_structures/dino_train.py:349-368) = sklearn KNeighborsClassifier(5).  Device path:
+    exact-fp32 score GEMM + top-k + vote; checked against sklearn's predictions and an fp64 brute-force neighbour search."""
+    from sklearn.neighbors import KNeighborsClassifier
+    g = torch.Generator().manual_seed(3)
+    N, M, D, k = 6000, 1500, 256, 5
+    centers = torch.randn(10, D, generator=g) * 1.5
+    ytr = torch.randint(0, 10, (N,), generator=g)
+    yte = torch.randint(0, 10, (M,), generator=g)
+    xtr = centers[ytr] + torch.randn(N, D, generator=g) * 2.0
+    xte = centers[yte] + torch.randn(M, D, generator=g) * 2.0
+    pred, nbr = ops.knn_predict(xtr.to(DEV), ytr.to(DEV), xte.to(DEV), k=k, n_classes=10, return_neighbours=True, chunk=640)
+    torch.cuda.synchronize()
+    pred, nbr = pred.cpu(), nbr.cpu().long()
+    d = torch.cdist(xte.double(), xtr.double())
+    want_nbr = d.topk(k, dim=1, largest=False).indices
+    same_sets = (nbr.sort(1).values == want_nbr.sort(1).values).all(1).float().mean()
+    assert float(same_sets) > 0.998, float(same_sets)
+    assert (nbr[:, 0] == want_nbr[:, 0]).float().mean() > 0.998          # nearest first
+    sk = KNeighborsClassifier(n_neighbors=k).fit(xtr.numpy(), ytr.numpy())
+    want = torch.from_numpy(sk.predict(xte.numpy()))
+    assert float((pred == want).float().mean()) > 0.998, float((pred == want).float().mean())
+    # vote ties go to the smallest label, equal scores to the smaller train index: a hand-made case
+    xt = torch.tensor([[0.0, 0.0], [2.0, 0.0], [0.0, 2.0], [-2.0, 0.0], [9.0, 9.0]])
+    yt = torch.tensor([3, 1, 3, 1, 0])
+    q = torch.tensor([[0.0, 0.0]])
+    p4, n4 = ops.knn_predict(xt.to(DEV), yt.to(DEV), q.to(DEV), k=4, n_classes=10, return_neighbours=True)
+    assert int(p4[0]) == 1 and n4[0].tolist() == [0, 1, 2, 3]               # 2 votes each for labels 1 and 3 -> 1
