@@ -481,7 +481,7 @@ def run_ours(args):
         eng.train_step(img_d, aud_d, lab_d)
         eng.prefetch_augment(img_d, aud_d)
     barrier()
-    use_graph = bool(args.graph) and world == 1
+    use_graph = bool(args.graph)             # data parallel too: the NCCL all-reduces (C ABI) are captured with the kernels
     graph_launches = None
     if use_graph:
         eng._prefetch = None
@@ -664,8 +664,8 @@ def main():
                     help="--impl reference only: 'gpu' times the same oracle step with stock PyTorch kernels on cuda:0 (library bar)")
     ap.add_argument("--reference-fp32", action="store_true", help="library bar without fp16 autocast")
     ap.add_argument("--graph", action="store_true",
-                    help="replay the whole step from one CUDA graph (single GPU; meant for small per-GPU batches, where the "
-                         "~165 host-side launches bound the step)")
+                    help="replay the whole step from one CUDA graph (meant for small per-GPU batches, where the ~165 host-side "
+                         "launches bound the step; with N > 1 the all-reduces are captured too)")
     ap.add_argument("--kind", default="multi_central", choices=["multi_central", "image_simple"],
                     help="image_simple = BASELINE.json configs[0] (unimodal image DINO); the headline line is multi_central")
     ap.add_argument("--mode", default="default", choices=["default", "semi_supervised", "infonce", "mse"],

@@ -328,6 +328,24 @@ int b200_knn_neg_half_sqnorm(const float* x, int64_t ldx, int N, int D, float* o
 int b200_knn_topk_vote(const float* scores, int64_t lds, const int64_t* labels, int M, int N, int k, int n_classes,
                        int64_t* pred, int32_t* neighbours, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Data-parallel exchange -- what Lightning's strategy="ddp" (run_dino.py:359) does for the reference: ONE
+ * NCCL communicator per process (one process per GPU).  Rank 0 calls b200_dp_unique_id and ships the 128 bytes to the other
+ * ranks by any means (the Python host uses the torch.distributed store); every rank then calls b200_dp_init with its GPU
+ * current.  The two all-reduces (sum, fp32, in place) are asynchronous on `stream` and may be captured into a CUDA graph.
+ *   b200_dp_allreduce_grads  -- a slice of the flat gradient arena (the 1/world average is folded into Adam's grad_scale)
+ *   b200_dp_allreduce_center -- the [D] column sums of the un-centred teacher projections (then b200_center_apply)
+ * NCCL is bound at run time with dlopen (no link-time dependency); return codes >= 1000 are 1000 + ncclResult_t.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200_dp_nccl_version(void);
+int b200_dp_unique_id(char* id_out /* 128 bytes */);
+int b200_dp_init(const char* id /* 128 bytes */, int rank, int world);
+int b200_dp_world(void);
+int b200_dp_rank(void);
+int b200_dp_allreduce_grads(float* grad, int64_t n, void* stream);
+int b200_dp_allreduce_center(float* colsum, int D, void* stream);
+int b200_dp_destroy(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libavmnist_b200.so")
-SOURCES = ["core.cu", "loss.cu", "augment.cu", "encoder.cu", "linear.cu", "conv_tc.cu", "act8.cu", "gemm_tc.cu", "knn.cu"]  # missing files are skipped
+SOURCES = ["core.cu", "loss.cu", "augment.cu", "encoder.cu", "linear.cu", "conv_tc.cu", "act8.cu", "gemm_tc.cu", "knn.cu", "dp.cu"]  # missing files are skipped
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
@@ -55,7 +55,7 @@ def build(force=False, verbose=False):
         with open(os.path.join(HERE, "build", name.replace(".cu", ".ptxas.log")), "w") as f:
             f.write(out)
     if relink or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]
         subprocess.check_call(cmd)
     return LIB
 

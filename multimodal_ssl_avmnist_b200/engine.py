@@ -193,6 +193,10 @@ class DinoStepEngine:
         self.n_trainable_prefix = self.student.range_of([n for n, _ in enc_used + head])[1]
         self.aux_range = self.student.range_of([n for n, _ in aux]) if aux else None
         self.grad_plan = dp.GradientPlan([(0, self.n_trainable_prefix)] + ([self.aux_range] if self.aux_range else []))
+        # gradient exchange in two slices: [split, end of the trainable prefix) -- audio encoder linear, fusion MLP, projection head:
+        # complete as soon as the linear weight gradients are (early in the backward pass), exchanged beside the conv stacks'
+        # backward -- and [0, split): the conv stacks + the image encoder linear, complete at the end of the backward pass
+        self._bucket_split = self.student.offsets["enc.audio_encoder.1.weight"][0] if kind == "multi_central" else 0
         self._grad_scale = 1.0
         self.grad = torch.zeros_like(self.student.flat)
         self.exp_avg = torch.zeros_like(self.student.flat)
@@ -236,6 +240,11 @@ class DinoStepEngine:
         self._side_stream2 = torch.cuda.Stream(device=self.device)
         self._wgrad_streams = {m: torch.cuda.Stream(device=self.device) for m in ("img", "aud")}
         self._aug_stream = torch.cuda.Stream(device=self.device)
+        # data parallel: the exchange runs inside the C ABI (NCCL, b200_dp_*) on a communication stream beside the compute streams
+        self.comm = dp.AbiComm.get(process_group) if self.world > 1 else None
+        self._comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
+        self._center_ready = None          # event: the all-reduced centre EMA of the last step has landed
+        self._comm_pending = False         # gradient all-reduces in flight on the communication stream
         self._prefetch, self._step_done, self._step_done_prev = None, None, None
         self._eval_wrole = "s"
         self._ws = {}
@@ -290,6 +299,13 @@ class DinoStepEngine:
         if B in self._ws:
             return self._ws[B]
         dev, V, Vg = self.device, self.V, self.Vg
+        if self.world > 1:
+            # the gradient average (sum / world) and the centre mean (rows * world) assume equal per-rank batches: refuse otherwise
+            lohi = torch.tensor([B, -B], dtype=torch.int64, device=dev)
+            torch.distributed.all_reduce(lohi, op=torch.distributed.ReduceOp.MAX, group=self.pg)
+            if int(lohi[0]) != B or int(-lohi[1]) != B:
+                raise ops._lib.B200Error(f"data parallel: per-rank batch sizes differ ({int(-lohi[1])}..{int(lohi[0])}); use equal shards "
+                                         "(drop_last) -- the gradient average and the centre EMA weight every rank equally")
         extra = 1 if self.mode != "default" else 0
         Ns, Nt = (V + extra) * B, Vg * B
 
@@ -797,6 +813,7 @@ class DinoStepEngine:
         multi = self.kind == "multi_central"
         xi = w["x_img"]
         xa = w["x_aud"] if multi else None
+        self._join_center()
         w["zarena"].zero_()                             # all statistics / backward-sum accumulators of this step
         packed = x_img.dtype == torch.bfloat16          # augment(direct=True): the quad8 workspace images are already filled
         w["packed"] = packed
@@ -871,12 +888,24 @@ class DinoStepEngine:
                               variant=variant, t_colmean=w["t_colmean"] if variant == 1 else None)
         loss = w["loss"]
         if self.world > 1:
-            # data parallel: centre = EMA of the mean over ALL ranks' teacher rows
+            # data parallel: centre = EMA of the mean over ALL ranks' teacher rows.  The centre is next read by the NEXT
+            # step's loss, so the 512-byte all-reduce + EMA run on the communication stream and never stall the backward pass
             ops.center_update(None, w["part_colsum"], w["part_loss"], Vg * B, self.center_momentum, loss[0:1], colsum_out=w["colsum"][:P])
-            rows = dp.allreduce_colsum_(w["colsum"][:P], Vg * B, self.pg)
-            ops.center_apply(self.center, w["colsum"][:P], rows, self.center_momentum)
+            main, cs = torch.cuda.current_stream(), self._comm_stream
+            cs.wait_stream(main)
+            with torch.cuda.stream(cs):
+                self.comm.allreduce_center_(w["colsum"][:P], cs.cuda_stream)
+                ops.center_apply(self.center, w["colsum"][:P], Vg * B * self.world, self.center_momentum)
+                self._center_ready = torch.cuda.Event()
+                self._center_ready.record(cs)
         else:
             ops.center_update(self.center, w["part_colsum"], w["part_loss"], Vg * B, self.center_momentum, loss[0:1])
+
+    def _join_center(self):
+        """Make the current stream wait for the last step's all-reduced centre EMA (data parallel only)."""
+        if self._center_ready is not None:
+            torch.cuda.current_stream().wait_event(self._center_ready)
+            self._center_ready = None
 
     def aux_loss_pass(self, w, labels=None):
         """MSE / InfoNCE / CE on the mode heads' outputs, forward+backward fused (fills w['aux_*.d.out'], loss[1])."""
@@ -932,6 +961,8 @@ class DinoStepEngine:
                 with ctx:
                     p_last = w[f"s.{mod}.p{len(layers) - 1}"].view(Ns, nflat)
                     self._lin_wgrad(d_cat[:, sl], p_last, G[lin + ".weight"], G[lin + ".bias"])
+                    if mod == "aud" and self.world > 1:
+                        self._exchange_late_gradients()
                     d_p = w[f"{mod}.dp_a"][:Ns * nflat].view(Ns, nflat)
                     ops.linear_bwd_data(d_cat[:, sl], S[lin + ".weight"], d_p, tc=self.lin_tc)
                     self._conv_stack_bwd(w, mod, layers, x, d_p, Ns, B)
@@ -950,6 +981,19 @@ class DinoStepEngine:
             self._lin_wg_pending = False
         if self.world > 1:
             self.allreduce_gradients()
+
+    def _exchange_late_gradients(self):
+        """The gradients of [audio encoder linear | fusion MLP | projection head] (+ the mode heads) are complete once the linear
+        weight gradients issued so far are: all-reduce them on the communication stream while the conv stacks run backward."""
+        main, cs = torch.cuda.current_stream(), self._comm_stream
+        cs.wait_stream(main)
+        if self._lin_wg_pending:
+            cs.wait_stream(self._lin_wg_stream)
+        with torch.cuda.stream(cs):
+            self.comm.allreduce_grads_(self.grad[self._bucket_split:self.n_trainable_prefix], cs.cuda_stream)
+            if self.aux_range is not None:
+                self.comm.allreduce_grads_(self.grad[self.aux_range[0]:self.aux_range[1]], cs.cuda_stream)
+        self._comm_pending = "late"
 
     def forward_backward(self, x_img, x_aud, masks=None, raw=None, labels=None):
         """Student + teacher forward, losses, centre EMA and the full backward for already-augmented views.
@@ -970,9 +1014,19 @@ class DinoStepEngine:
         return loss
 
     def allreduce_gradients(self):
-        """Data parallel exchange: ONE NCCL all-reduce of the trainable gradient prefix (+ one for the mode heads);
-        the 1/world average is folded into Adam's grad_scale."""
-        self._grad_scale = self.grad_plan.allreduce_(self.grad, self.pg)
+        """Data parallel exchange of the gradient arena through the C ABI (NCCL): the slices that were not exchanged during the
+        backward pass, on the communication stream; Adam joins that stream.  The 1/world average is folded into Adam's grad_scale."""
+        main, cs = torch.cuda.current_stream(), self._comm_stream
+        cs.wait_stream(main)
+        with torch.cuda.stream(cs):
+            if self._comm_pending == "late":
+                if self._bucket_split > 0:
+                    self.comm.allreduce_grads_(self.grad[:self._bucket_split], cs.cuda_stream)
+            else:
+                for lo, hi in self.grad_plan.ranges:
+                    self.comm.allreduce_grads_(self.grad[lo:hi], cs.cuda_stream)
+        self._comm_pending = True
+        self._grad_scale = 1.0 / self.world
 
     def update_teacher(self):
         """Teacher EMA over the whole common arena prefix: one kernel (models/dino.py:635-646)."""
@@ -981,6 +1035,9 @@ class DinoStepEngine:
     def optimizer_step(self, grad_scale=None):
         """Adam (lr, weight_decay; models/dino.py:953-962) over the parameters that received gradients."""
         self.step_count += 1
+        if self._comm_pending:          # the gradient all-reduces of this step (the teacher EMA before this call overlapped them)
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+            self._comm_pending = False
         gs = self._grad_scale if grad_scale is None else grad_scale
         n = self.n_trainable_prefix
         ranges = [(0, n)] + ([self.aux_range] if self.aux_range is not None else [])
@@ -1020,6 +1077,7 @@ class DinoStepEngine:
         loss = self.forward_backward(x_img, x_aud, masks=masks, raw=raw, labels=labels)
         self.update_teacher()
         self.optimizer_step()
+        self._join_center()
         self.rng_step += 1
         if self._ctr is not None:
             ops.counters_advance(self._ctr)
@@ -1053,10 +1111,9 @@ class DinoStepEngine:
     def capture_train_step(self, B, image_dtype=torch.float32, audio_dtype=torch.uint8):
         """Captures train_step (sampling, augmentation, forward, losses, EMA, backward, Adam, all side streams) for per-GPU batch
         B into ONE CUDA graph.  The per-step scalars (RNG stream position, Adam step) move to device counters that the graph
-        advances itself, so a replay needs no host arguments and reproduces the eager step bit for bit.  Single GPU; lr /
-        temperatures are baked in (re-capture after changing them).  Use graph_step() afterwards."""
-        if self.world > 1:
-            raise ops._lib.B200Error("capture_train_step: the data-parallel exchange is not captured; use train_step")
+        advances itself, so a replay needs no host arguments and reproduces the eager step bit for bit.  Data parallel: the
+        NCCL all-reduces (b200_dp_*, communication stream) are captured with the kernels; every rank must capture and replay in
+        lock-step.  lr / temperatures are baked in (re-capture after changing them).  Use graph_step() afterwards."""
         dev = self.device
         g = {"B": B, "img": torch.zeros(B, 28, 28, dtype=image_dtype, device=dev)}
         if self.aud_layers:

@@ -66,6 +66,32 @@ for mode in ("default", "infonce"):
     ok &= same
     if rank == 0:
         print(f"mode={mode} replicas identical after 3 steps on different shards: {same}")
+# CUDA-graph replay of the data-parallel step: the NCCL all-reduces (C ABI, communication stream) are captured with the kernels
+eager = DinoStepEngine(kind="multi_central", mode="default", seed=11 + rank, device=dev)
+graph = DinoStepEngine(kind="multi_central", mode="default", seed=11 + rank, device=dev)
+graph.student.flat.copy_(eager.student.flat)
+graph.sync_teacher()
+eager.sync_teacher()
+gen = torch.Generator().manual_seed(1000 + rank)
+batches = [(torch.rand(B, 28, 28, generator=gen).to(dev), torch.randint(0, 256, (B, 112, 112), generator=gen, dtype=torch.uint8).to(dev))
+           for _ in range(4)]
+eager.train_step(*batches[0])
+graph.train_step(*batches[0])
+graph.capture_train_step(B)
+for img, aud in batches[1:]:
+    eager.train_step(img, aud)
+    graph.graph_step(img, aud)
+torch.cuda.synchronize()
+same_graph = torch.equal(eager.student.flat, graph.student.flat) and torch.equal(eager.teacher.flat, graph.teacher.flat) \
+    and torch.equal(eager.center, graph.center)
+chk = eager.student.flat.double().sum().reshape(1)
+gathered = [torch.empty_like(chk) for _ in range(world)]
+dist.all_gather(gathered, chk)
+same_graph &= all(torch.equal(gathered[0], g_) for g_ in gathered)
+ok &= same_graph
+if rank == 0:
+    print(f"data-parallel CUDA-graph replay == eager data-parallel steps (bit for bit, replicas identical): {same_graph}; "
+          f"NCCL {eager.comm.version} through the C ABI")
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
