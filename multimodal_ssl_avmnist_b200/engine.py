@@ -243,6 +243,10 @@ class DinoStepEngine:
         # data parallel: the exchange runs inside the C ABI (NCCL, b200_dp_*) on a communication stream beside the compute streams
         self.comm = dp.AbiComm.get(process_group) if self.world > 1 else None
         self._comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
+        # exchange the late-layout gradient slice beside the conv stacks' backward?  Measured at N = 2 (profiles/r2c_*): the NCCL CTAs
+        # take SMs from the persistent conv kernels (grids sized to fill the GPU) and the step gets 0.13 ms SLOWER, so the default
+        # is one exchange at the end of the backward pass (it still overlaps the teacher EMA)
+        self.overlap_grad_exchange = False
         self._center_ready = None          # event: the all-reduced centre EMA of the last step has landed
         self._comm_pending = False         # gradient all-reduces in flight on the communication stream
         self._prefetch, self._step_done, self._step_done_prev = None, None, None
@@ -961,7 +965,7 @@ class DinoStepEngine:
                 with ctx:
                     p_last = w[f"s.{mod}.p{len(layers) - 1}"].view(Ns, nflat)
                     self._lin_wgrad(d_cat[:, sl], p_last, G[lin + ".weight"], G[lin + ".bias"])
-                    if mod == "aud" and self.world > 1:
+                    if mod == "aud" and self.world > 1 and self.overlap_grad_exchange:
                         self._exchange_late_gradients()
                     d_p = w[f"{mod}.dp_a"][:Ns * nflat].view(Ns, nflat)
                     ops.linear_bwd_data(d_cat[:, sl], S[lin + ".weight"], d_p, tc=self.lin_tc)

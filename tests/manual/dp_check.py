@@ -67,8 +67,9 @@ for mode in ("default", "infonce"):
     if rank == 0:
         print(f"mode={mode} replicas identical after 3 steps on different shards: {same}")
 # CUDA-graph replay of the data-parallel step: the NCCL all-reduces (C ABI, communication stream) are captured with the kernels
-eager = DinoStepEngine(kind="multi_central", mode="default", seed=11 + rank, device=dev)
-graph = DinoStepEngine(kind="multi_central", mode="default", seed=11 + rank, device=dev)
+eager = DinoStepEngine(kind="multi_central", mode="default", seed=11, device=dev)      # same initial weights on every rank ...
+graph = DinoStepEngine(kind="multi_central", mode="default", seed=11, device=dev)
+eager.seed = graph.seed = 11 + rank                                                    # ... different augmentation / dropout streams
 graph.student.flat.copy_(eager.student.flat)
 graph.sync_teacher()
 eager.sync_teacher()
@@ -87,10 +88,10 @@ same_graph = torch.equal(eager.student.flat, graph.student.flat) and torch.equal
 chk = eager.student.flat.double().sum().reshape(1)
 gathered = [torch.empty_like(chk) for _ in range(world)]
 dist.all_gather(gathered, chk)
-same_graph &= all(torch.equal(gathered[0], g_) for g_ in gathered)
-ok &= same_graph
+same_replicas = all(torch.equal(gathered[0], g_) for g_ in gathered)
+ok &= same_graph and same_replicas
 if rank == 0:
-    print(f"data-parallel CUDA-graph replay == eager data-parallel steps (bit for bit, replicas identical): {same_graph}; "
+    print(f"data-parallel CUDA-graph replay == eager data-parallel steps (bit for bit): {same_graph}; replicas identical: {same_replicas}; "
           f"NCCL {eager.comm.version} through the C ABI")
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
