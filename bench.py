@@ -240,6 +240,20 @@ def op_cost(name, meta):
         Ho, Wo = H + 2 * pad - K + 1, W + 2 * pad - K + 1
         out_bytes = numel(out) * (4 if len(out) == 4 else 2)
         return 2.0 * N * Cout * Ho * Wo * Cin * K * K, numel(x) * 2.0 + out_bytes
+    if name == "conv_tc_pool" and len(meta) >= 5 and len(ints) >= 4:
+        # (x8 | quad8, wprep, bias, gamma, [z], e) + (n_per_view, Cout, K, pad): forward conv whose epilogue also emits the 2x2 window
+        # extreme e (fp16, a quarter of z); z is only written for the student
+        x, e8 = meta[0], meta[-1]
+        n_per_view, Cout, K, pad = ints[:4]
+        if len(x) == 4:
+            N, H, W, Cin = x[0], x[1], x[1], 1
+        else:
+            N, H, W, Cin = x[0], x[2], x[3], x[1] * 8
+        Ho, Wo = H + 2 * pad - K + 1, W + 2 * pad - K + 1
+        z_bytes = numel(meta[-2]) * 2.0 if len(meta) >= 6 else 0.0
+        return 2.0 * N * Cout * Ho * Wo * Cin * K * K, numel(x) * 2.0 + z_bytes + numel(e8) * 2.0
+    if name == "bn_relu_apply8" and len(meta) >= 4:
+        return 0.0, numel(meta[0]) * 2.0 + numel(meta[3]) * (2.0 if len(meta[3]) == 5 else 4.0)
     if name == "conv_tc_wgrad" and len(meta) >= 3:
         x, dz, dw = meta[0], meta[1], meta[2]
         Cout, Cin, K, _ = dw
@@ -463,7 +477,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     B = per_gpu_batch(args, world)
     eng = DinoStepEngine(kind=args.kind, mode=args.mode, augment_values=augment_values() if args.kind == "multi_central" else None,
-                         seed=1 + rank, device=dev)
+                         seed=1 + rank, device=dev, fused_pool=not args.no_fused_pool)
     g = torch.Generator().manual_seed(1 + rank)
     img_h = torch.rand(B, 28, 28, generator=g).pin_memory()
     aud_h = torch.randint(0, 256, (B, 112, 112), generator=g, dtype=torch.uint8).pin_memory() if args.kind == "multi_central" else None
@@ -594,7 +608,7 @@ def run_ours(args):
         if NCU_EXTRA.get("tensor_pipe_busy_pct", 0) > 80:
             roof["note"] = (roof.get("note", "") + "; ncu: the tensor pipe is busy %.0f %% of the time (a UMMA occupies it for its shared-memory operand "
                             "fetch whatever its N): the kernel's real ceiling" % NCU_EXTRA["tensor_pipe_busy_pct"]).lstrip("; ")
-    tc_rows = [r for r in rows if r["op"] in ("conv_tc", "conv_tc_wgrad")]
+    tc_rows = [r for r in rows if r["op"] in ("conv_tc", "conv_tc_pool", "conv_tc_wgrad")]
     if tc_rows:
         tc_ms = sum(r["ms_per_step"] for r in tc_rows)
         tc_fl = sum(r["flops"] * r["calls_per_step"] for r in tc_rows)
@@ -663,6 +677,8 @@ def main():
     ap.add_argument("--reference-device", default="cpu", choices=["cpu", "gpu"],
                     help="--impl reference only: 'gpu' times the same oracle step with stock PyTorch kernels on cuda:0 (library bar)")
     ap.add_argument("--reference-fp32", action="store_true", help="library bar without fp16 autocast")
+    ap.add_argument("--no-fused-pool", action="store_true",
+                    help="A/B: the round-1 forward (full-resolution z -> bn_relu_pool8_fwd) instead of the fused max-pool epilogue")
     ap.add_argument("--graph", action="store_true",
                     help="replay the whole step from one CUDA graph (meant for small per-GPU batches, where the ~165 host-side "
                          "launches bound the step; with N > 1 the all-reduces are captured too)")

@@ -195,6 +195,21 @@ int64_t b200_conv_tc_wgrad_l0_fused_work_floats(int N, int n_per_view, int Cout,
 int b200_conv_tc_wgrad_l0_fused(const void* x_quad8, const void* z8, const void* dp8, const float* scale, const float* shift,
                                 const float* mean, const float* invstd, const double* sums, float* dw, double* dbsum,
                                 float* work, int N, int n_per_view, int Cout, int H, int W, int K, int pad, void* stream);
+/* Forward convolution with the 2x2 max-pool FUSED INTO ITS EPILOGUE (conv -> BatchNorm -> ReLU -> MaxPool2 of
+ * models/unimodal.py:129-140, 186-208; models/dino.py:20-30).  Train-mode BatchNorm is a*z + b with a = gamma * invstd, so
+ * ReLU(maxpool(a z + b)) = ReLU(a ext(z) + b) with ext = max where gamma >= 0 and min where gamma < 0 -- known BEFORE the batch
+ * statistics are.  The epilogue therefore emits, besides the statistics, the window extreme `pool_out` (fp16 act8
+ * [N][Cout/8][Ho/2][Wo/2][8], a quarter of z) and b200_bn_relu_apply8 finishes p = ReLU(a e + b) once b200_bn_finalize has run:
+ * bit-identical to b200_bn_relu_pool8_fwd on the full-resolution z.  z_out (fp16 / bf16 act8, z_fmt 2 / 1) is still written for
+ * the student (its backward needs the dense z) and may be NULL for the teacher and for evaluation: full-resolution z then never
+ * leaves the SM.  gamma: the BatchNorm weight [Cout] (device pointer, read at kernel start). */
+int b200_conv_tc_pool_supported(int Cin, int Cout, int H, int W, int K, int pad);
+int b200_conv_tc_pool(const void* x_act8, const void* wprep, const float* bias, const float* gamma, void* z_out, void* pool_out,
+                      double* stats, int N, int n_per_view, int Cin, int Cout, int H, int W, int K, int pad, int z_fmt,
+                      void* stream);
+/* e8: fp16 act8 [N][C/8][HP][WP][8] from b200_conv_tc_pool; out_fmt 0 = fp32 NCHW [N][C][HP][WP], 1 = bf16 act8 */
+int b200_bn_relu_apply8(const void* e8, const float* scale, const float* shift, void* out, int N, int n_per_view, int C, int HP,
+                        int WP, int out_fmt, void* stream);
 /* BatchNorm-apply + ReLU + MaxPool2 on bf16 act8 activations (same reference call sites as b200_bn_relu_pool_*):
  *   z8 [N][C/8][H][W][8] bf16 (z_f16 = 0) or fp16 (z_f16 = 1) (H, W even); scale/shift/mean/invstd [views][C] from b200_bn_finalize;
  *   out_fmt / dp_fmt: 0 = fp32 NCHW [N][C][H/2][W/2], 1 = bf16 act8 [N][C/8][H/2][W/2][8];

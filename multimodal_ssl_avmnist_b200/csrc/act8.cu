@@ -121,6 +121,56 @@ __global__ void __launch_bounds__(256) bn_relu_pool8_fwd_kernel(const uint4* __r
     }
 }
 
+// BatchNorm-apply + ReLU on the POOLED extreme e (fp16 act8 [N][C/8][HP][WP][8]) that the convolution's fused max-pool epilogue
+// emitted (conv_tc.cu): p = ReLU(a e + b).  Because e = max(z) where gamma >= 0 and min(z) where gamma < 0 and a = gamma * invstd,
+// a e + b is exactly the maximum of a z + b over the window: bit-identical to bn_relu_pool8_fwd_kernel on the full-resolution z,
+// at a quarter of its reads.  Two adjacent units per thread (256-bit accesses) when the plane size is even.
+__global__ void __launch_bounds__(256) bn_relu_apply8_kernel(const uint4* __restrict__ e8, const float* __restrict__ scale,
+                                                             const float* __restrict__ shift, void* __restrict__ out, int n_per_view, int C,
+                                                             int HP, int WP, int out_fmt) {
+    const int oct = blockIdx.y, v = blockIdx.z, P = C >> 3;
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        a[j] = __ldg(scale + v * C + oct * 8 + j);
+        b[j] = __ldg(shift + v * C + oct * 8 + j);
+    }
+    const int hw = HP * WP;
+    const bool wide = ((hw & 1) == 0) && ((reinterpret_cast<uintptr_t>(e8) & 31) == 0) && (out_fmt == 0 || (reinterpret_cast<uintptr_t>(out) & 31) == 0);
+    const int step = wide ? 2 : 1;
+    const long units = (long)n_per_view * hw / step;
+    const long u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
+    for (long uu = u0 + threadIdx.x; uu < u1; uu += blockDim.x) {
+        const long u = uu * step;
+        const int s = (int)(u / hw), e = (int)(u - (long)s * hw);
+        const long n = (long)v * n_per_view + s;
+        const long base = (n * P + oct) * hw + e;
+        uint4 r0, r1 = make_uint4(0, 0, 0, 0);
+        if (wide) ld_pair(e8 + base, true, r0, r1);
+        else r0 = __ldg(e8 + base);
+        float w0[8], w1[8], m0[8], m1[8];
+        unpack8h(r0, w0);
+        unpack8h(r1, w1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            m0[j] = fmaxf(fmaf(a[j], w0[j], b[j]), 0.f);
+            m1[j] = fmaxf(fmaf(a[j], w1[j], b[j]), 0.f);
+        }
+        if (out_fmt) {
+            uint4* op = reinterpret_cast<uint4*>(out) + base;
+            if (wide) st_pair(op, true, pack8(m0), pack8(m1));
+            else *op = pack8(m0);
+        } else {
+            float* op = reinterpret_cast<float*>(out) + (n * C + oct * 8) * hw + e;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                op[(long)j * hw] = m0[j];
+                if (wide) op[(long)j * hw + 1] = m1[j];
+            }
+        }
+    }
+}
+
 // argmax in PyTorch scan order (first maximum wins)
 __device__ __forceinline__ int argmax4(float y0, float y1, float y2, float y3, float& m) {
     int k = 0;
@@ -429,6 +479,22 @@ int b200_bn_relu_pool8_fwd(const void* z8, const float* scale, const float* shif
         bn_relu_pool8_fwd_kernel<false><<<tile_grid(N, n_per_view, C, H, W), 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(z8), scale,
                                                                                                           shift, out, n_per_view, C, H, W, out_fmt);
     return launch_status("bn_relu_pool8_fwd_kernel");
+}
+
+int b200_bn_relu_apply8(const void* e8, const float* scale, const float* shift, void* out, int N, int n_per_view, int C, int HP, int WP,
+                        int out_fmt, void* stream) {
+    B200_REQUIRE(e8 && scale && shift && out, -1, "bn_relu_apply8: null pointer");
+    B200_REQUIRE(N > 0 && n_per_view > 0 && N % n_per_view == 0 && C > 0 && C % 8 == 0 && HP > 0 && WP > 0 && N / n_per_view <= 65535, -2,
+                 "bn_relu_apply8: bad shape");
+    const int views = N / n_per_view, P = C / 8;
+    const long units = (long)n_per_view * HP * WP;
+    long chunks = (8L * sm_count() + (long)views * P - 1) / ((long)views * P);
+    const long max_chunks = (units + 511) / 512;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    bn_relu_apply8_kernel<<<dim3((unsigned)chunks, (unsigned)P, (unsigned)views), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const uint4*>(e8), scale, shift, out, n_per_view, C, HP, WP, out_fmt);
+    return launch_status("bn_relu_apply8_kernel");
 }
 
 int b200_bn_relu_pool8_bwd_reduce(const void* z8, const void* dp, const float* scale, const float* shift, const float* mean,

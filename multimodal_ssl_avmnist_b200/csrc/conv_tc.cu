@@ -125,7 +125,19 @@ struct TcCfg {
     static_assert(!L0 || KWX <= 8, "first layer: all taps of all phases must lie inside one 8-pixel unit");
     static constexpr int IMG_BYTES = SLOTS * SLOT_BYTES + TAIL;
     static constexpr int BAR_OFF = W_BYTES + IMG_BYTES;
-    static constexpr int SMEM = BAR_OFF + 256 + NPADL * 4;
+    // Fused 2x2 max-pool of the forward layers (ReLU(maxpool(a z + b)) = ReLU(a ext(z) + b), ext = max or min by sign(gamma)): the
+    // epilogue keeps the horizontally pooled even rows in a small shared-memory ring ("stash": POOL_R pooled rows) until the odd
+    // row below them has been computed, then emits the window extreme -- a quarter of z.  A 128-row tile spans 128 / WQ image rows,
+    // so the ring holds every even row a tile can touch plus the ones the warps of the NEXT tile may already be writing.
+    static constexpr bool POOL_OK = (CIN_ == 1 || COUT_ > CIN_) && NSPLIT_ == 1 && HO % 2 == 0 && HB % 2 == 0 && WO % 2 == 0 &&
+                                    (XPH % 2 == 0 || WQ % 2 == 0);
+    static constexpr int POOL_R = 128 / WQ + 3;             // pooled rows of two consecutive tiles (a fast warp may be one tile phase ahead) + margin
+    static constexpr int OCTL = COUTL / 8;
+    static constexpr int POOL_ROW_UNITS = (WO / 2) * OCTL;       // 16-byte units (one pooled pixel of one channel octet, fp16) per pooled row
+    static constexpr int POOL_BYTES = POOL_OK ? POOL_R * POOL_ROW_UNITS * 16 : 0;
+    static constexpr int SIGN_OFF = BAR_OFF + 256 + NPADL * 4;   // per accumulator column pair: fp16 sign-bit masks (sign of gamma)
+    static constexpr int POOL_OFF = round_up(SIGN_OFF + NPADL * 2, 16);
+    static constexpr int SMEM = POOL_OFF + POOL_BYTES;
     static constexpr int NBUF = nbuf_for(NPADL, CTAS);          // TMEM accumulator stages
     static constexpr int TMEM_COLS = pow2_cols(NBUF * NPADL);
     // One issuing thread sustains only ~1 UMMA per 140 cycles at these tile shapes (measured, tools/umma_probe.cu); four
@@ -134,7 +146,7 @@ struct TcCfg {
     static constexpr int THREADS = 32 * (1 + ISS + 4);
     static_assert(NBUF % ISS == 0, "a TMEM stage must always be filled by the same issuer");
     static_assert(TMEM_COLS * CTAS <= 512, "TMEM columns per SM");
-    static_assert((SMEM_EST(NMMA, NPADL, SLOTS, SLOT_BYTES, TAIL) + 1024) * CTAS <= 227 * 1024, "shared memory per SM");
+    static_assert((SMEM_EST(NMMA, NPADL, SLOTS, SLOT_BYTES, TAIL) + POOL_BYTES + NPADL * 2 + 16 + 1024) * CTAS <= 227 * 1024, "shared memory per SM");
     static_assert(2 * SLOTS + 2 * NBUF <= 24, "barrier area");
     static_assert(CIN == 1 || (CIN % 8 == 0 && (CIN == 8 || CIN % 16 == 0)), "C_in must be 1, 8 or a multiple of 16");
     static_assert(NPAD % 16 == 0 && NPAD >= 16 && NPADL <= 128 && COUT <= NPAD && COUT % 8 == 0, "N tile");
@@ -143,19 +155,42 @@ struct TcCfg {
     static_assert(XPL * PHASE_BYTES < (1 << 18) && PLANE_BYTES % 16 == 0, "descriptor range");
 };
 
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+// stash / output unit (pooled x * OCTL + octet) of the h-th pooled 16-byte value a thread holds for pixel group xq; -1: padding columns
+template <class C>
+__device__ __forceinline__ int pool_unit(int h, int xq) {
+    if constexpr (C::XPH % 2 == 0) {
+        const int col0 = h * 16;                                  // chunk h = pixels (ph0, ph0 + 1) of octet oct0
+        if (col0 >= C::XPH * C::COUTL) return -1;
+        const int ph0 = C::col_phase(col0), oct0 = C::col_channel(col0) / 8;
+        return ((xq * C::XPH + ph0) >> 1) * C::OCTL + oct0;
+    } else {
+        const int oct = h;                                        // value h = octet h of the pixel pair (xq, xq + 1)
+        if (oct * 8 >= C::COUTL) return -1;
+        return (xq >> 1) * C::OCTL + oct;
+    }
+}
+
 // out: fp32 NCHW [N][COUT][HO][WO] (out_bf16 == 0), bf16 act8 [N][COUT/8][HO][WO][8] (1) or the same in fp16 (2: the pre-BatchNorm
 // z, which is never an MMA operand -- 11 mantissa bits keep max-pool arg-max ties as rare as on the reference's fp16 autocast path).
 // bias may be null (no bias, no statistics); stats: double [views][COUT][2] (sum, sum of squares), accumulated.
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS)
 conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wprep, const float* __restrict__ bias,
-               void* __restrict__ out, double* __restrict__ stats, int n_per_view, int out_bf16) {
+               void* __restrict__ out, double* __restrict__ stats, int n_per_view, int out_bf16,
+               uint4* __restrict__ pool_out, const float* __restrict__ gamma) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_s = smem;
     uint8_t* img_s = smem + C::W_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);   // full[SLOTS], empty[SLOTS], tfull[NBUF], tempty[NBUF]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::BAR_OFF + 200);
     float* bias_s = reinterpret_cast<float*>(smem + C::BAR_OFF + 256);
+    uint32_t* sign_s = reinterpret_cast<uint32_t*>(smem + C::SIGN_OFF);     // [NPADL / 2]: 0x8000 bits where gamma < 0 (two columns per word)
+    uint4* stash = reinterpret_cast<uint4*>(smem + C::POOL_OFF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int view = blockIdx.y, G = gridDim.x, g = blockIdx.x;
@@ -181,6 +216,17 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
         for (int i = threadIdx.x; i < C::IMG_BYTES / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
         for (int i = threadIdx.x; i < C::NPADL; i += blockDim.x)     // column (octet, phase, channel): the bias repeats per phase
             bias_s[i] = (bias != nullptr && i < C::XPH * C::COUTL) ? bias[blockIdx.z * C::COUTL + C::col_channel(i)] : 0.f;
+        if constexpr (C::POOL_OK) {
+            for (int i = threadIdx.x; i < C::NPADL / 2; i += blockDim.x) {
+                uint32_t m = 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int col = 2 * i + h;
+                    if (gamma != nullptr && col < C::XPH * C::COUTL && gamma[blockIdx.z * C::COUTL + C::col_channel(col)] < 0.f) m |= 0x8000u << (16 * h);
+                }
+                sign_s[i] = m;
+            }
+        }
         fence_proxy_async_smem();
     }
     if (warp == 0 && lane == 0) {
@@ -283,10 +329,14 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
         for (int c = 0; c < C::COUTL; ++c) s1[c] = s2[c] = 0.f;
         const int co0 = blockIdx.z * C::COUTL;                  // first output channel of this CTA's slice
         const bool do_stats = (bias != nullptr) && (stats != nullptr);
+        const bool do_pool = C::POOL_OK && pool_out != nullptr;
+        constexpr int NCH = C::NPADL / 16;                       // 16-column chunks of the accumulator
+        constexpr int NHP = C::POOL_OK ? (C::XPH % 2 == 0 ? NCH : 2 * NCH) : 1;      // pooled 16-byte units this thread may own per tile
         uint32_t tcount = 0;
         for (int i = i0; i < i1; ++i) {
             const int n = view * n_per_view + i / C::BANDS, band = i % C::BANDS;
             for (int t = 0; t < C::TILES; ++t, ++tcount) {
+                uint4 hp[NHP];                                   // horizontally pooled sign(gamma) * z of this tile row, fp16
                 const uint32_t buf = tcount % C::NBUF, u = tcount / C::NBUF;
                 mbar_wait(tfull_bar(buf), u & 1);
                 tc_fence_after_sync();
@@ -315,7 +365,26 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
                             s2[ch] += f[j] * f[j];
                         }
                     }
-                    if (valid) {
+                    if constexpr (C::POOL_OK) {
+                        if (do_pool) {
+                            // t = sign(gamma) * z in fp16 (rounding is monotonic and symmetric: ext(round(z)) == round(ext(z))); max over the pixel pair
+                            uint4 a, b;
+                            a.x = pack_f16(f[0], f[1]); a.y = pack_f16(f[2], f[3]); a.z = pack_f16(f[4], f[5]); a.w = pack_f16(f[6], f[7]);
+                            b.x = pack_f16(f[8], f[9]); b.y = pack_f16(f[10], f[11]); b.z = pack_f16(f[12], f[13]); b.w = pack_f16(f[14], f[15]);
+                            const uint4 ma = *reinterpret_cast<const uint4*>(sign_s + cc * 8), mb = *reinterpret_cast<const uint4*>(sign_s + cc * 8 + 4);
+                            a.x ^= ma.x; a.y ^= ma.y; a.z ^= ma.z; a.w ^= ma.w;
+                            b.x ^= mb.x; b.y ^= mb.y; b.z ^= mb.z; b.w ^= mb.w;
+                            if constexpr (C::XPH % 2 == 0) {     // the chunk = two adjacent pixels of one octet: the horizontal pair
+                                hp[cc].x = hmax2_u32(a.x, b.x); hp[cc].y = hmax2_u32(a.y, b.y); hp[cc].z = hmax2_u32(a.z, b.z); hp[cc].w = hmax2_u32(a.w, b.w);
+                            } else {                             // the chunk = two octets of one pixel: the horizontal partner is the next lane
+                                hp[2 * cc].x = hmax2_u32(a.x, __shfl_xor_sync(0xffffffffu, a.x, 1)); hp[2 * cc].y = hmax2_u32(a.y, __shfl_xor_sync(0xffffffffu, a.y, 1));
+                                hp[2 * cc].z = hmax2_u32(a.z, __shfl_xor_sync(0xffffffffu, a.z, 1)); hp[2 * cc].w = hmax2_u32(a.w, __shfl_xor_sync(0xffffffffu, a.w, 1));
+                                hp[2 * cc + 1].x = hmax2_u32(b.x, __shfl_xor_sync(0xffffffffu, b.x, 1)); hp[2 * cc + 1].y = hmax2_u32(b.y, __shfl_xor_sync(0xffffffffu, b.y, 1));
+                                hp[2 * cc + 1].z = hmax2_u32(b.z, __shfl_xor_sync(0xffffffffu, b.z, 1)); hp[2 * cc + 1].w = hmax2_u32(b.w, __shfl_xor_sync(0xffffffffu, b.w, 1));
+                            }
+                        }
+                    }
+                    if (valid && out != nullptr) {
                         if (out_bf16) {
                             uint4 pk[2];
 #pragma unroll
@@ -356,6 +425,39 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
                             for (int j = 0; j < 16; ++j) {
                                 const int col = cc * 16 + j, ph = C::col_phase(col), ch = C::col_channel(col);
                                 if (col < C::XPH * C::COUTL) dst[(long)ch * C::HO * C::WO + ph] = f[j];
+                            }
+                        }
+                    }
+                }
+                if constexpr (C::POOL_OK) {
+                    if (do_pool) {
+                        // vertical half of the window: even rows park their pooled values in the ring, the odd row below combines and emits
+                        const int slot = (int)(((long)(i - i0) * (C::HB / 2) + (y >> 1)) % C::POOL_R);
+                        const bool own = valid && (C::XPH % 2 == 0 || (xq & 1) == 0);
+                        uint4* srow = stash + slot * C::POOL_ROW_UNITS;
+                        if (own && (y & 1) == 0) {
+#pragma unroll
+                            for (int h = 0; h < NHP; ++h) {
+                                const int u = pool_unit<C>(h, xq);
+                                if (u >= 0) srow[u] = hp[h];
+                            }
+                        }
+                        asm volatile("bar.sync 2, 128;" ::: "memory");        // the four epilogue warps
+                        if (own && (y & 1) == 1) {
+                            const int ypg = (band * C::HB + y) >> 1;
+#pragma unroll
+                            for (int h = 0; h < NHP; ++h) {
+                                const int u = pool_unit<C>(h, xq);
+                                if (u >= 0) {
+                                    const uint4 up = srow[u];
+                                    const int col0 = (C::XPH % 2 == 0 ? h : h / 2) * 16 + (C::XPH % 2 == 0 ? 0 : (h & 1) * 8);
+                                    const uint4 m = *reinterpret_cast<const uint4*>(sign_s + col0 / 2);
+                                    uint4 e;
+                                    e.x = hmax2_u32(hp[h].x, up.x) ^ m.x; e.y = hmax2_u32(hp[h].y, up.y) ^ m.y;
+                                    e.z = hmax2_u32(hp[h].z, up.z) ^ m.z; e.w = hmax2_u32(hp[h].w, up.w) ^ m.w;
+                                    const int xp = u / C::OCTL, oct = u - xp * C::OCTL;
+                                    pool_out[(((long)n * (C::COUT / 8) + co0 / 8 + oct) * (C::HO / 2) + ypg) * (C::WO / 2) + xp] = e;
+                                }
                             }
                         }
                     }
@@ -499,7 +601,11 @@ __global__ void pack_quad8_kernel(const float* __restrict__ x, uint4* __restrict
 
 template <class C>
 int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* out, double* stats, int N, int n_per_view, int out_bf16,
-                   cudaStream_t st) {
+                   cudaStream_t st, void* pool_out = nullptr, const float* gamma = nullptr) {
+    if (pool_out != nullptr && !C::POOL_OK) {
+        set_error("conv_tc: this geometry has no fused max-pool epilogue");
+        return -5;
+    }
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
@@ -524,7 +630,8 @@ int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* ou
     if (G < 1) G = 1;
     const long items = (long)n_per_view * C::BANDS;
     if (G > items) G = (int)items;
-    conv_tc_kernel<C><<<dim3(G, views, C::NSPLIT), C::THREADS, C::SMEM, st>>>(tm, reinterpret_cast<const uint4*>(wprep), bias, out, stats, n_per_view, out_bf16);
+    conv_tc_kernel<C><<<dim3(G, views, C::NSPLIT), C::THREADS, C::SMEM, st>>>(tm, reinterpret_cast<const uint4*>(wprep), bias, out, stats, n_per_view, out_bf16,
+                                                                                reinterpret_cast<uint4*>(pool_out), gamma);
     return launch_status("conv_tc_kernel");
 }
 
@@ -1468,6 +1575,29 @@ int b200_conv_tc(const void* x_act8, const void* wprep, const float* bias, void*
     TC_RUN(CfgA1) TC_RUN(CfgA2) TC_RUN(CfgA3) TC_RUN(CfgI1) TC_RUN(CfgA1d) TC_RUN(CfgA2d) TC_RUN(CfgA3d) TC_RUN(CfgI1d) TC_RUN(CfgS1) TC_RUN(CfgS1d) TC_RUN(CfgA0) TC_RUN(CfgI0) TC_RUN(CfgS0) TC_RUN(CfgS2) TC_RUN(CfgS2d)
 #undef TC_RUN
     set_error("conv_tc: unsupported geometry Cin=%d Cout=%d H=%d W=%d K=%d pad=%d", Cin, Cout, H, W, K, pad);
+    return -4;
+}
+
+int b200_conv_tc_pool_supported(int Cin, int Cout, int H, int W, int K, int pad) {
+#define TC_HAS(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) return CFG::POOL_OK ? 1 : 0;
+    TC_HAS(CfgA1) TC_HAS(CfgA2) TC_HAS(CfgA3) TC_HAS(CfgI1) TC_HAS(CfgS1) TC_HAS(CfgA0) TC_HAS(CfgI0) TC_HAS(CfgS0) TC_HAS(CfgS2)
+#undef TC_HAS
+    return 0;
+}
+
+int b200_conv_tc_pool(const void* x_act8, const void* wprep, const float* bias, const float* gamma, void* z_out, void* pool_out, double* stats,
+                      int N, int n_per_view, int Cin, int Cout, int H, int W, int K, int pad, int z_fmt, void* stream) {
+    B200_REQUIRE(x_act8 && wprep && bias && gamma && pool_out && stats, -1, "conv_tc_pool: null pointer");
+    B200_REQUIRE(N > 0 && n_per_view > 0 && N % n_per_view == 0, -2, "conv_tc_pool: N=%d must be a multiple of n_per_view=%d", N, n_per_view);
+    B200_REQUIRE(((uintptr_t)x_act8 & 15) == 0 && ((uintptr_t)wprep & 15) == 0 && ((uintptr_t)z_out & 15) == 0 && ((uintptr_t)pool_out & 15) == 0, -3,
+                 "conv_tc_pool: pointers must be 16-byte aligned");
+    B200_REQUIRE(z_out == nullptr || z_fmt == 1 || z_fmt == 2, -2, "conv_tc_pool: z must be bf16 (1) or fp16 (2) act8");
+    cudaStream_t st = as_stream(stream);
+#define TC_RUN(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) \
+        return launch_conv_tc<CFG>(x_act8, wprep, bias, z_out, stats, N, n_per_view, z_fmt, st, pool_out, gamma);
+    TC_RUN(CfgA1) TC_RUN(CfgA2) TC_RUN(CfgA3) TC_RUN(CfgI1) TC_RUN(CfgS1) TC_RUN(CfgA0) TC_RUN(CfgI0) TC_RUN(CfgS0)
+#undef TC_RUN
+    set_error("conv_tc_pool: unsupported geometry Cin=%d Cout=%d H=%d W=%d K=%d pad=%d", Cin, Cout, H, W, K, pad);
     return -4;
 }
 

@@ -143,7 +143,7 @@ class DinoStepEngine:
                  n_global_views=2, n_local_views=4, momentum=0.996, center_momentum=0.9, student_temperature=0.1,
                  teacher_temperature=0.04, learning_rate=1e-4, weight_decay=1e-6, dropout=0.3, fusion_dropout=0.3, alpha=1.0,
                  cosine_loss_alpha=0.0, augment_values=None, seed=0, device=None, process_group=None, data_parallel=None,
-                 precision="bf16"):
+                 precision="bf16", fused_pool=True):
         if not torch.cuda.is_available():
             raise ops._lib.B200Error("DinoStepEngine needs a CUDA device: the hot path has no CPU fallback")
         ops._lib.load()
@@ -224,6 +224,12 @@ class DinoStepEngine:
             # which consumes the bf16 act8 pooled gradient written by the second layer's tensor-core data gradient
             if self.tc[mod] and self.tc[mod][0] and not (len(self.tc[mod]) > 1 and self.tc[mod][1]):
                 self.tc[mod][0] = False
+        # forward layers whose 2x2 max-pool runs inside the convolution's epilogue (the pooled extreme e, a quarter of z, goes to the
+        # BatchNorm-apply kernel; the teacher and the evaluation pass never write the full-resolution z)
+        self.fused_pool = bool(fused_pool)      # False: the round-1 path (full-resolution z -> bn_relu_pool8_fwd), kept for A/B measurements
+        self.pool = {mod: [self.fused_pool and bool(self.tc[mod][li]) and ops.conv_tc_pool_supported(ci, co, hw, hw, k, pad)
+                           for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers)]
+                     for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers))}
         self._tcw = {}
         self._prep_desc = {}
         for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers)):
@@ -353,9 +359,12 @@ class DinoStepEngine:
                         wq = ops.quad8_width(hw, pad)
                         w[f"{mod}.xs8"] = e(N, hw, wq, 8, dtype=BF)             # first-layer input, quad8 (shared by the teacher)
                         w[f"{mod}.xs8_b"] = e(N, hw, wq, 8, dtype=BF)           # ... and the slot the next step's views are prefetched into
-                    if tc:
+                    pooled = tc and self.pool[mod][li]
+                    if pooled:
+                        w[f"{role}.{mod}.e{li}"] = e(N, co // 8, ho // 2, ho // 2, 8, dtype=torch.float16)     # 2x2 window extreme of z
+                    if tc and (role == "s" or not pooled):
                         w[f"{role}.{mod}.z{li}"] = e(N, co // 8, ho, ho, 8, dtype=torch.float16)   # act8 layout, fp16: never an MMA operand
-                    else:
+                    elif not tc:
                         w[f"{role}.{mod}.z{li}"] = e(N, co, ho, ho)
                     if next_tc:
                         w[f"{role}.{mod}.p8{li}"] = e(N, co // 8, ho // 2, ho // 2, 8, dtype=BF)
@@ -551,19 +560,25 @@ class DinoStepEngine:
         nv = N // B
         cur = x
         for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers):
-            z, stats = w[f"{role}.{mod}.z{li}"], w[f"{role}.{mod}.stats{li}"]
+            z, stats = w.get(f"{role}.{mod}.z{li}"), w[f"{role}.{mod}.stats{li}"]
             tc = self.tc[mod][li]
             next_tc = li + 1 < len(layers) and self.tc[mod][li + 1]
+            pooled = tc and self.pool[mod][li]
             if "zarena" not in w:
                 stats.zero_()
             wrole = role if role in ("s", "t") else self._eval_wrole      # the evaluation role "e" borrows a role's weight images
-            if tc and ci == 1:
-                xs8 = w[f"{mod}.xs8"]
-                if role == "s" and not w.get("packed", False):
-                    ops.pack_quad8(cur.view(N, hw, hw), xs8, pad)
-                ops.conv_tc(xs8[:N], self._tcw[(wrole, mod, li)], P["enc." + conv + ".bias"], z, stats, B, co, k, pad)
-            elif tc:
-                ops.conv_tc(cur, self._tcw[(wrole, mod, li)], P["enc." + conv + ".bias"], z, stats, B, co, k, pad)
+            if tc:
+                xin = cur
+                if ci == 1:
+                    xs8 = w[f"{mod}.xs8"]
+                    if role == "s" and not w.get("packed", False):
+                        ops.pack_quad8(cur.view(N, hw, hw), xs8, pad)
+                    xin = xs8[:N]
+                if pooled:      # conv + statistics + window extreme in one kernel; only the student keeps z (for its backward)
+                    ops.conv_tc_pool(xin, self._tcw[(wrole, mod, li)], P["enc." + conv + ".bias"], P["enc." + bn + ".weight"],
+                                     z if role == "s" else None, w[f"{role}.{mod}.e{li}"], stats, B, co, k, pad)
+                else:
+                    ops.conv_tc(xin, self._tcw[(wrole, mod, li)], P["enc." + conv + ".bias"], z, stats, B, co, k, pad)
             else:
                 ops.conv_fwd(cur.view(N, ci, hw, hw), P["enc." + conv + ".weight"], P["enc." + conv + ".bias"], z, stats, B, pad)
             b = bns["enc." + bn]
@@ -573,7 +588,10 @@ class DinoStepEngine:
                             b.num_batches_tracked, sc, sh, w[f"{role}.{mod}.mean{li}"], w[f"{role}.{mod}.invstd{li}"], nv, B * ho * ho, train=train)
             if tc:
                 cur = w[f"{role}.{mod}.p8{li}"] if next_tc else w[f"{role}.{mod}.p{li}"]
-                ops.bn_relu_pool8_fwd(z, sc, sh, cur, B)
+                if pooled:
+                    ops.bn_relu_apply8(w[f"{role}.{mod}.e{li}"], sc, sh, cur, B)
+                else:
+                    ops.bn_relu_pool8_fwd(z, sc, sh, cur, B)
             else:
                 cur = w[f"{role}.{mod}.p{li}"]
                 ops.bn_relu_pool_fwd(z, sc, sh, cur, B)
@@ -752,7 +770,10 @@ class DinoStepEngine:
                 next_tc = li + 1 < len(layers) and self.tc[mod][li + 1]
                 if tc and ci == 1:
                     w[f"{mod}.xs8"] = e(B, hw, ops.quad8_width(hw, pad), 8, dtype=BF)
-                w[f"e.{mod}.z{li}"] = e(B, co // 8, ho, ho, 8, dtype=torch.float16) if tc else e(B, co, ho, ho)
+                if tc and self.pool[mod][li]:
+                    w[f"e.{mod}.e{li}"] = e(B, co // 8, ho // 2, ho // 2, 8, dtype=torch.float16)
+                else:
+                    w[f"e.{mod}.z{li}"] = e(B, co // 8, ho, ho, 8, dtype=torch.float16) if tc else e(B, co, ho, ho)
                 if next_tc:
                     w[f"e.{mod}.p8{li}"] = e(B, co // 8, ho // 2, ho // 2, 8, dtype=BF)
                 if not next_tc or not tc:

@@ -290,6 +290,36 @@ def conv_tc(x8, wprep, bias, out, stats, n_per_view, Cout, K, pad):
                                     fmt, _stream()), "conv_tc")
 
 
+def conv_tc_pool_supported(Cin, Cout, H, W, K, pad):
+    return bool(_lib_().b200_conv_tc_pool_supported(Cin, Cout, H, W, K, pad))
+
+
+def conv_tc_pool(x8, wprep, bias, gamma, z_out, pool_out, stats, n_per_view, Cout, K, pad):
+    """Forward convolution + BatchNorm statistics + the 2x2 window extreme (max / min by sign(gamma)) in the epilogue.
+    x8 as in conv_tc; pool_out: fp16 act8 [N, Cout/8, Ho/2, Wo/2, 8]; z_out: fp16 / bf16 act8 [N, Cout/8, Ho, Wo, 8] or None."""
+    Wo = pool_out.shape[-2] * 2
+    if x8.dim() == 4:
+        N, H, WQ, _ = x8.shape
+        W = Wo - 2 * pad + K - 1
+        if WQ != quad8_width(W, pad):
+            raise _lib.B200Error(f"conv_tc_pool: quad8 input of width {WQ} does not match W={W}, pad={pad}")
+        Cin = 1
+    else:
+        N, P, H, W, _ = x8.shape
+        Cin = P * 8
+    fmt = 0 if z_out is None else (1 if z_out.dtype == BF16 else 2)
+    _lib.check(_lib_().b200_conv_tc_pool(_ptr(x8, BF16), _ptr(wprep), _ptr(bias, F32), _ptr(gamma, F32), _ptr(z_out) if z_out is not None else None,
+                                         _ptr(pool_out, torch.float16), _ptr(stats, F64), N, n_per_view, Cin, Cout, H, W, K, pad, fmt, _stream()),
+               "conv_tc_pool")
+
+
+def bn_relu_apply8(e8, scale, shift, out, n_per_view):
+    """p = ReLU(scale * e + shift) on the pooled extreme e8 (fp16 act8) -> out: fp32 NCHW or bf16 act8 (by dtype)."""
+    N, P, HP, WP, _ = e8.shape
+    _lib.check(_lib_().b200_bn_relu_apply8(_ptr(e8, torch.float16), _ptr(scale, F32), _ptr(shift, F32), _ptr(out), N, n_per_view, P * 8, HP, WP,
+                                           _fmt(out), _stream()), "bn_relu_apply8")
+
+
 def conv_tc_prep_weights_multi(desc):
     """desc: int64 CUDA tensor [n, 6] = (w data_ptr, out data_ptr, Cin, Cout, K, flip) per weight image; one launch for all"""
     _lib.check(_lib_().b200_conv_tc_prep_weights_multi(_ptr(desc, torch.int64), desc.shape[0], _stream()), "conv_tc_prep_weights_multi")
@@ -551,7 +581,7 @@ def knn_predict(train_feats, train_labels, test_feats, k=5, n_classes=10, return
 # ---- launch accounting and optional per-op timing ------------------------------------------------------------
 # Every wrapper above issues a fixed number of kernel launches; the table lists the ones that issue more than one.
 _LAUNCHES = {"ntxent_fwd_bwd": 5, "conv_tc_wgrad_l0_fused": 3, "conv_tc_wgrad": 2, "conv_bwd_weight": 3, "linear_bwd_weight": 3, "infonce_fwd_bwd": 9}
-_NOT_KERNELS = {"knn_predict", "quad8_width", "ntxent_work_floats", "conv_tc_wgrad_l0_fused_work_floats", "conv_tc_wgrad_work_floats", "conv_tc_supported", "conv_tc_weight_bytes", "dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
+_NOT_KERNELS = {"knn_predict", "conv_tc_pool_supported", "quad8_width", "ntxent_work_floats", "conv_tc_wgrad_l0_fused_work_floats", "conv_tc_wgrad_work_floats", "conv_tc_supported", "conv_tc_weight_bytes", "dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
 LAUNCH_COUNT = 0
 _PROFILE = None          # None, or a list receiving (name, start_event, end_event, meta)
 
@@ -591,7 +621,8 @@ def _wrap(name, fn):
         a.record()
         out = fn(*args, **kwargs)
         b.record()
-        meta = tuple(tuple(t.shape) for t in list(args[:4]) + list(kwargs.values()) if isinstance(t, torch.Tensor))
+        head = args[:6] if name == "conv_tc_pool" else args[:4]        # conv_tc_pool: (x, wprep, bias, gamma, z | None, e)
+        meta = tuple(tuple(t.shape) for t in list(head) + list(kwargs.values()) if isinstance(t, torch.Tensor))
         meta = meta + (("i",) + tuple(int(v) for v in args if isinstance(v, int) and not isinstance(v, bool)),)
         _PROFILE.append((name, a, b, meta))
         return out

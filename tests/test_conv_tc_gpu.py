@@ -411,3 +411,73 @@ def test_infonce_tensor_core(B, D):
         assert float((got.double() - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
         cos = float((got.double().flatten() @ ref.flatten()) / (got.double().norm() * ref.norm()))
         assert cos > 0.9995, cos
+
+
+POOLED = [(8, 16, 56, 5, 2), (16, 32, 28, 5, 2), (32, 64, 14, 5, 2), (32, 64, 14, 5, 0), (32, 64, 14, 3, 1), (1, 8, 112, 5, 2), (1, 32, 28, 5, 2),
+          (1, 32, 28, 3, 1)]
+
+
+@pytest.mark.parametrize("geom", POOLED)
+@pytest.mark.parametrize("views,B", [(1, 3), (3, 5), (6, 43)])
+def test_conv_tc_fused_pool_epilogue_is_bit_identical_to_the_unfused_chain(geom, views, B):
+    """b200_conv_tc_pool (conv + statistics + 2x2 window extreme by sign(gamma) in the epilogue) -> bn_finalize -> b200_bn_relu_apply8
+    must equal conv_tc -> bn_finalize -> bn_relu_pool8_fwd BIT FOR BIT (p, z, statistics), with mixed-sign BatchNorm weights, with
+    and without the z store, for bf16-act8 and fp32-NCHW outputs; the extreme itself is checked against torch max / min pooling."""
+    Cin, Cout, H, K, pad = geom
+    assert ops.conv_tc_pool_supported(Cin, Cout, H, H, K, pad)
+    g = torch.Generator().manual_seed(Cin * 7 + Cout + views + H)
+    N = views * B
+    Ho = H + 2 * pad - K + 1
+    w = (torch.randn(Cout, Cin, K, K, generator=g) / (Cin * K * K) ** 0.5).to(DEV)
+    bias = torch.randn(Cout, generator=g).to(DEV)
+    gamma = torch.randn(Cout, generator=g).to(DEV)          # both signs
+    gamma[0] = 0.0
+    beta = torch.randn(Cout, generator=g).to(DEV)
+    if Cin == 1:
+        x = torch.rand(N, 1, H, H, generator=g).to(DEV)
+        x8 = torch.empty(N, H, ops.quad8_width(H, pad), 8, dtype=torch.bfloat16, device=DEV)
+        ops.pack_quad8(x, x8, pad)
+    else:
+        x = torch.randn(N, Cin, H, H, generator=g).to(DEV)
+        x8 = torch.empty(N, Cin // 8, H, H, 8, dtype=torch.bfloat16, device=DEV)
+        ops.pack_act8(x, x8)
+    wp = torch.empty(ops.conv_tc_weight_bytes(Cin, Cout, K), dtype=torch.uint8, device=DEV)
+    ops.conv_tc_prep_weights(w, wp)
+
+    def finalize(stats):
+        sc, sh, mu, inv = (torch.empty(views, Cout, device=DEV) for _ in range(4))
+        rm, rv, nbt = torch.zeros(Cout, device=DEV), torch.ones(Cout, device=DEV), torch.zeros(1, dtype=torch.int64, device=DEV)
+        ops.bn_finalize(stats, gamma, beta, rm, rv, nbt, sc, sh, mu, inv, views, B * Ho * Ho)
+        return sc, sh
+
+    # unfused chain
+    z_ref = torch.full((N, Cout // 8, Ho, Ho, 8), float("nan"), dtype=torch.float16, device=DEV)
+    st_ref = torch.zeros(views, Cout, 2, dtype=torch.float64, device=DEV)
+    ops.conv_tc(x8, wp, bias, z_ref, st_ref, B, Cout, K, pad)
+    sc, sh = finalize(st_ref)
+    p8_ref = torch.empty(N, Cout // 8, Ho // 2, Ho // 2, 8, dtype=torch.bfloat16, device=DEV)
+    p32_ref = torch.empty(N, Cout, Ho // 2, Ho // 2, device=DEV)
+    ops.bn_relu_pool8_fwd(z_ref, sc, sh, p8_ref, B)
+    ops.bn_relu_pool8_fwd(z_ref, sc, sh, p32_ref, B)
+    for keep_z in (True, False):
+        z = torch.full_like(z_ref, float("nan")) if keep_z else None
+        e8 = torch.full((N, Cout // 8, Ho // 2, Ho // 2, 8), float("nan"), dtype=torch.float16, device=DEV)
+        st = torch.zeros_like(st_ref)
+        ops.conv_tc_pool(x8, wp, bias, gamma, z, e8, st, B, Cout, K, pad)
+        torch.cuda.synchronize()
+        assert torch.equal(st, st_ref)
+        if keep_z:
+            assert torch.equal(z, z_ref)
+        # the extreme: max where gamma >= 0, min where gamma < 0, of the fp16 z
+        zr = _unpack8(z_ref)
+        sgn = torch.where(gamma < 0, -1.0, 1.0).view(1, Cout, 1, 1)
+        want_e = F.max_pool2d(zr * sgn, 2) * sgn
+        assert torch.equal(_unpack8(e8), want_e), float((_unpack8(e8) - want_e).abs().max())
+        sc2, sh2 = finalize(st)
+        assert torch.equal(sc2, sc) and torch.equal(sh2, sh)
+        p8 = torch.full_like(p8_ref, float("nan"))
+        p32 = torch.full_like(p32_ref, float("nan"))
+        ops.bn_relu_apply8(e8, sc2, sh2, p8, B)
+        ops.bn_relu_apply8(e8, sc2, sh2, p32, B)
+        torch.cuda.synchronize()
+        assert torch.equal(p8, p8_ref) and torch.equal(p32, p32_ref)
