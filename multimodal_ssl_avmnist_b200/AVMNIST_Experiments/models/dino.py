@@ -318,9 +318,10 @@ class UniModalDINO(_DinoBase):
 # Downstream models (reference models/dino.py:1764-1850): frozen-encoder features through the CUDA encoder forward
 # ------------------------------------------------------------------------------------------------------------
 class FeatureExtractor(nn.Module):
-    """Frozen student-encoder features of un-augmented batches.  The reference deep-copies the encoder; here the features
-    come from the live student weights through DinoStepEngine.encode_features (identical while nothing trains in between).
-    train()/eval() select BatchNorm batch / running statistics exactly like the copy's mode would."""
+    """Frozen student-encoder features of un-augmented batches.  The reference deep-copies the encoder; here the weights are the
+    live student's (identical while nothing trains in between) and the part of the copy that DOES change during a probe -- the
+    BatchNorm running statistics, which adapt in train() mode and are read in eval() mode -- is a per-extractor copy held by the
+    engine (DinoStepEngine.begin_probe).  train()/eval() select batch / running statistics exactly like the copy's mode would."""
 
     def __init__(self, pretrained_model, is_dino_based=True):
         super().__init__()
@@ -330,14 +331,17 @@ class FeatureExtractor(nn.Module):
         self.is_unimodal = hasattr(pretrained_model.student, "modality")
         self.modality = getattr(pretrained_model.student, "modality", None)
         self.output_dim = pretrained_model.student.output_dim
+        self._probe = None
 
     @torch.no_grad()
     def forward(self, images, spectrograms=None):
         dino = self._dino[0]
         eng = dino._b200.ensure(dino.center.device)
+        if self._probe is None:
+            self._probe = eng.begin_probe()
         img = images.to(eng.device).reshape(-1, 28, 28).contiguous()
         aud = None if (self.is_unimodal or spectrograms is None) else spectrograms.to(eng.device).reshape(-1, 112, 112).contiguous()
-        return eng.encode_features(img, aud, train=self.training).clone()
+        return eng.encode_features(img, aud, train=self.training, probe=self._probe).clone()
 
 
 class DownstreamClassifier(nn.Module):

@@ -137,7 +137,8 @@ struct TcCfg {
     static constexpr int POOL_BYTES = POOL_OK ? POOL_R * POOL_ROW_UNITS * 16 : 0;
     static constexpr int SIGN_OFF = BAR_OFF + 256 + NPADL * 4;   // per accumulator column pair: fp16 sign-bit masks (sign of gamma)
     static constexpr int POOL_OFF = round_up(SIGN_OFF + NPADL * 2, 16);
-    static constexpr int SMEM = POOL_OFF + POOL_BYTES;
+    static constexpr int SMEM = POOL_OFF + POOL_BYTES;           // the pooling instance
+    static constexpr int SMEM_NOPOOL = BAR_OFF + 256 + NPADL * 4;
     static constexpr int NBUF = nbuf_for(NPADL, CTAS);          // TMEM accumulator stages
     static constexpr int TMEM_COLS = pow2_cols(NBUF * NPADL);
     // One issuing thread sustains only ~1 UMMA per 140 cycles at these tile shapes (measured, tools/umma_probe.cu); four
@@ -178,7 +179,7 @@ __device__ __forceinline__ int pool_unit(int h, int xq) {
 // out: fp32 NCHW [N][COUT][HO][WO] (out_bf16 == 0), bf16 act8 [N][COUT/8][HO][WO][8] (1) or the same in fp16 (2: the pre-BatchNorm
 // z, which is never an MMA operand -- 11 mantissa bits keep max-pool arg-max ties as rare as on the reference's fp16 autocast path).
 // bias may be null (no bias, no statistics); stats: double [views][COUT][2] (sum, sum of squares), accumulated.
-template <class C>
+template <class C, bool POOL>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS)
 conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wprep, const float* __restrict__ bias,
                void* __restrict__ out, double* __restrict__ stats, int n_per_view, int out_bf16,
@@ -216,7 +217,7 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
         for (int i = threadIdx.x; i < C::IMG_BYTES / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
         for (int i = threadIdx.x; i < C::NPADL; i += blockDim.x)     // column (octet, phase, channel): the bias repeats per phase
             bias_s[i] = (bias != nullptr && i < C::XPH * C::COUTL) ? bias[blockIdx.z * C::COUTL + C::col_channel(i)] : 0.f;
-        if constexpr (C::POOL_OK) {
+        if constexpr (POOL) {
             for (int i = threadIdx.x; i < C::NPADL / 2; i += blockDim.x) {
                 uint32_t m = 0;
 #pragma unroll
@@ -329,14 +330,13 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
         for (int c = 0; c < C::COUTL; ++c) s1[c] = s2[c] = 0.f;
         const int co0 = blockIdx.z * C::COUTL;                  // first output channel of this CTA's slice
         const bool do_stats = (bias != nullptr) && (stats != nullptr);
-        const bool do_pool = C::POOL_OK && pool_out != nullptr;
         constexpr int NCH = C::NPADL / 16;                       // 16-column chunks of the accumulator
-        constexpr int NHP = C::POOL_OK ? (C::XPH % 2 == 0 ? NCH : 2 * NCH) : 1;      // pooled 16-byte units this thread may own per tile
+        constexpr int NHP = POOL ? (C::XPH % 2 == 0 ? NCH : 2 * NCH) : 1;      // pooled 16-byte units this thread may own per tile
         uint32_t tcount = 0;
         for (int i = i0; i < i1; ++i) {
             const int n = view * n_per_view + i / C::BANDS, band = i % C::BANDS;
             for (int t = 0; t < C::TILES; ++t, ++tcount) {
-                uint4 hp[NHP];                                   // horizontally pooled sign(gamma) * z of this tile row, fp16
+                [[maybe_unused]] uint4 hp[NHP];                  // horizontally pooled sign(gamma) * z of this tile row, fp16
                 const uint32_t buf = tcount % C::NBUF, u = tcount / C::NBUF;
                 mbar_wait(tfull_bar(buf), u & 1);
                 tc_fence_after_sync();
@@ -365,8 +365,8 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
                             s2[ch] += f[j] * f[j];
                         }
                     }
-                    if constexpr (C::POOL_OK) {
-                        if (do_pool) {
+                    if constexpr (POOL) {
+                        {
                             // t = sign(gamma) * z in fp16 (rounding is monotonic and symmetric: ext(round(z)) == round(ext(z))); max over the pixel pair
                             uint4 a, b;
                             a.x = pack_f16(f[0], f[1]); a.y = pack_f16(f[2], f[3]); a.z = pack_f16(f[4], f[5]); a.w = pack_f16(f[6], f[7]);
@@ -384,7 +384,7 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
                             }
                         }
                     }
-                    if (valid && out != nullptr) {
+                    if (valid && (!POOL || out != nullptr)) {
                         if (out_bf16) {
                             uint4 pk[2];
 #pragma unroll
@@ -429,8 +429,8 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
                         }
                     }
                 }
-                if constexpr (C::POOL_OK) {
-                    if (do_pool) {
+                if constexpr (POOL) {
+                    {
                         // vertical half of the window: even rows park their pooled values in the ring, the odd row below combines and emits
                         const int slot = (int)(((long)(i - i0) * (C::HB / 2) + (y >> 1)) % C::POOL_R);
                         const bool own = valid && (C::XPH % 2 == 0 || (xq & 1) == 0);
@@ -445,6 +445,7 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
                         asm volatile("bar.sync 2, 128;" ::: "memory");        // the four epilogue warps
                         if (own && (y & 1) == 1) {
                             const int ypg = (band * C::HB + y) >> 1;
+                            uint4 ev[NHP];
 #pragma unroll
                             for (int h = 0; h < NHP; ++h) {
                                 const int u = pool_unit<C>(h, xq);
@@ -452,11 +453,30 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
                                     const uint4 up = srow[u];
                                     const int col0 = (C::XPH % 2 == 0 ? h : h / 2) * 16 + (C::XPH % 2 == 0 ? 0 : (h & 1) * 8);
                                     const uint4 m = *reinterpret_cast<const uint4*>(sign_s + col0 / 2);
-                                    uint4 e;
-                                    e.x = hmax2_u32(hp[h].x, up.x) ^ m.x; e.y = hmax2_u32(hp[h].y, up.y) ^ m.y;
-                                    e.z = hmax2_u32(hp[h].z, up.z) ^ m.z; e.w = hmax2_u32(hp[h].w, up.w) ^ m.w;
-                                    const int xp = u / C::OCTL, oct = u - xp * C::OCTL;
-                                    pool_out[(((long)n * (C::COUT / 8) + co0 / 8 + oct) * (C::HO / 2) + ypg) * (C::WO / 2) + xp] = e;
+                                    ev[h].x = hmax2_u32(hp[h].x, up.x) ^ m.x; ev[h].y = hmax2_u32(hp[h].y, up.y) ^ m.y;
+                                    ev[h].z = hmax2_u32(hp[h].z, up.z) ^ m.z; ev[h].w = hmax2_u32(hp[h].w, up.w) ^ m.w;
+                                }
+                            }
+                            const long plane = (long)(C::HO / 2) * (C::WO / 2);
+                            uint4* erow = pool_out + ((long)n * (C::COUT / 8) + co0 / 8) * plane + (long)ypg * (C::WO / 2);
+                            if constexpr (C::XPH == 4) {
+                                // values (2m, 2m+1) = the two pooled pixels 2 xq, 2 xq + 1 of octet m: 32 contiguous, aligned bytes
+#pragma unroll
+                                for (int h = 0; h + 1 < NHP; h += 2) {
+                                    const int u = pool_unit<C>(h, xq);
+                                    if (u >= 0) {
+                                        const int xp = u / C::OCTL, oct = u - xp * C::OCTL;
+                                        st_global_256(erow + oct * plane + xp, ev[h], ev[h + 1]);
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int h = 0; h < NHP; ++h) {
+                                    const int u = pool_unit<C>(h, xq);
+                                    if (u >= 0) {
+                                        const int xp = u / C::OCTL, oct = u - xp * C::OCTL;
+                                        erow[oct * plane + xp] = ev[h];
+                                    }
                                 }
                             }
                         }
@@ -608,7 +628,8 @@ int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* ou
     }
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_NOPOOL);
+        if (e == cudaSuccess && C::POOL_OK) e = cudaFuncSetAttribute(conv_tc_kernel<C, C::POOL_OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) {
             set_error("conv_tc: cannot set %d bytes of shared memory: %s", C::SMEM, cudaGetErrorString(e));
             return (int)e;
@@ -630,8 +651,12 @@ int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* ou
     if (G < 1) G = 1;
     const long items = (long)n_per_view * C::BANDS;
     if (G > items) G = (int)items;
-    conv_tc_kernel<C><<<dim3(G, views, C::NSPLIT), C::THREADS, C::SMEM, st>>>(tm, reinterpret_cast<const uint4*>(wprep), bias, out, stats, n_per_view, out_bf16,
-                                                                                reinterpret_cast<uint4*>(pool_out), gamma);
+    if (pool_out != nullptr)
+        conv_tc_kernel<C, C::POOL_OK><<<dim3(G, views, C::NSPLIT), C::THREADS, C::SMEM, st>>>(tm, reinterpret_cast<const uint4*>(wprep), bias, out, stats,
+                                                                                              n_per_view, out_bf16, reinterpret_cast<uint4*>(pool_out), gamma);
+    else
+        conv_tc_kernel<C, false><<<dim3(G, views, C::NSPLIT), C::THREADS, C::SMEM_NOPOOL, st>>>(tm, reinterpret_cast<const uint4*>(wprep), bias, out, stats,
+                                                                                                n_per_view, out_bf16, nullptr, nullptr);
     return launch_status("conv_tc_kernel");
 }
 

@@ -790,18 +790,35 @@ class DinoStepEngine:
         self._ws[key] = w
         return w
 
+    def begin_probe(self, teacher=False):
+        """Start a linear-probe session (reference models/dino.py:878-951: `DownstreamClassifier` deep-copies the student, trains the
+        probe with the copy in train() mode -- its BatchNorm running statistics adapt to the un-augmented batches -- and evaluates
+        with those statistics).  Returns a token holding the copy's running statistics (initialised from the live ones) and its own
+        dropout counter; pass it to encode_features(probe=token).  The live statistics are never touched."""
+        src = self.bn_t if teacher else self.bn_s
+        bns = {}
+        for k, v in src.items():
+            c = _BN(v.C, self.device)
+            c.running_mean.copy_(v.running_mean)
+            c.running_var.copy_(v.running_var)
+            c.num_batches_tracked.copy_(v.num_batches_tracked)
+            bns[k] = c
+        return {"bns": bns, "step": 0, "teacher": teacher}
+
     @torch.no_grad()
-    def encode_features(self, images, audios=None, train=False, teacher=False):
+    def encode_features(self, images, audios=None, train=False, teacher=False, probe=None):
         """Encoder features [B, O] of an UN-augmented batch (images [B,28,28] fp32 in [0,1] or uint8, audios [B,112,112] fp32 in
         [0,1] or uint8), as DownstreamClassifier / FeatureExtractor of the reference use them (models/dino.py:1764-1850).
-        train=False: BatchNorm with the running statistics, no dropout (module.eval()); train=True: batch statistics and an
-        active fusion dropout, like the reference's probe training on a train()-mode copy -- the copy's running statistics are
-        scratch, the live ones are never touched."""
+        train=False: BatchNorm with running statistics, no dropout (module.eval()); train=True: batch statistics and an active
+        fusion dropout.  probe (a begin_probe() token): the running statistics read / updated are the probe copy's, and every
+        train-mode call draws a fresh dropout mask; without a token train-mode updates go to scratch and eval reads the live ones."""
         B = images.shape[0]
         w = self._eval_workspace(B)
         P = self.T if teacher else self.S
         bns = self.bn_t if teacher else self.bn_s
-        if train:       # scratch running statistics
+        if probe is not None:
+            bns = probe["bns"]
+        elif train:       # scratch running statistics
             bns = {k: _BN(v.C, self.device) for k, v in bns.items()}
         xi = w["x_img"]
         xi.copy_((images.float() / 255.0 if images.dtype == torch.uint8 else images).reshape(B, 1, 28, 28))
@@ -819,7 +836,9 @@ class DinoStepEngine:
         fmask = None
         if train and self.kind == "multi_central" and self.fusion_dropout > 0:
             fmask = w["e.fmask"]
-            ops.dropout_mask(fmask, self.fusion_dropout, self.seed + 17, self.rng_step * 4 + 3)
+            if probe is not None:
+                probe["step"] += 1
+            ops.dropout_mask(fmask, self.fusion_dropout, self.seed + 17, (self.rng_step + (probe["step"] if probe is not None else 0)) * 4 + 3)
         self._eval_wrole = "t" if teacher else "s"
         return self._encode(w, "e", P, bns, xi, xa, B, B, B, fmask, train=train)
 

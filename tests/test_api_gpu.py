@@ -219,6 +219,14 @@ def test_feature_path_and_linear_probe(tmp_path):
     assert float((ftrain - feats).abs().max()) > 1e-3            # batch statistics + dropout differ from the eval path
     sd2 = lit.model.student.state_dict()
     assert all(torch.equal(sd2[k].cpu().float(), sd[k]) for k in sd if "running" in k), "feature passes must not touch the running statistics"
+    # like the reference's deep-copied encoder: train-mode passes adapt the EXTRACTOR's running statistics, its eval-mode passes read them
+    fx3 = md.FeatureExtractor(lit.model)
+    fx3.train()
+    a1, a2 = fx3(image.to(DEV), audio.to(DEV)), fx3(image.to(DEV), audio.to(DEV))
+    assert float((a1 - a2).abs().max()) > 1e-4                   # a fresh dropout mask per probe batch
+    adapted = fx3.eval()(image.to(DEV), audio.to(DEV))
+    assert float((adapted - feats).abs().max()) > 1e-3           # the copy's statistics moved towards the un-augmented data
+    assert torch.equal(md.FeatureExtractor(lit.model).eval()(image.to(DEV), audio.to(DEV)), feats)      # a new extractor starts from the live ones
     # the probe through the trainer
     d = str(tmp_path) + "/"
     gd.write_synthetic_avmnist(d, n_train=64, n_test=16)
