@@ -388,21 +388,29 @@ __device__ int sample_chain(const int32_t* spec, int S, Draw& d, int32_t* rec /*
 }
 
 constexpr int NGROUPS = 784;
-__global__ void __launch_bounds__(32) aug_sample_kernel(const int32_t* __restrict__ spec, int B, int Vg, int Vl, uint64_t seed,
-                                                        uint64_t step, int32_t* __restrict__ img_ops, int32_t* __restrict__ aud_ops,
-                                                        uint32_t* __restrict__ group_bits, const int64_t* __restrict__ step_dev) {
+constexpr int SAMPLE_WARPS = 4;         // records per CTA (one warp each): 4 x fewer, 4 x fuller CTAs than one warp per block
+__global__ void __launch_bounds__(32 * SAMPLE_WARPS) aug_sample_kernel(const int32_t* __restrict__ spec, int B, int Vg, int Vl, uint64_t seed,
+                                                                       uint64_t step, int32_t* __restrict__ img_ops, int32_t* __restrict__ aud_ops,
+                                                                       uint32_t* __restrict__ group_bits, const int64_t* __restrict__ step_dev) {
     if (step_dev != nullptr) step += (uint64_t)__ldg(step_dev);
     // one warp per (sample, view) record: lane 0 replays the two op chains (sequential by nature) and draws the grouped-masking
     // subset with a partial Fisher-Yates shuffle (gc draws instead of ranking 784 random keys); the warp stages and copies.
     __shared__ int32_t sspec[4 * B200_AUG_MAX_OPS * 8];
-    __shared__ int32_t rec_i[B200_AUG_MAX_OPS * 8], rec_a[B200_AUG_MAX_OPS * 8];
-    __shared__ uint16_t perm[NGROUPS];
-    __shared__ uint32_t bits[B200_AUG_GROUP_WORDS];
+    __shared__ int32_t rec_i_s[SAMPLE_WARPS][B200_AUG_MAX_OPS * 8], rec_a_s[SAMPLE_WARPS][B200_AUG_MAX_OPS * 8];
+    __shared__ uint16_t perm_s[SAMPLE_WARPS][NGROUPS];
+    __shared__ uint32_t bits_s[SAMPLE_WARPS][B200_AUG_GROUP_WORDS];
     const int V = Vg + Vl;
-    const int b = blockIdx.x / V, v = blockIdx.x - b * V;
-    const size_t rec = (size_t)b * V + v;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < 4 * B200_AUG_MAX_OPS * 8; i += 32) sspec[i] = __ldg(spec + i);
+    const int warp = threadIdx.x >> 5, tid = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 4 * B200_AUG_MAX_OPS * 8; i += blockDim.x) sspec[i] = __ldg(spec + i);
+    __syncthreads();
+    const long rec_l = (long)blockIdx.x * SAMPLE_WARPS + warp;
+    if (rec_l >= (long)B * V) return;
+    const int b = (int)(rec_l / V), v = (int)(rec_l - (long)b * V);
+    const size_t rec = (size_t)rec_l;
+    int32_t* rec_i = rec_i_s[warp];
+    int32_t* rec_a = rec_a_s[warp];
+    uint16_t* perm = perm_s[warp];
+    uint32_t* bits = bits_s[warp];
     for (int i = tid; i < NGROUPS; i += 32) perm[i] = (uint16_t)i;
     if (tid < B200_AUG_GROUP_WORDS) bits[tid] = 0u;
     __syncwarp();
@@ -481,7 +489,9 @@ int b200_aug_sample_dev(const int32_t* spec, int B, int Vg, int Vl, uint64_t see
                         int32_t* aud_ops, uint32_t* group_bits, void* stream) {
     B200_REQUIRE(spec && img_ops && aud_ops && group_bits && B > 0 && Vg >= 0 && Vl >= 0 && Vg + Vl > 0, B200_E_ARG,
                  "aug_sample: bad arguments");
-    aug_sample_kernel<<<B * (Vg + Vl), 32, 0, as_stream(stream)>>>(spec, B, Vg, Vl, seed, step, img_ops, aud_ops, group_bits, step_dev);
+    const long recs = (long)B * (Vg + Vl);
+    aug_sample_kernel<<<(unsigned)((recs + SAMPLE_WARPS - 1) / SAMPLE_WARPS), 32 * SAMPLE_WARPS, 0, as_stream(stream)>>>(spec, B, Vg, Vl, seed, step, img_ops,
+                                                                                                                     aud_ops, group_bits, step_dev);
     return launch_status("aug_sample");
 }
 

@@ -129,8 +129,9 @@ struct TcCfg {
     // epilogue keeps the horizontally pooled even rows in a small shared-memory ring ("stash": POOL_R pooled rows) until the odd
     // row below them has been computed, then emits the window extreme -- a quarter of z.  A 128-row tile spans 128 / WQ image rows,
     // so the ring holds every even row a tile can touch plus the ones the warps of the NEXT tile may already be writing.
-    static constexpr bool POOL_OK = (CIN_ == 1 || COUT_ > CIN_) && NSPLIT_ == 1 && HO % 2 == 0 && HB % 2 == 0 && WO % 2 == 0 &&
-                                    (XPH % 2 == 0 || WQ % 2 == 0);
+    // Offered where the horizontal pair lives in one thread (XPH even).  The single-phase 32 -> 64 layers would need 64 lane shuffles
+    // per tile on top of their 128 statistics registers: measured 0.17 -> 0.28 / 0.34 ms (profiles/r2e_*), so they keep the z path.
+    static constexpr bool POOL_OK = (CIN_ == 1 || COUT_ > CIN_) && NSPLIT_ == 1 && HO % 2 == 0 && HB % 2 == 0 && WO % 2 == 0 && XPH % 2 == 0;
     static constexpr int POOL_R = 128 / WQ + 3;             // pooled rows of two consecutive tiles (a fast warp may be one tile phase ahead) + margin
     static constexpr int OCTL = COUTL / 8;
     static constexpr int POOL_ROW_UNITS = (WO / 2) * OCTL;       // 16-byte units (one pooled pixel of one channel octet, fp16) per pooled row

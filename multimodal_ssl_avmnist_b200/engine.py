@@ -225,11 +225,16 @@ class DinoStepEngine:
             if self.tc[mod] and self.tc[mod][0] and not (len(self.tc[mod]) > 1 and self.tc[mod][1]):
                 self.tc[mod][0] = False
         # forward layers whose 2x2 max-pool runs inside the convolution's epilogue (the pooled extreme e, a quarter of z, goes to the
-        # BatchNorm-apply kernel; the teacher and the evaluation pass never write the full-resolution z)
-        self.fused_pool = bool(fused_pool)      # False: the round-1 path (full-resolution z -> bn_relu_pool8_fwd), kept for A/B measurements
-        self.pool = {mod: [self.fused_pool and bool(self.tc[mod][li]) and ops.conv_tc_pool_supported(ci, co, hw, hw, k, pad)
-                           for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers)]
-                     for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers))}
+        # BatchNorm-apply kernel).  The epilogue pays for it with a per-tile barrier between its four warps (profiles/r2e_*): it wins
+        # where no z is written at all (teacher, evaluation) and on the HBM-bound first audio layer of the student; the student's other
+        # layers keep the z -> bn_relu_pool8_fwd path.  self.pool[role][mod][li]; role "t" also serves evaluation.
+        self.fused_pool = bool(fused_pool)      # False: the round-1 path everywhere (A/B measurements)
+        self.pool = {}
+        for role in ("s", "t"):
+            self.pool[role] = {mod: [self.fused_pool and bool(self.tc[mod][li]) and ops.conv_tc_pool_supported(ci, co, hw, hw, k, pad)
+                                     and (role == "t" or (ci == 1 and hw >= 112))
+                                     for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers)]
+                               for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers))}
         self._tcw = {}
         self._prep_desc = {}
         for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers)):
@@ -359,7 +364,7 @@ class DinoStepEngine:
                         wq = ops.quad8_width(hw, pad)
                         w[f"{mod}.xs8"] = e(N, hw, wq, 8, dtype=BF)             # first-layer input, quad8 (shared by the teacher)
                         w[f"{mod}.xs8_b"] = e(N, hw, wq, 8, dtype=BF)           # ... and the slot the next step's views are prefetched into
-                    pooled = tc and self.pool[mod][li]
+                    pooled = tc and self.pool[role][mod][li]
                     if pooled:
                         w[f"{role}.{mod}.e{li}"] = e(N, co // 8, ho // 2, ho // 2, 8, dtype=torch.float16)     # 2x2 window extreme of z
                     if tc and (role == "s" or not pooled):
@@ -563,7 +568,7 @@ class DinoStepEngine:
             z, stats = w.get(f"{role}.{mod}.z{li}"), w[f"{role}.{mod}.stats{li}"]
             tc = self.tc[mod][li]
             next_tc = li + 1 < len(layers) and self.tc[mod][li + 1]
-            pooled = tc and self.pool[mod][li]
+            pooled = tc and self.pool["s" if role == "s" else "t"][mod][li]
             if "zarena" not in w:
                 stats.zero_()
             wrole = role if role in ("s", "t") else self._eval_wrole      # the evaluation role "e" borrows a role's weight images
@@ -770,7 +775,7 @@ class DinoStepEngine:
                 next_tc = li + 1 < len(layers) and self.tc[mod][li + 1]
                 if tc and ci == 1:
                     w[f"{mod}.xs8"] = e(B, hw, ops.quad8_width(hw, pad), 8, dtype=BF)
-                if tc and self.pool[mod][li]:
+                if tc and self.pool["t"][mod][li]:
                     w[f"e.{mod}.e{li}"] = e(B, co // 8, ho // 2, ho // 2, 8, dtype=torch.float16)
                 else:
                     w[f"e.{mod}.z{li}"] = e(B, co // 8, ho, ho, 8, dtype=torch.float16) if tc else e(B, co, ho, ho)
