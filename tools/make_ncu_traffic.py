@@ -54,7 +54,8 @@ def main():
                 n = 1024 * (views if views > 1 else V_STUDENT)
                 npv = 1024 if views > 1 else n
                 shape = f"{n}x{hin}x{qw(win, pad)}x8" if cin == 1 else f"{n}x{cin // 8}x{hin}x{win}x8"
-                key = f"conv_tc:{shape}:{npv}x{cout}x{ks}x{pad}"
+                pooled = re.search(r">\s*,\s*(1|true)\s*>", name) is not None        # conv_tc_kernel<TcCfg<...>, POOL>
+                key = f"{'conv_tc_pool' if pooled else 'conv_tc'}:{shape}:{npv}x{cout}x{ks}x{pad}"
             elif m2:
                 a = [int(x) for x in m2.group(1).split(",")]
                 cin, hin, win, pad = a[0], a[2], a[3], a[5]
