@@ -552,8 +552,19 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
-    if use_graph:
-        eng.release_graph()                     # the per-op profile below steps eagerly
+    # launches per step, COUNTED: the kernel nodes of the step captured as one CUDA graph (all streams; NCCL kernels when N > 1);
+    # the per-wrapper tally above stays as a cross-check
+    launch_detail = {"tally_from_wrappers": int(launches)}
+    try:
+        if not use_graph:
+            eng._prefetch = None
+            eng.capture_train_step(B)
+        counts = eng.graph_node_counts()
+        launch_detail.update(counts, source="kernel nodes of one training step captured as a CUDA graph (cudaGraphGetNodes)")
+        launches = counts["kernels"]
+    except Exception as exc:
+        launch_detail["source"] = f"per-wrapper tally (graph census failed: {type(exc).__name__}: {exc})"
+    eng.release_graph()                         # the per-op profile below steps eagerly
     # per-op profile; every rank runs it (the step contains collectives when N > 1).  Consistency gate: with the side streams
     # off the per-op times must add up to about the step time (<= 1.3 x: the overlapped step hides ~15 %); otherwise a stall sat
     # between two events (allocation, clock ramp) and the profile is taken again.
@@ -656,7 +667,7 @@ def run_ours(args):
                     "ms_per_step": ms_e2e, "last_loss": last,
                     "note": "every step: H2D of its raw batch from pinned memory + D2H of its total loss (fp32 scalar, read back one "
                             "call later so that the host never waits for the step it has just enqueued)"},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "hbm_kernels": hbm, "cpu_baseline": cpu, "drop_in_module_path": drop_in,
+            "gpu_launches": int(launches), "gpu_launches_detail": launch_detail, "clocks": clk, "roofline": roof, "hbm_kernels": hbm, "cpu_baseline": cpu, "drop_in_module_path": drop_in,
             "impl": "ours"}
     print(json.dumps(line))
     if world > 1:

@@ -31,6 +31,8 @@ extern "C" {
 const char* b200_last_error(void);
 int b200_abi_version(void);                      /* bumped whenever a signature below changes */
 int b200_device_sm_count(int device);            /* helper for the host-side launch planner */
+/* node census of a captured CUDA graph (cudaGraph_t): counts[0..3] = kernel, memset, memcpy, other nodes */
+int b200_graph_node_counts(void* graph, int64_t* counts);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Teacher EMA  --  MultiModalDINO.update_teacher, models/dino.py:635-646 (UniModalDINO :1300-1311)

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -158,6 +160,37 @@ extern "C" {
 
 const char* b200_last_error(void) { return g_err; }
 int b200_abi_version(void) { return 1; }
+
+// Node census of a captured CUDA graph (cudaGraph_t): counts[0..3] = kernel, memset, memcpy, other nodes.  The engine uses it to
+// COUNT the kernel launches of one training step instead of tallying them by hand.
+int b200_graph_node_counts(void* graph, int64_t* counts) {
+    B200_REQUIRE(graph && counts, B200_E_ARG, "graph_node_counts: null pointer");
+    cudaGraph_t g = reinterpret_cast<cudaGraph_t>(graph);
+    size_t n = 0;
+    cudaError_t e = cudaGraphGetNodes(g, nullptr, &n);
+    if (e != cudaSuccess) {
+        set_error("graph_node_counts: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    cudaGraphNode_t* nodes = n ? (cudaGraphNode_t*)malloc(n * sizeof(cudaGraphNode_t)) : nullptr;
+    if (n) e = cudaGraphGetNodes(g, nodes, &n);
+    counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    for (size_t i = 0; e == cudaSuccess && i < n; ++i) {
+        cudaGraphNodeType t;
+        e = cudaGraphNodeGetType(nodes[i], &t);
+        if (e != cudaSuccess) break;
+        if (t == cudaGraphNodeTypeKernel) ++counts[0];
+        else if (t == cudaGraphNodeTypeMemset) ++counts[1];
+        else if (t == cudaGraphNodeTypeMemcpy) ++counts[2];
+        else ++counts[3];
+    }
+    free(nodes);
+    if (e != cudaSuccess) {
+        set_error("graph_node_counts: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
 int b200_device_sm_count(int device) {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;

@@ -1194,9 +1194,10 @@ class DinoStepEngine:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         restore()
-        graph = torch.cuda.CUDAGraph()
+        graph = torch.cuda.CUDAGraph(keep_graph=True)        # keep the cudaGraph_t: graph_node_counts() reads it
         with torch.cuda.graph(graph):
             g["loss"] = body()
+        graph.instantiate()
         restore()
         torch.cuda.synchronize()
         g["graph"] = graph
@@ -1217,6 +1218,16 @@ class DinoStepEngine:
         self.rng_step += 1
         self.step_count += 1
         return g["loss"]
+
+    def graph_node_counts(self):
+        """{'kernels', 'memsets', 'memcpys', 'other'} of the captured step: the step's launches COUNTED from the CUDA graph (every
+        kernel of every stream, the NCCL kernels of a data-parallel step included) rather than tallied per wrapper."""
+        if self._graph is None:
+            raise ops._lib.B200Error("graph_node_counts: call capture_train_step first")
+        import ctypes
+        counts = (ctypes.c_int64 * 4)()
+        ops._lib.check(ops._lib_().b200_graph_node_counts(self._graph["graph"].raw_cuda_graph(), counts), "graph_node_counts")
+        return dict(zip(("kernels", "memsets", "memcpys", "other"), (int(c) for c in counts)))
 
     def release_graph(self):
         """Back to eager stepping (the host counters are authoritative again)."""
