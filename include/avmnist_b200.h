@@ -322,7 +322,9 @@ int b200_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_a
                    float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
                    float bias_correction2_sqrt, float grad_scale, void* stream);
 /* CUDA-graph replay: bc_out[0] = 1 - beta1^t, bc_out[1] = sqrt(1 - beta2^t) for t = *step_dev + 1 (double arithmetic, rounded
- * to fp32 like the host path); b200_adam_flat_dev reads them from device memory; b200_counters_advance adds 1 to n counters. */
+ * to fp32 like the host path); b200_adam_flat_dev reads them from device memory -- bc_dev is float[3]: with lr < 0 the learning
+ * rate is read from bc_dev[2] as well, so a per-epoch scheduler (CosineAnnealingLR, models/dino.py:959) changes it without a
+ * re-capture; b200_counters_advance adds 1 to n counters. */
 int b200_adam_bias_dev(const int64_t* step_dev, double beta1, double beta2, float* bc_out, void* stream);
 int b200_adam_flat_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                        float beta1, float beta2, float eps, float weight_decay, const float* bc_dev, float grad_scale,

@@ -90,25 +90,47 @@ __global__ void __launch_bounds__(256) ema_multi_kernel(float* const* __restrict
 // Adam over a flat arena (torch.optim.Adam semantics: g += wd*p; m,v EMAs; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps))
 // 28 B per element.  grad_scale multiplies the incoming gradient (DP mean, AMP unscale).
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void adam_one(float& pi, float gi_raw, float& mi, float& vi, float step, float b1, float b2, float eps, float wd,
+                                         float bc2s, float gs) {
+    const float gi = gi_raw * gs + wd * pi;
+    mi = mi * b1 + (1.0f - b1) * gi;
+    vi = vi * b2 + (1.0f - b2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2s + eps;
+    pi = pi - step * (mi / denom);
+}
+
 __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
                                                         float b1, float b2, float eps, float wd, float bc1, float bc2s,
                                                         float gs, const float* __restrict__ bc_dev) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    if (bc_dev != nullptr) {          // CUDA-graph replay: the bias corrections of this step were computed on the device
+    if (bc_dev != nullptr) {          // CUDA-graph replay: the bias corrections (and the learning rate) of this step live on the device
         bc1 = __ldg(bc_dev);
         bc2s = __ldg(bc_dev + 1);
+        if (lr < 0.f) lr = __ldg(bc_dev + 2);
     }
     const float step = lr / bc1;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        float pi = p[i];
-        float gi = __ldg(g + i) * gs + wd * pi;
-        float mi = m[i] * b1 + (1.0f - b1) * gi;
-        float vi = v[i] * b2 + (1.0f - b2) * gi * gi;
+    // 128-bit accesses over the aligned body (the arenas are 16-byte aligned and padded; same arithmetic per element either way)
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                       reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+    const int64_t n4 = vec ? n / 4 : 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+        adam_one(pp.x, gg.x, mm.x, vv.x, step, b1, b2, eps, wd, bc2s, gs);
+        adam_one(pp.y, gg.y, mm.y, vv.y, step, b1, b2, eps, wd, bc2s, gs);
+        adam_one(pp.z, gg.z, mm.z, vv.z, step, b1, b2, eps, wd, bc2s, gs);
+        adam_one(pp.w, gg.w, mm.w, vv.w, step, b1, b2, eps, wd, bc2s, gs);
+        reinterpret_cast<float4*>(m)[i] = mm;
+        reinterpret_cast<float4*>(v)[i] = vv;
+        reinterpret_cast<float4*>(p)[i] = pp;
+    }
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float pi = p[i], mi = m[i], vi = v[i];
+        adam_one(pi, __ldg(g + i), mi, vi, step, b1, b2, eps, wd, bc2s, gs);
         m[i] = mi;
         v[i] = vi;
-        float denom = sqrtf(vi) / bc2s + eps;
-        p[i] = pi - step * (mi / denom);
+        p[i] = pi;
     }
 }
 

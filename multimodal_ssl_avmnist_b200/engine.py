@@ -1094,8 +1094,8 @@ class DinoStepEngine:
             ops.adam_bias_dev(self._ctr[1:2], self._bc)
         for lo, hi in ranges:
             if self._ctr is not None:
-                ops.adam_flat_dev(self.student.flat[lo:hi], self.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self._bc, self.lr,
-                                  weight_decay=self.weight_decay, grad_scale=gs)
+                ops.adam_flat_dev(self.student.flat[lo:hi], self.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self._bc, -1.0,
+                                  weight_decay=self.weight_decay, grad_scale=gs)       # lr < 0: read from self._bc[2] (scheduler-friendly)
             else:
                 ops.adam_flat(self.student.flat[lo:hi], self.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.step_count,
                               self.lr, weight_decay=self.weight_decay, grad_scale=gs)
@@ -1162,7 +1162,8 @@ class DinoStepEngine:
         B into ONE CUDA graph.  The per-step scalars (RNG stream position, Adam step) move to device counters that the graph
         advances itself, so a replay needs no host arguments and reproduces the eager step bit for bit.  Data parallel: the
         NCCL all-reduces (b200_dp_*, communication stream) are captured with the kernels; every rank must capture and replay in
-        lock-step.  lr / temperatures are baked in (re-capture after changing them).  Use graph_step() afterwards."""
+        lock-step.  The learning rate is a device scalar (schedulers may change engine.lr between replays); temperatures, momenta and
+        weight decay are baked in (re-capture after changing them).  Use graph_step() afterwards."""
         dev = self.device
         g = {"B": B, "img": torch.zeros(B, 28, 28, dtype=image_dtype, device=dev)}
         if self.aud_layers:
@@ -1174,7 +1175,9 @@ class DinoStepEngine:
         snap = [t.clone() for t in state]
         host = (self.rng_step, self.step_count)
         self._ctr = torch.tensor(host, dtype=torch.int64, device=dev)
-        self._bc = torch.zeros(2, device=dev)
+        self._bc = torch.zeros(3, device=dev)               # bias corrections of the step + the learning rate (read by the captured Adam)
+        self._bc[2:3].fill_(float(self.lr))
+        self._graph_lr = float(self.lr)
 
         def body():
             return self.train_step(g["img"], g.get("aud"), g.get("lab"))
@@ -1214,6 +1217,9 @@ class DinoStepEngine:
             g["aud"].copy_(audios.reshape(g["aud"].shape))
         if "lab" in g:
             g["lab"].copy_(labels)
+        if float(self.lr) != self._graph_lr:                 # a scheduler moved the learning rate: one 4-byte fill, no re-capture
+            self._graph_lr = float(self.lr)
+            self._bc[2:3].fill_(self._graph_lr)
         g["graph"].replay()
         self.rng_step += 1
         self.step_count += 1
