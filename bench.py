@@ -252,6 +252,11 @@ def op_cost(name, meta):
         Ho, Wo = H + 2 * pad - K + 1, W + 2 * pad - K + 1
         z_bytes = numel(meta[-2]) * 2.0 if len(meta) >= 6 else 0.0
         return 2.0 * N * Cout * Ho * Wo * Cin * K * K, numel(x) * 2.0 + z_bytes + numel(e8) * 2.0
+    if name == "conv_tc_dgrad_bnstat" and len(meta) >= 4 and len(ints) >= 3:
+        # (dz8, wprep, dx8, p8) + (n_per_view, K, pad'): data gradient whose epilogue also reads p and accumulates the BN-backward sums
+        dz, dx, p8 = meta[0], meta[2], meta[3]
+        K = ints[1]
+        return 2.0 * dx[0] * dx[1] * 8 * dx[2] * dx[3] * dz[1] * 8 * K * K, (numel(dz) + numel(dx) + numel(p8)) * 2.0
     if name == "bn_relu_apply8" and len(meta) >= 4:
         return 0.0, numel(meta[0]) * 2.0 + numel(meta[3]) * (2.0 if len(meta[3]) == 5 else 4.0)
     if name == "conv_tc_wgrad" and len(meta) >= 3:
@@ -477,7 +482,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     B = per_gpu_batch(args, world)
     eng = DinoStepEngine(kind=args.kind, mode=args.mode, augment_values=augment_values() if args.kind == "multi_central" else None,
-                         seed=1 + rank, device=dev, fused_pool=not args.no_fused_pool)
+                         seed=1 + rank, device=dev, fused_pool=not args.no_fused_pool, fused_bnstat=not args.no_fused_bnstat)
     g = torch.Generator().manual_seed(1 + rank)
     img_h = torch.rand(B, 28, 28, generator=g).pin_memory()
     aud_h = torch.randint(0, 256, (B, 112, 112), generator=g, dtype=torch.uint8).pin_memory() if args.kind == "multi_central" else None
@@ -622,7 +627,7 @@ def run_ours(args):
         if NCU_EXTRA.get("tensor_pipe_busy_pct", 0) > 80:
             roof["note"] = (roof.get("note", "") + "; ncu: the tensor pipe is busy %.0f %% of the time (a UMMA occupies it for its shared-memory operand "
                             "fetch whatever its N): the kernel's real ceiling" % NCU_EXTRA["tensor_pipe_busy_pct"]).lstrip("; ")
-    tc_rows = [r for r in rows if r["op"] in ("conv_tc", "conv_tc_pool", "conv_tc_wgrad")]
+    tc_rows = [r for r in rows if r["op"] in ("conv_tc", "conv_tc_pool", "conv_tc_dgrad_bnstat", "conv_tc_wgrad")]
     if tc_rows:
         tc_ms = sum(r["ms_per_step"] for r in tc_rows)
         tc_fl = sum(r["flops"] * r["calls_per_step"] for r in tc_rows)
@@ -693,6 +698,8 @@ def main():
     ap.add_argument("--reference-fp32", action="store_true", help="library bar without fp16 autocast")
     ap.add_argument("--no-fused-pool", action="store_true",
                     help="A/B: the round-1 forward (full-resolution z -> bn_relu_pool8_fwd) instead of the fused max-pool epilogue")
+    ap.add_argument("--no-fused-bnstat", action="store_true",
+                    help="A/B: separate bn_pool8_bwd_reduce_p passes instead of the BN-backward sums in the data-gradient epilogue")
     ap.add_argument("--graph", action="store_true",
                     help="replay the whole step from one CUDA graph (meant for small per-GPU batches, where the ~165 host-side "
                          "launches bound the step; with N > 1 the all-reduces are captured too)")

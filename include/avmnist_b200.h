@@ -209,6 +209,15 @@ int b200_conv_tc_pool_supported(int Cin, int Cout, int H, int W, int K, int pad)
 int b200_conv_tc_pool(const void* x_act8, const void* wprep, const float* bias, const float* gamma, void* z_out, void* pool_out,
                       double* stats, int N, int n_per_view, int Cin, int Cout, int H, int W, int K, int pad, int z_fmt,
                       void* stream);
+/* Data gradient of a convolution whose output dx is the gradient dp of the layer below's pooled activation p (bf16 act8, same
+ * shape as dx), with that layer's BatchNorm-backward statistics fused into the epilogue:
+ *   sums[view][c] += { sum_{p>0} dp, sum_{p>0} dp * (p - beta[c]) / gamma[c] }      (what b200_bn_pool8_bwd_reduce_p computes in a
+ * pass of its own; gamma / beta = the lower layer's BatchNorm weight / bias, sums zeroed by the caller).  Arguments as b200_conv_tc
+ * for a data gradient: (Cin, Cout) = (channels of dz, channels of dx), H/W those of dz, pad = K-1-pad_forward, flipped weights. */
+int b200_conv_tc_dgrad_bnstat_supported(int Cin, int Cout, int H, int W, int K, int pad);
+int b200_conv_tc_dgrad_bnstat(const void* dz_act8, const void* wprep_flip, void* dx_act8, const void* p_act8, const float* gamma,
+                              const float* beta, double* sums, int N, int n_per_view, int Cin, int Cout, int H, int W, int K,
+                              int pad, void* stream);
 /* e8: fp16 act8 [N][C/8][HP][WP][8] from b200_conv_tc_pool; out_fmt 0 = fp32 NCHW [N][C][HP][WP], 1 = bf16 act8 */
 int b200_bn_relu_apply8(const void* e8, const float* scale, const float* shift, void* out, int N, int n_per_view, int C, int HP,
                         int WP, int out_fmt, void* stream);

@@ -132,6 +132,7 @@ struct TcCfg {
     // Offered where the horizontal pair lives in one thread (XPH even).  The single-phase 32 -> 64 layers would need 64 lane shuffles
     // per tile on top of their 128 statistics registers: measured 0.17 -> 0.28 / 0.34 ms (profiles/r2e_*), so they keep the z path.
     static constexpr bool POOL_OK = (CIN_ == 1 || COUT_ > CIN_) && NSPLIT_ == 1 && HO % 2 == 0 && HB % 2 == 0 && WO % 2 == 0 && XPH % 2 == 0;
+    static constexpr bool BSTAT_OK = CIN_ > COUT_ && NSPLIT_ == 1;          // data-gradient instances (channels shrink): fused BN-backward sums
     static constexpr int POOL_R = 128 / WQ + 3;             // pooled rows of two consecutive tiles (a fast warp may be one tile phase ahead) + margin
     static constexpr int OCTL = COUTL / 8;
     static constexpr int POOL_ROW_UNITS = (WO / 2) * OCTL;       // 16-byte units (one pooled pixel of one channel octet, fp16) per pooled row
@@ -139,7 +140,7 @@ struct TcCfg {
     static constexpr int SIGN_OFF = BAR_OFF + 256 + NPADL * 4;   // per accumulator column pair: fp16 sign-bit masks (sign of gamma)
     static constexpr int POOL_OFF = round_up(SIGN_OFF + NPADL * 2, 16);
     static constexpr int SMEM = POOL_OFF + POOL_BYTES;           // the pooling instance
-    static constexpr int SMEM_NOPOOL = BAR_OFF + 256 + NPADL * 4;
+    static constexpr int SMEM_NOPOOL = SIGN_OFF + NPADL * 4;     // bias / beta [NPADL] + 1 / gamma [NPADL] (BSTAT instances)
     static constexpr int NBUF = nbuf_for(NPADL, CTAS);          // TMEM accumulator stages
     static constexpr int TMEM_COLS = pow2_cols(NBUF * NPADL);
     // One issuing thread sustains only ~1 UMMA per 140 cycles at these tile shapes (measured, tools/umma_probe.cu); four
@@ -157,6 +158,11 @@ struct TcCfg {
     static_assert(XPL * PHASE_BYTES < (1 << 18) && PLANE_BYTES % 16 == 0, "descriptor range");
 };
 
+__device__ __forceinline__ void ld_global_nc_256(const uint4* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
 __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
     uint32_t d;
     asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
@@ -180,11 +186,15 @@ __device__ __forceinline__ int pool_unit(int h, int xq) {
 // out: fp32 NCHW [N][COUT][HO][WO] (out_bf16 == 0), bf16 act8 [N][COUT/8][HO][WO][8] (1) or the same in fp16 (2: the pre-BatchNorm
 // z, which is never an MMA operand -- 11 mantissa bits keep max-pool arg-max ties as rare as on the reference's fp16 autocast path).
 // bias may be null (no bias, no statistics); stats: double [views][COUT][2] (sum, sum of squares), accumulated.
-template <class C, bool POOL>
+// BSTAT (data-gradient instances): the output dx is the gradient dp of the layer BELOW's pooled activation p; the epilogue also
+// reads p (same shape, bf16 act8: `pool_out` carries the pointer) and accumulates that layer's BatchNorm-backward sums
+// {sum_{p>0} dp, sum_{p>0} dp * (p - beta) / gamma} into `stats` -- exactly what bn_pool8_bwd_reduce_p computes in a pass of its own
+// (gamma / beta2 = that layer's BatchNorm weight / bias).
+template <class C, bool POOL, bool BSTAT = false>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS)
 conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wprep, const float* __restrict__ bias,
                void* __restrict__ out, double* __restrict__ stats, int n_per_view, int out_bf16,
-               uint4* __restrict__ pool_out, const float* __restrict__ gamma) {
+               uint4* __restrict__ pool_out, const float* __restrict__ gamma, const float* __restrict__ beta2 = nullptr) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_s = smem;
     uint8_t* img_s = smem + C::W_BYTES;
@@ -192,6 +202,7 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::BAR_OFF + 200);
     float* bias_s = reinterpret_cast<float*>(smem + C::BAR_OFF + 256);
     uint32_t* sign_s = reinterpret_cast<uint32_t*>(smem + C::SIGN_OFF);     // [NPADL / 2]: 0x8000 bits where gamma < 0 (two columns per word)
+    float* ig_s = reinterpret_cast<float*>(smem + C::SIGN_OFF);             // BSTAT: 1 / gamma per column (bias_s then holds beta)
     uint4* stash = reinterpret_cast<uint4*>(smem + C::POOL_OFF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -218,6 +229,14 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
         for (int i = threadIdx.x; i < C::IMG_BYTES / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
         for (int i = threadIdx.x; i < C::NPADL; i += blockDim.x)     // column (octet, phase, channel): the bias repeats per phase
             bias_s[i] = (bias != nullptr && i < C::XPH * C::COUTL) ? bias[blockIdx.z * C::COUTL + C::col_channel(i)] : 0.f;
+        if constexpr (BSTAT) {
+            for (int i = threadIdx.x; i < C::NPADL; i += blockDim.x) {
+                const bool real = i < C::XPH * C::COUTL;
+                const float gm = real ? gamma[blockIdx.z * C::COUTL + C::col_channel(i)] : 0.f;
+                ig_s[i] = gm != 0.f ? 1.0f / gm : 0.f;
+                bias_s[i] = real ? beta2[blockIdx.z * C::COUTL + C::col_channel(i)] : 0.f;
+            }
+        }
         if constexpr (POOL) {
             for (int i = threadIdx.x; i < C::NPADL / 2; i += blockDim.x) {
                 uint32_t m = 0;
@@ -330,7 +349,7 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
 #pragma unroll
         for (int c = 0; c < C::COUTL; ++c) s1[c] = s2[c] = 0.f;
         const int co0 = blockIdx.z * C::COUTL;                  // first output channel of this CTA's slice
-        const bool do_stats = (bias != nullptr) && (stats != nullptr);
+        const bool do_stats = BSTAT ? (stats != nullptr) : ((bias != nullptr) && (stats != nullptr));
         constexpr int NCH = C::NPADL / 16;                       // 16-column chunks of the accumulator
         constexpr int NHP = POOL ? (C::XPH % 2 == 0 ? NCH : 2 * NCH) : 1;      // pooled 16-byte units this thread may own per tile
         uint32_t tcount = 0;
@@ -360,10 +379,41 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int col = cc * 16 + j, ch = C::col_channel(col);
-                        f[j] = __uint_as_float(v[j]) + bias_s[col];
-                        if (col < C::XPH * C::COUTL && valid) {
-                            s1[ch] += f[j];
-                            s2[ch] += f[j] * f[j];
+                        if constexpr (BSTAT) {
+                            f[j] = __uint_as_float(v[j]);
+                        } else {
+                            f[j] = __uint_as_float(v[j]) + bias_s[col];
+                            if (col < C::XPH * C::COUTL && valid) {
+                                s1[ch] += f[j];
+                                s2[ch] += f[j] * f[j];
+                            }
+                        }
+                    }
+                    if constexpr (BSTAT) {
+                        // BatchNorm-backward sums of the layer below from (p, dp = this output, as stored: bf16-rounded)
+                        const int col0 = cc * 16;
+                        if (valid && col0 < C::XPH * C::COUTL) {
+                            const int ph0 = C::col_phase(col0), oct0 = C::col_channel(col0) / 8;
+                            const uint4* pin = pool_out;
+                            uint4 pa, pb;
+                            if constexpr (C::XPH % 2 == 0) {     // two adjacent pixels of one octet: 32 contiguous bytes
+                                ld_global_nc_256(pin + (((long)n * (C::COUT / 8) + co0 / 8 + oct0) * C::HO + yy) * C::WO + xq * C::XPH + ph0, pa, pb);
+                            } else {                             // two octets of one pixel
+                                pa = __ldg(pin + (((long)n * (C::COUT / 8) + co0 / 8 + oct0) * C::HO + yy) * C::WO + xq);
+                                pb = (oct0 + 1) * 8 < C::COUTL ? __ldg(pin + (((long)n * (C::COUT / 8) + co0 / 8 + oct0 + 1) * C::HO + yy) * C::WO + xq)
+                                                               : make_uint4(0, 0, 0, 0);
+                            }
+                            const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int col = col0 + j, ch = C::col_channel(col);
+                                const float pv = __uint_as_float((j & 1) ? (pw[j >> 1] & 0xFFFF0000u) : (pw[j >> 1] << 16));
+                                const float gr = __bfloat162float(__float2bfloat16_rn(f[j]));
+                                if (col < C::XPH * C::COUTL && pv > 0.f) {
+                                    s1[ch] += gr;
+                                    s2[ch] += gr * ((pv - bias_s[col]) * ig_s[col]);
+                                }
+                            }
                         }
                     }
                     if constexpr (POOL) {
@@ -622,7 +672,7 @@ __global__ void pack_quad8_kernel(const float* __restrict__ x, uint4* __restrict
 
 template <class C>
 int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* out, double* stats, int N, int n_per_view, int out_bf16,
-                   cudaStream_t st, void* pool_out = nullptr, const float* gamma = nullptr) {
+                   cudaStream_t st, void* pool_out = nullptr, const float* gamma = nullptr, const float* beta2 = nullptr) {
     if (pool_out != nullptr && !C::POOL_OK) {
         set_error("conv_tc: this geometry has no fused max-pool epilogue");
         return -5;
@@ -631,6 +681,8 @@ int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* ou
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_NOPOOL);
         if (e == cudaSuccess && C::POOL_OK) e = cudaFuncSetAttribute(conv_tc_kernel<C, C::POOL_OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e == cudaSuccess && C::BSTAT_OK)
+            e = cudaFuncSetAttribute(conv_tc_kernel<C, false, C::BSTAT_OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_NOPOOL);
         if (e != cudaSuccess) {
             set_error("conv_tc: cannot set %d bytes of shared memory: %s", C::SMEM, cudaGetErrorString(e));
             return (int)e;
@@ -652,7 +704,14 @@ int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* ou
     if (G < 1) G = 1;
     const long items = (long)n_per_view * C::BANDS;
     if (G > items) G = (int)items;
-    if (pool_out != nullptr)
+    if (beta2 != nullptr) {
+        if (!C::BSTAT_OK) {
+            set_error("conv_tc: this geometry has no fused BatchNorm-backward statistics");
+            return -5;
+        }
+        conv_tc_kernel<C, false, C::BSTAT_OK><<<dim3(G, views, C::NSPLIT), C::THREADS, C::SMEM_NOPOOL, st>>>(
+            tm, reinterpret_cast<const uint4*>(wprep), nullptr, out, stats, n_per_view, out_bf16, reinterpret_cast<uint4*>(pool_out), gamma, beta2);
+    } else if (pool_out != nullptr)
         conv_tc_kernel<C, C::POOL_OK><<<dim3(G, views, C::NSPLIT), C::THREADS, C::SMEM, st>>>(tm, reinterpret_cast<const uint4*>(wprep), bias, out, stats,
                                                                                               n_per_view, out_bf16, reinterpret_cast<uint4*>(pool_out), gamma);
     else
@@ -1624,6 +1683,28 @@ int b200_conv_tc_pool(const void* x_act8, const void* wprep, const float* bias, 
     TC_RUN(CfgA1) TC_RUN(CfgA2) TC_RUN(CfgA3) TC_RUN(CfgI1) TC_RUN(CfgS1) TC_RUN(CfgA0) TC_RUN(CfgI0) TC_RUN(CfgS0)
 #undef TC_RUN
     set_error("conv_tc_pool: unsupported geometry Cin=%d Cout=%d H=%d W=%d K=%d pad=%d", Cin, Cout, H, W, K, pad);
+    return -4;
+}
+
+int b200_conv_tc_dgrad_bnstat_supported(int Cin, int Cout, int H, int W, int K, int pad) {
+#define TC_HAS(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) return CFG::BSTAT_OK ? 1 : 0;
+    TC_HAS(CfgA1d) TC_HAS(CfgA2d) TC_HAS(CfgA3d) TC_HAS(CfgI1d) TC_HAS(CfgS1d) TC_HAS(CfgS2d)
+#undef TC_HAS
+    return 0;
+}
+
+int b200_conv_tc_dgrad_bnstat(const void* dz_act8, const void* wprep_flip, void* dx_act8, const void* p_act8, const float* gamma, const float* beta,
+                              double* sums, int N, int n_per_view, int Cin, int Cout, int H, int W, int K, int pad, void* stream) {
+    B200_REQUIRE(dz_act8 && wprep_flip && dx_act8 && p_act8 && gamma && beta && sums, -1, "conv_tc_dgrad_bnstat: null pointer");
+    B200_REQUIRE(N > 0 && n_per_view > 0 && N % n_per_view == 0, -2, "conv_tc_dgrad_bnstat: N=%d must be a multiple of n_per_view=%d", N, n_per_view);
+    B200_REQUIRE((((uintptr_t)dz_act8 | (uintptr_t)wprep_flip | (uintptr_t)dx_act8) & 15) == 0 && ((uintptr_t)p_act8 & 31) == 0, -3,
+                 "conv_tc_dgrad_bnstat: pointers must be 16-byte aligned (p: 32-byte)");
+    cudaStream_t st = as_stream(stream);
+#define TC_RUN(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) \
+        return launch_conv_tc<CFG>(dz_act8, wprep_flip, nullptr, dx_act8, sums, N, n_per_view, 1, st, const_cast<void*>(p_act8), gamma, beta);
+    TC_RUN(CfgA1d) TC_RUN(CfgA2d) TC_RUN(CfgA3d) TC_RUN(CfgI1d) TC_RUN(CfgS1d) TC_RUN(CfgS2d)
+#undef TC_RUN
+    set_error("conv_tc_dgrad_bnstat: unsupported geometry Cin=%d Cout=%d H=%d W=%d K=%d pad=%d", Cin, Cout, H, W, K, pad);
     return -4;
 }
 

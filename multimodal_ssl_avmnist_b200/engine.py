@@ -143,7 +143,7 @@ class DinoStepEngine:
                  n_global_views=2, n_local_views=4, momentum=0.996, center_momentum=0.9, student_temperature=0.1,
                  teacher_temperature=0.04, learning_rate=1e-4, weight_decay=1e-6, dropout=0.3, fusion_dropout=0.3, alpha=1.0,
                  cosine_loss_alpha=0.0, augment_values=None, seed=0, device=None, process_group=None, data_parallel=None,
-                 precision="bf16", fused_pool=True):
+                 precision="bf16", fused_pool=True, fused_bnstat=True):
         if not torch.cuda.is_available():
             raise ops._lib.B200Error("DinoStepEngine needs a CUDA device: the hot path has no CPU fallback")
         ops._lib.load()
@@ -235,6 +235,13 @@ class DinoStepEngine:
                                      and (role == "t" or (ci == 1 and hw >= 112))
                                      for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers)]
                                for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers))}
+        # data-gradient convolutions that also produce the BatchNorm-backward sums of the layer below in their epilogue (the separate
+        # bn_pool8_bwd_reduce_p pass over p and dp disappears): layer li's data gradient serves layer li - 1
+        self.fused_bnstat = bool(fused_bnstat)
+        self.bnstat = {mod: [self.fused_bnstat and li > 0 and bool(self.tc[mod][li]) and bool(self.tc[mod][li - 1]) and
+                             ops.conv_tc_dgrad_bnstat_supported(co, ci, hw + 2 * pad - k + 1, hw + 2 * pad - k + 1, k, k - 1 - pad)
+                             for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers)]
+                       for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers))}
         self._tcw = {}
         self._prep_desc = {}
         for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers)):
@@ -704,7 +711,8 @@ class DinoStepEngine:
                 if not fused:
                     dz = w[f"{mod}.dz8" if par == 0 else f"{mod}.dz8b"][:z.numel()].view_as(z)
                 p_out = w[f"s.{mod}.p8{li}"] if f"s.{mod}.p8{li}" in w else w[f"s.{mod}.p{li}"]
-                ops.bn_pool8_bwd_reduce_p(p_out, d_p, S["enc." + bn + ".weight"], S["enc." + bn + ".bias"], sums, B)
+                if not (li + 1 < len(layers) and self.bnstat[mod][li + 1]):      # else: the data gradient above already accumulated them
+                    ops.bn_pool8_bwd_reduce_p(p_out, d_p, S["enc." + bn + ".weight"], S["enc." + bn + ".bias"], sums, B)
                 if not fused:
                     ops.bn_relu_pool8_bwd_apply(z, d_p, sc, sh, mu, inv, sums, dz, B, dbsum=w[f"{mod}.dbsum"][li])
                     ops.bias_grad_finalize(w[f"{mod}.dbsum"][li], G["enc." + conv + ".bias"])
@@ -744,7 +752,12 @@ class DinoStepEngine:
                         d_in = nxt.view(BF)[:N * ci * hw * hw].view(N, ci // 8, hw, hw, 8)
                     else:
                         d_in = nxt[:N * ci * hw * hw].view(N, ci, hw, hw)
-                    ops.conv_tc(dz, self._tcw[("flip", mod, li)], None, d_in, None, N, ci, k, k - 1 - pad)
+                    if self.bnstat[mod][li]:
+                        lbn = layers[li - 1][1]
+                        ops.conv_tc_dgrad_bnstat(dz, self._tcw[("flip", mod, li)], d_in, w[f"s.{mod}.p8{li - 1}"], S["enc." + lbn + ".weight"],
+                                                 S["enc." + lbn + ".bias"], w[f"s.{mod}.sums{li - 1}"], B, k, k - 1 - pad)
+                    else:
+                        ops.conv_tc(dz, self._tcw[("flip", mod, li)], None, d_in, None, N, ci, k, k - 1 - pad)
                 else:
                     d_in = nxt[:N * ci * hw * hw].view(N, ci, hw, hw)
                     ops.conv_bwd_data(dz, S["enc." + conv + ".weight"], d_in, pad)

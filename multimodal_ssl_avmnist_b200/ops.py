@@ -313,6 +313,19 @@ def conv_tc_pool(x8, wprep, bias, gamma, z_out, pool_out, stats, n_per_view, Cou
                "conv_tc_pool")
 
 
+def conv_tc_dgrad_bnstat_supported(Cin, Cout, H, W, K, pad):
+    return bool(_lib_().b200_conv_tc_dgrad_bnstat_supported(Cin, Cout, H, W, K, pad))
+
+
+def conv_tc_dgrad_bnstat(dz8, wprep_flip, dx8, p8, gamma, beta, sums, n_per_view, K, pad):
+    """Data gradient (dz8 -> dx8, bf16 act8) + the BatchNorm-backward sums of the layer below (from its pooled output p8 and dx8 = dp)
+    in the epilogue.  pad = K - 1 - pad_forward."""
+    N, P, H, W, _ = dz8.shape
+    Cout = dx8.shape[1] * 8
+    _lib.check(_lib_().b200_conv_tc_dgrad_bnstat(_ptr(dz8, BF16), _ptr(wprep_flip), _ptr(dx8, BF16), _ptr(p8, BF16), _ptr(gamma, F32), _ptr(beta, F32),
+                                                 _ptr(sums, F64), N, n_per_view, P * 8, Cout, H, W, K, pad, _stream()), "conv_tc_dgrad_bnstat")
+
+
 def bn_relu_apply8(e8, scale, shift, out, n_per_view):
     """p = ReLU(scale * e + shift) on the pooled extreme e8 (fp16 act8) -> out: fp32 NCHW or bf16 act8 (by dtype)."""
     N, P, HP, WP, _ = e8.shape
@@ -581,7 +594,7 @@ def knn_predict(train_feats, train_labels, test_feats, k=5, n_classes=10, return
 # ---- launch accounting and optional per-op timing ------------------------------------------------------------
 # Every wrapper above issues a fixed number of kernel launches; the table lists the ones that issue more than one.
 _LAUNCHES = {"ntxent_fwd_bwd": 5, "conv_tc_wgrad_l0_fused": 3, "conv_tc_wgrad": 2, "conv_bwd_weight": 3, "linear_bwd_weight": 3, "infonce_fwd_bwd": 9}
-_NOT_KERNELS = {"knn_predict", "conv_tc_pool_supported", "quad8_width", "ntxent_work_floats", "conv_tc_wgrad_l0_fused_work_floats", "conv_tc_wgrad_work_floats", "conv_tc_supported", "conv_tc_weight_bytes", "dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
+_NOT_KERNELS = {"knn_predict", "conv_tc_pool_supported", "conv_tc_dgrad_bnstat_supported", "quad8_width", "ntxent_work_floats", "conv_tc_wgrad_l0_fused_work_floats", "conv_tc_wgrad_work_floats", "conv_tc_supported", "conv_tc_weight_bytes", "dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
 LAUNCH_COUNT = 0
 _PROFILE = None          # None, or a list receiving (name, start_event, end_event, meta)
 

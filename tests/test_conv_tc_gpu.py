@@ -481,3 +481,41 @@ def test_conv_tc_fused_pool_epilogue_is_bit_identical_to_the_unfused_chain(geom,
         ops.bn_relu_apply8(e8, sc, sh, p32, B)
         torch.cuda.synchronize()
         assert torch.equal(p8, p8_ref) and torch.equal(p32, p32_ref)
+
+
+# data gradients (forward geometry: Cin, Cout, H, K, pad) whose epilogue also produces the BN-backward sums of the layer below
+DGRAD_BNSTAT = [(8, 16, 56, 5, 2), (16, 32, 28, 5, 2), (32, 64, 14, 5, 2), (32, 64, 14, 5, 0), (32, 64, 14, 3, 1)]
+
+
+@pytest.mark.parametrize("geom", DGRAD_BNSTAT)
+@pytest.mark.parametrize("views,B", [(1, 3), (3, 5), (7, 41)])
+def test_dgrad_with_fused_bn_backward_statistics(geom, views, B):
+    """b200_conv_tc_dgrad_bnstat == b200_conv_tc (data gradient) followed by b200_bn_pool8_bwd_reduce_p on (p, dp): dx bit for bit,
+    the per-(view, channel) sums to fp64-atomic rounding; mixed-sign / zero BatchNorm weights, dead (p == 0) units."""
+    Cin, Cout, H, K, pad = geom
+    Ho = H + 2 * pad - K + 1
+    assert ops.conv_tc_dgrad_bnstat_supported(Cout, Cin, Ho, Ho, K, K - 1 - pad)
+    g = torch.Generator().manual_seed(Cin + 3 * Cout + views)
+    N = views * B
+    dz = torch.randn(N, Cout, Ho, Ho, generator=g).to(DEV)
+    w = (torch.randn(Cout, Cin, K, K, generator=g) / (Cout * K * K) ** 0.5).to(DEV)
+    gamma = (torch.randn(Cin, generator=g) * 0.5 + 0.8).to(DEV)
+    gamma[1] = -0.6
+    gamma[2] = 0.0
+    beta = (torch.randn(Cin, generator=g) * 0.3).to(DEV)
+    p = torch.relu(torch.randn(N, Cin, H, H, generator=g)).to(DEV)            # pooled activations of the layer below: half of them dead
+    dz8 = _pack8(dz)
+    p8 = _pack8(p)
+    wp = _prep(w, flip=True)
+    dx_ref = torch.full((N, Cin // 8, H, H, 8), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.conv_tc(dz8, wp, None, dx_ref, None, N, Cin, K, K - 1 - pad)
+    want = torch.zeros(views, Cin, 2, dtype=torch.float64, device=DEV)
+    ops.bn_pool8_bwd_reduce_p(p8, dx_ref, gamma, beta, want, B)
+    dx = torch.full_like(dx_ref, float("nan"))
+    got = torch.zeros_like(want)
+    ops.conv_tc_dgrad_bnstat(dz8, wp, dx, p8, gamma, beta, got, B, K, K - 1 - pad)
+    torch.cuda.synchronize()
+    assert torch.equal(dx, dx_ref)
+    scale = want.abs().max(dim=1, keepdim=True).values + 1e-9
+    # same fp32 products, summed per thread in a different order than the stand-alone reduction: 1e-5 of the per-view scale
+    assert float(((got - want).abs() / scale).max()) < 1e-5, float(((got - want).abs() / scale).max())
