@@ -673,7 +673,7 @@ __global__ void pack_quad8_kernel(const float* __restrict__ x, uint4* __restrict
 template <class C>
 int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* out, double* stats, int N, int n_per_view, int out_bf16,
                    cudaStream_t st, void* pool_out = nullptr, const float* gamma = nullptr, const float* beta2 = nullptr) {
-    if (pool_out != nullptr && !C::POOL_OK) {
+    if (pool_out != nullptr && beta2 == nullptr && !C::POOL_OK) {
         set_error("conv_tc: this geometry has no fused max-pool epilogue");
         return -5;
     }
