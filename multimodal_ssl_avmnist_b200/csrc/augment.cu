@@ -190,10 +190,11 @@ __global__ void __launch_bounds__(T) aug_apply_kernel(const void* __restrict__ s
                     uint4 r = rng((uint64_t)q, (uint64_t)rec * 4 + 1);
                     // two Box-Muller pairs
                     float u1 = 1.0f - u01(r.x), u2 = u01(r.y), u3 = 1.0f - u01(r.z), u4 = u01(r.w);
-                    float ra = sqrtf(-2.0f * logf(u1)), rb = sqrtf(-2.0f * logf(u3));
+                    // device-sampled noise only has to be N(0, 1): hardware log / sin / cos approximations (2^-21 abs) are enough
+                    float ra = sqrtf(-2.0f * __logf(u1)), rb = sqrtf(-2.0f * __logf(u3));
                     float s1, c1, s2, c2;
-                    sincospif(2.0f * u2, &s1, &c1);
-                    sincospif(2.0f * u4, &s2, &c2);
+                    __sincosf(6.283185307179586f * u2, &s1, &c1);
+                    __sincosf(6.283185307179586f * u4, &s2, &c2);
                     cur[4 * q + 0] += ra * c1 * std;
                     cur[4 * q + 1] += ra * s1 * std;
                     cur[4 * q + 2] += rb * c2 * std;
@@ -202,11 +203,14 @@ __global__ void __launch_bounds__(T) aug_apply_kernel(const void* __restrict__ s
             }
             __syncthreads();
         } else if (kind == OP_GROUP_MASK) {
-            constexpr int GW = S / 4;
-            for (int e = tid; e < NPIX; e += T) {
-                const int y = e / S, x = e - y * S;
-                const int g = (y >> 2) * GW + (x >> 2);
-                if ((sbits[g >> 5] >> (g & 31)) & 1u) cur[e] = 0.f;
+            // 4 x 4 pixel groups: iterate over (group, row-in-group) = one aligned float4 each; only masked groups write
+            constexpr int GW = S / 4, NG = GW * GW;
+            for (int e = tid; e < NG * 4; e += T) {
+                const int g = e >> 2, r = e & 3;
+                if ((sbits[g >> 5] >> (g & 31)) & 1u) {
+                    const int gy = g / GW, gx = g - gy * GW;
+                    reinterpret_cast<float4*>(cur + (gy * 4 + r) * S)[gx] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
             __syncthreads();
         } else if (kind == OP_TIME_WARP) {
@@ -248,10 +252,20 @@ __global__ void __launch_bounds__(T) aug_apply_kernel(const void* __restrict__ s
             const int y = i / WQ, xq = i - y * WQ;
             const float* r = cur + y * S;
             float f[8];
+            const int x0 = 4 * xq - pad8;
+            if ((pad8 & 1) == 0 && x0 >= 0 && x0 + 8 <= S) {          // interior unit, 8-byte aligned: four 64-bit shared loads
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int xc = 4 * xq - pad8 + c;
-                f[c] = (xc >= 0 && xc < S) ? r[xc] : 0.f;
+                for (int c = 0; c < 4; ++c) {
+                    const float2 v2 = *reinterpret_cast<const float2*>(r + x0 + 2 * c);
+                    f[2 * c] = v2.x;
+                    f[2 * c + 1] = v2.y;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int xc = x0 + c;
+                    f[c] = (xc >= 0 && xc < S) ? r[xc] : 0.f;
+                }
             }
             __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
             __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);

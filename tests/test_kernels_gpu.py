@@ -544,3 +544,27 @@ def test_knn_matches_sklearn_and_fp64_brute_force():
     q = torch.tensor([[0.0, 0.0]])
     p4, n4 = ops.knn_predict(xt.to(DEV), yt.to(DEV), q.to(DEV), k=4, n_classes=10, return_neighbours=True)
     assert int(p4[0]) == 1 and n4[0].tolist() == [0, 1, 2, 3]               # 2 votes each for labels 1 and 3 -> 1
+
+
+def test_device_generated_noise_is_standard_normal():
+    """GaussianNoise (utils/get_data.py:21-31) on the throughput path: Philox + Box-Muller inside the augmentation kernel.  Only the
+    distribution is specified (the reference draws torch.randn): mean 0, variance std^2, normal tails, no repeats across views / seeds."""
+    B, V, std = 64, 6, 0.25
+    rec = np.zeros((B, V, A.MAX_OPS, A.OP_WORDS), dtype=np.int32)
+    A.pack_ops([(A.OP_NOISE, (std,))], rec[0, 0])
+    rec[:] = rec[0, 0]
+    src = torch.zeros(B, 112, 112, device=DEV)
+    bits = torch.zeros(B, V, A.GROUP_WORDS, dtype=torch.int32, device=DEV)
+    outs = []
+    for seed in (11, 12):
+        out = torch.empty(V, B, 112, 112, device=DEV)
+        ops.aug_apply_audio(src, torch.from_numpy(rec).to(DEV), bits, out, noise=None, seed=seed)
+        outs.append(out)
+    x = (outs[0] / std).double().flatten()
+    n = x.numel()
+    assert abs(float(x.mean())) < 5 / n ** 0.5 and abs(float(x.var()) - 1.0) < 5 * (2 / n) ** 0.5
+    assert abs(float((x ** 4).mean()) - 3.0) < 0.02 and abs(float((x ** 3).mean())) < 0.01        # kurtosis / skewness of N(0, 1)
+    assert abs(float((x.abs() > 3).double().mean()) - 0.0027) < 3e-4 and float(x.abs().max()) < 6.5
+    assert float((outs[0][0, 0] - outs[0][1, 0]).abs().max()) > 0.1 and float((outs[0] - outs[1]).abs().max()) > 0.1
+    a, b = outs[0][0].flatten(), outs[0][1].flatten()
+    assert abs(float((a * b).mean() / (a.std() * b.std()))) < 0.01                                  # views are uncorrelated
