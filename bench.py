@@ -482,7 +482,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     B = per_gpu_batch(args, world)
     eng = DinoStepEngine(kind=args.kind, mode=args.mode, augment_values=augment_values() if args.kind == "multi_central" else None,
-                         seed=1 + rank, device=dev, fused_pool=not args.no_fused_pool, fused_bnstat=not args.no_fused_bnstat)
+                         seed=1 + rank, device=dev, fused_pool=not args.no_fused_pool, fused_bnstat=args.fused_bnstat)
     g = torch.Generator().manual_seed(1 + rank)
     img_h = torch.rand(B, 28, 28, generator=g).pin_memory()
     aud_h = torch.randint(0, 256, (B, 112, 112), generator=g, dtype=torch.uint8).pin_memory() if args.kind == "multi_central" else None
@@ -698,8 +698,8 @@ def main():
     ap.add_argument("--reference-fp32", action="store_true", help="library bar without fp16 autocast")
     ap.add_argument("--no-fused-pool", action="store_true",
                     help="A/B: the round-1 forward (full-resolution z -> bn_relu_pool8_fwd) instead of the fused max-pool epilogue")
-    ap.add_argument("--no-fused-bnstat", action="store_true",
-                    help="A/B: separate bn_pool8_bwd_reduce_p passes instead of the BN-backward sums in the data-gradient epilogue")
+    ap.add_argument("--fused-bnstat", action="store_true",
+                    help="A/B: BN-backward sums in the data-gradient epilogue instead of separate bn_pool8_bwd_reduce_p passes (measured slower)")
     ap.add_argument("--graph", action="store_true",
                     help="replay the whole step from one CUDA graph (meant for small per-GPU batches, where the ~165 host-side "
                          "launches bound the step; with N > 1 the all-reduces are captured too)")

@@ -143,7 +143,7 @@ class DinoStepEngine:
                  n_global_views=2, n_local_views=4, momentum=0.996, center_momentum=0.9, student_temperature=0.1,
                  teacher_temperature=0.04, learning_rate=1e-4, weight_decay=1e-6, dropout=0.3, fusion_dropout=0.3, alpha=1.0,
                  cosine_loss_alpha=0.0, augment_values=None, seed=0, device=None, process_group=None, data_parallel=None,
-                 precision="bf16", fused_pool=True, fused_bnstat=True):
+                 precision="bf16", fused_pool=True, fused_bnstat=False):
         if not torch.cuda.is_available():
             raise ops._lib.B200Error("DinoStepEngine needs a CUDA device: the hot path has no CPU fallback")
         ops._lib.load()
@@ -236,7 +236,9 @@ class DinoStepEngine:
                                      for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers)]
                                for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers))}
         # data-gradient convolutions that also produce the BatchNorm-backward sums of the layer below in their epilogue (the separate
-        # bn_pool8_bwd_reduce_p pass over p and dp disappears): layer li's data gradient serves layer li - 1
+        # bn_pool8_bwd_reduce_p pass over p and dp disappears): layer li's data gradient serves layer li - 1.  Correct (tests) but OFF by
+        # default: the four epilogue warps of these tensor-pipe-bound kernels have ~1.4x issue slack, the ~5 extra instructions per element
+        # make the epilogue the bottleneck (16->8 @56^2: 0.32 -> 1.10 ms; step 7.66 -> 8.61 ms, profiles/r2k_*)
         self.fused_bnstat = bool(fused_bnstat)
         self.bnstat = {mod: [self.fused_bnstat and li > 0 and bool(self.tc[mod][li]) and bool(self.tc[mod][li - 1]) and
                              ops.conv_tc_dgrad_bnstat_supported(co, ci, hw + 2 * pad - k + 1, hw + 2 * pad - k + 1, k, k - 1 - pad)
