@@ -561,6 +561,8 @@ def run_ours(args):
     # the per-wrapper tally above stays as a cross-check
     launch_detail = {"tally_from_wrappers": int(launches)}
     try:
+        if world > 1 and not use_graph:
+            raise RuntimeError("census skipped at N > 1 (a capture that failed on one rank only would desynchronise the collectives)")
         if not use_graph:
             eng._prefetch = None
             eng.capture_train_step(B)
@@ -571,7 +573,7 @@ def run_ours(args):
         if counts["kernels"] < launches:        # the tally may never exceed what the graph really contains
             launches = counts["kernels"]
     except Exception as exc:
-        launch_detail["source"] = f"per-wrapper tally (graph census failed: {type(exc).__name__}: {exc})"
+        launch_detail["source"] = f"per-wrapper tally ({exc})"
     eng.release_graph()                         # the per-op profile below steps eagerly
     # per-op profile; every rank runs it (the step contains collectives when N > 1).  Consistency gate: with the side streams
     # off the per-op times must add up to about the step time (<= 1.3 x: the overlapped step hides ~15 %); otherwise a stall sat
