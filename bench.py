@@ -459,6 +459,7 @@ def run_module_path(args, B, steps, warmup):
         return {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warmup, "per_gpu_batch": B,
                 "api": "Trainer.fit(MultiModalDINOLightning(CentralMultiModalEncoder), AVMNISTDinoDataModule(device_resident=True)): "
                        "training_step -> loss.backward() -> B200Adam.step(), reference flow run_dino.py:356-373",
+                "fused_graph_step": bool(lit.model.engine is not None and lit.model.engine._graph is not None),
                 "last_loss": float(tr.callback_metrics.get("train_loss", float("nan")))}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)

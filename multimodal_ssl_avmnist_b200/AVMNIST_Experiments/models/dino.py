@@ -364,6 +364,18 @@ class DownstreamClassifier(nn.Module):
 # ------------------------------------------------------------------------------------------------------------
 class _DinoLightningBase(pl.LightningModule):
     LOSS_VARIANT = 0
+    # Raw (un-augmented) device batches of at most this many samples take the fused CUDA-graph step (EngineBinding.fused_train_step):
+    # one graph replay per batch instead of ~165 launches + autograd + optimizer calls.  "auto": only under the built-in trainer shim
+    # (real Lightning may run hooks between backward and optimizer.step that a fused step would bypass); True / False force it.
+    b200_fused_step = "auto"
+    B200_FUSED_MAX_BATCH = 512
+
+    def _use_fused_step(self, batch_size):
+        flag = self.b200_fused_step
+        if flag == "auto":
+            from _compat import HAVE_LIGHTNING
+            flag = (not HAVE_LIGHTNING) and getattr(self, "_trainer", None) is not None
+        return bool(flag) and batch_size <= self.B200_FUSED_MAX_BATCH and self.model._b200.optimizer is not None
 
     def forward(self, batch):
         return self.model(batch)
@@ -469,6 +481,14 @@ class MultiModalDINOLightning(_DinoLightningBase):
         if len(batch) in (2, 3) and batch[0].dim() == 4:          # raw (image, audio[, label]) batch: augment on the device
             av = "keep" if getattr(self, "_aug_set", False) else self._augment_values()
             self._aug_set = True
+            if self._use_fused_step(batch[0].shape[0]):           # small batch: the whole step is one CUDA-graph replay
+                dev = self.model.center.device
+                if av != "keep":
+                    self.model._b200.ensure(dev).set_augmentation(av)
+                loss = self.model._b200.fused_train_step(batch[0].to(dev), batch[1].to(dev))
+                if loss is not None:
+                    self.log("train_loss", loss, on_step=True, on_epoch=True, prog_bar=True)
+                    return loss
             student_out, teacher_out, alignment_loss = self.model.forward_raw(batch[0], batch[1], av)
         else:
             student_out, teacher_out, alignment_loss = self.model(batch)
@@ -488,6 +508,14 @@ class _SideLossLightning(MultiModalDINOLightning):
             image, audio, labels = batch
             av = "keep" if getattr(self, "_aug_set", False) else self._augment_values()
             self._aug_set = True
+            if self._use_fused_step(image.shape[0]):               # small batch: the whole step (side loss included) is one graph replay
+                dev = self.model.center.device
+                if av != "keep":
+                    self.model._b200.ensure(dev).set_augmentation(av)
+                loss = self.model._b200.fused_train_step(image.to(dev), audio.to(dev), labels.to(dev), alpha=float(self.alpha))
+                if loss is not None:
+                    self.log("train_loss", loss, on_step=True, on_epoch=True, prog_bar=True)
+                    return loss
             student_out, teacher_out, _ = self.model.forward_raw(image, audio, av, with_raw=True)
             image_out, audio_out = self.model._extra
         else:

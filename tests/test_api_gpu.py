@@ -267,3 +267,34 @@ def test_standalone_ntxent_is_a_drop_in_for_the_reference_loss():
     want.backward()
     assert abs(float(loss) - float(want)) < 1e-5 * float(want)
     assert float((z.grad - z2.grad.float()).abs().max()) <= 2e-5 * float(z2.grad.abs().max())
+
+
+@pytest.mark.parametrize("mode", ["default", "semi_supervised"])
+def test_fused_graph_step_through_the_trainer_equals_the_step_by_step_path(tmp_path, mode):
+    """Small batches through `Trainer.fit`: the fused path (the whole step = one CUDA-graph replay; loss.backward() and
+    optimizer.step() become no-ops for that batch) must train exactly like training_step -> backward -> B200Adam.step():
+    same seeds, same data order -> bit-identical student, teacher, Adam moments, centre after two epochs; the cosine LR schedule
+    reaches the captured Adam through the device-side learning rate."""
+    from _compat import pl
+    d = str(tmp_path) + "/"
+    gd.write_synthetic_avmnist(d, n_train=96, n_test=16)
+    cls = WRAPPERS[mode]
+    results = []
+    for fused in (False, True):
+        torch.manual_seed(7)
+        dm_cls = gd.AVMNISTDinoDataModuleExtended if mode != "default" else gd.AVMNISTDinoDataModule
+        dm = dm_cls(data_dir=d, batch_size=16, num_workers=0, type="burst_noise", device_resident=True)
+        dm.probe_dataloaders = None
+        lit = cls(**dict(KW, data_dir=d, num_epochs=2))
+        lit.b200_fused_step = fused
+        tr = pl.Trainer(max_epochs=2, logger=None, log_every_n_steps=1, devices=1, accelerator="gpu")
+        tr.fit(lit, datamodule=dm)
+        torch.cuda.synchronize()
+        eng = lit.model.engine
+        assert (eng._graph is not None) == fused
+        assert tr.global_step == 2 * (len(dm.train_dataset) // 16) and eng.step_count == tr.global_step
+        results.append((eng.student.flat.clone(), eng.teacher.flat.clone(), eng.exp_avg.clone(), eng.exp_avg_sq.clone(), lit.model.center.clone(),
+                        float(tr.callback_metrics["train_loss_epoch"])))
+    for a, b in zip(results[0][:5], results[1][:5]):
+        assert torch.equal(a, b), float((a - b).abs().max())
+    assert abs(results[0][5] - results[1][5]) < 1e-6
