@@ -115,6 +115,8 @@ int b200_cosine_consistency_fwd_bwd(const float* emb, int V, int B, int D, float
  * One op record = 8 int32 words: kind, then 7 payload words (ints, or float bit patterns):
  *   1 CROP_RESIZE i,j,h,w   2 AFFINE m0..m5 (fp32 inverse matrix)   3 ERASE i,j,h,w   4 FREQ_MASK start,end
  *   5 TIME_MASK start,end   6 NOISE std   7 GROUP_MASK (bits in group_bits)   8 TIME_WARP rate   0 NOP
+ *   9 BLUR3 k0,k1,k2 (fp32 taps of torchvision GaussianBlur(3))   10 ELASTIC [alpha, sigma] (torchvision ElasticTransform: the
+ *   sampling grid comes from elastic_grid, or is drawn in-kernel) -- the SimCLR image chain, utils/get_data.py:311-339
  * ops: int32 [B, V, B200_AUG_MAX_OPS, 8]; group_bits: uint32 [B, V, 28] (784 bits, 4x4 groups, 1 = zeroed).
  * Output is view-major: out [V, B, S, S] (S = 28 image / 112 audio) so that every view-call of the encoder
  * reads a contiguous batch.
@@ -127,6 +129,11 @@ int b200_cosine_consistency_fwd_bwd(const float* emb, int V, int B, int D, float
  * image: src float [B,28,28] in [0,1] (src_u8 == 0) or uint8 [B,28,28] scaled by 1/255 (src_u8 == 1) */
 int b200_aug_apply_image(const void* src, int src_u8, const int32_t* ops, float* out, void* out_quad8, int pad, int B,
                          int V, void* stream);
+/* the same with the side inputs of the SimCLR image chain: elastic_grid = optional fp32 [B, V, 2, 28, 28] absolute sampling grid
+ * (x, y in [-1, 1] units, identity + displacement: parity mode); NULL -> the displacement field of an ELASTIC op is drawn in-kernel
+ * from Philox(seed, sample*V+view) */
+int b200_aug_apply_image_ex(const void* src, int src_u8, const int32_t* ops, const float* elastic_grid, uint64_t seed,
+                            float* out, void* out_quad8, int pad, int B, int V, void* stream);
 /* audio: src uint8 [B,112,112] (scaled by 1/255, utils/get_data.py:467) or float; noise: optional injected N(0,1)
  * field [B,V,112,112] (parity mode), NULL -> Philox(seed, sample*V+view) in-kernel */
 int b200_aug_apply_audio(const void* src, int src_u8, const int32_t* ops, const uint32_t* group_bits,

@@ -109,6 +109,56 @@ class MultiModalAugmentation:
         return "\n".join(lines)
 
 
+class SimCLRMultiModalAugmentation:
+    """Two augmented views per modality for the SimCLR-style models (reference utils/get_data.py:299-408).  Like the reference, the
+    transforms act on the whole [B,C,H,W] batch at once: ONE parameter set (crop box, angle, elastic field, blur sigma, masks,
+    warp rate) per call and view, Gaussian noise per element.  Parameters are drawn on the host in the reference's RNG order
+    (HostSampler), the pixels are produced by the CUDA augmentation kernels (crop-resize, affine, ElasticTransform, GaussianBlur /
+    crop-resize, time-warp, frequency / time masks, noise).  `augment_values` is accepted and, as in the reference (whose custom
+    list is built but never installed, :366-383), does not change the transforms."""
+
+    def __init__(self, image_size=28, spec_size=112, augment_values=None):
+        if image_size != 28 or spec_size != 112:
+            raise ValueError("the compiled augmentation kernels handle 28x28 images and 112x112 spectrograms")
+        self.image_size, self.spec_size = image_size, spec_size
+        self.augment_values = augment_values
+        self.image_transform, self.spectrogram_transform = A.simclr_chains()
+        self._sampler = A.HostSampler()
+
+    @torch.no_grad()
+    def __call__(self, images, audios):
+        """images [B,1,28,28], audios [B,1,112,112] -> (aug_images1, aug_audios1, aug_images2, aug_audios2), CUDA tensors of those shapes."""
+        from multimodal_ssl_avmnist_b200 import ops
+        if not torch.cuda.is_available():
+            raise RuntimeError("SimCLRMultiModalAugmentation runs its pixels on the GPU: no CUDA device available")
+        dev = images.device if images.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        B, V = images.shape[0], 2
+        img_ops = np.zeros((B, V, A.MAX_OPS, A.OP_WORDS), dtype=np.int32)
+        aud_ops = np.zeros_like(img_ops)
+        grids = np.zeros((B, V, 2, 28, 28), dtype=np.float32)
+        noise = torch.zeros(B, V, 112, 112)
+        for v in range(V):                      # reference order: both image views, then both spectrogram views (:398-404)
+            o, _, _ = self._sampler.sample_view(self.image_transform, 28, 28, batch=B)
+            A.pack_ops(o, img_ops[0, v])
+            img_ops[:, v] = img_ops[0, v]
+            if self._sampler.last_grid is not None:
+                grids[:, v] = self._sampler.last_grid
+        for v in range(V):
+            o, _, nz = self._sampler.sample_view(self.spectrogram_transform, 112, 112, batch=B)
+            A.pack_ops(o, aud_ops[0, v])
+            aud_ops[:, v] = aud_ops[0, v]
+            if nz is not None:
+                noise[:, v] = nz
+        out_i = torch.empty(V, B, 28, 28, device=dev)
+        out_a = torch.empty(V, B, 112, 112, device=dev)
+        bits = torch.zeros(B, V, A.GROUP_WORDS, dtype=torch.int32, device=dev)
+        ops.aug_apply_image(images.reshape(B, 28, 28).float().contiguous().to(dev), torch.from_numpy(img_ops).to(dev), out_i,
+                            elastic_grid=torch.from_numpy(grids).to(dev))
+        ops.aug_apply_audio(audios.reshape(B, 112, 112).float().contiguous().to(dev), torch.from_numpy(aud_ops).to(dev), bits, out_a,
+                            noise=noise.to(dev))
+        return out_i[0].unsqueeze(1), out_a[0].unsqueeze(1), out_i[1].unsqueeze(1), out_a[1].unsqueeze(1)
+
+
 # ---- datasets -------------------------------------------------------------------------------------------------
 class BaseAVMNISTDataset(Dataset):
     """image/<split>_data.npy (np.load-able, N x 784), audio/<split>_data_augmented_<type>.npy (headerless uint8 memmap,

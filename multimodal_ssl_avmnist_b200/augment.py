@@ -28,6 +28,8 @@ OP_TIME_MASK = 5
 OP_NOISE = 6
 OP_GROUP_MASK = 7
 OP_TIME_WARP = 8
+OP_BLUR3 = 9          # 3x3 Gaussian blur, payload = the three normalised 1-D taps (SimCLR image chain, utils/get_data.py:337)
+OP_ELASTIC = 10       # elastic deformation; the sampling grid (identity + displacement) lives in a side array (get_data.py:330)
 
 # ---- chain-spec kinds (b200_aug_spec_op.kind): what to *sample* ------------------------------------------
 SPEC_RRC = 1          # a = scale_lo, scale_hi, log_ratio_lo, log_ratio_hi
@@ -39,6 +41,8 @@ SPEC_TIME_MASK = 6    # a = mask_param
 SPEC_NOISE = 7        # a = std
 SPEC_GROUP_MASK = 8   # a = number of masked groups (int(ratio * 784)), group size
 SPEC_TIME_WARP = 9    # a = min_factor, max_factor
+SPEC_BLUR = 10        # a = sigma_lo, sigma_hi  (kernel size 3)
+SPEC_ELASTIC = 11     # a = alpha, sigma
 
 MAX_OPS = 8
 OP_WORDS = 8          # int32 words per op record: kind + 7 payload words
@@ -92,6 +96,42 @@ def image_chains():
     l = [rrc_spec((0.3, 0.75)), rotate_spec(15.0), affine_spec(0.0, (0.2, 0.2), (0.8, 1.2)),
          erase_spec(0.3, (0.02, 0.15))]
     return g, l
+
+
+def simclr_chains():
+    """The fixed chains of SimCLRMultiModalAugmentation (utils/get_data.py:311-363): (image chain, spectrogram chain)."""
+    img = [rrc_spec((0.5, 1.0), ratio=(0.8, 1.2)), rotate_spec(5.0), affine_spec(0.0, (0.1, 0.1), None),
+           OpSpec(SPEC_ELASTIC, 0.3, 20.0, 3.0), OpSpec(SPEC_BLUR, 0.3, 0.1, 0.5)]
+    aud = [rrc_spec((0.5, 1.0)), OpSpec(SPEC_TIME_WARP, 0.5, 0.9, 1.1), OpSpec(SPEC_FREQ_MASK, 0.5, 10), OpSpec(SPEC_TIME_MASK, 0.5, 10),
+           OpSpec(SPEC_NOISE, 0.3, 0.05)]
+    return img, aud
+
+
+def gaussian_taps(ksize, sigma):
+    """torchvision _get_gaussian_kernel1d (fp32): the normalised taps of a Gaussian blur."""
+    half = (ksize - 1) * 0.5
+    x = torch.linspace(-half, half, steps=ksize, dtype=torch.float32)
+    pdf = torch.exp(-0.5 * (x / sigma).pow(2))
+    return pdf / pdf.sum()
+
+
+def elastic_grid(alpha, sigma, H, W):
+    """ElasticTransform.get_params + the grid of F.elastic_transform (torchvision), drawing the two uniform fields from torch's CPU
+    generator exactly like the transform: displacement = gaussian_blur(2 rand - 1) * alpha / size, grid = identity + displacement.
+    The blur is torchvision's (reflect padding + depth-wise conv2d with the outer-product kernel).  Returns fp32 [2, H, W] (x, y)."""
+    out = []
+    for size, axis in ((W, 1), (H, 0)):
+        d = torch.rand([1, 1, H, W]) * 2 - 1
+        if sigma > 0.0:
+            k = int(8 * sigma + 1)
+            k += 1 - k % 2
+            t = gaussian_taps(k, sigma)
+            kernel = torch.mm(t[:, None], t[None, :])[None, None]
+            d = torch.nn.functional.conv2d(torch.nn.functional.pad(d, [k // 2] * 4, mode="reflect"), kernel)
+        d = d * alpha / size
+        ident = torch.linspace((-size + 1) / size, (size - 1) / size, size)
+        out.append((ident[None, :] if axis == 1 else ident[:, None]) + d[0, 0])
+    return torch.stack(out).numpy()
 
 
 def default_audio_chains():
@@ -231,10 +271,13 @@ class HostSampler:
         end = start + int(value.long())
         return start, end
 
-    def sample_view(self, chain, H, W):
+    def sample_view(self, chain, H, W, batch=None):
         """Returns (ops, group_bits, noise): ops = [(kind, params)], group_bits = np.uint8[(H/4)*(W/4)] or None,
-        noise = torch.float32[H,W] or None."""
+        noise = torch.float32[H,W] or None.  batch = B: the chain is applied to a whole [B,1,H,W] tensor at once like the SimCLR
+        transforms (one parameter set for the batch, but GaussianNoise draws randn_like of the batch: noise is [B,H,W]).
+        self.last_grid: the elastic sampling grid [2,H,W] of this view, or None."""
         ops, bits, noise = [], None, None
+        self.last_grid = None
         for op in chain:
             if op.kind == SPEC_ERASE:
                 if not bool(torch.rand(1) < op.p):
@@ -271,7 +314,7 @@ class HostSampler:
             elif op.kind == SPEC_NOISE:
                 if noise is not None:
                     raise ValueError("at most one gaussian_noise op per chain")
-                noise = torch.randn(1, H, W)[0]
+                noise = torch.randn(1, H, W)[0] if batch is None else torch.randn(batch, 1, H, W)[:, 0]
                 ops.append((OP_NOISE, (op.a[0],)))
             elif op.kind == SPEC_GROUP_MASK:
                 if bits is not None:
@@ -283,6 +326,14 @@ class HostSampler:
                 ops.append((OP_GROUP_MASK, ()))
             elif op.kind == SPEC_TIME_WARP:
                 ops.append((OP_TIME_WARP, (random.uniform(op.a[0], op.a[1]),)))
+            elif op.kind == SPEC_ELASTIC:
+                if self.last_grid is not None:
+                    raise ValueError("at most one elastic op per chain")
+                self.last_grid = elastic_grid(op.a[0], op.a[1], H, W)
+                ops.append((OP_ELASTIC, ()))
+            elif op.kind == SPEC_BLUR:
+                sigma = _u(op.a[0], op.a[1])
+                ops.append((OP_BLUR3, tuple(float(v) for v in gaussian_taps(3, sigma))))
             else:
                 raise ValueError(f"unknown spec kind {op.kind}")
         return ops, bits, noise
@@ -300,7 +351,7 @@ def pack_ops(view_ops, out):
         if kind in (OP_CROP_RESIZE, OP_ERASE, OP_FREQ_MASK, OP_TIME_MASK):
             for t, v in enumerate(p):
                 out[k, 1 + t] = int(v)
-        elif kind in (OP_AFFINE, OP_NOISE):
+        elif kind in (OP_AFFINE, OP_NOISE, OP_BLUR3):
             vals = np.asarray(p, dtype=np.float32)
             out[k, 1:1 + len(vals)] = vals.view(np.int32)
         elif kind == OP_TIME_WARP:            # the rate is a Python double (random.uniform): keep all 64 bits

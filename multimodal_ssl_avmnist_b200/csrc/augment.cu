@@ -15,8 +15,9 @@
 
 namespace b200 {
 
-enum { OP_NOP = 0, OP_CROP_RESIZE, OP_AFFINE, OP_ERASE, OP_FREQ_MASK, OP_TIME_MASK, OP_NOISE, OP_GROUP_MASK, OP_TIME_WARP };
-enum { SPEC_RRC = 1, SPEC_ROTATE, SPEC_AFFINE, SPEC_ERASE, SPEC_FREQ_MASK, SPEC_TIME_MASK, SPEC_NOISE, SPEC_GROUP_MASK, SPEC_TIME_WARP };
+enum { OP_NOP = 0, OP_CROP_RESIZE, OP_AFFINE, OP_ERASE, OP_FREQ_MASK, OP_TIME_MASK, OP_NOISE, OP_GROUP_MASK, OP_TIME_WARP, OP_BLUR3, OP_ELASTIC };
+enum { SPEC_RRC = 1, SPEC_ROTATE, SPEC_AFFINE, SPEC_ERASE, SPEC_FREQ_MASK, SPEC_TIME_MASK, SPEC_NOISE, SPEC_GROUP_MASK, SPEC_TIME_WARP, SPEC_BLUR,
+       SPEC_ELASTIC };
 
 struct AATable {  // per output index: first source index, tap count, up to 3 weights
     int lo;
@@ -68,7 +69,7 @@ template <int S, int T>
 __global__ void __launch_bounds__(T) aug_apply_kernel(const void* __restrict__ src, int src_u8, const int32_t* __restrict__ ops,
                                                       const uint32_t* __restrict__ group_bits, const float* __restrict__ noise,
                                                       uint64_t seed, float* __restrict__ out, uint4* __restrict__ out8, int pad8, int B, int V,
-                                                      const int64_t* __restrict__ step_dev) {
+                                                      const int64_t* __restrict__ step_dev, const float* __restrict__ egrid) {
     constexpr int NPIX = S * S;
     if (step_dev != nullptr) seed = (seed + (uint64_t)__ldg(step_dev)) & 0xFFFFFFFFFFFFull;      // CUDA-graph replay: the step lives on the device
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -236,6 +237,116 @@ __global__ void __launch_bounds__(T) aug_apply_kernel(const void* __restrict__ s
             }
             __syncthreads();
             float* t = cur; cur = alt; alt = t;
+        } else if (kind == OP_BLUR3) {
+            // torchvision GaussianBlur(3): reflect padding, kernel2d = k (outer) k, fp32 FMA accumulation row by row (get_data.py:337)
+            const float k0 = __int_as_float(p[0]), k1 = __int_as_float(p[1]), k2 = __int_as_float(p[2]);
+            const float kk[3] = {k0, k1, k2};
+            for (int e = tid; e < NPIX; e += T) {
+                const int y = e / S, x = e - y * S;
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    int yy = y + i - 1;
+                    yy = yy < 0 ? -yy : (yy >= S ? 2 * S - 2 - yy : yy);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        int xx = x + j - 1;
+                        xx = xx < 0 ? -xx : (xx >= S ? 2 * S - 2 - xx : xx);
+                        acc = __fmaf_rn(cur[yy * S + xx], __fmul_rn(kk[i], kk[j]), acc);
+                    }
+                }
+                alt[e] = acc;
+            }
+            __syncthreads();
+            float* t = cur; cur = alt; alt = t;
+        } else if (kind == OP_ELASTIC) {
+            // torchvision ElasticTransform (get_data.py:330): bilinear grid_sample (zeros padding, align_corners=False) of the image and
+            // of a ones mask at grid = identity + displacement, out = img * mask.  Parity mode: the grid [2,S,S] comes from the host
+            // (egrid); throughput mode: the displacement field is drawn here (uniform field, separable Gaussian blur, reflect padding).
+            const float* gxp = nullptr;
+            const float* gyp = nullptr;
+            if (egrid != nullptr) {
+                gxp = egrid + rec * 2 * NPIX;
+                gyp = gxp + NPIX;
+            }
+            if constexpr (S <= 32) {
+                __shared__ float fld[3 * S * S];                   // dx, dy, scratch
+                if (egrid == nullptr) {
+                    const float alpha = __int_as_float(p[0]), sigma = __int_as_float(p[1]);
+                    int kr = (int)(8.f * sigma + 1.f);
+                    kr = (kr | 1) / 2;                              // radius of the odd kernel size
+                    if (kr > S - 1) kr = S - 1;
+                    Philox rng(seed);
+                    for (int q = tid; q < NPIX / 2; q += T) {       // 2 * NPIX uniforms in [-1, 1)
+                        const uint4 r = rng((uint64_t)q, (uint64_t)rec * 4 + 2);
+                        fld[4 * q + 0] = 2.f * u01(r.x) - 1.f;
+                        fld[4 * q + 1] = 2.f * u01(r.y) - 1.f;
+                        fld[4 * q + 2] = 2.f * u01(r.z) - 1.f;
+                        fld[4 * q + 3] = 2.f * u01(r.w) - 1.f;
+                    }
+                    __syncthreads();
+                    const float inv2s2 = sigma > 0.f ? 0.5f / (sigma * sigma) : 0.f;
+                    float norm = 0.f;
+                    for (int d = -kr; d <= kr; ++d) norm += __expf(-(float)(d * d) * inv2s2);
+                    for (int f = 0; f < 2 && sigma > 0.f; ++f) {    // separable blur of field f: rows into scratch, columns back
+                        float* src_f = fld + f * NPIX;
+                        float* tmp = fld + 2 * NPIX;
+                        for (int e = tid; e < NPIX; e += T) {
+                            const int y = e / S, x = e - y * S;
+                            float a = 0.f;
+                            for (int d = -kr; d <= kr; ++d) {
+                                int xx = x + d;
+                                xx = xx < 0 ? -xx : (xx >= S ? 2 * S - 2 - xx : xx);
+                                a += src_f[y * S + xx] * __expf(-(float)(d * d) * inv2s2);
+                            }
+                            tmp[e] = a / norm;
+                        }
+                        __syncthreads();
+                        for (int e = tid; e < NPIX; e += T) {
+                            const int y = e / S, x = e - y * S;
+                            float a = 0.f;
+                            for (int d = -kr; d <= kr; ++d) {
+                                int yy = y + d;
+                                yy = yy < 0 ? -yy : (yy >= S ? 2 * S - 2 - yy : yy);
+                                a += tmp[yy * S + x] * __expf(-(float)(d * d) * inv2s2);
+                            }
+                            src_f[e] = a / norm * alpha / (float)S;
+                        }
+                        __syncthreads();
+                    }
+                    for (int e = tid; e < NPIX; e += T) {           // + identity grid
+                        const int y = e / S, x = e - y * S;
+                        fld[e] += (2.f * (float)x + 1.f) / (float)S - 1.f;
+                        fld[NPIX + e] += (2.f * (float)y + 1.f) / (float)S - 1.f;
+                    }
+                    __syncthreads();
+                    gxp = fld;
+                    gyp = fld + NPIX;
+                }
+            }
+            if (gxp != nullptr) {
+                for (int e = tid; e < NPIX; e += T) {
+                    const float gx = gxp[e], gy = gyp[e];
+                    const float ix = __fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f * (float)S), 0.5f);
+                    const float iy = __fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f * (float)S), 0.5f);
+                    const float fx = floorf(ix), fy = floorf(iy);
+                    const float w = __fsub_rn(ix, fx), ee = __fsub_rn(1.f, w), n = __fsub_rn(iy, fy), sn = __fsub_rn(1.f, n);
+                    const int x0 = (int)fx, y0 = (int)fy;
+                    float img = 0.f, msk = 0.f;
+                    const float wt[4] = {__fmul_rn(sn, ee), __fmul_rn(sn, w), __fmul_rn(n, ee), __fmul_rn(n, w)};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int xx = x0 + (c & 1), yy = y0 + (c >> 1);
+                        if (xx >= 0 && xx < S && yy >= 0 && yy < S) {
+                            img = __fmaf_rn(cur[yy * S + xx], wt[c], img);
+                            msk = __fadd_rn(msk, wt[c]);
+                        }
+                    }
+                    alt[e] = __fmul_rn(img, msk);
+                }
+                __syncthreads();
+                float* t = cur; cur = alt; alt = t;
+            }
         }
     }
     // ---- write the finished view (view-major layout [V,B,S,S]) ----
@@ -389,6 +500,19 @@ __device__ int sample_chain(const int32_t* spec, int S, Draw& d, int32_t* rec /*
             r[0] = OP_GROUP_MASK;
             *group_count = (int)a[0];
             ++n_out;
+        } else if (kind == SPEC_BLUR) {
+            const float sigma = d.uniform(a[0], a[1]);               // GaussianBlur.get_params; taps of the 3-wide kernel
+            const float e1 = expf(-0.5f / (sigma * sigma)), inv = 1.0f / (1.0f + 2.0f * e1);
+            r[0] = OP_BLUR3;
+            r[1] = __float_as_int(e1 * inv);
+            r[2] = __float_as_int(inv);
+            r[3] = __float_as_int(e1 * inv);
+            ++n_out;
+        } else if (kind == SPEC_ELASTIC) {
+            r[0] = OP_ELASTIC;                                       // the field itself is drawn inside the apply kernel
+            r[1] = __float_as_int(a[0]);
+            r[2] = __float_as_int(a[1]);
+            ++n_out;
         } else if (kind == SPEC_TIME_WARP) {
             const double u = u01d(d.bits(), d.bits());
             const double rate = (double)a[0] + ((double)a[1] - (double)a[0]) * u;   // random.uniform(min, max)
@@ -463,12 +587,17 @@ using namespace b200;
 extern "C" {
 
 int b200_aug_apply_image(const void* src, int src_u8, const int32_t* ops, float* out, void* out_quad8, int pad, int B, int V, void* stream) {
+    return b200_aug_apply_image_ex(src, src_u8, ops, nullptr, 0, out, out_quad8, pad, B, V, stream);
+}
+
+int b200_aug_apply_image_ex(const void* src, int src_u8, const int32_t* ops, const float* elastic_grid, uint64_t seed, float* out, void* out_quad8,
+                            int pad, int B, int V, void* stream) {
     B200_REQUIRE(src && ops && (out || out_quad8) && B > 0 && V > 0 && pad >= 0, B200_E_ARG, "aug_apply_image: bad arguments");
     B200_REQUIRE((((uintptr_t)src | (uintptr_t)out | (uintptr_t)out_quad8) & 15) == 0, B200_E_ARG, "aug_apply_image: pointers must be 16-byte aligned");
     constexpr int S = 28, T = 128;
     const size_t smem = 2 * S * S * sizeof(float) + 2 * S * sizeof(AATable);
-    aug_apply_kernel<S, T><<<B * V, T, smem, as_stream(stream)>>>(src, src_u8, ops, nullptr, nullptr, 0, out, reinterpret_cast<uint4*>(out_quad8), pad, B, V,
-                                                                  nullptr);
+    aug_apply_kernel<S, T><<<B * V, T, smem, as_stream(stream)>>>(src, src_u8, ops, nullptr, nullptr, seed, out, reinterpret_cast<uint4*>(out_quad8), pad, B, V,
+                                                                  nullptr, elastic_grid);
     return launch_status("aug_apply_image");
 }
 
@@ -490,7 +619,7 @@ int b200_aug_apply_audio_dev(const void* src, int src_u8, const int32_t* ops, co
         attr_done = true;
     }
     aug_apply_kernel<S, T><<<B * V, T, smem, as_stream(stream)>>>(src, src_u8, ops, group_bits, noise, seed, out, reinterpret_cast<uint4*>(out_quad8), pad, B, V,
-                                                                  step_dev);
+                                                                  step_dev, nullptr);
     return launch_status("aug_apply_audio");
 }
 

@@ -195,11 +195,12 @@ def _aug_outs(out, out8, pad):
     return ref.shape[0], ref.shape[1], (_ptr(out, F32) if out is not None else None), (_ptr(out8, torch.bfloat16) if out8 is not None else None)
 
 
-def aug_apply_image(src, ops, out, out8=None, pad=0):
-    """out: fp32 [V, B, 28, 28] and / or out8: bf16 quad8 [V, B, 28, ceil((28 + 2 pad) / 4), 8] (first-layer tensor-core input)."""
+def aug_apply_image(src, ops, out, out8=None, pad=0, elastic_grid=None, seed=0):
+    """out: fp32 [V, B, 28, 28] and / or out8: bf16 quad8 [V, B, 28, ceil((28 + 2 pad) / 4), 8] (first-layer tensor-core input).
+    elastic_grid: fp32 [B, V, 2, 28, 28] sampling grids of ELASTIC ops (parity mode); None -> drawn in-kernel from Philox(seed)."""
     V, B, po, p8 = _aug_outs(out, out8, pad)
-    _lib.check(_lib_().b200_aug_apply_image(_ptr(src), 1 if src.dtype == U8 else 0, _ptr(ops, I32), po, p8, pad, B, V, _stream()),
-               "aug_apply_image")
+    _lib.check(_lib_().b200_aug_apply_image_ex(_ptr(src), 1 if src.dtype == U8 else 0, _ptr(ops, I32), _ptr(elastic_grid, F32), seed, po, p8, pad,
+                                               B, V, _stream()), "aug_apply_image")
 
 
 def aug_apply_audio(src, ops, group_bits, out, noise=None, seed=0, out8=None, pad=0, step_dev=None):

@@ -24,6 +24,8 @@ OP_TIME_MASK = 5      # ints  start, end   (columns)
 OP_NOISE = 6          # f32   std
 OP_GROUP_MASK = 7     # bits live in a side array (one bit per 4x4 group, row-major 28x28)
 OP_TIME_WARP = 8      # f32   rate
+OP_BLUR3 = 9          # f32   k0, k1, k2 (normalised 1-D Gaussian taps; SimCLR chain, utils/get_data.py:337)
+OP_ELASTIC = 10       # the sampling grid (identity + displacement, normalised units) lives in a side array [2, H, W] (get_data.py:330)
 
 
 def inverse_affine_matrix(angle, tx, ty, scale):
@@ -182,7 +184,84 @@ def op_time_warp(x, rate):
     return out
 
 
-def apply_chain(src, ops, group_bits=None, noise=None):
+def gaussian_kernel1d(ksize, sigma):
+    """torchvision _get_gaussian_kernel1d in fp32: linspace(-h, h, k), exp(-0.5 (x / sigma)^2), normalised.  Evaluated with torch's own
+    fp32 exp (ATen's vectorised exp is not numpy's expf bit for bit, and the taps feed bit-exact comparisons)."""
+    import torch
+    half = (ksize - 1) * 0.5
+    x = torch.linspace(-half, half, steps=ksize, dtype=torch.float32)
+    pdf = torch.exp(-0.5 * (x / sigma).pow(2))
+    return (pdf / pdf.sum()).numpy().astype(f32)
+
+
+def blur2d_reflect(x, k1d):
+    """torchvision gaussian_blur: reflect padding, depth-wise conv2d with kernel2d = k (outer) k; fp32 row-major FMA accumulation
+    (bit-exact against torch 2.11 CPU for the 25-tap displacement blur; within 1 ulp of oneDNN's 3x3 kernels)."""
+    k = np.asarray(k1d, dtype=f32)
+    n = k.shape[0]
+    k2 = (k[:, None] * k[None, :]).astype(f32)
+    H, W = x.shape
+    xp = np.pad(x.astype(f32), n // 2, mode="reflect")
+    acc = np.zeros((H, W), dtype=f32)
+    for i in range(n):
+        for j in range(n):
+            acc = (xp[i:i + H, j:j + W].astype(np.float64) * np.float64(k2[i, j]) + acc.astype(np.float64)).astype(f32)
+    return acc
+
+
+def op_blur3(x, k0, k1, k2):
+    return blur2d_reflect(x, [k0, k1, k2])
+
+
+def elastic_grid(u_dx, u_dy, alpha, sigma):
+    """torchvision ElasticTransform.get_params + F.elastic_transform's grid from the transform's two uniform draws u = torch.rand(H, W):
+    displacement = blur(2u - 1) * alpha / size (kernel size int(8 sigma + 1) made odd), grid = identity + displacement with the identity
+    from torch.linspace((-s+1)/s, (s-1)/s, s) (ATen's vectorised linspace is used as is: its rounding is not numpy's).
+    Returns [2, H, W] fp32 (x, y), the layout the kernels consume."""
+    import torch
+    H, W = u_dx.shape
+    out = []
+    for u, size, axis in ((u_dx, W, 1), (u_dy, H, 0)):
+        d = (u.astype(f32) * f32(2) - f32(1)).astype(f32)
+        if sigma > 0.0:
+            ks = int(8 * sigma + 1)
+            ks += 1 - ks % 2
+            d = blur2d_reflect(d, gaussian_kernel1d(ks, sigma))
+        d = (d * f32(alpha) / f32(size)).astype(f32)
+        ident = torch.linspace((-size + 1) / size, (size - 1) / size, size).numpy().astype(f32)
+        out.append((ident[None, :] + d if axis == 1 else ident[:, None] + d).astype(f32))
+    return np.stack(out)
+
+
+def op_elastic(x, grid):
+    """torchvision F.elastic_transform(img, displacement, BILINEAR, fill=0) given grid = identity + displacement:
+    grid_sample(bilinear, zeros, align_corners=False) of the image AND of a ones mask; out = img * mask."""
+    H, W = x.shape
+    gx, gy = grid[0].astype(f32), grid[1].astype(f32)
+    # ATen GridSamplerKernel.cpp (vectorised CPU path), align_corners=False: unnormalize(g) = (g + 1) * (size / 2) - 0.5; corner
+    # weights w = x - floor(x), e = 1 - w, n = y - floor(y), s = 1 - n; nw = s*e, ne = s*w, sw = n*e, se = n*w; sum in that order
+    ix = (((gx + f32(1)).astype(f32) * f32(W / 2)).astype(f32) - f32(0.5)).astype(f32)
+    iy = (((gy + f32(1)).astype(f32) * f32(H / 2)).astype(f32) - f32(0.5)).astype(f32)
+    x0 = np.floor(ix)
+    y0 = np.floor(iy)
+    w_ = (ix - x0).astype(f32)
+    e_ = (f32(1) - w_).astype(f32)
+    n_ = (iy - y0).astype(f32)
+    s_ = (f32(1) - n_).astype(f32)
+    xs = np.concatenate([x.astype(f32).reshape(-1), np.zeros(1, dtype=f32)])
+    img = np.zeros((H, W), dtype=f32)
+    mask = np.zeros((H, W), dtype=f32)
+    for dy, dx, wgt in ((0, 0, (s_ * e_).astype(f32)), (0, 1, (s_ * w_).astype(f32)), (1, 0, (n_ * e_).astype(f32)), (1, 1, (n_ * w_).astype(f32))):
+        xi = (x0 + dx).astype(np.int64)
+        yi = (y0 + dy).astype(np.int64)
+        ok = (xi >= 0) & (xi < W) & (yi >= 0) & (yi < H)
+        idx = np.where(ok, yi * W + xi, H * W)
+        img = (xs[idx].astype(np.float64) * wgt.astype(np.float64) + img.astype(np.float64)).astype(f32)          # fmadd, like ATen's Vec path
+        mask = (ok.astype(np.float64) * wgt.astype(np.float64) + mask.astype(np.float64)).astype(f32)
+    return (img * mask).astype(f32)
+
+
+def apply_chain(src, ops, group_bits=None, noise=None, grid=None):
     """Run one view's op list over a [H,W] fp32 array.  `ops` = list of (kind, params-tuple)."""
     x = np.asarray(src, dtype=f32)
     for kind, p in ops:
@@ -204,6 +283,10 @@ def apply_chain(src, ops, group_bits=None, noise=None):
             x = op_group_mask(x, group_bits)
         elif kind == OP_TIME_WARP:
             x = op_time_warp(x, p[0])
+        elif kind == OP_BLUR3:
+            x = op_blur3(x, p[0], p[1], p[2])
+        elif kind == OP_ELASTIC:
+            x = op_elastic(x, grid)
         else:
             raise ValueError(f"unknown op kind {kind}")
     return x

@@ -277,7 +277,31 @@ def api_surface():
     return out
 
 
+def simclr_fixtures(n_seeds=8, B=3):
+    """SimCLRMultiModalAugmentation of the reference (utils/get_data.py:299-408) on seeded batches -> tests/golden/simclr_aug.npz.
+    The transforms are applied to the whole [B,1,H,W] batch at once: one parameter set per call, GaussianNoise per element."""
+    arrays = {}
+    aug = gd.SimCLRMultiModalAugmentation()
+    for s in range(n_seeds):
+        g = torch.Generator().manual_seed(2000 + s)
+        img = torch.rand(B, 1, 28, 28, generator=g)
+        aud = torch.rand(B, 1, 112, 112, generator=g)
+        torch.manual_seed(s)
+        random.seed(s)
+        i1, a1, i2, a2 = aug(img, aud)
+        arrays[f"s{s}_i1"], arrays[f"s{s}_i2"] = i1.numpy(), i2.numpy()
+        for nm, a in (("a1", a1), ("a2", a2)):
+            a = a.numpy()
+            arrays[f"s{s}_{nm}_dec"] = a[:, :, ::4, 1::4].copy()
+            arrays[f"s{s}_{nm}_rows"] = a.astype(np.float64).sum(-1)
+    np.savez_compressed(os.path.join(HERE, "simclr_aug.npz"), **arrays)
+    return sorted(arrays)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "simclr":
+        print("wrote simclr_aug.npz:", len(simclr_fixtures()), "arrays")
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "api":
         with open(os.path.join(HERE, "api_surface.json"), "w") as f:
             json.dump(api_surface(), f, indent=1)

@@ -568,3 +568,82 @@ def test_device_generated_noise_is_standard_normal():
     assert float((outs[0][0, 0] - outs[0][1, 0]).abs().max()) > 0.1 and float((outs[0] - outs[1]).abs().max()) > 0.1
     a, b = outs[0][0].flatten(), outs[0][1].flatten()
     assert abs(float((a * b).mean() / (a.std() * b.std()))) < 0.01                                  # views are uncorrelated
+
+
+def test_simclr_augmentation_kernels_vs_oracle_and_reference(golden):
+    """the SimCLR chains (utils/get_data.py:299-408) on the CUDA augmentation kernels.  (1) host-sampled records incl.
+    ElasticTransform grids and GaussianBlur taps -> kernel == numpy oracle (same arithmetic: <= 1e-6, image ops mostly bit-equal);
+    (2) the API mirror's SimCLRMultiModalAugmentation, seeded like the reference, against the imported reference's outputs
+    (tests/golden/simclr_aug.npz) at 2e-6; (3) the device-sampled variant (Philox elastic field + blur sigma) is finite, differs per
+    view and applies each op at its configured rate."""
+    import sys
+    MIRROR = os.path.join(os.path.dirname(CFG))
+    sys.path.insert(0, MIRROR)
+    import utils.get_data as gd
+    img_chain, aud_chain = A.simclr_chains()
+    # (1) kernel vs oracle on host-sampled records, B = 5, 2 views
+    B, V = 5, 2
+    g = torch.Generator().manual_seed(31)
+    img = torch.rand(B, 28, 28, generator=g)
+    n_el = n_bl = 0
+    for seed in range(12):
+        torch.manual_seed(seed)
+        random.seed(seed)
+        hs = A.HostSampler()
+        rec = np.zeros((B, V, A.MAX_OPS, A.OP_WORDS), dtype=np.int32)
+        grids = np.zeros((B, V, 2, 28, 28), dtype=np.float32)
+        want = np.zeros((V, B, 28, 28), dtype=np.float32)
+        for v in range(V):
+            o, _, _ = hs.sample_view(img_chain, 28, 28, batch=B)
+            A.pack_ops(o, rec[0, v])
+            rec[:, v] = rec[0, v]
+            if hs.last_grid is not None:
+                grids[:, v] = hs.last_grid
+            n_el += any(k == A.OP_ELASTIC for k, _ in o)
+            n_bl += any(k == A.OP_BLUR3 for k, _ in o)
+            for b in range(B):
+                want[v, b] = AR.apply_chain(img[b].numpy(), o, None, None, grid=hs.last_grid)
+        out = torch.full((V, B, 28, 28), float("nan"), device=DEV)
+        ops.aug_apply_image(img.to(DEV), torch.from_numpy(rec).to(DEV), out, elastic_grid=torch.from_numpy(grids).to(DEV))
+        got = out.cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)
+        assert (got != want).mean() < 0.05
+    assert n_el >= 3 and n_bl >= 3
+    # (2) the API mirror against the imported reference
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "simclr_aug.npz"))
+    aug = gd.SimCLRMultiModalAugmentation()
+    for s in range(8):
+        gg = torch.Generator().manual_seed(2000 + s)
+        im = torch.rand(3, 1, 28, 28, generator=gg)
+        au = torch.rand(3, 1, 112, 112, generator=gg)
+        torch.manual_seed(s)
+        random.seed(s)
+        i1, a1, i2, a2 = aug(im, au)
+        assert i1.shape == (3, 1, 28, 28) and a2.shape == (3, 1, 112, 112) and i1.is_cuda
+        np.testing.assert_allclose(i1.cpu().numpy(), fx[f"s{s}_i1"], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(i2.cpu().numpy(), fx[f"s{s}_i2"], rtol=0, atol=2e-6)
+        for nm, a in (("a1", a1), ("a2", a2)):
+            a = a.cpu().numpy()
+            np.testing.assert_allclose(a[:, :, ::4, 1::4], fx[f"s{s}_{nm}_dec"], rtol=0, atol=2e-6)
+            np.testing.assert_allclose(a.astype(np.float64).sum(-1), fx[f"s{s}_{nm}_rows"], rtol=0, atol=2e-3)
+    # (3) device-sampled throughput variant
+    B = 512
+    spec = torch.from_numpy(np.stack([A.pack_spec(c) for c in (img_chain, img_chain, aud_chain, aud_chain)])).to(DEV)
+    io = torch.zeros(B, 2, A.MAX_OPS, A.OP_WORDS, dtype=torch.int32, device=DEV)
+    ao = torch.zeros_like(io)
+    gb = torch.zeros(B, 2, A.GROUP_WORDS, dtype=torch.int32, device=DEV)
+    ops.aug_sample(spec, B, 2, 0, 77, 3, io, ao, gb)
+    src = torch.rand(B, 28, 28, generator=g).to(DEV)
+    out = torch.full((2, B, 28, 28), float("nan"), device=DEV)
+    ops.aug_apply_image(src, io, out, seed=77)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all() and float(out.min()) >= -1e-6 and float(out.max()) <= 1.0 + 1e-6
+    kinds = io.cpu().numpy()[:, :, :, 0]
+    for k, p in ((A.OP_ELASTIC, 0.3), (A.OP_BLUR3, 0.3)):
+        rate = (kinds == k).any(-1).mean()
+        assert abs(rate - p) < 0.05, (k, rate)
+    taps = io.cpu().numpy()[kinds == A.OP_BLUR3][:, 1:4].copy().view(np.float32)
+    assert np.allclose(taps.sum(-1), 1.0, atol=1e-6) and (taps[:, 1] > taps[:, 0]).all() and np.allclose(taps[:, 0], taps[:, 2])
+    el = torch.from_numpy((kinds == A.OP_ELASTIC).any(-1)).to(DEV)          # [B, 2]
+    moved = (out - torch.stack([src, src])).abs().amax(dim=(2, 3)).t()      # every view is at least cropped / rotated
+    assert float(moved.min()) > 1e-3 and float((out[0] - out[1]).abs().max()) > 1e-3 and bool(el.any())

@@ -245,3 +245,43 @@ def test_unimodal_step_loss_and_gradients_against_reference(key, alpha, golden):
         assert ok, (k, why)
         checked += 1
     assert checked >= 10
+
+
+def test_simclr_augmentation_against_reference_fixture():
+    """SimCLRMultiModalAugmentation (utils/get_data.py:299-408: RandomResizedCrop, rotation, affine, ElasticTransform,
+    GaussianBlur on the image; crop, time-warp, masks, Gaussian noise on the spectrogram; one parameter set per BATCH).  The host
+    sampler replays the reference's RNG order, the numpy oracle applies the records: against the imported reference's outputs
+    (tests/golden/simclr_aug.npz) 2e-6 abs (ATen's 3x3 blur / grid-sampler accumulation order is not reproduced bit for bit)."""
+    import random
+    import numpy as np
+    from multimodal_ssl_avmnist_b200 import augment as A
+    from oracle import augment_ref as AR
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "simclr_aug.npz"))
+    img_chain, aud_chain = A.simclr_chains()
+    kinds = set()
+    B = 3
+    for s in range(8):
+        g = torch.Generator().manual_seed(2000 + s)
+        img = torch.rand(B, 1, 28, 28, generator=g)
+        aud = torch.rand(B, 1, 112, 112, generator=g)
+        torch.manual_seed(s)
+        random.seed(s)
+        hs = A.HostSampler()
+        # reference call order: image view 1, image view 2, spectrogram view 1, spectrogram view 2
+        recs = []
+        for chain, size in ((img_chain, 28), (img_chain, 28), (aud_chain, 112), (aud_chain, 112)):
+            ops_, bits, noise = hs.sample_view(chain, size, size, batch=B)
+            recs.append((ops_, noise, hs.last_grid))
+            kinds |= {k for k, _ in ops_}
+        for v, name in ((0, "i1"), (1, "i2")):
+            ops_, _, grid = recs[v]
+            for b in range(B):
+                got = AR.apply_chain(img[b, 0].numpy(), ops_, None, None, grid=grid)
+                np.testing.assert_allclose(got, fx[f"s{s}_{name}"][b, 0], rtol=0, atol=2e-6)
+        for v, name in ((2, "a1"), (3, "a2")):
+            ops_, noise, _ = recs[v]
+            for b in range(B):
+                got = AR.apply_chain(aud[b, 0].numpy(), ops_, None, None if noise is None else noise[b].numpy())
+                np.testing.assert_allclose(got[::4, 1::4], fx[f"s{s}_{name}_dec"][b, 0], rtol=0, atol=2e-6)
+                np.testing.assert_allclose(got.astype(np.float64).sum(-1), fx[f"s{s}_{name}_rows"][b, 0], rtol=0, atol=2e-3)
+    assert {A.OP_ELASTIC, A.OP_BLUR3, A.OP_NOISE, A.OP_TIME_WARP} <= kinds          # the seeds exercise every new op

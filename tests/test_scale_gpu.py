@@ -179,3 +179,45 @@ def test_device_sampled_augmentation_chain_at_bench_batch():
             n_diff += int((np.abs(got_a[v, b] - want) > 0).sum())
             n_tot += want.size
     assert n_diff / n_tot < 0.02
+
+
+@pytest.mark.parametrize("mode", ["mse", "infonce", "semi_supervised"])
+def test_mode_steps_on_the_product_path_at_benchmark_batch(mode):
+    """BASELINE configs 3-5 (mse / infonce / semi_supervised: DINO + side loss on a 7th, un-augmented view-call) at B = 256 on the
+    product path (bf16 tensor-core kernels, tf32 linears; InfoNCE through the tcgen05 3xTF32 similarity GEMM) against the fp32 CPU
+    oracle: total loss 2e-3, side loss 5e-3, student projections 2e-2 of scale, mode-head outputs 3e-2, gradient direction > 0.97,
+    BatchNorm running statistics after SEVEN sequential updates 1e-2."""
+    from oracle.fixtures import synth_raw
+    B, V = 256, 6
+    st = R.CentralDinoState(seed=23, mode=mode)
+    eng = DinoStepEngine(kind="multi_central", mode=mode, device=DEV, precision="bf16")
+    eng.load_named(student=st.student, teacher=st.teacher, student_head=st.student_head, teacher_head=st.teacher_head,
+                   aux_image=st.aux.get("image"), aux_audio=st.aux.get("audio"))
+    img, aud = views_to_vb(*synth_views(B, seed=500))
+    masks = make_masks(seed=501, V=V, Vg=2, B=B, E=256, hidden=512)
+    image, audio, labels = synth_raw(B, seed=502)
+    want = R.central_dino_step(st, img, aud, masks, raw=(image, audio), labels=labels)
+    loss = eng.forward_backward(img[:, :, 0].to(DEV).contiguous(), aud[:, :, 0].to(DEV).contiguous(),
+                                masks={k: v.to(torch.uint8).to(DEV) for k, v in masks.items()},
+                                raw=(image[:, 0].to(DEV).contiguous(), audio[:, 0].to(DEV).contiguous()), labels=labels.to(DEV))
+    torch.cuda.synchronize()
+    w = eng._ws[B]
+    assert abs(float(loss[3]) - float(want["loss"])) < 2e-3 * abs(float(want["loss"])), (float(loss[3]), float(want["loss"]))
+    assert abs(float(loss[1]) - float(want["aux"])) < 5e-3 * max(abs(float(want["aux"])), 0.1), (float(loss[1]), float(want["aux"]))
+    assert _rel(w["s.proj"].view(V, B, -1), want["student_out"]) < 2e-2
+    fm, fw = [], []
+    groups = [("enc.", want["grads"]["student"]), ("head.", want["grads"]["student_head"]), ("aux_image.", want["grads"]["image"]),
+              ("aux_audio.", want["grads"]["audio"])]
+    for prefix, gd in groups:
+        for k, g in gd.items():
+            if g.dim() >= 2:
+                fm.append(eng.G[prefix + k].detach().cpu().double().flatten())
+                fw.append(g.double().flatten())
+    fm, fw = torch.cat(fm), torch.cat(fw)
+    cos = float((fm @ fw) / (fm.norm() * fw.norm()))
+    print(mode, "B=256 bf16: loss", float(loss[3]), float(want["loss"]), "aux", float(loss[1]), float(want["aux"]), "cos", cos)
+    assert cos > 0.97, cos
+    for k in ("image_encoder.0.bn1", "image_encoder.0.bn2", "audio_encoder.0.bn1", "audio_encoder.0.bn4"):
+        assert _rel(eng.bn_s["enc." + k].running_mean, st.student_buf[k + ".running_mean"]) < 1e-2, k
+        assert _rel(eng.bn_s["enc." + k].running_var, st.student_buf[k + ".running_var"]) < 1e-2, k
+        assert int(eng.bn_s["enc." + k].num_batches_tracked) == int(st.student_buf[k + ".num_batches_tracked"]) == 7
