@@ -298,3 +298,38 @@ def test_fused_graph_step_through_the_trainer_equals_the_step_by_step_path(tmp_p
     for a, b in zip(results[0][:5], results[1][:5]):
         assert torch.equal(a, b), float((a - b).abs().max())
     assert abs(results[0][5] - results[1][5]) < 1e-6
+
+
+def test_adam_state_belongs_to_the_optimizer_object():
+    """run_dino.py builds a fresh optimizer per fit / per seed on the same model (run_dino.py:94-104): a new B200Adam must start from
+    zero moments and step 0 like a new torch.optim.Adam, and state_dict() / load_state_dict() must carry the arena moments."""
+    torch.manual_seed(0)
+    lit = md.MultiModalDINOLightning(**KW).to(DEV)
+    B = 8
+
+    def steps(opt, n, seed0):
+        for it in range(n):
+            opt.zero_grad(set_to_none=True)
+            lit.training_step(_batch("default", B, seed0 + it), it).backward()
+            opt.step()
+
+    opt1 = lit.configure_optimizers()["optimizer"]
+    steps(opt1, 2, 40)
+    eng = lit.model.engine
+    assert eng.step_count == 2 and float(eng.exp_avg.abs().max()) > 0
+    sd = opt1.state_dict()
+    assert sd["b200_arena_state"]["step"] == 2 and torch.equal(sd["b200_arena_state"]["exp_avg"], eng.exp_avg.cpu())
+    m_after_2 = eng.exp_avg.clone()
+    # a second fit: fresh optimizer -> fresh Adam (bias correction restarts at step 1, moments from zero)
+    opt2 = lit.configure_optimizers()["optimizer"]
+    steps(opt2, 1, 50)
+    assert eng.step_count == 1
+    n = eng.n_trainable_prefix          # first step from zero moments: exp_avg = (1 - beta1) * (grad + weight_decay * param), wd = 1e-6
+    assert torch.allclose(eng.exp_avg[:n], 0.1 * eng.grad[:n], rtol=1e-2, atol=1e-7)
+    # resume: a new optimizer that loads the checkpointed state continues from it
+    opt3 = lit.configure_optimizers()["optimizer"]
+    opt3.load_state_dict(sd)
+    assert sd["b200_arena_state"]["step"] == 2                      # the caller's dict is not consumed
+    steps(opt3, 1, 60)
+    assert eng.step_count == 3
+    assert not torch.equal(eng.exp_avg, m_after_2) and float((eng.exp_avg - 0.9 * m_after_2).abs().max()) < float(m_after_2.abs().max())
