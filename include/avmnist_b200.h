@@ -364,6 +364,26 @@ int b200_knn_topk_vote(const float* scores, int64_t lds, const int64_t* labels, 
                        int64_t* pred, int32_t* neighbours, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Feature mixing of the "simple" multimodal encoder family, between the per-modality encoders and the fusion MLP:
+ *   GatedMultiModalEncoder.forward (models/dino.py:249-263): features * sigmoid(gate), gate a learnable scalar --
+ *     b200_gate_apply: y[M,N] = sigmoid(*gate) * x[M,N] (forward on the features AND backward on their gradient);
+ *     b200_gate_grad : dgate (+)= sigmoid'(gate) * sum(dy . x) over the [M,N] block, fixed summation order;
+ *                      work: b200_gate_grad_work_floats() floats, ZERO before the first call (left zero by every call).
+ *   CrossModalAttention.forward (models/dino.py:385-405): attention over the BATCH of one view-call,
+ *     softmax((x1 Wq)(x2 Wk)^T * dim^-0.5) (x2 Wv) + x1.  The products are b200_linear_* calls; the rest:
+ *     b200_softmax_rows     : s[M, ld >= N] <- softmax(scale * s) per row, in place;
+ *     b200_softmax_rows_bwd : dp <- scale * p * (dp - sum_n dp p) per row, in place on dp;
+ *     b200_add2d            : dst[M,N] += src[M,N] with row strides (residual connection, gradient sums).
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200_gate_apply(const float* x, int64_t ldx, float* y, int64_t ldy, const float* gate, int M, int N, void* stream);
+int64_t b200_gate_grad_work_floats(void);
+int b200_gate_grad(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* gate, float* dgate, float* work, int M, int N,
+                   int accumulate, void* stream);
+int b200_softmax_rows(float* s, int64_t ld, int M, int N, float scale, void* stream);
+int b200_softmax_rows_bwd(float* dp, int64_t lddp, const float* p, int64_t ldp, int M, int N, float scale, void* stream);
+int b200_add2d(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int M, int N, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Data-parallel exchange -- what Lightning's strategy="ddp" (run_dino.py:359) does for the reference: ONE
  * NCCL communicator per process (one process per GPU).  Rank 0 calls b200_dp_unique_id and ships the 128 bytes to the other
  * ranks by any means (the Python host uses the torch.distributed store); every rank then calls b200_dp_init with its GPU

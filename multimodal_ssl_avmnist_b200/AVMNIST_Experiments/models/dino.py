@@ -6,9 +6,10 @@ projection heads, the centred + sharpened cross-entropy, the MSE / InfoNCE / cro
 Adam -- runs in hand-written sm_100a kernels behind libavmnist_b200.so (multimodal_ssl_avmnist_b200.engine / .binding).
 There is no PyTorch fallback: on a CPU tensor, or without the library, the step raises.
 
-Compiled encoders: CentralMultiModalEncoder ("multi_central") and ImageEncoder ("image_simple").  The other encoder
-families of the reference (LSTM, ViT, MobileViT, ResNet, gated, cross-attention, spectrogram-only) are outside the
-hot-path scope; their names exist so that driver scripts import, and constructing one raises NotImplementedError.
+Compiled encoders: CentralMultiModalEncoder ("multi_central"), the conv encoders SimpleMultiModalEncoder ("multi_simple"),
+GatedMultiModalEncoder ("multi_simple_gated") and CrossAttentionMultiModalEncoder ("multi_cross_attention"), and
+ImageEncoder ("image_simple").  The other encoder families of the reference (LSTM, ViT, MobileViT, ResNet, spectrogram-only)
+are outside the hot-path scope; their names exist so that driver scripts import, and constructing one raises NotImplementedError.
 """
 import os
 import sys
@@ -55,7 +56,7 @@ class BaseMultiModalEncoder(nn.Module):
 
 class SimpleMultiModalEncoder(BaseMultiModalEncoder):
     """Concatenation fusion: image_encoder || audio_encoder -> Linear(2E,E) -> ReLU -> Dropout -> Linear(E,O)."""
-    B200_KIND = None        # "multi_simple" is a listed next step (SURVEY 8f-4); only its inference forward is available
+    B200_KIND = "multi_simple"
 
     def __init__(self, output_dim=256, encoder_output_dim=512, fusion_dropout=0.3):
         super().__init__(output_dim, encoder_output_dim, fusion_dropout)
@@ -70,10 +71,68 @@ class SimpleMultiModalEncoder(BaseMultiModalEncoder):
     def encode_audio(self, spectrograms):
         return MF.sequential_cnn_forward(self.audio_encoder, spectrograms)
 
+    def mix(self, image_features, audio_features):
+        """What happens between the encoders and the fusion MLP: plain concatenation here (models/dino.py:232-233)."""
+        return torch.cat([image_features, audio_features], dim=1)
+
     def forward(self, images, spectrograms):
         """Inference-form forward (feature extraction); the training step goes through MultiModalDINO."""
-        feats = torch.cat([self.encode_image(images), self.encode_audio(spectrograms)], dim=1)
-        return MF.fusion_forward(self.fusion, feats)
+        return MF.fusion_forward(self.fusion, self.mix(self.encode_image(images), self.encode_audio(spectrograms)))
+
+
+class GatedMultiModalEncoder(SimpleMultiModalEncoder):
+    """Simple encoders + one learnable sigmoid gate per modality (reference models/dino.py:237-263)."""
+    B200_KIND = "multi_simple_gated"
+
+    def __init__(self, output_dim=256, encoder_output_dim=512):
+        super().__init__(output_dim, encoder_output_dim)
+        self.gate_image = nn.Parameter(torch.tensor(0.5))
+        self.gate_audio = nn.Parameter(torch.tensor(0.5))
+
+    def mix(self, image_features, audio_features):
+        out = torch.empty(image_features.shape[0], 2 * self.encoder_output_dim, device=image_features.device)
+        E = self.encoder_output_dim
+        MF.ops.gate_apply(image_features.contiguous(), self.gate_image.detach(), out[:, :E])
+        MF.ops.gate_apply(audio_features.contiguous(), self.gate_audio.detach(), out[:, E:])
+        return out
+
+
+class CrossModalAttention(nn.Module):
+    """x1 + softmax((x1 Wq)(x2 Wk)^T dim^-0.5) (x2 Wv): attention over the batch of one call (reference models/dino.py:385-405)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+        self.q_proj = nn.Linear(dim, dim)
+        self.kv_proj = nn.Linear(dim, 2 * dim)
+        self.scale = dim ** -0.5
+
+    @torch.no_grad()
+    def forward(self, x1, x2):
+        q = MF._linear(x1, self.q_proj)
+        kv = MF._linear(x2, self.kv_proj)
+        k, v = kv[:, :self.dim].contiguous(), kv[:, self.dim:].contiguous()
+        attn = torch.empty(x1.shape[0], x2.shape[0], device=x1.device)
+        MF.ops.linear_fwd(q, k, None, attn)
+        MF.ops.softmax_rows(attn, self.scale)
+        out = torch.empty_like(q)
+        MF.ops.linear_bwd_data(attn, v, out)
+        MF.ops.add2d(out, x1.contiguous())
+        return out
+
+
+class CrossAttentionMultiModalEncoder(SimpleMultiModalEncoder):
+    """Simple encoders + bidirectional batch-wide cross attention before the fusion MLP (reference models/dino.py:407-452)."""
+    B200_KIND = "multi_cross_attention"
+
+    def __init__(self, output_dim=256, encoder_output_dim=512, fusion_dropout=0.3):
+        super().__init__(output_dim, encoder_output_dim, fusion_dropout)
+        self.image_to_audio_attention = CrossModalAttention(dim=encoder_output_dim)
+        self.audio_to_image_attention = CrossModalAttention(dim=encoder_output_dim)
+
+    def mix(self, image_features, audio_features):
+        return torch.cat([self.image_to_audio_attention(image_features, audio_features),
+                          self.audio_to_image_attention(audio_features, image_features)], dim=1)
 
 
 class _HeadedCNN(nn.Sequential):
@@ -128,12 +187,12 @@ class ImageEncoder(BaseUniModalEncoder):
 def _out_of_scope(name):
     def __init__(self, *a, **k):
         raise NotImplementedError(f"{name} is outside the B200 hot-path scope (see DESIGN.md section 7); "
-                                  "compiled encoders: CentralMultiModalEncoder, ImageEncoder")
+                                  "compiled encoders: Central / Simple / Gated / CrossAttention MultiModalEncoder, ImageEncoder")
     return type(name, (nn.Module,), {"__init__": __init__, "B200_KIND": None})
 
 
 for _n in ("LSTMImageEncoder", "LSTMMultiModalEncoder", "ViTMultiModalEncoder", "DualViTMultiModalEncoder", "MobileViTMultiModalEncoder",
-           "ResNetMultiModalEncoder", "GatedMultiModalEncoder", "CrossAttentionMultiModalEncoder", "SpectrogramEncoder",
+           "ResNetMultiModalEncoder", "SpectrogramEncoder",
            "SpectrogramEncoderCentral", "SpectrogramEncoderLSTM", "SpectrogramEncoderResNet", "SpectrogramEncoderViT",
            "SpectrogramEncoderMobileViT", "UniModalDINOV2"):
     globals()[_n] = _out_of_scope(_n)
@@ -177,7 +236,7 @@ class _DinoBase(nn.Module):
         kind = getattr(encoder_class, "B200_KIND", None)
         if kind is None:
             raise NotImplementedError(f"{encoder_class.__name__} has no compiled B200 training step "
-                                      "(compiled: CentralMultiModalEncoder, ImageEncoder)")
+                                      "(compiled: Central / Simple / Gated / CrossAttention MultiModalEncoder, ImageEncoder)")
         self._b200 = B.EngineBinding(self, kind, self.MODE)
         self.student_temperature, self.teacher_temperature = 0.1, 0.04
         self.n_global_views, self.n_local_views = 2, 4

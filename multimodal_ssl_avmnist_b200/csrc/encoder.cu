@@ -686,7 +686,11 @@ static int stream_grid(long warps_needed) {
     X(32, 64, 14, 14, 5, 2, 14, 7, 8, 8)      /* audio conv4                    */     \
     X(1, 32, 28, 28, 3, 1, 7, 4, 8, 1)        /* image_simple conv1             */     \
     X(32, 64, 14, 14, 3, 1, 14, 7, 8, 16)     /* image_simple conv2             */     \
-    X(64, 128, 7, 7, 3, 1, 7, 7, 8, 16)       /* image_simple conv3             */
+    X(64, 128, 7, 7, 3, 1, 7, 7, 8, 16)       /* image_simple conv3             */     \
+    X(1, 32, 112, 112, 3, 1, 4, 4, 8, 1)      /* multi_simple audio conv1 (models/dino.py:43-72) */ \
+    X(32, 64, 56, 56, 3, 1, 8, 4, 8, 8)       /* multi_simple audio conv2       */     \
+    X(64, 128, 28, 28, 3, 1, 7, 4, 8, 8)      /* multi_simple audio conv3       */     \
+    X(128, 256, 14, 14, 3, 1, 14, 7, 8, 8)    /* multi_simple audio conv4       */
 
 // data-gradient instances: (CIN' = Cout, COUT' = Cin, H' = HO, W' = WO, K, PAD' = K-1-pad)
 #define DGRAD_SHAPES(X)                                                                \
@@ -696,7 +700,10 @@ static int stream_grid(long warps_needed) {
     X(16, 32, 28, 28, 5, 2, 14, 4, 8, 16)                                              \
     X(32, 64, 14, 14, 5, 2, 14, 7, 8, 16)                                              \
     X(32, 64, 14, 14, 3, 1, 14, 7, 8, 16)                                              \
-    X(64, 128, 7, 7, 3, 1, 7, 7, 8, 16)
+    X(64, 128, 7, 7, 3, 1, 7, 7, 8, 16)                                                \
+    X(32, 64, 56, 56, 3, 1, 14, 4, 8, 16)                                              \
+    X(64, 128, 28, 28, 3, 1, 14, 4, 8, 16)                                             \
+    X(128, 256, 14, 14, 3, 1, 14, 7, 8, 16)
 
 #define WGRAD_SHAPES(X)                                                                \
     /*      CIN COUT  H   W  K PAD  TY TCO CIB */                                      \
@@ -705,13 +712,17 @@ static int stream_grid(long warps_needed) {
     X(16, 32, 28, 28, 5, 2, 14, 8, 16)                                                 \
     X(32, 64, 14, 14, 5, 2, 14, 8, 8)                                                  \
     X(32, 64, 14, 14, 3, 1, 14, 8, 8)                                                  \
-    X(64, 128, 7, 7, 3, 1, 7, 8, 8)
+    X(64, 128, 7, 7, 3, 1, 7, 8, 8)                                                    \
+    X(32, 64, 56, 56, 3, 1, 4, 8, 8)                                                   \
+    X(64, 128, 28, 28, 3, 1, 4, 8, 8)                                                  \
+    X(128, 256, 14, 14, 3, 1, 7, 8, 8)
 
 #define WGRAD1_SHAPES(X)                                                               \
     /*     COUT  H    W   K PAD  TY SX */                                              \
     X(32, 28, 28, 5, 2, 4, 4)                                                          \
     X(8, 112, 112, 5, 2, 4, 4)                                                         \
-    X(32, 28, 28, 3, 1, 4, 4)
+    X(32, 28, 28, 3, 1, 4, 4)                                                          \
+    X(32, 112, 112, 3, 1, 1, 4)
 
 }  // namespace b200
 

@@ -84,6 +84,26 @@ def image_simple_params(O):
     return used, []
 
 
+def simple_multi_params(E, O, mix=None):
+    """Parameter specs of SimpleMultiModalEncoder (models/dino.py:214-234: image_encoder() / audio_encoder() `nn.Sequential`s,
+    :18-73, + the concatenation fusion) and its two subclasses: GatedMultiModalEncoder (:237-263, two scalar gates) and
+    CrossAttentionMultiModalEncoder (:407-452, two CrossModalAttention blocks :385-405).  Every parameter receives gradients."""
+    used = []
+    for i, (ci, co) in zip((0, 4, 8), ((1, 32), (32, 64), (64, 128))):
+        used += _conv(f"image_encoder.{i}", co, ci, 3) + _vec2(f"image_encoder.{i + 1}", co)
+    used += _lin("image_encoder.14", E, 128)
+    for i, (ci, co) in zip((0, 4, 8, 12), ((1, 32), (32, 64), (64, 128), (128, 256))):
+        used += _conv(f"audio_encoder.{i}", co, ci, 3) + _vec2(f"audio_encoder.{i + 1}", co)
+    used += _lin("audio_encoder.18", E, 256)
+    used += _lin("fusion.0", E, 2 * E) + _lin("fusion.3", O, E)
+    if mix == "gated":
+        used += [("gate_image", ()), ("gate_audio", ())]
+    elif mix == "cross":
+        for a in ("image_to_audio_attention", "audio_to_image_attention"):
+            used += _lin(f"{a}.q_proj", E, E) + _lin(f"{a}.kv_proj", 2 * E, E)
+    return used, []
+
+
 def head_params(in_dim, out_dim, hidden=512):
     return _lin("mlp.0", hidden, in_dim) + _vec2("mlp.1", hidden) + _lin("mlp.4", out_dim, hidden)
 
@@ -96,6 +116,12 @@ CENTRAL_AUDIO_LAYERS = [("audio_encoder.0.conv1", "audio_encoder.0.bn1", 1, 8, 1
                         ("audio_encoder.0.conv4", "audio_encoder.0.bn4", 32, 64, 14, 5, 2)]
 SIMPLE_IMAGE_LAYERS = [("encoder.0", "encoder.1", 1, 32, 28, 3, 1), ("encoder.4", "encoder.5", 32, 64, 14, 3, 1),
                        ("encoder.8", "encoder.9", 64, 128, 7, 3, 1)]
+MULTI_SIMPLE_IMAGE_LAYERS = [("image_encoder.0", "image_encoder.1", 1, 32, 28, 3, 1), ("image_encoder.4", "image_encoder.5", 32, 64, 14, 3, 1),
+                             ("image_encoder.8", "image_encoder.9", 64, 128, 7, 3, 1)]
+MULTI_SIMPLE_AUDIO_LAYERS = [("audio_encoder.0", "audio_encoder.1", 1, 32, 112, 3, 1), ("audio_encoder.4", "audio_encoder.5", 32, 64, 56, 3, 1),
+                             ("audio_encoder.8", "audio_encoder.9", 64, 128, 28, 3, 1), ("audio_encoder.12", "audio_encoder.13", 128, 256, 14, 3, 1)]
+# kind -> feature mixing between the encoders and the fusion MLP
+MULTI_KINDS = {"multi_central": None, "multi_simple": None, "multi_simple_gated": "gated", "multi_cross_attention": "cross"}
 
 
 class Arena:
@@ -136,8 +162,9 @@ class _BN:
 
 
 class DinoStepEngine:
-    """See module docstring.  kind: 'multi_central' (CentralMultiModalEncoder) or 'image_simple' (ImageEncoder);
-    mode: 'default' | 'semi_supervised' | 'infonce' | 'mse' (multi_central only)."""
+    """See module docstring.  kind: 'multi_central' (CentralMultiModalEncoder), 'multi_simple' (SimpleMultiModalEncoder),
+    'multi_simple_gated' (GatedMultiModalEncoder), 'multi_cross_attention' (CrossAttentionMultiModalEncoder) or 'image_simple'
+    (ImageEncoder); mode: 'default' | 'semi_supervised' | 'infonce' | 'mse' (multimodal kinds only)."""
 
     def __init__(self, kind="multi_central", mode="default", encoder_output_dim=256, output_dim=256, projection_dim=128,
                  n_global_views=2, n_local_views=4, momentum=0.996, center_momentum=0.9, student_temperature=0.1,
@@ -148,8 +175,10 @@ class DinoStepEngine:
             raise ops._lib.B200Error("DinoStepEngine needs a CUDA device: the hot path has no CPU fallback")
         ops._lib.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-        assert kind in ("multi_central", "image_simple")
-        assert mode == "default" or kind == "multi_central"
+        assert kind in MULTI_KINDS or kind == "image_simple"
+        self.multi = kind in MULTI_KINDS
+        self.mix = MULTI_KINDS.get(kind)
+        assert mode == "default" or self.multi
         assert precision in ("bf16", "fp32")
         self.precision = precision
         self.lin_tc = precision == "bf16"          # linear layers on the tensor cores (tcgen05 kind::tf32)
@@ -173,12 +202,19 @@ class DinoStepEngine:
         self._bc = None              #   ... and Adam's two bias corrections of the current step (device, fp32)
         self._graph = None
 
+        # self.top[mod] = (global average pool before the linear?, linear input width, linear name)
         if kind == "multi_central":
             used, unused = central_encoder_params(self.E, self.O)
             self.img_layers, self.aud_layers = CENTRAL_IMAGE_LAYERS, CENTRAL_AUDIO_LAYERS
+            self.top = {"img": (False, 1600, "enc.image_encoder.1"), "aud": (False, 3136, "enc.audio_encoder.1")}
+        elif self.multi:
+            used, unused = simple_multi_params(self.E, self.O, self.mix)
+            self.img_layers, self.aud_layers = MULTI_SIMPLE_IMAGE_LAYERS, MULTI_SIMPLE_AUDIO_LAYERS
+            self.top = {"img": (True, 128, "enc.image_encoder.14"), "aud": (True, 256, "enc.audio_encoder.18")}
         else:
             used, unused = image_simple_params(self.O)
             self.img_layers, self.aud_layers = SIMPLE_IMAGE_LAYERS, []
+            self.top = {}
         head = [("head." + n, s) for n, s in head_params(self.O, self.P)]
         enc_used = [("enc." + n, s) for n, s in used]
         enc_unused = [("enc." + n, s) for n, s in unused]
@@ -196,7 +232,7 @@ class DinoStepEngine:
         # gradient exchange in two slices: [split, end of the trainable prefix) -- audio encoder linear, fusion MLP, projection head:
         # complete as soon as the linear weight gradients are (early in the backward pass), exchanged beside the conv stacks'
         # backward -- and [0, split): the conv stacks + the image encoder linear, complete at the end of the backward pass
-        self._bucket_split = self.student.offsets["enc.audio_encoder.1.weight"][0] if kind == "multi_central" else 0
+        self._bucket_split = self.student.offsets[self.top["aud"][2] + ".weight"][0] if self.multi else 0
         self._grad_scale = 1.0
         self.grad = torch.zeros_like(self.student.flat)
         self.exp_avg = torch.zeros_like(self.student.flat)
@@ -287,6 +323,8 @@ class DinoStepEngine:
             base = name.rsplit(".", 1)[0]
             if base in bn_bases:
                 v.fill_(1.0 if name.endswith(".weight") else 0.0)
+            elif len(shape) == 0:
+                v.fill_(0.5)                  # gate_image / gate_audio (models/dino.py:242-243)
             elif len(shape) > 1:
                 bounds[base] = 1.0 / math.sqrt(int(np.prod(shape[1:])))
                 v.copy_(((torch.rand(shape, generator=g) * 2 - 1) * bounds[base]).to(self.device))
@@ -413,14 +451,29 @@ class DinoStepEngine:
             w[f"{m}.wg_work_b"] = e(max(sc["wg"], 4))
         E, O, P = self.E, self.O, self.P
         Nv = V * B
-        if self.kind == "multi_central":
+        if self.multi:
             for role, N, nfus in (("s", Ns, Nv), ("t", Nt, Nt)):
-                w[f"{role}.cat"] = e(N, 2 * E)
+                self._mix_workspace(w, role, N, nfus, B, e)
                 w[f"{role}.h1"] = e(nfus, E)
                 w[f"{role}.feat"] = e(nfus, O)
                 w[f"{role}.fmask"] = torch.ones(nfus, E, dtype=torch.uint8, device=dev)
+                for mod, layers in (("img", self.img_layers), ("aud", self.aud_layers)):
+                    if self.top[mod][0]:
+                        w[f"{role}.{mod}.gap"] = e(N, self.top[mod][1])
             w["d.cat"] = e(Ns, 2 * E)
+            w["d.catr"] = e(Ns, 2 * E) if self.mix else w["d.cat"]       # gradient w.r.t. the un-mixed encoder features
             w["d.h1"] = e(Nv, E)
+            for mod in ("img", "aud"):
+                if self.top[mod][0]:
+                    w[f"d.{mod}.gap"] = e(Ns, self.top[mod][1])
+            if self.mix == "gated":
+                w["gate_work"] = torch.zeros(ops.gate_grad_work_floats(), device=dev)
+            elif self.mix == "cross":
+                w["att.dA"] = e(B, B)
+                w["att.tmp"] = e(Nv, E)
+                for mi in (0, 1):
+                    for nm in ("dq", "dk", "dv"):
+                        w[f"att{mi}.{nm}"] = e(Nv, E)
         else:
             for role, N in (("s", Ns), ("t", Nt)):
                 w[f"{role}.pool"] = e(N, 128)
@@ -455,10 +508,90 @@ class DinoStepEngine:
                     w[f"{m}.{nm}"] = e(1, 512)
             if self.mode == "infonce":
                 w["infonce_work"] = e(ops.infonce_work_floats(B, P, tc=self.lin_tc))
-        if self.kind != "multi_central" or self.cosine_loss_alpha > 0:
+        if not self.multi or self.cosine_loss_alpha > 0:
             w["d.emb"] = e(Nv, O)          # cosine-consistency gradient (UniModalDINO, cosine_loss_alpha may be switched on later)
         self._ws[B] = w
         return w
+
+    def _mix_workspace(self, w, role, N, nfus, B, e):
+        """Encoder-feature buffers of one role: catr [N, 2E] = (image | audio) features as the encoders' linears produce them, cat =
+        the fusion MLP's input (the same tensor, or for the gated / cross-attention encoders the mixed features of the nfus rows)."""
+        E = self.E
+        w[f"{role}.catr"] = e(N, 2 * E)
+        w[f"{role}.cat"] = e(nfus, 2 * E) if self.mix else w[f"{role}.catr"]
+        if self.mix == "cross":
+            for mi in (0, 1):
+                for nm in ("q", "k", "v"):
+                    w[f"{role}.att{mi}.{nm}"] = e(nfus, E)
+                w[f"{role}.att{mi}.A"] = e(nfus // B, B, B)          # attention weights over the batch of each view-call
+
+    # the two CrossModalAttention blocks: (module name, columns of x1 (queries, residual), columns of x2 (keys / values))
+    def _att_blocks(self):
+        E = self.E
+        return (("image_to_audio_attention", slice(0, E), slice(E, 2 * E)), ("audio_to_image_attention", slice(E, 2 * E), slice(0, E)))
+
+    def _mix_fwd(self, w, role, P, nfus, B):
+        """Encoder features -> fusion input.  Gated (models/dino.py:249-261): sigmoid(gate) * features per modality.  Cross attention
+        (models/dino.py:393-405, 436-442): per view-call, out = x1 + softmax((x1 Wq)(x2 Wk)^T / sqrt(E)) (x2 Wv) for (image, audio)
+        and (audio, image); the attention runs over the BATCH dimension of one encoder call."""
+        if not self.mix:
+            return
+        E = self.E
+        catr, cat = w[f"{role}.catr"], w[f"{role}.cat"]
+        if self.mix == "gated":
+            ops.gate_apply(catr[:nfus, :E], P["enc.gate_image"], cat[:, :E])
+            ops.gate_apply(catr[:nfus, E:], P["enc.gate_audio"], cat[:, E:])
+            return
+        scale = float(E) ** -0.5
+        for mi, (name, c1, c2) in enumerate(self._att_blocks()):
+            x1, x2 = catr[:nfus, c1], catr[:nfus, c2]
+            Wq, bq = P[f"enc.{name}.q_proj.weight"], P[f"enc.{name}.q_proj.bias"]
+            Wkv, bkv = P[f"enc.{name}.kv_proj.weight"], P[f"enc.{name}.kv_proj.bias"]
+            q, k, v, A = (w[f"{role}.att{mi}.{nm}"] for nm in ("q", "k", "v", "A"))
+            ops.linear_fwd(x1, Wq, bq, q, tc=self.lin_tc)
+            ops.linear_fwd(x2, Wkv[:E], bkv[:E], k, tc=self.lin_tc)
+            ops.linear_fwd(x2, Wkv[E:], bkv[E:], v, tc=self.lin_tc)
+            for vv in range(nfus // B):
+                r = slice(vv * B, (vv + 1) * B)
+                ops.linear_fwd(q[r], k[r], None, A[vv], tc=self.lin_tc)            # q k^T
+                ops.softmax_rows(A[vv], scale)
+                ops.linear_bwd_data(A[vv], v[r], cat[r, c1], tc=self.lin_tc)       # attn v
+                ops.add2d(cat[r, c1], x1[r])                                       # + x1
+
+    def _mix_bwd(self, w, Nv, B):
+        """d.cat[:Nv] (gradient w.r.t. the fusion input) -> d.catr[:Nv] (gradient w.r.t. the encoder features) + the gradients of
+        the gates / attention projections."""
+        if not self.mix:
+            return
+        E, S, G = self.E, self.S, self.G
+        catr, d_cat, d_catr = w["s.catr"], w["d.cat"], w["d.catr"]
+        if self.mix == "gated":
+            for gname, c in (("enc.gate_image", slice(0, E)), ("enc.gate_audio", slice(E, 2 * E))):
+                ops.gate_grad(d_cat[:Nv, c], catr[:Nv, c], S[gname], G[gname], w["gate_work"])
+                ops.gate_apply(d_cat[:Nv, c], S[gname], d_catr[:Nv, c])
+            return
+        scale = float(E) ** -0.5
+        d_catr[:Nv].copy_(d_cat[:Nv])                                               # the residual paths
+        dA, tmp = w["att.dA"], w["att.tmp"]
+        for mi, (name, c1, c2) in enumerate(self._att_blocks()):
+            x1, x2, d_out = catr[:Nv, c1], catr[:Nv, c2], d_cat[:Nv, c1]
+            Wq, Wkv = S[f"enc.{name}.q_proj.weight"], S[f"enc.{name}.kv_proj.weight"]
+            q, k, v, A = (w[f"s.att{mi}.{nm}"] for nm in ("q", "k", "v", "A"))
+            dq, dk, dv = (w[f"att{mi}.{nm}"] for nm in ("dq", "dk", "dv"))
+            for vv in range(Nv // B):
+                r = slice(vv * B, (vv + 1) * B)
+                ops.linear_fwd(d_out[r], v[r], None, dA, tc=self.lin_tc)            # d attn = d_out v^T
+                ops.linear_bwd_weight(A[vv], d_out[r], dv[r], None, tc=self.lin_tc)  # d v = attn^T d_out
+                ops.softmax_rows_bwd(dA, A[vv], scale)                              # d (q k^T)
+                ops.linear_bwd_data(dA, k[r], dq[r], tc=self.lin_tc)                # d q = dS k
+                ops.linear_bwd_weight(dA, q[r], dk[r], None, tc=self.lin_tc)        # d k = dS^T q
+            gq, gkv = G[f"enc.{name}.q_proj.weight"], G[f"enc.{name}.kv_proj.weight"]
+            gbq, gbkv = G[f"enc.{name}.q_proj.bias"], G[f"enc.{name}.kv_proj.bias"]
+            for dy, x, wt, gw, gb, c in ((dq, x1, Wq, gq, gbq, c1), (dk, x2, Wkv[:E], gkv[:E], gbkv[:E], c2),
+                                         (dv, x2, Wkv[E:], gkv[E:], gbkv[E:], c2)):
+                self._lin_wgrad(dy, x, gw, gb)
+                ops.linear_bwd_data(dy, wt, tmp, tc=self.lin_tc)
+                ops.add2d(d_catr[:Nv, c], tmp)
 
     # ------------------------------------------------------------------------------------------------------
     # augmentation
@@ -654,9 +787,19 @@ class DinoStepEngine:
 
     def _encode(self, w, role, P, bns, x_img, x_aud, N, B, n_fusion, fmask, train=True):
         """Encoder forward for N = n_views*B samples; fusion only over the first n_fusion rows."""
-        if self.kind == "multi_central":
+        if self.multi:
             E = self.E
-            cat = w[f"{role}.cat"]
+            catr = w[f"{role}.catr"]
+
+            def top(mod, p_last, cols):
+                pool, nflat, lin = self.top[mod]
+                if pool:                      # AdaptiveAvgPool2d(1) + Flatten (models/dino.py:34-36, 66-68)
+                    ops.avgpool_fwd(p_last, w[f"{role}.{mod}.gap"])
+                    x = w[f"{role}.{mod}.gap"]
+                else:
+                    x = p_last.view(N, nflat)
+                ops.linear_fwd(x, P[lin + ".weight"], P[lin + ".bias"], catr[:, cols], tc=self.lin_tc)
+
             # the student's image stack runs beside its audio stack on a second side stream (independent until the fusion MLP)
             main = torch.cuda.current_stream()
             side = self._side_stream2 if (self.overlap_teacher and role == "s") else None
@@ -664,11 +807,13 @@ class DinoStepEngine:
                 side.wait_stream(main)
             with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
                 pi = self._conv_stack(w, role, "img", self.img_layers, x_img, N, B, P, bns, train=train)
-                ops.linear_fwd(pi.view(N, 1600), P["enc.image_encoder.1.weight"], P["enc.image_encoder.1.bias"], cat[:, :E], tc=self.lin_tc)
+                top("img", pi, slice(0, E))
             pa = self._conv_stack(w, role, "aud", self.aud_layers, x_aud, N, B, P, bns, train=train)
             if side is not None:
                 main.wait_stream(side)
-            ops.linear_fwd(pa.view(N, 3136), P["enc.audio_encoder.1.weight"], P["enc.audio_encoder.1.bias"], cat[:, E:], tc=self.lin_tc)
+            top("aud", pa, slice(E, 2 * E))
+            self._mix_fwd(w, role, P, n_fusion, B)
+            cat = w[f"{role}.cat"]
             h1, feat = w[f"{role}.h1"], w[f"{role}.feat"]
             if fmask is None:        # evaluation mode: no dropout
                 ops.linear_fwd(cat[:n_fusion], P["enc.fusion.0.weight"], P["enc.fusion.0.bias"], h1, act=1, tc=self.lin_tc)
@@ -802,9 +947,13 @@ class DinoStepEngine:
                 for nm in ("scale", "shift", "mean", "invstd"):
                     w[f"e.{mod}.{nm}{li}"] = e(1, co)
         E, O = self.E, self.O
-        if self.kind == "multi_central":
-            w["e.cat"], w["e.h1"], w["e.feat"] = e(B, 2 * E), e(B, E), e(B, O)
+        if self.multi:
+            self._mix_workspace(w, "e", B, B, B, e)
+            w["e.h1"], w["e.feat"] = e(B, E), e(B, O)
             w["e.fmask"] = torch.ones(B, E, dtype=torch.uint8, device=dev)
+            for mod in ("img", "aud"):
+                if self.top[mod][0]:
+                    w[f"e.{mod}.gap"] = e(B, self.top[mod][1])
         else:
             w["e.pool"], w["e.e14"], w["e.feat"] = e(B, 128), e(B, 512), e(B, O)
         self._ws[key] = w
@@ -854,7 +1003,7 @@ class DinoStepEngine:
                 ops.pack_quad8(x.view(B, layers[0][4], layers[0][4]), w[f"{mod}.xs8"], layers[0][6])
         w["packed"] = True
         fmask = None
-        if train and self.kind == "multi_central" and self.fusion_dropout > 0:
+        if train and self.multi and self.fusion_dropout > 0:
             fmask = w["e.fmask"]
             if probe is not None:
                 probe["step"] += 1
@@ -874,7 +1023,7 @@ class DinoStepEngine:
         w = self._workspace(B)
         Ns, Nt, Nv = w["Ns"], w["Nt"], V * B
         S, T = self.S, self.T
-        multi = self.kind == "multi_central"
+        multi = self.multi
         xi = w["x_img"]
         xa = w["x_aud"] if multi else None
         self._join_center()
@@ -935,7 +1084,7 @@ class DinoStepEngine:
             feat_t = self._encode(w, "t", T, self.bn_t, xi[:Nt], xa[:Nt] if multi else None, Nt, B, Nt, w.get("t.fmask"))
             self._head_fwd(w, "t", "head.", T, self.bn_t["head.mlp.1"], feat_t, w["t.proj"], w["t.hh"], w["t.g"], None, 0.0)
         if self.mode != "default":
-            cat = w["s.cat"]
+            cat = w["s.catr"]               # the mode heads read the un-mixed encoder features (models/dino.py:972-980)
             for m, sl in (("aux_image", slice(0, E)), ("aux_audio", slice(E, 2 * E))):
                 self._head_fwd(w, m, m + ".", S, self.bn_s[f"{m}.mlp.1"], cat[Nv:, sl], w[f"{m}.out"], w[f"{m}.hh"], w[f"{m}.g"], None, 0.0)
         w["loss"].zero_()
@@ -945,7 +1094,7 @@ class DinoStepEngine:
         """Fused DINO loss forward+backward (fills w['d.proj'], loss[0]) and the centre EMA (all-reduced when data parallel)."""
         V, Vg, P, B = self.V, self.Vg, self.P, w["B"]
         s_out, t_out = w["s.proj"].view(V, B, P), w["t.proj"].view(Vg, B, P)
-        variant = 0 if self.kind == "multi_central" else 1
+        variant = 0 if self.multi else 1
         if variant == 1:
             ops.teacher_norm_colmean(t_out, self.center, w["t_colmean"])
         ops.dino_loss_fwd_bwd(s_out, t_out, self.center, self.tau_s, self.tau_t, w["d.proj"].view(V, B, P), w["part_loss"], w["part_colsum"],
@@ -992,7 +1141,7 @@ class DinoStepEngine:
         B = w["B"]
         Ns, Nv = w["Ns"], V * B
         S, G = self.S, self.G
-        multi = self.kind == "multi_central"
+        multi = self.multi
         xi, xa = w["x_img"], w.get("x_aud")
         feat_s = w["s.feat"]
         d_proj = w["d.proj"] if d_proj is None else d_proj.reshape(Nv, self.P)
@@ -1003,32 +1152,39 @@ class DinoStepEngine:
                                            work=w["loss_work"])
             d_feat.add_(w["d.emb"])
         if multi:
-            d_cat, d_h1 = w["d.cat"], w["d.h1"]
+            d_cat, d_catr, d_h1 = w["d.cat"], w["d.catr"], w["d.h1"]
             self._lin_wgrad(d_feat, w["s.h1"], G["enc.fusion.3.weight"], G["enc.fusion.3.bias"])
             ops.linear_bwd_data(d_feat, S["enc.fusion.3.weight"], d_h1, tc=self.lin_tc)
             ops.act_bwd(d_h1, w["s.h1"], self.fusion_dropout)
             self._lin_wgrad(d_h1, w["s.cat"][:Nv], G["enc.fusion.0.weight"], G["enc.fusion.0.bias"])
             ops.linear_bwd_data(d_h1, S["enc.fusion.0.weight"], d_cat[:Nv], tc=self.lin_tc)
+            self._mix_bwd(w, Nv, B)
             if self.mode != "default":
                 for i, (m, sl) in enumerate((("aux_image", slice(0, E)), ("aux_audio", slice(E, 2 * E)))):
                     d_out = w[f"{m}.d.out"] if d_aux is None else d_aux[i]
-                    self._head_bwd(w, m, m + ".", w["s.cat"][Nv:, sl], d_out, w[f"{m}.hh"], w[f"{m}.g"], w[f"{m}.d.g"],
-                                   w[f"{m}.d.hh"], d_cat[Nv:, sl], None, 0.0)
+                    self._head_bwd(w, m, m + ".", w["s.catr"][Nv:, sl], d_out, w[f"{m}.hh"], w[f"{m}.g"], w[f"{m}.d.g"],
+                                   w[f"{m}.d.hh"], d_catr[Nv:, sl], None, 0.0)
             # the image and the audio stacks are independent from here on: the (small) image stack runs on the side stream
             main = torch.cuda.current_stream()
             side = self._side_stream if self.overlap_teacher else None
-            for mod, layers, sl, nflat, lin, x in (("img", self.img_layers, slice(0, E), 1600, "enc.image_encoder.1", xi),
-                                                   ("aud", self.aud_layers, slice(E, 2 * E), 3136, "enc.audio_encoder.1", xa)):
+            for mod, layers, sl, x in (("img", self.img_layers, slice(0, E), xi), ("aud", self.aud_layers, slice(E, 2 * E), xa)):
+                pool, nflat, lin = self.top[mod]
                 ctx = torch.cuda.stream(side) if (side is not None and mod == "img") else contextlib.nullcontext()
                 if side is not None and mod == "img":
                     side.wait_stream(main)
                 with ctx:
-                    p_last = w[f"s.{mod}.p{len(layers) - 1}"].view(Ns, nflat)
-                    self._lin_wgrad(d_cat[:, sl], p_last, G[lin + ".weight"], G[lin + ".bias"])
+                    p_last = w[f"s.{mod}.p{len(layers) - 1}"]
+                    x_lin = w[f"s.{mod}.gap"] if pool else p_last.view(Ns, nflat)
+                    self._lin_wgrad(d_catr[:, sl], x_lin, G[lin + ".weight"], G[lin + ".bias"])
                     if mod == "aud" and self.world > 1 and self.overlap_grad_exchange:
                         self._exchange_late_gradients()
-                    d_p = w[f"{mod}.dp_a"][:Ns * nflat].view(Ns, nflat)
-                    ops.linear_bwd_data(d_cat[:, sl], S[lin + ".weight"], d_p, tc=self.lin_tc)
+                    if pool:
+                        ops.linear_bwd_data(d_catr[:, sl], S[lin + ".weight"], w[f"d.{mod}.gap"], tc=self.lin_tc)
+                        d_p = w[f"{mod}.dp_a"][:p_last.numel()].view_as(p_last)
+                        ops.avgpool_bwd(w[f"d.{mod}.gap"], d_p)
+                    else:
+                        d_p = w[f"{mod}.dp_a"][:Ns * nflat].view(Ns, nflat)
+                        ops.linear_bwd_data(d_catr[:, sl], S[lin + ".weight"], d_p, tc=self.lin_tc)
                     self._conv_stack_bwd(w, mod, layers, x, d_p, Ns, B)
             if side is not None:
                 main.wait_stream(side)

@@ -541,6 +541,51 @@ def linear_bwd_weight(dy, x, dw, db, accumulate=False, work=None, tc=False):
                "linear_bwd_weight")
 
 
+# ---- feature mixing of the simple multimodal encoder family (gates, batch-wide cross attention; csrc/mix.cu) ----------
+def gate_apply(x, gate, y):
+    """y = sigmoid(gate) * x over a 2-D block (rows may be strided); models/dino.py:249-256."""
+    M, N = x.shape
+    xp, ldx = _rows(x)
+    yp, ldy = _rows(y)
+    _lib.check(_lib_().b200_gate_apply(xp, ldx, yp, ldy, _ptr(gate, F32), M, N, _stream()), "gate_apply")
+
+
+def gate_grad_work_floats():
+    return int(_lib_().b200_gate_grad_work_floats())
+
+
+def gate_grad(dy, x, gate, dgate, work, accumulate=False):
+    """dgate (+)= sigmoid'(gate) * sum(dy * x); work: zero-initialised scratch of gate_grad_work_floats() floats."""
+    M, N = x.shape
+    dyp, lddy = _rows(dy)
+    xp, ldx = _rows(x)
+    _lib.check(_lib_().b200_gate_grad(dyp, lddy, xp, ldx, _ptr(gate, F32), _ptr(dgate, F32), _ptr(work, F32), M, N, 1 if accumulate else 0,
+                                      _stream()), "gate_grad")
+
+
+def softmax_rows(s, scale):
+    """s <- softmax(scale * s) per row, in place (attention weights, models/dino.py:400-401)."""
+    M, N = s.shape
+    sp, ld = _rows(s)
+    _lib.check(_lib_().b200_softmax_rows(sp, ld, M, N, scale, _stream()), "softmax_rows")
+
+
+def softmax_rows_bwd(dp, p, scale):
+    """dp <- scale * p * (dp - sum_n dp p) per row, in place on dp."""
+    M, N = p.shape
+    dpp, lddp = _rows(dp)
+    pp, ldp = _rows(p)
+    _lib.check(_lib_().b200_softmax_rows_bwd(dpp, lddp, pp, ldp, M, N, scale, _stream()), "softmax_rows_bwd")
+
+
+def add2d(dst, src):
+    """dst += src for 2-D blocks with row strides."""
+    M, N = dst.shape
+    dp, ldd = _rows(dst)
+    sp, lds = _rows(src)
+    _lib.check(_lib_().b200_add2d(dp, ldd, sp, lds, M, N, _stream()), "add2d")
+
+
 def act_bwd(dy, y, drop_p=0.0):
     _lib.check(_lib_().b200_act_bwd(_ptr(dy, F32), _ptr(y, F32), None, drop_p, dy.numel(), _stream()), "act_bwd")
 
@@ -594,8 +639,8 @@ def knn_predict(train_feats, train_labels, test_feats, k=5, n_classes=10, return
 
 # ---- launch accounting and optional per-op timing ------------------------------------------------------------
 # Every wrapper above issues a fixed number of kernel launches; the table lists the ones that issue more than one.
-_LAUNCHES = {"ntxent_fwd_bwd": 5, "conv_tc_wgrad_l0_fused": 3, "conv_tc_wgrad": 2, "conv_bwd_weight": 3, "linear_bwd_weight": 3, "infonce_fwd_bwd": 9}
-_NOT_KERNELS = {"knn_predict", "conv_tc_pool_supported", "conv_tc_dgrad_bnstat_supported", "quad8_width", "ntxent_work_floats", "conv_tc_wgrad_l0_fused_work_floats", "conv_tc_wgrad_work_floats", "conv_tc_supported", "conv_tc_weight_bytes", "dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
+_LAUNCHES = {"gate_grad": 2, "ntxent_fwd_bwd": 5, "conv_tc_wgrad_l0_fused": 3, "conv_tc_wgrad": 2, "conv_bwd_weight": 3, "linear_bwd_weight": 3, "infonce_fwd_bwd": 9}
+_NOT_KERNELS = {"gate_grad_work_floats", "knn_predict", "conv_tc_pool_supported", "conv_tc_dgrad_bnstat_supported", "quad8_width", "ntxent_work_floats", "conv_tc_wgrad_l0_fused_work_floats", "conv_tc_wgrad_work_floats", "conv_tc_supported", "conv_tc_weight_bytes", "dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
 LAUNCH_COUNT = 0
 _PROFILE = None          # None, or a list receiving (name, start_event, end_event, meta)
 

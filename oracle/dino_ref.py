@@ -64,6 +64,41 @@ def image_simple_bn_names():
     return ["encoder.1", "encoder.5", "encoder.9"]
 
 
+def simple_multi_spec(E=256, O=256, mix=None):
+    """SimpleMultiModalEncoder (models/dino.py:214-234) over image_encoder(E) / audio_encoder(E) (models/dino.py:18-73);
+    mix="gated": GatedMultiModalEncoder (:237-263); mix="cross": CrossAttentionMultiModalEncoder (:407-452, CrossModalAttention :385-405)."""
+    s = []
+    for i, (ci, co) in zip((0, 4, 8), ((1, 32), (32, 64), (64, 128))):
+        s += _conv(f"image_encoder.{i}", co, ci, 3) + _bn(f"image_encoder.{i + 1}", co)
+    s += _lin("image_encoder.14", E, 128)
+    for i, (ci, co) in zip((0, 4, 8, 12), ((1, 32), (32, 64), (64, 128), (128, 256))):
+        s += _conv(f"audio_encoder.{i}", co, ci, 3) + _bn(f"audio_encoder.{i + 1}", co)
+    s += _lin("audio_encoder.18", E, 256)
+    s += _lin("fusion.0", E, 2 * E) + _lin("fusion.3", O, E)
+    if mix == "gated":
+        s += [("gate_image", ()), ("gate_audio", ())]
+    elif mix == "cross":
+        for a in ("image_to_audio_attention", "audio_to_image_attention"):
+            s += _lin(f"{a}.q_proj", E, E) + _lin(f"{a}.kv_proj", 2 * E, E)
+    return s
+
+
+def simple_multi_bn_names():
+    return ["image_encoder.1", "image_encoder.5", "image_encoder.9", "audio_encoder.1", "audio_encoder.5", "audio_encoder.9",
+            "audio_encoder.13"]
+
+
+KIND_MIX = {"multi_central": None, "multi_simple": None, "multi_simple_gated": "gated", "multi_cross_attention": "cross"}
+
+
+def encoder_spec(kind, E=256, O=256):
+    return central_encoder_spec(E, O) if kind == "multi_central" else simple_multi_spec(E, O, KIND_MIX[kind])
+
+
+def encoder_bn_names(kind):
+    return central_bn_names() if kind == "multi_central" else simple_multi_bn_names()
+
+
 def head_spec(in_dim, out_dim, hidden=512):
     """ProjectionHead (models/dino.py:1240-1254)."""
     return _lin("mlp.0", hidden, in_dim) + _bn("mlp.1", hidden) + _lin("mlp.4", out_dim, hidden)
@@ -90,6 +125,8 @@ def make_params(spec, seed, dtype=torch.float32):
             t = (torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * b
         elif name.endswith(".weight"):
             t = 1.0 + 0.1 * torch.randn(shape, generator=g, dtype=torch.float64)
+        elif len(shape) == 0:           # the scalar gates of GatedMultiModalEncoder
+            t = 0.5 + 0.3 * torch.randn(shape, generator=g, dtype=torch.float64)
         else:
             t = 0.1 * torch.randn(shape, generator=g, dtype=torch.float64)
         out[name] = t.to(dtype)
@@ -157,6 +194,52 @@ def central_encoder(img, aud, p, buf, fusion_keep=None, fusion_p=0.3):
     """SimpleMultiModalEncoder.forward (models/dino.py:229-234) with the Central encoders."""
     fi = central_image_features(img, p, buf)
     fa = central_audio_features(aud, p, buf)
+    h = F.relu(F.linear(torch.cat([fi, fa], 1), p["fusion.0.weight"], p["fusion.0.bias"]))
+    h = _dropout(h, fusion_keep, fusion_p)
+    return F.linear(h, p["fusion.3.weight"], p["fusion.3.bias"])
+
+
+def simple_image_features(x, p, buf, pre="image_encoder", train=True):
+    """image_encoder(E) (models/dino.py:18-41): 3 x [conv3x3 pad 1, BN, ReLU, maxpool 2] -> global average pool -> Linear(128, E)."""
+    for i in (0, 4, 8):
+        x = _block(x, p, buf, f"{pre}.{i}", f"{pre}.{i + 1}", 1, train)
+    return F.linear(x.mean(dim=(2, 3)), p[f"{pre}.14.weight"], p[f"{pre}.14.bias"])
+
+
+def simple_audio_features(x, p, buf, pre="audio_encoder", train=True):
+    """audio_encoder(E) (models/dino.py:43-73): 4 x [conv3x3 pad 1, BN, ReLU, maxpool 2] -> global average pool -> Linear(256, E)."""
+    for i in (0, 4, 8, 12):
+        x = _block(x, p, buf, f"{pre}.{i}", f"{pre}.{i + 1}", 1, train)
+    return F.linear(x.mean(dim=(2, 3)), p[f"{pre}.18.weight"], p[f"{pre}.18.bias"])
+
+
+def cross_modal_attention(x1, x2, p, name):
+    """CrossModalAttention.forward (models/dino.py:393-405): attention over the batch of one encoder call, plus the residual."""
+    q = F.linear(x1, p[f"{name}.q_proj.weight"], p[f"{name}.q_proj.bias"])
+    k, v = F.linear(x2, p[f"{name}.kv_proj.weight"], p[f"{name}.kv_proj.bias"]).chunk(2, dim=-1)
+    attn = ((q @ k.transpose(-2, -1)) * (x1.shape[-1] ** -0.5)).softmax(dim=-1)
+    return x1 + attn @ v
+
+
+def image_features(kind, x, p, buf, train=True):
+    return (central_image_features if kind == "multi_central" else simple_image_features)(x, p, buf, train=train)
+
+
+def audio_features(kind, x, p, buf, train=True):
+    return (central_audio_features if kind == "multi_central" else simple_audio_features)(x, p, buf, train=train)
+
+
+def multimodal_encoder(kind, img, aud, p, buf, fusion_keep=None, fusion_p=0.3, train=True):
+    """forward() of SimpleMultiModalEncoder (models/dino.py:229-234; inherited by CentralMultiModalEncoder), GatedMultiModalEncoder
+    (:249-263) and CrossAttentionMultiModalEncoder (:431-452)."""
+    fi = image_features(kind, img, p, buf, train)
+    fa = audio_features(kind, aud, p, buf, train)
+    mix = KIND_MIX[kind]
+    if mix == "gated":
+        fi, fa = torch.sigmoid(p["gate_image"]) * fi, torch.sigmoid(p["gate_audio"]) * fa
+    elif mix == "cross":
+        fi, fa = (cross_modal_attention(fi, fa, p, "image_to_audio_attention"),
+                  cross_modal_attention(fa, fi, p, "audio_to_image_attention"))
     h = F.relu(F.linear(torch.cat([fi, fa], 1), p["fusion.0.weight"], p["fusion.0.bias"]))
     h = _dropout(h, fusion_keep, fusion_p)
     return F.linear(h, p["fusion.3.weight"], p["fusion.3.bias"])
@@ -282,18 +365,19 @@ def adam_step(params, grads, state, lr=1e-4, weight_decay=1e-6, betas=(0.9, 0.99
 # ------------------------------------------------------------------------------------------------------------
 
 class CentralDinoState:
-    """All state of MultiModalDINO(+mode heads) with CentralMultiModalEncoder, as flat dicts."""
+    """All state of MultiModalDINO(+mode heads) as flat dicts; kind selects the encoder: CentralMultiModalEncoder (default),
+    SimpleMultiModalEncoder, GatedMultiModalEncoder or CrossAttentionMultiModalEncoder."""
 
-    def __init__(self, seed=0, E=256, O=256, P=128, mode="default", dtype=torch.float32):
-        self.E, self.O, self.P, self.mode, self.dtype = E, O, P, mode, dtype
-        self.enc_spec = central_encoder_spec(E, O)
+    def __init__(self, seed=0, E=256, O=256, P=128, mode="default", dtype=torch.float32, kind="multi_central"):
+        self.E, self.O, self.P, self.mode, self.dtype, self.kind = E, O, P, mode, dtype, kind
+        self.enc_spec = encoder_spec(kind, E, O)
         self.head_spec = head_spec(O, P)
         self.student = make_params(self.enc_spec, seed, dtype)
         self.student_head = make_params(self.head_spec, seed + 1, dtype)
         self.teacher = {k: v.clone() for k, v in self.student.items()}
         self.teacher_head = {k: v.clone() for k, v in self.student_head.items()}
-        self.student_buf = make_bn_buffers(self.enc_spec, central_bn_names(), dtype)
-        self.teacher_buf = make_bn_buffers(self.enc_spec, central_bn_names(), dtype)
+        self.student_buf = make_bn_buffers(self.enc_spec, encoder_bn_names(kind), dtype)
+        self.teacher_buf = make_bn_buffers(self.enc_spec, encoder_bn_names(kind), dtype)
         self.student_head_buf = make_bn_buffers(self.head_spec, ["mlp.1"], dtype)
         self.teacher_head_buf = make_bn_buffers(self.head_spec, ["mlp.1"], dtype)
         self.center = torch.zeros(1, P, dtype=dtype)
@@ -325,11 +409,12 @@ def central_dino_step(st, img_views, aud_views, masks, n_global=2, tau_s=0.1, ta
     SH = {k: v.clone().requires_grad_(True) for k, v in st.student_head.items()}
     AUX = {m: {k: v.clone().requires_grad_(True) for k, v in st.aux[m].items()} for m in ("image", "audio") if m in st.aux}
 
-    feats = [central_encoder(img_views[v], aud_views[v], S, st.student_buf, masks["student_fusion"][v], 0.3)
+    kind = getattr(st, "kind", "multi_central")
+    feats = [multimodal_encoder(kind, img_views[v], aud_views[v], S, st.student_buf, masks["student_fusion"][v], 0.3)
              for v in range(V)]
     student_features = torch.cat(feats)
     with torch.no_grad():
-        tf = [central_encoder(img_views[v], aud_views[v], st.teacher, st.teacher_buf, masks["teacher_fusion"][v], 0.3)
+        tf = [multimodal_encoder(kind, img_views[v], aud_views[v], st.teacher, st.teacher_buf, masks["teacher_fusion"][v], 0.3)
               for v in range(n_global)]
         teacher_features = torch.cat(tf)
     student_projs = projection_head(student_features, SH, st.student_head_buf, masks["student_head"], dropout)
@@ -343,8 +428,8 @@ def central_dino_step(st, img_views, aud_views, masks, n_global=2, tau_s=0.1, ta
     aux_val = None
     if st.mode != "default":
         image, audio = raw
-        fi = central_image_features(image, S, st.student_buf)
-        fa = central_audio_features(audio, S, st.student_buf)
+        fi = image_features(kind, image, S, st.student_buf)
+        fa = audio_features(kind, audio, S, st.student_buf)
         zi = projection_head(fi, AUX["image"], st.aux["image_buf"])
         za = projection_head(fa, AUX["audio"], st.aux["audio_buf"])
         if st.mode == "semi_supervised":

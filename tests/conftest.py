@@ -23,3 +23,11 @@ def golden():
 def golden_aug():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "augment.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_simple():
+    """Step fixtures of the imported reference for the simple / gated / cross-attention encoders (make_golden.py simple)."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "golden_simple.json")) as f:
+        return json.load(f)

@@ -161,14 +161,18 @@ def _load(module, prefix_params, buffers=None):
     module.load_state_dict(sd)
 
 
-def step_fixture(mode, B=4, seed=5, n_steps=2):
-    st = R.CentralDinoState(seed=seed, mode=mode)
+ENCODER_CLASSES = {"multi_central": "CentralMultiModalEncoder", "multi_simple": "SimpleMultiModalEncoder",
+                   "multi_simple_gated": "GatedMultiModalEncoder", "multi_cross_attention": "CrossAttentionMultiModalEncoder"}
+
+
+def step_fixture(mode, B=4, seed=5, n_steps=2, kind="multi_central"):
+    st = R.CentralDinoState(seed=seed, mode=mode, kind=kind)
     cls = {"default": md.MultiModalDINO, "semi_supervised": md.MultiModalDINOSemiSupervised,
            "infonce": md.MultiModalDINOWithINFONCE, "mse": md.MultiModalDINOWithMSE}[mode]
     lcls = {"default": md.MultiModalDINOLightning, "semi_supervised": md.MultiModalDINOSemiSupervisedLightning,
             "infonce": md.MultiModalDINOWithINFONCELightning, "mse": md.MultiModalDINOWithMSELightning}[mode]
     torch.manual_seed(0)
-    model = cls(encoder_class=md.CentralMultiModalEncoder, output_dim=256, encoder_output_dim=256, projection_dim=128,
+    model = cls(encoder_class=getattr(md, ENCODER_CLASSES[kind]), output_dim=256, encoder_output_dim=256, projection_dim=128,
                 momentum=0.996, center_momentum=0.9, dropout=0.3)
     _load(model.student, st.student)
     _load(model.teacher, st.teacher)
@@ -193,7 +197,7 @@ def step_fixture(mode, B=4, seed=5, n_steps=2):
     lit = L(model)
     lit.train()
     opt = torch.optim.Adam(lit.parameters(), lr=1e-4, weight_decay=1e-6)
-    out = {"mode": mode, "B": B, "seed": seed, "steps": []}
+    out = {"mode": mode, "kind": kind, "B": B, "seed": seed, "steps": []}
     for it in range(n_steps):
         gi, ga, li, la = synth_views(B, seed=100 + it)
         m = make_masks(seed=200 + it, V=6, Vg=2, B=B, E=256, hidden=512)
@@ -301,6 +305,16 @@ def simclr_fixtures(n_seeds=8, B=3):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "simclr":
         print("wrote simclr_aug.npz:", len(simclr_fixtures()), "arrays")
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "simple":
+        # the other conv encoders (models/dino.py:214-263, 385-452) -> tests/golden/golden_simple.json
+        fx = {f"{k}/{m}": step_fixture(m, kind=k) for k, m in (("multi_simple", "default"), ("multi_simple", "mse"), ("multi_simple_gated", "default"),
+                                                              ("multi_simple_gated", "semi_supervised"), ("multi_cross_attention", "default"),
+                                                              ("multi_cross_attention", "infonce"))}
+        fx["versions"] = {"torch": torch.__version__}
+        with open(os.path.join(HERE, "golden_simple.json"), "w") as f:
+            json.dump(fx, f, indent=1)
+        print("wrote golden_simple.json:", sorted(fx))
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "api":
         with open(os.path.join(HERE, "api_surface.json"), "w") as f:

@@ -80,8 +80,18 @@ def test_every_encoder_name_of_run_dino_imports():
         assert hasattr(md, name)
     with pytest.raises(NotImplementedError):
         md.LSTMMultiModalEncoder()
-    with pytest.raises(NotImplementedError):
-        md.MultiModalDINO(encoder_class=md.SimpleMultiModalEncoder)      # containers exist, the compiled step does not (yet)
+    # the conv encoder family of SURVEY 8f-4 has a compiled step: state_dict keys as in the reference (models/dino.py:214-263, 385-452)
+    for cls, extra in ((md.SimpleMultiModalEncoder, set()), (md.GatedMultiModalEncoder, {"gate_image", "gate_audio"}),
+                       (md.CrossAttentionMultiModalEncoder, {f"{a}.{p}.{w}" for a in ("image_to_audio_attention", "audio_to_image_attention")
+                                                             for p in ("q_proj", "kv_proj") for w in ("weight", "bias")})):
+        m = md.MultiModalDINO(encoder_class=cls, output_dim=256, encoder_output_dim=256, projection_dim=128)
+        keys = set(m.student.state_dict())
+        assert extra <= keys and {"image_encoder.14.weight", "audio_encoder.18.weight", "audio_encoder.12.weight", "fusion.3.bias"} <= keys
+        assert m._b200.kind == cls.B200_KIND
+        from multimodal_ssl_avmnist_b200.engine import simple_multi_params, MULTI_KINDS
+        spec = dict(simple_multi_params(256, 256, MULTI_KINDS[cls.B200_KIND])[0])
+        params = {k: tuple(v.shape) for k, v in m.student.named_parameters()}
+        assert params == spec, set(params) ^ set(spec)
 
 
 def test_no_cpu_fallback():

@@ -314,7 +314,9 @@ def test_augment_device_sampler_distributions():
 
 # ------------------------------------------------------------------------------------------------------------
 CONV_SHAPES = [(1, 32, 28, 28, 5, 2), (32, 64, 14, 14, 5, 0), (1, 8, 112, 112, 5, 2), (8, 16, 56, 56, 5, 2), (16, 32, 28, 28, 5, 2),
-               (32, 64, 14, 14, 5, 2), (1, 32, 28, 28, 3, 1), (32, 64, 14, 14, 3, 1), (64, 128, 7, 7, 3, 1)]
+               (32, 64, 14, 14, 5, 2), (1, 32, 28, 28, 3, 1), (32, 64, 14, 14, 3, 1), (64, 128, 7, 7, 3, 1),
+               # multi_simple audio stack (models/dino.py:43-72)
+               (1, 32, 112, 112, 3, 1), (32, 64, 56, 56, 3, 1), (64, 128, 28, 28, 3, 1), (128, 256, 14, 14, 3, 1)]
 
 
 @pytest.mark.parametrize("shape", CONV_SHAPES)
@@ -352,7 +354,7 @@ def test_conv_block_fwd_bwd(shape, N, npv):
     out = torch.empty(N, Cout, HO // 2, WO // 2, device=DEV)
     ops.bn_relu_pool_fwd(z, scale, shift, out, npv)
     zref = torch.cat([F.conv2d(x[v * npv:(v + 1) * npv], w, b, padding=pad) for v in range(n_views)])
-    _close(z, zref, 1e-5, 2e-6, "conv z")
+    _close(z, zref, 1e-5, 2e-6 * max(1.0, (Cin * K * K / 200) ** 0.5), "conv z")        # rounding grows with the reduction length
     _close(out, out_ref, 2e-5, 1e-5, "block out")
     _close(rmd, rm, 1e-5, 1e-6, "running_mean")
     _close(rvd, rv, 1e-5, 1e-6, "running_var")
@@ -371,12 +373,22 @@ def test_conv_block_fwd_bwd(shape, N, npv):
     dw, db = torch.empty_like(wd), torch.empty(Cout, device=DEV)
     work = torch.empty(ops.conv_bwd_weight_work_floats(N, Cin, Cout, H, W, K, pad), device=DEV)
     ops.conv_bwd_weight(xd, dz, dw, db, work, pad)
-    _close(dw, wr.grad, 2e-4, 2e-5 * float(wr.grad.abs().max()), "dw")
+    # the kernel itself, with the pooling decisions fixed: against the fp64 weight gradient of OUR dz (a near-tie arg-max that flips
+    # between the CUDA and the ATen forward moves a whole dout term, which is not the convolution kernels' business)
+    dz64 = dz.detach().cpu().double()
+    dw_iso = torch.nn.grad.conv2d_weight(x.double(), w.shape, dz64, padding=pad)
+    _close(dw, dw_iso, 2e-4, 2e-5 * float(dw_iso.abs().max()), "dw (given dz)")
+    big = N * Cout * HO * WO > 2_000_000          # > 0.5 M pooling windows: end-to-end flips are expected, see above
+    if not big:
+        _close(dw, wr.grad, 2e-4, 2e-5 * float(wr.grad.abs().max()), "dw")
     assert float(db.abs().max()) < 1e-3 * max(1.0, float(dout.abs().sum()) ** 0.5)       # bias feeds BN: exact gradient is 0
     if Cin > 1:
         dx = torch.empty_like(xd)
         ops.conv_bwd_data(dz, wd, dx, pad)
-        _close(dx, xr.grad, 2e-4, 2e-5 * float(xr.grad.abs().max()), "dx")
+        dx_iso = torch.nn.grad.conv2d_input(x.shape, w.double(), dz64, padding=pad)
+        _close(dx, dx_iso, 2e-4, 2e-5 * float(dx_iso.abs().max()), "dx (given dz)")
+        if not big:
+            _close(dx, xr.grad, 2e-4, 2e-5 * float(xr.grad.abs().max()), "dx")
 
 
 def test_conv_odd_output_and_avgpool():
@@ -647,3 +659,44 @@ def test_simclr_augmentation_kernels_vs_oracle_and_reference(golden):
     el = torch.from_numpy((kinds == A.OP_ELASTIC).any(-1)).to(DEV)          # [B, 2]
     moved = (out - torch.stack([src, src])).abs().amax(dim=(2, 3)).t()      # every view is at least cropped / rotated
     assert float(moved.min()) > 1e-3 and float((out[0] - out[1]).abs().max()) > 1e-3 and bool(el.any())
+
+
+def test_mix_kernels_gate_softmax_add2d():
+    """csrc/mix.cu against plain torch fp32/fp64: sigmoid gates (models/dino.py:249-256), the attention row softmax and its
+    backward (models/dino.py:400-401), the strided accumulate; strided (column-slice) operands as the engine passes them."""
+    g = torch.Generator().manual_seed(3)
+    M, E = 37, 24
+    cat = torch.randn(M, 2 * E, generator=g).to(DEV)
+    dy = torch.randn(M, 2 * E, generator=g).to(DEV)
+    gate = torch.tensor(0.37, device=DEV)
+    out = torch.full((M, 2 * E), float("nan"), device=DEV)
+    ops.gate_apply(cat[:, E:], gate, out[:, E:])
+    torch.cuda.synchronize()
+    assert torch.allclose(out[:, E:], torch.sigmoid(gate) * cat[:, E:], rtol=1e-6, atol=1e-7) and bool(torch.isnan(out[:, :E]).all())
+    work = torch.zeros(ops.gate_grad_work_floats(), device=DEV)
+    dgate = torch.full((), float("nan"), device=DEV)
+    s = torch.sigmoid(gate.double())
+    want = float((dy[:, E:].double() * cat[:, E:].double()).sum() * s * (1 - s))
+    for _ in range(2):          # the ticket is left zero: a second call gives the same answer
+        ops.gate_grad(dy[:, E:], cat[:, E:], gate, dgate, work)
+        torch.cuda.synchronize()
+        assert abs(float(dgate) - want) < 1e-5 * max(1.0, abs(want)), (float(dgate), want)
+    ops.gate_grad(dy[:, E:], cat[:, E:], gate, dgate, work, accumulate=True)
+    torch.cuda.synchronize()
+    assert abs(float(dgate) - 2 * want) < 2e-5 * max(1.0, abs(want))
+    for B in (4, 300, 1024):
+        S = torch.randn(B, B, generator=g).to(DEV) * 3
+        A = S.clone()
+        scale = 256 ** -0.5
+        ops.softmax_rows(A, scale)
+        ref = torch.softmax(S.double() * scale, dim=-1)
+        assert float((A.double() - ref).abs().max()) < 1e-6
+        dA = torch.randn(B, B, generator=g).to(DEV)
+        d = dA.clone()
+        ops.softmax_rows_bwd(d, A, scale)
+        dref = scale * ref * (dA.double() - (dA.double() * ref).sum(-1, keepdim=True))
+        assert float((d.double() - dref).abs().max()) < 1e-6 * max(1.0, float(dref.abs().max()))
+    dst = cat.clone()
+    ops.add2d(dst[:, :E], dy[:, E:])
+    torch.cuda.synchronize()
+    assert torch.equal(dst[:, :E], cat[:, :E] + dy[:, E:]) and torch.equal(dst[:, E:], cat[:, E:])

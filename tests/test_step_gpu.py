@@ -19,7 +19,7 @@ DEV = "cuda"
 
 
 def _cancelled(name):
-    return re.search(r"(\.conv[1-4]\.bias|mlp\.0\.bias|fusion\.3\.bias|projection\.0\.bias|encoder\.[048]\.bias|encoder\.14\.bias)$", name) is not None
+    return re.search(r"(\.conv[1-4]\.bias|mlp\.0\.bias|fusion\.3\.bias|projection\.0\.bias|(?<!_)encoder\.[048]\.bias|(?<!_)encoder\.14\.bias|(image|audio)_encoder\.(0|4|8|12)\.bias)$", name) is not None
 
 
 def _rel(a, b):
@@ -173,10 +173,65 @@ def test_step_vs_oracle_and_reference(mode, golden):
     step the engine is re-synchronised to the oracle's state after the first, so the comparison is per step and not along a
     chaotic free-running trajectory.  Against the imported reference's own numbers (golden) the second step is bounded by what
     separates the oracle from the reference there (1e-2, tests/test_oracle_golden.py) plus the engine-vs-oracle 3e-4."""
-    fx = golden["steps"][mode]
+    _step_vs_oracle_and_reference(golden["steps"][mode], mode, "multi_central")
+
+
+SIMPLE_CASES = ["multi_simple/default", "multi_simple/mse", "multi_simple_gated/default", "multi_simple_gated/semi_supervised",
+                "multi_cross_attention/default", "multi_cross_attention/infonce"]
+
+
+@pytest.mark.parametrize("case", SIMPLE_CASES)
+def test_simple_family_step_vs_oracle_and_reference(case, golden_simple):
+    """the training step of SimpleMultiModalEncoder / GatedMultiModalEncoder / CrossAttentionMultiModalEncoder
+    (models/dino.py:214-263, 385-452) on the exact-fp32 path against the oracle and the imported reference's own numbers
+    (tests/golden/golden_simple.json).  Reference tolerances as in tests/test_oracle_golden.py for this family."""
+    kind, mode = case.split("/")
+    _step_vs_oracle_and_reference(golden_simple[case], mode, kind, ref_rtol=(1e-3, 5e-2), ref_loss1=5e-5, flip_floor=5e-2)
+
+
+@pytest.mark.parametrize("kind", ["multi_simple", "multi_simple_gated", "multi_cross_attention"])
+def test_simple_family_bf16_path_vs_oracle(kind, golden_simple):
+    """The product path (precision="bf16": tensor-core convolutions where the library has the geometry, tf32 tensor-core linears and
+    attention products) of the simple encoder family against the fp32 oracle: the bf16 tolerances of the central encoder's test
+    (loss 2e-3 relative, projections 2e-2 of the output scale, gradient direction cosine > 0.97)."""
+    fx = golden_simple[kind + "/default"]
     B = fx["B"]
-    st = R.CentralDinoState(seed=fx["seed"], mode=mode)
-    eng = DinoStepEngine(kind="multi_central", mode=mode, device=DEV, precision="fp32")
+    st = R.CentralDinoState(seed=fx["seed"], mode="default", kind=kind)
+    eng = DinoStepEngine(kind=kind, mode="default", device=DEV, precision="bf16")
+    assert all(eng.tc["img"]), "the 28x28 image stack must run on the tensor cores"
+    _load_state(eng, st)
+    img, aud = views_to_vb(*synth_views(B, seed=100))
+    masks = make_masks(seed=200, V=6, Vg=2, B=B, E=256, hidden=512)
+    want = R.central_dino_step(st, img, aud, masks)
+    loss = eng.forward_backward(img[:, :, 0].to(DEV).contiguous(), aud[:, :, 0].to(DEV).contiguous(), masks=_gpu_masks(masks))
+    torch.cuda.synchronize()
+    total = float(loss[3])
+    assert abs(total - float(want["loss"])) < 2e-3 * abs(float(want["loss"])), (total, float(want["loss"]))
+    assert _rel(eng._ws[B]["s.proj"].view(6, B, -1), want["student_out"]) < 2e-2
+    flat_m, flat_w = [], []
+    for prefix, gd in (("enc.", want["grads"]["student"]), ("head.", want["grads"]["student_head"])):
+        for k, g in gd.items():
+            if not _cancelled(k):
+                flat_m.append(eng.G[prefix + k].detach().cpu().double().flatten())
+                flat_w.append(g.double().flatten())
+    fm, fw = torch.cat(flat_m), torch.cat(flat_w)
+    cos = float((fm @ fw) / (fm.norm() * fw.norm()))
+    print(kind, "bf16 step: loss", total, float(want["loss"]), "cosine(grad, oracle grad)", cos)
+    assert cos > 0.97, cos
+
+
+def _step_vs_oracle_and_reference(fx, mode, kind, ref_rtol=(3e-4, 1.2e-2), ref_loss1=2e-5, flip_floor=0.0):
+    """flip_floor (the simple family's 3x3 stacks on 112x112 inputs): with 24 x 32 x 56^2 = 2.4 M first-layer pooling windows per
+    step, a different-but-valid fp32 summation order flips O(1) near-tie max-pool arg-maxes, and ONE flip moves a gradient term to
+    the neighbouring pixel: that changes the (heavily cancelling) conv weight gradient of its channel by ~2e-3 of the tensor's
+    maximum, more for the layers above it.  The ORACLE run in fp64 differs from the oracle run in fp32 by 2e-3 .. 3e-2 on exactly
+    those tensors and by 1e-6 on all others (measured).  The conv-stack tensors are therefore held to flip_floor, every other
+    tensor (encoder linears, gates, attention, fusion, heads) to 1e-3 (what separates the oracle from the reference itself on the
+    two-path encoder-linear gradients of the non-default modes at B = 4, tests/test_oracle_golden.py); the convolution kernels of these geometries are
+    checked tightly on their own, with the pooling decisions fixed (tests/test_kernels_gpu.py::test_conv_block_fwd_bwd)."""
+    B = fx["B"]
+    st = R.CentralDinoState(seed=fx["seed"], mode=mode, kind=kind)
+    eng = DinoStepEngine(kind=kind, mode=mode, device=DEV, precision="fp32")
     _load_state(eng, st)
     for it, rec in enumerate(fx["steps"]):
         if it > 0:
@@ -195,23 +250,29 @@ def test_step_vs_oracle_and_reference(mode, golden):
         torch.cuda.synchronize()
         total = float(loss[3])
         assert abs(total - float(want["loss"])) < 1e-5 * max(1.0, abs(float(want["loss"]))), (mode, it, total, float(want["loss"]))
-        assert abs(total - rec["loss"]) < 2e-5 * max(1.0, abs(rec["loss"])), (mode, it, total, rec["loss"])     # the reference itself
+        assert abs(total - rec["loss"]) < (2e-5 if it == 0 else ref_loss1) * max(1.0, abs(rec["loss"])), (mode, it, total, rec["loss"])     # the reference itself
         # outputs
         assert _rel(eng._ws[B]["s.proj"].view(6, B, -1), want["student_out"]) < 2e-5
         # gradients: vs the oracle at 3e-4 in every step; vs the reference golden 3e-4 (step 0) / 1.2e-2 (step 1, see docstring)
-        gtol, rtol = 3e-4, (3e-4 if it == 0 else 1.2e-2)
-        groups = [("enc.", want["grads"]["student"], "model.student."), ("head.", want["grads"]["student_head"], "model.student_projection.")]
+        gtol, rtol = (3e-4 if flip_floor == 0.0 else 1e-3), ref_rtol[min(it, 1)]
+        noise = max(1e-3, 1e-5 * max(v["abs_sum"] for v in rec["grads"].values()))        # exactly-cancelled biases: rounding noise
+        groups = [("enc.", "student", "model.student."), ("head.", "student_head", "model.student_projection.")]
         if mode != "default":
             nm = ("image_classifier", "audio_classifier") if mode == "semi_supervised" else ("image_projection_head", "audio_projection_head")
-            groups += [("aux_image.", want["grads"]["image"], f"model.{nm[0]}."), ("aux_audio.", want["grads"]["audio"], f"model.{nm[1]}.")]
-        for prefix, gd, refprefix in groups:
-            for k, g in gd.items():
+            groups += [("aux_image.", "image", f"model.{nm[0]}."), ("aux_audio.", "audio", f"model.{nm[1]}.")]
+        for prefix, gname, refprefix in groups:
+            for k, g in want["grads"][gname].items():
                 mine = eng.G[prefix + k]
                 if _cancelled(k):
-                    assert float(mine.abs().sum()) < 1e-3, (k, float(mine.abs().sum()))
+                    assert float(mine.abs().sum()) < noise, (k, float(mine.abs().sum()))
                     continue
-                assert _rel(mine, g) < gtol, (mode, it, k, _rel(mine, g))
-                ok, why = summaries_close(summarize(mine), rec["grads"][refprefix + k], rtol, 1e-7 if it == 0 else 1e-6)
+                cond = flip_floor if (gname == "student" and k.split(".")[0] in ("image_encoder", "audio_encoder") and not k.endswith(("14.weight", "14.bias", "18.weight", "18.bias"))) else 0.0
+                if mode != "default" and k in ("image_encoder.14.bias", "audio_encoder.18.bias"):
+                    # the mode head's BatchNorm1d cancels this bias on the extra pass: that part of its gradient is rounding noise
+                    # of the (InfoNCE: 1 / 0.07 times larger) side-loss gradients on top of the DINO part
+                    cond = max(cond, 1e-2)
+                assert _rel(mine, g) < max(gtol, cond), (mode, it, k, _rel(mine, g), cond)
+                ok, why = summaries_close(summarize(mine), rec["grads"][refprefix + k], max(rtol, cond), 1e-7 if it == 0 else 1e-6)
                 assert ok, (mode, it, k, why)
         # EMA (before the optimizer) and Adam
         eng.update_teacher()
@@ -227,10 +288,11 @@ def test_step_vs_oracle_and_reference(mode, golden):
             # BatchNorm-cancelled biases) may differ by up to 2*lr; everything else must agree to fp32 rounding
             assert float(diff.max()) <= 2.5e-4, ("student after adam (max)", k, float(diff.max()))
             if not _cancelled(k):
-                assert float(diff.mean()) <= 2e-7, ("student after adam (mean)", k, float(diff.mean()))
+                # (flip_floor: a relative gradient error c moves Adam's ~lr-sized step by ~c * lr)
+                assert float(diff.mean()) <= max(2e-7, 2e-4 * flip_floor), ("student after adam (mean)", k, float(diff.mean()))
         # centre and BatchNorm running statistics
         assert _rel(eng.center, st.center) < 1e-5
-        for k in ("image_encoder.0.bn1", "image_encoder.0.bn2", "audio_encoder.0.bn1", "audio_encoder.0.bn4"):
+        for k in R.encoder_bn_names(kind):
             assert _rel(eng.bn_s["enc." + k].running_mean, st.student_buf[k + ".running_mean"]) < 1e-5, k
             assert _rel(eng.bn_s["enc." + k].running_var, st.student_buf[k + ".running_var"]) < 1e-5, k
             assert _rel(eng.bn_t["enc." + k].running_var, st.teacher_buf[k + ".running_var"]) < 1e-5, k
