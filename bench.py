@@ -180,8 +180,10 @@ REF_SAMPLE_BATCH = 64        # the CPU arm steps on a fixed 64-sample slice of t
 def workload_config(args, world):
     """The `config` object of the JSON line -- identical for our arm and the reference arm."""
     B = per_gpu_batch(args, world)
-    if args.kind == "multi_central":
+    if args.kind.startswith("multi"):
         wl = WORKLOAD if args.mode == "default" else WORKLOAD.replace("default mode", args.mode + " mode")
+        if args.kind != "multi_central":            # the 3x3 conv encoders of SURVEY 8f-4 (models/dino.py:214-263, 385-452)
+            wl = wl.replace("multi_central", args.kind)
     else:
         wl = "image_simple unimodal DINO step (2 global + 4 local views of 28x28 images, O=256, P=128)"
     return {"workload": wl, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
@@ -387,6 +389,20 @@ def step_work(kind, mode, B):
         enc, act_elems, aug = 39_770_624, 219_648, 373_184
         n_ema, n_adam = 6_600_580, 1_728_368
         raw_pass = 39_770_624 - 196_608                      # conv stacks + encoder linears, no fusion
+    elif kind.startswith("multi"):
+        # SimpleMultiModalEncoder family (models/dino.py:18-73, 214-234): image 3 x conv3x3 (1->32->64->128 @28/14/7) + Linear(128,E),
+        # audio 4 x conv3x3 (1->32->64->128->256 @112/56/28/14) + Linear(256,E), fusion 2E->E->O; cross attention adds 6 E^2 MACs of
+        # projections and 4 B E MACs of batch-wide attention per row
+        img = 9 * (28 * 28 * 32 + 14 * 14 * 64 * 32 + 7 * 7 * 128 * 64) + 128 * 256
+        aud = 9 * (112 * 112 * 32 + 56 * 56 * 64 * 32 + 28 * 28 * 128 * 64 + 14 * 14 * 256 * 128) + 256 * 256
+        raw_pass = img + aud
+        enc = raw_pass + 196_608 + (6 * 256 * 256 + 4 * B * 256 if kind == "multi_cross_attention" else 0)
+        act_elems = (32 * 784 + 64 * 196 + 128 * 49) + (32 * 12544 + 64 * 3136 + 128 * 784 + 256 * 196)
+        aug = 373_184
+        import numpy as np
+        from multimodal_ssl_avmnist_b200.engine import MULTI_KINDS, head_params, simple_multi_params
+        n_adam = sum(int(np.prod(sh)) if sh else 1 for _, sh in simple_multi_params(256, 256, MULTI_KINDS[kind])[0] + head_params(256, 128))
+        n_ema = n_adam
     else:
         enc = 225_792 + 3_612_672 + 3_612_672 + 128 * 512 + 512 * 256       # 3 x conv3x3 + Linear(128,512) + Linear(512,256)
         act_elems, aug = 32 * 28 * 28 + 64 * 14 * 14 + 128 * 7 * 7, 21_952
@@ -482,11 +498,11 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     B = per_gpu_batch(args, world)
-    eng = DinoStepEngine(kind=args.kind, mode=args.mode, augment_values=augment_values() if args.kind == "multi_central" else None,
+    eng = DinoStepEngine(kind=args.kind, mode=args.mode, augment_values=augment_values() if args.kind.startswith("multi") else None,
                          seed=1 + rank, device=dev, fused_pool=not args.no_fused_pool, fused_bnstat=args.fused_bnstat)
     g = torch.Generator().manual_seed(1 + rank)
     img_h = torch.rand(B, 28, 28, generator=g).pin_memory()
-    aud_h = torch.randint(0, 256, (B, 112, 112), generator=g, dtype=torch.uint8).pin_memory() if args.kind == "multi_central" else None
+    aud_h = torch.randint(0, 256, (B, 112, 112), generator=g, dtype=torch.uint8).pin_memory() if args.kind.startswith("multi") else None
     img_d, aud_d = img_h.to(dev), (aud_h.to(dev) if aud_h is not None else None)
     lab_h = torch.randint(0, 10, (B,), generator=g).pin_memory() if args.mode == "semi_supervised" else None
     lab_d = lab_h.to(dev) if lab_h is not None else None
@@ -713,8 +729,9 @@ def main():
     ap.add_argument("--graph", action="store_true",
                     help="replay the whole step from one CUDA graph (meant for small per-GPU batches, where the ~165 host-side "
                          "launches bound the step; with N > 1 the all-reduces are captured too)")
-    ap.add_argument("--kind", default="multi_central", choices=["multi_central", "image_simple"],
-                    help="image_simple = BASELINE.json configs[0] (unimodal image DINO); the headline line is multi_central")
+    ap.add_argument("--kind", default="multi_central", choices=["multi_central", "image_simple", "multi_simple", "multi_simple_gated", "multi_cross_attention"],
+                    help="image_simple = BASELINE.json configs[0] (unimodal image DINO); multi_simple* / multi_cross_attention = the 3x3 conv "
+                         "encoders of SURVEY 8f-4; the headline line is multi_central")
     ap.add_argument("--mode", default="default", choices=["default", "semi_supervised", "infonce", "mse"],
                     help="training mode (BASELINE.json configs 2-5); the headline line is --mode default")
     args = ap.parse_args()
