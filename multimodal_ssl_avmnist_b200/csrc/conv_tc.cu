@@ -86,9 +86,19 @@ struct TMaps {
     CUtensorMap m[4];                                           // one per x phase (residue of the global column)
 };
 
-template <int CIN_, int COUT_, int NPAD_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int CTAS_ = 1, int NSPLIT_ = 1>
+constexpr int nbuf_chunked(int tiles, int npadl, int ctas) {     // K-chunked instances: every tile of an item owns a stage until the last chunk
+    int m = 512 / (ctas * npadl * tiles);
+    while (m > 1 && m * tiles > 8) --m;
+    return (m < 1 ? 1 : m) * tiles;
+}
+
+template <int CIN_, int COUT_, int NPAD_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int CTAS_ = 1, int NSPLIT_ = 1, int KCH_ = 1>
 struct TcCfg {
     static constexpr int NSPLIT = NSPLIT_;                      // output channels split over gridDim.z (halves the smem weight image)
+    // K chunking (wide layers, SURVEY 8f-4's 3x3 stacks up to 256 channels): the input channel planes of an item arrive in KCH
+    // slots of P / KCH planes each; the weights stay resident, the accumulators of ALL tiles of the item live in TMEM until the
+    // last chunk has been multiplied in (chunk-outer, tile-inner MMA order)
+    static constexpr int KCH = KCH_;
     // First layers (C_in = 1) read the "quad8" image: unit (y, xq) = the 8 padded-row pixels 4*xq .. 4*xq+7, which are exactly
     // the taps kw' = ph + kw < 8 of the four output phases -- only that one plane exists (no other phase planes to load)
     static constexpr int XPH = CIN_ == 1 ? 4 : xph_for(CIN_, COUT_, KS_);       // output x phases packed into N
@@ -113,10 +123,12 @@ struct TcCfg {
     static constexpr int Q = (HB - 1) * WQ + WOQ;               // flat tile rows per band (incl. junk columns)
     static constexpr int TILES = (Q + 127) / 128;
     static constexpr int PLANE_BYTES = HPB * WQ * 16;           // one (x phase, channel plane)
-    static constexpr int PHASE_BYTES = round_up(P * PLANE_BYTES, 128);   // stride of a phase-plane group: TMA destinations are 128-byte aligned
+    static constexpr int PC = P / KCH;                          // channel planes per slot
+    static constexpr int PHASE_BYTES = round_up(PC * PLANE_BYTES, 128);  // stride of a phase-plane group: TMA destinations are 128-byte aligned
     static constexpr int SLOT_BYTES = round_up(XPL * PHASE_BYTES, 128);
     static constexpr int NJ = (KWX + 1) / 2;                    // kw' pairs when CIN == 8
     static constexpr int PH = P / 2;                            // plane pairs when CIN >= 16
+    static constexpr int PHC = PC / 2;                          //   ... per slot
     static constexpr int NMMA = L0 ? (KS + 1) / 2 : (CIN == 8) ? KS * NJ : KS * KWX * PH;
     static constexpr int W_BYTES = round_up(NMMA * NPADL * 32, 128);
     static constexpr int MAXPIX = TILES * 128 + (L0 ? KS : KS - 1) * WQ + (KWX - 1) / XPH + 2;   // exclusive bound of units a tile may touch
@@ -141,13 +153,17 @@ struct TcCfg {
     static constexpr int POOL_OFF = round_up(SIGN_OFF + NPADL * 2, 16);
     static constexpr int SMEM = POOL_OFF + POOL_BYTES;           // the pooling instance
     static constexpr int SMEM_NOPOOL = SIGN_OFF + NPADL * 4;     // bias / beta [NPADL] + 1 / gamma [NPADL] (BSTAT instances)
-    static constexpr int NBUF = nbuf_for(NPADL, CTAS);          // TMEM accumulator stages
+    static constexpr int NBUF = KCH > 1 ? nbuf_chunked(TILES, NPADL, CTAS) : nbuf_for(NPADL, CTAS);          // TMEM accumulator stages
+    static_assert(KCH == 1 || (CIN >= 16 && P % KCH == 0 && PC % 2 == 0 && NBUF % TILES == 0 && NBUF * NPADL * CTAS <= 512), "K chunking");
     static constexpr int TMEM_COLS = pow2_cols(NBUF * NPADL);
     // One issuing thread sustains only ~1 UMMA per 140 cycles at these tile shapes (measured, tools/umma_probe.cu); four
     // concurrent issue streams per SM -- CTAs or warps -- reach the shared-memory operand bandwidth (39-48 cycles per UMMA).
     static constexpr int ISS = CTAS >= 3 ? 1 : (CTAS == 2 ? 2 : 4);     // MMA-issuer warps per CTA
     static constexpr int THREADS = 32 * (1 + ISS + 4);
-    static_assert(NBUF % ISS == 0, "a TMEM stage must always be filled by the same issuer");
+    // buffer (k * TILES + t) % NBUF must always meet the issuer t % ISS: an issuer that met a buffer only every other use could run two
+    // mbarrier phases ahead and pass a parity wait on the stale phase (seen with TILES = 13, ISS = NBUF = 2)
+    static_assert(TILES % ISS == 0 || NBUF % TILES == 0, "a TMEM stage must always be filled by the same issuer");
+    static_assert(KCH > 1 || NBUF % ISS == 0, "a TMEM stage must always be filled by the same issuer");     // (chunked: NBUF % TILES == 0 gives the same)
     static_assert(TMEM_COLS * CTAS <= 512, "TMEM columns per SM");
     static_assert((SMEM_EST(NMMA, NPADL, SLOTS, SLOT_BYTES, TAIL) + POOL_BYTES + NPADL * 2 + 16 + 1024) * CTAS <= 227 * 1024, "shared memory per SM");
     static_assert(2 * SLOTS + 2 * NBUF <= 24, "barrier area");
@@ -273,17 +289,20 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
         // ===== TMA producer =====
         if (lane == 0) {
             for (int i = i0; i < i1; ++i) {
-                const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
-                mbar_wait(empty_bar(slot), (use & 1) ^ 1);
-                mbar_expect_tx(full_bar(slot), C::XPL * C::P * C::PLANE_BYTES);
                 const int n = view * n_per_view + i / C::BANDS, band = i % C::BANDS;
+#pragma unroll 1
+                for (int c = 0; c < C::KCH; ++c) {                  // one slot per channel chunk (KCH == 1: the whole item)
+                    const int k = (i - i0) * C::KCH + c, slot = k % C::SLOTS, use = k / C::SLOTS;
+                    mbar_wait(empty_bar(slot), (use & 1) ^ 1);
+                    mbar_expect_tx(full_bar(slot), C::XPL * C::PC * C::PLANE_BYTES);
 #pragma unroll
-                for (int rp = 0; rp < C::XPL; ++rp) {
-                    // phase plane rp holds the padded columns x' = XPH*i + rp, i.e. the global columns x' - PAD = XPH*(i + a) + r
-                    constexpr int X = C::XPH;
-                    const int r = ((rp - C::PAD) % X + X) % X, a = (rp - C::PAD - r) / X;
-                    tma_load_4d(img_addr + slot * C::SLOT_BYTES + rp * C::PHASE_BYTES, &tmaps.m[r], full_bar(slot), 0, C::L0 ? 0 : a,
-                                band * C::HB - C::PAD, n * C::P);
+                    for (int rp = 0; rp < C::XPL; ++rp) {
+                        // phase plane rp holds the padded columns x' = XPH*i + rp, i.e. the global columns x' - PAD = XPH*(i + a) + r
+                        constexpr int X = C::XPH;
+                        const int r = ((rp - C::PAD) % X + X) % X, a = (rp - C::PAD - r) / X;
+                        tma_load_4d(img_addr + slot * C::SLOT_BYTES + rp * C::PHASE_BYTES, &tmaps.m[r], full_bar(slot), 0, C::L0 ? 0 : a,
+                                    band * C::HB - C::PAD, n * C::P + c * C::PC);
+                    }
                 }
             }
         }
@@ -292,15 +311,19 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
         if (lane == 0) {
             constexpr uint32_t idesc = idesc_bf16(C::NPADL);
             for (int i = i0; i < i1; ++i) {
-                const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
+#pragma unroll 1
+              for (int c = 0; c < C::KCH; ++c) {
+                const int k = (i - i0) * C::KCH + c, slot = k % C::SLOTS, use = k / C::SLOTS;
                 mbar_wait(full_bar(slot), use & 1);
                 tc_fence_after_sync();
                 const uint32_t slot_addr = img_addr + slot * C::SLOT_BYTES;
                 for (int t = warp - 1; t < C::TILES; t += C::ISS) {
-                    const uint32_t tcount = (uint32_t)k * C::TILES + t;
+                    const uint32_t tcount = (uint32_t)(i - i0) * C::TILES + t;
                     const uint32_t buf = tcount % C::NBUF, u = tcount / C::NBUF;
-                    mbar_wait(tempty_bar(buf), (u & 1) ^ 1);
-                    tc_fence_after_sync();
+                    if (c == 0) {
+                        mbar_wait(tempty_bar(buf), (u & 1) ^ 1);
+                        tc_fence_after_sync();
+                    }
                     const uint32_t d = tmem_base + buf * C::NPADL;
                     const uint32_t a0 = slot_addr + t * 2048;
                     int idx = 0;
@@ -327,19 +350,22 @@ conv_tc_kernel(const __grid_constant__ TMaps tmaps, const uint4* __restrict__ wp
 #pragma unroll
                             for (int kw = 0; kw < C::KWX; ++kw) {
 #pragma unroll
-                                for (int pp = 0; pp < C::PH; ++pp, ++idx) {
+                                for (int pp = 0; pp < C::PHC; ++pp, ++idx) {
+                                    // weight image index of (kh, kw', plane pair c * PHC + pp); the slot holds this chunk's planes only
+                                    const int widx = (kh * C::KWX + kw) * C::PH + c * C::PHC + pp;
                                     const uint64_t ad = smem_desc(a0 + (kw % C::XPH) * C::PHASE_BYTES + (kh * C::WQ + kw / C::XPH) * 16 +
                                                                       pp * 2 * C::PLANE_BYTES, C::PLANE_BYTES, 128);
-                                    const uint64_t bd = smem_desc(w_addr + idx * C::NPADL * 32, C::NPADL * 16, 128);
-                                    mma_bf16(d, ad, bd, idesc, idx > 0);
+                                    const uint64_t bd = smem_desc(w_addr + widx * C::NPADL * 32, C::NPADL * 16, 128);
+                                    mma_bf16(d, ad, bd, idesc, (c > 0 || idx > 0) ? 1u : 0u);
                                 }
                             }
                         }
                     }
                     }
-                    mma_commit(tfull_bar(buf));
+                    if (c == C::KCH - 1) mma_commit(tfull_bar(buf));
                 }
                 mma_commit(empty_bar(slot));
+              }
             }
         }
     } else {
@@ -707,7 +733,7 @@ int launch_conv_tc(const void* x, const void* wprep, const float* bias, void* ou
     for (int r = 0; r < C::XPL; ++r) {                             // map r: the columns x = XPH*i + r of every row
         const uint64_t dims[4] = {8, WT / C::XPL, (uint64_t)C::HIN, (uint64_t)N * C::P};
         const uint64_t strides[3] = {16 * (uint64_t)C::XPL, WT * 16, WT * C::HIN * 16};
-        const uint32_t box[4] = {8, (uint32_t)C::WQ, (uint32_t)C::HPB, (uint32_t)C::P};
+        const uint32_t box[4] = {8, (uint32_t)C::WQ, (uint32_t)C::HPB, (uint32_t)C::PC};
         int rc = encode_tmap_bf16_4d(&tm.m[r], reinterpret_cast<const uint8_t*>(x) + 16 * r, dims, strides, box);
         if (rc) return rc;
     }
@@ -1516,6 +1542,12 @@ using WgA0 = TcWgCfg<1, 8, 112, 112, 5, 2, 7, 1, 1, 3>;   // first layers (shift
 using WgI0 = TcWgCfg<1, 32, 28, 28, 5, 2, 1, 3, 1>;
 using WgS0 = TcWgCfg<1, 32, 28, 28, 3, 1, 1, 3, 1>;
 using WgS2 = TcWgCfg<64, 128, 7, 7, 3, 1, 1, 3, 4, 1, 2>;
+// the 3x3 audio stack of the simple multimodal encoders (models/dino.py:43-72): input planes / dz planes split over gridDim.z
+//                  CIN COUT HIN WIN KS PAD BANDS SLOTS PSPLIT CTAS NSPLIT
+using WgB0 = TcWgCfg<1, 32, 112, 112, 3, 1, 7, 2, 1, 1, 2>;          // (unfused first-layer weight gradient: tests / fp32-dz fallback)
+using WgB1 = TcWgCfg<32, 64, 56, 56, 3, 1, 7, 2, 2>;
+using WgB2 = TcWgCfg<64, 128, 28, 28, 3, 1, 1, 2, 4, 1, 4>;
+using WgB3 = TcWgCfg<128, 256, 14, 14, 3, 1, 1, 4, 8, 1, 4>;
 
 //                         CIN COUT NPAD HIN  WIN KS PAD BANDS SLOTS
 using CfgA1 = TcCfg<8, 16, 16, 56, 56, 5, 2, 2, 2, 2>;   // audio conv2 forward (4 x phases: N = 64)
@@ -1533,6 +1565,16 @@ using CfgS2 = TcCfg<64, 128, 128, 7, 7, 3, 1, 1, 3, 2, 2>;   // image_simple con
 using CfgS2d = TcCfg<128, 64, 64, 7, 7, 3, 1, 1, 2, 1, 1>;
 using CfgS1 = TcCfg<32, 64, 64, 14, 14, 3, 1, 1, 4>;     // image_simple conv2 forward / its data gradient
 using CfgS1d = TcCfg<64, 32, 32, 14, 14, 3, 1, 1, 4>;
+// the 3x3 audio stack of the simple multimodal encoders (models/dino.py:43-72), forward / data gradient.  The wide layers keep their
+// weights resident by splitting the output channels over gridDim.z (NSPLIT) and stream the input channel planes in KCH chunks.
+//                    CIN COUT NPAD HIN WIN KS PAD BANDS SLOTS CTAS NSPLIT KCH
+using CfgB0 = TcCfg<1, 32, 32, 112, 112, 3, 1, 7, 2, 2>;             // quad8 first layer, N = 4 phases x 32 (7 bands: 4 tiles per item)
+using CfgB1 = TcCfg<32, 64, 64, 56, 56, 3, 1, 7, 2>;                 // 2 x phases: N = 128
+using CfgB1d = TcCfg<64, 32, 32, 56, 56, 3, 1, 7, 2, 1, 1, 2>;       // 2 x phases: N = 64, two chunks of 32 input channels
+using CfgB2 = TcCfg<64, 128, 128, 28, 28, 3, 1, 2, 3, 1, 2, 2>;
+using CfgB2d = TcCfg<128, 64, 64, 28, 28, 3, 1, 2, 2, 1, 1, 4>;
+using CfgB3 = TcCfg<128, 256, 256, 14, 14, 3, 1, 1, 3, 1, 4, 4>;
+using CfgB3d = TcCfg<256, 128, 128, 14, 14, 3, 1, 1, 3, 1, 4, 8>;
 
 }  // namespace
 }  // namespace b200
@@ -1545,6 +1587,7 @@ int b200_conv_tc_supported(int Cin, int Cout, int H, int W, int K, int pad) {
 #define TC_MATCH(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) return 1;
     TC_MATCH(CfgA1) TC_MATCH(CfgA2) TC_MATCH(CfgA3) TC_MATCH(CfgI1) TC_MATCH(CfgA1d) TC_MATCH(CfgA2d) TC_MATCH(CfgA3d) TC_MATCH(CfgI1d)
     TC_MATCH(CfgS1) TC_MATCH(CfgS1d) TC_MATCH(CfgA0) TC_MATCH(CfgI0) TC_MATCH(CfgS0) TC_MATCH(CfgS2) TC_MATCH(CfgS2d)
+    TC_MATCH(CfgB0) TC_MATCH(CfgB1) TC_MATCH(CfgB1d) TC_MATCH(CfgB2) TC_MATCH(CfgB2d) TC_MATCH(CfgB3) TC_MATCH(CfgB3d)
 #undef TC_MATCH
     return 0;
 }
@@ -1559,7 +1602,7 @@ int b200_conv_tc_prep_weights(const float* w, void* out, int Cin, int Cout, int 
     B200_REQUIRE(w && out, -1, "conv_tc_prep_weights: null pointer");
     B200_REQUIRE(Cin == 1 || Cin == 8 || (Cin % 16 == 0 && Cin > 0), -2, "conv_tc_prep_weights: C_in must be 1, 8 or a multiple of 16 (got %d)", Cin);
     B200_REQUIRE(!(Cin == 1 && flip), -2, "conv_tc_prep_weights: the first layer has no data gradient");
-    B200_REQUIRE(Cout % 8 == 0 && Cout > 0 && Cout <= 128, -2, "conv_tc_prep_weights: C_out must be a multiple of 8, <= 128 (got %d)", Cout);
+    B200_REQUIRE(Cout % 8 == 0 && Cout > 0 && Cout <= 256, -2, "conv_tc_prep_weights: C_out must be a multiple of 8, <= 256 (got %d)", Cout);
     const int xph = Cin == 1 ? 4 : xph_for(Cin, Cout, K);
     const int npad = (xph * Cout + 15) / 16 * 16;
     const int total = (int)(b200_conv_tc_weight_bytes(Cin, Cout, K) / 2);
@@ -1582,7 +1625,7 @@ static int wgrad_tc_dispatch(const void* x, const void* dz, float* dw, float* wo
         return launch_conv_tc_wgrad_ph<CFG>(x, dz, dw, work, N, st, need);
     WGP_RUN(WgA1) WGP_RUN(WgA2)
 #undef WGP_RUN
-    WG_RUN(WgA3) WG_RUN(WgI1) WG_RUN(WgS1) WG_RUN(WgA0) WG_RUN(WgI0) WG_RUN(WgS0) WG_RUN(WgS2)
+    WG_RUN(WgA3) WG_RUN(WgI1) WG_RUN(WgS1) WG_RUN(WgA0) WG_RUN(WgI0) WG_RUN(WgS0) WG_RUN(WgS2) WG_RUN(WgB0) WG_RUN(WgB1) WG_RUN(WgB2) WG_RUN(WgB3)
 #undef WG_RUN
     set_error("conv_tc_wgrad: unsupported geometry Cin=%d Cout=%d H=%d W=%d K=%d pad=%d", Cin, Cout, H, W, K, pad);
     return -4;
@@ -1593,13 +1636,14 @@ static int wgrad_tc_dispatch(const void* x, const void* dz, float* dw, float* wo
 using WgF_A0 = L0FCfg<8, 112, 112, 5, 2, 7, 2, 2>;
 using WgF_I0 = L0FCfg<32, 28, 28, 5, 2, 1, 2, 1>;
 using WgF_S0 = L0FCfg<32, 28, 28, 3, 1, 1, 2, 1>;
+using WgF_B0 = L0FCfg<32, 112, 112, 3, 1, 7, 1, 1>;      // simple audio stack: one 156 KB slot (x slab + 4 x 32 dz phase planes + dp tile)
 
 static int wgrad_l0_dispatch(const void* x, const void* z, const void* dp, const float* scale, const float* shift, const float* mean,
                              const float* invstd, const double* sums, float* dw, double* dbsum, float* work, int N, int n_per_view, int Cout,
                              int H, int W, int K, int pad, cudaStream_t st, int64_t* need) {
 #define WF_RUN(CFG) if (Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) \
         return launch_conv_tc_wgrad_l0_fused<CFG>(x, z, dp, scale, shift, mean, invstd, sums, dw, dbsum, work, N, n_per_view, st, need);
-    WF_RUN(WgF_A0) WF_RUN(WgF_I0) WF_RUN(WgF_S0)
+    WF_RUN(WgF_A0) WF_RUN(WgF_I0) WF_RUN(WgF_S0) WF_RUN(WgF_B0)
 #undef WF_RUN
     set_error("conv_tc_wgrad_l0_fused: unsupported geometry Cout=%d H=%d W=%d K=%d pad=%d", Cout, H, W, K, pad);
     return -4;
@@ -1671,6 +1715,7 @@ int b200_conv_tc(const void* x_act8, const void* wprep, const float* bias, void*
 #define TC_RUN(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) \
         return launch_conv_tc<CFG>(x_act8, wprep, bias, out, stats, N, n_per_view, out_bf16, st);
     TC_RUN(CfgA1) TC_RUN(CfgA2) TC_RUN(CfgA3) TC_RUN(CfgI1) TC_RUN(CfgA1d) TC_RUN(CfgA2d) TC_RUN(CfgA3d) TC_RUN(CfgI1d) TC_RUN(CfgS1) TC_RUN(CfgS1d) TC_RUN(CfgA0) TC_RUN(CfgI0) TC_RUN(CfgS0) TC_RUN(CfgS2) TC_RUN(CfgS2d)
+    TC_RUN(CfgB0) TC_RUN(CfgB1) TC_RUN(CfgB1d) TC_RUN(CfgB2) TC_RUN(CfgB2d) TC_RUN(CfgB3) TC_RUN(CfgB3d)
 #undef TC_RUN
     set_error("conv_tc: unsupported geometry Cin=%d Cout=%d H=%d W=%d K=%d pad=%d", Cin, Cout, H, W, K, pad);
     return -4;
@@ -1679,6 +1724,7 @@ int b200_conv_tc(const void* x_act8, const void* wprep, const float* bias, void*
 int b200_conv_tc_pool_supported(int Cin, int Cout, int H, int W, int K, int pad) {
 #define TC_HAS(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) return CFG::POOL_OK ? 1 : 0;
     TC_HAS(CfgA1) TC_HAS(CfgA2) TC_HAS(CfgA3) TC_HAS(CfgI1) TC_HAS(CfgS1) TC_HAS(CfgA0) TC_HAS(CfgI0) TC_HAS(CfgS0) TC_HAS(CfgS2)
+    TC_HAS(CfgB0) TC_HAS(CfgB1)
 #undef TC_HAS
     return 0;
 }
@@ -1694,6 +1740,7 @@ int b200_conv_tc_pool(const void* x_act8, const void* wprep, const float* bias, 
 #define TC_RUN(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) \
         return launch_conv_tc<CFG>(x_act8, wprep, bias, z_out, stats, N, n_per_view, z_fmt, st, pool_out, gamma);
     TC_RUN(CfgA1) TC_RUN(CfgA2) TC_RUN(CfgA3) TC_RUN(CfgI1) TC_RUN(CfgS1) TC_RUN(CfgA0) TC_RUN(CfgI0) TC_RUN(CfgS0)
+    TC_RUN(CfgB0) TC_RUN(CfgB1)
 #undef TC_RUN
     set_error("conv_tc_pool: unsupported geometry Cin=%d Cout=%d H=%d W=%d K=%d pad=%d", Cin, Cout, H, W, K, pad);
     return -4;

@@ -445,7 +445,7 @@ class DinoStepEngine:
             w[f"{m}.dz"] = e(max(sc["z"], 4))
             w[f"{m}.dz8"] = e(max(sc["z8"], 8), dtype=BF)
             w[f"{m}.dz8b"] = e(max(sc["z8"], 8), dtype=BF)      # second buffer: the weight gradient of layer l overlaps layer l-1
-            w[f"{m}.dbsum"] = zalloc(8, 128)
+            w[f"{m}.dbsum"] = zalloc(8, 256)
             w[f"{m}.dp_a"], w[f"{m}.dp_b"] = e(sc["p"]), e(sc["p"])
             w[f"{m}.wg_work"] = e(max(sc["wg"], 4))
             w[f"{m}.wg_work_b"] = e(max(sc["wg"], 4))

@@ -11,7 +11,9 @@ from multimodal_ssl_avmnist_b200 import ops
 DEV = "cuda"
 # (Cin, Cout, H, W, K, pad) forward geometries of the encoders (models/unimodal.py:129-140, 186-208; dino.py:20-30)
 FWD = [(8, 16, 56, 56, 5, 2), (16, 32, 28, 28, 5, 2), (32, 64, 14, 14, 5, 2), (32, 64, 14, 14, 5, 0), (32, 64, 14, 14, 3, 1),
-       (64, 128, 7, 7, 3, 1)]
+       (64, 128, 7, 7, 3, 1),
+       # the 3x3 audio stack of the simple multimodal encoders (models/dino.py:43-72): K-chunked / N-split instances
+       (32, 64, 56, 56, 3, 1), (64, 128, 28, 28, 3, 1), (128, 256, 14, 14, 3, 1)]
 
 
 def _bf(x):
@@ -62,7 +64,7 @@ def test_conv_tc_forward(geom, views, B):
         wv = want.view(views, B, Cout, Ho, Ho).double()
         s_want = torch.stack([wv.sum(dim=(1, 3, 4)), (wv * wv).sum(dim=(1, 3, 4))], dim=-1)
         rel = float(((stats - s_want).abs() / (s_want.abs() + 1.0)).max())
-        assert rel < 1e-5, (geom, "stats", rel)
+        assert rel < (1e-5 if Cin * K * K < 1000 else 3e-5), (geom, "stats", rel)      # fp32 per-thread partial sums; longer reductions, larger |z|
 
 
 def test_prep_weights_multi_matches_single_launches():
@@ -131,7 +133,7 @@ def test_conv_tc_weight_gradient(geom, N):
     torch.cuda.synchronize()
     scale = float(wd.grad.abs().max())
     err = float((dw.double() - wd.grad).abs().max())
-    assert err <= 3e-5 * scale, (geom, N, err, scale)
+    assert err <= (3e-5 if N * Ho * Ho < 200_000 else 6e-5) * scale, (geom, N, err, scale)       # fp32 TMEM accumulation over K = N * pixels
 
 
 def _pack8(x):
@@ -200,7 +202,7 @@ def test_bn_relu_pool8(C, H, views, B, zdt):
 
 
 # first layers (C_in = 1) on the shift8 image: (Cout, H, K, pad)
-FIRST = [(8, 112, 5, 2), (32, 28, 5, 2), (32, 28, 3, 1)]
+FIRST = [(8, 112, 5, 2), (32, 28, 5, 2), (32, 28, 3, 1), (32, 112, 3, 1)]
 
 
 @pytest.mark.parametrize("geom", FIRST)
@@ -413,7 +415,8 @@ def test_infonce_tensor_core(B, D):
         assert cos > 0.9995, cos
 
 
-POOLED = [(8, 16, 56, 5, 2), (16, 32, 28, 5, 2), (32, 64, 14, 3, 1), (1, 8, 112, 5, 2), (1, 32, 28, 5, 2), (1, 32, 28, 3, 1)]
+POOLED = [(8, 16, 56, 5, 2), (16, 32, 28, 5, 2), (32, 64, 14, 3, 1), (1, 8, 112, 5, 2), (1, 32, 28, 5, 2), (1, 32, 28, 3, 1),
+          (1, 32, 112, 3, 1), (32, 64, 56, 3, 1)]
 
 
 @pytest.mark.parametrize("geom", POOLED)
