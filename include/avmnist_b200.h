@@ -188,6 +188,10 @@ int b200_conv_tc(const void* x_act8, const void* wprep, const float* bias, void*
  * First layers (Cin = 1): b200_conv_tc takes the "quad8" image (b200_pack_quad8); the stand-alone b200_conv_tc_wgrad takes the
  * "shift8" image bf16 [N][H][W+pad][8] written by b200_pack_shift8 (unit (y,xs) = x[y][xs-pad .. xs-pad+7], zero outside the
  * row) -- the training step uses b200_conv_tc_wgrad_l0_fused (quad8) instead. */
+/* Selects the weight-gradient formulation of the wide 3x3 layers: 1 (default) = one TMEM accumulator per filter tap, 0 = the
+ * shift-row kernel everywhere (A/B measurements; the work size depends on it: query b200_conv_tc_wgrad_work_floats afterwards).
+ * Any other value only queries.  Returns the previous setting. */
+int b200_conv_tc_wgrad_variant(int tap);
 int64_t b200_conv_tc_wgrad_work_floats(int N, int Cin, int Cout, int H, int W, int K, int pad);
 int b200_conv_tc_wgrad(const void* x_act8, const void* dz_act8, float* dw, float* work, int N, int Cin, int Cout, int H,
                        int W, int K, int pad, void* stream);

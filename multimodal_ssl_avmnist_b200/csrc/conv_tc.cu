@@ -994,6 +994,194 @@ int launch_conv_tc_wgrad(const void* x, const void* dz, float* dw, float* work, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Weight gradient, one accumulator per filter TAP (wide 3x3 layers of the simple encoders, models/dino.py:20-66).  The
+// (8 pixel shifts x 8 channels) M rows of conv_tc_wgrad_kernel use K of 8 shifts: a 3x3 filter wastes 5/8 of every MMA.
+// Here the operand roles are swapped and the tap is a start-address shift of the x operand:
+//   A (M = 64 / 128 output channels): the dz image, MN-major, M units = channel planes (SBO = plane stride);
+//   B (N = 8 * PI input channels):    the x slab, MN-major, N units = channel planes, start moved by (kh*WP + kw) pixels;
+//   D_tap[co][ci] += sum over K = flat padded pixel index   =>   dW[co][ci][kh][kw] = D_(kh,kw)[co][ci]
+// -- every MMA row and column is a real weight.  KS*KS accumulators of N columns live in TMEM for the whole kernel (9 x 32 = 288
+// columns).  dz is loaded PLANE BY PLANE (one TMA each) at a plane stride rounded up to whole K steps, and the gap stays zero, so
+// that row bands need no alignment between HB*WP and the K step (the x positions a gap multiplies are finite bf16 values of the slot).
+template <int CIN_, int COUT_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int PSPLIT_, int NSPLIT_, int ISS_ = 3>
+struct TapWgCfg {
+    static constexpr int CIN = CIN_, COUT = COUT_, HIN = HIN_, WIN = WIN_, KS = KS_, PAD = PAD_, BANDS = BANDS_, SLOTS = SLOTS_;
+    static constexpr int PSPLIT = PSPLIT_, NSPLIT = NSPLIT_, ISS = ISS_;
+    static constexpr int P_IN = CIN / 8, PI = P_IN / PSPLIT, P_OUT = COUT / 8, P_OUTL = P_OUT / NSPLIT;
+    static constexpr int M = P_OUTL * 8, N = PI * 8, TAPS = KS * KS;
+    static constexpr int WP = WIN + 2 * PAD, HO = HIN + 2 * PAD - KS + 1, WO = WP - KS + 1;
+    static constexpr int HB = HO / BANDS, HPB = HB + KS - 1;
+    static constexpr int KPOS = HB * WP, KSTEPS = (KPOS + 15) / 16;
+    static constexpr int PLANE_X = HPB * WP * 16, PLANE_Z = KSTEPS * 256, Z_LOAD = KPOS * 16;   // bytes; Z_LOAD = what TMA writes per dz plane
+    static constexpr int X_BYTES = round_up(PI * PLANE_X, 128), Z_BYTES = P_OUTL * PLANE_Z;
+    static constexpr int SLOT_BYTES = X_BYTES + Z_BYTES;
+    static constexpr int TMEM_COLS = pow2_cols(TAPS * N);
+    static constexpr int BAR_OFF = SLOTS * SLOT_BYTES, SMEM = BAR_OFF + 256;
+    static constexpr int THREADS = 32 * (1 + ISS + 4);
+    static constexpr int PART = COUT * CIN * KS * KS;
+    static_assert(CIN % 8 == 0 && COUT % 8 == 0 && P_IN % PSPLIT == 0 && P_OUT % NSPLIT == 0 && HO % BANDS == 0, "splits");
+    static_assert((M == 64 || M == 128) && N % 16 == 0 && N >= 16 && N <= 256 && TAPS * N <= 512, "MMA shape / TMEM columns");
+    // the last K step of the last tap reads x up to position KSTEPS*16 - 1 + (KS-1)*WP + KS-1 of a plane: past the slab it must land in dz
+    static_assert((KSTEPS * 16 + (KS - 1) * WP + KS - 1 - HPB * WP) * 16 <= Z_BYTES, "x overrun must stay inside the slot");
+    static_assert(SMEM + 1024 <= 227 * 1024 && 2 * SLOTS + 1 <= 24, "shared memory / barriers");
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1)
+conv_tc_wgrad_tap_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_z, float* __restrict__ work, int N) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);     // full[SLOTS], empty[SLOTS], done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::BAR_OFF + 200);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = gridDim.x, g = blockIdx.x, ps = blockIdx.z % C::PSPLIT, ns = blockIdx.z / C::PSPLIT;
+    const long items = (long)N * C::BANDS;
+    const int i0 = (int)(items * g / G), i1 = (int)(items * (g + 1) / G);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (C::SLOTS + s); };
+    const uint32_t done_bar = bar0 + 8u * (2 * C::SLOTS);
+    {
+        uint4* z = reinterpret_cast<uint4*>(smem);                      // incl. the gaps behind the dz planes, which must stay zero
+        for (int i = threadIdx.x; i < C::BAR_OFF / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async_smem();
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        prefetch_tmap(&tmap_z);
+        for (int s = 0; s < C::SLOTS; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), C::ISS);
+        }
+        mbar_init(done_bar, C::ISS);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<C::TMEM_COLS>(smem_u32(tmem_slot));
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem0 = smem_u32(smem);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = i0; i < i1; ++i) {
+                const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
+                mbar_wait(empty_bar(slot), (use & 1) ^ 1);
+                mbar_expect_tx(full_bar(slot), C::PI * C::PLANE_X + C::P_OUTL * C::Z_LOAD);
+                const int n = i / C::BANDS, band = i % C::BANDS;
+                const uint32_t sa = smem0 + slot * C::SLOT_BYTES;
+                tma_load_4d(sa, &tmap_x, full_bar(slot), 0, -C::PAD, band * C::HB - C::PAD, n * C::P_IN + ps * C::PI);
+#pragma unroll 1
+                for (int p = 0; p < C::P_OUTL; ++p)
+                    tma_load_4d(sa + C::X_BYTES + p * C::PLANE_Z, &tmap_z, full_bar(slot), 0, 0, band * C::HB, n * C::P_OUT + ns * C::P_OUTL + p);
+            }
+        }
+    } else if (warp <= C::ISS) {
+        if (lane == 0) {                     // issuer w owns the taps t == w-1 (mod ISS)
+            constexpr uint32_t idesc = idesc_bf16(C::N, true, true, C::M);
+            for (int i = i0; i < i1; ++i) {
+                const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
+                mbar_wait(full_bar(slot), use & 1);
+                tc_fence_after_sync();
+                const uint32_t xa = smem0 + slot * C::SLOT_BYTES, za = xa + C::X_BYTES;
+#pragma unroll 1
+                for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                    const uint32_t acc = (i > i0 || ks > 0) ? 1u : 0u;
+                    const uint64_t ad = smem_desc(za + ks * 256, 128, C::PLANE_Z);
+#pragma unroll
+                    for (int t = 0; t < C::TAPS; ++t) {
+                        if (t % C::ISS != warp - 1) continue;
+                        const uint64_t bd = smem_desc(xa + (ks * 16 + (t / C::KS) * C::WP + (t % C::KS)) * 16, 128, C::PLANE_X);
+                        mma_bf16(tmem_base + t * C::N, ad, bd, idesc, acc);
+                    }
+                }
+                mma_commit(empty_bar(slot));
+            }
+            mma_commit(done_bar);
+        }
+    } else {
+        // epilogue: M = 128: lane = row of the quadrant; M = 64: rows occupy lanes 0-15 of each 32-lane quadrant
+        const int quad = warp & 3;
+        const int row = C::M == 128 ? quad * 32 + lane : quad * 16 + (lane & 15);
+        const bool rowok = C::M == 128 || lane < 16;
+        float* part = work + (long)g * C::PART;
+        if (i1 > i0) {
+            mbar_wait(done_bar, 0);
+            tc_fence_after_sync();
+        }
+        const int co = ns * C::M + row;
+#pragma unroll 1
+        for (int t = 0; t < C::TAPS; ++t) {
+#pragma unroll
+            for (int cc = 0; cc < C::N / 16; ++cc) {
+                uint32_t v[16];
+                if (i1 > i0) {
+                    tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + t * C::N + cc * 16, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0u;
+                }
+                if (rowok) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int ci = ps * C::N + cc * 16 + j;
+                        part[((long)co * C::CIN + ci) * C::TAPS + t] = __uint_as_float(v[j]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    }
+}
+
+template <class C>
+int launch_conv_tc_wgrad_tap(const void* x, const void* dz, float* dw, float* work, int N, cudaStream_t st, int64_t* need) {
+    int G = sm_count() / (C::PSPLIT * C::NSPLIT);
+    const long items = (long)N * C::BANDS;
+    if (G > items) G = (int)items;
+    if (G < 1) G = 1;
+    if (need) {
+        *need = (int64_t)G * C::PART;
+        return 0;
+    }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_tap_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) {
+            set_error("conv_tc_wgrad (tap): cannot set %d bytes of shared memory: %s", C::SMEM, cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured = true;
+    }
+    CUtensorMap tx, tz;
+    {
+        const uint64_t dims[4] = {8, (uint64_t)C::WIN, (uint64_t)C::HIN, (uint64_t)N * C::P_IN};
+        const uint64_t strides[3] = {16, (uint64_t)C::WIN * 16, (uint64_t)C::WIN * C::HIN * 16};
+        const uint32_t box[4] = {8, (uint32_t)C::WP, (uint32_t)C::HPB, (uint32_t)C::PI};
+        int rc = encode_tmap_bf16_4d(&tx, x, dims, strides, box);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[4] = {8, (uint64_t)C::WO, (uint64_t)C::HO, (uint64_t)N * C::P_OUT};
+        const uint64_t strides[3] = {16, (uint64_t)C::WO * 16, (uint64_t)C::WO * C::HO * 16};
+        const uint32_t box[4] = {8, (uint32_t)C::WP, (uint32_t)C::HB, 1};
+        int rc = encode_tmap_bf16_4d(&tz, dz, dims, strides, box);
+        if (rc) return rc;
+    }
+    conv_tc_wgrad_tap_kernel<C><<<dim3(G, 1, C::PSPLIT * C::NSPLIT), C::THREADS, C::SMEM, st>>>(tx, tz, work, N);
+    int rc = launch_status("conv_tc_wgrad_tap_kernel");
+    if (rc) return rc;
+    wgrad_reduce_kernel<<<(C::PART + 255) / 256, 256, 0, st>>>(work, G, C::PART, dw);
+    return launch_status("wgrad_reduce_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Weight gradient with output-pixel phases in N (small-channel layers, where the tensor pipe is saturated by N = 16 / 32
 // MMAs that do a fraction of its work).  K = flat index of PIXEL GROUPS (y, xq) over the pitch WQ, XPH pixels per group:
 //   B (N = XPH*C_out): dz de-interleaved by phase ph = x mod XPH (strided TMA maps), N units = (ph, channel octet) planes;
@@ -1545,9 +1733,16 @@ using WgS2 = TcWgCfg<64, 128, 7, 7, 3, 1, 1, 3, 4, 1, 2>;
 // the 3x3 audio stack of the simple multimodal encoders (models/dino.py:43-72): input planes / dz planes split over gridDim.z
 //                  CIN COUT HIN WIN KS PAD BANDS SLOTS PSPLIT CTAS NSPLIT
 using WgB0 = TcWgCfg<1, 32, 112, 112, 3, 1, 7, 2, 1, 1, 2>;          // (unfused first-layer weight gradient: tests / fp32-dz fallback)
-using WgB1 = TcWgCfg<32, 64, 56, 56, 3, 1, 7, 2, 2>;
+using WgB1 = TcWgCfg<32, 64, 56, 56, 3, 1, 7, 2, 2>;                    // (shift-row formulation, 3 of 8 M rows per plane used: kept for A/B)
 using WgB2 = TcWgCfg<64, 128, 28, 28, 3, 1, 1, 2, 4, 1, 4>;
 using WgB3 = TcWgCfg<128, 256, 14, 14, 3, 1, 1, 4, 8, 1, 4>;
+// one accumulator per tap (every MMA row / column a real weight): the wide 3x3 layers
+//                     CIN COUT HIN WIN KS PAD BANDS SLOTS PSPLIT NSPLIT
+using TapB1 = TapWgCfg<32, 64, 56, 56, 3, 1, 7, 2, 1, 1>;            // M = 64,  N = 32
+using TapB2 = TapWgCfg<64, 128, 28, 28, 3, 1, 4, 2, 2, 1>;           // M = 128, N = 32 (two input-channel halves)
+using TapB3 = TapWgCfg<128, 256, 14, 14, 3, 1, 1, 2, 4, 2>;          // M = 128, N = 32
+using TapS1 = TapWgCfg<32, 64, 14, 14, 3, 1, 1, 3, 1, 1>;            // image stack of the simple encoders / image_simple
+using TapS2 = TapWgCfg<64, 128, 7, 7, 3, 1, 1, 4, 2, 1>;
 
 //                         CIN COUT NPAD HIN  WIN KS PAD BANDS SLOTS
 using CfgA1 = TcCfg<8, 16, 16, 56, 56, 5, 2, 2, 2, 2>;   // audio conv2 forward (4 x phases: N = 64)
@@ -1617,6 +1812,8 @@ int b200_conv_tc_prep_weights_multi(const int64_t* desc_dev, int n, void* stream
     return launch_status("conv_tc_prep_weights_multi_kernel");
 }
 
+static int g_wgrad_tap = 1;      // 0: the shift-row weight gradient for every geometry (A/B measurements, b200_conv_tc_wgrad_variant)
+
 static int wgrad_tc_dispatch(const void* x, const void* dz, float* dw, float* work, int N, int Cin, int Cout, int H, int W,
                              int K, int pad, cudaStream_t st, int64_t* need) {
 #define WG_RUN(CFG) if (Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) \
@@ -1625,6 +1822,10 @@ static int wgrad_tc_dispatch(const void* x, const void* dz, float* dw, float* wo
         return launch_conv_tc_wgrad_ph<CFG>(x, dz, dw, work, N, st, need);
     WGP_RUN(WgA1) WGP_RUN(WgA2)
 #undef WGP_RUN
+#define WGT_RUN(CFG) if (g_wgrad_tap && Cin == CFG::CIN && Cout == CFG::COUT && H == CFG::HIN && W == CFG::WIN && K == CFG::KS && pad == CFG::PAD) \
+        return launch_conv_tc_wgrad_tap<CFG>(x, dz, dw, work, N, st, need);
+    WGT_RUN(TapB1) WGT_RUN(TapB2) WGT_RUN(TapB3) WGT_RUN(TapS1) WGT_RUN(TapS2)
+#undef WGT_RUN
     WG_RUN(WgA3) WG_RUN(WgI1) WG_RUN(WgS1) WG_RUN(WgA0) WG_RUN(WgI0) WG_RUN(WgS0) WG_RUN(WgS2) WG_RUN(WgB0) WG_RUN(WgB1) WG_RUN(WgB2) WG_RUN(WgB3)
 #undef WG_RUN
     set_error("conv_tc_wgrad: unsupported geometry Cin=%d Cout=%d H=%d W=%d K=%d pad=%d", Cin, Cout, H, W, K, pad);
@@ -1666,6 +1867,12 @@ int b200_conv_tc_wgrad_l0_fused(const void* x_quad8, const void* z8, const void*
                    reinterpret_cast<uintptr_t>(work)) & 15) == 0, -3, "conv_tc_wgrad_l0_fused: pointers must be 16-byte aligned");
     return wgrad_l0_dispatch(x_quad8, z8, dp8, scale, shift, mean, invstd, sums, dw, dbsum, work, N, n_per_view, Cout, H, W, K, pad,
                              as_stream(stream), nullptr);
+}
+
+int b200_conv_tc_wgrad_variant(int tap) {
+    const int old = g_wgrad_tap;
+    if (tap == 0 || tap == 1) g_wgrad_tap = tap;
+    return old;
 }
 
 int64_t b200_conv_tc_wgrad_work_floats(int N, int Cin, int Cout, int H, int W, int K, int pad) {

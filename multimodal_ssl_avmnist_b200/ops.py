@@ -339,6 +339,12 @@ def conv_tc_prep_weights_multi(desc):
     _lib.check(_lib_().b200_conv_tc_prep_weights_multi(_ptr(desc, torch.int64), desc.shape[0], _stream()), "conv_tc_prep_weights_multi")
 
 
+def conv_tc_wgrad_variant(tap=-1):
+    """1: one TMEM accumulator per filter tap for the wide 3x3 layers (default), 0: the shift-row kernel everywhere (A/B); -1 queries.
+    Returns the previous setting.  Work sizes depend on it."""
+    return int(_lib_().b200_conv_tc_wgrad_variant(tap))
+
+
 def conv_tc_wgrad_work_floats(N, Cin, Cout, H, W, K, pad):
     n = int(_lib_().b200_conv_tc_wgrad_work_floats(N, Cin, Cout, H, W, K, pad))
     if n < 0:
@@ -640,7 +646,7 @@ def knn_predict(train_feats, train_labels, test_feats, k=5, n_classes=10, return
 # ---- launch accounting and optional per-op timing ------------------------------------------------------------
 # Every wrapper above issues a fixed number of kernel launches; the table lists the ones that issue more than one.
 _LAUNCHES = {"gate_grad": 2, "ntxent_fwd_bwd": 5, "conv_tc_wgrad_l0_fused": 3, "conv_tc_wgrad": 2, "conv_bwd_weight": 3, "linear_bwd_weight": 3, "infonce_fwd_bwd": 9}
-_NOT_KERNELS = {"gate_grad_work_floats", "knn_predict", "conv_tc_pool_supported", "conv_tc_dgrad_bnstat_supported", "quad8_width", "ntxent_work_floats", "conv_tc_wgrad_l0_fused_work_floats", "conv_tc_wgrad_work_floats", "conv_tc_supported", "conv_tc_weight_bytes", "dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
+_NOT_KERNELS = {"conv_tc_wgrad_variant", "gate_grad_work_floats", "knn_predict", "conv_tc_pool_supported", "conv_tc_dgrad_bnstat_supported", "quad8_width", "ntxent_work_floats", "conv_tc_wgrad_l0_fused_work_floats", "conv_tc_wgrad_work_floats", "conv_tc_supported", "conv_tc_weight_bytes", "dino_loss_parts", "infonce_work_floats", "conv_supported", "conv_bwd_weight_work_floats", "launch_count", "start_profile", "stop_profile"}
 LAUNCH_COUNT = 0
 _PROFILE = None          # None, or a list receiving (name, start_event, end_event, meta)
 

@@ -112,8 +112,21 @@ def test_conv_tc_data_gradient(geom):
 
 @pytest.mark.parametrize("geom", FWD)
 @pytest.mark.parametrize("N", [1, 7, 300])
-def test_conv_tc_weight_gradient(geom, N):
-    """dW, db against autograd in fp64 on the same bf16-rounded x and dz (K = N*pixels, fp32 accumulate in TMEM)."""
+@pytest.mark.parametrize("variant", [1, 0])
+def test_conv_tc_weight_gradient(geom, N, variant):
+    """dW, db against autograd in fp64 on the same bf16-rounded x and dz (K = N*pixels, fp32 accumulate in TMEM).  variant 1 = the
+    per-tap accumulators of the wide 3x3 layers, 0 = the shift-row kernel for every geometry."""
+    Cin, Cout, H, W, K, pad = geom
+    if variant == 0 and K != 3:
+        pytest.skip("only the 3x3 layers have two formulations")
+    old = ops.conv_tc_wgrad_variant(variant)
+    try:
+        _weight_gradient_case(geom, N)
+    finally:
+        ops.conv_tc_wgrad_variant(old)
+
+
+def _weight_gradient_case(geom, N):
     Cin, Cout, H, W, K, pad = geom
     Ho = H + 2 * pad - K + 1
     g = torch.Generator().manual_seed(11 + Cin + N)
