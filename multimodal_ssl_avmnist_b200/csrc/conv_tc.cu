@@ -1399,34 +1399,37 @@ int launch_conv_tc_wgrad_ph(const void* x, const void* dz, float* dw, float* wor
 // planes was measured slower -- 0.73 ms with one CTA and 8 transform warps, 0.83 ms with two CTAs, against 0.55 ms -- and removed.)
 constexpr int L0F_ISS = 3;                       // MMA-issuer warps (K steps interleaved, one TMEM accumulator each)
 
-template <int COUT_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int CTAS_>
+template <int COUT_, int HIN_, int WIN_, int KS_, int PAD_, int BANDS_, int SLOTS_, int CTAS_, int NSPLIT_ = 1>
 struct L0FCfg {
     static constexpr int COUT = COUT_, HIN = HIN_, WIN = WIN_, KS = KS_, PAD = PAD_, BANDS = BANDS_, SLOTS = SLOTS_, CTAS = CTAS_;
+    // output channels split over gridDim.z (32 channels at 112x112: the four dz phase-plane groups of all channels are 119 KB; two
+    // 16-channel CTAs per SM double the transform warps and interleave their load / transform / MMA phases)
+    static constexpr int NSPLIT = NSPLIT_, COUTL = COUT / NSPLIT;
     static constexpr int TW = 4;                                                 // transform warps
     static constexpr int THREADS = 32 * (1 + L0F_ISS + TW);
-    static constexpr int P_OUT = COUT / 8, NTOT = 4 * COUT;
+    static constexpr int P_OUT = COUT / 8, P_OUTL = COUTL / 8, NTOT = 4 * COUTL;
     static constexpr int WP = WIN + 2 * PAD, WQ = (WP + 3) / 4;                  // quad8 units per row
     static constexpr int HO = HIN + 2 * PAD - KS + 1, WO = WP - KS + 1;
     static constexpr int HB = HO / BANDS, HPB = HB + KS - 1, HBZ = hbz_for(HB, WQ);
     static constexpr int KSTEPS = HBZ * WQ / 16;
     static constexpr int PLANE_X = HPB * WQ * 16, PLANE_Z = HBZ * WQ * 16;       // x slab; one (phase, octet) dz plane
-    static constexpr int X_BYTES = round_up(PLANE_X, 128), Z_BYTES = round_up(4 * P_OUT * PLANE_Z, 128);
+    static constexpr int X_BYTES = round_up(PLANE_X, 128), Z_BYTES = round_up(4 * P_OUTL * PLANE_Z, 128);
     static constexpr int HBP = HB / 2, WOP = WO / 2;                             // pooled rows / columns of a band
-    static constexpr int G_BYTES = round_up(P_OUT * HBP * WOP * 16, 128);
+    static constexpr int G_BYTES = round_up(P_OUTL * HBP * WOP * 16, 128);
     static constexpr int SLOT = X_BYTES + Z_BYTES + G_BYTES;
-    static constexpr int STAGE_BYTES = 4 * COUT * KS * KS * 4;                   // end-of-kernel staging of the phase terms
-    static constexpr int CST_OFF = SLOTS * SLOT, BAR_OFF = CST_OFF + COUT * 16 + TW * COUT * 4;
+    static constexpr int STAGE_BYTES = 4 * COUTL * KS * KS * 4;                   // end-of-kernel staging of the phase terms
+    static constexpr int CST_OFF = SLOTS * SLOT, BAR_OFF = CST_OFF + COUTL * 16 + TW * COUTL * 4;
     static constexpr int SMEM = BAR_OFF + 256;
     static constexpr int ACC_COLS = round_up(NTOT, 32), TCOLS = pow2_cols(L0F_ISS * ACC_COLS);
-    static constexpr int PART = COUT * KS * KS;
-    static_assert(HO == HIN && WO == WIN && HO % BANDS == 0 && HB % 2 == 0 && WO % 4 == 0 && COUT % 8 == 0, "geometry");
+    static constexpr int PART = COUT * KS * KS, PARTL = COUTL * KS * KS;
+    static_assert(HO == HIN && WO == WIN && HO % BANDS == 0 && HB % 2 == 0 && WO % 4 == 0 && COUT % (8 * NSPLIT) == 0, "geometry");
     static_assert(KS + 3 <= 8, "all taps of all phases must lie inside one 8-pixel unit");
     static_assert(BANDS == 1 || HBZ == HB, "row bands need HB*WQ to be a multiple of 16");
     static_assert(TCOLS * CTAS <= 512 && NTOT <= 256 && NTOT % 16 == 0, "TMEM columns / N");
     static_assert((SMEM + 1024) * CTAS <= 227 * 1024, "shared memory per SM");
     static_assert(STAGE_BYTES <= SLOT, "staging reuses the first slot");
     static_assert((KSTEPS * 16 + 7 * WQ + 8 - HPB * WQ) * 16 <= Z_BYTES, "x overrun must stay inside the slot");
-    static_assert((P_OUT * PLANE_Z) % 128 == 0, "TMA destinations (phase planes) must be 128-byte aligned");
+    static_assert((P_OUTL * PLANE_Z) % 128 == 0, "TMA destinations (phase planes) must be 128-byte aligned");
     static_assert(KSTEPS >= L0F_ISS, "every issuer needs a K step");
 };
 
@@ -1438,11 +1441,11 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
     constexpr int HBP = C::HBP, WOP = C::WOP, SLOT = C::SLOT;
     extern __shared__ __align__(1024) uint8_t smem[];
     float4* cst_s = reinterpret_cast<float4*>(smem + C::CST_OFF);
-    float* db_s = reinterpret_cast<float*>(smem + C::CST_OFF + C::COUT * 16);
+    float* db_s = reinterpret_cast<float*>(smem + C::CST_OFF + C::COUTL * 16);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);     // full[S], ready[S], empty[S], done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::BAR_OFF + 200);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int G = gridDim.x, g = blockIdx.x;
+    const int G = gridDim.x, g = blockIdx.x, ns = blockIdx.z;
     const long items = (long)N * C::BANDS;
     const int i0 = (int)(items * g / G), i1 = (int)(items * (g + 1) / G);
     const uint32_t bar0 = smem_u32(bars);
@@ -1453,7 +1456,7 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
     {
         uint4* z = reinterpret_cast<uint4*>(smem);
         for (int i = threadIdx.x; i < C::CST_OFF / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
-        for (int i = threadIdx.x; i < C::TW * C::COUT; i += blockDim.x) db_s[i] = 0.f;   // [transform warp][channel]
+        for (int i = threadIdx.x; i < C::TW * C::COUTL; i += blockDim.x) db_s[i] = 0.f;   // [transform warp][channel]
         fence_proxy_async_smem();
     }
     if (warp == 0 && lane == 0) {
@@ -1480,14 +1483,14 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
             for (int i = i0; i < i1; ++i) {
                 const int k = i - i0, slot = k % C::SLOTS, use = k / C::SLOTS;
                 mbar_wait(empty_bar(slot), (use & 1) ^ 1);
-                mbar_expect_tx(full_bar(slot), C::PLANE_X + 4 * C::P_OUT * C::PLANE_Z + C::P_OUT * HBP * WOP * 16);
+                mbar_expect_tx(full_bar(slot), C::PLANE_X + 4 * C::P_OUTL * C::PLANE_Z + C::P_OUTL * HBP * WOP * 16);
                 const int n = i / C::BANDS, band = i % C::BANDS;
                 const uint32_t sa = smem0 + slot * SLOT;
                 tma_load_4d(sa, &tmap_x, full_bar(slot), 0, 0, band * C::HB - C::PAD, n);
 #pragma unroll
                 for (int ph = 0; ph < 4; ++ph)      // columns x = 4*xq + ph of every z row -> plane group ph
-                    tma_load_4d(sa + C::X_BYTES + ph * C::P_OUT * C::PLANE_Z, &tmaps_z.m[ph], full_bar(slot), 0, 0, band * C::HB, n * C::P_OUT);
-                tma_load_4d(sa + C::X_BYTES + C::Z_BYTES, &tmap_g, full_bar(slot), 0, 0, band * HBP, n * C::P_OUT);
+                    tma_load_4d(sa + C::X_BYTES + ph * C::P_OUTL * C::PLANE_Z, &tmaps_z.m[ph], full_bar(slot), 0, 0, band * C::HB, n * C::P_OUT + ns * C::P_OUTL);
+                tma_load_4d(sa + C::X_BYTES + C::Z_BYTES, &tmap_g, full_bar(slot), 0, 0, band * HBP, n * C::P_OUT + ns * C::P_OUTL);
             }
         }
     } else if (warp <= L0F_ISS) {
@@ -1522,7 +1525,7 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
             const int n = i / C::BANDS, view = n / n_per_view;
             if (view != cur_view) {                                      // uniform over the four warps
                 asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");    // nobody still reads the previous view's constants
-                if (t < C::COUT) cst_s[t] = __ldg(cst + (size_t)view * C::COUT + t);
+                if (t < C::COUTL) cst_s[t] = __ldg(cst + (size_t)view * C::COUT + ns * C::COUTL + t);
                 asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
                 cur_view = view;
             }
@@ -1530,7 +1533,7 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
             uint8_t* zimg = smem + slot * SLOT + C::X_BYTES;
             const uint4* gimg = reinterpret_cast<const uint4*>(smem + slot * SLOT + C::X_BYTES + C::Z_BYTES);
 #pragma unroll 1
-            for (int o = 0; o < C::P_OUT; ++o) {
+            for (int o = 0; o < C::P_OUTL; ++o) {
                 float4 c4[8];
                 float acc[8];
 #pragma unroll
@@ -1542,8 +1545,8 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
                     const int py = e / WOP, px = e - py * WOP;
                     // pooling window: rows 2py, 2py+1; columns 2px, 2px+1 = pixel group px/2, phases 2(px&1) and 2(px&1)+1
                     const int ph0 = 2 * (px & 1);
-                    uint4* zp0 = reinterpret_cast<uint4*>(zimg + (size_t)(ph0 * C::P_OUT + o) * C::PLANE_Z) + (2 * py) * C::WQ + (px >> 1);
-                    uint4* zp1 = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(zp0) + (size_t)C::P_OUT * C::PLANE_Z);
+                    uint4* zp0 = reinterpret_cast<uint4*>(zimg + (size_t)(ph0 * C::P_OUTL + o) * C::PLANE_Z) + (2 * py) * C::WQ + (px >> 1);
+                    uint4* zp1 = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(zp0) + (size_t)C::P_OUTL * C::PLANE_Z);
                     const uint4 raw[4] = {zp0[0], zp1[0], zp0[C::WQ], zp1[C::WQ]};
                     const uint4 graw = gimg[o * (HBP * WOP) + e];
                     uint32_t outw[4][4];
@@ -1590,7 +1593,7 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
                         float v = acc[j];
 #pragma unroll
                         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                        if (lane == 0) db_s[tw * C::COUT + o * 8 + j] += v;      // single writer per slot: deterministic
+                        if (lane == 0) db_s[tw * C::COUTL + o * 8 + j] += v;      // single writer per slot: deterministic
                     }
                 }
             }
@@ -1599,11 +1602,11 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
         }
         // ---- end of kernel: bias-gradient sums and the dW partial of this CTA ----
         asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
-        if (t < C::COUT && dbsum != nullptr) {
+        if (t < C::COUTL && dbsum != nullptr) {
             double v = 0.0;
 #pragma unroll
-            for (int q = 0; q < C::TW; ++q) v += (double)db_s[q * C::COUT + t];
-            atomicAdd(&dbsum[t], v);
+            for (int q = 0; q < C::TW; ++q) v += (double)db_s[q * C::COUTL + t];
+            atomicAdd(&dbsum[ns * C::COUTL + t], v);
         }
         const int quad = warp & 3;
         const int m = quad * 16 + (lane & 15), j = m >> 3, e8 = m & 7;   // accumulator row = (image row kh = j, tap kw' = e8)
@@ -1627,20 +1630,20 @@ conv_tc_wgrad_l0_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const 
                 }
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
-                    const int col = cc * 16 + q, ph = col / C::COUT, co = col % C::COUT;
+                    const int col = cc * 16 + q, ph = col / C::COUTL, co = col % C::COUTL;
                     const int kw = e8 - ph;
-                    if (lane < 16 && j < C::KS && kw >= 0 && kw < C::KS) stage[((ph * C::COUT + co) * C::KS + j) * C::KS + kw] = sum[q];
+                    if (lane < 16 && j < C::KS && kw >= 0 && kw < C::KS) stage[((ph * C::COUTL + co) * C::KS + j) * C::KS + kw] = sum[q];
                 }
             }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
-        for (int idx = t; idx < C::PART; idx += NT) {                    // fixed summation order over the four phases
+        for (int idx = t; idx < C::PARTL; idx += NT) {                   // fixed summation order over the four phases
             float v = 0.f;
             if (i1 > i0) {
 #pragma unroll
-                for (int ph = 0; ph < 4; ++ph) v += stage[ph * C::PART + idx];
+                for (int ph = 0; ph < 4; ++ph) v += stage[ph * C::PARTL + idx];
             }
-            part[idx] = v;
+            part[ns * C::PARTL + idx] = v;
         }
     }
     tc_fence_before_sync();
@@ -1666,7 +1669,7 @@ template <class C>
 int launch_conv_tc_wgrad_l0_fused(const void* x, const void* z, const void* dp, const float* scale, const float* shift, const float* mean,
                                   const float* invstd, const double* sums, float* dw, double* dbsum, float* work, int N, int n_per_view,
                                   cudaStream_t st, int64_t* need) {
-    int G = sm_count() * C::CTAS;
+    int G = sm_count() * C::CTAS / C::NSPLIT;
     const long items = (long)N * C::BANDS;
     if (G > items) G = (int)items;
     if (G < 1) G = 1;
@@ -1701,18 +1704,18 @@ int launch_conv_tc_wgrad_l0_fused(const void* x, const void* z, const void* dp, 
         // columns 4*i + ph
         const uint64_t dims[4] = {8, (uint64_t)C::WO / 4, (uint64_t)C::HO, (uint64_t)N * C::P_OUT};
         const uint64_t strides[3] = {64, (uint64_t)C::WO * 16, (uint64_t)C::WO * C::HO * 16};
-        const uint32_t box[4] = {8, (uint32_t)C::WQ, (uint32_t)C::HBZ, (uint32_t)C::P_OUT};
+        const uint32_t box[4] = {8, (uint32_t)C::WQ, (uint32_t)C::HBZ, (uint32_t)C::P_OUTL};
         int rc = encode_tmap_bf16_4d(&tz.m[ph], reinterpret_cast<const uint8_t*>(z) + 16 * ph, dims, strides, box);
         if (rc) return rc;
     }
     {
         const uint64_t dims[4] = {8, (uint64_t)C::WOP, (uint64_t)(C::HO / 2), (uint64_t)N * C::P_OUT};
         const uint64_t strides[3] = {16, (uint64_t)C::WOP * 16, (uint64_t)C::WOP * (C::HO / 2) * 16};
-        const uint32_t box[4] = {8, (uint32_t)C::WOP, (uint32_t)C::HBP, (uint32_t)C::P_OUT};
+        const uint32_t box[4] = {8, (uint32_t)C::WOP, (uint32_t)C::HBP, (uint32_t)C::P_OUTL};
         int rc = encode_tmap_bf16_4d(&tg, dp, dims, strides, box);
         if (rc) return rc;
     }
-    conv_tc_wgrad_l0_fused_kernel<C><<<G, C::THREADS, C::SMEM, st>>>(tx, tz, tg, cst, work, dbsum, N, n_per_view);
+    conv_tc_wgrad_l0_fused_kernel<C><<<dim3(G, 1, C::NSPLIT), C::THREADS, C::SMEM, st>>>(tx, tz, tg, cst, work, dbsum, N, n_per_view);
     int rc = launch_status("conv_tc_wgrad_l0_fused_kernel");
     if (rc) return rc;
     wgrad_reduce_kernel<<<(C::PART + 255) / 256, 256, 0, st>>>(work, G, C::PART, dw);
@@ -1837,7 +1840,7 @@ static int wgrad_tc_dispatch(const void* x, const void* dz, float* dw, float* wo
 using WgF_A0 = L0FCfg<8, 112, 112, 5, 2, 7, 2, 2>;
 using WgF_I0 = L0FCfg<32, 28, 28, 5, 2, 1, 2, 1>;
 using WgF_S0 = L0FCfg<32, 28, 28, 3, 1, 1, 2, 1>;
-using WgF_B0 = L0FCfg<32, 112, 112, 3, 1, 7, 1, 1>;      // simple audio stack: one 156 KB slot (x slab + 4 x 32 dz phase planes + dp tile)
+using WgF_B0 = L0FCfg<32, 112, 112, 3, 1, 7, 1, 2, 2>;   // simple audio stack: two 16-channel CTAs per SM, one 82 KB slot each
 
 static int wgrad_l0_dispatch(const void* x, const void* z, const void* dp, const float* scale, const float* shift, const float* mean,
                              const float* invstd, const double* sums, float* dw, double* dbsum, float* work, int N, int n_per_view, int Cout,
