@@ -91,7 +91,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_reference(batch, steps, warmup, cores, with_aug=True):
+def cpu_reference(batch, steps, warmup, cores, with_aug=True, kind="multi_central", mode="default"):
     """The reference's CPU path for this workload (oracle port): torchvision-composed augmentation in `cores` worker
     processes + the fp32 torch-CPU step (forward, loss, EMA, backward, Adam) with `cores` intra-op threads.
     Returns (samples/s, ms per step, description)."""
@@ -100,14 +100,21 @@ def cpu_reference(batch, steps, warmup, cores, with_aug=True):
     from oracle import dino_ref as R
     from oracle.fixtures import make_masks, synth_views, views_to_vb
     torch.set_num_threads(cores)
-    st = R.CentralDinoState(seed=1, mode="default")
+    from oracle.fixtures import synth_raw
+    if kind not in R.KIND_MIX:
+        kind = "multi_central"          # (image_simple: the multimodal oracle step stands in; only the headline kinds are compared)
+    st = R.CentralDinoState(seed=1, mode=mode, kind=kind)
     img, aud = views_to_vb(*synth_views(batch, seed=1))
     masks = make_masks(seed=2, V=6, Vg=2, B=batch, E=256, hidden=512)
+    raw = labels = None
+    if mode != "default":
+        image, audio, labels = synth_raw(batch, seed=3)
+        raw = (image, audio)
     for _ in range(warmup):
-        R.central_dino_step(st, img, aud, masks)
+        R.central_dino_step(st, img, aud, masks, raw=raw, labels=labels)
     t0 = time.perf_counter()
     for _ in range(steps):
-        R.central_dino_step(st, img, aud, masks)
+        R.central_dino_step(st, img, aud, masks, raw=raw, labels=labels)
     step_s = (time.perf_counter() - t0) / steps
     step_rate = batch / step_s
     aug_rate = None
@@ -211,7 +218,7 @@ def run_reference(args):
     torch.set_num_threads(cores)
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     batch = REF_SAMPLE_BATCH
-    rate, ms, desc = cpu_reference(batch, args.steps, args.warmup, cores)
+    rate, ms, desc = cpu_reference(batch, args.steps, args.warmup, cores, kind=args.kind, mode=args.mode)
     line = {"metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "impl": "reference",
@@ -676,9 +683,9 @@ def run_ours(args):
     except Exception:
         pass
     cpu = None
-    if world == 1 and not args.no_cpu_baseline and args.kind == "multi_central" and args.mode == "default":
+    if world == 1 and not args.no_cpu_baseline and args.kind.startswith("multi") and args.mode == "default":
         cores = os.cpu_count() or 1
-        rate, _, desc = cpu_reference(REF_SAMPLE_BATCH, 3, 1, cores)
+        rate, _, desc = cpu_reference(REF_SAMPLE_BATCH, 3, 1, cores, kind=args.kind)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"each step = a {REF_SAMPLE_BATCH}-sample slice of the workload batch; " + desc}
     drop_in = None

@@ -333,3 +333,44 @@ def test_adam_state_belongs_to_the_optimizer_object():
     steps(opt3, 1, 60)
     assert eng.step_count == 3
     assert not torch.equal(eng.exp_avg, m_after_2) and float((eng.exp_avg - 0.9 * m_after_2).abs().max()) < float(m_after_2.abs().max())
+
+
+SIMPLE_ENCODERS = [("SimpleMultiModalEncoder", "default"), ("GatedMultiModalEncoder", "mse"), ("CrossAttentionMultiModalEncoder", "semi_supervised")]
+
+
+@pytest.mark.parametrize("enc,mode", SIMPLE_ENCODERS)
+def test_simple_family_through_the_lightning_modules(enc, mode):
+    """SURVEY 8f-4 through the reference-shaped API: `--model multi_simple | multi_simple_gated | multi_cross_attention` of run_dino.py
+    (models/dino.py:214-263, 385-452): training_step -> backward -> B200Adam.step moves every encoder parameter (gates and attention
+    projections included), the teacher follows by EMA, and the containers' own inference forward (FeatureExtractor-style call of
+    `student(images, spectrograms)`) agrees with the engine's evaluation forward on the same weights."""
+    torch.manual_seed(0)
+    lit = WRAPPERS[mode](**dict(KW, encoder_class=getattr(md, enc))).to(DEV)
+    opt = lit.configure_optimizers()["optimizer"]
+    B = 8
+    before = {k: v.detach().clone() for k, v in lit.model.student.named_parameters()}
+    losses = []
+    for it in range(3):
+        opt.zero_grad(set_to_none=True)
+        loss = lit.training_step(_batch(mode, B, 10 + it), it)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    torch.cuda.synchronize()
+    assert all(l == l and 3.0 < l < 14.0 for l in losses), losses
+    for k, v in lit.model.student.named_parameters():
+        assert float((v - before[k]).abs().max()) > 0, f"{k} did not move"
+    eng = lit.model.engine
+    assert eng.kind == getattr(md, enc).B200_KIND and all(eng.tc["aud"]) and all(eng.tc["img"])
+    if enc == "GatedMultiModalEncoder":
+        assert lit.model.student.gate_image.data_ptr() == eng.S["enc.gate_image"].data_ptr()
+        assert float((lit.model.teacher.gate_image - 0.5).abs()) > 0          # EMA'd like every other parameter
+    # inference forward of the containers (fp32 kernels) vs the engine's evaluation forward (bf16 product path)
+    image, audio, _ = synth_raw(B, seed=77)
+    lit.model.eval()
+    with torch.no_grad():
+        feats_mod = lit.model.student(image.to(DEV), audio.to(DEV))
+        feats_eng = eng.encode_features(image[:, 0].to(DEV).contiguous(), audio[:, 0].to(DEV).contiguous(), train=False)
+    torch.cuda.synchronize()
+    rel = float((feats_mod - feats_eng).norm() / feats_eng.norm())
+    assert rel < 3e-2, rel

@@ -1,5 +1,5 @@
-"""Small fixed workload for ncu: W warm-up steps + K steps of the multi_central DINO step at per-GPU batch B.
-    python tools/profile_step.py [B] [warmup] [steps]"""
+"""Small fixed workload for ncu: W warm-up steps + K steps of the DINO step at per-GPU batch B.
+    python tools/profile_step.py [B] [warmup] [steps] [kind = multi_central]"""
 import os
 import sys
 
@@ -13,7 +13,8 @@ from multimodal_ssl_avmnist_b200.engine import DinoStepEngine
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 K = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-eng = DinoStepEngine(kind="multi_central", augment_values=augment_values(), seed=1, device="cuda:0")
+KIND = sys.argv[4] if len(sys.argv) > 4 else "multi_central"
+eng = DinoStepEngine(kind=KIND, augment_values=augment_values(), seed=1, device="cuda:0")
 g = torch.Generator().manual_seed(1)
 img = torch.rand(B, 28, 28, generator=g).cuda()
 aud = torch.randint(0, 256, (B, 112, 112), generator=g, dtype=torch.uint8).cuda()
