@@ -371,7 +371,7 @@ def profile_ops(engine, images, audios, steps=3, labels=None):
     ops.stop_profile()
     engine.overlap_teacher = overlap
     agg = {}
-    for name, a, b, meta in rec:
+    for name, a, b, meta, *_ in rec:
         agg.setdefault((name, meta), []).append(a.elapsed_time(b))
     rows = []
     for (name, meta), ts in agg.items():

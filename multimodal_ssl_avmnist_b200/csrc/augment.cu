@@ -531,11 +531,10 @@ __global__ void __launch_bounds__(32 * SAMPLE_WARPS) aug_sample_kernel(const int
                                                                        uint64_t step, int32_t* __restrict__ img_ops, int32_t* __restrict__ aud_ops,
                                                                        uint32_t* __restrict__ group_bits, const int64_t* __restrict__ step_dev) {
     if (step_dev != nullptr) step += (uint64_t)__ldg(step_dev);
-    // one warp per (sample, view) record: lane 0 replays the two op chains (sequential by nature) and draws the grouped-masking
-    // subset with a partial Fisher-Yates shuffle (gc draws instead of ranking 784 random keys); the warp stages and copies.
+    // one warp per (sample, view) record: lane 0 replays the two op chains (sequential by nature), the whole warp draws the
+    // grouped-masking subset (random keys + threshold selection) and copies the records out.
     __shared__ int32_t sspec[4 * B200_AUG_MAX_OPS * 8];
     __shared__ int32_t rec_i_s[SAMPLE_WARPS][B200_AUG_MAX_OPS * 8], rec_a_s[SAMPLE_WARPS][B200_AUG_MAX_OPS * 8];
-    __shared__ uint16_t perm_s[SAMPLE_WARPS][NGROUPS];
     __shared__ uint32_t bits_s[SAMPLE_WARPS][B200_AUG_GROUP_WORDS];
     const int V = Vg + Vl;
     const int warp = threadIdx.x >> 5, tid = threadIdx.x & 31;
@@ -547,30 +546,74 @@ __global__ void __launch_bounds__(32 * SAMPLE_WARPS) aug_sample_kernel(const int
     const size_t rec = (size_t)rec_l;
     int32_t* rec_i = rec_i_s[warp];
     int32_t* rec_a = rec_a_s[warp];
-    uint16_t* perm = perm_s[warp];
     uint32_t* bits = bits_s[warp];
-    for (int i = tid; i < NGROUPS; i += 32) perm[i] = (uint16_t)i;
     if (tid < B200_AUG_GROUP_WORDS) bits[tid] = 0u;
     __syncwarp();
     const bool local = v >= Vg;
     const uint64_t stream = (step << 36) ^ ((uint64_t)rec << 4);
+    int gc = -1;
     if (tid == 0) {
         Draw di(seed, stream | 2), da(seed, stream | 3);
-        int gc;
         sample_chain(sspec + (local ? 1 : 0) * B200_AUG_MAX_OPS * 8, 28, di, rec_i, &gc);
         sample_chain(sspec + (local ? 3 : 2) * B200_AUG_MAX_OPS * 8, 112, da, rec_a, &gc);
         if (gc > NGROUPS) gc = NGROUPS;
+    }
+    gc = __shfl_sync(0xffffffffu, gc, 0);
+    if (gc > 0) {
+        // Uniformly random subset of gc of the 784 groups, by the whole warp: every group draws an independent 32-bit key and the gc
+        // smallest keys win (i.i.d. keys: every gc-subset is equally likely; equal keys at the threshold are taken in index order).
+        // Lane l owns the 32 groups of mask word l.  (Round 1-2: a 508-step Fisher-Yates chain on lane 0 -- the kernel was latency
+        // bound on that one lane, 23 % warps active.)
+        constexpr int NW = (NGROUPS + 31) / 32;                           // 25 words, the last one half full
+        const int nvalid = tid < NW ? (NGROUPS - 32 * tid < 32 ? NGROUPS - 32 * tid : 32) : 0;
+        uint32_t key[32];
         Philox rng(seed);
-        uint4 r = make_uint4(0, 0, 0, 0);
-        for (int i = 0; i < gc; ++i) {           // uniformly random subset of gc groups
-            if ((i & 3) == 0) r = rng((uint64_t)(i >> 2), stream | 4);
-            const uint32_t u = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
-            const int j = i + (int)(((uint64_t)u * (uint32_t)(NGROUPS - i)) >> 32);
-            const uint16_t pj = perm[j];
-            perm[j] = perm[i];
-            perm[i] = pj;
-            bits[pj >> 5] |= 1u << (pj & 31);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint4 r = make_uint4(0, 0, 0, 0);
+            if (tid < NW) r = rng((uint64_t)(tid * 8 + j), stream | 4);
+            key[4 * j + 0] = r.x; key[4 * j + 1] = r.y; key[4 * j + 2] = r.z; key[4 * j + 3] = r.w;
         }
+        uint32_t lo = 0u, hi = 0xFFFFFFFFu;                                // smallest T with #(key <= T) >= gc
+#pragma unroll 1
+        for (int it = 0; it < 32 && lo < hi; ++it) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            int c = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) c += (j < nvalid && key[j] <= mid) ? 1 : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (c >= gc) hi = mid; else lo = mid + 1u;
+        }
+        const uint32_t T = lo;
+        int less = 0, eq = 0;
+        uint32_t mless = 0u, meq = 0u;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (j < nvalid) {
+                if (key[j] < T) { mless |= 1u << j; ++less; }
+                else if (key[j] == T) { meq |= 1u << j; ++eq; }
+            }
+        }
+        int tot_less = less, eq_before = eq;                               // warp total of `less`; exclusive prefix of `eq` over the lanes
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot_less += __shfl_xor_sync(0xffffffffu, tot_less, o);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t2 = __shfl_up_sync(0xffffffffu, eq_before, o);
+            if (tid >= o) eq_before += t2;
+        }
+        eq_before -= eq;
+        int take = gc - tot_less - eq_before;                              // how many of this lane's threshold-equal keys are still needed
+        take = take < 0 ? 0 : (take > eq ? eq : take);
+        uint32_t m = mless;
+        while (take > 0) {                                                 // lowest set bits of meq first (index order)
+            const uint32_t b = meq & (0u - meq);
+            m |= b;
+            meq ^= b;
+            --take;
+        }
+        if (tid < B200_AUG_GROUP_WORDS) bits[tid] = m;
     }
     __syncwarp();
     for (int i = tid; i < B200_AUG_MAX_OPS * 8; i += 32) {

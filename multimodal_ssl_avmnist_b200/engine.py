@@ -161,6 +161,17 @@ class _BN:
         self.num_batches_tracked = torch.zeros(1, dtype=torch.int64, device=device)
 
 
+def _main_chain(fn):
+    """Method decorator: the launches of `fn` go to the engine's high-priority main stream (DinoStepEngine._on_main)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        with self._on_main():
+            return fn(self, *args, **kwargs)
+    return wrapped
+
+
 class DinoStepEngine:
     """See module docstring.  kind: 'multi_central' (CentralMultiModalEncoder), 'multi_simple' (SimpleMultiModalEncoder),
     'multi_simple_gated' (GatedMultiModalEncoder), 'multi_cross_attention' (CrossAttentionMultiModalEncoder) or 'image_simple'
@@ -170,7 +181,7 @@ class DinoStepEngine:
                  n_global_views=2, n_local_views=4, momentum=0.996, center_momentum=0.9, student_temperature=0.1,
                  teacher_temperature=0.04, learning_rate=1e-4, weight_decay=1e-6, dropout=0.3, fusion_dropout=0.3, alpha=1.0,
                  cosine_loss_alpha=0.0, augment_values=None, seed=0, device=None, process_group=None, data_parallel=None,
-                 precision="bf16", fused_pool=True, fused_bnstat=False):
+                 precision="bf16", fused_pool=True, fused_bnstat=False, stream_priorities=False):
         if not torch.cuda.is_available():
             raise ops._lib.B200Error("DinoStepEngine needs a CUDA device: the hot path has no CPU fallback")
         ops._lib.load()
@@ -290,12 +301,30 @@ class DinoStepEngine:
                     if ci > 1:
                         self._tcw[("flip", mod, li)] = torch.empty(ops.conv_tc_weight_bytes(co, ci, k), dtype=torch.uint8, device=self.device)
         self.overlap_teacher = True
-        self._side_stream = torch.cuda.Stream(device=self.device)
-        self._lin_wg_stream = torch.cuda.Stream(device=self.device)       # linear weight gradients
+        # Stream priorities (optional, `stream_priorities=True`).  Most conv kernels are persistent grids that fill the GPU, so with several
+        # streams in flight every SM slot is taken and hundreds of CTAs are pending; a one-CTA kernel of the main chain (bn_finalize, bias /
+        # BatchNorm parameter gradients) then waits 0.15 - 0.25 ms for a slot behind them (event timeline, tools/timeline_step.py,
+        # profiles/r2t_timeline_*.txt).  With the main chain on a high-priority stream (teacher / image stack below it, weight gradients
+        # and the augmentation prefetch at the bottom) the block scheduler serves its pending CTAs first and the main chain of a B = 1024
+        # step ends 0.77 ms earlier -- but the step does NOT get shorter (7.65 vs 7.62 ms): the side streams' work then forms a 1.2 ms
+        # tail.  The step is bound by the total work of its kernels on a saturated GPU, not by the latency of its critical chain.
+        lo, hi = 0, -1
+        try:
+            hi = int(os.environ.get("B200_TOP_PRIORITY", "-3"))
+        except ValueError:
+            pass
+        self.stream_priorities = bool(stream_priorities)
+
+        def mk(level):          # level 0 = top ... 3 = bottom; clamped by the driver to the device's priority range
+            return torch.cuda.Stream(device=self.device, priority=(min(lo, hi + level) if self.stream_priorities else 0))
+
+        self._main_stream = mk(0) if self.stream_priorities else None
+        self._side_stream = mk(1)
+        self._lin_wg_stream = mk(3)       # linear weight gradients
         self._lin_wg_pending = False
-        self._side_stream2 = torch.cuda.Stream(device=self.device)
-        self._wgrad_streams = {m: torch.cuda.Stream(device=self.device) for m in ("img", "aud")}
-        self._aug_stream = torch.cuda.Stream(device=self.device)
+        self._side_stream2 = mk(1)
+        self._wgrad_streams = {m: mk(2) for m in ("img", "aud")}
+        self._aug_stream = mk(3)
         # data parallel: the exchange runs inside the C ABI (NCCL, b200_dp_*) on a communication stream beside the compute streams
         self.comm = dp.AbiComm.get(process_group) if self.world > 1 else None
         self._comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
@@ -310,6 +339,20 @@ class DinoStepEngine:
         self._ws = {}
         self._init_parameters()
         self.set_augmentation(augment_values)
+
+    @contextlib.contextmanager
+    def _on_main(self):
+        """Run the enclosed launches on the engine's high-priority main stream, ordered after the caller's current stream, and make the
+        caller's stream wait for them afterwards (a no-op when priorities are off or we already are on that stream)."""
+        hp = self._main_stream
+        cur = torch.cuda.current_stream()
+        if hp is None or cur == hp:
+            yield
+            return
+        hp.wait_stream(cur)
+        with torch.cuda.stream(hp):
+            yield
+        cur.wait_stream(hp)
 
     # ------------------------------------------------------------------------------------------------------
     def _init_parameters(self):
@@ -862,17 +905,26 @@ class DinoStepEngine:
                     ops.bn_pool8_bwd_reduce_p(p_out, d_p, S["enc." + bn + ".weight"], S["enc." + bn + ".bias"], sums, B)
                 if not fused:
                     ops.bn_relu_pool8_bwd_apply(z, d_p, sc, sh, mu, inv, sums, dz, B, dbsum=w[f"{mod}.dbsum"][li])
-                    ops.bias_grad_finalize(w[f"{mod}.dbsum"][li], G["enc." + conv + ".bias"])
             else:
                 dz = w[f"{mod}.dz"][:z.numel()].view_as(z)
                 ops.bn_relu_pool_bwd_reduce(z, d_p, sc, sh, mu, inv, sums, B)
                 ops.bn_relu_pool_bwd_apply(z, d_p, sc, sh, mu, inv, sums, dz, B)
-            ops.bn_param_grads(sums, G["enc." + bn + ".weight"], G["enc." + bn + ".bias"], N // B)
+
+            def param_grads(li=li, tc=tc, fused=tc and ci == 1, conv=conv, bn=bn, sums=sums):
+                # one-CTA kernels nothing waits for before Adam: with the weight gradient on its stream, not in the main chain
+                if tc and not fused:
+                    ops.bias_grad_finalize(w[f"{mod}.dbsum"][li], G["enc." + conv + ".bias"])
+                ops.bn_param_grads(sums, G["enc." + bn + ".weight"], G["enc." + bn + ".bias"], N // B)
+
+            if not (tc and wside is not None):
+                param_grads()
             if tc:
                 xin8 = w[f"{mod}.xs8"] if ci == 1 else w[f"s.{mod}.p8{li - 1}"]
                 wk = w[f"{mod}.wg_work" if (li & 1) == 0 else f"{mod}.wg_work_b"]
 
                 def wgrad():
+                    if wside is not None:
+                        param_grads()
                     if fused:       # BatchNorm / ReLU / pool backward-apply happens inside the weight-gradient kernel
                         ops.conv_tc_wgrad_l0_fused(xin8, z, d_p, sc, sh, mu, inv, sums, G["enc." + conv + ".weight"], w[f"{mod}.dbsum"][li], wk,
                                                    B, pad)
@@ -974,6 +1026,7 @@ class DinoStepEngine:
             bns[k] = c
         return {"bns": bns, "step": 0, "teacher": teacher}
 
+    @_main_chain
     @torch.no_grad()
     def encode_features(self, images, audios=None, train=False, teacher=False, probe=None):
         """Encoder features [B, O] of an UN-augmented batch (images [B,28,28] fp32 in [0,1] or uint8, audios [B,112,112] fp32 in
@@ -1014,6 +1067,7 @@ class DinoStepEngine:
     # ------------------------------------------------------------------------------------------------------
     # the step
     # ------------------------------------------------------------------------------------------------------
+    @_main_chain
     def forward_pass(self, x_img, x_aud, masks=None, raw=None):
         """Student (all views [+ the un-augmented pass in the non-default modes]) and teacher (global views) forward
         through encoders and heads.  Returns the workspace dict; outputs: w['s.proj'] [V*B,P], w['t.proj'] [Vg*B,P]
@@ -1090,6 +1144,7 @@ class DinoStepEngine:
         w["loss"].zero_()
         return w
 
+    @_main_chain
     def dino_loss_pass(self, w):
         """Fused DINO loss forward+backward (fills w['d.proj'], loss[0]) and the centre EMA (all-reduced when data parallel)."""
         V, Vg, P, B = self.V, self.Vg, self.P, w["B"]
@@ -1120,6 +1175,7 @@ class DinoStepEngine:
             torch.cuda.current_stream().wait_event(self._center_ready)
             self._center_ready = None
 
+    @_main_chain
     def aux_loss_pass(self, w, labels=None):
         """MSE / InfoNCE / CE on the mode heads' outputs, forward+backward fused (fills w['aux_*.d.out'], loss[1])."""
         loss = w["loss"]
@@ -1134,6 +1190,7 @@ class DinoStepEngine:
         elif self.mode == "mse":
             ops.mse_align_fwd_bwd(oi, oa, w["aux_image.d.out"], w["aux_audio.d.out"], loss[1:2], grad_scale=self.alpha, work=w["loss_work"])
 
+    @_main_chain
     def backward_pass(self, w, d_proj=None, d_aux=None):
         """Backward from the gradient w.r.t. the student projections (default: the fused loss's own w['d.proj']) and, in the
         non-default modes, w.r.t. the two mode-head outputs (default: w['aux_*.d.out']).  Fills self.grad."""
@@ -1215,6 +1272,7 @@ class DinoStepEngine:
                 self.comm.allreduce_grads_(self.grad[self.aux_range[0]:self.aux_range[1]], cs.cuda_stream)
         self._comm_pending = "late"
 
+    @_main_chain
     def forward_backward(self, x_img, x_aud, masks=None, raw=None, labels=None):
         """Student + teacher forward, losses, centre EMA and the full backward for already-augmented views.
 
@@ -1248,10 +1306,12 @@ class DinoStepEngine:
         self._comm_pending = True
         self._grad_scale = 1.0 / self.world
 
+    @_main_chain
     def update_teacher(self):
         """Teacher EMA over the whole common arena prefix: one kernel (models/dino.py:635-646)."""
         ops.ema_flat(self.teacher.flat[:self.n_ema], self.student.flat[:self.n_ema], self.momentum)
 
+    @_main_chain
     def optimizer_step(self, grad_scale=None):
         """Adam (lr, weight_decay; models/dino.py:953-962) over the parameters that received gradients."""
         self.step_count += 1
@@ -1292,6 +1352,7 @@ class DinoStepEngine:
         if self._ctr is not None:
             self._ctr[1:2].fill_(self.step_count)
 
+    @_main_chain
     def train_step_views(self, x_img, x_aud, masks=None, raw=None, labels=None):
         """Reference step order on given views: forward/loss/backward, EMA (before the optimizer, dino.py:871), Adam."""
         loss = self.forward_backward(x_img, x_aud, masks=masks, raw=raw, labels=labels)
@@ -1303,6 +1364,7 @@ class DinoStepEngine:
             ops.counters_advance(self._ctr)
         return loss
 
+    @_main_chain
     def train_step(self, images, audios=None, labels=None):
         """Whole step from a raw device batch: images [B,28,28] fp32 in [0,1] or uint8; audios [B,112,112] uint8 (or fp32);
         labels int64 [B] (semi_supervised).  Returns the device loss tensor [4] (dino, aux, cosine, total)."""

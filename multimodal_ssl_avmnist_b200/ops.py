@@ -689,7 +689,7 @@ def _wrap(name, fn):
         head = args[:6] if name == "conv_tc_pool" else args[:4]        # conv_tc_pool: (x, wprep, bias, gamma, z | None, e)
         meta = tuple(tuple(t.shape) for t in list(head) + list(kwargs.values()) if isinstance(t, torch.Tensor))
         meta = meta + (("i",) + tuple(int(v) for v in args if isinstance(v, int) and not isinstance(v, bool)),)
-        _PROFILE.append((name, a, b, meta))
+        _PROFILE.append((name, a, b, meta, _stream()))
         return out
 
     wrapped.__name__ = name

@@ -299,6 +299,13 @@ def test_augment_device_sampler_distributions():
     applied = (kinds == A.OP_GROUP_MASK).any(-1)
     pop = np.unpackbits(gbn[:, Vg:].view(np.uint8), axis=-1).sum(-1)
     assert (pop[applied] == n_mask).all() and (pop[~applied] == 0).all()
+    # ... uniformly: every one of the 784 groups is masked with frequency n_mask / 784 (5 sigma), none of the padding bits ever
+    sel = np.unpackbits(gbn[:, Vg:].view(np.uint8), axis=-1, bitorder="little")[applied]          # [records, 28 * 32], bit g = group g
+    assert sel[:, 784:].sum() == 0
+    pr = n_mask / 784.0
+    assert np.abs(sel[:, :784].mean(0) - pr).max() < 5.0 * (pr * (1 - pr) / sel.shape[0]) ** 0.5 + 1e-3
+    both = (sel[:, :783] & sel[:, 1:784]).mean(0)                    # neighbouring groups: no correlation beyond the fixed-size constraint
+    assert np.abs(both - pr * (n_mask - 1) / 783.0).max() < 5.0 * (0.25 / sel.shape[0]) ** 0.5 + 1e-3
     # the sampled records drive the apply kernels without faults and produce finite, bounded views
     src_i = torch.rand(B, 28, 28, device=DEV)
     src_a = torch.randint(0, 256, (B, 112, 112), dtype=torch.uint8, device=DEV)
