@@ -697,8 +697,14 @@ def run_ours(args):
         except Exception as exc:        # reported, never hidden: the engine numbers above stand on their own
             drop_in = {"error": f"{type(exc).__name__}: {exc}"}
     h2d = img_h.numel() * 4 + (aud_h.numel() if aud_h is not None else 0)
+    # the ONE published throughput of the reference for a configuration this repo runs: the semi-supervised
+    # SimpleMultiModalEncoder DINO step at B = 128, 1.74 it/s = 223 samples/s on an unnamed single GPU
+    # (archive/semi-supervised_dino/semi-supervised_dino.ipynb:153).  Every other configuration has no published number: null.
+    vs_base = None
+    if world == 1 and args.kind == "multi_simple" and args.mode == "semi_supervised" and B == 128:
+        vs_base = B * world / (ms / 1e3) / 223.0
     line = {"metric": METRIC, "value": B * world / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": vs_base,
             "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, world),
             "details": {"execution": "one CUDA graph replay per step (device-side step counters)" if use_graph else "eager launches on 6 streams",
