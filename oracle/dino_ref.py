@@ -466,3 +466,71 @@ def central_dino_step(st, img_views, aud_views, masks, n_global=2, tau_s=0.1, ta
     return {"loss": loss.detach(), "aux": None if aux_val is None else aux_val.detach(), "grads": grads,
             "student_out": s_out.detach(), "teacher_out": t_out.detach(),
             "student_features": student_features.detach()}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# stand-alone contrastive steps (SURVEY 8f-4 / BASELINE config 4): other_ssl/info_nce/info_nce.py:15-36, 120-142 and
+# other_ssl/multimodal_simclr/multimodal_simclr.py:12-46, 91-110 -- ImageEncoder + SpectrogramEncoder + two ProjectionHeads,
+# InfoNCE between the modalities of the un-augmented batch / NT-Xent between two augmented views with a random modality pairing
+# ------------------------------------------------------------------------------------------------------------
+
+def spectrogram_spec(O=256):
+    """SpectrogramEncoder (models/dino.py:502-513) = audio_encoder(O) (models/dino.py:43-73)."""
+    s = []
+    for i, (ci, co) in zip((0, 4, 8, 12), ((1, 32), (32, 64), (64, 128), (128, 256))):
+        s += _conv(f"encoder.{i}", co, ci, 3) + _bn(f"encoder.{i + 1}", co)
+    return s + _lin("encoder.18", O, 256)
+
+
+def spectrogram_bn_names():
+    return ["encoder.1", "encoder.5", "encoder.9", "encoder.13"]
+
+
+CONTRASTIVE_MODULES = ("image_encoder", "audio_encoder", "image_projection_head", "audio_projection_head")
+
+
+class ContrastiveState:
+    """Parameters / BatchNorm buffers / Adam state of InfoNCEModel or MultiModalSimCLRModel, one flat dict per sub-module."""
+
+    def __init__(self, seed=0, O=256, P=256, dtype=torch.float32):
+        self.O, self.P, self.dtype = O, P, dtype
+        self.spec = {"image_encoder": image_simple_spec(O), "audio_encoder": spectrogram_spec(O),
+                     "image_projection_head": head_spec(O, P), "audio_projection_head": head_spec(O, P)}
+        bn = {"image_encoder": image_simple_bn_names(), "audio_encoder": spectrogram_bn_names(),
+              "image_projection_head": ["mlp.1"], "audio_projection_head": ["mlp.1"]}
+        self.params = {m: make_params(self.spec[m], seed + i, dtype) for i, m in enumerate(CONTRASTIVE_MODULES)}
+        self.buf = {m: make_bn_buffers(self.spec[m], bn[m], dtype) for m in CONTRASTIVE_MODULES}
+        self.adam = {m: {} for m in CONTRASTIVE_MODULES}
+
+
+def contrastive_step(st, kind, batch, mode=None, lr=1e-4, temperature=0.07, do_adam=True):
+    """One training step of MultiModalInfoNCELightning (kind="infonce": batch = (images [B,1,28,28], spectrograms [B,1,112,112])) or
+    MultiModalSimCLRLightning (kind="simclr": batch = (img1, spec1, img2, spec2), mode in 0..3 = the reference's torch.randint draw:
+    0 image-image, 1 audio-audio, 2 image-audio, 3 audio-image).  Adam(lr), no weight decay; torch's Adam skips parameters without
+    a gradient and keeps a step count per parameter, so a branch that was not used this step is left untouched."""
+    P = {m: {k: v.clone().requires_grad_(True) for k, v in st.params[m].items()} for m in CONTRASTIVE_MODULES}
+
+    def enc(which, x):
+        if which == "image":
+            f = image_simple_encoder(x, P["image_encoder"], st.buf["image_encoder"])
+            return projection_head(f, P["image_projection_head"], st.buf["image_projection_head"])
+        f = simple_audio_features(x, P["audio_encoder"], st.buf["audio_encoder"], pre="encoder")
+        return projection_head(f, P["audio_projection_head"], st.buf["audio_projection_head"])
+
+    if kind == "infonce":
+        images, specs = batch
+        z1, z2 = enc("image", images), enc("audio", specs)
+        loss = infonce_loss(z1, z2, temperature)
+    else:
+        img1, spec1, img2, spec2 = batch
+        first, second = (("image", "image"), ("audio", "audio"), ("image", "audio"), ("audio", "image"))[mode]
+        z1 = enc(first, img1 if first == "image" else spec1)
+        z2 = enc(second, img2 if second == "image" else spec2)
+        loss = ntxent_loss(torch.cat([z1, z2]), temperature)
+    loss.backward()
+    grads = {m: {k: v.grad for k, v in P[m].items() if v.grad is not None} for m in CONTRASTIVE_MODULES}
+    if do_adam:
+        for m in CONTRASTIVE_MODULES:
+            if grads[m]:
+                adam_step(st.params[m], grads[m], st.adam[m], lr, 0.0)
+    return {"loss": loss.detach(), "grads": grads, "z1": z1.detach(), "z2": z2.detach()}

@@ -31,3 +31,11 @@ def golden_simple():
     import json
     with open(os.path.join(ROOT, "tests", "golden", "golden_simple.json")) as f:
         return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def golden_contrastive():
+    """Step fixtures of the imported reference's stand-alone InfoNCE / SimCLR Lightning modules (make_golden.py contrastive)."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "golden_contrastive.json")) as f:
+        return json.load(f)

@@ -264,6 +264,47 @@ def unimodal_fixture(B=4, seed=9, alpha=0):
     return rec
 
 
+def contrastive_fixture(kind, B=4, seed=21, modes=(2, 0, 1, 3)):
+    """training_step -> backward -> Adam.step of the imported MultiModalInfoNCELightning (other_ssl/info_nce/info_nce.py) or
+    MultiModalSimCLRLightning (other_ssl/multimodal_simclr/multimodal_simclr.py) with the oracle's deterministic weights.  SimCLR draws its
+    modality pairing with torch.randint(0, 4, (1,)): patched here to the recorded `modes`, one per step."""
+    st = R.ContrastiveState(seed=seed)
+    if kind == "infonce":
+        import other_ssl.info_nce.info_nce as mod
+        lit = mod.MultiModalInfoNCELightning(projection_dim=256, output_dim=256)
+        n_steps = 2
+    else:
+        import other_ssl.multimodal_simclr.multimodal_simclr as mod
+        lit = mod.MultiModalSimCLRLightning(projection_dim=256, output_dim=256)
+        n_steps = len(modes)
+    for m in R.CONTRASTIVE_MODULES:
+        _load(getattr(lit.model, m), st.params[m])
+    lit.train()
+    opt = torch.optim.Adam(lit.parameters(), lr=1e-4)
+    out = {"kind": kind, "B": B, "seed": seed, "modes": list(modes), "steps": []}
+    orig_randint = torch.randint
+    for it in range(n_steps):
+        g = torch.Generator().manual_seed(400 + it)
+        img1, spec1 = torch.rand(B, 1, 28, 28, generator=g), torch.rand(B, 1, 112, 112, generator=g)
+        img2, spec2 = torch.rand(B, 1, 28, 28, generator=g), torch.rand(B, 1, 112, 112, generator=g)
+        opt.zero_grad(set_to_none=True)
+        if kind == "infonce":
+            loss = lit.training_step((img1, spec1, torch.zeros(B, dtype=torch.long)), it)
+        else:
+            torch.randint = lambda *a, **k: torch.tensor([modes[it]])
+            try:
+                loss = lit.training_step((img1, spec1, img2, spec2), it)
+            finally:
+                torch.randint = orig_randint
+        loss.backward()
+        rec = {"loss": float(loss.detach()), "grads": {n: summarize(p.grad) for n, p in lit.model.named_parameters() if p.grad is not None}}
+        opt.step()
+        rec["params_after_adam"] = {n: summarize(p) for n, p in lit.model.named_parameters()}
+        rec["bn"] = {n: summarize(b) for n, b in lit.model.named_buffers()}
+        out["steps"].append(rec)
+    return out
+
+
 def api_surface():
     """state_dict keys/shapes of the reference modules and seeded-initialisation checksums (API-compatibility fixtures)."""
     out = {}
@@ -315,6 +356,13 @@ if __name__ == "__main__":
         with open(os.path.join(HERE, "golden_simple.json"), "w") as f:
             json.dump(fx, f, indent=1)
         print("wrote golden_simple.json:", sorted(fx))
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "contrastive":
+        # the stand-alone contrastive steps (other_ssl/info_nce, other_ssl/multimodal_simclr) -> tests/golden/golden_contrastive.json
+        fx = {"infonce": contrastive_fixture("infonce"), "simclr": contrastive_fixture("simclr"), "versions": {"torch": torch.__version__}}
+        with open(os.path.join(HERE, "golden_contrastive.json"), "w") as f:
+            json.dump(fx, f, indent=1)
+        print("wrote golden_contrastive.json")
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "api":
         with open(os.path.join(HERE, "api_surface.json"), "w") as f:

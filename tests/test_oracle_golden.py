@@ -2,6 +2,7 @@
 (tests/golden/make_golden.py) and the known answers of SURVEY.md §8c."""
 import os
 import random
+import re
 
 import numpy as np
 import pytest
@@ -307,3 +308,48 @@ def test_simclr_augmentation_against_reference_fixture():
                 np.testing.assert_allclose(got[::4, 1::4], fx[f"s{s}_{name}_dec"][b, 0], rtol=0, atol=2e-6)
                 np.testing.assert_allclose(got.astype(np.float64).sum(-1), fx[f"s{s}_{name}_rows"][b, 0], rtol=0, atol=2e-3)
     assert {A.OP_ELASTIC, A.OP_BLUR3, A.OP_NOISE, A.OP_TIME_WARP} <= kinds          # the seeds exercise every new op
+
+
+def contrastive_batch(B, it):
+    """The seeded batches of make_golden.contrastive_fixture."""
+    g = torch.Generator().manual_seed(400 + it)
+    img1, spec1 = torch.rand(B, 1, 28, 28, generator=g), torch.rand(B, 1, 112, 112, generator=g)
+    img2, spec2 = torch.rand(B, 1, 28, 28, generator=g), torch.rand(B, 1, 112, 112, generator=g)
+    return img1, spec1, img2, spec2
+
+
+@pytest.mark.parametrize("kind", ["infonce", "simclr"])
+def test_contrastive_step_against_reference(kind, golden_contrastive):
+    """other_ssl/info_nce/info_nce.py and other_ssl/multimodal_simclr/multimodal_simclr.py (BASELINE config 4): the oracle's
+    contrastive_step against training_step -> backward -> Adam.step of the imported Lightning modules, incl. the SimCLR modality pairing
+    (all four modes) and Adam's per-parameter step counts (a branch without gradients is skipped)."""
+    fx = golden_contrastive[kind]
+    B = fx["B"]
+    st = R.ContrastiveState(seed=fx["seed"])
+    for it, rec in enumerate(fx["steps"]):
+        img1, spec1, img2, spec2 = contrastive_batch(B, it)
+        if kind == "infonce":
+            out = R.contrastive_step(st, "infonce", (img1, spec1))
+        else:
+            out = R.contrastive_step(st, "simclr", (img1, spec1, img2, spec2), mode=fx["modes"][it])
+        assert abs(float(out["loss"]) - rec["loss"]) < (5e-6 if it == 0 else 1e-4) * max(1.0, abs(rec["loss"])), (kind, it, float(out["loss"]), rec["loss"])
+        grads = {f"{m}.{k}": v for m in R.CONTRASTIVE_MODULES for k, v in out["grads"][m].items()}
+        assert set(grads) == set(rec["grads"]), (kind, it, set(grads) ^ set(rec["grads"]))
+        noise = max(1e-4, 1e-5 * max(v["abs_sum"] for v in rec["grads"].values()))
+        for name, ref in rec["grads"].items():
+            mine = summarize(grads[name])
+            if re.search(r"(encoder\.(0|4|8|12|14|18)\.bias|projection\.0\.bias|mlp\.0\.bias)$", name):      # feeds a BatchNorm: exact gradient 0
+                assert mine["abs_sum"] < noise and ref["abs_sum"] < noise, (kind, it, name)
+                continue
+            ok, why = summaries_close(mine, ref, 1e-3 if it == 0 else 5e-2, 1e-8 if it == 0 else 1e-6)
+            assert ok, (kind, it, name, why)
+        for name, ref in rec["params_after_adam"].items():
+            # Adam's first steps are ~lr * sign(g): an element whose gradient is rounding noise (dead unit, cancelled bias) may land
+            # 2 * lr = 2e-4 away; everything else agrees to fp32 rounding
+            m, k = name.split(".", 1)
+            ok, why = summaries_close(summarize(st.params[m][k]), ref, 1e-5, 2.5e-4 * (it + 1))
+            assert ok, (kind, it, name, why)
+        for name, ref in rec["bn"].items():
+            m, k = name.split(".", 1)
+            ok, why = summaries_close(summarize(st.buf[m][k]), ref, 1e-5, 1e-7 if it == 0 else 4e-4)
+            assert ok, (kind, it, name, why)
