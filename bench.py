@@ -721,6 +721,75 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_contrastive(args):
+    """The stand-alone contrastive steps of the reference's other_ssl/ modules (BASELINE config 4): kind contrastive_infonce =
+    other_ssl/info_nce/info_nce.py (InfoNCE between the modalities of the un-augmented batch), contrastive_simclr =
+    other_ssl/multimodal_simclr/multimodal_simclr.py (two augmented views, random modality pairing, NT-Xent).  One GPU; `value` with
+    the raw batch resident in HBM, `e2e` with the pinned host batch copied in and the loss read back every step."""
+    import torch
+    from multimodal_ssl_avmnist_b200 import ops
+    from multimodal_ssl_avmnist_b200.contrastive import ContrastiveStepEngine
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("bench.py: the contrastive kinds run on one GPU (no data-parallel exchange is wired for them)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    kind = args.kind.split("_", 1)[1]
+    B = args.batch
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(1)
+    eng = ContrastiveStepEngine(kind=kind, device=dev, seed=1)
+    g = torch.Generator().manual_seed(1)
+    img_h = torch.rand(B, 28, 28, generator=g).pin_memory()
+    aud_h = torch.randint(0, 256, (B, 112, 112), generator=g, dtype=torch.uint8).pin_memory()
+    img_d, aud_d = img_h.to(dev), aud_h.to(dev)
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        loss = eng.train_step(img_d, aud_d)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = eng.train_step(img_d, aud_d)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (ops.launch_count() - l0) // args.steps
+    buf_i, buf_a = torch.empty_like(img_d), torch.empty_like(aud_d)
+    e0.record()
+    for _ in range(args.steps):
+        buf_i.copy_(img_h, non_blocking=True)
+        buf_a.copy_(aud_h, non_blocking=True)
+        last = float(eng.train_step(buf_i, buf_a)[3].item())
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    clk = sampler.stop()
+    # algorithmic FLOPs per sample: ImageEncoder 7.65 M + head, SpectrogramEncoder 177.1 M + head MACs per encoder call, x3 (fwd, dgrad, wgrad)
+    img_macs = 9 * (28 * 28 * 32 + 14 * 14 * 64 * 32 + 7 * 7 * 128 * 64) + 128 * 512 + 512 * 256 + 256 * 512 + 512 * 256
+    aud_macs = 9 * (112 * 112 * 32 + 56 * 56 * 64 * 32 + 28 * 28 * 128 * 64 + 14 * 14 * 256 * 128) + 256 * 256 + 256 * 512 + 512 * 256
+    per_sample = (img_macs + aud_macs) * 6.0        # infonce: one call of each encoder; simclr: two calls, on average one of each
+    published = {("infonce", 128): (2180.0, "other_ssl/info_nce/info_nce.ipynb:156"), ("simclr", 256): (790.0, "other_ssl/multimodal_simclr/multimodal_simclr.ipynb:87")}
+    pub = published.get((kind, B))
+    rate = B / (ms / 1e3)
+    wl = ("stand-alone multimodal InfoNCE step (ImageEncoder + SpectrogramEncoder + 2 projection heads, un-augmented batch)" if kind == "infonce" else
+          "multimodal SimCLR step (2 augmented views per modality, random modality pairing, NT-Xent)")
+    print(json.dumps({"metric": METRIC.replace("DINO", "contrastive"), "value": rate, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": W,
+                      "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": (rate / pub[0]) if pub else None,
+                      "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": wl, "per_gpu_batch": B, "global_batch": B, "parallelism": "dp1",
+                                 "published_reference": ({"samples_per_s": pub[0], "source": pub[1], "hardware": "unnamed single GPU"} if pub else None),
+                                 "l2": "activations of a step exceed the 126 MB L2"},
+                      "e2e": {"value": B / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": img_h.numel() * 4 + aud_h.numel(), "d2h_bytes_per_step": 4,
+                              "ms_per_step": ms_e2e, "last_loss": last},
+                      "gpu_launches": int(launches), "clocks": clk,
+                      "roofline": {"bound": "tensor", "kernel": "whole step", "achieved": per_sample * B / ms / 1e9, "peak": load_peaks()["tflops"], "unit": "TFLOP/s",
+                                   "frac": per_sample * B / ms / 1e9 / load_peaks()["tflops"], "traffic": None,
+                                   "note": "whole-step algorithmic FLOPs (6 x forward MACs of one call of each encoder + head) over the step time"},
+                      "cpu_baseline": None, "impl": "ours"}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -742,7 +811,8 @@ def main():
     ap.add_argument("--graph", action="store_true",
                     help="replay the whole step from one CUDA graph (meant for small per-GPU batches, where the ~165 host-side "
                          "launches bound the step; with N > 1 the all-reduces are captured too)")
-    ap.add_argument("--kind", default="multi_central", choices=["multi_central", "image_simple", "multi_simple", "multi_simple_gated", "multi_cross_attention"],
+    ap.add_argument("--kind", default="multi_central", choices=["multi_central", "image_simple", "multi_simple", "multi_simple_gated", "multi_cross_attention", "contrastive_infonce",
+                             "contrastive_simclr"],
                     help="image_simple = BASELINE.json configs[0] (unimodal image DINO); multi_simple* / multi_cross_attention = the 3x3 conv "
                          "encoders of SURVEY 8f-4; the headline line is multi_central")
     ap.add_argument("--mode", default="default", choices=["default", "semi_supervised", "infonce", "mse"],
@@ -750,6 +820,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.kind.startswith("contrastive"):
+        run_contrastive(args)
     else:
         run_ours(args)
 
