@@ -184,6 +184,21 @@ class ImageEncoder(BaseUniModalEncoder):
         return MF._linear(MF.sequential_cnn_forward(self.encoder, images), self.projection[0])
 
 
+class SpectrogramEncoder(BaseUniModalEncoder):
+    """audio_encoder(output_dim) on the spectrogram (reference models/dino.py:502-513).  Used by the stand-alone contrastive models
+    (other_ssl/info_nce, other_ssl/multimodal_simclr); as a unimodal DINO encoder it has no compiled step (B200_KIND None)."""
+    B200_KIND = None
+
+    def __init__(self, output_dim=256):
+        super().__init__(output_dim, modality="audio")
+        self.encoder = audio_encoder(output_dim=output_dim)
+
+    def forward(self, images=None, spectrograms=None):
+        if spectrograms is None:
+            raise ValueError("SpectrogramEncoder requires spectrogram input")
+        return MF.sequential_cnn_forward(self.encoder, spectrograms)
+
+
 def _out_of_scope(name):
     def __init__(self, *a, **k):
         raise NotImplementedError(f"{name} is outside the B200 hot-path scope (see DESIGN.md section 7); "
@@ -192,8 +207,7 @@ def _out_of_scope(name):
 
 
 for _n in ("LSTMImageEncoder", "LSTMMultiModalEncoder", "ViTMultiModalEncoder", "DualViTMultiModalEncoder", "MobileViTMultiModalEncoder",
-           "ResNetMultiModalEncoder", "SpectrogramEncoder",
-           "SpectrogramEncoderCentral", "SpectrogramEncoderLSTM", "SpectrogramEncoderResNet", "SpectrogramEncoderViT",
+           "ResNetMultiModalEncoder", "SpectrogramEncoderCentral", "SpectrogramEncoderLSTM", "SpectrogramEncoderResNet", "SpectrogramEncoderViT",
            "SpectrogramEncoderMobileViT", "UniModalDINOV2"):
     globals()[_n] = _out_of_scope(_n)
 

@@ -336,3 +336,74 @@ def standalone_cosine_loss(emb):
     g, lo = torch.empty_like(x), torch.empty(1, device=x.device)
     ops.cosine_consistency_fwd_bwd(x, g, lo)
     return fused_loss(lo[0], (emb,), (g,))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# stand-alone contrastive models (other_ssl/info_nce, other_ssl/multimodal_simclr)
+# ------------------------------------------------------------------------------------------------------------
+class ContrastiveAdam(torch.optim.Optimizer):
+    """torch.optim.Adam-shaped front of ContrastiveStepEngine.optimizer_step(): Adam(lr), no weight decay, over the branches that
+    received gradients in the last training_step, one step count per branch (what torch's per-parameter step state amounts to)."""
+
+    def __init__(self, params, binding, lr=1e-4):
+        super().__init__(params, dict(lr=lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8))
+        self.binding = binding
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        eng = self.binding.engine
+        if eng is None:
+            raise ops._lib.B200Error("ContrastiveAdam.step() before the first CUDA training_step")
+        eng.lr = self.param_groups[0]["lr"]
+        eng.optimizer_step()
+        return loss
+
+
+class ContrastiveBinding:
+    """Adopts the parameters / BatchNorm buffers of an InfoNCEModel or MultiModalSimCLRModel container into a ContrastiveStepEngine
+    (module tensors become views of the engine's arena) and runs the reference's training_step on it."""
+
+    def __init__(self, model, kind):
+        self.model, self.kind, self.engine = model, kind, None
+
+    def ensure(self, device):
+        from .contrastive import ContrastiveStepEngine
+        m = self.model
+        if self.engine is None:
+            self.engine = ContrastiveStepEngine(kind=self.kind, output_dim=m.output_dim, projection_dim=m.projection_dim, device=device,
+                                                seed=int(torch.initial_seed()) & 0x7FFFFFFF,
+                                                precision="bf16" if getattr(m, "use_mixed_precision", True) else "fp32")
+        eng = self.engine
+        params = dict(m.named_parameters())
+        first = next(iter(params))
+        if params[first].data_ptr() == eng.S["enc." + first].data_ptr():
+            return eng
+        with torch.no_grad():
+            for name, p in params.items():
+                view = eng.S["enc." + name]
+                view.copy_(p.data.to(eng.device))
+                p.data = view
+            for name, mod in m.named_modules():
+                if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+                    bn = eng.bn_s["enc." + name]
+                    for attr in ("running_mean", "running_var", "num_batches_tracked"):
+                        t = getattr(mod, attr)
+                        if t.device != eng.device:
+                            t.data = t.data.to(eng.device)
+                    bn.running_mean, bn.running_var, bn.num_batches_tracked = mod.running_mean, mod.running_var, mod.num_batches_tracked
+        return eng
+
+    def training_step(self, batch, mode=None):
+        """Forward + loss + backward on the CUDA kernels; gradients land in the arena (every used parameter's .grad is a view of it,
+        unused branches get .grad = None like in the reference).  Returns the loss as an autograd-visible scalar whose backward is a no-op."""
+        dev = batch[0].device if batch[0].is_cuda else torch.device("cuda", torch.cuda.current_device())
+        eng = self.ensure(dev)
+        views = [t.to(dev).float().reshape(t.shape[0], *t.shape[-2:]).contiguous() for t in batch]
+        loss = eng.forward_backward(tuple(views), mode=mode)
+        used = {"img": ("image_encoder", "image_projection_head"), "aud": ("audio_encoder", "audio_projection_head")}
+        live = {m for b in eng._used for m in used[b]}
+        for name, p in self.model.named_parameters():
+            p.grad = eng.G["enc." + name] if name.split(".", 1)[0] in live else None
+        anchor = next(self.model.parameters())
+        return _AppliedLoss.apply(loss[3], anchor)

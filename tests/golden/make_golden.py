@@ -281,7 +281,8 @@ def contrastive_fixture(kind, B=4, seed=21, modes=(2, 0, 1, 3)):
         _load(getattr(lit.model, m), st.params[m])
     lit.train()
     opt = torch.optim.Adam(lit.parameters(), lr=1e-4)
-    out = {"kind": kind, "B": B, "seed": seed, "modes": list(modes), "steps": []}
+    out = {"kind": kind, "B": B, "seed": seed, "modes": list(modes), "steps": [],
+           "state_dict": {k: list(v.shape) for k, v in lit.state_dict().items()}}          # API surface: keys / shapes of the Lightning module
     orig_randint = torch.randint
     for it in range(n_steps):
         g = torch.Generator().manual_seed(400 + it)

@@ -226,3 +226,22 @@ def test_ddp_ranks_train_on_disjoint_shards(tmp_path, monkeypatch):
     assert sum(b[0].numel() for b in sharded) == 20
     with pytest.raises(RuntimeError):
         tr._shard_loader([1, 2, 3])
+
+
+def test_contrastive_mirrors_have_the_reference_surface(golden_contrastive):
+    """other_ssl/info_nce/info_nce.py and other_ssl/multimodal_simclr/multimodal_simclr.py of the mirror: same classes, constructor
+    keywords, methods and state_dict keys / shapes as the imported reference (tests/golden/golden_contrastive.json 'state_dict')."""
+    import other_ssl.info_nce.info_nce as nce
+    import other_ssl.multimodal_simclr.multimodal_simclr as simclr
+    for mod, cls, key, loss_name in ((nce, "MultiModalInfoNCELightning", "infonce", "infoNCE_loss"),
+                                     (simclr, "MultiModalSimCLRLightning", "simclr", "nt_xent_loss")):
+        lit = getattr(mod, cls)(projection_dim=256, output_dim=256, learning_rate=1e-4, num_epochs=100, use_mixed_precision=True)
+        want = golden_contrastive[key]["state_dict"]
+        got = {k: list(v.shape) for k, v in lit.state_dict().items()}
+        assert got == want, set(got) ^ set(want)
+        for attr in ("training_step", "configure_optimizers", "forward", "model", loss_name):
+            assert hasattr(lit, attr)
+        cfg = lit.configure_optimizers()
+        assert isinstance(cfg["optimizer"], torch.optim.Optimizer) and cfg["lr_scheduler"]["monitor"] == "train_loss"
+        with pytest.raises(Exception):                       # no CPU fallback
+            lit.training_step((torch.rand(2, 1, 28, 28), torch.rand(2, 1, 112, 112), torch.rand(2, 1, 28, 28), torch.rand(2, 1, 112, 112)), 0)

@@ -374,3 +374,48 @@ def test_simple_family_through_the_lightning_modules(enc, mode):
     torch.cuda.synchronize()
     rel = float((feats_mod - feats_eng).norm() / feats_eng.norm())
     assert rel < 3e-2, rel
+
+
+@pytest.mark.parametrize("which", ["infonce", "simclr"])
+def test_contrastive_lightning_modules_train(which):
+    """other_ssl/info_nce and other_ssl/multimodal_simclr through their Lightning-shaped modules: training_step -> backward ->
+    optimizer.step; parameters alias the engine arena, the branch a SimCLR step did not use has .grad None and does not move."""
+    import other_ssl.info_nce.info_nce as nce
+    import other_ssl.multimodal_simclr.multimodal_simclr as simclr
+    torch.manual_seed(3)
+    lit = (nce.MultiModalInfoNCELightning if which == "infonce" else simclr.MultiModalSimCLRLightning)(learning_rate=1e-3).to(DEV)
+    opt = lit.configure_optimizers()["optimizer"]
+    B = 16
+    losses = []
+    for it in range(6):
+        g = torch.Generator().manual_seed(it)
+        i1, s1 = torch.rand(B, 1, 28, 28, generator=g).to(DEV), torch.rand(B, 1, 112, 112, generator=g).to(DEV)
+        i2, s2 = torch.rand(B, 1, 28, 28, generator=g).to(DEV), torch.rand(B, 1, 112, 112, generator=g).to(DEV)
+        batch = (i1, s1, torch.zeros(B, dtype=torch.long, device=DEV)) if which == "infonce" else (i1, s1, i2, s2)
+        before = {k: v.detach().clone() for k, v in lit.model.named_parameters()}
+        opt.zero_grad(set_to_none=True)
+        loss = lit.training_step(batch, it)
+        assert loss.requires_grad and loss.dim() == 0
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+        eng = lit._b200.engine
+        for k, p in lit.model.named_parameters():
+            branch = "img" if k.startswith("image") else "aud"
+            moved = float((p.detach() - before[k]).abs().max())
+            if branch in eng._used:
+                assert p.grad is not None and p.grad.data_ptr() == eng.G["enc." + k].data_ptr()
+            else:
+                assert p.grad is None and moved == 0.0, k
+    torch.cuda.synchronize()
+    assert all(l == l and 0.0 < l < 20.0 for l in losses), losses
+    eng = lit._b200.engine
+    assert lit.model.image_encoder.encoder[0].weight.data_ptr() == eng.S["enc.image_encoder.encoder.0.weight"].data_ptr()
+    assert sum(eng.step_counts.values()) == 12 if which == "infonce" else 6 <= sum(eng.step_counts.values()) <= 12
+    sd = lit.state_dict()
+    assert "model.audio_encoder.encoder.18.weight" in sd and "model.image_projection_head.mlp.1.running_mean" in sd
+    # the containers' own inference forward runs on the CUDA kernels too
+    lit.model.eval()
+    with torch.no_grad():
+        out = lit.model(batch)
+    assert out[0].shape == (B, 256) and torch.isfinite(out[0]).all() and torch.isfinite(out[1]).all()
