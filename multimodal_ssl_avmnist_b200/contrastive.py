@@ -349,11 +349,81 @@ class ContrastiveStepEngine(DinoStepEngine):
 
     def optimizer_step(self):
         """Adam(lr), no weight decay, over the branches that received gradients; one step count per branch."""
+        if self._ctr is not None:       # CUDA-graph mode (infonce: both branches step together): step and learning rate live on the device
+            ops.adam_bias_dev(self._ctr[1:2], self._bc)
+            for mod in self._used:
+                lo, hi = self.branch_range[mod]
+                ops.adam_flat_dev(self.student.flat[lo:hi], self.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self._bc, -1.0, weight_decay=0.0)
+            ops.counters_advance(self._ctr)
+            return
         for mod in self._used:
             self.step_counts[mod] += 1
             lo, hi = self.branch_range[mod]
             ops.adam_flat(self.student.flat[lo:hi], self.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.step_counts[mod], self.lr,
                           weight_decay=0.0)
+
+    # ------------------------------------------------------------------------------------------------------
+    def capture_train_step(self, B, image_dtype=torch.float32, audio_dtype=torch.uint8):
+        """kind="infonce": the whole step (forward, InfoNCE, backward, Adam) of a raw batch of B samples as ONE CUDA graph -- at the
+        reference notebook's B = 128 the ~150 launches of a step cost more host time than GPU time.  The Adam step count and the
+        learning rate are device scalars (schedulers may change self.lr between replays).  Use graph_step() afterwards.  (The SimCLR step
+        draws its modality pairing and its augmentation parameters on the host every step and is not captured.)"""
+        if self.kind != "infonce":
+            raise ops._lib.B200Error("capture_train_step: only the InfoNCE step has a step-invariant launch sequence")
+        if self.step_counts["img"] != self.step_counts["aud"]:
+            raise ops._lib.B200Error("capture_train_step: the two branches must have taken the same number of Adam steps")
+        dev = self.device
+        g = {"B": B, "img": torch.zeros(B, 28, 28, dtype=image_dtype, device=dev), "aud": torch.zeros(B, 112, 112, dtype=audio_dtype, device=dev)}
+        state = [self.student.flat, self.exp_avg, self.exp_avg_sq]
+        for bn in self.bn_s.values():
+            state += [bn.running_mean, bn.running_var, bn.num_batches_tracked]
+        snap = [t.clone() for t in state]
+        host = int(self.step_counts["img"])
+        self._ctr = torch.tensor([0, host], dtype=torch.int64, device=dev)
+        self._bc = torch.zeros(3, device=dev)
+        self._bc[2:3].fill_(float(self.lr))
+        self._graph_lr = float(self.lr)
+
+        def restore():
+            for t, c in zip(state, snap):
+                t.copy_(c)
+            self._ctr.copy_(torch.tensor([0, host], dtype=torch.int64))
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.train_step(g["img"], g["aud"])
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        restore()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            g["loss"] = self.train_step(g["img"], g["aud"])
+        restore()
+        torch.cuda.synchronize()
+        g["graph"] = graph
+        self._graph = g
+        return g
+
+    def graph_step(self, images, audios):
+        g = self._graph
+        if g is None or images.shape[0] != g["B"]:
+            raise ops._lib.B200Error("graph_step: call capture_train_step(B) for this batch size first")
+        g["img"].copy_(images.reshape(g["img"].shape))
+        g["aud"].copy_(audios.reshape(g["aud"].shape))
+        if float(self.lr) != self._graph_lr:
+            self._graph_lr = float(self.lr)
+            self._bc[2:3].fill_(self._graph_lr)
+        g["graph"].replay()
+        for mod in ("img", "aud"):
+            self.step_counts[mod] += 1
+        self.rng_step += 1
+        return g["loss"]
+
+    def release_graph(self):
+        self._graph = None
+        self._ctr = self._bc = None
 
     def train_step_views(self, batch, mode=None):
         loss = self.forward_backward(batch, mode=mode)

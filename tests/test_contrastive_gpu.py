@@ -163,3 +163,26 @@ def test_contrastive_raw_batches_run_and_learn(kind):
     assert sum(eng.step_counts.values()) == (24 if kind == "infonce" else sum(eng.step_counts.values()))
     if kind == "infonce":
         assert losses[-1] < losses[0]
+
+
+def test_infonce_cuda_graph_replay_equals_eager_steps():
+    """capture_train_step / graph_step of the stand-alone InfoNCE step: three replays reproduce three eager steps bit for bit (parameters,
+    Adam moments, BatchNorm buffers, loss), starting from a non-zero Adam step count."""
+    B = 32
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.rand(B, 28, 28, generator=g).to(DEV), torch.randint(0, 256, (B, 112, 112), generator=g, dtype=torch.uint8).to(DEV)) for _ in range(4)]
+    engs = [ContrastiveStepEngine(kind="infonce", device=DEV, seed=7, learning_rate=1e-3) for _ in range(2)]
+    for e in engs:
+        e.train_step(*batches[0])                      # one eager step first: Adam step 1, BatchNorm buffers moved
+    engs[1].capture_train_step(B)
+    for img, aud in batches[1:]:
+        le = engs[0].train_step(img, aud).clone()
+        lg = engs[1].graph_step(img, aud).clone()
+        assert torch.equal(le, lg), (float(le[3]), float(lg[3]))
+    torch.cuda.synchronize()
+    assert torch.equal(engs[0].student.flat, engs[1].student.flat)
+    assert torch.equal(engs[0].exp_avg, engs[1].exp_avg) and torch.equal(engs[0].exp_avg_sq, engs[1].exp_avg_sq)
+    for k in engs[0].bn_s:
+        assert torch.equal(engs[0].bn_s[k].running_var, engs[1].bn_s[k].running_var), k
+        assert int(engs[0].bn_s[k].num_batches_tracked) == int(engs[1].bn_s[k].num_batches_tracked)
+    assert engs[0].step_counts == engs[1].step_counts == {"img": 4, "aud": 4}
