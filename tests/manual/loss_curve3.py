@@ -36,8 +36,8 @@ def to_cuda(obj):
     return obj
 
 
-def cuda_state(seed):
-    st = R.CentralDinoState(seed=seed, mode="default")
+def cuda_state(seed, kind="multi_central"):
+    st = R.CentralDinoState(seed=seed, mode="default", kind=kind)
     for name, val in list(vars(st).items()):
         setattr(st, name, to_cuda(val))
     return st
@@ -49,16 +49,17 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--lr", type=float, default=1e-4)
     ap.add_argument("--pool", type=int, default=64, help="number of distinct synthetic batches cycled through")
+    ap.add_argument("--kind", default="multi_central", help="multi_central | multi_simple | multi_simple_gated | multi_cross_attention")
     ap.add_argument("--out", default="gpurun_out/r2_loss_curve.json")
     args = ap.parse_args()
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     dev, B = "cuda:0", args.batch
-    cpu0 = R.CentralDinoState(seed=11, mode="default")
-    arms = {"oracle_fp32": cuda_state(11), "oracle_fp16ac": cuda_state(11)}
+    cpu0 = R.CentralDinoState(seed=11, mode="default", kind=args.kind)
+    arms = {"oracle_fp32": cuda_state(11, args.kind), "oracle_fp16ac": cuda_state(11, args.kind)}
     engines = {}
     for prec in ("fp32", "bf16"):
-        e = DinoStepEngine(kind="multi_central", device=dev, precision=prec, learning_rate=args.lr)
+        e = DinoStepEngine(kind=args.kind, device=dev, precision=prec, learning_rate=args.lr)
         e.load_named(student=cpu0.student, teacher=cpu0.teacher, student_head=cpu0.student_head, teacher_head=cpu0.teacher_head)
         engines["engine_" + prec] = e
     curves = {k: [] for k in list(arms) + list(engines)}
@@ -103,7 +104,8 @@ def main():
              "mean_abs_last_100": [summary["engine_bf16"]["mean_abs_last_100"], 1.5 * summary["oracle_fp16ac"]["mean_abs_last_100"]]}
     bound["ok"] = all(a <= b for a, b in (bound["mean_abs"], bound["mean_abs_last_100"]))
     out = {"steps": args.steps, "batch": B, "lr": args.lr, "pool": args.pool,
-           "note": "default mode multi_central; identical inputs / masks / initial weights in all four arms; deviations are |loss - oracle_fp32 loss|",
+           "kind": args.kind,
+           "note": "default mode; identical inputs / masks / initial weights in all four arms; deviations are |loss - oracle_fp32 loss|",
            "summary": summary, "bound": bound,
            "fp16_autocast_vs_fp32_gradient_cosine_step0": {"min": min(grad_cos.values()), "per_matrix": grad_cos},
            "curves_every_10": {k_: v[::10] for k_, v in curves.items()}}
