@@ -729,35 +729,47 @@ def run_contrastive(args):
     import torch
     from multimodal_ssl_avmnist_b200 import ops
     from multimodal_ssl_avmnist_b200.contrastive import ContrastiveStepEngine
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        raise SystemExit("bench.py: the contrastive kinds run on one GPU (no data-parallel exchange is wired for them)")
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     kind = args.kind.split("_", 1)[1]
     B = args.batch
-    dev = torch.device("cuda", 0)
-    torch.manual_seed(1)
-    eng = ContrastiveStepEngine(kind=kind, device=dev, seed=1)
-    g = torch.Generator().manual_seed(1)
+    torch.manual_seed(1 + rank)
+    eng = ContrastiveStepEngine(kind=kind, device=dev, seed=1)          # replicated weights (same seed), rank-local data below
+    g = torch.Generator().manual_seed(1 + rank)
     img_h = torch.rand(B, 28, 28, generator=g).pin_memory()
     aud_h = torch.randint(0, 256, (B, 112, 112), generator=g, dtype=torch.uint8).pin_memory()
     img_d, aud_d = img_h.to(dev), aud_h.to(dev)
     W = max(args.warmup, 3)
-    use_graph = bool(args.graph) and kind == "infonce"
+    use_graph = bool(args.graph) and kind == "infonce" and world == 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     if use_graph:
         eng.capture_train_step(B)
     step = eng.graph_step if use_graph else eng.train_step
     for _ in range(W):
         loss = step(img_d, aud_d)
-    torch.cuda.synchronize()
-    sampler = ClockSampler(0)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
     l0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         loss = step(img_d, aud_d)
     e1.record()
-    torch.cuda.synchronize()
+    barrier()
     ms = e0.elapsed_time(e1) / args.steps
     launches = (ops.launch_count() - l0) // args.steps
     if use_graph:                       # a replay issues no wrapper calls: count one eager step of the same engine state instead
@@ -774,32 +786,41 @@ def run_contrastive(args):
         buf_a.copy_(aud_h, non_blocking=True)
         last = float(step(buf_i, buf_a)[3].item())
     e1.record()
-    torch.cuda.synchronize()
+    barrier()
     ms_e2e = e0.elapsed_time(e1) / args.steps
-    clk = sampler.stop()
+    if world > 1:                       # max over ranks (device-timed)
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    clk = sampler.stop() if sampler is not None else None
+    if rank != 0:
+        dist.destroy_process_group()
+        return
     # algorithmic FLOPs per sample: ImageEncoder 7.65 M + head, SpectrogramEncoder 177.1 M + head MACs per encoder call, x3 (fwd, dgrad, wgrad)
     img_macs = 9 * (28 * 28 * 32 + 14 * 14 * 64 * 32 + 7 * 7 * 128 * 64) + 128 * 512 + 512 * 256 + 256 * 512 + 512 * 256
     aud_macs = 9 * (112 * 112 * 32 + 56 * 56 * 64 * 32 + 28 * 28 * 128 * 64 + 14 * 14 * 256 * 128) + 256 * 256 + 256 * 512 + 512 * 256
     per_sample = (img_macs + aud_macs) * 6.0        # infonce: one call of each encoder; simclr: two calls, on average one of each
     published = {("infonce", 128): (2180.0, "other_ssl/info_nce/info_nce.ipynb:156"), ("simclr", 256): (790.0, "other_ssl/multimodal_simclr/multimodal_simclr.ipynb:87")}
-    pub = published.get((kind, B))
-    rate = B / (ms / 1e3)
+    pub = published.get((kind, B)) if world == 1 else None
+    rate = B * world / (ms / 1e3)
     wl = ("stand-alone multimodal InfoNCE step (ImageEncoder + SpectrogramEncoder + 2 projection heads, un-augmented batch)" if kind == "infonce" else
           "multimodal SimCLR step (2 augmented views per modality, random modality pairing, NT-Xent)")
-    print(json.dumps({"metric": METRIC.replace("DINO", "contrastive"), "value": rate, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": W,
+    print(json.dumps({"metric": METRIC.replace("DINO", "contrastive"), "value": rate, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
                       "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": (rate / pub[0]) if pub else None,
                       "dtype": "bf16", "data": "synthetic",
-                      "config": {"workload": wl, "per_gpu_batch": B, "global_batch": B, "parallelism": "dp1",
+                      "config": {"workload": wl, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                                  "published_reference": ({"samples_per_s": pub[0], "source": pub[1], "hardware": "unnamed single GPU"} if pub else None),
                                  "l2": "activations of a step exceed the 126 MB L2"},
-                      "e2e": {"value": B / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": img_h.numel() * 4 + aud_h.numel(), "d2h_bytes_per_step": 4,
+                      "e2e": {"value": B * world / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": img_h.numel() * 4 + aud_h.numel(), "d2h_bytes_per_step": 4,
                               "ms_per_step": ms_e2e, "last_loss": last},
                       "details": {"execution": "one CUDA graph replay per step" if use_graph else "eager launches"},
                       "gpu_launches": int(launches), "clocks": clk,
                       "roofline": {"bound": "tensor", "kernel": "whole step", "achieved": per_sample * B / ms / 1e9, "peak": load_peaks()["tflops"], "unit": "TFLOP/s",
                                    "frac": per_sample * B / ms / 1e9 / load_peaks()["tflops"], "traffic": None,
-                                   "note": "whole-step algorithmic FLOPs (6 x forward MACs of one call of each encoder + head) over the step time"},
+                                   "note": "per GPU; whole-step algorithmic FLOPs (6 x forward MACs of one call of each encoder + head) over the step time"},
                       "cpu_baseline": None, "impl": "ours"}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

@@ -19,6 +19,7 @@ import math
 import numpy as np
 import torch
 
+from . import dp
 from . import ops
 from .engine import F32, Arena, DinoStepEngine, _BN, _conv, _lin, _vec2, head_params
 
@@ -48,7 +49,7 @@ def contrastive_params(O, P):
 
 class ContrastiveStepEngine(DinoStepEngine):
     def __init__(self, kind="infonce", output_dim=256, projection_dim=256, learning_rate=1e-4, temperature=0.07, seed=0, device=None,
-                 precision="bf16", fused_pool=True):
+                 precision="bf16", fused_pool=True, process_group=None, data_parallel=None, mode_seed=0):
         if not torch.cuda.is_available():
             raise ops._lib.B200Error("ContrastiveStepEngine needs a CUDA device: the hot path has no CPU fallback")
         ops._lib.load()
@@ -60,7 +61,12 @@ class ContrastiveStepEngine(DinoStepEngine):
         self.O, self.P = output_dim, projection_dim
         self.lr, self.weight_decay, self.temperature = learning_rate, 0.0, temperature
         self.seed, self.rng_step = seed, 0
-        self.world, self.pg, self.comm, self._comm_stream = 1, None, None, None
+        # data parallel (one process per GPU): samples sharded over the ranks, BatchNorm statistics and contrastive negatives rank-local
+        # (what Lightning's DDP gives the reference), ONE exchange per step: all-reduce of the gradients of the branches the step used,
+        # through the C ABI (b200_dp_allreduce_grads) on a communication stream; the 1 / world average is folded into Adam's grad_scale
+        self.pg = process_group
+        self.world = dp.world_size(process_group) if (data_parallel is None or data_parallel) else 1
+        self.comm, self._comm_stream = None, None
         self._ctr = self._bc = self._graph = None
         self.img_layers, self.aud_layers = IMG_LAYERS, AUD_LAYERS
         img, aud = contrastive_params(self.O, self.P)
@@ -102,7 +108,13 @@ class ContrastiveStepEngine(DinoStepEngine):
         self._wgrad_streams = {m: torch.cuda.Stream(device=self.device) for m in ("img", "aud")}
         self._eval_wrole = "s"
         self._ws = {}
-        self._mode_rng = torch.Generator().manual_seed(seed)         # host draw of the SimCLR modality pairing (torch.randint in the reference)
+        # host draw of the SimCLR modality pairing (torch.randint in the reference): the SAME sequence on every rank (mode_seed, not the
+        # per-rank seed), so that all ranks run -- and exchange -- the same branches
+        self._mode_rng = torch.Generator().manual_seed(mode_seed)
+        if self.world > 1:
+            self.comm = dp.AbiComm.get(process_group)
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        self._comm_pending = False
         self._init_parameters()
 
     # ------------------------------------------------------------------------------------------------------
@@ -345,22 +357,35 @@ class ContrastiveStepEngine(DinoStepEngine):
             torch.cuda.current_stream().wait_stream(self._lin_wg_stream)
             self._lin_wg_pending = False
         self._used = [m for m in ("img", "aud") if sched[m]]
+        if self.world > 1:
+            main, cs = torch.cuda.current_stream(), self._comm_stream
+            cs.wait_stream(main)
+            with torch.cuda.stream(cs):
+                for mod in self._used:
+                    lo, hi = self.branch_range[mod]
+                    self.comm.allreduce_grads_(self.grad[lo:hi], cs.cuda_stream)
+            self._comm_pending = True
         return loss
 
     def optimizer_step(self):
         """Adam(lr), no weight decay, over the branches that received gradients; one step count per branch."""
+        gs = 1.0 / self.world
+        if self._comm_pending:
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+            self._comm_pending = False
         if self._ctr is not None:       # CUDA-graph mode (infonce: both branches step together): step and learning rate live on the device
             ops.adam_bias_dev(self._ctr[1:2], self._bc)
             for mod in self._used:
                 lo, hi = self.branch_range[mod]
-                ops.adam_flat_dev(self.student.flat[lo:hi], self.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self._bc, -1.0, weight_decay=0.0)
+                ops.adam_flat_dev(self.student.flat[lo:hi], self.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self._bc, -1.0, weight_decay=0.0,
+                                  grad_scale=gs)
             ops.counters_advance(self._ctr)
             return
         for mod in self._used:
             self.step_counts[mod] += 1
             lo, hi = self.branch_range[mod]
             ops.adam_flat(self.student.flat[lo:hi], self.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self.step_counts[mod], self.lr,
-                          weight_decay=0.0)
+                          weight_decay=0.0, grad_scale=gs)
 
     # ------------------------------------------------------------------------------------------------------
     def capture_train_step(self, B, image_dtype=torch.float32, audio_dtype=torch.uint8):
