@@ -9,8 +9,13 @@ and runs the reference's step order: multi-crop augmentation -
 teacher on the global views (BatchNorm statistics per view-call) -> projection heads -> fused DINO loss
 (+ centre EMA) [+ MSE / InfoNCE / CE on an extra un-augmented pass] -> teacher EMA -> backward -> Adam.
 
-Every arithmetic stage is a `b200_*` call into libavmnist_b200.so (ops.py); torch only provides device memory,
-streams and (for data parallel runs) the NCCL all-reduce of the gradient arena and of the centre column sums.
+Every arithmetic stage is a `b200_*` call into libavmnist_b200.so (ops.py); torch only provides device memory and
+streams; for data parallel runs the two exchanges (gradient arena, centre column sums) are C-ABI calls too (b200_dp_*).
+
+Encoders (`kind`): 'multi_central' (CentralMultiModalEncoder, the headline), 'multi_simple' / 'multi_simple_gated' /
+'multi_cross_attention' (the 3x3 conv encoders of models/dino.py:214-263, 385-452: stack tops are avgpool -> linear and a mix stage --
+sigmoid gates or batch-wide cross attention -- sits before the fusion MLP) and 'image_simple' (unimodal).  The stand-alone contrastive
+steps of other_ssl/ reuse these building blocks from contrastive.ContrastiveStepEngine.
 
 Arena layout (student):  [ encoder params that receive gradients | projection head | unused fc1/fc2 | mode heads ]
         (teacher):       [ encoder params that receive gradients | projection head | unused fc1/fc2 ]
