@@ -419,3 +419,26 @@ def test_contrastive_lightning_modules_train(which):
     with torch.no_grad():
         out = lit.model(batch)
     assert out[0].shape == (B, 256) and torch.isfinite(out[0]).all() and torch.isfinite(out[1]).all()
+
+
+def test_infonce_trainer_fit_on_synthetic_files(tmp_path):
+    """The flow of other_ssl/info_nce/info_nce.ipynb in miniature: AVMNISTDataModule batches (image, spectrogram, label) ->
+    Trainer.fit(MultiModalInfoNCELightning) with the CSV logger and a checkpoint; the loss decreases, the checkpoint reloads with the
+    reference's state_dict keys."""
+    import other_ssl.info_nce.info_nce as nce
+    from _compat import pl, ModelCheckpoint, CSVLogger
+    d = str(tmp_path) + "/"
+    gd.write_synthetic_avmnist(d, n_train=96, n_test=16)
+    dm = gd.AVMNISTDataModule(data_dir=d, batch_size=16, num_workers=0, type="burst_noise")
+    torch.manual_seed(0)
+    lit = nce.MultiModalInfoNCELightning(projection_dim=256, output_dim=256, learning_rate=1e-3, num_epochs=3)
+    ckpt = ModelCheckpoint(dirpath=str(tmp_path), monitor="train_loss_epoch", mode="min")
+    tr = pl.Trainer(max_epochs=3, logger=CSVLogger(str(tmp_path), name="logs"), callbacks=[ckpt], log_every_n_steps=1, devices=1, accelerator="gpu")
+    tr.fit(lit, datamodule=dm)
+    assert tr.global_step >= 9 and "train_loss_epoch" in tr.callback_metrics
+    assert 0.0 < float(tr.callback_metrics["train_loss_epoch"]) < 4.0
+    assert sum(lit._b200.engine.step_counts.values()) == 2 * tr.global_step
+    assert os.path.exists(ckpt.best_model_path)
+    again = nce.MultiModalInfoNCELightning.load_from_checkpoint(ckpt.best_model_path)
+    a, b = again.state_dict(), lit.state_dict()
+    assert set(a) == set(b) and all(a[k].shape == b[k].shape for k in a)
