@@ -13,7 +13,6 @@ The engine reuses DinoStepEngine's building blocks (tensor-core conv stacks with
 kernels, linear kernels, flat-arena Adam) with its own parameter inventory and schedule; parameters are named as in the reference's
 state_dict (`image_encoder.encoder.0.weight`, `audio_projection_head.mlp.4.bias`, ...).  No CPU fallback.
 """
-import contextlib
 import math
 
 import numpy as np
@@ -140,6 +139,14 @@ class ContrastiveStepEngine(DinoStepEngine):
 
     def sync_teacher(self):          # no teacher here
         pass
+
+    def _dino_only(self, *a, **k):
+        raise ops._lib.B200Error("this entry point belongs to the DINO step engine; the contrastive engine offers forward_backward / "
+                                 "optimizer_step / train_step_views / train_step / capture_train_step / graph_step")
+
+    # inherited DINO-specific entry points that have no meaning here
+    forward_pass = dino_loss_pass = aux_loss_pass = backward_pass = update_teacher = train_step_host = encode_features = begin_probe = _dino_only
+    augment = augment_with_params = prefetch_augment = allreduce_gradients = graph_node_counts = _dino_only
 
     # ------------------------------------------------------------------------------------------------------
     def _workspace(self, B):
@@ -274,7 +281,7 @@ class ContrastiveStepEngine(DinoStepEngine):
             ops.bn1d_gelu_drop_fwd(hh[r], sc[cc:cc + 1], sh[cc:cc + 1], None, 0.0, g[r])
         return g, head
 
-    def _branch_bwd(self, w, mod, d_z, z_in, calls):
+    def _branch_bwd(self, w, mod, d_z, calls):
         """Backward of one branch from d loss / d z [calls*B, P]."""
         B, S, G = w["B"], self.S, self.G
         N = calls * B
@@ -352,7 +359,7 @@ class ContrastiveStepEngine(DinoStepEngine):
                 continue
             first = min(v for v, (m, _) in enumerate(order) if m == mod)        # the branch's rows of reps are contiguous, in call order
             d_z = d_reps[first * B:(first + calls) * B]
-            self._branch_bwd(w, mod, d_z, z[mod], calls)
+            self._branch_bwd(w, mod, d_z, calls)
         if self._lin_wg_pending:
             torch.cuda.current_stream().wait_stream(self._lin_wg_stream)
             self._lin_wg_pending = False

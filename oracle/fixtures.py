@@ -64,3 +64,11 @@ def summaries_close(a, b, rtol, atol):
         if abs(x - y) > rtol * max(abs(x), abs(y), mean_abs) + atol:
             return False, f"value {x} vs {y}"
     return True, ""
+
+
+def contrastive_batch(B, it):
+    """The seeded (img1, spec1, img2, spec2) batch of step `it` of tests/golden/make_golden.py::contrastive_fixture."""
+    g = torch.Generator().manual_seed(400 + it)
+    img1, spec1 = torch.rand(B, 1, 28, 28, generator=g), torch.rand(B, 1, 112, 112, generator=g)
+    img2, spec2 = torch.rand(B, 1, 28, 28, generator=g), torch.rand(B, 1, 112, 112, generator=g)
+    return img1, spec1, img2, spec2

@@ -11,9 +11,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import dino_ref as R
-from oracle.fixtures import summaries_close, summarize
+from oracle.fixtures import contrastive_batch, summaries_close, summarize
 from multimodal_ssl_avmnist_b200.contrastive import ContrastiveStepEngine
-from test_oracle_golden import contrastive_batch
 
 DEV = "cuda"
 CANCELLED = re.compile(r"(encoder\.(0|4|8|12|14|18)\.bias|projection\.0\.bias|mlp\.0\.bias)$")

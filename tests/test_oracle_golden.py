@@ -310,12 +310,7 @@ def test_simclr_augmentation_against_reference_fixture():
     assert {A.OP_ELASTIC, A.OP_BLUR3, A.OP_NOISE, A.OP_TIME_WARP} <= kinds          # the seeds exercise every new op
 
 
-def contrastive_batch(B, it):
-    """The seeded batches of make_golden.contrastive_fixture."""
-    g = torch.Generator().manual_seed(400 + it)
-    img1, spec1 = torch.rand(B, 1, 28, 28, generator=g), torch.rand(B, 1, 112, 112, generator=g)
-    img2, spec2 = torch.rand(B, 1, 28, 28, generator=g), torch.rand(B, 1, 112, 112, generator=g)
-    return img1, spec1, img2, spec2
+from oracle.fixtures import contrastive_batch  # noqa: E402
 
 
 @pytest.mark.parametrize("kind", ["infonce", "simclr"])
