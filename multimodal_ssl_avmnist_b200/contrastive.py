@@ -48,7 +48,7 @@ def contrastive_params(O, P):
 
 class ContrastiveStepEngine(DinoStepEngine):
     def __init__(self, kind="infonce", output_dim=256, projection_dim=256, learning_rate=1e-4, temperature=0.07, seed=0, device=None,
-                 precision="bf16", fused_pool=True, process_group=None, data_parallel=None, mode_seed=0):
+                 precision="bf16", fused_pool=False, process_group=None, data_parallel=None, mode_seed=0):
         if not torch.cuda.is_available():
             raise ops._lib.B200Error("ContrastiveStepEngine needs a CUDA device: the hot path has no CPU fallback")
         ops._lib.load()
@@ -85,8 +85,9 @@ class ContrastiveStepEngine(DinoStepEngine):
             self.tc[mod] = [precision == "bf16" and ops.conv_tc_supported(ci, co, hw, hw, k, pad) and
                             (ci == 1 or ops.conv_tc_supported(co, ci, hw + 2 * pad - k + 1, hw + 2 * pad - k + 1, k, k - 1 - pad))
                             for (conv, bn, ci, co, hw, k, pad) in layers]
+        # no max-pool in the forward epilogues: for these 32 - 256 channel layers the fused variant measured slower than conv + pool pass
+        # (engine.py, profiles/r2zf_*); `fused_pool=True` re-enables it on the 112x112 first audio layer for A/B runs
         self.fused_pool = bool(fused_pool)
-        # max-pool in the forward epilogue where the central step found it to win: the HBM-bound 112x112 first audio layer
         self.pool = {"s": {mod: [self.fused_pool and bool(self.tc[mod][li]) and ops.conv_tc_pool_supported(ci, co, hw, hw, k, pad) and ci == 1 and hw >= 112
                                  for li, (conv, bn, ci, co, hw, k, pad) in enumerate(layers)] for mod, layers in (("img", IMG_LAYERS), ("aud", AUD_LAYERS))}}
         self.pool["t"] = self.pool["s"]

@@ -280,7 +280,10 @@ class DinoStepEngine:
         # BatchNorm-apply kernel).  The epilogue pays for it with a per-tile barrier between its four warps (profiles/r2e_*): it wins
         # where no z is written at all (teacher, evaluation) and on the HBM-bound first audio layer of the student; the student's other
         # layers keep the z -> bn_relu_pool8_fwd path.  self.pool[role][mod][li]; role "t" also serves evaluation.
-        self.fused_pool = bool(fused_pool)      # False: the round-1 path everywhere (A/B measurements)
+        # False: the round-1 path everywhere (A/B measurements).  The simple encoder family keeps it off: its layers are 32 - 256 channels
+        # wide, and the per-tile barrier + the wider pooled rows cost the epilogue far more than the z read saves (first audio layer,
+        # 32 channels at 112x112: 2.86 ms fused against 0.96 + 1.15 ms conv + pool pass; whole step 26.1 vs 25.1 ms, profiles/r2zf_*)
+        self.fused_pool = bool(fused_pool) and kind in ("multi_central", "image_simple")
         self.pool = {}
         for role in ("s", "t"):
             self.pool[role] = {mod: [self.fused_pool and bool(self.tc[mod][li]) and ops.conv_tc_pool_supported(ci, co, hw, hw, k, pad)
