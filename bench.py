@@ -101,6 +101,21 @@ def cpu_reference(batch, steps, warmup, cores, with_aug=True, kind="multi_centra
     from oracle.fixtures import make_masks, synth_views, views_to_vb
     torch.set_num_threads(cores)
     from oracle.fixtures import synth_raw
+    if kind.startswith("contrastive"):     # other_ssl/info_nce, other_ssl/multimodal_simclr: the oracle's contrastive_step (no augmentation timed)
+        from oracle.fixtures import contrastive_batch
+        ck = kind.split("_", 1)[1]
+        st = R.ContrastiveState(seed=1)
+        img1, spec1, img2, spec2 = contrastive_batch(batch, 0)
+        data = (img1, spec1) if ck == "infonce" else (img1, spec1, img2, spec2)
+        for i in range(warmup):
+            R.contrastive_step(st, ck, data, mode=i % 4)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            R.contrastive_step(st, ck, data, mode=i % 4)
+        step_s = (time.perf_counter() - t0) / steps
+        rate = batch / step_s
+        return rate, 1e3 * step_s, (f"{steps} steps of B={batch} of the {ck} step (fwd+loss+bwd+Adam, fp32 torch CPU, {cores} threads): "
+                                    f"{rate:.1f} samples/s; augmentation not timed")
     if kind not in R.KIND_MIX:
         kind = "multi_central"          # (image_simple: the multimodal oracle step stands in; only the headline kinds are compared)
     st = R.CentralDinoState(seed=1, mode=mode, kind=kind)
@@ -191,6 +206,10 @@ def workload_config(args, world):
         wl = WORKLOAD if args.mode == "default" else WORKLOAD.replace("default mode", args.mode + " mode")
         if args.kind != "multi_central":            # the 3x3 conv encoders of SURVEY 8f-4 (models/dino.py:214-263, 385-452)
             wl = wl.replace("multi_central", args.kind)
+    elif args.kind == "contrastive_infonce":
+        wl = "stand-alone multimodal InfoNCE step (ImageEncoder + SpectrogramEncoder + 2 projection heads, un-augmented batch)"
+    elif args.kind == "contrastive_simclr":
+        wl = "multimodal SimCLR step (2 augmented views per modality, random modality pairing, NT-Xent)"
     else:
         wl = "image_simple unimodal DINO step (2 global + 4 local views of 28x28 images, O=256, P=128)"
     return {"workload": wl, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
@@ -219,7 +238,8 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     batch = REF_SAMPLE_BATCH
     rate, ms, desc = cpu_reference(batch, args.steps, args.warmup, cores, kind=args.kind, mode=args.mode)
-    line = {"metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": METRIC.replace("DINO", "contrastive") if args.kind.startswith("contrastive") else METRIC, "value": rate, "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "impl": "reference",
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
